@@ -1,0 +1,1551 @@
+// =============================================================================
+//  oracle/insilico_oracle.cpp  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE
+// =============================================================================
+//  CPU restatement (std-only C++17, no Boost, no Eigen) of the element-assembly
+//  hot path of thrueberg/inSilico.  Only tests/, __graft_entry__.smoke() and the
+//  cpu_baseline / --impl reference legs of bench.py may load this library; the
+//  product (insilico_b200/) never does.
+//
+//  The reference itself cannot be compiled here: every header on the path needs
+//  Boost 1.55 and Eigen 3.2.0 (ext/boost/getIt.sh:1, ext/Eigen3/getIt.sh:1), and
+//  neither is installed nor vendored.  So each function below restates the
+//  reference algorithm and cites the file:line it follows (paths relative to the
+//  reference root).  Eigen's fixed-size 3x3 / 2x2 inverse, determinant and small
+//  products are restated from the published Eigen 3.2 algorithm (LU/Inverse.h,
+//  LU/Determinant.h, coefficient-wise products accumulate left to right).
+//
+//  Pinning (see tests/test_oracle_golden.py):
+//    * numbering + sparsity : reference/03-doFHandler/sparsity.{1,2,3}.ref.dat (exact)
+//    * quadrature+Jacobian  : reference/02-areaVolume/measure.ref.dat (6 digits)
+//    * full chain HyperElastic<StVenant>+Lame, Q1 hex, Dirichlet lift, solve, L2
+//      error: reference/06-elastic/linearElastic3D.ref.dat (6 digits)
+//    * HierarchicOrder tables + worked numbering example of
+//      base/dof/generateDoFIndicesFromFaces.hpp:141-160
+//  Entry-wise 1e-12 matrix parity is NOT pinned by any reference golden (the
+//  reference only pins values to 6 digits through a linear solve); for that level
+//  this oracle is the pin: "parity unpinned by the reference at 1e-12".
+// =============================================================================
+#include <algorithm>
+#include <array>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <set>
+#include <string>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+// base/shape.hpp:25-45
+enum Shape { POINT = 0, LINE = 1, TRI = 2, QUAD = 3, TET = 4, HEX = 5 };
+enum NFace { VERTEX = 0, EDGE = 1, FACE = 2, CELL = 3 };
+// base/dof/DegreeOfFreedom.hpp:33-38
+enum DoFStatus { ACTIVE = 0, CONSTRAINED = 1, INACTIVE = 2 };
+
+static const int64_t kInvalid = -1;
+
+static int shapeDim(int s) {
+    switch (s) { case LINE: return 1; case TRI: case QUAD: return 2; case TET: case HEX: return 3; }
+    return 0;
+}
+static bool isHyperCube(int s) { return s == LINE || s == QUAD || s == HEX; }
+static int numNFaces(int s, int nf) {
+    // base/shape.hpp NumNFaces
+    static const int tab[6][4] = {
+        {1, 0, 0, 0}, {2, 1, 0, 0}, {3, 3, 1, 0}, {4, 4, 1, 0}, {4, 6, 4, 1}, {8, 12, 6, 1}};
+    return tab[s][nf];
+}
+static int ipow(int m, int n) { int r = 1; for (int i = 0; i < n; i++) r *= m; return r; }
+static int binomial(int n, int k) {
+    if (k < 0 || k > n) return 0;
+    long r = 1; for (int i = 1; i <= k; i++) r = r * (n - k + i) / i; return (int)r;
+}
+
+// -----------------------------------------------------------------------------
+// base/mesh/HierarchicOrder.hpp:130-454 : H[lexicographic] = hierarchic
+static std::vector<int> hierarchicOrder(int shape, int K) {
+    const int dim = shapeDim(shape);
+    std::vector<int> t;
+    if (!isHyperCube(shape)) {  // :43-59 identity for simplices
+        int n = binomial(K + dim, K);
+        t.resize(n); for (int i = 0; i < n; i++) t[i] = i; return t;
+    }
+    if (dim == 1) {  // :130-152
+        int n = K + 1; t.assign(n, -1);
+        t[0] = 0; for (int i = 1; i < n - 1; i++) t[i] = i + 1; if (K > 0) t[n - 1] = 1;
+        return t;
+    }
+    if (dim == 2) {  // :200-272
+        t.assign((K + 1) * (K + 1), -1);
+        const int vertices[4] = {0, K, K * (K + 2), K * (K + 1)};
+        const int edges[4][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}};
+        int ctr = 0;
+        for (int i = 0; i < 4; i++) t[vertices[i]] = ctr++;
+        for (int i = 0; i < 4; i++) {
+            int ev1 = vertices[edges[i][0]], ev2 = vertices[edges[i][1]];
+            int delta = (ev2 - ev1) / K;
+            for (int n = 0; n < K - 1; n++) t[(ev1 + delta) + n * delta] = ctr++;
+        }
+        int fv1 = vertices[0], fv2 = vertices[1], fv3 = vertices[3];
+        int d1 = (fv2 - fv1) / K, d2 = (fv3 - fv1) / K;
+        for (int n2 = 0; n2 < K - 1; n2++)
+            for (int n1 = 0; n1 < K - 1; n1++) t[(fv1 + d1 + d2) + n1 * d1 + n2 * d2] = ctr++;
+        return t;
+    }
+    // dim == 3, :344-454
+    t.assign((K + 1) * (K + 1) * (K + 1), -1);
+    const int dZ = K * (K + 1) * (K + 1);
+    const int vertices[8] = {0, K, K * (K + 2), K * (K + 1), dZ, K + dZ, K * (K + 2) + dZ, K * (K + 1) + dZ};
+    const int edges[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6},
+                              {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    const int faces[6][3] = {{0, 1, 3}, {4, 5, 7}, {0, 1, 4}, {1, 2, 5}, {2, 3, 6}, {3, 0, 7}};
+    int ctr = 0;
+    for (int i = 0; i < 8; i++) t[vertices[i]] = ctr++;
+    for (int i = 0; i < 12; i++) {
+        int ev1 = vertices[edges[i][0]], ev2 = vertices[edges[i][1]];
+        int delta = (ev2 - ev1) / K;
+        for (int n = 0; n < K - 1; n++) t[(ev1 + delta) + n * delta] = ctr++;
+    }
+    for (int i = 0; i < 6; i++) {
+        int fv1 = vertices[faces[i][0]], fv2 = vertices[faces[i][1]], fv3 = vertices[faces[i][2]];
+        int d1 = (fv2 - fv1) / K, d2 = (fv3 - fv1) / K;
+        for (int n2 = 0; n2 < K - 1; n2++)
+            for (int n1 = 0; n1 < K - 1; n1++) t[(fv1 + d1 + d2) + n1 * d1 + n2 * d2] = ctr++;
+    }
+    {
+        int cv1 = vertices[0], cv2 = vertices[1], cv3 = vertices[3], cv4 = vertices[4];
+        int d1 = (cv2 - cv1) / K, d2 = (cv3 - cv1) / K, d3 = (cv4 - cv1) / K;
+        for (int n3 = 0; n3 < K - 1; n3++)
+            for (int n2 = 0; n2 < K - 1; n2++)
+                for (int n1 = 0; n1 < K - 1; n1++)
+                    t[(cv1 + d1 + d2 + d3) + n1 * d1 + n2 * d2 + n3 * d3] = ctr++;
+    }
+    return t;
+}
+
+// -----------------------------------------------------------------------------
+// Shape functions. base/LagrangeShapeFun.hpp, base/sfun/*.
+struct SFun {
+    int shape = 0, deg = 0, dim = 0, nfun = 0;
+    std::vector<int> hier;  // lexicographic -> hierarchic (hypercubes)
+
+    void init(int s, int d) {
+        shape = s; deg = d; dim = shapeDim(s);
+        nfun = isHyperCube(s) ? ipow(d + 1, dim) : binomial(d + dim, d);
+        hier = hierarchicOrder(s, d);
+    }
+
+    // base/sfun/Lagrange1D.ipp:18-147
+    void fun1D(double x, double* v) const {
+        switch (deg) {
+            case 0: v[0] = 1.; break;
+            case 1: v[0] = 1. - x; v[1] = x; break;
+            case 2:
+                v[0] = (1. - x) * (1. - 2. * x); v[1] = 4. * x * (1. - x); v[2] = x * (2. * x - 1.);
+                break;
+            case 3: {
+                const double z0 = 1. - x, z1 = x;
+                v[0] = 0.5 * z0 * (3. * z0 - 1.) * (3. * z0 - 2.);
+                v[1] = 4.5 * z0 * (3. * z0 - 1.) * z1;
+                v[2] = 4.5 * z1 * (3. * z1 - 1.) * z0;
+                v[3] = 0.5 * z1 * (3. * z1 - 1.) * (3. * z1 - 2.);
+            } break;
+            default: std::abort();
+        }
+    }
+    void grad1D(double x, double* g) const {
+        switch (deg) {
+            case 0: g[0] = 0.; break;
+            case 1: g[0] = -1.; g[1] = 1.; break;
+            case 2: g[0] = 4. * x - 3.; g[1] = 4. - 8. * x; g[2] = 4. * x - 1.; break;
+            case 3: {
+                const double z0 = 1. - x, z1 = x;
+                g[0] = -0.5 * ((3. * z0 - 1.) * (3. * z0 - 2.) + 3. * z0 * (6. * z0 - 3.));
+                g[1] = -4.5 * (z1 * (6. * z0 - 1.) - z0 * (3. * z0 - 1.));
+                g[2] = 4.5 * (z0 * (6. * z1 - 1.) - z1 * (3. * z1 - 1.));
+                g[3] = 0.5 * ((3. * z1 - 1.) * (3. * z1 - 2.) + 3. * z1 * (6. * z1 - 3.));
+            } break;
+            default: std::abort();
+        }
+    }
+
+    // lexicographic tensor-product evaluation, base/sfun/TensorProduct.hpp:240-320
+    void tpFun(int D, const double* xi, double* v) const {
+        const int n1 = deg + 1;
+        if (D == 1) { fun1D(xi[0], v); return; }
+        const int nl = ipow(n1, D - 1);
+        std::vector<double> lower(nl), one(n1);
+        tpFun(D - 1, xi, lower.data());
+        fun1D(xi[D - 1], one.data());
+        int ctr = 0;
+        for (int o = 0; o < n1; o++)
+            for (int i = 0; i < nl; i++) v[ctr++] = lower[i] * one[o];
+    }
+    void tpGrad(int D, const double* xi, double* g /* [n][D] */) const {
+        const int n1 = deg + 1;
+        if (D == 1) { grad1D(xi[0], g); return; }
+        const int nl = ipow(n1, D - 1);
+        std::vector<double> lower(nl), lowerG(nl * (D - 1)), one(n1), oneG(n1);
+        tpFun(D - 1, xi, lower.data());
+        tpGrad(D - 1, xi, lowerG.data());
+        fun1D(xi[D - 1], one.data());
+        grad1D(xi[D - 1], oneG.data());
+        int ctr = 0;
+        for (int o = 0; o < n1; o++)
+            for (int i = 0; i < nl; i++) {
+                for (int d = 0; d < D - 1; d++) g[ctr * D + d] = one[o] * lowerG[i * (D - 1) + d];
+                g[ctr * D + (D - 1)] = oneG[o] * lower[i];
+                ctr++;
+            }
+    }
+
+    // function values in hierarchic order
+    void fun(const double* xi, double* v) const {
+        if (isHyperCube(shape)) {
+            std::vector<double> lexi(nfun);
+            tpFun(dim, xi, lexi.data());
+            for (int n = 0; n < nfun; n++) v[hier[n]] = lexi[n];  // TensorProduct.hpp:39-58
+            return;
+        }
+        if (shape == TRI) {  // base/sfun/LagrangeTriangle.ipp
+            if (deg == 1) { v[0] = 1. - xi[0] - xi[1]; v[1] = xi[0]; v[2] = xi[1]; return; }
+            if (deg == 2) {
+                v[0] = (1. - xi[0] - xi[1]) * (1. - 2. * xi[0] - 2. * xi[1]);
+                v[1] = xi[0] * (2. * xi[0] - 1.);
+                v[2] = xi[1] * (2. * xi[1] - 1.);
+                v[3] = 4. * xi[0] * (1. - xi[0] - xi[1]);
+                v[4] = 4. * xi[0] * xi[1];
+                v[5] = 4. * xi[1] * (1. - xi[0] - xi[1]);
+                return;
+            }
+        }
+        if (shape == TET) {  // base/sfun/LagrangeTetrahedron.ipp:30-82
+            if (deg == 1) {
+                v[0] = 1. - xi[0] - xi[1] - xi[2]; v[1] = xi[0]; v[2] = xi[1]; v[3] = xi[2]; return;
+            }
+            if (deg == 2) {
+                const double z1 = xi[0], z2 = xi[1], z3 = xi[2];
+                const double z0 = 1. - z1 - z2 - z3;
+                v[0] = z0 * (2. * z0 - 1.); v[1] = z1 * (2. * z1 - 1.);
+                v[2] = z2 * (2. * z2 - 1.); v[3] = z3 * (2. * z3 - 1.);
+                v[4] = 4. * z0 * z1; v[5] = 4. * z1 * z2; v[6] = 4. * z2 * z0;
+                v[7] = 4. * z0 * z3; v[8] = 4. * z1 * z3; v[9] = 4. * z2 * z3;
+                return;
+            }
+        }
+        std::abort();
+    }
+
+    // reference-space gradients g[n*dim+d], hierarchic order
+    void grad(const double* xi, double* g) const {
+        if (isHyperCube(shape)) {
+            std::vector<double> lexi(nfun * dim);
+            tpGrad(dim, xi, lexi.data());
+            for (int n = 0; n < nfun; n++)
+                for (int d = 0; d < dim; d++) g[hier[n] * dim + d] = lexi[n * dim + d];
+            return;
+        }
+        if (shape == TRI) {
+            if (deg == 1) {
+                const double t[6] = {-1., -1., 1., 0., 0., 1.};
+                std::copy(t, t + 6, g); return;
+            }
+            if (deg == 2) {
+                g[0] = 4. * xi[0] + 4. * xi[1] - 3.; g[1] = g[0];
+                g[2] = 4. * xi[0] - 1.; g[3] = 0.;
+                g[4] = 0.; g[5] = 4. * xi[1] - 1.;
+                g[6] = 4. - 8. * xi[0] - 4. * xi[1]; g[7] = -4. * xi[0];
+                g[8] = 4. * xi[1]; g[9] = 4. * xi[0];
+                g[10] = -4. * xi[1]; g[11] = 4. - 4. * xi[0] - 8. * xi[1];
+                return;
+            }
+        }
+        if (shape == TET) {  // LagrangeTetrahedron.ipp:40-138
+            if (deg == 1) {
+                const double t[12] = {-1., -1., -1., 1., 0., 0., 0., 1., 0., 0., 0., 1.};
+                std::copy(t, t + 12, g); return;
+            }
+            if (deg == 2) {
+                const double z1 = xi[0], z2 = xi[1], z3 = xi[2];
+                const double z0 = 1. - z1 - z2 - z3;
+                const double dz[4][3] = {{-1., -1., -1.}, {1., 0., 0.}, {0., 1., 0.}, {0., 0., 1.}};
+                const double z[4] = {z0, z1, z2, z3};
+                for (int d = 0; d < 3; d++) {
+                    for (int a = 0; a < 4; a++) g[a * 3 + d] = (4. * z[a] - 1.) * dz[a][d];
+                    g[4 * 3 + d] = 4. * (z0 * dz[1][d] + dz[0][d] * z1);
+                    g[5 * 3 + d] = 4. * (z1 * dz[2][d] + dz[1][d] * z2);
+                    g[6 * 3 + d] = 4. * (z0 * dz[2][d] + dz[0][d] * z2);
+                    g[7 * 3 + d] = 4. * (z0 * dz[3][d] + dz[0][d] * z3);
+                    g[8 * 3 + d] = 4. * (z1 * dz[3][d] + dz[1][d] * z3);
+                    g[9 * 3 + d] = 4. * (z2 * dz[3][d] + dz[2][d] * z3);
+                }
+                return;
+            }
+        }
+        std::abort();
+    }
+
+    // support points, hierarchic order (sfun/Lagrange1D.hpp:68-78,
+    // TensorProduct.hpp supportPoints, LagrangeTetrahedron.ipp:140-156)
+    void support(double* p) const {
+        if (isHyperCube(shape)) {
+            const int n1 = deg + 1;
+            std::vector<double> s1(n1);
+            s1[0] = (deg == 0 ? 0.5 : 0.);
+            for (int i = 1; i < n1; i++) s1[i] = double(i) / double(deg);
+            for (int n = 0; n < nfun; n++) {
+                int r = n;
+                for (int d = 0; d < dim; d++) { p[hier[n] * dim + d] = s1[r % n1]; r /= n1; }
+            }
+            return;
+        }
+        if (shape == TRI) {
+            const double t1[6] = {0., 0., 1., 0., 0., 1.};
+            const double t2[12] = {0., 0., 1., 0., 0., 1., .5, 0., .5, .5, 0., .5};
+            if (deg == 1) { std::copy(t1, t1 + 6, p); return; }
+            if (deg == 2) { std::copy(t2, t2 + 12, p); return; }
+        }
+        if (shape == TET) {
+            const double t2[30] = {0., 0., 0., 1., 0., 0., 0., 1., 0., 0., 0., 1., .5, 0., 0.,
+                                   .5, .5, 0., 0., .5, 0., 0., 0., .5, .5, 0., .5, 0., .5, .5};
+            if (deg == 1) { std::copy(t2, t2 + 12, p); return; }
+            if (deg == 2) { std::copy(t2, t2 + 30, p); return; }
+        }
+        std::abort();
+    }
+};
+
+// -----------------------------------------------------------------------------
+// Quadrature. base/Quadrature.hpp:28-79, base/quad/*.
+struct Quad {
+    int n = 0, dim = 0;
+    std::vector<double> w, p;  // p[n*dim]
+};
+
+// base/quad/GaussLegendre.hpp:116-218 (weights, points) on (0,1)
+static void gaussLegendre(int npts, std::vector<double>& w, std::vector<double>& x) {
+    static const double W[11][10] = {
+        {},
+        {1},
+        {0.5, 0.5},
+        {0.277777777777777, 0.444444444444444, 0.277777777777777},
+        {0.173927422568727, 0.326072577431273, 0.326072577431273, 0.173927422568727},
+        {0.118463442528095, 0.239314335249683, 0.284444444444444, 0.239314335249683, 0.118463442528095},
+        {0.085662246189585, 0.180380786524069, 0.233956967286345, 0.233956967286345, 0.180380786524069,
+         0.085662246189585},
+        {0.064742483084435, 0.139852695744638, 0.190915025252559, 0.208979591836735, 0.190915025252559,
+         0.139852695744638, 0.064742483084435},
+        {0.0506142681451885, 0.111190517226687, 0.156853322938943, 0.181341891689181, 0.181341891689181,
+         0.156853322938943, 0.111190517226687, 0.0506142681451885},
+        {0.0406371941807875, 0.0903240803474285, 0.130305348201468, 0.156173538520001, 0.16511967750063,
+         0.156173538520001, 0.130305348201468, 0.0903240803474285, 0.0406371941807875},
+        {0.033335672154344, 0.0747256745752905, 0.109543181257991, 0.134633359654998, 0.147762112357376,
+         0.147762112357376, 0.134633359654998, 0.109543181257991, 0.0747256745752905, 0.033335672154344}};
+    static const double X[11][10] = {
+        {},
+        {0.5},
+        {0.788675134594813, 0.211324865405187},
+        {0.887298334620741, 0.5, 0.112701665379259},
+        {0.930568155797026, 0.669990521792428, 0.330009478207572, 0.069431844202974},
+        {0.953089922969332, 0.769234655052841, 0.5, 0.230765344947159, 0.046910077030668},
+        {0.966234757101576, 0.830604693233132, 0.619309593041598, 0.380690406958402, 0.169395306766868,
+         0.033765242898424},
+        {0.974553956171379, 0.870765592799697, 0.702922575688699, 0.5, 0.297077424311301, 0.129234407200303,
+         0.025446043828621},
+        {0.980144928248768, 0.898333238706813, 0.762766204958164, 0.591717321247825, 0.408282678752175,
+         0.237233795041836, 0.101666761293187, 0.019855071751232},
+        {0.984080119753813, 0.918015553663318, 0.806685716350295, 0.662126711701905, 0.5, 0.337873288298095,
+         0.193314283649705, 0.081984446336682, 0.015919880246187},
+        {0.986953264258586, 0.932531683344493, 0.839704784149512, 0.716697697064623, 0.574437169490815,
+         0.425562830509185, 0.283302302935377, 0.160295215850488, 0.0674683166555075, 0.013046735741414}};
+    if (npts < 1 || npts > 10) std::abort();
+    w.assign(W[npts], W[npts] + npts);
+    x.assign(X[npts], X[npts] + npts);
+}
+
+static Quad makeQuadrature(int shape, int degree) {
+    Quad q;
+    q.dim = shapeDim(shape);
+    if (isHyperCube(shape)) {
+        // GaussLegendre.hpp:36 numPoints=(DEG+2)/2 ; quad/TensorProduct.hpp:122-177
+        const int n1 = (degree + 2) / 2;
+        std::vector<double> w1, x1;
+        gaussLegendre(n1, w1, x1);
+        // recursive construction: lower-dimensional rule repeated, weight *= outer weight
+        std::vector<double> w = w1, p = x1;
+        int curDim = 1;
+        while (curDim < q.dim) {
+            const int nl = (int)w.size();
+            std::vector<double> nw(nl * n1), np(nl * n1 * (curDim + 1));
+            for (int o = 0; o < n1; o++)
+                for (int i = 0; i < nl; i++) {
+                    const int idx = o * nl + i;
+                    nw[idx] = w[i];
+                    for (int d = 0; d < curDim; d++) np[idx * (curDim + 1) + d] = p[i * curDim + d];
+                }
+            for (int o = 0; o < n1; o++)
+                for (int i = 0; i < nl; i++) {
+                    const int idx = o * nl + i;
+                    nw[idx] *= w1[o];
+                    np[idx * (curDim + 1) + curDim] = x1[o];
+                }
+            w.swap(nw); p.swap(np); curDim++;
+        }
+        q.n = (int)w.size(); q.w = w; q.p = p;
+        return q;
+    }
+    auto add = [&](double w, std::initializer_list<double> pt) {
+        q.w.push_back(w); for (double c : pt) q.p.push_back(c); q.n++;
+    };
+    if (shape == TET) {  // base/quad/GaussTetrahedron.hpp:93-176
+        switch (degree) {
+            case 1: add(0.166666666666666, {0.25, 0.25, 0.25}); break;
+            case 2: {
+                const double a = 0.13819660112501051518, b = 0.58541019662496845446, w = 0.04166666666666666667;
+                add(w, {a, a, a}); add(w, {b, a, a}); add(w, {a, b, a}); add(w, {a, a, b});
+            } break;
+            case 3: {
+                const double x = 0.1666666666666667, w1 = -0.13333333333333333;
+                add(w1, {0.25, 0.25, 0.25}); add(0.075, {x, x, x}); add(0.075, {0.5, x, x});
+                add(0.075, {x, 0.5, x}); add(0.075, {x, x, 0.5});
+            } break;
+            case 4: {
+                add(-0.01315555555555555556, {0.25, 0.25, 0.25});
+                double x = 0.071428571428571, y = 0.785714285714286, w = 0.0076222222222222;
+                add(w, {x, x, x}); add(w, {y, x, x}); add(w, {x, y, x}); add(w, {x, x, y});
+                x = 0.100596423833201; y = 0.399403576166799; w = 0.024888888888889;
+                add(w, {y, y, x}); add(w, {y, x, x}); add(w, {x, y, x}); add(w, {x, x, y});
+                add(w, {y, x, y}); add(w, {x, y, y});
+            } break;
+            case 5: {
+                add(0.030283678097089, {0.25, 0.25, 0.25});
+                double x = 0.333333333333333, y = 0.0, w = 0.006026785714286;
+                add(w, {x, x, x}); add(w, {y, x, x}); add(w, {x, y, x}); add(w, {x, x, y});
+                x = 0.090909090909091; y = 0.727272727272727; w = 0.011645249086029;
+                add(w, {x, x, x}); add(w, {y, x, x}); add(w, {x, y, x}); add(w, {x, x, y});
+                x = 0.066550153573664; y = 0.433449846426336; w = 0.010949141561386;
+                add(w, {y, y, x}); add(w, {y, x, x}); add(w, {x, y, x}); add(w, {x, x, y});
+                add(w, {y, x, y}); add(w, {x, y, y});
+            } break;
+            default: std::abort();
+        }
+        return q;
+    }
+    if (shape == TRI) {  // base/quad/GaussTriangle.hpp:97-180 (degrees 1..5)
+        switch (degree) {
+            case 1: add(0.5, {0.333333333333333, 0.333333333333333}); break;
+            case 2:
+                add(0.166666666666666, {0.666666666666667, 0.166666666666667});
+                add(0.166666666666666, {0.166666666666667, 0.666666666666667});
+                add(0.166666666666666, {0.166666666666667, 0.166666666666667});
+                break;
+            case 3:
+                add(-0.28125, {0.333333333333333, 0.333333333333333});
+                add(0.260416666666667, {0.6, 0.2}); add(0.260416666666667, {0.2, 0.6});
+                add(0.260416666666667, {0.2, 0.2});
+                break;
+            case 4:
+                add(0.111690794839005, {0.10810301816807, 0.445948490915965});
+                add(0.054975871827661, {0.816847572980459, 0.091576213509771});
+                add(0.111690794839005, {0.445948490915965, 0.10810301816807});
+                add(0.111690794839005, {0.445948490915965, 0.445948490915965});
+                add(0.054975871827661, {0.091576213509771, 0.816847572980459});
+                add(0.054975871827661, {0.091576213509771, 0.091576213509771});
+                break;
+            case 5:
+                add(0.1125, {0.333333333333333, 0.333333333333333});
+                add(0.066197076394253, {0.05971587178977, 0.470142064105115});
+                add(0.0629695902724135, {0.797426985353087, 0.101286507323456});
+                add(0.066197076394253, {0.470142064105115, 0.05971587178977});
+                add(0.066197076394253, {0.470142064105115, 0.470142064105115});
+                add(0.0629695902724135, {0.101286507323456, 0.797426985353087});
+                add(0.0629695902724135, {0.101286507323456, 0.101286507323456});
+                break;
+            default: std::abort();
+        }
+        return q;
+    }
+    std::abort();
+}
+
+// -----------------------------------------------------------------------------
+// base/mesh/ElementFaces.hpp:224-434 vertex tables of edges / faces
+static const int kEdgeTab[6][12][2] = {
+    {},
+    {{0, 1}},
+    {{0, 1}, {1, 2}, {2, 0}},
+    {{0, 1}, {1, 2}, {2, 3}, {3, 0}},
+    {{0, 1}, {1, 2}, {2, 0}, {3, 0}, {3, 1}, {3, 2}},
+    {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}}};
+static const int kFaceTab[6][6][4] = {
+    {}, {},
+    {{0, 1, 2, -1}},
+    {{0, 1, 2, 3}},
+    {{0, 2, 1, -1}, {0, 1, 3, -1}, {1, 2, 3, -1}, {2, 0, 3, -1}},
+    {{0, 3, 2, 1}, {4, 5, 6, 7}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}}};
+// base/mesh/ElementFaces.hpp:529-611 FaceEdges index + sign
+static const int kFaceEdgeIdx[6][6][4] = {
+    {}, {},
+    {{0, 1, 2, -1}},
+    {{0, 1, 2, 3}},
+    {{2, 1, 0, -1}, {0, 4, 3, -1}, {1, 5, 4, -1}, {2, 3, 5, -1}},
+    {{3, 2, 1, 0}, {4, 5, 6, 7}, {0, 9, 4, 8}, {1, 10, 5, 9}, {2, 11, 6, 10}, {3, 8, 7, 11}}};
+static const int kFaceEdgeSign[6][6][4] = {
+    {}, {},
+    {{1, 1, 1, 0}},
+    {{1, 1, 1, 1}},
+    {{-1, -1, -1, 0}, {1, 1, -1, 0}, {1, 1, -1, 0}, {1, 1, -1, 0}},
+    {{-1, -1, -1, -1}, {1, 1, 1, 1}, {1, 1, -1, -1}, {1, 1, -1, -1}, {1, 1, -1, -1}, {1, 1, -1, -1}}};
+
+static int faceNumVertices(int shape, int nface) {
+    if (nface == VERTEX) return 1;
+    if (nface == EDGE) return 2;
+    if (nface == FACE) return (shape == TRI || shape == TET) ? 3 : 4;
+    return numNFaces(shape, VERTEX);  // CELL
+}
+// j-th vertex of i-th n-face, ElementFaces::index
+static int faceVertex(int shape, int nface, int i, int j) {
+    if (nface == VERTEX) return i;
+    if (nface == EDGE) return kEdgeTab[shape][i][j];
+    if (nface == FACE) return kFaceTab[shape][i][j];
+    return j;
+}
+
+// base/fe/LagrangeElement.hpp:25-115 DoF counts per n-face
+struct FECounts {
+    int perNFace[4], numNF[4], begin[4], total;
+};
+static FECounts feCounts(int shape, int deg) {
+    FECounts c;
+    const int dim = shapeDim(shape);
+    c.perNFace[VERTEX] = 1;
+    if (deg == 0) {  // LagrangeElement<SHAPE,0>: one cell-ish dof; not on the path
+        std::abort();
+    }
+    if (isHyperCube(shape)) {
+        c.perNFace[EDGE] = ipow(deg - 1, 1);
+        c.perNFace[FACE] = dim > 1 ? ipow(deg - 1, 2) : 0;
+        c.perNFace[CELL] = dim > 2 ? ipow(deg - 1, 3) : 0;
+    } else {
+        c.perNFace[EDGE] = binomial(deg - 1, 1);
+        c.perNFace[FACE] = dim > 1 ? binomial(deg - 1, 2) : 0;
+        c.perNFace[CELL] = dim > 2 ? binomial(deg - 1, 3) : 0;
+    }
+    c.numNF[VERTEX] = numNFaces(shape, VERTEX);
+    c.numNF[EDGE] = numNFaces(shape, EDGE);
+    c.numNF[FACE] = numNFaces(shape, FACE);
+    c.numNF[CELL] = (dim == 3 ? 1 : 0);
+    int pos = 0;
+    for (int f = 0; f < 4; f++) { c.begin[f] = pos; pos += c.perNFace[f] * c.numNF[f]; }  // fe/Policies.hpp:38-77
+    c.total = pos;
+    return c;
+}
+
+// -----------------------------------------------------------------------------
+struct Mesh {
+    int shape = 0, geomDeg = 0, dim = 0, npe = 0;
+    int64_t nNodes = 0, nElems = 0;
+    std::vector<double> X;      // [nNodes*dim]
+    std::vector<int64_t> conn;  // [nElems*npe] hierarchic node order
+    SFun geomFun;
+};
+
+struct Field {
+    bool set = false;
+    int deg = 0, dofSize = 0, ndpe = 0;
+    int64_t nObj = 0;
+    std::vector<int64_t> elemDof;   // [nElems*ndpe]
+    std::vector<int64_t> eqn;       // [nObj*dofSize]  (kInvalid when not numbered)
+    std::vector<uint8_t> status;    // [nObj*dofSize]
+    std::vector<double> prescribed; // constraint rhs (valid where CONSTRAINED)
+    std::vector<double> values;     // current values (history 0)
+    SFun feFun;
+};
+
+struct Problem {
+    Mesh mesh;
+    Field fields[5];
+};
+
+// -----------------------------------------------------------------------------
+// DoF-object numbering: base/dof/IndexMap.hpp:221-280
+static int64_t generateDoFIndices(const Mesh& m, int feDeg, std::vector<int64_t>& out) {
+    const FECounts fc = feCounts(m.shape, feDeg);
+    out.assign(m.nElems * fc.total, kInvalid);
+    int64_t numDoFs = 0;
+    const bool iso = (feDeg == m.geomDeg);  // FEFun type == GeomFun type, continuous (IndexMap.hpp:245-258)
+    if (iso) {
+        // base/dof/copyConnectivity.hpp:34-62
+        for (int64_t e = 0; e < m.nElems; e++)
+            for (int n = 0; n < m.npe; n++) {
+                const int64_t id = m.conn[e * m.npe + n];
+                out[e * fc.total + n] = id;
+                numDoFs = std::max(numDoFs, id + 1);
+            }
+        return numDoFs;
+    }
+    // base/dof/generateDoFIndicesFromFaces.hpp:169-298, called for VERTEX, EDGE, FACE, CELL
+    // (IndexMap.hpp:103-121)
+    const int dim = shapeDim(m.shape);
+    const int nV = numNFaces(m.shape, VERTEX);
+    for (int nf = 0; nf <= dim; nf++) {
+        const int stride = fc.perNFace[nf], begin = fc.begin[nf];
+        const int end = begin + stride * fc.numNF[nf];
+        const int coDim = dim - nf;
+        const bool continuityCheck = coDim > 0;
+        const int nfv = faceNumVertices(m.shape, nf);
+        const int numFaces = (nf == CELL ? 1 : numNFaces(m.shape, nf));
+        typedef std::array<int64_t, 4> Key;  // sorted vertex ids (unused slots = -1 sort first, harmless)
+        std::map<Key, std::pair<int64_t, int>> faceMap;
+        for (int64_t e = 0; e < m.nElems; e++) {
+            if (continuityCheck) {
+                for (int f = 0; f < numFaces; f++) {
+                    Key key; key.fill(-1);
+                    for (int v = 0; v < nfv; v++) key[v] = m.conn[e * m.npe + faceVertex(m.shape, nf, f, v)];
+                    std::sort(key.begin(), key.begin() + nfv);
+                    auto check = faceMap.insert(std::make_pair(key, std::make_pair(e, f)));
+                    if (!check.second) {
+                        const int64_t other = check.first->second.first;
+                        const int faceNum = check.first->second.second;
+                        for (int d = 0; d < stride; d++)
+                            out[e * fc.total + begin + f * stride + d] =
+                                out[other * fc.total + begin + faceNum * stride + d];
+                    } else {
+                        for (int d = 0; d < stride; d++) out[e * fc.total + begin + f * stride + d] = numDoFs++;
+                    }
+                }
+            } else {
+                // no continuity check; visited once per (element, face) pair of the FaceIterator
+                for (int rep = 0; rep < numFaces; rep++)
+                    for (int d = begin; d < end; d++) out[e * fc.total + d] = numDoFs++;
+            }
+        }
+        (void)nV;
+    }
+    return numDoFs;
+}
+
+// base/mesh/createBoundaryFromUnstructured.hpp:55-106
+static void meshBoundary(const Mesh& m, std::vector<std::pair<int64_t, int>>& out) {
+    const int dim = shapeDim(m.shape);
+    const int surf = dim - 1;
+    const int nfv = faceNumVertices(m.shape, surf);
+    const int numFaces = numNFaces(m.shape, surf);
+    typedef std::array<int64_t, 4> Key;
+    std::map<Key, std::pair<int64_t, int>> bmap;
+    for (int64_t e = 0; e < m.nElems; e++)
+        for (int f = 0; f < numFaces; f++) {
+            Key key; key.fill(-1);
+            for (int v = 0; v < nfv; v++) key[v] = m.conn[e * m.npe + faceVertex(m.shape, surf, f, v)];
+            std::sort(key.begin(), key.begin() + nfv);
+            auto it = bmap.find(key);
+            if (it == bmap.end()) bmap.insert(std::make_pair(key, std::make_pair(e, f)));
+            else bmap.erase(it);
+        }
+    out.clear();
+    // NOTE: std::map<boost::array> iterates in lexicographic order of the sorted key; unused
+    // trailing slots (-1) only exist when nfv<4 and are equal for all keys.
+    for (auto& kv : bmap) out.push_back(kv.second);
+}
+
+// base/fe/Policies.hpp:99-204 FaceExtraction<FELEMENT,NFACE>
+static void faceExtraction(int shape, int deg, int nface, int faceNo, std::vector<int>& ids) {
+    const FECounts fc = feCounts(shape, deg);
+    if (nface == VERTEX) { ids.push_back(faceNo); return; }
+    if (nface == EDGE) {
+        for (int v = 0; v < 2; v++) ids.push_back(kEdgeTab[shape][faceNo][v]);
+        for (int d = 0; d < fc.perNFace[EDGE]; d++) ids.push_back(fc.begin[EDGE] + faceNo * fc.perNFace[EDGE] + d);
+        return;
+    }
+    if (nface == FACE) {
+        const int nv = faceNumVertices(shape, FACE);
+        for (int v = 0; v < nv; v++) ids.push_back(kFaceTab[shape][faceNo][v]);
+        const int nfe = nv;  // edges per face == vertices per face
+        const int es = fc.perNFace[EDGE];
+        for (int e = 0; e < nfe; e++) {
+            const int en = kFaceEdgeIdx[shape][faceNo][e], sg = kFaceEdgeSign[shape][faceNo][e];
+            for (int d = 0; d < es; d++) {
+                const int ctr = (sg > 0 ? d : es - d - 1);
+                ids.push_back(fc.begin[EDGE] + en * es + ctr);
+            }
+        }
+        for (int d = 0; d < fc.perNFace[FACE]; d++) ids.push_back(fc.begin[FACE] + faceNo * fc.perNFace[FACE] + d);
+        return;
+    }
+    for (int i = 0; i < fc.total; i++) ids.push_back(i);
+}
+
+// -----------------------------------------------------------------------------
+// Geometry. base/geometry.hpp
+// Eigen 3.2 LU/Inverse.h size-3 cofactor
+static inline double cof3(const double m[3][3], int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+}
+// Eigen computeInverseAndDetWithCheck, size 3: returns det, inv(i,j)=cof(j,i)*invdet
+static double inverse3(const double m[3][3], double inv[3][3]) {
+    const double c0 = cof3(m, 0, 0), c1 = cof3(m, 1, 0), c2 = cof3(m, 2, 0);
+    // redux over a 3-vector unrolls as a0 + (a1 + a2) (Core/Redux.h redux_novec_unroller)
+    const double det = c0 * m[0][0] + (c1 * m[1][0] + c2 * m[2][0]);
+    const double invdet = 1. / det;
+    inv[0][0] = c0 * invdet; inv[0][1] = c1 * invdet; inv[0][2] = c2 * invdet;
+    inv[1][0] = cof3(m, 0, 1) * invdet; inv[1][1] = cof3(m, 1, 1) * invdet; inv[1][2] = cof3(m, 2, 1) * invdet;
+    inv[2][0] = cof3(m, 0, 2) * invdet; inv[2][1] = cof3(m, 1, 2) * invdet; inv[2][2] = cof3(m, 2, 2) * invdet;
+    return det;
+}
+static double inverse2(const double m[3][3], double inv[3][3]) {
+    const double det = m[0][0] * m[1][1] - m[1][0] * m[0][1];
+    const double invdet = 1. / det;
+    inv[0][0] = m[1][1] * invdet; inv[1][0] = -m[1][0] * invdet;
+    inv[0][1] = -m[0][1] * invdet; inv[1][1] = m[0][0] * invdet;
+    return det;
+}
+// Eigen LU/Determinant.h bruteforce 3x3
+static inline double det3h(const double m[3][3], int a, int b, int c) {
+    return m[0][a] * (m[1][b] * m[2][c] - m[1][c] * m[2][b]);
+}
+static double determinant3(const double m[3][3]) { return det3h(m, 0, 1, 2) - det3h(m, 1, 0, 2) + det3h(m, 2, 0, 1); }
+
+struct ElemGeom {
+    const Mesh* m; int64_t e;
+    std::vector<double> X;  // [npe][dim] gathered (geometry.hpp:62-86)
+};
+
+static void nodalCoordinates(const Mesh& m, int64_t e, std::vector<double>& X) {
+    X.resize(m.npe * m.dim);
+    for (int n = 0; n < m.npe; n++) {
+        const int64_t id = m.conn[e * m.npe + n];
+        for (int d = 0; d < m.dim; d++) X[n * m.dim + d] = m.X[id * m.dim + d];
+    }
+}
+
+// base/geometry.hpp:142-177 : J(i,a) = sum_n X_n[i] * dphi_n/dxi_a
+static void jacobiMatrix(const Mesh& m, int64_t e, const double* xi, double J[3][3]) {
+    std::vector<double> g(m.npe * m.dim), X;
+    m.geomFun.grad(xi, g.data());
+    nodalCoordinates(m, e, X);
+    for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) J[i][a] = 0.;
+    for (int n = 0; n < m.npe; n++)
+        for (int i = 0; i < m.dim; i++)
+            for (int a = 0; a < m.dim; a++) J[i][a] += X[n * m.dim + i] * g[n * m.dim + a];
+}
+// base/geometry.hpp:186-220,419-445 : contra = (J^T)^{-1}, returns det
+static double contraVariantBasis(const Mesh& m, int64_t e, const double* xi, double contra[3][3]) {
+    double J[3][3], aux[3][3];
+    jacobiMatrix(m, e, xi, J);
+    for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) aux[i][a] = J[a][i];
+    return m.dim == 3 ? inverse3(aux, contra) : inverse2(aux, contra);
+}
+// base/geometry.hpp:226-251,470-488
+static double jacobian(const Mesh& m, int64_t e, const double* xi) {
+    double J[3][3];
+    jacobiMatrix(m, e, xi, J);
+    if (m.dim == 3) return determinant3(J);
+    return J[0][0] * J[1][1] - J[1][0] * J[0][1];
+}
+// base/geometry.hpp:98-128 : x(xi) = sum X_i phi_i
+static void geometryEval(const Mesh& m, int64_t e, const double* xi, double* x) {
+    std::vector<double> f(m.npe), X;
+    m.geomFun.fun(xi, f.data());
+    nodalCoordinates(m, e, X);
+    for (int d = 0; d < m.dim; d++) x[d] = 0.;
+    for (int n = 0; n < m.npe; n++)
+        for (int d = 0; d < m.dim; d++) x[d] += X[n * m.dim + d] * f[n];
+}
+// base/LagrangeShapeFun.hpp:181-202 : gradX[i] = contra * gradXi[i], returns detJ
+static double evaluateGradient(const Mesh& m, const SFun& sf, int64_t e, const double* xi,
+                               std::vector<double>& gradX /* [nfun][dim] */) {
+    std::vector<double> g(sf.nfun * sf.dim);
+    sf.grad(xi, g.data());
+    double contra[3][3];
+    const double detJ = contraVariantBasis(m, e, xi, contra);
+    const int dim = m.dim;
+    gradX.resize(sf.nfun * dim);
+    for (int i = 0; i < sf.nfun; i++)
+        for (int r = 0; r < dim; r++) {
+            double s = contra[r][0] * g[i * dim + 0];
+            for (int c = 1; c < dim; c++) s += contra[r][c] * g[i * dim + c];
+            gradX[i * dim + r] = s;
+        }
+    return detJ;
+}
+
+// -----------------------------------------------------------------------------
+// Element-level integrand kernels
+enum KernelId {
+    K_LAPLACE = 1,           // heat::Laplace / base::kernel::Laplace (any dofSize)
+    K_HYPEL_STVENANT = 2,    // solid::HyperElastic<mat::hypel::StVenant>
+    K_HYPEL_NEOHOOKE = 3,    // solid::HyperElastic<mat::hypel::NeoHookeanCompressible>
+    K_PRESSURE_GRADIENT = 4, // fluid::PressureGradient
+    K_VELOCITY_DIVERGENCE = 5, // fluid::VelocityDivergence (params[0] != 0 : changeSign)
+    K_VECTOR_LAPLACE = 6     // fluid::VectorLaplace (tangent == K_LAPLACE; own residual)
+};
+
+struct Tuple {  // asmb/FieldElementPointerTuple.hpp : (geom, test, trial)
+    const Problem* p; int64_t e; const Field* test; const Field* trial;
+    bool bubnov() const { return test == trial; }  // auxi/EqualPointers
+};
+
+// mat/TensorAlgebra.hpp:149-164
+static inline int voigt(int i, int j) {
+    static const int map[9] = {0, 3, 4, 1, -1, 5, -1, -1, 2};
+    return map[(i + 1) * (j + 1) - 1];
+}
+// mat/TensorAlgebra.hpp:54-59
+static double matDeterminant(const double A[3][3]) {
+    return (A[0][0] * A[1][1] * A[2][2] + A[0][1] * A[1][2] * A[2][0] + A[0][2] * A[1][0] * A[2][1] -
+            A[0][0] * A[1][2] * A[2][1] - A[0][1] * A[1][0] * A[2][2] - A[0][2] * A[1][1] * A[2][0]);
+}
+static void matTransposeTimes(const double A[3][3], const double B[3][3], double C[3][3]) {  // A^T B
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = A[0][i] * B[0][j];
+            for (int k = 1; k < 3; k++) s += A[k][i] * B[k][j];
+            C[i][j] = s;
+        }
+}
+
+struct Material {
+    int kind; double lambda, mu;
+    // mat/hypel/StVenant.hpp:77-88 , NeoHookeanCompressible.hpp:77-93
+    void secondPiolaKirchhoff(const double F[3][3], double S[3][3]) const {
+        if (kind == K_HYPEL_STVENANT) {
+            double C[3][3], E[3][3];
+            matTransposeTimes(F, F, C);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) E[i][j] = 0.5 * (C[i][j] - (i == j ? 1. : 0.));  // greenLagrange
+            const double trE = E[0][0] + E[1][1] + E[2][2];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) S[i][j] = lambda * trE * (i == j ? 1. : 0.) + 2. * mu * E[i][j];
+        } else {
+            double C[3][3], Cinv[3][3];
+            matTransposeTimes(F, F, C);
+            inverse3(C, Cinv);  // A.inverse(), mat/TensorAlgebra.hpp:67-70
+            const double J = matDeterminant(F);
+            const double logJ = std::log(J);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) S[i][j] = (lambda * logJ - mu) * Cinv[i][j] + mu * (i == j ? 1. : 0.);
+        }
+    }
+    // StVenant.hpp:100-114 , NeoHookeanCompressible.hpp:128-172
+    void materialElasticityTensor(const double F[3][3], double C[6][6]) const {
+        if (kind == K_HYPEL_STVENANT) {
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) C[i][j] = 0.;
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[i][j] = lambda;
+            for (int i = 0; i < 3; i++) C[i][i] += 2. * mu;
+            for (int i = 3; i < 6; i++) C[i][i] += mu;
+        } else {
+            double CG[3][3], Cinv[3][3];
+            matTransposeTimes(F, F, CG);
+            inverse3(CG, Cinv);
+            const double J = matDeterminant(F);
+            const double fac2 = mu - lambda * std::log(J);
+            // NOTE: the reference leaves elC entries below the (A<=B, C<=D) fill uninitialised only
+            // where Voigt pairs are not produced; all 36 (AB,CD) pairs are produced by the loops.
+            for (int A = 0; A < 3; A++)
+                for (int B = A; B < 3; B++) {
+                    const int AB = voigt(A, B);
+                    for (int Cc = 0; Cc < 3; Cc++)
+                        for (int D = Cc; D < 3; D++) {
+                            const double cEntry = lambda * Cinv[A][B] * Cinv[Cc][D] +
+                                                  fac2 * (Cinv[A][Cc] * Cinv[B][D] + Cinv[A][D] * Cinv[B][Cc]);
+                            C[AB][voigt(Cc, D)] = cEntry;
+                        }
+                }
+        }
+    }
+};
+
+// post/evaluateField.hpp:228-274 : GradU(J,i) = sum_f g_f[J] * u_f[i]
+static void evaluateFieldGradient(const Tuple& t, const Field& fld, const double* xi, double GradU[3][3]) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> g;
+    evaluateGradient(m, fld.feFun, t.e, xi, g);
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) GradU[a][b] = 0.;
+    for (int f = 0; f < fld.ndpe; f++) {
+        const int64_t obj = fld.elemDof[t.e * fld.ndpe + f];
+        for (int J = 0; J < m.dim; J++)
+            for (int i = 0; i < fld.dofSize; i++) GradU[J][i] += g[f * m.dim + J] * fld.values[obj * fld.dofSize + i];
+    }
+}
+// post/evaluateField.hpp:~200 : u(xi) = sum phi_f u_f
+static void evaluateField(const Tuple& t, const Field& fld, const double* xi, double* u) {
+    std::vector<double> fv(fld.ndpe);
+    fld.feFun.fun(xi, fv.data());
+    for (int i = 0; i < fld.dofSize; i++) u[i] = 0.;
+    for (int f = 0; f < fld.ndpe; f++) {
+        const int64_t obj = fld.elemDof[t.e * fld.ndpe + f];
+        for (int i = 0; i < fld.dofSize; i++) u[i] += fv[f] * fld.values[obj * fld.dofSize + i];
+    }
+}
+// solid/Deformation.hpp:25-46 : F = I + GradU^T
+static void deformationGradient(const Tuple& t, const double* xi, double F[3][3]) {
+    double GradU[3][3];
+    evaluateFieldGradient(t, *t.trial, xi, GradU);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = (i == j ? 1. : 0.);
+    const int dim = t.p->mesh.dim, ds = t.trial->dofSize;
+    for (int i = 0; i < ds; i++) for (int J = 0; J < dim; J++) F[i][J] += GradU[J][i];
+}
+
+// K is row-major [nRow][nCol] here (the reference MatrixXd is column-major; storage only)
+struct LocalMat { int nr, nc; std::vector<double> a; double& operator()(int r, int c) { return a[(size_t)r * nc + c]; } };
+
+// base/kernel/Laplace.hpp:100-151 (via heat/Laplace.hpp:113-126, fluid/VectorLaplace.hpp:40-59)
+static void laplaceTangent(const Tuple& t, double factor, const double* xi, double weight, LocalMat& K) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG, trialG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    if (t.bubnov()) trialG = testG;
+    else evaluateGradient(m, t.trial->feFun, t.e, xi, trialG);
+    const int nRB = t.test->ndpe, nCB = t.trial->ndpe, ds = t.trial->dofSize, dim = m.dim;
+    const double scalar = factor * detJ * weight;
+    for (int M = 0; M < nRB; M++)
+        for (int N = 0; N < nCB; N++) {
+            double entry = 0.;
+            for (int k = 0; k < dim; k++) entry += testG[M * dim + k] * trialG[N * dim + k];
+            entry *= scalar;
+            for (int d = 0; d < ds; d++) K(M * ds + d, N * ds + d) += entry;
+        }
+}
+
+// solid/HyperElastic.hpp:282-310
+static double effectiveElasticity(const double F[3][3], const double S[3][3], const double C[6][6], int nDoFs, int i,
+                                  int J, int k, int L) {
+    double result = (i == k ? S[J][L] : 0.);
+    for (int A = 0; A < nDoFs; A++) {
+        const int v1 = voigt(A, J);
+        for (int B = 0; B < nDoFs; B++) {
+            const int v2 = voigt(B, L);
+            result += F[i][A] * C[v1][v2] * F[k][B];
+        }
+    }
+    return result;
+}
+// solid/HyperElastic.hpp:110-179
+static void hyperElasticTangent(const Tuple& t, const Material& mat, const double* xi, double weight, LocalMat& K) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG, trialG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    if (t.bubnov()) trialG = testG;
+    else evaluateGradient(m, t.trial->feFun, t.e, xi, trialG);
+    const int nRB = t.test->ndpe, nCB = t.trial->ndpe, nD = t.test->dofSize, dim = m.dim;
+    double F[3][3], S[3][3], C[6][6];
+    deformationGradient(t, xi, F);
+    mat.secondPiolaKirchhoff(F, S);
+    mat.materialElasticityTensor(F, C);
+    for (int M = 0; M < nRB; M++)
+        for (int N = 0; N < nCB; N++)
+            for (int i = 0; i < nD; i++)
+                for (int k = 0; k < nD; k++) {
+                    double sum = 0.;
+                    for (int J = 0; J < nD; J++)
+                        for (int L = 0; L < nD; L++)
+                            sum += testG[M * dim + J] * effectiveElasticity(F, S, C, nD, i, J, k, L) * trialG[N * dim + L];
+                    sum *= detJ * weight;
+                    K(M * nD + i, N * nD + k) += sum;
+                }
+}
+// solid/HyperElastic.hpp:209-257
+static void hyperElasticResidual(const Tuple& t, const Material& mat, const double* xi, double weight,
+                                 std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    const int nRB = t.test->ndpe, nD = t.test->dofSize, dim = m.dim;
+    double F[3][3], S[3][3], P[3][3];
+    deformationGradient(t, xi, F);
+    mat.secondPiolaKirchhoff(F, S);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double s = F[i][0] * S[0][j];
+            for (int k = 1; k < 3; k++) s += F[i][k] * S[k][j];
+            P[i][j] = s;
+        }
+    for (int M = 0; M < nRB; M++)
+        for (int i = 0; i < nD; i++) {
+            double sum = 0.;
+            for (int J = 0; J < nD; J++) sum += P[i][J] * testG[M * dim + J];
+            sum *= detJ * weight;
+            v[M * nD + i] += sum;
+        }
+}
+// heat/Laplace.hpp:153-181 : F[i] = (kappa gradU . gradphi_i) detJ w
+static void heatLaplaceResidual(const Tuple& t, double kappa, const double* xi, double weight, std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    double GradU[3][3];
+    evaluateFieldGradient(t, *t.trial, xi, GradU);
+    double flux[3];
+    for (int d = 0; d < m.dim; d++) flux[d] = kappa * GradU[d][0];
+    for (int i = 0; i < t.test->ndpe; i++) {
+        double dot = flux[0] * testG[i * m.dim + 0];
+        for (int d = 1; d < m.dim; d++) dot += flux[d] * testG[i * m.dim + d];
+        v[i] += dot * detJ * weight;
+    }
+}
+// fluid/VectorLaplace.hpp:78-106
+static void vectorLaplaceResidual(const Tuple& t, double visc, const double* xi, double weight, std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    double GradU[3][3];
+    evaluateFieldGradient(t, *t.trial, xi, GradU);
+    const int ds = t.trial->dofSize;
+    for (int M = 0; M < t.test->ndpe; M++)
+        for (int i = 0; i < ds; i++) {
+            double dot = 0.;
+            for (int k = 0; k < m.dim; k++) dot += GradU[k][i] * testG[M * m.dim + k];
+            v[M * ds + i] += visc * dot * detJ * weight;
+        }
+}
+// fluid/PressureGradient.hpp:76-112 ; geom, test(velocity), trial(pressure) passed explicitly
+static void pressureGradientTangent(const Problem& p, int64_t e, const Field& vel, const Field& pre, const double* xi,
+                                    double weight, LocalMat& K) {
+    const Mesh& m = p.mesh;
+    std::vector<double> testG;
+    const double detJ = evaluateGradient(m, vel.feFun, e, xi, testG);
+    std::vector<double> trialF(pre.ndpe);
+    pre.feFun.fun(xi, trialF.data());
+    const int nD = vel.dofSize;
+    for (int M = 0; M < vel.ndpe; M++)
+        for (int N = 0; N < pre.ndpe; N++)
+            for (int d = 0; d < m.dim; d++) K(M * nD + d, N) += -detJ * weight * testG[M * m.dim + d] * trialF[N];
+}
+// fluid/PressureGradient.hpp:130-155 ; p from fluid/evaluations.hpp pressureHistory = evaluateField
+static void pressureGradientResidual(const Tuple& t, const double* xi, double weight, std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testG;
+    const double detJ = evaluateGradient(m, t.test->feFun, t.e, xi, testG);
+    double pr[3];
+    evaluateField(t, *t.trial, xi, pr);
+    const int nD = t.test->dofSize;
+    for (int M = 0; M < t.test->ndpe; M++)
+        for (int i = 0; i < nD; i++) v[M * m.dim + i] += -testG[M * m.dim + i] * pr[0] * detJ * weight;
+}
+// fluid/VelocityDivergence.hpp:67-82
+static void velocityDivergenceTangent(const Tuple& t, bool changeSign, const double* xi, double weight, LocalMat& K) {
+    LocalMat aux; aux.nr = K.nc; aux.nc = K.nr; aux.a.assign((size_t)aux.nr * aux.nc, 0.);
+    pressureGradientTangent(*t.p, t.e, *t.trial, *t.test, xi, weight, aux);  // transposed tuple
+    if (changeSign) for (auto& x : aux.a) x *= -1.0;
+    for (int r = 0; r < K.nr; r++) for (int c = 0; c < K.nc; c++) K(r, c) += aux(c, r);
+}
+// fluid/VelocityDivergence.hpp:100-124 ; divU = trace of velocity gradient (fluid/evaluations.hpp)
+static void velocityDivergenceResidual(const Tuple& t, bool changeSign, const double* xi, double weight,
+                                       std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> testF(t.test->ndpe);
+    t.test->feFun.fun(xi, testF.data());
+    double GradU[3][3];
+    evaluateFieldGradient(t, *t.trial, xi, GradU);
+    double divU = 0.;
+    for (int d = 0; d < m.dim; d++) divU += GradU[d][d];
+    const double detJ = jacobian(m, t.e, xi);
+    for (int M = 0; M < t.test->ndpe; M++) v[M] += (changeSign ? -1.0 : +1.0) * testF[M] * divU * detJ * weight;
+}
+// asmb/BodyForce.hpp:172-205 with a constant force vector f
+static void bodyForceKernel(const Tuple& t, const double* f, const double* xi, double weight, std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    const double detJ = jacobian(m, t.e, xi);
+    std::vector<double> fv(t.test->ndpe);
+    t.test->feFun.fun(xi, fv.data());
+    const int ds = t.test->dofSize;
+    for (int s = 0; s < t.test->ndpe; s++)
+        for (int d = 0; d < ds; d++) v[s * ds + d] += f[d] * fv[s] * weight * detJ;
+}
+
+static void tangentKernel(int kid, const double* params, const Tuple& t, const double* xi, double w, LocalMat& K) {
+    switch (kid) {
+        case K_LAPLACE: case K_VECTOR_LAPLACE: laplaceTangent(t, params[0], xi, w, K); break;
+        case K_HYPEL_STVENANT: case K_HYPEL_NEOHOOKE: {
+            Material mat{kid, params[0], params[1]};
+            hyperElasticTangent(t, mat, xi, w, K);
+        } break;
+        case K_PRESSURE_GRADIENT: pressureGradientTangent(*t.p, t.e, *t.test, *t.trial, xi, w, K); break;
+        case K_VELOCITY_DIVERGENCE: velocityDivergenceTangent(t, params[0] != 0., xi, w, K); break;
+        default: std::abort();
+    }
+}
+static void residualKernel(int kid, const double* params, const Tuple& t, const double* xi, double w,
+                           std::vector<double>& v) {
+    switch (kid) {
+        case K_LAPLACE: heatLaplaceResidual(t, params[0], xi, w, v); break;
+        case K_VECTOR_LAPLACE: vectorLaplaceResidual(t, params[0], xi, w, v); break;
+        case K_HYPEL_STVENANT: case K_HYPEL_NEOHOOKE: {
+            Material mat{kid, params[0], params[1]};
+            hyperElasticResidual(t, mat, xi, w, v);
+        } break;
+        case K_PRESSURE_GRADIENT: pressureGradientResidual(t, xi, w, v); break;
+        case K_VELOCITY_DIVERGENCE: velocityDivergenceResidual(t, params[0] != 0., xi, w, v); break;
+        default: std::abort();
+    }
+}
+
+// -----------------------------------------------------------------------------
+// Solver: base/solver/Eigen3.hpp + base/solver/TripletContainer.hpp
+struct Triplet {  // TripletContainer.hpp:68-126 (Index = int)
+    int row, col; mutable double value;
+    bool operator<(const Triplet& o) const { return (row < o.row) || (!(o.row < row) && (col < o.col)); }
+};
+
+struct System {
+    size_t n = 0;
+    bool preStructured = false;
+    std::set<Triplet> tmp;
+    std::vector<Triplet> trip;
+    std::vector<double> b;
+    // finished CSR
+    std::vector<int64_t> rowptr; std::vector<int32_t> col; std::vector<double> val;
+    std::string error;
+
+    // TripletContainer.hpp:305-352
+    void insert(int i, int j, double value) {
+        Triplet t{i, j, value};
+        if (!preStructured) {
+            auto check = tmp.insert(t);
+            if (!check.second) {
+                t.value += check.first->value;  // addTo
+                auto hint = check.first; ++hint;
+                tmp.erase(check.first);
+                tmp.insert(hint, t);
+            }
+        } else {
+            auto it = std::lower_bound(trip.begin(), trip.end(), t);
+            const bool ok = it != trip.end() && it->row == i && it->col == j;
+            if (!ok) { error = "TripletContainer had not been properly set up"; return; }
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+            it->value += value;
+        }
+    }
+    // Eigen3.hpp:81-106
+    void insertToLHS(const LocalMat& mat, const std::vector<size_t>& rows, const std::vector<size_t>& cols) {
+        for (size_t i = 0; i < rows.size(); i++)
+            for (size_t j = 0; j < cols.size(); j++) {
+                if (rows[i] >= n || cols[j] >= n) { error = "index out of bound"; return; }
+                insert((int)rows[i], (int)cols[j], mat.a[i * cols.size() + j]);
+            }
+    }
+    // Eigen3.hpp:111-124 (the reference's += is not atomic; the port makes it atomic under OpenMP)
+    void insertToRHS(const std::vector<double>& v, const std::vector<size_t>& dofs) {
+        for (size_t i = 0; i < dofs.size(); i++) {
+            if (dofs[i] >= n) { error = "index out of bound"; return; }
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+            b[dofs[i]] += v[i];
+        }
+    }
+    // Eigen3.hpp:142-153 + TripletContainer::prepare :356-368 ; setFromTriplets keeps explicit zeros.
+    void finishAssembly() {
+        if (!preStructured) {
+            trip.assign(tmp.begin(), tmp.end());
+            tmp.clear();
+        }
+        // triplets are sorted by (row, col) and unique -> canonical CSR
+        rowptr.assign(n + 1, 0);
+        col.resize(trip.size()); val.resize(trip.size());
+        for (size_t k = 0; k < trip.size(); k++) {
+            rowptr[trip[k].row + 1]++;
+            col[k] = trip[k].col; val[k] = trip[k].value;
+        }
+        for (size_t r = 0; r < n; r++) rowptr[r + 1] += rowptr[r];
+        trip.clear(); std::vector<Triplet>().swap(trip);
+    }
+};
+
+// asmb/collectFromDoFs.hpp:82-136 (plain Dirichlet constraints: empty weighted-DoF lists)
+static bool collectFromDoFs(const Field& f, int64_t e, std::vector<uint8_t>& status, std::vector<size_t>& ids,
+                            std::vector<double>& values, bool incremental) {
+    bool allInactive = true;
+    for (int d = 0; d < f.ndpe; d++) {
+        const int64_t obj = f.elemDof[e * f.ndpe + d];
+        for (int s = 0; s < f.dofSize; s++) {
+            const size_t k = obj * f.dofSize + s;
+            status.push_back(f.status[k]);
+            ids.push_back((size_t)f.eqn[k]);
+            // DegreeOfFreedom.hpp:248-264
+            if (f.status[k] == CONSTRAINED) values.push_back(incremental ? f.prescribed[k] - f.values[k] : f.prescribed[k]);
+            else values.push_back(std::numeric_limits<double>::max());
+            if (f.status[k] != INACTIVE) allInactive = false;
+        }
+    }
+    return !allInactive;
+}
+
+// asmb/assembleMatrix.hpp:212-338 with detail_::assembleRow :56-130 (no master DoFs)
+static void assembleMatrix(LocalMat& K, const std::vector<uint8_t>& rS, const std::vector<uint8_t>& cS,
+                           const std::vector<size_t>& rID, const std::vector<size_t>& cID,
+                           const std::vector<double>& cVal, System& solver) {
+    std::vector<size_t> effR, effC;
+    for (size_t r = 0; r < rID.size(); r++) if (rS[r] == ACTIVE) effR.push_back(rID[r]);
+    for (size_t c = 0; c < cID.size(); c++) if (cS[c] == ACTIVE) effC.push_back(cID[c]);
+    LocalMat sys; sys.nr = (int)effR.size(); sys.nc = (int)effC.size(); sys.a.assign((size_t)sys.nr * sys.nc, 0.);
+    std::vector<double> vec(effR.size(), 0.);
+    unsigned activeRow = 0;
+    for (size_t r = 0; r < rID.size(); r++) {
+        if (rS[r] != ACTIVE) continue;  // CONSTRAINED rows without masters contribute nothing
+        unsigned activeCol = 0;
+        const double rowWeight = 1.0;
+        for (size_t c = 0; c < cID.size(); c++) {
+            if (cS[c] == ACTIVE) { sys(activeRow, activeCol) = rowWeight * K((int)r, (int)c); activeCol++; }
+            else if (cS[c] == CONSTRAINED) vec[activeRow] -= cVal[c] * rowWeight * K((int)r, (int)c);
+        }
+        activeRow++;
+    }
+    solver.insertToLHS(sys, effR, effC);
+    solver.insertToRHS(vec, effR);
+}
+
+// asmb/assembleForces.hpp:58-139
+static void assembleForces(const std::vector<double>& f, const std::vector<uint8_t>& st, const std::vector<size_t>& ids,
+                           System& solver) {
+    std::vector<size_t> eff; std::vector<double> v;
+    for (size_t d = 0; d < ids.size(); d++) if (st[d] == ACTIVE) { eff.push_back(ids[d]); v.push_back(f[d]); }
+    solver.insertToRHS(v, eff);
+}
+
+// asmb/StiffnessMatrix.hpp:159-225
+static void stiffnessElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
+                             int trialId, bool incremental, int64_t e) {
+    const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
+    Tuple t{&p, e, &test, &trial};
+    std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
+    bool doSomething = collectFromDoFs(test, e, rS, rID, rV, incremental);
+    if (!doSomething) return;
+    if (t.bubnov()) { cS = rS; cID = rID; cV = rV; }
+    else doSomething = collectFromDoFs(trial, e, cS, cID, cV, incremental);
+    if (!doSomething) return;
+    LocalMat K; K.nr = (int)rID.size(); K.nc = (int)cID.size(); K.a.assign((size_t)K.nr * K.nc, 0.);
+    for (int g = 0; g < q.n; g++) tangentKernel(kid, params, t, &q.p[g * q.dim], q.w[g], K);  // Quadrature.hpp:132-141
+    assembleMatrix(K, rS, cS, rID, cID, cV, solver);
+}
+
+// asmb/ForceIntegrator.hpp:126-160
+static void forceElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
+                         int trialId, double factor, bool body, int64_t e) {
+    const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
+    Tuple t{&p, e, &test, &trial};
+    std::vector<uint8_t> st; std::vector<size_t> ids; std::vector<double> pv;
+    if (!collectFromDoFs(test, e, st, ids, pv, false)) return;
+    std::vector<double> f(ids.size(), 0.);
+    for (int g = 0; g < q.n; g++) {
+        if (body) bodyForceKernel(t, params, &q.p[g * q.dim], q.w[g], f);
+        else residualKernel(kid, params, t, &q.p[g * q.dim], q.w[g], f);
+    }
+    for (auto& x : f) x *= factor;
+    assembleForces(f, st, ids, solver);
+}
+
+// solver/TripletContainer.hpp:158-301
+static void registerFields(const Problem& p, System& solver, int testId, int trialId) {
+    const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
+    const bool bubnov = (&test == &trial);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) {
+        std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
+        if (!collectFromDoFs(test, e, rS, rID, rV, false)) continue;
+        if (bubnov) { cS = rS; cID = rID; }
+        else if (!collectFromDoFs(trial, e, cS, cID, cV, false)) continue;
+        std::vector<size_t> effR, effC;
+        for (size_t r = 0; r < rID.size(); r++) if (rS[r] == ACTIVE) effR.push_back(rID[r]);
+        for (size_t c = 0; c < cID.size(); c++) if (cS[c] == ACTIVE) effC.push_back(cID[c]);
+        for (size_t r : effR) for (size_t c : effC) solver.tmp.insert(Triplet{(int)r, (int)c, 0.});
+    }
+    const size_t cur = solver.trip.size();
+    solver.trip.insert(solver.trip.end(), solver.tmp.begin(), solver.tmp.end());
+    solver.tmp.clear();
+    if (cur > 0) std::sort(solver.trip.begin(), solver.trip.end());
+    solver.preStructured = true;
+}
+
+}  // namespace orc
+
+// =============================================================================
+// C interface (ctypes) -- flat arrays, handles
+// =============================================================================
+using namespace orc;
+
+extern "C" {
+
+int orc_shape_nfun(int shape, int deg) { SFun s; s.init(shape, deg); return s.nfun; }
+void orc_shape_eval(int shape, int deg, const double* xi, double* fun, double* grad) {
+    SFun s; s.init(shape, deg);
+    if (fun) s.fun(xi, fun);
+    if (grad) s.grad(xi, grad);
+}
+void orc_support_points(int shape, int deg, double* pts) { SFun s; s.init(shape, deg); s.support(pts); }
+int orc_hierarchic_order(int shape, int deg, int* out) {
+    auto t = hierarchicOrder(shape, deg);
+    for (size_t i = 0; i < t.size(); i++) out[i] = t[i];
+    return (int)t.size();
+}
+int orc_quadrature(int shape, int degree, double* w, double* p) {
+    Quad q = makeQuadrature(shape, degree);
+    if (w) std::copy(q.w.begin(), q.w.end(), w);
+    if (p) std::copy(q.p.begin(), q.p.end(), p);
+    return q.n;
+}
+int orc_face_dofs(int shape, int deg, int nface, int faceNo, int* out) {
+    std::vector<int> ids; faceExtraction(shape, deg, nface, faceNo, ids);
+    for (size_t i = 0; i < ids.size(); i++) out[i] = ids[i];
+    return (int)ids.size();
+}
+
+void* orc_problem_new() { return new Problem(); }
+void orc_problem_free(void* h) { delete (Problem*)h; }
+
+void orc_set_mesh(void* h, int shape, int geomDeg, int dim, int64_t nNodes, const double* coords, int64_t nElems,
+                  const int64_t* conn) {
+    Problem& p = *(Problem*)h;
+    Mesh& m = p.mesh;
+    m.shape = shape; m.geomDeg = geomDeg; m.dim = dim; m.nNodes = nNodes; m.nElems = nElems;
+    m.geomFun.init(shape, geomDeg);
+    m.npe = m.geomFun.nfun;
+    m.X.assign(coords, coords + nNodes * dim);
+    m.conn.assign(conn, conn + nElems * m.npe);
+}
+
+// base/dof/generate.hpp:65-115 ; returns number of DoF objects, fills elem_dof[nElems*ndpe]
+int64_t orc_dof_generate(void* h, int feDeg, int64_t* elemDof) {
+    Problem& p = *(Problem*)h;
+    std::vector<int64_t> out;
+    const int64_t n = generateDoFIndices(p.mesh, feDeg, out);
+    std::copy(out.begin(), out.end(), elemDof);
+    return n;
+}
+int orc_ndpe(int shape, int feDeg) { return feCounts(shape, feDeg).total; }
+
+// IndexMap::generateSparsityPattern, base/dof/IndexMap.hpp:292-319. Returns nnz; pairs may be NULL to count.
+int64_t orc_sparsity_pattern(int64_t nElems, int ndpe, const int64_t* elemDof, int64_t nDoFs, int64_t* pairs) {
+    std::vector<std::set<int64_t>> conn(nDoFs);
+    for (int64_t e = 0; e < nElems; e++)
+        for (int d1 = 0; d1 < ndpe; d1++)
+            for (int d2 = 0; d2 < ndpe; d2++) conn[elemDof[e * ndpe + d1]].insert(elemDof[e * ndpe + d2]);
+    int64_t k = 0;
+    for (int64_t d = 0; d < nDoFs; d++)
+        for (int64_t c : conn[d]) { if (pairs) { pairs[2 * k] = d; pairs[2 * k + 1] = c; } k++; }
+    return k;
+}
+
+// MeshBoundary::create ; out pairs (elem, face); returns count (out may be NULL)
+int64_t orc_mesh_boundary(void* h, int64_t* out) {
+    Problem& p = *(Problem*)h;
+    std::vector<std::pair<int64_t, int>> b;
+    meshBoundary(p.mesh, b);
+    if (out) for (size_t i = 0; i < b.size(); i++) { out[2 * i] = b[i].first; out[2 * i + 1] = b[i].second; }
+    return (int64_t)b.size();
+}
+
+// Support-point locations of the DoFs a boundary face carries: base/dof/constrainBoundary.hpp:49-123.
+// For boundary pair k: writes local dof numbers + physical x (via Geometry) in visiting order.
+// Returns number of (pair, localDof) visits; arrays may be NULL for counting.
+int64_t orc_boundary_dof_points(void* h, int feDeg, int64_t nPairs, const int64_t* pairs, int64_t* elemOut,
+                                int* localOut, double* xOut) {
+    Problem& p = *(Problem*)h;
+    const Mesh& m = p.mesh;
+    SFun fe; fe.init(m.shape, feDeg);
+    std::vector<double> sp(fe.nfun * fe.dim);
+    fe.support(sp.data());
+    const int surf = shapeDim(m.shape) - 1;
+    int64_t k = 0;
+    for (int64_t b = 0; b < nPairs; b++) {
+        const int64_t e = pairs[2 * b]; const int fno = (int)pairs[2 * b + 1];
+        std::vector<int> ids; faceExtraction(m.shape, feDeg, surf, fno, ids);
+        for (int id : ids) {
+            if (elemOut) {
+                elemOut[k] = e; localOut[k] = id;
+                geometryEval(m, e, &sp[id * fe.dim], &xOut[k * m.dim]);
+            }
+            k++;
+        }
+    }
+    return k;
+}
+
+void orc_set_field(void* h, int id, int feDeg, int dofSize, int64_t nObj, const int64_t* elemDof, const int64_t* eqn,
+                   const uint8_t* status, const double* prescribed, const double* values) {
+    Problem& p = *(Problem*)h;
+    Field& f = p.fields[id];
+    f.set = true; f.deg = feDeg; f.dofSize = dofSize; f.nObj = nObj;
+    f.feFun.init(p.mesh.shape, feDeg);
+    f.ndpe = f.feFun.nfun;
+    f.elemDof.assign(elemDof, elemDof + p.mesh.nElems * f.ndpe);
+    const size_t n = (size_t)nObj * dofSize;
+    f.eqn.assign(eqn, eqn + n);
+    f.status.assign(status, status + n);
+    f.prescribed.assign(prescribed, prescribed + n);
+    f.values.assign(values, values + n);
+}
+void orc_set_field_values(void* h, int id, const double* values) {
+    Field& f = ((Problem*)h)->fields[id];
+    f.values.assign(values, values + (size_t)f.nObj * f.dofSize);
+}
+
+// base/dof/numbering.hpp:44-68
+int64_t orc_number_dofs(int64_t nObj, int dofSize, const uint8_t* status, int64_t init, int64_t* eqn) {
+    int64_t counter = init;
+    for (int64_t o = 0; o < nObj; o++)
+        for (int d = 0; d < dofSize; d++) {
+            if (status[o * dofSize + d] == ACTIVE) eqn[o * dofSize + d] = counter++;
+            else eqn[o * dofSize + d] = kInvalid;
+        }
+    return counter - init;
+}
+
+void* orc_system_new(int64_t n) { System* s = new System(); s->n = (size_t)n; s->b.assign(n, 0.); return s; }
+void orc_system_free(void* s) { delete (System*)s; }
+void orc_register_fields(void* s, void* h, int test, int trial) { registerFields(*(Problem*)h, *(System*)s, test, trial); }
+
+// asmb/StiffnessMatrix.hpp:49-87 + auxi/parallel.hpp:25-60. nthreads>1 requires a pre-structured system
+// (TripletContainer.hpp:314-318). Returns 0 or -1 (error string via orc_system_error).
+int orc_stiffness(void* s, void* h, int kid, const double* params, int quadDeg, int test, int trial, int incremental,
+                  int nthreads) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    if (nthreads != 1 && !sys.preStructured) { sys.error = "Multiple threads are not allowed for this method"; return -1; }
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_num_procs();
+#pragma omp parallel for num_threads(nthreads)
+#endif
+    for (int64_t e = 0; e < p.mesh.nElems; e++) stiffnessElement(p, sys, q, kid, params, test, trial, incremental != 0, e);
+    return sys.error.empty() ? 0 : -1;
+}
+// asmb/ForceIntegrator.hpp:37-71 (factor -1, serial loop)
+int orc_residual(void* s, void* h, int kid, const double* params, int quadDeg, int test, int trial) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, kid, params, test, trial, -1.0, false, e);
+    return sys.error.empty() ? 0 : -1;
+}
+// asmb/BodyForce.hpp:65-84 with f(x) = const vector f[dofSize]
+int orc_bodyforce(void* s, void* h, const double* f, int quadDeg, int test) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, f, test, test, 1.0, true, e);
+    return sys.error.empty() ? 0 : -1;
+}
+void orc_finish(void* s) { ((System*)s)->finishAssembly(); }
+int64_t orc_nnz(void* s) { return (int64_t)((System*)s)->col.size(); }
+void orc_get_csr(void* s, int64_t* rowptr, int32_t* col, double* val, double* rhs) {
+    System& sys = *(System*)s;
+    if (rowptr) std::copy(sys.rowptr.begin(), sys.rowptr.end(), rowptr);
+    if (col) std::copy(sys.col.begin(), sys.col.end(), col);
+    if (val) std::copy(sys.val.begin(), sys.val.end(), val);
+    if (rhs) std::copy(sys.b.begin(), sys.b.end(), rhs);
+}
+const char* orc_system_error(void* s) { return ((System*)s)->error.c_str(); }
+// Eigen3.hpp:128-138 : ||b||_2 / length (quirk kept)
+double orc_rhs_norm(void* s) {
+    System& sys = *(System*)s; double a = 0.;
+    for (double x : sys.b) a += x * x;
+    return std::sqrt(a) / (double)sys.b.size();
+}
+
+// sum over elements and quadrature points of detJ*w : base/kernel/Measure.hpp (volume), used by
+// reference/02-areaVolume/areaVolume.cpp:62-76
+double orc_measure(void* h, int quadDeg) {
+    Problem& p = *(Problem*)h;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    double vol = 0.;
+    for (int64_t e = 0; e < p.mesh.nElems; e++)
+        for (int g = 0; g < q.n; g++) vol += jacobian(p.mesh, e, &q.p[g * q.dim]) * q.w[g];
+    return vol;
+}
+
+// base/post/ErrorNorm.hpp L2 error against tabulated reference values at quadrature points:
+// caller supplies uref[e][g][dofSize]; returns sqrt(sum |u_h - uref|^2 detJ w). Also exports x(e,g) when xOut given.
+double orc_l2_error(void* h, int fieldId, int quadDeg, const double* uref, double* xOut) {
+    Problem& p = *(Problem*)h; const Field& f = p.fields[fieldId];
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    double err2 = 0.;
+    for (int64_t e = 0; e < p.mesh.nElems; e++)
+        for (int g = 0; g < q.n; g++) {
+            Tuple t{&p, e, &f, &f};
+            const double* xi = &q.p[g * q.dim];
+            if (xOut) { geometryEval(p.mesh, e, xi, &xOut[(e * q.n + g) * p.mesh.dim]); continue; }
+            double u[3]; evaluateField(t, f, xi, u);
+            const double detJ = jacobian(p.mesh, e, xi);
+            double d2 = 0.;
+            for (int i = 0; i < f.dofSize; i++) { const double d = u[i] - uref[(e * q.n + g) * f.dofSize + i]; d2 += d * d; }
+            err2 += d2 * q.w[g] * detJ;
+        }
+    return std::sqrt(err2);
+}
+
+// tools/meshGeneration/unitCube/unitCube.hpp:85-265 restated in memory (no SMF round trip).
+// dim in {2,3}; simplex: 6 tets per cube / 2 tris per square (degree 1 only); returns via out arrays.
+void orc_unit_cube_sizes(int dim, int simplex, int degree, int e1, int e2, int e3, int64_t* nNodes, int64_t* nElems,
+                         int* npe) {
+    const int n1 = degree * e1 + 1, n2 = dim > 1 ? degree * e2 + 1 : 1, n3 = dim > 2 ? degree * e3 + 1 : 1;
+    *nNodes = (int64_t)n1 * n2 * n3;
+    *nElems = (int64_t)e1 * (dim > 1 ? e2 : 1) * (dim > 2 ? e3 : 1) * (simplex ? (dim == 3 ? 6 : dim) : 1);
+    *npe = simplex ? dim + 1 : ipow(degree + 1, dim);
+}
+void orc_unit_cube(int dim, int simplex, int degree, int e1, int e2, int e3, double* coords /*[n*dim]*/, int64_t* conn) {
+    if (dim < 2) std::abort();
+    if (dim == 2) e3 = 1;
+    const int n1 = degree * e1 + 1, n2 = degree * e2 + 1, n3 = dim > 2 ? degree * e3 + 1 : 1;
+    const double h1 = 1.0 / double(degree * e1), h2 = 1.0 / double(degree * e2), h3 = 1.0 / double(degree * e3);
+    int64_t k = 0;
+    for (int i3 = 0; i3 < n3; i3++)
+        for (int i2 = 0; i2 < n2; i2++)
+            for (int i1 = 0; i1 < n1; i1++) {
+                coords[k * dim + 0] = h1 * i1; coords[k * dim + 1] = h2 * i2;
+                if (dim == 3) coords[k * dim + 2] = h3 * i3;
+                k++;
+            }
+    const int shape = dim == 2 ? QUAD : HEX;
+    const std::vector<int> HO = hierarchicOrder(shape, degree);
+    // base/cut/DecomposeHyperCube.hpp:70-90
+    static const int tri[2][3] = {{0, 1, 3}, {2, 3, 1}};
+    static const int tet[6][4] = {{0, 1, 3, 4}, {1, 3, 4, 5}, {3, 4, 5, 7}, {1, 3, 5, 2}, {3, 5, 2, 7}, {5, 2, 7, 6}};
+    int64_t ec = 0;
+    for (int i3 = 0; i3 < e3; i3++)
+        for (int i2 = 0; i2 < e2; i2++)
+            for (int i1 = 0; i1 < e1; i1++) {
+                std::vector<int64_t> cube;
+                const int64_t i = degree * i1 + (int64_t)degree * i2 * n1 + (dim > 2 ? (int64_t)degree * i3 * n1 * n2 : 0);
+                if (dim == 2) {
+                    for (int d2 = 0; d2 <= degree; d2++) for (int d1 = 0; d1 <= degree; d1++) cube.push_back(i + d2 * n1 + d1);
+                } else {
+                    for (int d3 = 0; d3 <= degree; d3++)
+                        for (int d2 = 0; d2 <= degree; d2++)
+                            for (int d1 = 0; d1 <= degree; d1++) cube.push_back(i + (int64_t)d3 * n1 * n2 + d2 * n1 + d1);
+                }
+                if (simplex) {
+                    const int ns = dim == 3 ? 6 : 2;
+                    for (int s = 0; s < ns; s++) {
+                        for (int v = 0; v < dim + 1; v++) {
+                            const int hv = dim == 3 ? tet[s][v] : tri[s][v];
+                            conn[ec * (dim + 1) + v] = cube[HO[hv]];
+                        }
+                        ec++;
+                    }
+                } else {
+                    const int npe = (int)cube.size();
+                    for (int v = 0; v < npe; v++) conn[ec * npe + HO[v]] = cube[v];
+                    ec++;
+                }
+            }
+}
+
+int orc_num_procs() {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
