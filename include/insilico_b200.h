@@ -1,0 +1,148 @@
+/* =============================================================================
+ * insilico_b200.h -- C ABI of the B200-native element-assembly engine
+ * =============================================================================
+ * Drop-in boundary for inSilico's assembly hot path.  The
+ * reference is header-only C++ templates with no FFI of its own; each entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on error; isl_last_error()
+ *     returns the message (the C++ facade turns it into the reference's
+ *     VERIFY_MSG behaviour: message on stderr + abort(), base/verify.hpp:139-149).
+ *   - array arguments may be HOST or DEVICE pointers (copied with
+ *     cudaMemcpyDefault under unified addressing).
+ *   - shapes, n-faces and DoF status use the reference's enum values
+ *     (base/shape.hpp:25-45, base/dof/DegreeOfFreedom.hpp:33-38).
+ *   - fields are addressed by 0-based id (the reference's FieldBinder uses 1-based
+ *     template indices, base/asmb/FieldBinder.hpp:132-138; the facade subtracts 1).
+ *   - element-local ordering is the reference's hierarchic ordering (vertices,
+ *     edges, faces, cell; base/mesh/HierarchicOrder.hpp), DoF object s major,
+ *     component d minor: local index s*dof_size+d (base/asmb/collectFromDoFs.hpp).
+ * ===========================================================================*/
+#ifndef INSILICO_B200_H
+#define INSILICO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* base/shape.hpp:25-32 */
+enum { ISL_POINT = 0, ISL_LINE = 1, ISL_TRI = 2, ISL_QUAD = 3, ISL_TET = 4, ISL_HEX = 5 };
+/* base/shape.hpp:40-45 */
+enum { ISL_VERTEX = 0, ISL_EDGE = 1, ISL_FACE = 2, ISL_CELL = 3 };
+/* base/dof/DegreeOfFreedom.hpp:33-38 */
+enum { ISL_ACTIVE = 0, ISL_CONSTRAINED = 1, ISL_INACTIVE = 2 };
+
+/* integrand kernels ("kernel objects" of the reference) */
+enum {
+    ISL_K_LAPLACE = 1,             /* heat::Laplace (heat/Laplace.hpp:113-181), base::kernel::Laplace
+                                      (base/kernel/Laplace.hpp:100-151); params = {factor}            */
+    ISL_K_HYPEL_STVENANT = 2,      /* solid::HyperElastic<mat::hypel::StVenant> (solid/HyperElastic.hpp:110-257,
+                                      mat/hypel/StVenant.hpp); params = {lambda, mu} (mat/Lame.hpp)      */
+    ISL_K_HYPEL_NEOHOOKE = 3,      /* solid::HyperElastic<mat::hypel::NeoHookeanCompressible>; {lambda, mu} */
+    ISL_K_PRESSURE_GRADIENT = 4,   /* fluid::PressureGradient (fluid/PressureGradient.hpp:76-155); no params */
+    ISL_K_VELOCITY_DIVERGENCE = 5, /* fluid::VelocityDivergence (fluid/VelocityDivergence.hpp:67-124);
+                                      params = {changeSign != 0}                                       */
+    ISL_K_VECTOR_LAPLACE = 6       /* fluid::VectorLaplace (fluid/VectorLaplace.hpp:40-112); {viscosity}   */
+};
+
+typedef struct isl_engine* isl_handle;
+
+const char* isl_last_error(void);
+int isl_version(void);
+
+/* ---- engine ------------------------------------------------------------- */
+int isl_engine_create(int device, isl_handle* out);
+int isl_engine_destroy(isl_handle h);
+int isl_synchronize(isl_handle h);
+/* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
+void* isl_engine_stream(isl_handle h);
+/* number of the engine's own kernels launched since creation (bench.py "gpu_launches") */
+int64_t isl_kernel_launches(isl_handle h);
+
+/* ---- host-side tables (no GPU needed) ------------------------------------ */
+/* base::Quadrature<DEG,SHAPE> (base/Quadrature.hpp:113-143): returns #points; weights[n], points[n*dim] */
+int isl_quadrature(int shape, int degree, double* weights, double* points);
+/* base::LagrangeShapeFun<DEG,SHAPE>::fun / gradient in hierarchic order (base/LagrangeShapeFun.hpp) */
+int isl_shape_nfun(int shape, int degree);
+int isl_shape_eval(int shape, int degree, const double* xi, double* fun, double* grad);
+int isl_support_points(int shape, int degree, double* pts);
+
+/* ---- DoF handling (host side, base/dof) ----------------------------------- */
+/* base::dof::generate<FEBasis>(mesh, field) (base/dof/generate.hpp:46-115, IndexMap.hpp:221-280):
+ * elem_dof[n_elems * ndpe] receives DoF-object ids per element, *n_obj their number.                     */
+int isl_dof_generate(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int fe_deg, int32_t* elem_dof,
+                     int64_t* n_obj);
+int isl_ndpe(int shape, int fe_deg);
+/* base::mesh::MeshBoundary::create (base/mesh/MeshBoundary.hpp, createBoundaryFromUnstructured.hpp:55-106):
+ * pairs[2*k] = element, pairs[2*k+1] = face number; pass NULL to query the count (*n_pairs).              */
+int isl_mesh_boundary(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int64_t* pairs,
+                      int64_t* n_pairs);
+/* DoFs visited by base::dof::constrainBoundary (base/dof/constrainBoundary.hpp:49-123) in visiting order:
+ * for each boundary pair the DoF objects on that face and the physical location of their support points.
+ * obj[n], x[n*dim]; pass obj = NULL to query *n.                                                          */
+int isl_boundary_dofs(int shape, int geom_deg, int dim, const double* coords, int64_t n_elems, const int32_t* conn,
+                      int fe_deg, const int32_t* elem_dof, int64_t n_pairs, const int64_t* pairs, int32_t* obj,
+                      double* x, int64_t* n);
+/* base::dof::numberDoFsConsecutively (base/dof/numbering.hpp:44-68): eqn[n_obj*dof_size], -1 where not ACTIVE */
+int isl_number_dofs(int64_t n_obj, int dof_size, const uint8_t* status, int64_t init, int64_t* eqn,
+                    int64_t* n_numbered);
+
+/* ---- mesh + fields on the device (base::Unstructured, base::Field, asmb::FieldBinder) ------------------ */
+/* base::Unstructured<SHAPE,GEOMDEG,DIM> (base/Unstructured.hpp:57-65): coords[n_nodes*dim], conn[n_elems*npe] */
+int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes, const double* coords,
+                 int64_t n_elems, const int32_t* conn);
+/* only the nodal coordinates change (moving mesh); pattern and maps stay valid */
+int isl_mesh_update_coords(isl_handle h, const double* coords);
+/* base::Field<FEBasis,DOFSIZE> (base/Field.hpp:50-55) flattened: per DoF component eqn / status / prescribed
+ * value (dof::Constraint rhs, base/dof/Constraint.hpp) / current value                                      */
+int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_obj, const int32_t* elem_dof,
+                  const int64_t* eqn, const uint8_t* status, const double* prescribed, const double* values);
+/* new Newton state / new Dirichlet values, numbering unchanged (either pointer may be NULL) */
+int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values);
+
+/* ---- solver hand-off (base::solver::Eigen3) ------------------------------------------------------------- */
+/* Solver solver(n) (base/solver/Eigen3.hpp:71-77): fresh system, zero rhs, no matrix entries.  The sparsity
+ * pattern and element->slot maps of previously registered field pairs stay cached on the device.          */
+int isl_system_create(isl_handle h, int64_t n_eqn);
+/* solver.registerFields<FTB>(fieldBinder) (Eigen3.hpp:332-336, TripletContainer.hpp:158-301): unions the
+ * (test,trial) block pattern into the system CSR                                                            */
+int isl_pattern_register(isl_handle h, int test_field, int trial_field);
+/* asmb::stiffnessMatrixComputation<FTB>(quad, solver, binder, kernelObj, incremental)
+ * (base/asmb/StiffnessMatrix.hpp:49-87): K scattered into CSR, Dirichlet lift into rhs                      */
+int isl_assemble_matrix(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,
+                        int trial_field, int incremental);
+/* asmb::computeResidualForces<FTB>(quad, solver, binder, kernelObj) (base/asmb/ForceIntegrator.hpp:37-71):
+ * rhs += factor * f_e with factor = -1 in the reference                                                     */
+int isl_assemble_residual(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,
+                          int trial_field, double factor);
+/* asmb::bodyForceComputation<FTB>(quad, solver, binder, f) with constant f[dof_size]
+ * (base/asmb/BodyForce.hpp:65-84,172-205)                                                                   */
+int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int test_field);
+/* solver.insertToLHS / insertToRHS (Eigen3.hpp:81-124) for host-side odd contributions:
+ * mat is row-major [n_rows*n_cols]; entries must exist in the registered pattern                            */
+int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols,
+                   int n_cols);
+int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_rows);
+/* solver.finishAssembly() (Eigen3.hpp:142-153): waits for the device, reports sizes                          */
+int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz);
+/* canonical CSR (rows ascending, columns ascending, explicit zeros kept) + rhs; NULL pointers are skipped   */
+int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs);
+/* zero-copy hand-off to a device solver: device pointers valid until the next create/register call         */
+int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs);
+/* solver.getValue(i), solver.norm() (Eigen3.hpp:293-296,128-138; norm = ||b||_2 / n, quirk kept)            */
+int isl_rhs_value(isl_handle h, int64_t index, double* value);
+int isl_rhs_norm(isl_handle h, double* norm);
+
+/* ---- multi-GPU interface exchange helpers (element blocks per GPU, owned row ranges) -------------------- */
+/* gather val[idx[k]] (or rhs when which = 1) into a packed device buffer / scatter-add a packed buffer      */
+int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev);
+int isl_unpack_add_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, const double* in_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSILICO_B200_H */

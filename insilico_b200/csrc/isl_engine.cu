@@ -1,0 +1,1261 @@
+// =============================================================================
+// isl_engine.cu -- B200 (sm_100a) element-assembly engine behind the C ABI of
+// include/insilico_b200.h.
+//
+// Data layout in HBM (all flat, SoA):
+//   coords  f64 [n_nodes][dim]        conn     i32 [n_elems][npe]
+//   per field: elem_dof i32 [n_elems][ndpe], eqn i32 [n_obj][ds] (-1 = not ACTIVE),
+//              status u8, prescribed f64, values f64 [n_obj][ds]
+//   system: rowptr i64 [n+1], col i32 [nnz] (ascending per row), val f64 [nnz], rhs f64 [n]
+//   per (test,trial) pair: slot i32 [n_elems][nr][nc] = position of local entry (i,j) in val
+//              (-1 when the row or the column is not ACTIVE)
+//
+// Kernels (FP64 CUDA cores; the per-element products are tiny, tensor cores do not apply):
+//   k_tangent<DIM>   generic cooperative element kernel: coordinates, Jacobians and physical shape-function
+//                    gradients staged in shared memory per element batch, then one thread per local
+//                    matrix entry reduces over quadrature points and scatter-adds through the slot map
+//                    (RED.ADD.F64); CONSTRAINED columns are lifted into rhs.
+//   k_force<DIM>     residual forces / body force with the same staging.
+//   k_q1hex_laplace  specialised hot path for Q1 hex scalar Laplace (BASELINE config 2), one thread per
+//                    element with the 8x8 symmetric local matrix in registers.
+//   pattern build    (row,col) 64-bit keys -> cub radix sort -> unique -> CSR; slot map by binary search.
+// =============================================================================
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include "../../include/insilico_b200.h"
+#include "isl_dof.hpp"
+#include "isl_tables.hpp"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct IslError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define ISL_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw IslError(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                           std::to_string(__LINE__));                                                    \
+    } while (0)
+
+#define ISL_REQUIRE(cond, msg) \
+    do { if (!(cond)) throw IslError(std::string(msg)); } while (0)
+
+template <class F>
+int guarded(F&& f) {
+    try { f(); return 0; }
+    catch (const std::exception& e) { g_error = e.what(); return 1; }
+    catch (...) { g_error = "unknown error"; return 1; }
+}
+
+// simple owning device buffer
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        if (count == n && p) return;
+        release();
+        if (count) ISL_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void swap(DevBuf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device-side parameter blocks
+struct AsmParams {
+    // mesh
+    const double* coords; const int32_t* conn; int64_t n_elems; int npe;
+    // tables
+    const double* w; const double* dNg; const double* Ng;
+    const double* Nt; const double* dNt; const double* Nc; const double* dNc;
+    int nq, nt, nc, dst, dsc, bubnov;
+    // fields
+    const int32_t* ed_t; const int32_t* ed_c;
+    const int32_t* eqn_t; const int32_t* eqn_c;
+    const uint8_t* st_c; const double* presc_c; const double* val_c;
+    // system
+    const int32_t* slot; double* val; double* rhs;
+    int kernel_id; double p0, p1; int incremental; double factor;
+    int EB; int need_gt, need_gc, nqdata;
+    int body; double f[3];
+};
+
+__device__ __forceinline__ int voigt_idx(int i, int j) {
+    // mat/TensorAlgebra.hpp:149-164
+    const int map[9] = {0, 3, 4, 1, -1, 5, -1, -1, 2};
+    return map[(i + 1) * (j + 1) - 1];
+}
+
+__device__ __forceinline__ double inv3(const double m[3][3], double inv[3][3]) {
+    const double c00 = m[1][1] * m[2][2] - m[1][2] * m[2][1];
+    const double c10 = m[2][1] * m[0][2] - m[2][2] * m[0][1];
+    const double c20 = m[0][1] * m[1][2] - m[0][2] * m[1][1];
+    const double det = c00 * m[0][0] + (c10 * m[1][0] + c20 * m[2][0]);
+    const double id = 1.0 / det;
+    inv[0][0] = c00 * id; inv[0][1] = c10 * id; inv[0][2] = c20 * id;
+    inv[1][0] = (m[1][2] * m[2][0] - m[1][0] * m[2][2]) * id;
+    inv[1][1] = (m[2][2] * m[0][0] - m[2][0] * m[0][2]) * id;
+    inv[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) * id;
+    inv[2][0] = (m[1][0] * m[2][1] - m[1][1] * m[2][0]) * id;
+    inv[2][1] = (m[2][0] * m[0][1] - m[2][1] * m[0][0]) * id;
+    inv[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) * id;
+    return det;
+}
+
+// material response at a quadrature point: S (2nd PK) and C (6x6 Voigt)
+// mat/hypel/StVenant.hpp:77-114, mat/hypel/NeoHookeanCompressible.hpp:77-172
+__device__ void material_eval(int kid, double lambda, double mu, const double F[3][3], double S[3][3], double C[6][6],
+                              bool want_C) {
+    double CG[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) CG[i][j] = F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j];
+    if (kid == ISL_K_HYPEL_STVENANT) {
+        double E[3][3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) E[i][j] = 0.5 * (CG[i][j] - (i == j ? 1. : 0.));
+        const double trE = E[0][0] + E[1][1] + E[2][2];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) S[i][j] = lambda * trE * (i == j ? 1. : 0.) + 2. * mu * E[i][j];
+        if (want_C) {
+            for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) C[i][j] = 0.;
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[i][j] = lambda;
+            for (int i = 0; i < 3; i++) C[i][i] += 2. * mu;
+            for (int i = 3; i < 6; i++) C[i][i] += mu;
+        }
+    } else {
+        double Ci[3][3];
+        inv3(CG, Ci);
+        const double J = F[0][0] * F[1][1] * F[2][2] + F[0][1] * F[1][2] * F[2][0] + F[0][2] * F[1][0] * F[2][1] -
+                         F[0][0] * F[1][2] * F[2][1] - F[0][1] * F[1][0] * F[2][2] - F[0][2] * F[1][1] * F[2][0];
+        const double logJ = log(J);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) S[i][j] = (lambda * logJ - mu) * Ci[i][j] + mu * (i == j ? 1. : 0.);
+        if (want_C) {
+            const double fac2 = mu - lambda * logJ;
+            for (int A = 0; A < 3; A++)
+                for (int B = A; B < 3; B++)
+                    for (int Cc = 0; Cc < 3; Cc++)
+                        for (int D = Cc; D < 3; D++)
+                            C[voigt_idx(A, B)][voigt_idx(Cc, D)] =
+                                lambda * Ci[A][B] * Ci[Cc][D] + fac2 * (Ci[A][Cc] * Ci[B][D] + Ci[A][D] * Ci[B][Cc]);
+        }
+    }
+}
+
+// shared-memory staging common to tangent and force kernels.  Layout (doubles):
+//   sX [EB][npe][DIM] | sCon [EB][nq][DIM*DIM] | sDet [EB][nq] | sGt [EB][nq][nt][DIM] | sGc [...] | sQ [EB][nq][nqdata]
+template <int DIM>
+struct Stage {
+    double *sX, *sCon, *sDet, *sGt, *sGc, *sQ;
+    __device__ Stage(double* base, const AsmParams& p) {
+        sX = base; base += (size_t)p.EB * p.npe * DIM;
+        sCon = base; base += (size_t)p.EB * p.nq * DIM * DIM;
+        sDet = base; base += (size_t)p.EB * p.nq;
+        sGt = base; if (p.need_gt) base += (size_t)p.EB * p.nq * p.nt * DIM;
+        if (p.need_gc && !(p.bubnov && p.need_gt)) { sGc = base; base += (size_t)p.EB * p.nq * p.nc * DIM; }
+        else sGc = sGt;
+        sQ = base;
+    }
+};
+
+// geometry + gradients of one element batch:
+//   J(i,a) = sum_n x_n[i] dphi_n/dxi_a ; contra = J^{-T} ; grad_x phi = contra * grad_xi phi
+template <int DIM>
+__device__ void stage_batch(const AsmParams& p, const Stage<DIM>& s, int64_t base, int nb) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int t = tid; t < nb * p.npe * DIM; t += nth) {
+        const int eb = t / (p.npe * DIM), r = t % (p.npe * DIM);
+        const int a = r / DIM, d = r % DIM;
+        s.sX[t] = p.coords[(size_t)p.conn[(base + eb) * p.npe + a] * DIM + d];
+    }
+    __syncthreads();
+    for (int t = tid; t < nb * p.nq; t += nth) {
+        const int eb = t / p.nq, q = t % p.nq;
+        const double* X = s.sX + (size_t)eb * p.npe * DIM;
+        const double* dN = p.dNg + (size_t)q * p.npe * DIM;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int n = 0; n < p.npe; n++)
+            for (int i = 0; i < DIM; i++)
+                for (int a = 0; a < DIM; a++) J[i][a] += X[n * DIM + i] * dN[n * DIM + a];
+        double* con = s.sCon + (size_t)t * DIM * DIM;
+        double det;
+        if (DIM == 3) {
+            double aux[3][3], inv[3][3];
+            for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) aux[i][a] = J[a][i];
+            det = inv3(aux, inv);
+            for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) con[i * 3 + a] = inv[i][a];
+        } else {
+            // aux = J^T ; 2x2 inverse
+            const double a00 = J[0][0], a01 = J[1][0], a10 = J[0][1], a11 = J[1][1];
+            det = a00 * a11 - a10 * a01;
+            const double id = 1.0 / det;
+            con[0] = a11 * id; con[2] = -a10 * id; con[1] = -a01 * id; con[3] = a00 * id;
+        }
+        s.sDet[t] = det;
+    }
+    __syncthreads();
+    if (p.need_gt)
+        for (int t = tid; t < nb * p.nq * p.nt; t += nth) {
+            const int eq = t / p.nt, a = t % p.nt, q = eq % p.nq;
+            const double* con = s.sCon + (size_t)eq * DIM * DIM;
+            const double* dN = p.dNt + ((size_t)q * p.nt + a) * DIM;
+            for (int r = 0; r < DIM; r++) {
+                double v = con[r * DIM] * dN[0];
+                for (int c = 1; c < DIM; c++) v += con[r * DIM + c] * dN[c];
+                s.sGt[(size_t)t * DIM + r] = v;
+            }
+        }
+    if (p.need_gc && !(p.bubnov && p.need_gt))
+        for (int t = tid; t < nb * p.nq * p.nc; t += nth) {
+            const int eq = t / p.nc, a = t % p.nc, q = eq % p.nq;
+            const double* con = s.sCon + (size_t)eq * DIM * DIM;
+            const double* dN = p.dNc + ((size_t)q * p.nc + a) * DIM;
+            for (int r = 0; r < DIM; r++) {
+                double v = con[r * DIM] * dN[0];
+                for (int c = 1; c < DIM; c++) v += con[r * DIM + c] * dN[c];
+                s.sGc[(size_t)t * DIM + r] = v;
+            }
+        }
+    __syncthreads();
+}
+
+// displacement / velocity gradient of the trial field at (eb,q): GradU(J,i) = sum_f g_f[J] u_f[i]
+template <int DIM>
+__device__ void trial_gradient(const AsmParams& p, const Stage<DIM>& s, int64_t e, int eq, double GradU[3][3]) {
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) GradU[a][b] = 0.;
+    const double* g = s.sGc + (size_t)eq * p.nc * DIM;
+    for (int f = 0; f < p.nc; f++) {
+        const int32_t obj = p.ed_c[e * p.nc + f];
+        for (int J = 0; J < DIM; J++)
+            for (int i = 0; i < p.dsc; i++) GradU[J][i] += g[f * DIM + J] * p.val_c[(size_t)obj * p.dsc + i];
+    }
+}
+
+template <int DIM>
+__device__ void deformation_gradient(const AsmParams& p, const Stage<DIM>& s, int64_t e, int eq, double F[3][3]) {
+    double GradU[3][3];
+    trial_gradient<DIM>(p, s, e, eq, GradU);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = (i == j ? 1. : 0.);
+    for (int i = 0; i < p.dsc; i++) for (int J = 0; J < DIM; J++) F[i][J] += GradU[J][i];
+}
+
+// scatter one local matrix entry: ACTIVE x ACTIVE -> CSR value,
+// ACTIVE row x CONSTRAINED column -> rhs -= g * K
+__device__ __forceinline__ void scatter_entry(const AsmParams& p, int64_t e, int i, int j, int nr, int ncl, double v) {
+    const int32_t sl = p.slot[((size_t)e * nr + i) * ncl + j];
+    if (sl >= 0) { atomicAdd(p.val + sl, v); return; }
+    const int M = i / p.dst, ci = i % p.dst;
+    const int32_t r = p.eqn_t[(size_t)p.ed_t[e * p.nt + M] * p.dst + ci];
+    if (r < 0) return;
+    const int N = j / p.dsc, cj = j % p.dsc;
+    const size_t k = (size_t)p.ed_c[e * p.nc + N] * p.dsc + cj;
+    if (p.st_c[k] == ISL_CONSTRAINED) {
+        const double g = p.incremental ? p.presc_c[k] - p.val_c[k] : p.presc_c[k];
+        atomicAdd(p.rhs + r, -(g * v));
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
+    extern __shared__ double smem[];
+    const Stage<DIM> s(smem, p);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nr = p.nt * p.dst, ncl = p.nc * p.dsc;
+    for (int64_t base = (int64_t)blockIdx.x * p.EB; base < p.n_elems; base += (int64_t)gridDim.x * p.EB) {
+        const int nb = (int)min((int64_t)p.EB, p.n_elems - base);
+        stage_batch<DIM>(p, s, base, nb);
+        if (p.kernel_id == ISL_K_HYPEL_STVENANT || p.kernel_id == ISL_K_HYPEL_NEOHOOKE) {
+            // effective elasticity per quadrature point, hoisted out of the (M,N) loops
+            // (solid/HyperElastic.hpp:282-310 evaluates it per entry)
+            for (int t = tid; t < nb * p.nq; t += nth) {
+                const int eb = t / p.nq;
+                double F[3][3], S[3][3], C[6][6];
+                deformation_gradient<DIM>(p, s, base + eb, t, F);
+                material_eval(p.kernel_id, p.p0, p.p1, F, S, C, true);
+                double* ce = s.sQ + (size_t)t * 81;
+                for (int i = 0; i < DIM; i++)
+                    for (int J = 0; J < DIM; J++)
+                        for (int k = 0; k < DIM; k++)
+                            for (int L = 0; L < DIM; L++) {
+                                double r = (i == k ? S[J][L] : 0.);
+                                for (int A = 0; A < DIM; A++)
+                                    for (int B = 0; B < DIM; B++)
+                                        r += F[i][A] * C[voigt_idx(A, J)][voigt_idx(B, L)] * F[k][B];
+                                ce[((i * 3 + J) * 3 + k) * 3 + L] = r;
+                            }
+            }
+            __syncthreads();
+            for (int t = tid; t < nb * nr * ncl; t += nth) {
+                const int eb = t / (nr * ncl), ij = t % (nr * ncl), i = ij / ncl, j = ij % ncl;
+                const int M = i / DIM, ci = i % DIM, N = j / DIM, ck = j % DIM;
+                double acc = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
+                    const double* gN = s.sGc + ((size_t)eq * p.nc + N) * DIM;
+                    const double* ce = s.sQ + (size_t)eq * 81 + (ci * 3) * 9 + ck * 3;
+                    double sum = 0.;
+                    for (int J = 0; J < DIM; J++)
+                        for (int L = 0; L < DIM; L++) sum += gM[J] * ce[J * 9 + L] * gN[L];
+                    acc += sum * (s.sDet[eq] * p.w[q]);
+                }
+                scatter_entry(p, base + eb, i, j, nr, ncl, acc);
+            }
+        } else if (p.kernel_id == ISL_K_LAPLACE || p.kernel_id == ISL_K_VECTOR_LAPLACE) {
+            for (int t = tid; t < nb * p.nt * p.nc; t += nth) {
+                const int eb = t / (p.nt * p.nc), mn = t % (p.nt * p.nc), M = mn / p.nc, N = mn % p.nc;
+                double acc = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
+                    const double* gN = s.sGc + ((size_t)eq * p.nc + N) * DIM;
+                    double dot = gM[0] * gN[0];
+                    for (int k = 1; k < DIM; k++) dot += gM[k] * gN[k];
+                    acc += dot * (p.p0 * s.sDet[eq] * p.w[q]);
+                }
+                for (int c = 0; c < p.dsc; c++) scatter_entry(p, base + eb, M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+            }
+        } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
+            // B(M d + i, N) = -detJ w g_M[i] psi_N
+            for (int t = tid; t < nb * nr * ncl; t += nth) {
+                const int eb = t / (nr * ncl), ij = t % (nr * ncl), i = ij / ncl, N = ij % ncl;
+                const int M = i / p.dst, d = i % p.dst;
+                double acc = 0.;
+                if (d < DIM)
+                    for (int q = 0; q < p.nq; q++) {
+                        const int eq = eb * p.nq + q;
+                        acc += -s.sDet[eq] * p.w[q] * s.sGt[((size_t)eq * p.nt + M) * DIM + d] * p.Nc[q * p.nc + N];
+                    }
+                scatter_entry(p, base + eb, i, N, nr, ncl, acc);
+            }
+        } else if (p.kernel_id == ISL_K_VELOCITY_DIVERGENCE) {
+            // transpose of the pressure-gradient block on the transposed tuple, optional sign change
+            const double sgn = (p.p0 != 0.) ? -1.0 : 1.0;
+            for (int t = tid; t < nb * nr * ncl; t += nth) {
+                const int eb = t / (nr * ncl), ij = t % (nr * ncl), Mp = ij / ncl, j = ij % ncl;
+                const int N = j / p.dsc, d = j % p.dsc;
+                double acc = 0.;
+                if (d < DIM)
+                    for (int q = 0; q < p.nq; q++) {
+                        const int eq = eb * p.nq + q;
+                        acc += -s.sDet[eq] * p.w[q] * s.sGc[((size_t)eq * p.nc + N) * DIM + d] * p.Nt[q * p.nt + Mp];
+                    }
+                scatter_entry(p, base + eb, Mp, j, nr, ncl, sgn * acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// residual forces and body force
+template <int DIM>
+__global__ void __launch_bounds__(256) k_force(const AsmParams p) {
+    extern __shared__ double smem[];
+    const Stage<DIM> s(smem, p);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nr = p.nt * p.dst;
+    for (int64_t base = (int64_t)blockIdx.x * p.EB; base < p.n_elems; base += (int64_t)gridDim.x * p.EB) {
+        const int nb = (int)min((int64_t)p.EB, p.n_elems - base);
+        stage_batch<DIM>(p, s, base, nb);
+        if (!p.body) {
+            for (int t = tid; t < nb * p.nq; t += nth) {
+                const int eb = t / p.nq, q = t % p.nq;
+                const int64_t e = base + eb;
+                double* qd = s.sQ + (size_t)t * 9;
+                if (p.kernel_id == ISL_K_HYPEL_STVENANT || p.kernel_id == ISL_K_HYPEL_NEOHOOKE) {
+                    double F[3][3], S[3][3], C[6][6];
+                    deformation_gradient<DIM>(p, s, e, t, F);
+                    material_eval(p.kernel_id, p.p0, p.p1, F, S, C, false);
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++) qd[i * 3 + j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
+                } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
+                    double pr = 0.;
+                    for (int f = 0; f < p.nc; f++) pr += p.Nc[q * p.nc + f] * p.val_c[(size_t)p.ed_c[e * p.nc + f] * p.dsc];
+                    qd[0] = pr;
+                } else {
+                    double G[3][3];
+                    trial_gradient<DIM>(p, s, e, t, G);
+                    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) qd[a * 3 + b] = G[a][b];
+                }
+            }
+            __syncthreads();
+        }
+        for (int t = tid; t < nb * nr; t += nth) {
+            const int eb = t / nr, i = t % nr, M = i / p.dst, ci = i % p.dst;
+            const int64_t e = base + eb;
+            double acc = 0.;
+            for (int q = 0; q < p.nq; q++) {
+                const int eq = eb * p.nq + q;
+                const double detJ = s.sDet[eq], w = p.w[q];
+                const double* qd = s.sQ + (size_t)eq * 9;
+                if (p.body) {
+                    acc += p.f[ci] * p.Nt[q * p.nt + M] * w * detJ;
+                    continue;
+                }
+                const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
+                switch (p.kernel_id) {
+                    case ISL_K_LAPLACE: {  // heat/Laplace.hpp:153-181
+                        double dot = (p.p0 * qd[0]) * gM[0];
+                        for (int d = 1; d < DIM; d++) dot += (p.p0 * qd[d * 3]) * gM[d];
+                        acc += dot * detJ * w;
+                    } break;
+                    case ISL_K_VECTOR_LAPLACE: {  // fluid/VectorLaplace.hpp:78-106
+                        double dot = 0.;
+                        for (int k = 0; k < DIM; k++) dot += qd[k * 3 + ci] * gM[k];
+                        acc += p.p0 * dot * detJ * w;
+                    } break;
+                    case ISL_K_HYPEL_STVENANT:
+                    case ISL_K_HYPEL_NEOHOOKE: {  // solid/HyperElastic.hpp:209-257
+                        double sum = 0.;
+                        for (int J = 0; J < DIM; J++) sum += qd[ci * 3 + J] * gM[J];
+                        acc += sum * (detJ * w);
+                    } break;
+                    case ISL_K_PRESSURE_GRADIENT:  // fluid/PressureGradient.hpp:130-155
+                        if (ci < DIM) acc += -gM[ci] * qd[0] * detJ * w;
+                        break;
+                    case ISL_K_VELOCITY_DIVERGENCE: {  // fluid/VelocityDivergence.hpp:100-124
+                        double div = 0.;
+                        for (int d = 0; d < DIM; d++) div += qd[d * 3 + d];
+                        acc += ((p.p0 != 0.) ? -1.0 : 1.0) * p.Nt[q * p.nt + M] * div * detJ * w;
+                    } break;
+                }
+            }
+            const int32_t r = p.eqn_t[(size_t)p.ed_t[e * p.nt + M] * p.dst + ci];
+            if (r >= 0) atomicAdd(p.rhs + r, p.factor * acc);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// specialised hot path: Q1 hex geometry, Q1 scalar field, Laplace, 2x2x2 Gauss rule (BASELINE config 2).
+// One thread per element; symmetric 8x8 local matrix (36 accumulators) in registers; scatter through the
+// slot map with RED.ADD.F64; Dirichlet lift fused.  Tables live in constant memory.
+__constant__ double c_q1_dN[8 * 8 * 3];  // [q][a][d] reference gradients at the 8 Gauss points
+__constant__ double c_q1_w[8];
+
+struct Q1Params {
+    const double* coords; const int32_t* conn; int64_t n_elems;
+    const int32_t* slot;                                  // [n_elems][8][8]
+    const int32_t* eqn; const uint8_t* status; const double* presc; const double* values;  // per node (ds = 1)
+    double* val; double* rhs; double factor; int incremental;
+};
+
+__global__ void __launch_bounds__(128) k_q1hex_laplace(const Q1Params p) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n_elems) return;
+    int32_t node[8];
+    {
+        const int4* c4 = reinterpret_cast<const int4*>(p.conn + e * 8);
+        const int4 a = __ldg(c4), b = __ldg(c4 + 1);
+        node[0] = a.x; node[1] = a.y; node[2] = a.z; node[3] = a.w;
+        node[4] = b.x; node[5] = b.y; node[6] = b.z; node[7] = b.w;
+    }
+    double X[8][3];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const double* c = p.coords + (size_t)node[a] * 3;
+        X[a][0] = __ldg(c); X[a][1] = __ldg(c + 1); X[a][2] = __ldg(c + 2);
+    }
+    double K[36];
+#pragma unroll
+    for (int k = 0; k < 36; k++) K[k] = 0.;
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        const double* dN = c_q1_dN + q * 24;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int al = 0; al < 3; al++) J[i][al] = fma(X[a][i], dN[a * 3 + al], J[i][al]);
+        // contra = (J^T)^{-1}: contra[r][c] = cof(J)[r][c] / det
+        double co[3][3];
+        co[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        co[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        co[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        co[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+        co[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+        co[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+        co[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+        co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
+        const double id = 1.0 / det;
+        const double scal = p.factor * det * c_q1_w[q];
+        double g[8][3];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                g[a][r] = (co[r][0] * dN[a * 3] + co[r][1] * dN[a * 3 + 1] + co[r][2] * dN[a * 3 + 2]) * id;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const double h0 = g[a][0] * scal, h1 = g[a][1] * scal, h2 = g[a][2] * scal;
+#pragma unroll
+            for (int b = a; b < 8; b++, k++) K[k] = fma(h0, g[b][0], fma(h1, g[b][1], fma(h2, g[b][2], K[k])));
+        }
+    }
+    // scatter
+    const int32_t* sl = p.slot + e * 64;
+    int32_t rows[8]; double gval[8]; bool cons[8]; bool any_cons = false;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        rows[a] = __ldg(p.eqn + node[a]);
+        cons[a] = __ldg(p.status + node[a]) == ISL_CONSTRAINED;
+        any_cons |= cons[a];
+        gval[a] = 0.;
+    }
+    if (any_cons) {
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (cons[a]) gval[a] = p.incremental ? p.presc[node[a]] - p.values[node[a]] : p.presc[node[a]];
+    }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        const int4 s0 = __ldg(reinterpret_cast<const int4*>(sl + a * 8));
+        const int4 s1 = __ldg(reinterpret_cast<const int4*>(sl + a * 8 + 4));
+        const int32_t srow[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        double lift = 0.;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            // symmetric storage index of (min,max)
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            const int idx = lo * 8 - (lo * (lo - 1)) / 2 + (hi - lo);
+            const double v = K[idx];
+            if (srow[b] >= 0) atomicAdd(p.val + srow[b], v);
+            else if (cons[b]) lift += gval[b] * v;
+        }
+        if (any_cons && rows[a] >= 0 && lift != 0.) atomicAdd(p.rhs + rows[a], -lift);
+    }
+    (void)k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pattern build kernels
+__global__ void k_elem_eqn(const int32_t* ed, const int32_t* eqn, int64_t n_elems, int ndpe, int ds, int32_t* out) {
+    const int64_t n = n_elems * ndpe * ds;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ef = t / ds; const int c = (int)(t % ds);
+        out[t] = eqn[(size_t)ed[ef] * ds + c];
+    }
+}
+__global__ void k_make_keys(const int32_t* er, const int32_t* ec, int64_t n_elems, int nr, int ncl, uint64_t* keys) {
+    const int64_t n = n_elems * nr * ncl;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / (nr * ncl); const int ij = (int)(t % (nr * ncl));
+        const int32_t r = er[e * nr + ij / ncl], c = ec[e * ncl + ij % ncl];
+        keys[t] = (r < 0 || c < 0) ? ~0ull : (((uint64_t)(uint32_t)r << 32) | (uint32_t)c);
+    }
+}
+__global__ void k_csr_keys(const int64_t* rowptr, const int32_t* col, int64_t n, uint64_t* keys) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) keys[k] = ((uint64_t)r << 32) | (uint32_t)col[k];
+}
+__global__ void k_rowptr_from_keys(const uint64_t* keys, int64_t nnz, int64_t n, int64_t* rowptr) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t target = (uint64_t)r << 32;
+        int64_t lo = 0, hi = nnz;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+        rowptr[r] = lo;
+    }
+}
+__global__ void k_cols_from_keys(const uint64_t* keys, int64_t nnz, int32_t* col) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+        col[k] = (int32_t)(keys[k] & 0xffffffffu);
+}
+__device__ __forceinline__ int64_t find_in_row(const int64_t* rowptr, const int32_t* col, int32_t r, int32_t c) {
+    int64_t lo = rowptr[r], hi = rowptr[r + 1];
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (col[mid] < c) lo = mid + 1; else hi = mid; }
+    return (lo < rowptr[r + 1] && col[lo] == c) ? lo : -1;
+}
+__global__ void k_slotmap(const int32_t* er, const int32_t* ec, int64_t n_elems, int nr, int ncl, const int64_t* rowptr,
+                          const int32_t* col, int32_t* slot) {
+    const int64_t n = n_elems * nr * ncl;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / (nr * ncl); const int ij = (int)(t % (nr * ncl));
+        const int32_t r = er[e * nr + ij / ncl], c = ec[e * ncl + ij % ncl];
+        slot[t] = (r < 0 || c < 0) ? -1 : (int32_t)find_in_row(rowptr, col, r, c);
+    }
+}
+__global__ void k_remap_values(const int64_t* old_rowptr, const int32_t* old_col, const double* old_val, int64_t n,
+                               const int64_t* rowptr, const int32_t* col, double* val) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t k = old_rowptr[r]; k < old_rowptr[r + 1]; k++) {
+            const int64_t pos = find_in_row(rowptr, col, (int32_t)r, old_col[k]);
+            if (pos >= 0) val[pos] = old_val[k];
+        }
+}
+__global__ void k_insert_lhs(const double* mat, const int64_t* rows, int nr, const int64_t* cols, int ncl,
+                             const int64_t* rowptr, const int32_t* col, double* val, int* err) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nr * ncl) return;
+    const int64_t pos = find_in_row(rowptr, col, (int32_t)rows[t / ncl], (int32_t)cols[t % ncl]);
+    if (pos < 0) { *err = 1; return; }
+    atomicAdd(val + pos, mat[t]);
+}
+__global__ void k_insert_rhs(const double* vec, const int64_t* rows, int nr, double* rhs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nr) atomicAdd(rhs + rows[t], vec[t]);
+}
+__global__ void k_count_diff(const int32_t* a, const int32_t* b, int64_t n, int* ndiff) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (a[i] != b[i]) atomicAdd(ndiff, 1);
+}
+__global__ void k_sumsq(const double* x, int64_t n, double* out) {
+    double acc = 0.;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += x[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+__global__ void k_pack(const double* src, const int64_t* idx, int64_t n, double* out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
+}
+__global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const double* in) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(dst + idx[i], in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct FieldDev {
+    bool set = false;
+    bool dof_is_node = false;  // elem_dof identical to the mesh connectivity (isoparametric copy)
+    int deg = 0, ds = 0, ndpe = 0; int64_t n_obj = 0;
+    DevBuf<int32_t> elem_dof, eqn; DevBuf<uint8_t> status; DevBuf<double> presc, values;
+    DevBuf<int32_t> elem_eqn;  // [n_elems][ndpe*ds]
+    void reset() {
+        set = false; dof_is_node = false; deg = ds = ndpe = 0; n_obj = 0;
+        elem_dof.release(); eqn.release(); status.release(); presc.release(); values.release(); elem_eqn.release();
+    }
+};
+
+struct TableDev {
+    int nq = 0;
+    DevBuf<double> w, dNg, Ng, Nt, dNt, Nc, dNc;
+};
+
+}  // namespace
+
+struct isl_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n_sm = 148;
+    int64_t launches = 0;
+    // mesh
+    int shape = 0, geom_deg = 0, dim = 0, npe = 0; int64_t n_nodes = 0, n_elems = 0;
+    DevBuf<double> coords; DevBuf<int32_t> conn;
+    FieldDev fields[5];
+    // system
+    int64_t n_eqn = -1, nnz = 0;
+    DevBuf<int64_t> rowptr; DevBuf<int32_t> col; DevBuf<double> val, rhs;
+    std::set<std::pair<int, int>> pattern_pairs, sys_pairs;
+    std::map<std::pair<int, int>, std::unique_ptr<DevBuf<int32_t>>> slotmaps;
+    std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
+    bool q1_tables_loaded = false;
+    DevBuf<double> scratch_d; DevBuf<int> scratch_i;
+
+    int grid_for(int64_t n, int block) const {
+        const int64_t g = (n + block - 1) / block;
+        return (int)std::max<int64_t>(1, std::min<int64_t>(g, (int64_t)n_sm * 32));
+    }
+};
+
+namespace {
+
+#define ISL_LAUNCH(eng, kernel, grid, block, smem, ...)                       \
+    do {                                                                      \
+        kernel<<<(grid), (block), (smem), (eng)->stream>>>(__VA_ARGS__);      \
+        (eng)->launches++;                                                    \
+        ISL_CUDA(cudaGetLastError());                                         \
+    } while (0)
+
+template <class T>
+void upload(isl_engine* h, DevBuf<T>& dst, const T* src, size_t n) {
+    dst.alloc(n);
+    if (n) ISL_CUDA(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyDefault, h->stream));
+}
+template <class T>
+void upload_vec(isl_engine* h, DevBuf<T>& dst, const std::vector<T>& v) {
+    dst.alloc(v.size());
+    if (!v.empty()) {
+        ISL_CUDA(cudaMemcpyAsync(dst.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));  // v may be a temporary
+    }
+}
+
+void invalidate_pattern(isl_engine* h) {
+    h->pattern_pairs.clear();
+    h->slotmaps.clear();
+    h->nnz = 0;
+    h->rowptr.release(); h->col.release(); h->val.release();
+}
+
+void build_elem_eqn(isl_engine* h, FieldDev& f) {
+    if (f.elem_eqn.p) return;
+    const int64_t n = h->n_elems * f.ndpe * f.ds;
+    f.elem_eqn.alloc(n);
+    ISL_LAUNCH(h, k_elem_eqn, h->grid_for(n, 256), 256, 0, f.elem_dof.p, f.eqn.p, h->n_elems, f.ndpe, f.ds, f.elem_eqn.p);
+}
+
+// rebuild CSR for `pairs`; existing values are carried over into the new layout
+void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
+    ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+    ISL_REQUIRE(h->n_eqn < (int64_t)1 << 31, "more than 2^31 equations are not supported");
+    int64_t total = 0;
+    for (auto& pr : pairs) {
+        FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
+        ISL_REQUIRE(t.set && c.set, "pattern registration on a field that was not set");
+        total += h->n_elems * (int64_t)(t.ndpe * t.ds) * (c.ndpe * c.ds);
+    }
+    DevBuf<uint64_t> keys, keys2;
+    keys.alloc(total + 1);
+    int64_t off = 0;
+    for (auto& pr : pairs) {
+        FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
+        build_elem_eqn(h, t); build_elem_eqn(h, c);
+        const int nr = t.ndpe * t.ds, ncl = c.ndpe * c.ds;
+        const int64_t n = h->n_elems * nr * ncl;
+        ISL_LAUNCH(h, k_make_keys, h->grid_for(n, 256), 256, 0, t.elem_eqn.p, c.elem_eqn.p, h->n_elems, nr, ncl, keys.p + off);
+        off += n;
+    }
+    // sentinel so that the invalid key always exists exactly as the last unique key
+    const uint64_t inval = ~0ull;
+    ISL_CUDA(cudaMemcpyAsync(keys.p + total, &inval, sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    total += 1;
+    keys2.alloc(total);
+    // the invalid key has all bits set: sort on the full 64 bits so it stays last
+    size_t tmp_bytes = 0;
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys.p, keys2.p, total, 0, 64, h->stream));
+    DevBuf<char> tmp; tmp.alloc(tmp_bytes);
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, keys.p, keys2.p, total, 0, 64, h->stream));
+    h->launches += 8;
+    DevBuf<int64_t> nsel; nsel.alloc(1);
+    size_t tmp2 = 0;
+    ISL_CUDA(cub::DeviceSelect::Unique(nullptr, tmp2, keys2.p, keys.p, nsel.p, total, h->stream));
+    if (tmp2 > tmp.n) tmp.alloc(tmp2);
+    ISL_CUDA(cub::DeviceSelect::Unique(tmp.p, tmp2, keys2.p, keys.p, nsel.p, total, h->stream));
+    h->launches += 2;
+    int64_t nuniq = 0;
+    ISL_CUDA(cudaMemcpyAsync(&nuniq, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t nnz = nuniq - 1;  // drop the invalid key
+    ISL_REQUIRE(nnz < (int64_t)1 << 31, "more than 2^31 non-zeros need 64-bit slots (not supported yet)");
+    keys2.release(); tmp.release();
+
+    DevBuf<int64_t> rowptr; DevBuf<int32_t> col; DevBuf<double> val;
+    rowptr.alloc(h->n_eqn + 1); col.alloc(nnz); val.alloc(nnz);
+    ISL_LAUNCH(h, k_rowptr_from_keys, h->grid_for(h->n_eqn + 1, 256), 256, 0, keys.p, nnz, h->n_eqn, rowptr.p);
+    if (nnz) {
+        ISL_LAUNCH(h, k_cols_from_keys, h->grid_for(nnz, 256), 256, 0, keys.p, nnz, col.p);
+        ISL_CUDA(cudaMemsetAsync(val.p, 0, nnz * sizeof(double), h->stream));
+    }
+    if (h->nnz > 0 && h->val.p)
+        ISL_LAUNCH(h, k_remap_values, h->grid_for(h->n_eqn, 128), 128, 0, h->rowptr.p, h->col.p, h->val.p, h->n_eqn,
+                   rowptr.p, col.p, val.p);
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    h->rowptr.swap(rowptr); h->col.swap(col); h->val.swap(val);
+    h->nnz = nnz;
+    h->pattern_pairs = pairs;
+    h->slotmaps.clear();
+}
+
+void ensure_pair(isl_engine* h, int t, int c) {
+    ISL_REQUIRE(t >= 0 && t < 5 && c >= 0 && c < 5, "field index out of range");
+    h->sys_pairs.insert({t, c});
+    if (!h->pattern_pairs.count({t, c})) {
+        auto pairs = h->pattern_pairs;
+        pairs.insert({t, c});
+        build_pattern(h, pairs);
+    }
+}
+
+const int32_t* get_slotmap(isl_engine* h, int t, int c) {
+    auto key = std::make_pair(t, c);
+    auto it = h->slotmaps.find(key);
+    if (it != h->slotmaps.end()) return it->second->p;
+    FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
+    build_elem_eqn(h, ft); build_elem_eqn(h, fc);
+    const int nr = ft.ndpe * ft.ds, ncl = fc.ndpe * fc.ds;
+    const int64_t n = h->n_elems * nr * ncl;
+    auto buf = std::make_unique<DevBuf<int32_t>>();
+    buf->alloc(n);
+    ISL_LAUNCH(h, k_slotmap, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_elems, nr, ncl,
+               h->rowptr.p, h->col.p, buf->p);
+    const int32_t* p = buf->p;
+    h->slotmaps[key] = std::move(buf);
+    return p;
+}
+
+TableDev* get_tables(isl_engine* h, int quad_deg, int t, int c) {
+    std::array<int, 3> key = {quad_deg, t, c};
+    auto it = h->tables.find(key);
+    if (it != h->tables.end()) return it->second.get();
+    const isl::Rule R = isl::make_rule(h->shape, quad_deg);
+    const isl::Basis G(h->shape, h->geom_deg), T(h->shape, h->fields[t].deg), C(h->shape, h->fields[c].deg);
+    auto td = std::make_unique<TableDev>();
+    td->nq = R.n;
+    auto tab = [&](const isl::Basis& B, std::vector<double>& N, std::vector<double>& dN) {
+        N.resize((size_t)R.n * B.nfun); dN.resize((size_t)R.n * B.nfun * B.dim);
+        for (int q = 0; q < R.n; q++) B.eval(&R.p[(size_t)q * R.dim], &N[(size_t)q * B.nfun], &dN[(size_t)q * B.nfun * B.dim]);
+    };
+    std::vector<double> N, dN;
+    upload_vec(h, td->w, R.w);
+    tab(G, N, dN); upload_vec(h, td->Ng, N); upload_vec(h, td->dNg, dN);
+    tab(T, N, dN); upload_vec(h, td->Nt, N); upload_vec(h, td->dNt, dN);
+    tab(C, N, dN); upload_vec(h, td->Nc, N); upload_vec(h, td->dNc, dN);
+    TableDev* p = td.get();
+    h->tables[key] = std::move(td);
+    return p;
+}
+
+size_t stage_doubles_per_elem(const AsmParams& p, int dim) {
+    size_t n = (size_t)p.npe * dim + (size_t)p.nq * dim * dim + p.nq;
+    if (p.need_gt) n += (size_t)p.nq * p.nt * dim;
+    if (p.need_gc && !(p.bubnov && p.need_gt)) n += (size_t)p.nq * p.nc * dim;
+    n += (size_t)p.nq * p.nqdata;
+    return n;
+}
+
+void fill_common(isl_engine* h, AsmParams& p, int quad_deg, int t, int c) {
+    ISL_REQUIRE(h->n_elems > 0, "mesh not set");
+    FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
+    ISL_REQUIRE(ft.set && fc.set, "field not set");
+    TableDev* td = get_tables(h, quad_deg, t, c);
+    p.coords = h->coords.p; p.conn = h->conn.p; p.n_elems = h->n_elems; p.npe = h->npe;
+    p.w = td->w.p; p.dNg = td->dNg.p; p.Ng = td->Ng.p; p.Nt = td->Nt.p; p.dNt = td->dNt.p; p.Nc = td->Nc.p; p.dNc = td->dNc.p;
+    p.nq = td->nq; p.nt = ft.ndpe; p.nc = fc.ndpe; p.dst = ft.ds; p.dsc = fc.ds; p.bubnov = (t == c);
+    p.ed_t = ft.elem_dof.p; p.ed_c = fc.elem_dof.p; p.eqn_t = ft.eqn.p; p.eqn_c = fc.eqn.p;
+    p.st_c = fc.status.p; p.presc_c = fc.presc.p; p.val_c = fc.values.p;
+    p.val = h->val.p; p.rhs = h->rhs.p;
+}
+
+template <class K>
+void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
+    const size_t per = stage_doubles_per_elem(p, h->dim) * sizeof(double);
+    const size_t budget = 96 * 1024;
+    ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
+    int EB = (int)std::max<size_t>(1, std::min<size_t>(budget / per, 32));
+    p.EB = EB;
+    const size_t smem = per * EB;
+    ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    const int64_t nbatch = (h->n_elems + EB - 1) / EB;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
+    kernel<<<grid, 256, smem, h->stream>>>(p);
+    h->launches++;
+    ISL_CUDA(cudaGetLastError());
+}
+
+void check_kernel_fields(isl_engine* h, int kid, int t, int c, bool tangent) {
+    const FieldDev& ft = h->fields[t]; const FieldDev& fc = h->fields[c];
+    switch (kid) {
+        case ISL_K_LAPLACE:
+        case ISL_K_VECTOR_LAPLACE:
+            ISL_REQUIRE(ft.ds == fc.ds, "Laplace kernel: test and trial DoF sizes differ");
+            if (!tangent && kid == ISL_K_LAPLACE) ISL_REQUIRE(fc.ds == 1, "heat::Laplace residual needs a scalar field");
+            break;
+        case ISL_K_HYPEL_STVENANT:
+        case ISL_K_HYPEL_NEOHOOKE:
+            ISL_REQUIRE(ft.ds == h->dim && fc.ds == h->dim, "HyperElastic kernel: DoF size must equal the space dimension");
+            break;
+        case ISL_K_PRESSURE_GRADIENT:
+            ISL_REQUIRE(ft.ds == h->dim && fc.ds == 1, "PressureGradient: test = velocity (dim), trial = pressure (1)");
+            break;
+        case ISL_K_VELOCITY_DIVERGENCE:
+            ISL_REQUIRE(ft.ds == 1 && fc.ds == h->dim, "VelocityDivergence: test = pressure (1), trial = velocity (dim)");
+            break;
+        default: throw IslError("unknown kernel id " + std::to_string(kid));
+    }
+}
+
+void load_q1_tables(isl_engine* h) {
+    if (h->q1_tables_loaded) return;
+    const isl::Rule R = isl::make_rule(ISL_HEX, 3);
+    const isl::Basis B(ISL_HEX, 1);
+    std::vector<double> dN(8 * 8 * 3), N(8);
+    for (int q = 0; q < 8; q++) B.eval(&R.p[q * 3], N.data(), &dN[q * 24]);
+    ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_dN, dN.data(), sizeof(double) * 192, 0, cudaMemcpyHostToDevice, h->stream));
+    ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_w, R.w.data(), sizeof(double) * 8, 0, cudaMemcpyHostToDevice, h->stream));
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    h->q1_tables_loaded = true;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+const char* isl_last_error(void) { return g_error.c_str(); }
+int isl_version(void) { return 100; }
+
+int isl_engine_create(int device, isl_handle* out) {
+    return guarded([&] {
+        ISL_REQUIRE(out, "null output handle");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw IslError("no CUDA device available: the assembly engine has no CPU fallback");
+        ISL_REQUIRE(device >= 0 && device < count, "device index out of range");
+        ISL_CUDA(cudaSetDevice(device));
+        auto h = std::make_unique<isl_engine>();
+        h->device = device;
+        ISL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaDeviceProp prop;
+        ISL_CUDA(cudaGetDeviceProperties(&prop, device));
+        h->n_sm = prop.multiProcessorCount;
+        *out = h.release();
+    });
+}
+int isl_engine_destroy(isl_handle h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->stream);
+        cudaStream_t s = h->stream;
+        delete h;
+        cudaStreamDestroy(s);
+    });
+}
+int isl_synchronize(isl_handle h) { return guarded([&] { ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
+void* isl_engine_stream(isl_handle h) { return (void*)h->stream; }
+int64_t isl_kernel_launches(isl_handle h) { return h->launches; }
+
+// ---- host tables ----
+int isl_quadrature(int shape, int degree, double* w, double* p) {
+    int n = -1;
+    guarded([&] {
+        const isl::Rule R = isl::make_rule(shape, degree);
+        if (w) std::copy(R.w.begin(), R.w.end(), w);
+        if (p) std::copy(R.p.begin(), R.p.end(), p);
+        n = R.n;
+    });
+    return n;
+}
+int isl_shape_nfun(int shape, int degree) {
+    int n = -1;
+    guarded([&] { n = isl::Basis(shape, degree).nfun; });
+    return n;
+}
+int isl_shape_eval(int shape, int degree, const double* xi, double* fun, double* grad) {
+    return guarded([&] { isl::Basis(shape, degree).eval(xi, fun, grad); });
+}
+int isl_support_points(int shape, int degree, double* pts) {
+    return guarded([&] { isl::Basis(shape, degree).support(pts); });
+}
+
+// ---- DoF handling ----
+int isl_ndpe(int shape, int fe_deg) {
+    int n = -1;
+    guarded([&] { n = isl::fe_layout(shape, fe_deg).total; });
+    return n;
+}
+int isl_dof_generate(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int fe_deg, int32_t* elem_dof,
+                     int64_t* n_obj) {
+    return guarded([&] { *n_obj = isl::dof_generate(shape, geom_deg, n_elems, conn, fe_deg, elem_dof); });
+}
+int isl_mesh_boundary(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int64_t* pairs, int64_t* n_pairs) {
+    return guarded([&] {
+        std::vector<int64_t> b;
+        isl::mesh_boundary(shape, geom_deg, n_elems, conn, b);
+        *n_pairs = (int64_t)b.size() / 2;
+        if (pairs) std::copy(b.begin(), b.end(), pairs);
+    });
+}
+int isl_boundary_dofs(int shape, int geom_deg, int dim, const double* coords, int64_t n_elems, const int32_t* conn,
+                      int fe_deg, const int32_t* elem_dof, int64_t n_pairs, const int64_t* pairs, int32_t* obj,
+                      double* x, int64_t* n) {
+    return guarded([&] {
+        (void)n_elems;
+        std::vector<int32_t> o; std::vector<double> xx;
+        isl::boundary_dofs(shape, geom_deg, dim, coords, conn, fe_deg, elem_dof, n_pairs, pairs, o, xx);
+        *n = (int64_t)o.size();
+        if (obj) { std::copy(o.begin(), o.end(), obj); std::copy(xx.begin(), xx.end(), x); }
+    });
+}
+int isl_number_dofs(int64_t n_obj, int dof_size, const uint8_t* status, int64_t init, int64_t* eqn, int64_t* n_numbered) {
+    return guarded([&] { *n_numbered = isl::number_dofs(n_obj, dof_size, status, init, eqn); });
+}
+
+// ---- mesh / fields ----
+int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes, const double* coords, int64_t n_elems,
+                 const int32_t* conn) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(dim == isl::shape_dim(shape), "only DIM == shape dimension is supported (no manifolds)");
+        ISL_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
+        const isl::Basis G(shape, geom_deg);
+        h->shape = shape; h->geom_deg = geom_deg; h->dim = dim; h->npe = G.nfun;
+        h->n_nodes = n_nodes; h->n_elems = n_elems;
+        upload(h, h->coords, coords, (size_t)n_nodes * dim);
+        upload(h, h->conn, conn, (size_t)n_elems * h->npe);
+        for (auto& f : h->fields) f.reset();
+        h->tables.clear();
+        invalidate_pattern(h);
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_mesh_update_coords(isl_handle h, const double* coords) {
+    return guarded([&] {
+        ISL_REQUIRE(h->n_nodes > 0, "mesh not set");
+        ISL_CUDA(cudaMemcpyAsync(h->coords.p, coords, (size_t)h->n_nodes * h->dim * sizeof(double), cudaMemcpyDefault, h->stream));
+    });
+}
+int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_obj, const int32_t* elem_dof,
+                  const int64_t* eqn, const uint8_t* status, const double* prescribed, const double* values) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(field >= 0 && field < 5, "field index out of range (0..4)");
+        ISL_REQUIRE(h->n_elems > 0, "mesh must be set before fields");
+        ISL_REQUIRE(dof_size >= 1 && dof_size <= 3, "dof_size must be 1..3");
+        FieldDev& f = h->fields[field];
+        f.reset();
+        f.deg = fe_deg; f.ds = dof_size; f.n_obj = n_obj;
+        f.ndpe = isl::Basis(h->shape, fe_deg).nfun;
+        const size_t n = (size_t)n_obj * dof_size;
+        upload(h, f.elem_dof, elem_dof, (size_t)h->n_elems * f.ndpe);
+        // equation numbers are narrowed to int32 on the device
+        std::vector<int64_t> e64(n);
+        ISL_CUDA(cudaMemcpy(e64.data(), eqn, n * sizeof(int64_t), cudaMemcpyDefault));
+        std::vector<int32_t> e32(n);
+        for (size_t i = 0; i < n; i++) {
+            ISL_REQUIRE(e64[i] < ((int64_t)1 << 31), "equation number exceeds int32");
+            e32[i] = e64[i] < 0 ? -1 : (int32_t)e64[i];
+        }
+        upload_vec(h, f.eqn, e32);
+        upload(h, f.status, status, n);
+        upload(h, f.presc, prescribed, n);
+        upload(h, f.values, values, n);
+        f.set = true;
+        if (f.ndpe == h->npe) {
+            DevBuf<int> nd; nd.alloc(1);
+            ISL_CUDA(cudaMemsetAsync(nd.p, 0, sizeof(int), h->stream));
+            const int64_t cnt = h->n_elems * h->npe;
+            ISL_LAUNCH(h, k_count_diff, h->grid_for(cnt, 256), 256, 0, f.elem_dof.p, h->conn.p, cnt, nd.p);
+            int ndiff = 1;
+            ISL_CUDA(cudaMemcpyAsync(&ndiff, nd.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            f.dof_is_node = (ndiff == 0);
+        }
+        invalidate_pattern(h);
+        // tables depend on the field degrees only, but drop those that refer to this field id
+        for (auto it = h->tables.begin(); it != h->tables.end();)
+            if (it->first[1] == field || it->first[2] == field) it = h->tables.erase(it); else ++it;
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values) {
+    return guarded([&] {
+        ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
+        FieldDev& f = h->fields[field];
+        const size_t bytes = (size_t)f.n_obj * f.ds * sizeof(double);
+        if (prescribed) ISL_CUDA(cudaMemcpyAsync(f.presc.p, prescribed, bytes, cudaMemcpyDefault, h->stream));
+        if (values) ISL_CUDA(cudaMemcpyAsync(f.values.p, values, bytes, cudaMemcpyDefault, h->stream));
+    });
+}
+
+// ---- system ----
+int isl_system_create(isl_handle h, int64_t n_eqn) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(n_eqn >= 0, "negative system size");
+        if (n_eqn != h->n_eqn) { invalidate_pattern(h); h->n_eqn = n_eqn; h->rhs.alloc(n_eqn); }
+        h->sys_pairs.clear();
+        if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
+        if (h->nnz) ISL_CUDA(cudaMemsetAsync(h->val.p, 0, h->nnz * sizeof(double), h->stream));
+    });
+}
+int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ensure_pair(h, test_field, trial_field);
+        get_slotmap(h, test_field, trial_field);
+    });
+}
+
+int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, int incremental) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ensure_pair(h, t, c);
+        check_kernel_fields(h, kid, t, c, true);
+        const int32_t* slot = get_slotmap(h, t, c);
+        const FieldDev& ft = h->fields[t];
+        // hot path: Q1 hex, scalar Laplace, 2x2x2 rule
+        if ((kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE) && h->shape == ISL_HEX && h->geom_deg == 1 && t == c &&
+            ft.deg == 1 && ft.ds == 1 && ft.dof_is_node && (quad_deg == 2 || quad_deg == 3)) {
+            load_q1_tables(h);
+            Q1Params q;
+            q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_elems; q.slot = slot;
+            q.eqn = ft.eqn.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p;
+            q.val = h->val.p; q.rhs = h->rhs.p; q.factor = params ? params[0] : 1.0; q.incremental = incremental;
+            const int block = 128;
+            const int64_t grid = (h->n_elems + block - 1) / block;
+            ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
+            return;
+        }
+        AsmParams p; std::memset(&p, 0, sizeof(p));
+        fill_common(h, p, quad_deg, t, c);
+        p.slot = slot; p.kernel_id = kid; p.incremental = incremental;
+        p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
+        p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
+        p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT);
+        p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : 0;
+        if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+    });
+}
+
+int isl_assemble_residual(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, double factor) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        check_kernel_fields(h, kid, t, c, false);
+        AsmParams p; std::memset(&p, 0, sizeof(p));
+        fill_common(h, p, quad_deg, t, c);
+        p.kernel_id = kid; p.factor = factor;
+        p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
+        p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
+        p.need_gc = (kid != ISL_K_PRESSURE_GRADIENT);
+        p.nqdata = 9;
+        if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
+    });
+}
+
+int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        AsmParams p; std::memset(&p, 0, sizeof(p));
+        fill_common(h, p, quad_deg, t, t);
+        p.body = 1; p.factor = 1.0;
+        for (int d = 0; d < h->fields[t].ds; d++) p.f[d] = f[d];
+        p.need_gt = 0; p.need_gc = 0; p.nqdata = 0;
+        if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
+    });
+}
+
+int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols, int n_cols) {
+    return guarded([&] {
+        ISL_REQUIRE(h->nnz > 0, "no pattern registered");
+        for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, "Row index out of bound: " + std::to_string(rows[i]));
+        for (int j = 0; j < n_cols; j++) ISL_REQUIRE(cols[j] >= 0 && cols[j] < h->n_eqn, "Col index out of bound: " + std::to_string(cols[j]));
+        DevBuf<double> dm; DevBuf<int64_t> dr, dc; DevBuf<int> derr;
+        upload(h, dm, mat, (size_t)n_rows * n_cols); upload(h, dr, rows, n_rows); upload(h, dc, cols, n_cols);
+        derr.alloc(1); ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
+        const int n = n_rows * n_cols;
+        ISL_LAUNCH(h, k_insert_lhs, (n + 127) / 128, 128, 0, dm.p, dr.p, n_rows, dc.p, n_cols, h->rowptr.p, h->col.p, h->val.p, derr.p);
+        int err = 0;
+        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        ISL_REQUIRE(!err, "TripletContainer had not been properly set up");
+    });
+}
+int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_rows) {
+    return guarded([&] {
+        for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, std::to_string(rows[i]) + " out of bound");
+        DevBuf<double> dv; DevBuf<int64_t> dr;
+        upload(h, dv, vec, n_rows); upload(h, dr, rows, n_rows);
+        ISL_LAUNCH(h, k_insert_rhs, (n_rows + 127) / 128, 128, 0, dv.p, dr.p, n_rows, h->rhs.p);
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        if (h->sys_pairs != h->pattern_pairs && !h->sys_pairs.empty()) {
+            // the cached pattern holds blocks this system never registered: rebuild exactly
+            build_pattern(h, h->sys_pairs);
+        }
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        if (n_eqn) *n_eqn = h->n_eqn;
+        if (nnz) *nnz = h->sys_pairs.empty() ? 0 : h->nnz;
+    });
+}
+int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        if (rowptr) {
+            if (h->rowptr.p) ISL_CUDA(cudaMemcpyAsync(rowptr, h->rowptr.p, (h->n_eqn + 1) * sizeof(int64_t), cudaMemcpyDefault, h->stream));
+            else ISL_CUDA(cudaMemsetAsync(rowptr, 0, (h->n_eqn + 1) * sizeof(int64_t), h->stream));
+        }
+        if (col && h->nnz) ISL_CUDA(cudaMemcpyAsync(col, h->col.p, h->nnz * sizeof(int32_t), cudaMemcpyDefault, h->stream));
+        if (val && h->nnz) ISL_CUDA(cudaMemcpyAsync(val, h->val.p, h->nnz * sizeof(double), cudaMemcpyDefault, h->stream));
+        if (rhs && h->n_eqn) ISL_CUDA(cudaMemcpyAsync(rhs, h->rhs.p, h->n_eqn * sizeof(double), cudaMemcpyDefault, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs) {
+    return guarded([&] {
+        if (rowptr) *rowptr = h->rowptr.p;
+        if (col) *col = h->col.p;
+        if (val) *val = h->val.p;
+        if (rhs) *rhs = h->rhs.p;
+    });
+}
+int isl_rhs_value(isl_handle h, int64_t index, double* value) {
+    return guarded([&] {
+        ISL_REQUIRE(index >= 0 && index < h->n_eqn, "index out of bound");
+        ISL_CUDA(cudaMemcpyAsync(value, h->rhs.p + index, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_rhs_norm(isl_handle h, double* norm) {
+    return guarded([&] {
+        ISL_REQUIRE(h->n_eqn > 0, "empty system");
+        h->scratch_d.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(h->scratch_d.p, 0, sizeof(double), h->stream));
+        ISL_LAUNCH(h, k_sumsq, h->grid_for(h->n_eqn, 256), 256, 0, h->rhs.p, h->n_eqn, h->scratch_d.p);
+        double s = 0.;
+        ISL_CUDA(cudaMemcpyAsync(&s, h->scratch_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        *norm = std::sqrt(s) / (double)h->n_eqn;  // Eigen3.hpp:133-138 divides by the segment length
+    });
+}
+
+int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev) {
+    return guarded([&] {
+        if (n == 0) return;
+        const double* src = which == 1 ? h->rhs.p : h->val.p;
+        ISL_LAUNCH(h, k_pack, h->grid_for(n, 256), 256, 0, src, idx_dev, n, out_dev);
+    });
+}
+int isl_unpack_add_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, const double* in_dev) {
+    return guarded([&] {
+        if (n == 0) return;
+        double* dst = which == 1 ? h->rhs.p : h->val.p;
+        ISL_LAUNCH(h, k_unpack_add, h->grid_for(n, 256), 256, 0, dst, idx_dev, n, in_dev);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""ctypes binding of the C ABI (include/insilico_b200.h) plus a thin host-side mirror of the reference's
+assembly interface.
+
+Names follow the reference (paths relative to the reference root):
+  Engine.stiffness_matrix_computation  <- base::asmb::stiffnessMatrixComputation   (base/asmb/StiffnessMatrix.hpp:49-87)
+  Engine.compute_residual_forces       <- base::asmb::computeResidualForces        (base/asmb/ForceIntegrator.hpp:37-71)
+  Engine.body_force_computation        <- base::asmb::bodyForceComputation         (base/asmb/BodyForce.hpp:65-84)
+  Engine.new_solver / register_fields / finish_assembly / get_value / norm
+                                       <- base::solver::Eigen3                     (base/solver/Eigen3.hpp:71-336)
+  dof_generate / mesh_boundary / number_dofs_consecutively / boundary_dofs
+                                       <- base/dof/generate.hpp, base/mesh/MeshBoundary.hpp, base/dof/numbering.hpp,
+                                          base/dof/constrainBoundary.hpp
+
+There is no CPU fallback: creating an Engine without the CUDA library or without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libinsilico_b200.so")
+
+POINT, LINE, TRI, QUAD, TET, HEX = range(6)
+VERTEX, EDGE, FACE, CELL = range(4)
+ACTIVE, CONSTRAINED, INACTIVE = range(3)
+K_LAPLACE, K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE, K_PRESSURE_GRADIENT, K_VELOCITY_DIVERGENCE, K_VECTOR_LAPLACE = (
+    1, 2, 3, 4, 5, 6)
+SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
+
+# every symbol include/insilico_b200.h declares (checked by tests/test_cabi.py)
+EXPORTED = [
+    "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_synchronize", "isl_engine_stream",
+    "isl_kernel_launches", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
+    "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
+    "isl_mesh_update_coords", "isl_field_set", "isl_field_update", "isl_system_create", "isl_pattern_register",
+    "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_insert_lhs", "isl_insert_rhs",
+    "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_pack_entries",
+    "isl_unpack_add_entries",
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.isl_last_error.restype = C.c_char_p
+        L.isl_engine_stream.restype = C.c_void_p
+        L.isl_engine_stream.argtypes = [C.c_void_p]
+        L.isl_kernel_launches.restype = C.c_int64
+        L.isl_kernel_launches.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise EngineError(lib().isl_last_error().decode())
+
+
+def _ptr(a):
+    """numpy array, raw integer address (host or device) or None -> c_void_p"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i64(x):
+    return C.c_int64(int(x))
+
+
+# ---- host tables / DoF handling (no GPU needed) ------------------------------------------------------------
+def quadrature(shape, degree):
+    n = lib().isl_quadrature(shape, degree, None, None)
+    if n < 0:
+        raise EngineError(lib().isl_last_error().decode())
+    w = np.zeros(n)
+    p = np.zeros((n, SHAPE_DIM[shape]))
+    lib().isl_quadrature(shape, degree, _ptr(w), _ptr(p))
+    return w, p
+
+
+def shape_nfun(shape, degree):
+    n = lib().isl_shape_nfun(shape, degree)
+    if n < 0:
+        raise EngineError(lib().isl_last_error().decode())
+    return n
+
+
+def shape_eval(shape, degree, xi):
+    n = shape_nfun(shape, degree)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    f = np.zeros(n)
+    g = np.zeros((n, SHAPE_DIM[shape]))
+    _chk(lib().isl_shape_eval(shape, degree, _ptr(xi), _ptr(f), _ptr(g)))
+    return f, g
+
+
+def support_points(shape, degree):
+    p = np.zeros((shape_nfun(shape, degree), SHAPE_DIM[shape]))
+    _chk(lib().isl_support_points(shape, degree, _ptr(p)))
+    return p
+
+
+def ndpe(shape, fe_deg):
+    return lib().isl_ndpe(shape, fe_deg)
+
+
+def dof_generate(shape, geom_deg, conn, fe_deg):
+    """base::dof::generate: returns (elem_dof[n_elems, ndpe] int32, n_obj)."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    ed = np.zeros((conn.shape[0], ndpe(shape, fe_deg)), dtype=np.int32)
+    n = C.c_int64()
+    _chk(lib().isl_dof_generate(shape, geom_deg, _i64(conn.shape[0]), _ptr(conn), fe_deg, _ptr(ed), C.byref(n)))
+    return ed, n.value
+
+
+def mesh_boundary(shape, geom_deg, conn):
+    """base::mesh::MeshBoundary::create: (element, face number) pairs."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    n = C.c_int64()
+    _chk(lib().isl_mesh_boundary(shape, geom_deg, _i64(conn.shape[0]), _ptr(conn), None, C.byref(n)))
+    pairs = np.zeros((n.value, 2), dtype=np.int64)
+    _chk(lib().isl_mesh_boundary(shape, geom_deg, _i64(conn.shape[0]), _ptr(conn), _ptr(pairs), C.byref(n)))
+    return pairs
+
+
+def boundary_dofs(shape, geom_deg, coords, conn, fe_deg, elem_dof, pairs):
+    """DoF objects visited by base::dof::constrainBoundary and the positions of their support points."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    elem_dof = np.ascontiguousarray(elem_dof, dtype=np.int32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64)
+    dim = coords.shape[1]
+    n = C.c_int64()
+    args = (shape, geom_deg, dim, _ptr(coords), _i64(conn.shape[0]), _ptr(conn), fe_deg, _ptr(elem_dof),
+            _i64(len(pairs)), _ptr(pairs))
+    _chk(lib().isl_boundary_dofs(*args, None, None, C.byref(n)))
+    obj = np.zeros(n.value, dtype=np.int32)
+    x = np.zeros((n.value, dim))
+    _chk(lib().isl_boundary_dofs(*args, _ptr(obj), _ptr(x), C.byref(n)))
+    return obj, x
+
+
+def constrain_boundary(shape, geom_deg, coords, conn, fe_deg, dof_size, elem_dof, n_obj, fun, pairs=None):
+    """base::dof::constrainBoundary with a Dirichlet function of the position:
+    fun(x[n,dim]) -> values[n,dof_size].  Returns (status u8 [n_obj,ds], prescribed [n_obj,ds])."""
+    if pairs is None:
+        pairs = mesh_boundary(shape, geom_deg, conn)
+    obj, x = boundary_dofs(shape, geom_deg, coords, conn, fe_deg, elem_dof, pairs)
+    vals = np.asarray(fun(x), dtype=np.float64).reshape(len(obj), dof_size)
+    status = np.zeros((n_obj, dof_size), dtype=np.uint8)
+    prescribed = np.zeros((n_obj, dof_size))
+    status[obj] = CONSTRAINED
+    # later visits overwrite earlier ones (DegreeOfFreedom::constrainValue); numpy keeps the last assignment
+    prescribed[obj] = vals
+    return status, prescribed
+
+
+def number_dofs_consecutively(status, init=0):
+    """base::dof::numberDoFsConsecutively: eqn[n_obj, ds] (-1 where not ACTIVE), count."""
+    status = np.ascontiguousarray(status, dtype=np.uint8)
+    n_obj, ds = status.shape
+    eqn = np.zeros((n_obj, ds), dtype=np.int64)
+    n = C.c_int64()
+    _chk(lib().isl_number_dofs(_i64(n_obj), ds, _ptr(status), _i64(init), _ptr(eqn), C.byref(n)))
+    return eqn, n.value
+
+
+# ---- engine ---------------------------------------------------------------------------------------------
+class Engine:
+    """One engine per GPU: mesh + fields (asmb::FieldBinder) + one linear system (solver::Eigen3)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _chk(lib().isl_engine_create(int(device), C.byref(self.h)))
+        self.n_eqn = 0
+
+    def close(self):
+        if self.h:
+            lib().isl_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return lib().isl_engine_stream(self.h)
+
+    @property
+    def kernel_launches(self):
+        return lib().isl_kernel_launches(self.h)
+
+    def synchronize(self):
+        _chk(lib().isl_synchronize(self.h))
+
+    # base::Unstructured<SHAPE,GEOMDEG>
+    def set_mesh(self, shape, geom_deg, coords, conn, n_nodes=None, n_elems=None, dim=None):
+        if not isinstance(coords, (int, np.integer)):
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            n_nodes, dim = coords.shape
+        if not isinstance(conn, (int, np.integer)):
+            conn = np.ascontiguousarray(conn, dtype=np.int32)
+            n_elems = conn.shape[0]
+        self.shape, self.geom_deg, self.dim = shape, geom_deg, dim
+        self.n_nodes, self.n_elems = n_nodes, n_elems
+        _chk(lib().isl_mesh_set(self.h, shape, geom_deg, dim, _i64(n_nodes), _ptr(coords), _i64(n_elems), _ptr(conn)))
+
+    def update_coords(self, coords):
+        _chk(lib().isl_mesh_update_coords(self.h, _ptr(coords)))
+
+    # base::Field<FEBasis,DOFSIZE>
+    def set_field(self, fid, fe_deg, dof_size, n_obj, elem_dof, eqn, status, prescribed, values):
+        conv = lambda a, dt: a if isinstance(a, (int, np.integer)) else np.ascontiguousarray(a, dtype=dt)
+        elem_dof, eqn = conv(elem_dof, np.int32), conv(eqn, np.int64)
+        status, prescribed, values = conv(status, np.uint8), conv(prescribed, np.float64), conv(values, np.float64)
+        _chk(lib().isl_field_set(self.h, fid, fe_deg, dof_size, _i64(n_obj), _ptr(elem_dof), _ptr(eqn), _ptr(status),
+                                 _ptr(prescribed), _ptr(values)))
+
+    def update_field(self, fid, prescribed=None, values=None):
+        _chk(lib().isl_field_update(self.h, fid, _ptr(prescribed), _ptr(values)))
+
+    # base::solver::Eigen3
+    def new_solver(self, n_eqn):
+        self.n_eqn = int(n_eqn)
+        _chk(lib().isl_system_create(self.h, _i64(n_eqn)))
+
+    def register_fields(self, test, trial):
+        _chk(lib().isl_pattern_register(self.h, test, trial))
+
+    def stiffness_matrix_computation(self, kernel_id, params, quad_deg, test, trial, incremental=True):
+        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        _chk(lib().isl_assemble_matrix(self.h, kernel_id, _ptr(params), quad_deg, test, trial, int(incremental)))
+
+    def compute_residual_forces(self, kernel_id, params, quad_deg, test, trial, factor=-1.0):
+        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        _chk(lib().isl_assemble_residual(self.h, kernel_id, _ptr(params), quad_deg, test, trial, C.c_double(factor)))
+
+    def body_force_computation(self, f, quad_deg, test):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        _chk(lib().isl_assemble_bodyforce(self.h, _ptr(f), quad_deg, test))
+
+    def insert_to_lhs(self, mat, rows, cols):
+        mat = np.ascontiguousarray(mat, dtype=np.float64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        cols = np.ascontiguousarray(cols, dtype=np.int64)
+        _chk(lib().isl_insert_lhs(self.h, _ptr(mat), _ptr(rows), len(rows), _ptr(cols), len(cols)))
+
+    def insert_to_rhs(self, vec, rows):
+        vec = np.ascontiguousarray(vec, dtype=np.float64)
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        _chk(lib().isl_insert_rhs(self.h, _ptr(vec), _ptr(rows), len(rows)))
+
+    def finish_assembly(self):
+        n, nnz = C.c_int64(), C.c_int64()
+        _chk(lib().isl_finish(self.h, C.byref(n), C.byref(nnz)))
+        self.nnz = nnz.value
+        return n.value, nnz.value
+
+    def get_csr(self, rowptr=None, col=None, val=None, rhs=None, pattern=True):
+        """Copies the system out.  With no arguments allocates numpy arrays and returns (rowptr, col, val, rhs)."""
+        if rowptr is None and col is None and val is None and rhs is None:
+            n, nnz = self.finish_assembly()
+            rowptr = np.zeros(n + 1, dtype=np.int64) if pattern else None
+            col = np.zeros(nnz, dtype=np.int32) if pattern else None
+            val = np.zeros(nnz)
+            rhs = np.zeros(n)
+        _chk(lib().isl_get_csr(self.h, _ptr(rowptr), _ptr(col), _ptr(val), _ptr(rhs)))
+        return rowptr, col, val, rhs
+
+    def device_csr(self):
+        p = [C.c_void_p() for _ in range(4)]
+        _chk(lib().isl_get_device_csr(self.h, *[C.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def get_value(self, index):
+        v = C.c_double()
+        _chk(lib().isl_rhs_value(self.h, _i64(index), C.byref(v)))
+        return v.value
+
+    def norm(self):
+        v = C.c_double()
+        _chk(lib().isl_rhs_norm(self.h, C.byref(v)))
+        return v.value
+
+    def pack_entries(self, which, idx_dev, n, out_dev):
+        _chk(lib().isl_pack_entries(self.h, which, _ptr(idx_dev), _i64(n), _ptr(out_dev)))
+
+    def unpack_add_entries(self, which, idx_dev, n, in_dev):
+        _chk(lib().isl_unpack_add_entries(self.h, which, _ptr(idx_dev), _i64(n), _ptr(in_dev)))

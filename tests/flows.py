@@ -1,0 +1,220 @@
+"""Application flows run on BOTH the CPU oracle and the CUDA engine (through the C ABI) for parity tests.
+
+Each case follows one of the reference's applications:
+  laplace_*     reference/04-heat/dirichlet.cpp:79-167            (Dirichlet from the Laplace fundamental solution)
+  stvenant_*    reference/06-elastic/linearElastic.cpp:83-196     (HyperElastic<StVenant>, Lame from E, nu)
+  neohooke_*    reference/06-elastic/compressible.cpp:245-320     (tangent + residual per Newton step)
+  stokes_*      reference/07-drivenCavity/drivenCavity.cpp:176-275 (Taylor-Hood blocks UU, UP, PU)
+"""
+import numpy as np
+
+from insilico_b200 import engine as E
+from insilico_b200 import meshgen
+from oracle import oracle as orc
+from tests import helpers as H
+
+
+def lame(Emod, nu):
+    return Emod * nu / (1. + nu) / (1. - 2. * nu), Emod / 2. / (1. + nu)
+
+
+def make_mesh(shape, n, perturb, permute=False):
+    if shape == E.HEX:
+        coords, conn, _ = meshgen.unit_cube_hex(n, n, n)
+    elif shape == E.TET:
+        coords, conn = meshgen.unit_cube_tet(n, n, n)
+    elif shape == E.QUAD:
+        coords, conn = meshgen.unit_square_quad(n, n)
+    elif shape == E.TRI:
+        coords, conn = meshgen.unit_square_tri(n, n)
+    else:
+        raise ValueError(shape)
+    if perturb:
+        coords = meshgen.perturb_interior(coords, 1.0 / n, max_dist=0.15)
+    if permute:
+        conn = meshgen.permute_elements(conn)
+    return coords, conn
+
+
+class Case:
+    """mesh + fields + list of assembly operations"""
+
+    def __init__(self, shape, geom_deg, coords, conn):
+        self.shape, self.geom_deg = shape, geom_deg
+        self.coords = np.ascontiguousarray(coords, dtype=np.float64)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32)
+        self.dim = coords.shape[1]
+        self.fields = []
+        self.ops = []
+        self.n_eqn = 0
+
+    def add_field(self, fe_deg, ds, dirichlet=None, values=None, pin_first=False):
+        """dirichlet: fun(x)->[n,ds] applied on the whole boundary (dof::constrainBoundary);
+        values: fun(x_support)->[n_obj,ds] current field state; pin_first: constrain component 0 of DoF 0 to 0
+        (drivenCavity.cpp:199-202)."""
+        ed, nobj = E.dof_generate(self.shape, self.geom_deg, self.conn, fe_deg)
+        status = np.zeros((nobj, ds), dtype=np.uint8)
+        presc = np.zeros((nobj, ds))
+        if dirichlet is not None:
+            status, presc = E.constrain_boundary(self.shape, self.geom_deg, self.coords, self.conn, fe_deg, ds, ed,
+                                                 nobj, dirichlet)
+        if pin_first:
+            status[0, 0] = E.CONSTRAINED
+            presc[0, 0] = 0.0
+        eqn, n = E.number_dofs_consecutively(status, init=self.n_eqn)
+        self.n_eqn += n
+        vals = np.zeros((nobj, ds))
+        if values is not None:
+            vals = np.asarray(values(self.dof_positions(fe_deg, ed, nobj)), dtype=np.float64).reshape(nobj, ds)
+        self.fields.append(dict(fe_deg=fe_deg, ds=ds, n_obj=nobj, elem_dof=ed, status=status, presc=presc, eqn=eqn,
+                                values=vals))
+        return len(self.fields) - 1
+
+    def dof_positions(self, fe_deg, ed, nobj):
+        """physical position of every DoF object (support point mapped through the geometry)."""
+        sp = E.support_points(self.shape, fe_deg)
+        Ng = np.array([E.shape_eval(self.shape, self.geom_deg, s)[0] for s in sp])  # [ndpe, npe]
+        xe = self.coords[self.conn]                                                  # [ne, npe, dim]
+        xd = np.einsum("la,ead->eld", Ng, xe)                                        # [ne, ndpe, dim]
+        pos = np.zeros((nobj, self.dim))
+        pos[ed.reshape(-1)] = xd.reshape(-1, self.dim)
+        return pos
+
+    # ---- run on the oracle -------------------------------------------------------------------------
+    def run_oracle(self, register=False, nthreads=1):
+        prob = orc.Problem(self.shape, self.geom_deg, self.coords, self.conn.astype(np.int64))
+        for i, f in enumerate(self.fields):
+            prob.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"].astype(np.int64), f["eqn"], f["status"],
+                           f["presc"], f["values"])
+        s = orc.System(self.n_eqn)
+        if register:
+            for op in self.ops:
+                if op[0] == "matrix":
+                    s.register_fields(prob, op[4], op[5])
+        for op in self.ops:
+            if op[0] == "matrix":
+                s.stiffness(prob, op[1], op[2], op[3], op[4], op[5], incremental=op[6], nthreads=nthreads)
+            elif op[0] == "residual":
+                s.residual(prob, op[1], op[2], op[3], op[4], op[5])
+            elif op[0] == "body":
+                s.bodyforce(prob, op[1], op[2], op[3])
+        return s.finish()
+
+    # ---- run on the CUDA engine ----------------------------------------------------------------------
+    def run_engine(self, eng=None, register=False):
+        own = eng is None
+        if own:
+            eng = E.Engine(0)
+        eng.set_mesh(self.shape, self.geom_deg, self.coords, self.conn)
+        for i, f in enumerate(self.fields):
+            eng.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"],
+                          f["values"])
+        eng.new_solver(self.n_eqn)
+        if register:
+            for op in self.ops:
+                if op[0] == "matrix":
+                    eng.register_fields(op[4], op[5])
+        for op in self.ops:
+            if op[0] == "matrix":
+                eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+            elif op[0] == "residual":
+                eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5])
+            elif op[0] == "body":
+                eng.body_force_computation(op[1], op[2], op[3])
+        out = eng.get_csr()
+        if own:
+            eng.close()
+        return out
+
+
+def smooth_u(dim, amp=0.02):
+    return lambda x: amp * np.sin(np.pi * x[:, :dim]) * (1.0 + x[:, ::-1][:, :dim])
+
+
+def build_case(name, n=4, perturb=True, permute=False):
+    src3 = np.full(3, -0.5)
+    if name == "laplace_q1_hex":
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3))
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True), ("body", [1.0], 3, 0)]
+    elif name == "laplace_q1_hex_values":  # non-zero current values: incremental lift uses prescribed - current
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), values=lambda x: 0.3 * x[:, :1] + 0.1)
+        c.ops = [("matrix", E.K_LAPLACE, [2.5], 3, 0, 0, True), ("residual", E.K_LAPLACE, [2.5], 3, 0, 0)]
+    elif name == "laplace_q2_hex":
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(2, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3))
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 4, 0, 0, False), ("body", [1.0], 4, 0)]
+    elif name == "laplace_p1_tet":
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3))
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True), ("body", [1.0], 2, 0)]
+    elif name == "laplace_q1_quad":
+        c = Case(E.QUAD, 1, *make_mesh(E.QUAD, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, np.full(2, -0.5)))
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True), ("body", [1.0], 3, 0)]
+    elif name == "laplace_p2_tri":
+        c = Case(E.TRI, 1, *make_mesh(E.TRI, n, perturb, permute))
+        c.add_field(2, 1, dirichlet=lambda x: H.fund_sol_laplace(x, np.full(2, -0.5)))
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 4, 0, 0, True), ("body", [1.0], 4, 0)]
+    elif name == "vector_laplace_q1_hex":
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 3, dirichlet=lambda x: np.stack([x[:, 0], 0 * x[:, 1], -x[:, 2]], axis=1), values=smooth_u(3))
+        c.ops = [("matrix", E.K_VECTOR_LAPLACE, [0.7], 3, 0, 0, True), ("residual", E.K_VECTOR_LAPLACE, [0.7], 3, 0, 0),
+                 ("body", [0.0, 0.0, -1.0], 3, 0)]
+    elif name in ("stvenant_q1_hex", "stvenant_q2_hex", "neohooke_q1_hex"):
+        lam, mu = lame(1000.0, 0.25)
+        deg = 2 if "q2" in name else 1
+        kid = E.K_HYPEL_NEOHOOKE if "neohooke" in name else E.K_HYPEL_STVENANT
+        y0 = np.full(3, -0.1); d = np.array([0., 1., 0.])
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(deg, 3, dirichlet=lambda x: H.fund_sol_elastostatic(x, y0, d, lam, mu), values=smooth_u(3))
+        q = 4 if deg == 2 else 3
+        c.ops = [("matrix", kid, [lam, mu], q, 0, 0, True), ("residual", kid, [lam, mu], q, 0, 0)]
+    elif name == "stvenant_q1_quad":
+        lam, mu = lame(1000.0, 0.25)
+        y0 = np.full(2, -0.1); d = np.array([0., 1.])
+        c = Case(E.QUAD, 1, *make_mesh(E.QUAD, n, perturb, permute))
+        c.add_field(1, 2, dirichlet=lambda x: H.fund_sol_elastostatic(x, y0, d, lam, mu), values=smooth_u(2))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0, True),
+                 ("residual", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0)]
+    elif name == "neohooke_p2_tet":
+        lam, mu = lame(1000.0, 0.3)
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, values=lambda x: 0.05 * np.sin(np.pi * x))
+        c.ops = [("matrix", E.K_HYPEL_NEOHOOKE, [lam, mu], 4, 0, 0, True),
+                 ("residual", E.K_HYPEL_NEOHOOKE, [lam, mu], 4, 0, 0)]
+    elif name in ("stokes_p2p1_tet", "stokes_q2q1_hex", "stokes_q2q1_quad"):
+        shape = E.TET if "tet" in name else (E.HEX if "hex" in name else E.QUAD)
+        dim = E.SHAPE_DIM[shape]
+        c = Case(shape, 1, *make_mesh(shape, n, perturb, permute))
+        lid = lambda x: np.stack([(x[:, dim - 1] > 1 - 1e-9) * 1.0] + [0 * x[:, 0]] * (dim - 1), axis=1)
+        u = c.add_field(2, dim, dirichlet=lid, values=smooth_u(dim))
+        p = c.add_field(1, 1, pin_first=True, values=lambda x: x[:, :1] - 0.5)
+        c.ops = [("matrix", E.K_VECTOR_LAPLACE, [1.0], 4, u, u, True), ("matrix", E.K_PRESSURE_GRADIENT, None, 4, u, p, True),
+                 ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
+                 ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),
+                 ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
+    else:
+        raise ValueError(name)
+    for i, op in enumerate(c.ops):  # normalise params
+        if op[0] in ("matrix", "residual") and op[2] is None:
+            c.ops[i] = (op[0], op[1], [0.0]) + tuple(op[3:])
+    return c
+
+
+def compare(a, b):
+    """a, b = (rowptr, col, val, rhs).  Pattern must be identical; values by the SURVEY 8(d) metric."""
+    pattern_equal = np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    res = dict(pattern_equal=bool(pattern_equal), nnz=int(len(a[1])), n=int(len(a[3])))
+    if pattern_equal:
+        res["val_diff"] = H.csr_rel_diff(a[0], a[2], b[2])
+        res["rhs_diff"] = H.vec_rel_diff(a[3], b[3])
+    return res
+
+
+def run_case(name, n=4, perturb=True, permute=False, register=False, eng=None):
+    c = build_case(name, n, perturb, permute)
+    ref = c.run_oracle(register=register)
+    out = c.run_engine(eng=eng, register=register)
+    return compare(ref, out)
