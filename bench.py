@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the element-assembly hot path (BASELINE.json config 2).
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA engine (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on host cores
+
+Workload (per GPU, weak scaling): 3-D scalar Laplace, Q1 hexahedra, structured 256^3 unit-cube mesh, Dirichlet data
+from the Laplace fundamental solution on the whole boundary, constant body force f = 1, quadrature degree 3 (8 points).
+A "step" is one complete assembly pass: fresh solver (zero matrix values and rhs), stiffness matrix with Dirichlet
+lift, body force.  Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ELEM = 537.2  # conn 32 + slot map 256 + coords 24.28 + CSR values 216.84 + rhs 8.09
+METRIC = "fp64_elements_assembled_per_sec_into_csr"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks and throttle reasons during the timed region"""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.samples, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def fund_sol_laplace(x):
+    d = np.sqrt(((x + 0.5) ** 2).sum(axis=1))
+    return (1.0 / (4.0 * np.pi)) / d
+
+
+def build_workload(n, rank=0, world=1):
+    """structured slab of the (n x n x n*world) mesh owned by `rank`, flat field arrays with global numbering info."""
+    from insilico_b200 import meshgen
+    from insilico_b200 import partition
+    return partition.structured_laplace_slab(n, n, n * world, rank, world, fund_sol_laplace)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference(n_sample, steps, warmup, threads):
+    """the reference's CPU assembly (oracle port, oracle/insilico_oracle.cpp) on an n_sample^3 mesh of the same
+    workload.  Returns (elements/s pre-structured OpenMP, elements/s dynamic single thread, ms/step)."""
+    from oracle import oracle as orc
+    from insilico_b200 import meshgen
+    from insilico_b200 import engine as E
+    coords, conn, _ = meshgen.unit_cube_hex(n_sample, n_sample, n_sample)
+    onb = meshgen.boundary_node_mask(coords)
+    status = onb.astype(np.uint8)[:, None]
+    presc = np.where(onb, fund_sol_laplace(coords), 0.0)[:, None]
+    eqn, ndof = orc.number_dofs(status)
+    prob = orc.Problem(orc.HEX, 1, coords, conn.astype(np.int64))
+    prob.set_field(0, 1, 1, len(coords), conn.astype(np.int64), eqn, status, presc, np.zeros_like(presc))
+    ne = conn.shape[0]
+
+    def step(prestructured):
+        s = orc.System(ndof)
+        t_reg = 0.0
+        if prestructured:
+            t0 = time.perf_counter(); s.register_fields(prob, 0, 0); t_reg = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        s.stiffness(prob, orc.K_LAPLACE, [1.0], 3, 0, 0, True, nthreads=(threads if prestructured else 1))
+        s.bodyforce(prob, [1.0], 3, 0)
+        s.finish()
+        return time.perf_counter() - t0, t_reg
+
+    for _ in range(warmup):
+        step(True)
+    ts = [step(True) for _ in range(steps)]
+    t_pre = sum(t[0] for t in ts) / steps
+    t_reg = sum(t[1] for t in ts) / steps
+    t_dyn = step(False)[0]
+    return ne / t_pre, ne / t_dyn, t_pre * 1e3, t_reg * 1e3, ne
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="elements per direction per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="edge length of the CPU-baseline sample mesh")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ns = args.cpu_sample
+        v_pre, v_dyn, ms, ms_reg, ne = cpu_reference(ns, max(1, args.steps), min(args.warmup, 1), cores)
+        sample = ("%d^3 Q1 hex mesh (%d elements) of the same workload per step; pre-structured triplets + OpenMP "
+                  "%d threads (registerFields %.0f ms excluded); dynamic std::set mode single thread: %.0f elements/s"
+                  % (ns, ne, cores, ms_reg, v_dyn))
+        line = {"impl": "reference", "metric": METRIC, "value": v_pre, "unit": "elements/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2: 3D scalar Laplace Q1 hex structured mesh, stiffness + RHS (CPU sample %d^3)" % ns},
+                "cpu_baseline": {"value": v_pre, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": v_pre, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from insilico_b200 import engine as E
+    from insilico_b200 import partition
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.n
+    wl = build_workload(n, rank, world)
+    eng = E.Engine(local_rank)
+    part = partition.DistributedAssembly(eng, wl, rank, world) if world > 1 else None
+    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
+
+    eng.set_mesh(E.HEX, 1, wl["coords"], wl["conn"])
+    if world > 1:
+        part.setup_fields()
+    else:
+        eng.set_field(0, 1, 1, wl["n_obj"], wl["elem_dof"], wl["eqn"], wl["status"], wl["presc"], wl["values"])
+    n_eqn = wl["n_eqn_local"]
+    eng.new_solver(n_eqn)
+    t0 = time.perf_counter()
+    eng.register_fields(0, 0)
+    if world > 1:
+        part.setup_exchange()
+    eng.synchronize()
+    t_register = time.perf_counter() - t0
+    n_elems_rank = wl["n_owned_elems"]
+
+    def step(events=None):
+        eng.new_solver(n_eqn)
+        if events is not None:
+            events[0].record(stream)
+        eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
+        if events is not None:
+            events[1].record(stream)
+        eng.body_force_computation([1.0], 3, 0)
+        if world > 1:
+            part.exchange()
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_start.record(stream)
+    for k in range(args.steps):
+        step(kev[k])
+    ev_end.record(stream)
+    barrier()
+    launches = eng.kernel_launches - l0
+    ms_total = ev_start.elapsed_time(ev_end)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_elems_rank * world / (ms_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: H2D of coordinates + field state, D2H of values + rhs
+    e2e = None
+    if not args.no_e2e:
+        nnz = eng.finish_assembly()[1]
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        h_coords, h_presc, h_vals = pin(wl["coords"]), pin(wl["presc"]), pin(wl["values"])
+        h_val = torch.empty(nnz, dtype=torch.float64).pin_memory().numpy()
+        h_rhs = torch.empty(n_eqn, dtype=torch.float64).pin_memory().numpy()
+
+        def e2e_step():
+            eng.update_coords(h_coords)
+            eng.update_field(0, prescribed=h_presc, values=h_vals)
+            step()
+            eng.get_csr(None, None, h_val, h_rhs)   # synchronises
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(2, min(args.steps, 5))
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / ke
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_elems_rank * world / dt, "unit": "elements/s",
+               "h2d_bytes_per_step": int(h_coords.nbytes + h_presc.nbytes + h_vals.nbytes),
+               "d2h_bytes_per_step": int(h_val.nbytes + h_rhs.nbytes), "ms_per_step": dt * 1e3,
+               "what": "isl_mesh_update_coords + isl_field_update (pinned H2D), isl_system_create, isl_assemble_matrix, "
+                       "isl_assemble_bodyforce, isl_finish, isl_get_csr values+rhs (pinned D2H); pattern cached"}
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_ELEM * n_elems_rank / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_q1hex_laplace_bytes_per_launch_256")
+    except Exception:
+        pass
+    line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 3D scalar Laplace Q1 hex, structured %d^3 mesh per GPU, stiffness + RHS "
+                                   "(Dirichlet lift + constant body force), quadrature degree 3" % n,
+                       "n_elems_per_gpu": int(n_elems_rank), "n_eqn_per_gpu": int(n_eqn),
+                       "nnz_per_gpu": int(eng.finish_assembly()[1]),
+                       "partition": "z-slabs by element blocks, owned row ranges" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: %.1f GB touched per step, no flush needed"
+                             % (ALGO_BYTES_PER_ELEM * n_elems_rank / 1e9),
+                       "register_fields_ms": t_register * 1e3},
+            "achieved_hbm_gbs": ALGO_BYTES_PER_ELEM * value / world / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_q1hex_laplace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}
+    if not args.no_cpu_baseline:
+        ns = args.cpu_sample
+        v_pre, v_dyn, ms, ms_reg, ne = cpu_reference(ns, 2, 1, cores)
+        line["cpu_baseline"] = {
+            "value": v_pre, "unit": "elements/s", "cores": cores, "kind": "port",
+            "sample": "%d^3 mesh (%d elements) of the same workload, oracle port of the reference: pre-structured "
+                      "triplets + OpenMP %d threads %.0f ms/pass (registerFields %.0f ms excluded); dynamic std::set "
+                      "mode, 1 thread: %.0f elements/s" % (ns, ne, cores, ms, ms_reg, v_dyn)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

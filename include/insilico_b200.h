@@ -95,6 +95,9 @@ int isl_number_dofs(int64_t n_obj, int dof_size, const uint8_t* status, int64_t 
 /* base::Unstructured<SHAPE,GEOMDEG,DIM> (base/Unstructured.hpp:57-65): coords[n_nodes*dim], conn[n_elems*npe] */
 int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes, const double* coords,
                  int64_t n_elems, const int32_t* conn);
+/* multi-GPU element blocks: elements [0, n_owned) are assembled by this engine, the remaining (halo) elements
+ * only contribute to the sparsity pattern of the rows this GPU owns                                         */
+int isl_mesh_set_owned(isl_handle h, int64_t n_owned);
 /* only the nodal coordinates change (moving mesh); pattern and maps stay valid */
 int isl_mesh_update_coords(isl_handle h, const double* coords);
 /* base::Field<FEBasis,DOFSIZE> (base/Field.hpp:50-55) flattened: per DoF component eqn / status / prescribed

@@ -673,6 +673,7 @@ struct isl_engine {
     int64_t launches = 0;
     // mesh
     int shape = 0, geom_deg = 0, dim = 0, npe = 0; int64_t n_nodes = 0, n_elems = 0;
+    int64_t n_owned = 0;  // elements [0, n_owned) are assembled here; the rest (halo) only shape the pattern
     DevBuf<double> coords; DevBuf<int32_t> conn;
     FieldDev fields[5];
     // system
@@ -806,10 +807,10 @@ const int32_t* get_slotmap(isl_engine* h, int t, int c) {
     FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
     build_elem_eqn(h, ft); build_elem_eqn(h, fc);
     const int nr = ft.ndpe * ft.ds, ncl = fc.ndpe * fc.ds;
-    const int64_t n = h->n_elems * nr * ncl;
+    const int64_t n = h->n_owned * nr * ncl;
     auto buf = std::make_unique<DevBuf<int32_t>>();
     buf->alloc(n);
-    ISL_LAUNCH(h, k_slotmap, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_elems, nr, ncl,
+    ISL_LAUNCH(h, k_slotmap, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_owned, nr, ncl,
                h->rowptr.p, h->col.p, buf->p);
     const int32_t* p = buf->p;
     h->slotmaps[key] = std::move(buf);
@@ -851,7 +852,7 @@ void fill_common(isl_engine* h, AsmParams& p, int quad_deg, int t, int c) {
     FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
     ISL_REQUIRE(ft.set && fc.set, "field not set");
     TableDev* td = get_tables(h, quad_deg, t, c);
-    p.coords = h->coords.p; p.conn = h->conn.p; p.n_elems = h->n_elems; p.npe = h->npe;
+    p.coords = h->coords.p; p.conn = h->conn.p; p.n_elems = h->n_owned; p.npe = h->npe;
     p.w = td->w.p; p.dNg = td->dNg.p; p.Ng = td->Ng.p; p.Nt = td->Nt.p; p.dNt = td->dNt.p; p.Nc = td->Nc.p; p.dNc = td->dNc.p;
     p.nq = td->nq; p.nt = ft.ndpe; p.nc = fc.ndpe; p.dst = ft.ds; p.dsc = fc.ds; p.bubnov = (t == c);
     p.ed_t = ft.elem_dof.p; p.ed_c = fc.elem_dof.p; p.eqn_t = ft.eqn.p; p.eqn_c = fc.eqn.p;
@@ -868,7 +869,7 @@ void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
     p.EB = EB;
     const size_t smem = per * EB;
     ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    const int64_t nbatch = (h->n_elems + EB - 1) / EB;
+    const int64_t nbatch = (h->n_owned + EB - 1) / EB;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
     kernel<<<grid, 256, smem, h->stream>>>(p);
     h->launches++;
@@ -1016,13 +1017,20 @@ int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes
         ISL_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
         const isl::Basis G(shape, geom_deg);
         h->shape = shape; h->geom_deg = geom_deg; h->dim = dim; h->npe = G.nfun;
-        h->n_nodes = n_nodes; h->n_elems = n_elems;
+        h->n_nodes = n_nodes; h->n_elems = n_elems; h->n_owned = n_elems;
         upload(h, h->coords, coords, (size_t)n_nodes * dim);
         upload(h, h->conn, conn, (size_t)n_elems * h->npe);
         for (auto& f : h->fields) f.reset();
         h->tables.clear();
         invalidate_pattern(h);
         ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
+    return guarded([&] {
+        ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
+        h->n_owned = n_owned;
+        h->slotmaps.clear();
     });
 }
 int isl_mesh_update_coords(isl_handle h, const double* coords) {
@@ -1116,11 +1124,11 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
             ft.deg == 1 && ft.ds == 1 && ft.dof_is_node && (quad_deg == 2 || quad_deg == 3)) {
             load_q1_tables(h);
             Q1Params q;
-            q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_elems; q.slot = slot;
+            q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_owned; q.slot = slot;
             q.eqn = ft.eqn.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p;
             q.val = h->val.p; q.rhs = h->rhs.p; q.factor = params ? params[0] : 1.0; q.incremental = incremental;
             const int block = 128;
-            const int64_t grid = (h->n_elems + block - 1) / block;
+            const int64_t grid = (h->n_owned + block - 1) / block;
             ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
             return;
         }

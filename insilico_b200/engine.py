@@ -33,7 +33,7 @@ EXPORTED = [
     "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_synchronize", "isl_engine_stream",
     "isl_kernel_launches", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
-    "isl_mesh_update_coords", "isl_field_set", "isl_field_update", "isl_system_create", "isl_pattern_register",
+    "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_update", "isl_system_create", "isl_pattern_register",
     "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_insert_lhs", "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_pack_entries",
     "isl_unpack_add_entries",
@@ -221,6 +221,9 @@ class Engine:
         self.shape, self.geom_deg, self.dim = shape, geom_deg, dim
         self.n_nodes, self.n_elems = n_nodes, n_elems
         _chk(lib().isl_mesh_set(self.h, shape, geom_deg, dim, _i64(n_nodes), _ptr(coords), _i64(n_elems), _ptr(conn)))
+
+    def set_owned_elements(self, n_owned):
+        _chk(lib().isl_mesh_set_owned(self.h, _i64(n_owned)))
 
     def update_coords(self, coords):
         _chk(lib().isl_mesh_update_coords(self.h, _ptr(coords)))
