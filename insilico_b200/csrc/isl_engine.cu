@@ -33,6 +33,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -460,6 +461,8 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
 // slot map with RED.ADD.F64; Dirichlet lift fused.  Tables live in constant memory.
 __constant__ double c_q1_dN[8 * 8 * 3];  // [q][a][d] reference gradients at the 8 Gauss points
 __constant__ double c_q1_w[8];
+__constant__ double c_q1_n1[4];           // [q1d][i] 1-D linear shape values at the two Gauss abscissae
+__constant__ double c_q1_N[8 * 8];       // [q][a] shape-function values at the Gauss points
 
 struct Q1Params {
     const double* coords; const int32_t* conn; int64_t n_elems;
@@ -646,6 +649,8 @@ __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const d
         atomicAdd(dst + idx[i], in[i]);
 }
 
+#include "isl_patch.cuh"
+
 // ---------------------------------------------------------------------------------------------
 struct FieldDev {
     bool set = false;
@@ -684,6 +689,12 @@ struct isl_engine {
     std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
     bool q1_tables_loaded = false;
     DevBuf<double> scratch_d; DevBuf<int> scratch_i;
+    // patch assembly (isl_patch.cuh)
+    std::map<int, std::unique_ptr<PatchSet>> patchsets;  // per field
+    bool val_is_zero = false;   // matrix values known to be zero (fresh solver): complete rows may be stored
+    int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
+    int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
+    int q1_fast = 1;            // sum-factorised local matrix
 
     int grid_for(int64_t n, int block) const {
         const int64_t g = (n + block - 1) / block;
@@ -717,6 +728,7 @@ void upload_vec(isl_engine* h, DevBuf<T>& dst, const std::vector<T>& v) {
 void invalidate_pattern(isl_engine* h) {
     h->pattern_pairs.clear();
     h->slotmaps.clear();
+    h->patchsets.clear();
     h->nnz = 0;
     h->rowptr.release(); h->col.release(); h->val.release();
 }
@@ -788,6 +800,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     h->nnz = nnz;
     h->pattern_pairs = pairs;
     h->slotmaps.clear();
+    h->patchsets.clear();
 }
 
 void ensure_pair(isl_engine* h, int t, int c) {
@@ -903,11 +916,138 @@ void load_q1_tables(isl_engine* h) {
     const isl::Rule R = isl::make_rule(ISL_HEX, 3);
     const isl::Basis B(ISL_HEX, 1);
     std::vector<double> dN(8 * 8 * 3), N(8);
-    for (int q = 0; q < 8; q++) B.eval(&R.p[q * 3], N.data(), &dN[q * 24]);
+    std::vector<double> Nq(64);
+    for (int q = 0; q < 8; q++) { B.eval(&R.p[q * 3], N.data(), &dN[q * 24]); for (int a = 0; a < 8; a++) Nq[q * 8 + a] = N[a]; }
     ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_dN, dN.data(), sizeof(double) * 192, 0, cudaMemcpyHostToDevice, h->stream));
+    ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_N, Nq.data(), sizeof(double) * 64, 0, cudaMemcpyHostToDevice, h->stream));
+    const double g[2] = {R.p[0], R.p[3]};  // 1-D abscissae in table order (point 0 = (g0,g0,g0), point 1 = (g1,g0,g0))
+    const double n1[4] = {1. - g[0], g[0], 1. - g[1], g[1]};
+    ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_n1, n1, sizeof(double) * 4, 0, cudaMemcpyHostToDevice, h->stream));
     ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_w, R.w.data(), sizeof(double) * 8, 0, cudaMemcpyHostToDevice, h->stream));
     ISL_CUDA(cudaStreamSynchronize(h->stream));
     h->q1_tables_loaded = true;
+}
+
+bool qualifies_q1(const isl_engine* h, int t, int c) {
+    const FieldDev& ft = h->fields[t];
+    return h->shape == ISL_HEX && h->geom_deg == 1 && t == c && ft.set && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node;
+}
+
+// build (or fetch) the patch decomposition of a scalar Q1-hex field; returns nullptr when the mesh does not fit
+// the shared-memory accumulator (caller falls back to the atomic kernel)
+PatchSet* get_patchset(isl_engine* h, int field) {
+    auto it = h->patchsets.find(field);
+    if (it != h->patchsets.end()) return it->second->n_patches > 0 ? it->second.get() : nullptr;
+    auto ps = std::make_unique<PatchSet>();
+    PatchSet* out = nullptr;
+    FieldDev& f = h->fields[field];
+    const int64_t n = h->n_owned;
+    build_elem_eqn(h, f);
+    // 1. host copies: element equations / connectivity, CSR row pointer, row positions
+    const int64_t nrow = h->n_eqn;
+    std::vector<int32_t> heqn((size_t)n * 8), hconn((size_t)n * 8), hnode_eqn(h->n_nodes);
+    std::vector<int64_t> hrowptr(h->n_eqn + 1);
+    std::vector<double> hcoords((size_t)h->n_nodes * 3);
+    ISL_CUDA(cudaMemcpyAsync(heqn.data(), f.elem_eqn.p, (size_t)n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaMemcpyAsync(hconn.data(), h->conn.p, (size_t)n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaMemcpyAsync(hrowptr.data(), h->rowptr.p, (h->n_eqn + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaMemcpyAsync(hnode_eqn.data(), f.eqn.p, h->n_nodes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaMemcpyAsync(hcoords.data(), h->coords.p, hcoords.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> rowxyz((size_t)nrow * 3, 0.);
+    std::vector<int32_t> hperm; hperm.reserve(nrow);
+    for (int64_t nd = 0; nd < h->n_nodes; nd++) {
+        const int32_t r = hnode_eqn[nd];
+        if (r < 0) continue;
+        for (int d = 0; d < 3; d++) rowxyz[(size_t)r * 3 + d] = hcoords[(size_t)nd * 3 + d];
+        hperm.push_back(r);
+    }
+    hcoords.clear(); hcoords.shrink_to_fit();
+    // shared memory per CTA: accumulator (27 entries per row on a hex lattice) + coordinates of the patch's nodes
+    // (owned + halo, about (cbrt(R)+2)^3) + row metadata; shrink R until it fits the budget
+    const int smem_budget = (h->patch_ctas_per_sm >= 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024;
+    int rows_per_patch = h->patch_rows, cap_nodes = 0, cap_entries = 0;
+    for (;; rows_per_patch -= 8) {
+        const double c = std::cbrt((double)rows_per_patch) + 2.0;
+        cap_nodes = (int)(c * c * c * 1.1) + 32;
+        cap_entries = (smem_budget - cap_nodes * 28 - rows_per_patch * 24 - 256) / 8;
+        if (cap_entries >= rows_per_patch * 27 || rows_per_patch <= 16) break;
+    }
+    // 2. compact row boxes by recursive coordinate bisection, then the elements of every box (owner computes)
+    const int64_t n_leaves = std::max<int64_t>(1, ((int64_t)hperm.size() + rows_per_patch - 1) / rows_per_patch);
+    std::vector<int64_t> bounds(n_leaves + 1, 0);
+    bounds[n_leaves] = (int64_t)hperm.size();
+    if (!hperm.empty()) rcb_split(hperm.data(), rowxyz.data(), 0, (int64_t)hperm.size(), (int)n_leaves, 0, bounds.data(), 0);
+    rowxyz.clear(); rowxyz.shrink_to_fit();
+    PatchHost P;
+    form_patches(hperm, bounds, heqn, hconn, hrowptr, h->n_eqn, h->n_nodes, cap_entries, cap_nodes, P);
+    const bool fits = P.lattice && P.max_entries <= cap_entries && P.max_nodes <= cap_nodes && P.max_nodes < 65535 && cap_entries > 0;
+    if (fits) {
+        ps->n_patches = (int)P.inst_off.size() - 1;
+        ps->max_entries = P.max_entries; ps->max_rows = P.max_rows; ps->max_nodes = P.max_nodes;
+        ps->n_inst = (int64_t)P.inst_elem.size(); ps->n_elems = n;
+        ps->redundancy = n ? (double)ps->n_inst / (double)n : 0.;
+        upload_vec(h, ps->p_inst_off, P.inst_off); upload_vec(h, ps->p_row_off, P.row_off); upload_vec(h, ps->p_node_off, P.node_off);
+        upload_vec(h, ps->rows, P.rows); upload_vec(h, ps->soff, P.soff); upload_vec(h, ps->nodes, P.nodes);
+        upload_vec(h, ps->i_lnode, P.lnode); upload_vec(h, ps->i_lrow, P.lrow);
+        upload_vec(h, ps->p_run_off, P.run_off); upload_vec(h, ps->run_start, P.run_start); upload_vec(h, ps->run_soff, P.run_soff);
+        DevBuf<int32_t> inst_elem; upload_vec(h, inst_elem, P.inst_elem);
+        ps->i_pos.alloc((size_t)ps->n_inst * 64);
+        DevBuf<int> derr; derr.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_inst_pos, h->grid_for(ps->n_inst * 64, 256), 256, 0, inst_elem.p, f.elem_eqn.p, ps->n_inst, h->rowptr.p, h->col.p,
+                   ps->i_pos.p, derr.p);
+        int err = 0;
+        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        if (!err) out = ps.get(); else ps->n_patches = 0;
+    }
+    if (getenv("ISL_VERBOSE"))
+        fprintf(stderr, "[isl] patches: %d (<= %d rows), max entries %d (cap %d), max nodes %d (cap %d), element instances %.3fx, lattice %d%s\n",
+                (int)P.inst_off.size() - 1, rows_per_patch, P.max_entries, cap_entries, P.max_nodes, cap_nodes,
+                n ? (double)P.inst_elem.size() / (double)n : 0., (int)P.lattice, fits ? "" : " -> atomic fallback");
+    h->patchsets[field] = std::move(ps);
+    return out;
+}
+
+template <bool MATRIX>
+void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor, int incremental, int body, double f0) {
+    PatchParams p;
+    p.coords = h->coords.p;
+    p.p_inst_off = ps->p_inst_off.p; p.p_row_off = ps->p_row_off.p; p.p_node_off = ps->p_node_off.p;
+    p.rows = ps->rows.p; p.soff = ps->soff.p; p.nodes = ps->nodes.p;
+    p.p_run_off = ps->p_run_off.p; p.run_start = ps->run_start.p; p.run_soff = ps->run_soff.p;
+    p.i_lnode = ps->i_lnode.p; p.i_lrow = ps->i_lrow.p; p.i_pos = ps->i_pos.p; p.rowptr = h->rowptr.p;
+    p.status = ft.status.p; p.presc = ft.presc.p; p.values = ft.values.p;
+    p.val = h->val.p; p.rhs = h->rhs.p; p.factor = factor; p.incremental = incremental;
+    p.store_mode = h->val_is_zero ? 1 : 0; p.n_patches = ps->n_patches;
+    p.acc_cap = MATRIX ? ((ps->max_entries + 1) & ~1) : 0; p.row_cap = (ps->max_rows + 1) & ~1; p.node_cap = (ps->max_nodes + 1) & ~1;
+    p.body = body; p.f0 = f0; p.fast = h->q1_fast; p.dbg = getenv("ISL_DBG") ? atoi(getenv("ISL_DBG")) : 0;
+    p.prof = nullptr;
+    static DevBuf<unsigned long long> profbuf;
+    const bool prof = MATRIX && getenv("ISL_PROF");
+    if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
+    const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 +
+                        (size_t)p.node_cap * 4 + 16;
+    if (h->patch_threads == 128 && h->patch_ctas_per_sm >= 3) {
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 3>), ps->n_patches, 128, smem, p);
+    } else if (h->patch_threads == 128) {
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 2>), ps->n_patches, 128, smem, p);
+    } else {
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<256, MATRIX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ISL_LAUNCH(h, (k_q1hex_patch<256, MATRIX, 1>), ps->n_patches, 256, smem, p);
+    }
+    if (prof) {
+        unsigned long long t[8];
+        ISL_CUDA(cudaMemcpyAsync(t, profbuf.p, 64, cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        const char* nm[8] = {"prologue", "zero", "load", "K", "lift", "scatter", "writeout", "total"};
+        fprintf(stderr, "[isl-prof] cycles per patch (thread 0):");
+        for (int i = 0; i < 8; i++) fprintf(stderr, " %s %.0f", nm[i], (double)t[i] / ps->n_patches);
+        fprintf(stderr, "\n");
+    }
 }
 
 }  // namespace
@@ -935,6 +1075,11 @@ int isl_engine_create(int device, isl_handle* out) {
         cudaDeviceProp prop;
         ISL_CUDA(cudaGetDeviceProperties(&prop, device));
         h->n_sm = prop.multiProcessorCount;
+        if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
+        if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
+        if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
+        if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(3, atoi(m)));
         *out = h.release();
     });
 }
@@ -1031,6 +1176,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned;
         h->slotmaps.clear();
+        h->patchsets.clear();
     });
 }
 int isl_mesh_update_coords(isl_handle h, const double* coords) {
@@ -1101,12 +1247,14 @@ int isl_system_create(isl_handle h, int64_t n_eqn) {
         h->sys_pairs.clear();
         if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
         if (h->nnz) ISL_CUDA(cudaMemsetAsync(h->val.p, 0, h->nnz * sizeof(double), h->stream));
+        h->val_is_zero = true;
     });
 }
 int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ensure_pair(h, test_field, trial_field);
+        if (qualifies_q1(h, test_field, trial_field) && h->q1_mode == 1 && get_patchset(h, test_field)) return;
         get_slotmap(h, test_field, trial_field);
     });
 }
@@ -1117,12 +1265,20 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
         ensure_pair(h, t, c);
         check_kernel_fields(h, kid, t, c, true);
-        const int32_t* slot = get_slotmap(h, t, c);
         const FieldDev& ft = h->fields[t];
         // hot path: Q1 hex, scalar Laplace, 2x2x2 rule
-        if ((kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE) && h->shape == ISL_HEX && h->geom_deg == 1 && t == c &&
-            ft.deg == 1 && ft.ds == 1 && ft.dof_is_node && (quad_deg == 2 || quad_deg == 3)) {
+        if ((kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE) && qualifies_q1(h, t, c) && (quad_deg == 2 || quad_deg == 3)) {
             load_q1_tables(h);
+            const double factor = params ? params[0] : 1.0;
+            if (h->q1_mode == 1) {
+                if (PatchSet* ps = get_patchset(h, t)) {
+                    launch_patch<true>(h, ps, ft, factor, incremental, 0, 0.);
+                    h->val_is_zero = false;
+                    return;
+                }
+            }
+            h->val_is_zero = false;
+            const int32_t* slot = get_slotmap(h, t, c);
             Q1Params q;
             q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_owned; q.slot = slot;
             q.eqn = ft.eqn.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p;
@@ -1134,7 +1290,8 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         }
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
-        p.slot = slot; p.kernel_id = kid; p.incremental = incremental;
+        h->val_is_zero = false;
+        p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT);
@@ -1163,6 +1320,15 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ISL_REQUIRE(t >= 0 && t < 5 && h->fields[t].set, "field not set");
+        {
+            const FieldDev& ft = h->fields[t];
+            if (h->q1_mode == 1 && h->shape == ISL_HEX && h->geom_deg == 1 && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node &&
+                (quad_deg == 2 || quad_deg == 3) && h->pattern_pairs.count({t, t})) {
+                load_q1_tables(h);
+                if (PatchSet* ps = get_patchset(h, t)) { launch_patch<false>(h, ps, ft, 0., 0, 1, f[0]); return; }
+            }
+        }
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, t);
         p.body = 1; p.factor = 1.0;
@@ -1174,6 +1340,7 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
 
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols, int n_cols) {
     return guarded([&] {
+        h->val_is_zero = false;
         ISL_REQUIRE(h->nnz > 0, "no pattern registered");
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, "Row index out of bound: " + std::to_string(rows[i]));
         for (int j = 0; j < n_cols; j++) ISL_REQUIRE(cols[j] >= 0 && cols[j] < h->n_eqn, "Col index out of bound: " + std::to_string(cols[j]));

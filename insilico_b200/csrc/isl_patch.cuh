@@ -1,0 +1,709 @@
+// =============================================================================
+// isl_patch.cuh -- owner-computes shared-memory patch assembly for the Q1-hex scalar Laplace hot path
+// (included by isl_engine.cu inside its anonymous namespace, after DevBuf / ISL_CUDA / ISL_REQUIRE).
+//
+// Why (profiles/r1_a_*.md, r1_b_*.md): one thread per element with 64 RED.ADD.F64 per element is bound by the
+// RED issue rate (about 1.3 cycles per lane and SM) and by L2 atomic throughput; a first patch kernel that kept
+// atomics for patch-surface rows and coloured the elements was latency bound (barriers, divergence, gathers).
+//
+// Design: the ROWS of the system are cut into patches of <= R rows along a Morton curve of the row positions.  One
+// CTA owns one patch: it recomputes every element that touches an owned row (halo elements are recomputed by each
+// patch that needs them, about 1.45x the element work) and accumulates the owned rows in shared memory.  Every CSR
+// entry is then written to HBM exactly once with plain row-contiguous stores: no atomics, no memset of the matrix,
+// bit-reproducible results.
+//   * scatter without conflicts and without colouring: in phase a (a = 0..7) every element adds its local row a.
+//     On a lattice-like hex mesh a node is local node a of at most one element, so the threads of a phase touch
+//     distinct rows (checked per patch in the preprocessing; other meshes fall back to the atomic kernel),
+//   * nodal coordinates of the patch are staged in shared memory (one coalesced pass), elements read them by a
+//     uint16 local node index,
+//   * the position of (row a, col b) inside row a is a uint8 (64 B per element instead of a 256 B int32 slot map),
+//   * the local matrix uses q1_K_fast (sum factorisation, about 1.2 k FP64 instructions per element).
+// =============================================================================
+#pragma once
+
+__device__ __host__ __forceinline__ constexpr int sym_idx(int a, int b) {
+    return (a < b) ? (a * 8 - (a * (a - 1)) / 2 + (b - a)) : (b * 8 - (b * (b - 1)) / 2 + (a - b));
+}
+
+struct PatchParams {
+    const double* coords;
+    const int32_t* p_inst_off; const int32_t* p_row_off; const int32_t* p_node_off;
+    const int32_t* rows;      // global row id of every owned local row
+    const uint32_t* soff;     // per patch (nrows+1): offset of the row's entries in the accumulator
+    const int32_t* nodes;     // global node id of every local node
+    const int32_t* p_run_off; const int64_t* run_start; const uint32_t* run_soff;  // maximal runs of consecutive rows: global entry offset, accumulator offset (+ one end offset per patch)
+    const uint16_t* i_lnode;  // [inst][8] local node index
+    const uint16_t* i_lrow;   // [inst][8] local owned-row index or 0xffff
+    const uint8_t* i_pos;     // [inst][64] position of column b inside row a
+    const int64_t* rowptr;
+    const uint8_t* status; const double* presc; const double* values;
+    double* val; double* rhs;
+    double factor; int incremental; int store_mode; int n_patches;
+    int acc_cap, row_cap, node_cap;
+    int body; double f0;  // body force f (scalar field) fused when body != 0
+    int dbg;              // timing experiments only: bit0 skip scatter, bit1 skip write-out, bit2 skip K
+    int fast;             // 1 = sum-factorised local matrix (q1_K_fast), 0 = reference operation order
+    unsigned long long* prof;  // optional per-phase cycle counters (ISL_PROF=1): [prologue, zero, load, K, lift, scatter, writeout, total]
+};
+
+// ---------------------------------------------------------------------------------------------
+// local stiffness matrix of a trilinear hexahedron, 2x2x2 Gauss points, symmetric storage K[36]
+// (a <= b, index a*8 - a(a-1)/2 + (b-a)).  Reference operation order per point:
+// kernel/Laplace.hpp:100-151 with LagrangeShapeFun.hpp:181-202 and geometry.hpp:142-177,419-445.
+__device__ __forceinline__ void q1_K_naive(const double (&X)[8][3], double factor, double (&K)[36], double (&detw)[8]) {
+#pragma unroll
+    for (int k = 0; k < 36; k++) K[k] = 0.;
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        const double* dN = c_q1_dN + q * 24;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int al = 0; al < 3; al++) J[i][al] = fma(X[a][i], dN[a * 3 + al], J[i][al]);
+        double co[3][3];
+        co[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        co[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        co[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        co[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+        co[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+        co[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+        co[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+        co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
+        const double id = 1.0 / det;
+        detw[q] = det * c_q1_w[q];
+        const double scal = factor * det * c_q1_w[q];
+        double g[8][3];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                g[a][r] = (co[r][0] * dN[a * 3] + co[r][1] * dN[a * 3 + 1] + co[r][2] * dN[a * 3 + 2]) * id;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            const double h0 = g[a][0] * scal, h1 = g[a][1] * scal, h2 = g[a][2] * scal;
+#pragma unroll
+            for (int b = a; b < 8; b++, k++) K[k] = fma(h0, g[b][0], fma(h1, g[b][1], fma(h2, g[b][2], K[k])));
+        }
+    }
+}
+
+// det(J) * w at the 8 Gauss points only (body force)
+__device__ __forceinline__ void q1_detw(const double (&X)[8][3], double (&detw)[8]) {
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        const double* dN = c_q1_dN + q * 24;
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int al = 0; al < 3; al++) J[i][al] = fma(X[a][i], dN[a * 3 + al], J[i][al]);
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        detw[q] = det * c_q1_w[q];
+    }
+}
+
+
+
+// ---------------------------------------------------------------------------------------------
+// Same local matrix with far fewer FP64 instructions (about 1.2 k instead of 2.6 k per element), exploiting the
+// tensor-product structure of the trilinear element and of the 2x2x2 Gauss rule:
+//   * dx/dxi depends on (eta,zeta) only, etc.: the three Jacobian columns take 4 distinct values each, obtained by
+//     bilinear interpolation of the 4 edge-difference vectors of that direction,
+//   * K_ab = sum_q sum_{al,be} D_q^{al be} dN_a/dxi_al dN_b/dxi_be with D_q = (factor w_q / det J_q) cof(J_q)^T cof(J_q)
+//     (6 numbers per point); the reference-space gradients are products of 1-D values, so the sums over the points
+//     factorise direction by direction (sum factorisation) into 3 tables of 9 and 3 tables of 12 numbers, from which
+//     every entry is a signed sum of 9 table values.
+// The result differs from the reference operation order by rounding only (checked to 1e-12 against the oracle).
+__device__ __forceinline__ void q1_K_fast(const double (&X)[8][3], double factor, double (&K)[36], double (&detw)[8]) {
+    constexpr int H[8] = {0, 1, 3, 2, 4, 5, 7, 6};   // lexicographic corner i+2j+4k -> hierarchic node
+    constexpr int HI[8] = {0, 1, 1, 0, 0, 1, 1, 0};  // hierarchic node -> (i,j,k)
+    constexpr int HJ[8] = {0, 0, 1, 1, 0, 0, 1, 1};
+    constexpr int HK[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    double n1[2][2], p1[2][3];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        n1[q][0] = c_q1_n1[q * 2]; n1[q][1] = c_q1_n1[q * 2 + 1];
+        p1[q][0] = n1[q][0] * n1[q][0]; p1[q][1] = n1[q][0] * n1[q][1]; p1[q][2] = n1[q][1] * n1[q][1];
+    }
+    // Jacobian columns: c0[qy][qz], c1[qx][qz], c2[qx][qy]
+    double c0[2][2][3], c1[2][2][3], c2[2][2][3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double e0[2][2], e1[2][2], e2[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                e0[u][v] = X[H[1 + 2 * u + 4 * v]][d] - X[H[0 + 2 * u + 4 * v]][d];  // (j=u, k=v)
+                e1[u][v] = X[H[u + 2 + 4 * v]][d] - X[H[u + 0 + 4 * v]][d];          // (i=u, k=v)
+                e2[u][v] = X[H[u + 2 * v + 4]][d] - X[H[u + 2 * v + 0]][d];          // (i=u, j=v)
+            }
+#pragma unroll
+        for (int qa = 0; qa < 2; qa++) {
+            // interpolate in the first free direction at point qa, then in the second at point qb
+            const double a0k0 = n1[qa][0] * e0[0][0] + n1[qa][1] * e0[1][0], a0k1 = n1[qa][0] * e0[0][1] + n1[qa][1] * e0[1][1];
+            const double a1k0 = n1[qa][0] * e1[0][0] + n1[qa][1] * e1[1][0], a1k1 = n1[qa][0] * e1[0][1] + n1[qa][1] * e1[1][1];
+            const double a2j0 = n1[qa][0] * e2[0][0] + n1[qa][1] * e2[1][0], a2j1 = n1[qa][0] * e2[0][1] + n1[qa][1] * e2[1][1];
+#pragma unroll
+            for (int qb = 0; qb < 2; qb++) {
+                c0[qa][qb][d] = n1[qb][0] * a0k0 + n1[qb][1] * a0k1;  // qa = qy, qb = qz
+                c1[qa][qb][d] = n1[qb][0] * a1k0 + n1[qb][1] * a1k1;  // qa = qx, qb = qz
+                c2[qa][qb][d] = n1[qb][0] * a2j0 + n1[qb][1] * a2j1;  // qa = qx, qb = qy
+            }
+        }
+    }
+    double D[6][8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int qx = q & 1, qy = (q >> 1) & 1, qz = q >> 2;
+        double J[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { J[i][0] = c0[qy][qz][i]; J[i][1] = c1[qx][qz][i]; J[i][2] = c2[qx][qy][i]; }
+        double co[3][3];
+        co[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        co[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        co[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        co[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+        co[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+        co[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+        co[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+        co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
+        const double w = c_q1_w[q];
+        detw[q] = det * w;
+        const double s = (factor * w) / det;
+        D[0][q] = s * (co[0][0] * co[0][0] + co[1][0] * co[1][0] + co[2][0] * co[2][0]);
+        D[1][q] = s * (co[0][1] * co[0][1] + co[1][1] * co[1][1] + co[2][1] * co[2][1]);
+        D[2][q] = s * (co[0][2] * co[0][2] + co[1][2] * co[1][2] + co[2][2] * co[2][2]);
+        D[3][q] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
+        D[4][q] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
+        D[5][q] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
+    }
+    auto pr = [](int a, int b) constexpr { return a + b; };                 // pair index 00->0, 01/10->1, 11->2
+    auto sg = [](int a, int b) constexpr { return (a == b) ? 1.0 : -1.0; };  // sigma_a * sigma_b
+    // ---- diagonal terms
+    {   // (0,0): sum over qx first; remaining directions (eta, zeta)
+        double M[3][3];
+        double S[2][2];
+#pragma unroll
+        for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+            for (int qz = 0; qz < 2; qz++) S[qy][qz] = D[0][0 + 2 * qy + 4 * qz] + D[0][1 + 2 * qy + 4 * qz];
+#pragma unroll
+        for (int jj = 0; jj < 3; jj++) {
+            const double t0 = S[0][0] * p1[0][jj] + S[1][0] * p1[1][jj], t1 = S[0][1] * p1[0][jj] + S[1][1] * p1[1][jj];
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++) M[jj][kk] = t0 * p1[0][kk] + t1 * p1[1][kk];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] = sg(HI[a], HI[b]) * M[pr(HJ[a], HJ[b])][pr(HK[a], HK[b])];
+    }
+    {   // (1,1): sum over qy; remaining (xi, zeta)
+        double M[3][3];
+        double S[2][2];
+#pragma unroll
+        for (int qx = 0; qx < 2; qx++)
+#pragma unroll
+            for (int qz = 0; qz < 2; qz++) S[qx][qz] = D[1][qx + 0 + 4 * qz] + D[1][qx + 2 + 4 * qz];
+#pragma unroll
+        for (int ii = 0; ii < 3; ii++) {
+            const double t0 = S[0][0] * p1[0][ii] + S[1][0] * p1[1][ii], t1 = S[0][1] * p1[0][ii] + S[1][1] * p1[1][ii];
+#pragma unroll
+            for (int kk = 0; kk < 3; kk++) M[ii][kk] = t0 * p1[0][kk] + t1 * p1[1][kk];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] += sg(HJ[a], HJ[b]) * M[pr(HI[a], HI[b])][pr(HK[a], HK[b])];
+    }
+    {   // (2,2): sum over qz; remaining (xi, eta)
+        double M[3][3];
+        double S[2][2];
+#pragma unroll
+        for (int qx = 0; qx < 2; qx++)
+#pragma unroll
+            for (int qy = 0; qy < 2; qy++) S[qx][qy] = D[2][qx + 2 * qy] + D[2][qx + 2 * qy + 4];
+#pragma unroll
+        for (int ii = 0; ii < 3; ii++) {
+            const double t0 = S[0][0] * p1[0][ii] + S[1][0] * p1[1][ii], t1 = S[0][1] * p1[0][ii] + S[1][1] * p1[1][ii];
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) M[ii][jj] = t0 * p1[0][jj] + t1 * p1[1][jj];
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] += sg(HK[a], HK[b]) * M[pr(HI[a], HI[b])][pr(HJ[a], HJ[b])];
+    }
+    // ---- mixed terms
+    {   // (0,1): W[i'][j][kk] = sum_q D01 N_i'(xi) N_j(eta) P_kk(zeta)
+        double W[2][2][3];
+#pragma unroll
+        for (int ip = 0; ip < 2; ip++) {
+            double U1[2][2];
+#pragma unroll
+            for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+                for (int qz = 0; qz < 2; qz++)
+                    U1[qy][qz] = D[3][0 + 2 * qy + 4 * qz] * n1[0][ip] + D[3][1 + 2 * qy + 4 * qz] * n1[1][ip];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const double u0 = U1[0][0] * n1[0][j] + U1[1][0] * n1[1][j], u1 = U1[0][1] * n1[0][j] + U1[1][1] * n1[1][j];
+#pragma unroll
+                for (int kk = 0; kk < 3; kk++) W[ip][j][kk] = u0 * p1[0][kk] + u1 * p1[1][kk];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] += sg(HI[a], HJ[b]) * W[HI[b]][HJ[a]][pr(HK[a], HK[b])] +
+                                    sg(HJ[a], HI[b]) * W[HI[a]][HJ[b]][pr(HK[a], HK[b])];
+    }
+    {   // (0,2): W[i'][jj][k] = sum_q D02 N_i'(xi) P_jj(eta) N_k(zeta)
+        double W[2][3][2];
+#pragma unroll
+        for (int ip = 0; ip < 2; ip++) {
+            double U1[2][2];
+#pragma unroll
+            for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+                for (int qz = 0; qz < 2; qz++)
+                    U1[qy][qz] = D[4][0 + 2 * qy + 4 * qz] * n1[0][ip] + D[4][1 + 2 * qy + 4 * qz] * n1[1][ip];
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++) {
+                const double u0 = U1[0][0] * p1[0][jj] + U1[1][0] * p1[1][jj], u1 = U1[0][1] * p1[0][jj] + U1[1][1] * p1[1][jj];
+#pragma unroll
+                for (int k = 0; k < 2; k++) W[ip][jj][k] = u0 * n1[0][k] + u1 * n1[1][k];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] += sg(HI[a], HK[b]) * W[HI[b]][pr(HJ[a], HJ[b])][HK[a]] +
+                                    sg(HK[a], HI[b]) * W[HI[a]][pr(HJ[a], HJ[b])][HK[b]];
+    }
+    {   // (1,2): W[ii][j'][k] = sum_q D12 P_ii(xi) N_j'(eta) N_k(zeta)
+        double W[3][2][2];
+#pragma unroll
+        for (int ii = 0; ii < 3; ii++) {
+            double U1[2][2];
+#pragma unroll
+            for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+                for (int qz = 0; qz < 2; qz++)
+                    U1[qy][qz] = D[5][0 + 2 * qy + 4 * qz] * p1[0][ii] + D[5][1 + 2 * qy + 4 * qz] * p1[1][ii];
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) {
+                const double u0 = U1[0][0] * n1[0][jp] + U1[1][0] * n1[1][jp], u1 = U1[0][1] * n1[0][jp] + U1[1][1] * n1[1][jp];
+#pragma unroll
+                for (int k = 0; k < 2; k++) W[ii][jp][k] = u0 * n1[0][k] + u1 * n1[1][k];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = a; b < 8; b++)
+                K[sym_idx(a, b)] += sg(HJ[a], HK[b]) * W[pr(HI[a], HI[b])][HJ[b]][HK[a]] +
+                                    sg(HK[a], HJ[b]) * W[pr(HI[a], HI[b])][HJ[a]][HK[b]];
+    }
+}
+
+
+// MATRIX = true : stiffness matrix + Dirichlet lift (+ fused body force when p.body)
+// MATRIX = false: body force only
+template <int NT, bool MATRIX, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
+    extern __shared__ double smem[];
+    double* acc = smem;                                            // [acc_cap]
+    double* sX = acc + p.acc_cap;                                  // [node_cap][3]
+    double* srhs = sX + (size_t)p.node_cap * 3;                    // [row_cap]
+    int64_t* srun = reinterpret_cast<int64_t*>(srhs + p.row_cap);     // [row_cap] global entry offset of every run
+    uint32_t* ssoff = reinterpret_cast<uint32_t*>(srun + p.row_cap);  // [row_cap+2]
+    uint32_t* srsoff = ssoff + p.row_cap + 2;                            // [row_cap+2] accumulator offset of every run
+    int32_t* snode = reinterpret_cast<int32_t*>(srsoff + p.row_cap + 2);  // [node_cap]
+    const int tid = threadIdx.x;
+    const int pid = blockIdx.x;
+    long long tk0 = 0, tk = 0;
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define ISL_TICK(slot) do { if (p.prof && tid == 0) { const long long now = clock64(); tacc[slot] += (unsigned long long)(now - tk); tk = now; } } while (0)
+    if (p.prof && tid == 0) { tk0 = tk = clock64(); }
+    const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
+    const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
+    const int e0 = p.p_inst_off[pid], e1 = p.p_inst_off[pid + 1];
+    for (int r = tid; r <= nrows; r += NT) ssoff[r] = p.soff[r0 + pid + r];
+    for (int r = tid; r < nrows; r += NT) srhs[r] = 0.;
+    const int u0 = p.p_run_off[pid], nruns = p.p_run_off[pid + 1] - u0;
+    for (int u = tid; u <= nruns; u += NT) {
+        srsoff[u] = p.run_soff[u0 + pid + u];
+        if (u < nruns) srun[u] = p.run_start[u0 + u];
+    }
+    {   // node ids first (independent loads), then the three coordinates of every node
+        constexpr int U = 8;
+        for (int nb = 0; nb < nnodes; nb += U * NT) {
+            int32_t g[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) { const int n = nb + i * NT + tid; g[i] = (n < nnodes) ? __ldg(p.nodes + n0 + n) : 0; }
+            double x[U][3];
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const double* c = p.coords + (size_t)g[i] * 3;
+                x[i][0] = __ldg(c); x[i][1] = __ldg(c + 1); x[i][2] = __ldg(c + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const int n = nb + i * NT + tid;
+                if (n < nnodes) { snode[n] = g[i]; sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
+            }
+        }
+    }
+    __syncthreads();
+    ISL_TICK(0);
+    if (MATRIX) {
+        const int nent = (int)ssoff[nrows];
+        for (int k = tid; k < nent; k += NT) acc[k] = 0.;
+        __syncthreads();
+    }
+    ISL_TICK(1);
+
+    for (int eb = e0; eb < e1; eb += NT) {
+        const int e = eb + tid;
+        const bool have = e < e1;
+        double K[36]; double detw[8];
+        int lrow[8];
+        double lift[8];
+        bool any_lift = false;
+        uint32_t posw[16];
+#pragma unroll
+        for (int a = 0; a < 8; a++) { lrow[a] = 0xffff; lift[a] = 0.; }
+        if (have) {
+            int ln[8];
+            {
+                const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)e * 8));
+                ln[0] = l4.x & 0xffff; ln[1] = (unsigned)l4.x >> 16; ln[2] = l4.y & 0xffff; ln[3] = (unsigned)l4.y >> 16;
+                ln[4] = l4.z & 0xffff; ln[5] = (unsigned)l4.z >> 16; ln[6] = l4.w & 0xffff; ln[7] = (unsigned)l4.w >> 16;
+                const int4 r4 = __ldg(reinterpret_cast<const int4*>(p.i_lrow + (size_t)e * 8));
+                lrow[0] = r4.x & 0xffff; lrow[1] = (unsigned)r4.x >> 16; lrow[2] = r4.y & 0xffff; lrow[3] = (unsigned)r4.y >> 16;
+                lrow[4] = r4.z & 0xffff; lrow[5] = (unsigned)r4.z >> 16; lrow[6] = r4.w & 0xffff; lrow[7] = (unsigned)r4.w >> 16;
+            }
+            if (MATRIX) {
+                const int4* p4 = reinterpret_cast<const int4*>(p.i_pos + (size_t)e * 64);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int4 v = __ldg(p4 + i);
+                    posw[i * 4] = v.x; posw[i * 4 + 1] = v.y; posw[i * 4 + 2] = v.z; posw[i * 4 + 3] = v.w;
+                }
+            }
+            double X[8][3];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                X[a][0] = sX[ln[a] * 3]; X[a][1] = sX[ln[a] * 3 + 1]; X[a][2] = sX[ln[a] * 3 + 2];
+            }
+            ISL_TICK(2);
+            if (MATRIX) {
+                if (p.dbg & 4) { for (int k = 0; k < 36; k++) K[k] = X[k & 7][k % 3]; for (int q = 0; q < 8; q++) detw[q] = 1.; }
+                else if (p.fast) q1_K_fast(X, p.factor, K, detw); else q1_K_naive(X, p.factor, K, detw);
+            } else q1_detw(X, detw);
+            ISL_TICK(3);
+            // Dirichlet lift: rhs[a] -= g_b K_ab for CONSTRAINED b (assembleMatrix.hpp:56-130).  A node without a
+            // position in row a (pos byte 0xff) is not ACTIVE.
+            if (MATRIX) {
+                bool anyc = false;
+#pragma unroll
+                for (int b = 0; b < 8; b++) anyc |= (((posw[(b * 8 + b) >> 2] >> (((b * 8 + b) & 3) * 8)) & 0xff) == 0xff);
+                if (anyc) {
+                    double gv[8];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        gv[b] = 0.;
+                        const int32_t g = snode[ln[b]];
+                        if (p.status[g] == ISL_CONSTRAINED) gv[b] = p.incremental ? p.presc[g] - p.values[g] : p.presc[g];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 8; a++)
+#pragma unroll
+                        for (int b = 0; b < 8; b++) lift[a] = fma(gv[b], K[sym_idx(a, b)], lift[a]);
+                    any_lift = true;
+                }
+            }
+            if (!MATRIX || p.body) {
+                // f * sum_q N_a(q) w_q detJ_q  (BodyForce.hpp:172-205), added with the opposite sign of the lift
+#pragma unroll
+                for (int a = 0; a < 8; a++) {
+                    double s = 0.;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) s = fma(c_q1_N[q * 8 + a], detw[q], s);
+                    lift[a] -= p.f0 * s;
+                }
+                any_lift = true;
+            }
+        }
+        ISL_TICK(4);
+        // phase a: every element adds its local row a; rows touched in one phase are distinct (lattice property)
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            if (lrow[a] != 0xffff && !(p.dbg & 1)) {
+                if (MATRIX) {
+                    double* row = acc + ssoff[lrow[a]];
+                    double t[8];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                        t[b] = (pos != 0xff) ? row[pos] : 0.;
+                    }
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                        if (pos != 0xff) row[pos] = t[b] + K[sym_idx(a, b)];
+                    }
+                }
+                if (any_lift) srhs[lrow[a]] -= lift[a];
+            }
+            __syncthreads();
+        }
+        ISL_TICK(5);
+    }
+    ISL_TICK(5);
+    // write-out: every owned row exactly once, one warp per row, row-contiguous plain stores
+    if (p.dbg & 2) return;
+    // rhs: one thread per owned row (plain read-modify-write: the row belongs to this CTA alone)
+    for (int r = tid; r < nrows; r += NT) {
+        const double v = srhs[r];
+        if (v != 0.) { const int32_t g = p.rows[r0 + r]; p.rhs[g] += v; }
+    }
+    ISL_TICK(4);  // (prof: rhs loop is booked under "lift")
+    if (MATRIX) {
+        // matrix: maximal runs of consecutive rows are contiguous both in the CSR value array and in the accumulator
+        // one warp per run; the lanes stream the run (independent load/store pairs, unrolled)
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int u = warp; u < nruns; u += NT / 32) {
+            const int64_t gstart = srun[u];
+            const int s0 = (int)srsoff[u], len = (int)srsoff[u + 1] - s0;
+            double* dst = p.val + gstart;
+            const double* src = acc + s0;
+            if (p.store_mode) {
+#pragma unroll 4
+                for (int k = lane; k < len; k += 32) dst[k] = src[k];
+            } else {
+#pragma unroll 4
+                for (int k = lane; k < len; k += 32) dst[k] += src[k];
+            }
+        }
+    }
+    ISL_TICK(6);
+    if (p.prof) {
+        __syncthreads();
+        ISL_TICK(2);  // (prof: the final barrier wait is booked under "load")
+        if (tid == 0) {
+            tacc[7] = (unsigned long long)(clock64() - tk0);
+            for (int i = 0; i < 8; i++) atomicAdd(p.prof + i, tacc[i]);
+        }
+    }
+#undef ISL_TICK
+}
+
+// ---------------------------------------------------------------------------------------------
+// preprocessing
+__device__ __forceinline__ uint64_t morton3(double x, double y, double z) {
+    uint64_t q[3] = {(uint64_t)min(max(x, 0.0), 2097151.0), (uint64_t)min(max(y, 0.0), 2097151.0),
+                     (uint64_t)min(max(z, 0.0), 2097151.0)};
+    uint64_t key = 0;
+    for (int d = 0; d < 3; d++) {
+        uint64_t v = q[d] & 0x1fffff;  // spread 21 bits
+        v = (v | v << 32) & 0x1f00000000ffffull;
+        v = (v | v << 16) & 0x1f0000ff0000ffull;
+        v = (v | v << 8) & 0x100f00f00f00f00full;
+        v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+        v = (v | v << 2) & 0x1249249249249249ull;
+        key |= v << d;
+    }
+    return key;
+}
+// Morton key of every equation = position of the node that carries it (scalar field, DoF id = node id)
+__global__ void k_row_morton_keys(const double* coords, const int32_t* eqn, int64_t n_nodes, double x0, double y0, double z0,
+                                  double sx, double sy, double sz, uint64_t* keys, int32_t* idx) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t r = eqn[n];
+        if (r < 0) continue;
+        const double* x = coords + (size_t)n * 3;
+        keys[r] = morton3((x[0] - x0) * sx, (x[1] - y0) * sy, (x[2] - z0) * sz);
+        idx[r] = r;
+    }
+}
+__global__ void k_minmax3(const double* coords, int64_t n, double* out /* [gridDim][6] */) {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        for (int d = 0; d < 3; d++) { const double v = coords[i * 3 + d]; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v); }
+    for (int d = 0; d < 3; d++)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
+        }
+    __shared__ double s[32][6];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) for (int d = 0; d < 3; d++) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++)
+            for (int d = 0; d < 3; d++) { s[0][d] = fmin(s[0][d], s[k][d]); s[0][3 + d] = fmax(s[0][3 + d], s[k][3 + d]); }
+        for (int d = 0; d < 6; d++) out[blockIdx.x * 6 + d] = s[0][d];
+    }
+}
+// per element instance: uint8 position of column b inside row a (0xff when row or column is not ACTIVE)
+__global__ void k_inst_pos(const int32_t* inst_elem, const int32_t* elem_eqn, int64_t n_inst, const int64_t* rowptr,
+                           const int32_t* col, uint8_t* i_pos, int* err) {
+    const int64_t total = n_inst * 64;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ip = t >> 6; const int ab = (int)(t & 63), a = ab >> 3, b = ab & 7;
+        const int64_t e = inst_elem[ip];
+        const int32_t r = elem_eqn[e * 8 + a], c = elem_eqn[e * 8 + b];
+        uint8_t pos = 0xff;
+        if (r >= 0 && c >= 0) {
+            const int64_t s = find_in_row(rowptr, col, r, c);
+            const int64_t d = s - rowptr[r];
+            if (s < 0 || d > 254) { *err = 1; } else pos = (uint8_t)d;
+        }
+        i_pos[t] = pos;
+    }
+}
+
+struct PatchSet {
+    int n_patches = 0, max_entries = 0, max_rows = 0, max_nodes = 0;
+    int64_t n_inst = 0, n_elems = 0;
+    DevBuf<int32_t> p_inst_off, p_row_off, p_node_off, p_run_off, rows, nodes;
+    DevBuf<uint32_t> soff, run_soff;
+    DevBuf<int64_t> run_start;
+    DevBuf<uint16_t> i_lnode, i_lrow;
+    DevBuf<uint8_t> i_pos;
+    double redundancy = 0.;
+};
+
+struct PatchHost {
+    std::vector<int32_t> inst_off{0}, row_off{0}, node_off{0}, run_off{0}, rows, nodes, inst_elem;
+    std::vector<uint32_t> soff, run_soff;
+    std::vector<int64_t> run_start;
+    std::vector<uint16_t> lnode, lrow;
+    int max_entries = 0, max_rows = 0, max_nodes = 0;
+    bool lattice = true;
+};
+
+// rows in Morton order are cut into patches of <= rows_per_patch rows / cap_entries matrix entries; each patch lists
+// every element touching one of its rows (owner computes)
+// recursive coordinate bisection of the rows into `leaves` compact boxes of (almost) equal size; idx is permuted in
+// place, leaf k covers idx[bounds[k] .. bounds[k+1])
+inline void rcb_split(int32_t* idx, const double* xyz, int64_t lo, int64_t hi, int leaves, int64_t leaf0, int64_t* bounds,
+                      int depth) {
+    if (leaves <= 1) { bounds[leaf0] = lo; std::sort(idx + lo, idx + hi); return; }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int64_t k = lo; k < hi; k++)
+        for (int d = 0; d < 3; d++) { const double v = xyz[(size_t)idx[k] * 3 + d]; mn[d] = std::min(mn[d], v); mx[d] = std::max(mx[d], v); }
+    int d = 0;
+    if (mx[1] - mn[1] > mx[d] - mn[d]) d = 1;
+    if (mx[2] - mn[2] > mx[d] - mn[d]) d = 2;
+    const int l1 = leaves / 2;
+    const int64_t mid = lo + (hi - lo) * l1 / leaves;
+    std::nth_element(idx + lo, idx + mid, idx + hi, [&](int32_t a, int32_t b) {
+        const double va = xyz[(size_t)a * 3 + d], vb = xyz[(size_t)b * 3 + d];
+        return va < vb || (va == vb && a < b);
+    });
+    if (depth < 4) {
+        std::thread t([=] { rcb_split(idx, xyz, lo, mid, l1, leaf0, bounds, depth + 1); });
+        rcb_split(idx, xyz, mid, hi, leaves - l1, leaf0 + l1, bounds, depth + 1);
+        t.join();
+    } else {
+        rcb_split(idx, xyz, lo, mid, l1, leaf0, bounds, depth + 1);
+        rcb_split(idx, xyz, mid, hi, leaves - l1, leaf0 + l1, bounds, depth + 1);
+    }
+}
+
+inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector<int64_t>& leaf_bounds,
+                         const std::vector<int32_t>& eqn /* [n][8] */,
+                         const std::vector<int32_t>& conn /* [n][8] */, const std::vector<int64_t>& rowptr, int64_t n_eqn,
+                         int64_t n_nodes, int cap_entries, int cap_nodes, PatchHost& P) {
+    const int64_t n = (int64_t)eqn.size() / 8;
+    // row -> incident (element, local index) lists
+    std::vector<int64_t> adj_ptr(n_eqn + 1, 0);
+    for (int64_t k = 0; k < n * 8; k++) if (eqn[k] >= 0) adj_ptr[eqn[k] + 1]++;
+    for (int64_t r = 0; r < n_eqn; r++) adj_ptr[r + 1] += adj_ptr[r];
+    std::vector<int32_t> adj(adj_ptr[n_eqn]);
+    {
+        std::vector<int64_t> cur(adj_ptr.begin(), adj_ptr.end() - 1);
+        for (int64_t e = 0; e < n; e++)
+            for (int a = 0; a < 8; a++) { const int32_t g = eqn[e * 8 + a]; if (g >= 0) adj[cur[g]++] = (int32_t)e; }
+    }
+    std::vector<int32_t> row_stamp(n_eqn, -1), row_l(n_eqn, 0), el_stamp(n, -1), node_stamp(n_nodes, -1), node_l(n_nodes, 0);
+    std::vector<uint8_t> amask;
+    int pid = 0;
+    const int64_t n_leaves = (int64_t)leaf_bounds.size() - 1;
+    for (int64_t leaf = 0; leaf < n_leaves; leaf++) {
+        // rows of this patch
+        const size_t rbase = P.rows.size();
+        int entries = 0, nrows = 0;
+        for (int64_t k = leaf_bounds[leaf]; k < leaf_bounds[leaf + 1]; k++) {
+            const int32_t g = row_perm[k];
+            const int nnz = (int)(rowptr[g + 1] - rowptr[g]);
+            row_stamp[g] = pid; row_l[g] = nrows;
+            P.rows.push_back(g); P.soff.push_back((uint32_t)entries);
+            entries += nnz; nrows++;
+        }
+        if (nrows == 0) continue;
+        P.soff.push_back((uint32_t)entries);
+        {   // runs of consecutive global rows (rows are sorted by global id inside a patch)
+            int32_t prev = -2;
+            for (int r = 0; r < nrows; r++) {
+                const int32_t g = P.rows[rbase + r];
+                if (g != prev + 1) { P.run_start.push_back(rowptr[g]); P.run_soff.push_back(P.soff[P.soff.size() - 1 - nrows + r]); }
+                prev = g;
+            }
+            P.run_soff.push_back((uint32_t)entries);
+            P.run_off.push_back((int32_t)P.run_start.size());
+        }
+        amask.assign(nrows, 0);
+        // elements touching those rows, nodes of those elements
+        int nnodes = 0;
+        for (int r = 0; r < nrows; r++) {
+            const int32_t g = P.rows[rbase + r];
+            for (int64_t j = adj_ptr[g]; j < adj_ptr[g + 1]; j++) {
+                const int32_t e = adj[j];
+                if (el_stamp[e] == pid) continue;
+                el_stamp[e] = pid;
+                P.inst_elem.push_back(e);
+                for (int a = 0; a < 8; a++) {
+                    const int32_t nd = conn[(size_t)e * 8 + a];
+                    if (node_stamp[nd] != pid) { node_stamp[nd] = pid; node_l[nd] = nnodes++; P.nodes.push_back(nd); }
+                    P.lnode.push_back((uint16_t)node_l[nd]);
+                    const int32_t ge = eqn[(size_t)e * 8 + a];
+                    if (ge >= 0 && row_stamp[ge] == pid) {
+                        const int l = row_l[ge];
+                        P.lrow.push_back((uint16_t)l);
+                        if (amask[l] & (1u << a)) P.lattice = false;  // two elements see this row as local row a
+                        amask[l] |= (uint8_t)(1u << a);
+                    } else P.lrow.push_back((uint16_t)0xffff);
+                }
+            }
+        }
+        P.inst_off.push_back((int32_t)P.inst_elem.size());
+        P.row_off.push_back((int32_t)P.rows.size());
+        P.node_off.push_back((int32_t)P.nodes.size());
+        P.max_entries = std::max(P.max_entries, entries);
+        P.max_rows = std::max(P.max_rows, nrows);
+        P.max_nodes = std::max(P.max_nodes, nnodes);
+        pid++;
+    }
+    (void)cap_nodes; (void)cap_entries;
+}

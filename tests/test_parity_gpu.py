@@ -152,3 +152,31 @@ def test_large_mesh_properties(eng):
     rp3, col3, val3, rhs3 = c.run_engine(eng=eng)
     assert np.array_equal(rp, rp3) and np.array_equal(col, col3)
     assert H.csr_rel_diff(rp, 3.0 * val, val3) <= 1e-12 and H.vec_rel_diff(3.0 * rhs, rhs3) <= 1e-12
+
+
+@pytest.mark.parametrize("env", [{"ISL_Q1_MODE": "atomic"}, {"ISL_Q1_FAST": "0"}, {"ISL_PATCH_ROWS": "64"},
+                                 {"ISL_PATCH_ROWS": "200", "ISL_PATCH_THREADS": "256"}, {"ISL_PATCH_ROWS": "360"},
+                                 {"ISL_PATCH_ROWS": "512", "ISL_PATCH_THREADS": "256", "ISL_PATCH_CTAS": "1"}])
+@pytest.mark.parametrize("name,n,permute", [("laplace_q1_hex", 13, False), ("laplace_q1_hex_values", 9, True)])
+def test_q1_hot_path_variants(monkeypatch, env, name, n, permute):
+    """one-thread-per-element atomic kernel and shared-memory patch kernel (several patch sizes, Morton ordering of a
+    permuted element list) all reproduce the oracle; accumulation into a non-empty matrix (second assembly call in the
+    same solver) takes the read-modify-write path of complete rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    e = E.Engine(0)
+    try:
+        c = flows.build_case(name, n, True, permute)
+        ref = c.run_oracle()
+        out = c.run_engine(eng=e)
+        r = flows.compare(ref, out)
+        assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+        # assemble the matrix twice into the same solver: K doubles, lift doubles
+        ops = c.ops
+        c.ops = [ops[0], ops[0]]
+        ref2 = c.run_oracle()
+        out2 = c.run_engine(eng=e)
+        r2 = flows.compare(ref2, out2)
+        assert r2["pattern_equal"] and r2["val_diff"] <= TOL and r2["rhs_diff"] <= TOL, r2
+    finally:
+        e.close()
