@@ -964,23 +964,30 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     }
     hcoords.clear(); hcoords.shrink_to_fit();
     // shared memory per CTA: accumulator (27 entries per row on a hex lattice) + coordinates of the patch's nodes
-    // (owned + halo, about (cbrt(R)+2)^3) + row metadata; shrink R until it fits the budget
+    // (owned + halo) + row metadata.  R is shrunk until the estimate fits the budget; if the real patches still
+    // overflow (irregular boxes) the partition is redone with a smaller R.
     const int smem_budget = (h->patch_ctas_per_sm >= 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024;
     int rows_per_patch = h->patch_rows, cap_nodes = 0, cap_entries = 0;
-    for (;; rows_per_patch -= 8) {
-        const double c = std::cbrt((double)rows_per_patch) + 2.0;
-        cap_nodes = (int)(c * c * c * 1.1) + 32;
-        cap_entries = (smem_budget - cap_nodes * 28 - rows_per_patch * 24 - 256) / 8;
-        if (cap_entries >= rows_per_patch * 27 || rows_per_patch <= 16) break;
-    }
-    // 2. compact row boxes by recursive coordinate bisection, then the elements of every box (owner computes)
-    const int64_t n_leaves = std::max<int64_t>(1, ((int64_t)hperm.size() + rows_per_patch - 1) / rows_per_patch);
-    std::vector<int64_t> bounds(n_leaves + 1, 0);
-    bounds[n_leaves] = (int64_t)hperm.size();
-    if (!hperm.empty()) rcb_split(hperm.data(), rowxyz.data(), 0, (int64_t)hperm.size(), (int)n_leaves, 0, bounds.data(), 0);
-    rowxyz.clear(); rowxyz.shrink_to_fit();
     PatchHost P;
-    form_patches(hperm, bounds, heqn, hconn, hrowptr, h->n_eqn, h->n_nodes, cap_entries, cap_nodes, P);
+    for (int attempt = 0; attempt < 4; attempt++) {
+        for (;; rows_per_patch -= 8) {
+            const double c = std::cbrt((double)rows_per_patch) + 2.0;
+            cap_nodes = (int)(c * c * c * 1.35) + 32;
+            cap_entries = (smem_budget - cap_nodes * 24 - rows_per_patch * 24 - 256) / 8;
+            if (cap_entries >= rows_per_patch * 27 || rows_per_patch <= 16) break;
+        }
+        // compact row boxes by recursive coordinate bisection, then the elements of every box (owner computes)
+        std::vector<int32_t> perm_try = hperm;
+        const int64_t n_leaves = std::max<int64_t>(1, ((int64_t)perm_try.size() + rows_per_patch - 1) / rows_per_patch);
+        std::vector<int64_t> bounds(n_leaves + 1, 0);
+        bounds[n_leaves] = (int64_t)perm_try.size();
+        if (!perm_try.empty()) rcb_split(perm_try.data(), rowxyz.data(), 0, (int64_t)perm_try.size(), (int)n_leaves, 0, bounds.data(), 0);
+        P = PatchHost();
+        form_patches(perm_try, bounds, heqn, hconn, hrowptr, h->n_eqn, h->n_nodes, cap_entries, cap_nodes, P);
+        if (!P.lattice || (P.max_entries <= cap_entries && P.max_nodes <= cap_nodes) || rows_per_patch <= 16) break;
+        rows_per_patch = (int)(rows_per_patch * 0.88);
+    }
+    rowxyz.clear(); rowxyz.shrink_to_fit();
     const bool fits = P.lattice && P.max_entries <= cap_entries && P.max_nodes <= cap_nodes && P.max_nodes < 65535 && cap_entries > 0;
     if (fits) {
         ps->n_patches = (int)P.inst_off.size() - 1;
@@ -1027,8 +1034,7 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     static DevBuf<unsigned long long> profbuf;
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
-    const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 +
-                        (size_t)p.node_cap * 4 + 16;
+    const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
     if (h->patch_threads == 128 && h->patch_ctas_per_sm >= 3) {
         ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 3>), ps->n_patches, 128, smem, p);

@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
     int64_t* srun = reinterpret_cast<int64_t*>(srhs + p.row_cap);     // [row_cap] global entry offset of every run
     uint32_t* ssoff = reinterpret_cast<uint32_t*>(srun + p.row_cap);  // [row_cap+2]
     uint32_t* srsoff = ssoff + p.row_cap + 2;                            // [row_cap+2] accumulator offset of every run
-    int32_t* snode = reinterpret_cast<int32_t*>(srsoff + p.row_cap + 2);  // [node_cap]
     const int tid = threadIdx.x;
     const int pid = blockIdx.x;
     long long tk0 = 0, tk = 0;
@@ -368,7 +367,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
 #pragma unroll
             for (int i = 0; i < U; i++) {
                 const int n = nb + i * NT + tid;
-                if (n < nnodes) { snode[n] = g[i]; sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
+                if (n < nnodes) { sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
             }
         }
     }
@@ -431,7 +430,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
 #pragma unroll
                     for (int b = 0; b < 8; b++) {
                         gv[b] = 0.;
-                        const int32_t g = snode[ln[b]];
+                        const int32_t g = __ldg(p.nodes + n0 + ln[b]);
                         if (p.status[g] == ISL_CONSTRAINED) gv[b] = p.incremental ? p.presc[g] - p.values[g] : p.presc[g];
                     }
 #pragma unroll

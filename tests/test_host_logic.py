@@ -144,3 +144,18 @@ def test_oracle_symmetry_and_rigid_body_nullspace():
     A = sp.csr_matrix((val, col, rp))
     assert abs(A - A.T).max() < 1e-15
     assert np.abs(A @ np.ones(A.shape[0])).max() < 1e-14
+
+
+def test_cpp_facade_example_builds_and_fails_loudly_without_gpu():
+    """include/insilico_b200.hpp (reference template API surface) compiles and links; without a GPU the engine
+    aborts with the VERIFY_MSG-style message instead of falling back to the CPU."""
+    import subprocess
+    import torch
+    import __graft_entry__ as g
+    g.build()
+    exe = os.path.join(H.ROOT, "examples", "heat_dirichlet")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([exe, "4"], capture_output=True, text=True)
+    assert out.returncode != 0 and "no CUDA device available" in out.stderr

@@ -180,3 +180,21 @@ def test_q1_hot_path_variants(monkeypatch, env, name, n, permute):
         assert r2["pattern_equal"] and r2["val_diff"] <= TOL and r2["rhs_diff"] <= TOL, r2
     finally:
         e.close()
+
+
+def test_cpp_facade_example_matches_python_flow(eng):
+    """examples/heat_dirichlet.cpp drives the engine through include/insilico_b200.hpp with the reference's call
+    sequence; its system equals the one of the Python flow (and therefore the oracle's)."""
+    import os
+    import subprocess
+    exe = os.path.join(H.ROOT, "examples", "heat_dirichlet")
+    out = subprocess.run([exe, "7"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    ndof, nnz, norm, total = out.stdout.split()
+    c = flows.build_case("laplace_q1_hex", 7, perturb=False)
+    c.ops = c.ops[:1]
+    rp, col, val, rhs = c.run_engine(eng=eng)
+    ref = c.run_oracle()
+    assert int(ndof) == len(rhs) and int(nnz) == len(val)
+    assert float(norm) == pytest.approx(np.linalg.norm(ref[3]) / len(rhs), rel=1e-12)
+    assert float(total) == pytest.approx(ref[2].sum(), rel=1e-9, abs=1e-9 * np.abs(ref[2]).max())
