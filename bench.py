@@ -184,10 +184,12 @@ def main():
         eng.new_solver(n_eqn)
         if events is not None:
             events[0].record(stream)
+        # the engine defers the launch of the stiffness kernel by one call: the body force on the same field is fused
+        # into the same pass over the elements, so the dominant kernel is timed around both calls
         eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
+        eng.body_force_computation([1.0], 3, 0)
         if events is not None:
             events[1].record(stream)
-        eng.body_force_computation([1.0], 3, 0)
         if world > 1:
             part.exchange()
 
@@ -282,7 +284,7 @@ def main():
                              % (ALGO_BYTES_PER_ELEM * n_elems_rank / 1e9),
                        "register_fields_ms": t_register * 1e3},
             "achieved_hbm_gbs": ALGO_BYTES_PER_ELEM * value / world / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "k_q1hex_laplace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_q1hex_patch (stiffness + Dirichlet lift + body force, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}

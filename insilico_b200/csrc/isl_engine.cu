@@ -692,9 +692,12 @@ struct isl_engine {
     // patch assembly (isl_patch.cuh)
     std::map<int, std::unique_ptr<PatchSet>> patchsets;  // per field
     bool val_is_zero = false;   // matrix values known to be zero (fresh solver): complete rows may be stored
+    bool val_zero_pending = false;  // the memset of val has been postponed (a store-mode patch launch makes it unnecessary)
+    struct PendingQ1 { bool active = false; int field = 0; double factor = 1.; int incremental = 1; } pending_q1;
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
     int q1_fast = 1;            // sum-factorised local matrix
+    int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
 
     int grid_for(int64_t n, int block) const {
         const int64_t g = (n + block - 1) / block;
@@ -710,6 +713,10 @@ namespace {
         (eng)->launches++;                                                    \
         ISL_CUDA(cudaGetLastError());                                         \
     } while (0)
+
+void materialize_zero(isl_engine* h);
+void flush_pending(isl_engine* h, int fuse_body, double f0);
+inline void flush_pending(isl_engine* h) { flush_pending(h, 0, 0.); }
 
 template <class T>
 void upload(isl_engine* h, DevBuf<T>& dst, const T* src, size_t n) {
@@ -744,6 +751,7 @@ void build_elem_eqn(isl_engine* h, FieldDev& f) {
 void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
     ISL_REQUIRE(h->n_eqn < (int64_t)1 << 31, "more than 2^31 equations are not supported");
+    materialize_zero(h);  // values of the old layout are carried over
     int64_t total = 0;
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
@@ -1056,6 +1064,27 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     }
 }
 
+// the memset of the matrix values is postponed at isl_system_create; whoever accumulates into val materialises it
+void materialize_zero(isl_engine* h) {
+    if (h->val_zero_pending && h->nnz) ISL_CUDA(cudaMemsetAsync(h->val.p, 0, h->nnz * sizeof(double), h->stream));
+    h->val_zero_pending = false;
+}
+
+// launch of the Q1 patch matrix kernel is deferred by one call so that an immediately following body force on the same
+// field is fused into the same pass over the elements (the reference application order: stiffness, then body force)
+void flush_pending(isl_engine* h, int fuse_body, double f0) {
+    if (!h->pending_q1.active) return;
+    h->pending_q1.active = false;
+    const int t = h->pending_q1.field;
+    PatchSet* ps = get_patchset(h, t);
+    ISL_REQUIRE(ps, "internal: deferred patch launch without a patch set");
+    const bool full_store = h->val_is_zero && h->pattern_pairs.size() == 1;
+    if (full_store) h->val_zero_pending = false;  // every entry is written by a plain store
+    else materialize_zero(h);
+    launch_patch<true>(h, ps, h->fields[t], h->pending_q1.factor, h->pending_q1.incremental, fuse_body, f0);
+    h->val_is_zero = false;
+}
+
 }  // namespace
 
 // =============================================================================
@@ -1083,6 +1112,7 @@ int isl_engine_create(int device, isl_handle* out) {
         h->n_sm = prop.multiProcessorCount;
         if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
         if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(3, atoi(m)));
@@ -1099,7 +1129,7 @@ int isl_engine_destroy(isl_handle h) {
         cudaStreamDestroy(s);
     });
 }
-int isl_synchronize(isl_handle h) { return guarded([&] { ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
+int isl_synchronize(isl_handle h) { return guarded([&] { flush_pending(h); ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
 void* isl_engine_stream(isl_handle h) { return (void*)h->stream; }
 int64_t isl_kernel_launches(isl_handle h) { return h->launches; }
 
@@ -1163,6 +1193,7 @@ int isl_number_dofs(int64_t n_obj, int dof_size, const uint8_t* status, int64_t 
 int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes, const double* coords, int64_t n_elems,
                  const int32_t* conn) {
     return guarded([&] {
+        flush_pending(h);
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(dim == isl::shape_dim(shape), "only DIM == shape dimension is supported (no manifolds)");
         ISL_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
@@ -1179,6 +1210,7 @@ int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes
 }
 int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
     return guarded([&] {
+        flush_pending(h);
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned;
         h->slotmaps.clear();
@@ -1187,6 +1219,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
 }
 int isl_mesh_update_coords(isl_handle h, const double* coords) {
     return guarded([&] {
+        flush_pending(h);
         ISL_REQUIRE(h->n_nodes > 0, "mesh not set");
         ISL_CUDA(cudaMemcpyAsync(h->coords.p, coords, (size_t)h->n_nodes * h->dim * sizeof(double), cudaMemcpyDefault, h->stream));
     });
@@ -1194,6 +1227,7 @@ int isl_mesh_update_coords(isl_handle h, const double* coords) {
 int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_obj, const int32_t* elem_dof,
                   const int64_t* eqn, const uint8_t* status, const double* prescribed, const double* values) {
     return guarded([&] {
+        flush_pending(h);
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(field >= 0 && field < 5, "field index out of range (0..4)");
         ISL_REQUIRE(h->n_elems > 0, "mesh must be set before fields");
@@ -1236,6 +1270,7 @@ int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_o
 }
 int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values) {
     return guarded([&] {
+        flush_pending(h);
         ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
         FieldDev& f = h->fields[field];
         const size_t bytes = (size_t)f.n_obj * f.ds * sizeof(double);
@@ -1249,15 +1284,17 @@ int isl_system_create(isl_handle h, int64_t n_eqn) {
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(n_eqn >= 0, "negative system size");
+        h->pending_q1.active = false;  // a fresh solver discards what was queued for the old one
         if (n_eqn != h->n_eqn) { invalidate_pattern(h); h->n_eqn = n_eqn; h->rhs.alloc(n_eqn); }
         h->sys_pairs.clear();
         if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
-        if (h->nnz) ISL_CUDA(cudaMemsetAsync(h->val.p, 0, h->nnz * sizeof(double), h->stream));
+        h->val_zero_pending = true;   // memset of the matrix values postponed, see materialize_zero()
         h->val_is_zero = true;
     });
 }
 int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
     return guarded([&] {
+        flush_pending(h);
         ISL_CUDA(cudaSetDevice(h->device));
         ensure_pair(h, test_field, trial_field);
         if (qualifies_q1(h, test_field, trial_field) && h->q1_mode == 1 && get_patchset(h, test_field)) return;
@@ -1269,6 +1306,7 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        flush_pending(h);
         ensure_pair(h, t, c);
         check_kernel_fields(h, kid, t, c, true);
         const FieldDev& ft = h->fields[t];
@@ -1277,12 +1315,14 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
             load_q1_tables(h);
             const double factor = params ? params[0] : 1.0;
             if (h->q1_mode == 1) {
-                if (PatchSet* ps = get_patchset(h, t)) {
-                    launch_patch<true>(h, ps, ft, factor, incremental, 0, 0.);
-                    h->val_is_zero = false;
+                if (get_patchset(h, t)) {
+                    h->pending_q1.active = true; h->pending_q1.field = t; h->pending_q1.factor = factor;
+                    h->pending_q1.incremental = incremental;
+                    if (!h->defer_launch) flush_pending(h);
                     return;
                 }
             }
+            materialize_zero(h);
             h->val_is_zero = false;
             const int32_t* slot = get_slotmap(h, t, c);
             Q1Params q;
@@ -1296,6 +1336,7 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         }
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
+        materialize_zero(h);
         h->val_is_zero = false;
         p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
@@ -1310,6 +1351,7 @@ int isl_assemble_residual(isl_handle h, int kid, const double* params, int quad_
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        flush_pending(h);
         check_kernel_fields(h, kid, t, c, false);
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
@@ -1332,9 +1374,12 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
             if (h->q1_mode == 1 && h->shape == ISL_HEX && h->geom_deg == 1 && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node &&
                 (quad_deg == 2 || quad_deg == 3) && h->pattern_pairs.count({t, t})) {
                 load_q1_tables(h);
+                if (h->pending_q1.active && h->pending_q1.field == t) { flush_pending(h, 1, f[0]); return; }
+                flush_pending(h);
                 if (PatchSet* ps = get_patchset(h, t)) { launch_patch<false>(h, ps, ft, 0., 0, 1, f[0]); return; }
             }
         }
+        flush_pending(h);
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, t);
         p.body = 1; p.factor = 1.0;
@@ -1346,6 +1391,8 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
 
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols, int n_cols) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         h->val_is_zero = false;
         ISL_REQUIRE(h->nnz > 0, "no pattern registered");
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, "Row index out of bound: " + std::to_string(rows[i]));
@@ -1363,6 +1410,7 @@ int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_r
 }
 int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_rows) {
     return guarded([&] {
+        flush_pending(h);
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, std::to_string(rows[i]) + " out of bound");
         DevBuf<double> dv; DevBuf<int64_t> dr;
         upload(h, dv, vec, n_rows); upload(h, dr, rows, n_rows);
@@ -1373,6 +1421,8 @@ int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_r
 
 int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         ISL_CUDA(cudaSetDevice(h->device));
         if (h->sys_pairs != h->pattern_pairs && !h->sys_pairs.empty()) {
             // the cached pattern holds blocks this system never registered: rebuild exactly
@@ -1385,6 +1435,8 @@ int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz) {
 }
 int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         ISL_CUDA(cudaSetDevice(h->device));
         if (rowptr) {
             if (h->rowptr.p) ISL_CUDA(cudaMemcpyAsync(rowptr, h->rowptr.p, (h->n_eqn + 1) * sizeof(int64_t), cudaMemcpyDefault, h->stream));
@@ -1398,6 +1450,8 @@ int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double
 }
 int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         if (rowptr) *rowptr = h->rowptr.p;
         if (col) *col = h->col.p;
         if (val) *val = h->val.p;
@@ -1406,6 +1460,7 @@ int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** v
 }
 int isl_rhs_value(isl_handle h, int64_t index, double* value) {
     return guarded([&] {
+        flush_pending(h);
         ISL_REQUIRE(index >= 0 && index < h->n_eqn, "index out of bound");
         ISL_CUDA(cudaMemcpyAsync(value, h->rhs.p + index, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
@@ -1413,6 +1468,7 @@ int isl_rhs_value(isl_handle h, int64_t index, double* value) {
 }
 int isl_rhs_norm(isl_handle h, double* norm) {
     return guarded([&] {
+        flush_pending(h);
         ISL_REQUIRE(h->n_eqn > 0, "empty system");
         h->scratch_d.alloc(1);
         ISL_CUDA(cudaMemsetAsync(h->scratch_d.p, 0, sizeof(double), h->stream));
@@ -1426,6 +1482,8 @@ int isl_rhs_norm(isl_handle h, double* norm) {
 
 int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         if (n == 0) return;
         const double* src = which == 1 ? h->rhs.p : h->val.p;
         ISL_LAUNCH(h, k_pack, h->grid_for(n, 256), 256, 0, src, idx_dev, n, out_dev);
@@ -1433,6 +1491,8 @@ int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n,
 }
 int isl_unpack_add_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, const double* in_dev) {
     return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
         if (n == 0) return;
         double* dst = which == 1 ? h->rhs.p : h->val.p;
         ISL_LAUNCH(h, k_unpack_add, h->grid_for(n, 256), 256, 0, dst, idx_dev, n, in_dev);
