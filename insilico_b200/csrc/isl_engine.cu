@@ -697,6 +697,7 @@ struct isl_engine {
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
     int q1_fast = 1;            // sum-factorised local matrix
+    int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
 
     int grid_for(int64_t n, int block) const {
@@ -974,7 +975,8 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     // shared memory per CTA: accumulator (27 entries per row on a hex lattice) + coordinates of the patch's nodes
     // (owned + halo) + row metadata.  R is shrunk until the estimate fits the budget; if the real patches still
     // overflow (irregular boxes) the partition is redone with a smaller R.
-    const int smem_budget = (h->patch_ctas_per_sm >= 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024;
+    const int smem_budget = (h->patch_ctas_per_sm >= 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024 -
+                            (h->patch_ws ? 2 * WS_STAGE_DOUBLES * 128 * 8 + 64 : 0);
     int rows_per_patch = h->patch_rows, cap_nodes = 0, cap_entries = 0;
     PatchHost P;
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -1043,7 +1045,12 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
     const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
-    if (h->patch_threads == 128 && h->patch_ctas_per_sm >= 3) {
+    if (MATRIX && h->patch_ws) {
+        const size_t smem_ws = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 +
+                               (size_t)2 * WS_STAGE_DOUBLES * 128 * 8 + 4 * 8 + (size_t)(p.row_cap + 2) * 8 + 16;
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+        ISL_LAUNCH(h, k_q1hex_patch_ws, ps->n_patches, 256, smem_ws, p);
+    } else if (h->patch_threads == 128 && h->patch_ctas_per_sm >= 3) {
         ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 3>), ps->n_patches, 128, smem, p);
     } else if (h->patch_threads == 128) {
@@ -1057,7 +1064,9 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
         unsigned long long t[8];
         ISL_CUDA(cudaMemcpyAsync(t, profbuf.p, 64, cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
-        const char* nm[8] = {"prologue", "zero", "load", "K", "lift", "scatter", "writeout", "total"};
+        const char* nm_std[8] = {"prologue", "zero", "load", "K", "lift", "scatter", "writeout", "total"};
+        const char* nm_ws[8] = {"c:K+stage", "c:wait_empty", "s:load", "s:wait_full", "s:phases", "prologue", "writeout", "total"};
+        const char* const* nm = h->patch_ws ? nm_ws : nm_std;
         fprintf(stderr, "[isl-prof] cycles per patch (thread 0):");
         for (int i = 0; i < 8; i++) fprintf(stderr, " %s %.0f", nm[i], (double)t[i] / ps->n_patches);
         fprintf(stderr, "\n");
@@ -1113,6 +1122,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
         if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(3, atoi(m)));

@@ -123,7 +123,7 @@ __device__ __forceinline__ void q1_detw(const double (&X)[8][3], double (&detw)[
 //     factorise direction by direction (sum factorisation) into 3 tables of 9 and 3 tables of 12 numbers, from which
 //     every entry is a signed sum of 9 table values.
 // The result differs from the reference operation order by rounding only (checked to 1e-12 against the oracle).
-__device__ __forceinline__ void q1_K_fast(const double (&X)[8][3], double factor, double (&K)[36], double (&detw)[8]) {
+__device__ __forceinline__ void q1_K_fast(const double (&X)[8][3], double factor, double (&K)[36], double (&detw)[8], double (&bf)[8], bool want_bf) {
     constexpr int H[8] = {0, 1, 3, 2, 4, 5, 7, 6};   // lexicographic corner i+2j+4k -> hierarchic node
     constexpr int HI[8] = {0, 1, 1, 0, 0, 1, 1, 0};  // hierarchic node -> (i,j,k)
     constexpr int HJ[8] = {0, 0, 1, 1, 0, 0, 1, 1};
@@ -188,6 +188,23 @@ __device__ __forceinline__ void q1_K_fast(const double (&X)[8][3], double factor
         D[3][q] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
         D[4][q] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
         D[5][q] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
+    }
+    if (want_bf) {
+        // bf[a] = sum_q N_a(q) w_q det J_q by sum factorisation (N_a = n_i(xi) n_j(eta) n_k(zeta))
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            double s1[2][2];
+#pragma unroll
+            for (int qy = 0; qy < 2; qy++)
+#pragma unroll
+                for (int qz = 0; qz < 2; qz++) s1[qy][qz] = n1[0][i] * detw[0 + 2 * qy + 4 * qz] + n1[1][i] * detw[1 + 2 * qy + 4 * qz];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const double u0 = n1[0][j] * s1[0][0] + n1[1][j] * s1[1][0], u1 = n1[0][j] * s1[0][1] + n1[1][j] * s1[1][1];
+#pragma unroll
+                for (int k = 0; k < 2; k++) bf[H[i + 2 * j + 4 * k]] = n1[0][k] * u0 + n1[1][k] * u1;
+            }
+        }
     }
     auto pr = [](int a, int b) constexpr { return a + b; };                 // pair index 00->0, 01/10->1, 11->2
     auto sg = [](int a, int b) constexpr { return (a == b) ? 1.0 : -1.0; };  // sigma_a * sigma_b
@@ -383,13 +400,23 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
     for (int eb = e0; eb < e1; eb += NT) {
         const int e = eb + tid;
         const bool have = e < e1;
-        double K[36]; double detw[8];
+        double K[36]; double detw[8]; double bf[8];
+        bool have_bf = false;
         int lrow[8];
         double lift[8];
         bool any_lift = false;
         uint32_t posw[16];
 #pragma unroll
         for (int a = 0; a < 8; a++) { lrow[a] = 0xffff; lift[a] = 0.; }
+        if (e + NT < e1) {  // next batch's instance data towards L2 while this batch computes
+            const size_t en = (size_t)(e + NT);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.i_lnode + en * 8));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.i_lrow + en * 8));
+            if (MATRIX) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.i_pos + en * 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.i_pos + en * 64 + 32));
+            }
+        }
         if (have) {
             int ln[8];
             {
@@ -416,7 +443,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
             ISL_TICK(2);
             if (MATRIX) {
                 if (p.dbg & 4) { for (int k = 0; k < 36; k++) K[k] = X[k & 7][k % 3]; for (int q = 0; q < 8; q++) detw[q] = 1.; }
-                else if (p.fast) q1_K_fast(X, p.factor, K, detw); else q1_K_naive(X, p.factor, K, detw);
+                else if (p.fast) { q1_K_fast(X, p.factor, K, detw, bf, p.body != 0); have_bf = p.body != 0; } else q1_K_naive(X, p.factor, K, detw);
             } else q1_detw(X, detw);
             ISL_TICK(3);
             // Dirichlet lift: rhs[a] -= g_b K_ab for CONSTRAINED b (assembleMatrix.hpp:56-130).  A node without a
@@ -442,12 +469,17 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
             }
             if (!MATRIX || p.body) {
                 // f * sum_q N_a(q) w_q detJ_q  (BodyForce.hpp:172-205), added with the opposite sign of the lift
+                if (have_bf) {
 #pragma unroll
-                for (int a = 0; a < 8; a++) {
-                    double s = 0.;
+                    for (int a = 0; a < 8; a++) lift[a] -= p.f0 * bf[a];
+                } else {
 #pragma unroll
-                    for (int q = 0; q < 8; q++) s = fma(c_q1_N[q * 8 + a], detw[q], s);
-                    lift[a] -= p.f0 * s;
+                    for (int a = 0; a < 8; a++) {
+                        double s = 0.;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) s = fma(c_q1_N[q * 8 + a], detw[q], s);
+                        lift[a] -= p.f0 * s;
+                    }
                 }
                 any_lift = true;
             }
@@ -514,6 +546,217 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
         }
     }
 #undef ISL_TICK
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised variant of the owner-computes patch kernel (256 threads, one CTA per SM).
+//   warps 0-3 ("compute"): coordinates from shared memory, local matrix with q1_K_fast, result written to one of two
+//                          shared-memory stages;
+//   warps 4-7 ("scatter"): fetch the element's row/position bytes (global loads issued before the wait, so their
+//                          latency hides behind the compute warps), wait for the stage, add the eight local rows in
+//                          eight conflict-free phases (named barrier of the scatter warps only), release the stage.
+// The FP64 pipe is fed by the compute warps while the scatter warps use the shared-memory pipe: the two halves of the
+// work overlap inside one CTA instead of relying on a second resident CTA.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+
+constexpr int WS_STAGE_DOUBLES = 44;  // 36 symmetric matrix entries + 8 body-force sums per element
+
+__global__ void __launch_bounds__(256, 1) k_q1hex_patch_ws(const PatchParams p) {
+    extern __shared__ double smem[];
+    double* acc = smem;                                            // [acc_cap]
+    double* sX = acc + p.acc_cap;                                  // [node_cap][3]
+    double* srhs = sX + (size_t)p.node_cap * 3;                    // [row_cap]
+    int64_t* srun = reinterpret_cast<int64_t*>(srhs + p.row_cap);     // [row_cap]
+    double* stage = reinterpret_cast<double*>(srun + p.row_cap);   // [2][44][128]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(stage + 2 * WS_STAGE_DOUBLES * 128);  // full[2], empty[2]
+    uint32_t* ssoff = reinterpret_cast<uint32_t*>(mbar + 4);       // [row_cap+2]
+    uint32_t* srsoff = ssoff + p.row_cap + 2;                      // [row_cap+2]
+    constexpr int NT = 256;
+    const int tid = threadIdx.x;
+    const int pid = blockIdx.x;
+    long long tk = 0, tk0 = 0;
+    unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define WS_TICK(slot) do { if (p.prof) { const long long now = clock64(); tacc[slot] += (unsigned long long)(now - tk); tk = now; } } while (0)
+    if (p.prof) tk = tk0 = clock64();
+    const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
+    const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
+    const int e0 = p.p_inst_off[pid], e1 = p.p_inst_off[pid + 1];
+    const int u0 = p.p_run_off[pid], nruns = p.p_run_off[pid + 1] - u0;
+    if (tid == 0) { mbar_init(mbar + 0, 128); mbar_init(mbar + 1, 128); mbar_init(mbar + 2, 128); mbar_init(mbar + 3, 128); }
+    for (int r = tid; r <= nrows; r += NT) ssoff[r] = p.soff[r0 + pid + r];
+    for (int r = tid; r < nrows; r += NT) srhs[r] = 0.;
+    for (int u = tid; u <= nruns; u += NT) {
+        srsoff[u] = p.run_soff[u0 + pid + u];
+        if (u < nruns) srun[u] = p.run_start[u0 + u];
+    }
+    {
+        constexpr int U = 5;
+        for (int nb = 0; nb < nnodes; nb += U * NT) {
+            int32_t g[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) { const int n = nb + i * NT + tid; g[i] = (n < nnodes) ? __ldg(p.nodes + n0 + n) : 0; }
+            double x[U][3];
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const double* c = p.coords + (size_t)g[i] * 3;
+                x[i][0] = __ldg(c); x[i][1] = __ldg(c + 1); x[i][2] = __ldg(c + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const int n = nb + i * NT + tid;
+                if (n < nnodes) { sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int nent = (int)ssoff[nrows];
+        for (int k = tid; k < nent; k += NT) acc[k] = 0.;
+    }
+    __syncthreads();
+
+    WS_TICK(5);
+    const int nbatch = (e1 - e0 + 127) / 128;
+    if (tid < 128) {
+        // ---------------- compute warps
+        for (int i = 0; i < nbatch; i++) {
+            const int s = i & 1, par = (i >> 1) & 1;
+            const int e = e0 + i * 128 + tid;
+            const bool have = e < e1;
+            double K[36]; double detw[8]; double bf[8];
+            if (have) {
+                int ln[8];
+                const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)e * 8));
+                ln[0] = l4.x & 0xffff; ln[1] = (unsigned)l4.x >> 16; ln[2] = l4.y & 0xffff; ln[3] = (unsigned)l4.y >> 16;
+                ln[4] = l4.z & 0xffff; ln[5] = (unsigned)l4.z >> 16; ln[6] = l4.w & 0xffff; ln[7] = (unsigned)l4.w >> 16;
+                double X[8][3];
+#pragma unroll
+                for (int a = 0; a < 8; a++) { X[a][0] = sX[ln[a] * 3]; X[a][1] = sX[ln[a] * 3 + 1]; X[a][2] = sX[ln[a] * 3 + 2]; }
+                q1_K_fast(X, p.factor, K, detw, bf, true);
+            }
+            WS_TICK(0);
+            mbar_wait(mbar + 2 + s, par ^ 1);  // stage free (passes immediately the first time)
+            WS_TICK(1);
+            if (have) {
+                double* st = stage + (size_t)s * WS_STAGE_DOUBLES * 128 + tid;
+#pragma unroll
+                for (int k = 0; k < 36; k++) st[k * 128] = K[k];
+#pragma unroll
+                for (int a = 0; a < 8; a++) st[(36 + a) * 128] = bf[a];
+            }
+            mbar_arrive(mbar + s);  // stage full
+            WS_TICK(0);
+        }
+    } else {
+        // ---------------- scatter warps
+        const int st_id = tid - 128;
+        for (int i = 0; i < nbatch; i++) {
+            const int s = i & 1, par = (i >> 1) & 1;
+            const int e = e0 + i * 128 + st_id;
+            const bool have = e < e1;
+            int lrow[8];
+            uint32_t posw[16];
+            double gv[8];
+            bool anyc = false;
+#pragma unroll
+            for (int a = 0; a < 8; a++) { lrow[a] = 0xffff; gv[a] = 0.; }
+            if (have) {
+                const int4 r4 = __ldg(reinterpret_cast<const int4*>(p.i_lrow + (size_t)e * 8));
+                lrow[0] = r4.x & 0xffff; lrow[1] = (unsigned)r4.x >> 16; lrow[2] = r4.y & 0xffff; lrow[3] = (unsigned)r4.y >> 16;
+                lrow[4] = r4.z & 0xffff; lrow[5] = (unsigned)r4.z >> 16; lrow[6] = r4.w & 0xffff; lrow[7] = (unsigned)r4.w >> 16;
+                const int4* p4 = reinterpret_cast<const int4*>(p.i_pos + (size_t)e * 64);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int4 v = __ldg(p4 + j);
+                    posw[j * 4] = v.x; posw[j * 4 + 1] = v.y; posw[j * 4 + 2] = v.z; posw[j * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int b = 0; b < 8; b++) anyc |= (((posw[(b * 8 + b) >> 2] >> (((b * 8 + b) & 3) * 8)) & 0xff) == 0xff);
+                if (anyc) {  // Dirichlet values of the element's CONSTRAINED nodes
+                    const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)e * 8));
+                    const int ln[8] = {l4.x & 0xffff, (int)((unsigned)l4.x >> 16), l4.y & 0xffff, (int)((unsigned)l4.y >> 16),
+                                       l4.z & 0xffff, (int)((unsigned)l4.z >> 16), l4.w & 0xffff, (int)((unsigned)l4.w >> 16)};
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const int32_t g = __ldg(p.nodes + n0 + ln[b]);
+                        if (p.status[g] == ISL_CONSTRAINED) gv[b] = p.incremental ? p.presc[g] - p.values[g] : p.presc[g];
+                    }
+                }
+            }
+            WS_TICK(2);
+            mbar_wait(mbar + s, par);  // stage full
+            WS_TICK(3);
+            const double* st = stage + (size_t)s * WS_STAGE_DOUBLES * 128 + st_id;
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                if (lrow[a] != 0xffff) {
+                    double* row = acc + ssoff[lrow[a]];
+                    double kv[8], t[8];
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                        kv[b] = st[sym_idx(a, b) * 128];
+                        t[b] = (pos != 0xff) ? row[pos] : 0.;
+                    }
+                    double lift = 0.;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                        if (pos != 0xff) row[pos] = t[b] + kv[b];
+                        lift = fma(gv[b], kv[b], lift);
+                    }
+                    if (p.body) lift -= p.f0 * st[(36 + a) * 128];
+                    if (anyc || p.body) srhs[lrow[a]] -= lift;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_arrive(mbar + 2 + s);  // stage free
+            WS_TICK(4);
+        }
+    }
+    __syncthreads();
+    if (p.prof) tk = clock64();
+    // write-out: rhs rows, then the runs of consecutive matrix rows (plain stores, every entry exactly once)
+    for (int r = tid; r < nrows; r += NT) {
+        const double v = srhs[r];
+        if (v != 0.) { const int32_t g = p.rows[r0 + r]; p.rhs[g] += v; }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int u = warp; u < nruns; u += NT / 32) {
+        const int64_t gstart = srun[u];
+        const int s0 = (int)srsoff[u], len = (int)srsoff[u + 1] - s0;
+        double* dst = p.val + gstart;
+        const double* src = acc + s0;
+        if (p.store_mode) {
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) dst[k] = src[k];
+        } else {
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) dst[k] += src[k];
+        }
+    }
+    if (p.prof) {
+        __syncthreads();
+        WS_TICK(6);
+        tacc[7] = (unsigned long long)(clock64() - tk0);
+        if (tid == 0) { atomicAdd(p.prof + 0, tacc[0]); atomicAdd(p.prof + 1, tacc[1]); atomicAdd(p.prof + 5, tacc[5]); atomicAdd(p.prof + 6, tacc[6]); atomicAdd(p.prof + 7, tacc[7]); }
+        if (tid == 128) { atomicAdd(p.prof + 2, tacc[2]); atomicAdd(p.prof + 3, tacc[3]); atomicAdd(p.prof + 4, tacc[4]); }
+    }
+#undef WS_TICK
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -673,8 +916,9 @@ inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector
             P.run_off.push_back((int32_t)P.run_start.size());
         }
         amask.assign(nrows, 0);
-        // elements touching those rows, nodes of those elements
-        int nnodes = 0;
+        // elements touching those rows (sorted by element id: consecutive lanes then work on neighbouring elements,
+        // which keeps their shared-memory accesses on different banks), nodes of those elements
+        const size_t ibase = P.inst_elem.size();
         for (int r = 0; r < nrows; r++) {
             const int32_t g = P.rows[rbase + r];
             for (int64_t j = adj_ptr[g]; j < adj_ptr[g + 1]; j++) {
@@ -682,18 +926,23 @@ inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector
                 if (el_stamp[e] == pid) continue;
                 el_stamp[e] = pid;
                 P.inst_elem.push_back(e);
-                for (int a = 0; a < 8; a++) {
-                    const int32_t nd = conn[(size_t)e * 8 + a];
-                    if (node_stamp[nd] != pid) { node_stamp[nd] = pid; node_l[nd] = nnodes++; P.nodes.push_back(nd); }
-                    P.lnode.push_back((uint16_t)node_l[nd]);
-                    const int32_t ge = eqn[(size_t)e * 8 + a];
-                    if (ge >= 0 && row_stamp[ge] == pid) {
-                        const int l = row_l[ge];
-                        P.lrow.push_back((uint16_t)l);
-                        if (amask[l] & (1u << a)) P.lattice = false;  // two elements see this row as local row a
-                        amask[l] |= (uint8_t)(1u << a);
-                    } else P.lrow.push_back((uint16_t)0xffff);
-                }
+            }
+        }
+        std::sort(P.inst_elem.begin() + ibase, P.inst_elem.end());
+        int nnodes = 0;
+        for (size_t ii = ibase; ii < P.inst_elem.size(); ii++) {
+            const int32_t e = P.inst_elem[ii];
+            for (int a = 0; a < 8; a++) {
+                const int32_t nd = conn[(size_t)e * 8 + a];
+                if (node_stamp[nd] != pid) { node_stamp[nd] = pid; node_l[nd] = nnodes++; P.nodes.push_back(nd); }
+                P.lnode.push_back((uint16_t)node_l[nd]);
+                const int32_t ge = eqn[(size_t)e * 8 + a];
+                if (ge >= 0 && row_stamp[ge] == pid) {
+                    const int l = row_l[ge];
+                    P.lrow.push_back((uint16_t)l);
+                    if (amask[l] & (1u << a)) P.lattice = false;  // two elements see this row as local row a
+                    amask[l] |= (uint8_t)(1u << a);
+                } else P.lrow.push_back((uint16_t)0xffff);
             }
         }
         P.inst_off.push_back((int32_t)P.inst_elem.size());

@@ -156,7 +156,8 @@ def test_large_mesh_properties(eng):
 
 @pytest.mark.parametrize("env", [{"ISL_Q1_MODE": "atomic"}, {"ISL_Q1_FAST": "0"}, {"ISL_PATCH_ROWS": "64"},
                                  {"ISL_PATCH_ROWS": "200", "ISL_PATCH_THREADS": "256"}, {"ISL_PATCH_ROWS": "360"},
-                                 {"ISL_PATCH_ROWS": "512", "ISL_PATCH_THREADS": "256", "ISL_PATCH_CTAS": "1"}])
+                                 {"ISL_PATCH_ROWS": "512", "ISL_PATCH_THREADS": "256", "ISL_PATCH_CTAS": "1"},
+                                 {"ISL_PATCH_WS": "1"}, {"ISL_PATCH_WS": "1", "ISL_PATCH_ROWS": "120"}])
 @pytest.mark.parametrize("name,n,permute", [("laplace_q1_hex", 13, False), ("laplace_q1_hex_values", 9, True)])
 def test_q1_hot_path_variants(monkeypatch, env, name, n, permute):
     """one-thread-per-element atomic kernel and shared-memory patch kernel (several patch sizes, Morton ordering of a
@@ -198,3 +199,23 @@ def test_cpp_facade_example_matches_python_flow(eng):
     assert int(ndof) == len(rhs) and int(nnz) == len(val)
     assert float(norm) == pytest.approx(np.linalg.norm(ref[3]) / len(rhs), rel=1e-12)
     assert float(total) == pytest.approx(ref[2].sum(), rel=1e-9, abs=1e-9 * np.abs(ref[2]).max())
+
+
+def test_q1_non_lattice_connectivity_falls_back_to_atomic_kernel(eng):
+    """Rotating the local node order of some hexahedra (still valid elements) breaks the lattice property the patch
+    kernel relies on (a node must be local node a of at most one element); the engine detects that in the patch
+    preprocessing and uses the one-thread-per-element kernel.  Result must still equal the oracle."""
+    c = flows.build_case("laplace_q1_hex", 9, perturb=True)
+    rot = np.array([1, 2, 3, 0, 5, 6, 7, 4])          # rotation about the local zeta axis
+    conn = c.conn.copy()
+    conn[::3] = conn[::3][:, rot]
+    c2 = flows.Case(E.HEX, 1, c.coords, conn)
+    c2.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, np.full(3, -0.5)))
+    c2.ops = c.ops
+    ref = c2.run_oracle()
+    out = c2.run_engine(eng=eng)
+    r = flows.compare(ref, out)
+    assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+    # same operator as the unrotated mesh (local numbering does not change the assembled system)
+    r0 = flows.compare(c.run_oracle(), out)
+    assert r0["pattern_equal"] and r0["val_diff"] <= 1e-11
