@@ -190,7 +190,7 @@ def main():
         eng.body_force_computation([1.0], 3, 0)
         if events is not None:
             events[1].record(stream)
-        if world > 1:
+        if world > 1 and not os.environ.get("BENCH_NO_EXCHANGE"):
             part.exchange()
 
     def barrier():
@@ -216,6 +216,9 @@ def main():
     launches = eng.kernel_launches - l0
     ms_total = ev_start.elapsed_time(ev_end)
     ms_kernel = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    if os.environ.get("BENCH_ALL_RANKS"):
+        print("[bench] rank %d: %.3f ms/step, dominant kernel %.3f ms, launches %d" %
+              (rank, ms_total / args.steps, ms_kernel, launches), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

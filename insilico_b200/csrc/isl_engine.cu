@@ -963,12 +963,26 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     ISL_CUDA(cudaMemcpyAsync(hnode_eqn.data(), f.eqn.p, h->n_nodes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     ISL_CUDA(cudaMemcpyAsync(hcoords.data(), h->coords.p, hcoords.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     ISL_CUDA(cudaStreamSynchronize(h->stream));
+    // boxes must be compact in the mesh topology, not in physical space (anisotropic meshes): measure the mean element
+    // extent along every axis and bisect in coordinates scaled by it
+    double hmean[3] = {0., 0., 0.};
+    {
+        const int64_t stride = std::max<int64_t>(1, n / 200000);
+        int64_t cnt = 0;
+        for (int64_t e = 0; e < n; e += stride, cnt++)
+            for (int d = 0; d < 3; d++) {
+                double mn = 1e300, mx = -1e300;
+                for (int a = 0; a < 8; a++) { const double v = hcoords[(size_t)hconn[(size_t)e * 8 + a] * 3 + d]; mn = std::min(mn, v); mx = std::max(mx, v); }
+                hmean[d] += mx - mn;
+            }
+        for (int d = 0; d < 3; d++) hmean[d] = (cnt && hmean[d] > 0.) ? hmean[d] / (double)cnt : 1.0;
+    }
     std::vector<double> rowxyz((size_t)nrow * 3, 0.);
     std::vector<int32_t> hperm; hperm.reserve(nrow);
     for (int64_t nd = 0; nd < h->n_nodes; nd++) {
         const int32_t r = hnode_eqn[nd];
         if (r < 0) continue;
-        for (int d = 0; d < 3; d++) rowxyz[(size_t)r * 3 + d] = hcoords[(size_t)nd * 3 + d];
+        for (int d = 0; d < 3; d++) rowxyz[(size_t)r * 3 + d] = hcoords[(size_t)nd * 3 + d] / hmean[d];
         hperm.push_back(r);
     }
     hcoords.clear(); hcoords.shrink_to_fit();

@@ -1,8 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for ws in 0 1; do echo "== WS=$ws"; ISL_PROF=1 ISL_PATCH_WS=$ws timeout 300 python bench.py --steps 10 --no-cpu-baseline --no-e2e 2>&1 | grep -E "isl-prof|^{" | tail -2 | python -c "
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 8 --steps 20 --no-cpu-baseline --no-e2e 2>&1 | grep -E "^{" | python -c "
 import sys,json
 for l in sys.stdin:
-    if l.startswith('[isl'): print(l.strip()[:250])
-    if l.startswith('{'):
-        d=json.loads(l); print('ms_step %.2f kernel_ms %.2f frac %.3f'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac']))
-"; done
+    d=json.loads(l); print(d['ms_per_step'], d['clocks']['power_w_max'], d['roofline']['kernel_ms'])
+"; }
+echo "== no exchange"; BENCH_NO_EXCHANGE=1 run 29601
+echo "== NCCL channels limited"; NCCL_MAX_NCHANNELS=2 NCCL_MAX_P2P_NCHANNELS=2 NCCL_MIN_P2P_NCHANNELS=1 run 29602
+echo "== default"; run 29603
