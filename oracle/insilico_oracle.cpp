@@ -18,7 +18,9 @@
 //    * numbering + sparsity : reference/03-doFHandler/sparsity.{1,2,3}.ref.dat (exact)
 //    * quadrature+Jacobian  : reference/02-areaVolume/measure.ref.dat (6 digits)
 //    * full chain HyperElastic<StVenant>+Lame, Q1 hex, Dirichlet lift, solve, L2
-//      error: reference/06-elastic/linearElastic3D.ref.dat (6 digits)
+//      error: reference/06-elastic/linearElastic{2D,3D}.ref.dat (6 digits)
+//    * HyperElastic<NeoHookeanCompressible> tangent + residual, incremental Dirichlet lift, Newton history:
+//      reference/06-elastic/compRefOutD.dat (6 digits)
 //    * HierarchicOrder tables + worked numbering example of
 //      base/dof/generateDoFIndicesFromFaces.hpp:141-160
 //  Entry-wise 1e-12 matrix parity is NOT pinned by any reference golden (the

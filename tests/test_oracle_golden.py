@@ -142,3 +142,57 @@ def test_unit_cube_matches_fixture():
     shape, coords, conn = H.read_smf(os.path.join(H.REF, "square_20.smf"))
     c2, n2 = orc.unit_cube(2, False, 1, 20, 20)
     assert np.array_equal(conn, n2)
+
+
+def test_compressible_newton_history_golden():
+    """reference/06-elastic/compressible.cpp:245-320 (displacement controlled, inputCompRefD.dat) on quad.020.smf
+    (identical to square_20.smf): HyperElastic<NeoHookeanCompressible> tangent + residual on Q2 quads, five load steps
+    of Newton iterations.  Golden compRefOutD.dat: #dofs 3239 and |F|, |x| per iteration (6 digits)."""
+    E_, nu = 1000.0, 0.3
+    lam = E_ * nu / (1. + nu) / (1. - 2. * nu)
+    mu = E_ / 2. / (1. + nu)
+    pull, load_steps, tol, max_iter = 3.0, 5, 1e-12, 30
+    shape, coords, conn = H.read_smf(os.path.join(H.REF, "square_20.smf"))
+    prob = orc.Problem(shape, 1, coords, conn)
+    ed, nobj = prob.dof_generate(2)
+    # PulledSheet<2>::dirichletBC (PulledSheet.hpp:33-57): left side fixed, right side pulled in x
+    pairs = prob.mesh_boundary()
+    elem, loc, x = prob.boundary_dof_points(2, pairs)
+    status = np.zeros((nobj, 2), dtype=np.uint8)
+    presc = np.zeros((nobj, 2))
+    first_pull = pull / load_steps
+    for k in range(len(elem)):
+        o = ed[elem[k], loc[k]]
+        if abs(x[k, 0]) < 1e-6:
+            status[o, :] = 1; presc[o, :] = 0.0
+        if abs(x[k, 0] - 1.0) < 1e-6 and status[o, 0] == 0:
+            status[o, 0] = 1; presc[o, 0] = first_pull
+    eqn, ndof = orc.number_dofs(status)
+    assert ndof == 3239
+    gold = [l.split() for l in open(os.path.join(H.REF, "compRefOutD.dat")) if not l.startswith("#")]
+    values = np.zeros((nobj, 2))
+    g = 0
+    for step in range(load_steps):
+        presc *= 1.0 if step == 0 else (step + 1) / step          # dof::scaleConstraints
+        for it in range(max_iter):
+            prob.set_field(0, 2, 2, nobj, ed, eqn, status, presc, values)
+            s = orc.System(ndof)
+            s.residual(prob, orc.K_HYPEL_NEOHOOKE, [lam, mu], 3, 0, 0)
+            s.stiffness(prob, orc.K_HYPEL_NEOHOOKE, [lam, mu], 3, 0, 0, incremental=True)
+            conv1 = s.rhs_norm()
+            rowptr, col, val, rhs = s.finish()
+            row = gold[g]; g += 1
+            assert int(row[0]) == step and int(row[1]) == it
+            assert float("%.6g" % conv1) == pytest.approx(float(row[2]), rel=3e-5, abs=1e-13), (step, it, conv1)
+            if conv1 < tol * E_:
+                break
+            A = sp.csr_matrix((val, col, rowptr), shape=(ndof, ndof))
+            dx = spla.spsolve(A.tocsc(), rhs)
+            act = status == 0
+            values[act] += dx[eqn[act]]                              # dof::addToDoFsFromSolver
+            values[status == 1] = presc[status == 1]
+            conv2 = np.linalg.norm(dx) / ndof
+            assert float("%.6g" % conv2) == pytest.approx(float(row[3]), rel=3e-5), (step, it, conv2)
+            if conv2 < tol:
+                break
+    assert g == len(gold)
