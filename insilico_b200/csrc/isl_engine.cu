@@ -892,6 +892,7 @@ void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
     const size_t smem = per * EB;
     ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     const int64_t nbatch = (h->n_owned + EB - 1) / EB;
+    if (nbatch == 0) return;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
     kernel<<<grid, 256, smem, h->stream>>>(p);
     h->launches++;
@@ -1043,6 +1044,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
 
 template <bool MATRIX>
 void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor, int incremental, int body, double f0) {
+    if (ps->n_patches == 0) return;  // no ACTIVE row: nothing to assemble
     PatchParams p;
     p.coords = h->coords.p;
     p.p_inst_off = ps->p_inst_off.p; p.p_row_off = ps->p_row_off.p; p.p_node_off = ps->p_node_off.p;
@@ -1355,7 +1357,7 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
             q.val = h->val.p; q.rhs = h->rhs.p; q.factor = params ? params[0] : 1.0; q.incremental = incremental;
             const int block = 128;
             const int64_t grid = (h->n_owned + block - 1) / block;
-            ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
+            if (grid > 0) ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
             return;
         }
         AsmParams p; std::memset(&p, 0, sizeof(p));

@@ -219,3 +219,32 @@ def test_q1_non_lattice_connectivity_falls_back_to_atomic_kernel(eng):
     # same operator as the unrotated mesh (local numbering does not change the assembled system)
     r0 = flows.compare(c.run_oracle(), out)
     assert r0["pattern_equal"] and r0["val_diff"] <= 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_degenerate_sizes(eng, n):
+    """n=1: every node is on the boundary (no equation at all, nnz = 0); n=2: one ACTIVE node (1x1 system whose rhs is
+    pure Dirichlet lift); n=3: 8 equations.  Same flow as the big cases."""
+    c = flows.build_case("laplace_q1_hex", n, perturb=(n > 1))
+    ref = c.run_oracle()
+    out = c.run_engine(eng=eng)
+    assert len(out[3]) == (n - 1) ** 3
+    assert np.array_equal(ref[0], out[0]) and np.array_equal(ref[1], out[1])
+    if n > 1:
+        r = flows.compare(ref, out)
+        assert r["val_diff"] <= TOL and r["rhs_diff"] <= TOL
+
+
+def test_inactive_dofs_are_skipped(eng):
+    """INACTIVE DoFs (immersed methods, base/dof/DegreeOfFreedom.hpp:33-38) neither get an equation nor a lift; elements
+    whose DoFs are all INACTIVE contribute nothing (collectFromDoFs.hpp:118-134)."""
+    c = flows.build_case("laplace_q1_hex", 5, perturb=True)
+    f = c.fields[0]
+    inactive = (f["status"][:, 0] == 0) & (c.coords[:, 0] < 0.45)
+    f["status"][inactive, 0] = E.INACTIVE
+    f["eqn"], c.n_eqn = E.number_dofs_consecutively(f["status"])
+    ref = c.run_oracle()
+    out = c.run_engine(eng=eng)
+    r = flows.compare(ref, out)
+    assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+    assert c.n_eqn < 4 ** 3
