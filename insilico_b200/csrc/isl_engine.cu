@@ -581,10 +581,6 @@ __global__ void k_make_keys(const int32_t* er, const int32_t* ec, int64_t n_elem
         keys[t] = (r < 0 || c < 0) ? ~0ull : (((uint64_t)(uint32_t)r << 32) | (uint32_t)c);
     }
 }
-__global__ void k_csr_keys(const int64_t* rowptr, const int32_t* col, int64_t n, uint64_t* keys) {
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        for (int64_t k = rowptr[r]; k < rowptr[r + 1]; k++) keys[k] = ((uint64_t)r << 32) | (uint32_t)col[k];
-}
 __global__ void k_rowptr_from_keys(const uint64_t* keys, int64_t nnz, int64_t n, int64_t* rowptr) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t target = (uint64_t)r << 32;
@@ -947,7 +943,7 @@ bool qualifies_q1(const isl_engine* h, int t, int c) {
 // the shared-memory accumulator (caller falls back to the atomic kernel)
 PatchSet* get_patchset(isl_engine* h, int field) {
     auto it = h->patchsets.find(field);
-    if (it != h->patchsets.end()) return it->second->n_patches > 0 ? it->second.get() : nullptr;
+    if (it != h->patchsets.end()) return it->second->usable ? it->second.get() : nullptr;
     auto ps = std::make_unique<PatchSet>();
     PatchSet* out = nullptr;
     FieldDev& f = h->fields[field];
@@ -1032,7 +1028,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         int err = 0;
         ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
-        if (!err) out = ps.get(); else ps->n_patches = 0;
+        if (!err) { ps->usable = true; out = ps.get(); } else ps->n_patches = 0;
     }
     if (getenv("ISL_VERBOSE"))
         fprintf(stderr, "[isl] patches: %d (<= %d rows), max entries %d (cap %d), max nodes %d (cap %d), element instances %.3fx, lattice %d%s\n",

@@ -761,51 +761,6 @@ __global__ void __launch_bounds__(256, 1) k_q1hex_patch_ws(const PatchParams p) 
 
 // ---------------------------------------------------------------------------------------------
 // preprocessing
-__device__ __forceinline__ uint64_t morton3(double x, double y, double z) {
-    uint64_t q[3] = {(uint64_t)min(max(x, 0.0), 2097151.0), (uint64_t)min(max(y, 0.0), 2097151.0),
-                     (uint64_t)min(max(z, 0.0), 2097151.0)};
-    uint64_t key = 0;
-    for (int d = 0; d < 3; d++) {
-        uint64_t v = q[d] & 0x1fffff;  // spread 21 bits
-        v = (v | v << 32) & 0x1f00000000ffffull;
-        v = (v | v << 16) & 0x1f0000ff0000ffull;
-        v = (v | v << 8) & 0x100f00f00f00f00full;
-        v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-        v = (v | v << 2) & 0x1249249249249249ull;
-        key |= v << d;
-    }
-    return key;
-}
-// Morton key of every equation = position of the node that carries it (scalar field, DoF id = node id)
-__global__ void k_row_morton_keys(const double* coords, const int32_t* eqn, int64_t n_nodes, double x0, double y0, double z0,
-                                  double sx, double sy, double sz, uint64_t* keys, int32_t* idx) {
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t r = eqn[n];
-        if (r < 0) continue;
-        const double* x = coords + (size_t)n * 3;
-        keys[r] = morton3((x[0] - x0) * sx, (x[1] - y0) * sy, (x[2] - z0) * sz);
-        idx[r] = r;
-    }
-}
-__global__ void k_minmax3(const double* coords, int64_t n, double* out /* [gridDim][6] */) {
-    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        for (int d = 0; d < 3; d++) { const double v = coords[i * 3 + d]; mn[d] = fmin(mn[d], v); mx[d] = fmax(mx[d], v); }
-    for (int d = 0; d < 3; d++)
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[d] = fmin(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
-            mx[d] = fmax(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
-        }
-    __shared__ double s[32][6];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) for (int d = 0; d < 3; d++) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); k++)
-            for (int d = 0; d < 3; d++) { s[0][d] = fmin(s[0][d], s[k][d]); s[0][3 + d] = fmax(s[0][3 + d], s[k][3 + d]); }
-        for (int d = 0; d < 6; d++) out[blockIdx.x * 6 + d] = s[0][d];
-    }
-}
 // per element instance: uint8 position of column b inside row a (0xff when row or column is not ACTIVE)
 __global__ void k_inst_pos(const int32_t* inst_elem, const int32_t* elem_eqn, int64_t n_inst, const int64_t* rowptr,
                            const int32_t* col, uint8_t* i_pos, int* err) {
@@ -825,6 +780,7 @@ __global__ void k_inst_pos(const int32_t* inst_elem, const int32_t* elem_eqn, in
 }
 
 struct PatchSet {
+    bool usable = false;  // false: the mesh does not fit the patch kernel (atomic fallback)
     int n_patches = 0, max_entries = 0, max_rows = 0, max_nodes = 0;
     int64_t n_inst = 0, n_elems = 0;
     DevBuf<int32_t> p_inst_off, p_row_off, p_node_off, p_run_off, rows, nodes;
