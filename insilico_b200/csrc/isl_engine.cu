@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
 // slot map with RED.ADD.F64; Dirichlet lift fused.  Tables live in constant memory.
 __constant__ double c_q1_dN[8 * 8 * 3];  // [q][a][d] reference gradients at the 8 Gauss points
 __constant__ double c_q1_w[8];
+__constant__ double c_q1_aff[6 * 36];     // affine-element tables, see q1_K_affine
+__constant__ double c_q1_Nsum[8];        // sum_q N_a(q)
 __constant__ double c_q1_n1[4];           // [q1d][i] 1-D linear shape values at the two Gauss abscissae
 __constant__ double c_q1_N[8 * 8];       // [q][a] shape-function values at the Gauss points
 
@@ -692,7 +694,7 @@ struct isl_engine {
     struct PendingQ1 { bool active = false; int field = 0; double factor = 1.; int incremental = 1; } pending_q1;
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
-    int q1_fast = 1;            // sum-factorised local matrix
+    int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
 
@@ -926,6 +928,23 @@ void load_q1_tables(isl_engine* h) {
     for (int q = 0; q < 8; q++) { B.eval(&R.p[q * 3], N.data(), &dN[q * 24]); for (int a = 0; a < 8; a++) Nq[q * 8 + a] = N[a]; }
     ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_dN, dN.data(), sizeof(double) * 192, 0, cudaMemcpyHostToDevice, h->stream));
     ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_N, Nq.data(), sizeof(double) * 64, 0, cudaMemcpyHostToDevice, h->stream));
+    {
+        std::vector<double> aff(6 * 36, 0.), nsum(8, 0.);
+        const int al[6] = {0, 1, 2, 0, 0, 1}, be[6] = {0, 1, 2, 1, 2, 2};
+        for (int c = 0; c < 6; c++)
+            for (int a = 0; a < 8; a++)
+                for (int b = a; b < 8; b++) {
+                    double v = 0.;
+                    for (int q = 0; q < 8; q++) {
+                        v += dN[q * 24 + a * 3 + al[c]] * dN[q * 24 + b * 3 + be[c]];
+                        if (al[c] != be[c]) v += dN[q * 24 + a * 3 + be[c]] * dN[q * 24 + b * 3 + al[c]];
+                    }
+                    aff[c * 36 + sym_idx(a, b)] = v;
+                }
+        for (int a = 0; a < 8; a++) for (int q = 0; q < 8; q++) nsum[a] += Nq[q * 8 + a];
+        ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_aff, aff.data(), sizeof(double) * 216, 0, cudaMemcpyHostToDevice, h->stream));
+        ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_Nsum, nsum.data(), sizeof(double) * 8, 0, cudaMemcpyHostToDevice, h->stream));
+    }
     const double g[2] = {R.p[0], R.p[3]};  // 1-D abscissae in table order (point 0 = (g0,g0,g0), point 1 = (g1,g0,g0))
     const double n1[4] = {1. - g[0], g[0], 1. - g[1], g[1]};
     ISL_CUDA(cudaMemcpyToSymbolAsync(c_q1_n1, n1, sizeof(double) * 4, 0, cudaMemcpyHostToDevice, h->stream));
@@ -1065,6 +1084,9 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     } else if (h->patch_threads == 128 && h->patch_ctas_per_sm >= 3) {
         ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 3>), ps->n_patches, 128, smem, p);
+    } else if (h->patch_threads == 128 && MATRIX && (h->q1_fast & 2)) {
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 2, true>), ps->n_patches, 128, smem, p);
     } else if (h->patch_threads == 128) {
         ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch<128, MATRIX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ISL_LAUNCH(h, (k_q1hex_patch<128, MATRIX, 2>), ps->n_patches, 128, smem, p);
@@ -1132,7 +1154,7 @@ int isl_engine_create(int device, isl_handle* out) {
         ISL_CUDA(cudaGetDeviceProperties(&prop, device));
         h->n_sm = prop.multiProcessorCount;
         if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
-        if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m);  // 0 reference order, 1 sum factorisation, 3 + affine shortcut
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));

@@ -342,9 +342,64 @@ __device__ __forceinline__ void q1_K_fast(const double (&X)[8][3], double factor
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Affine elements (parallelepipeds: the four edge vectors of every direction coincide) have a constant Jacobian, so
+// K_ab = (factor w / det J) sum_{al<=be} (cof^T cof)^{al be} C^{al be}_ab with six constant 8x8 tables
+// C^{al be}_ab = sum_q (dN_a/dxi_al dN_b/dxi_be + dN_a/dxi_be dN_b/dxi_al) [second term only for al != be]
+// evaluated at the rule's points on the host (c_q1_aff).  About 0.3 k FP64 instructions.  Returns false (nothing
+// written) when the element is not affine; the test is exact, no tolerance.
+__device__ __forceinline__ bool q1_K_affine(const double (&X)[8][3], double factor, double (&K)[36], double (&detw)[8],
+                                            double (&bf)[8]) {
+    constexpr int H[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    double J[3][3];
+    bool affine = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double ex = X[H[1]][d] - X[H[0]][d], ey = X[H[2]][d] - X[H[0]][d], ez = X[H[4]][d] - X[H[0]][d];
+        affine &= (X[H[3]][d] - X[H[2]][d] == ex) & (X[H[5]][d] - X[H[4]][d] == ex) & (X[H[7]][d] - X[H[6]][d] == ex);
+        affine &= (X[H[3]][d] - X[H[1]][d] == ey) & (X[H[6]][d] - X[H[4]][d] == ey) & (X[H[7]][d] - X[H[5]][d] == ey);
+        affine &= (X[H[5]][d] - X[H[1]][d] == ez) & (X[H[6]][d] - X[H[2]][d] == ez) & (X[H[7]][d] - X[H[3]][d] == ez);
+        J[d][0] = ex; J[d][1] = ey; J[d][2] = ez;
+    }
+    if (!affine) return false;
+    double co[3][3];
+    co[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    co[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    co[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    co[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+    co[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+    co[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+    co[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+    co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+    co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
+    const double w = c_q1_w[0];
+    const double s = (factor * w) / det;
+    double D[6];
+    D[0] = s * (co[0][0] * co[0][0] + co[1][0] * co[1][0] + co[2][0] * co[2][0]);
+    D[1] = s * (co[0][1] * co[0][1] + co[1][1] * co[1][1] + co[2][1] * co[2][1]);
+    D[2] = s * (co[0][2] * co[0][2] + co[1][2] * co[1][2] + co[2][2] * co[2][2]);
+    D[3] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
+    D[4] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
+    D[5] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
+#pragma unroll
+    for (int k = 0; k < 36; k++) {
+        double v = D[0] * c_q1_aff[k];
+#pragma unroll
+        for (int c = 1; c < 6; c++) v = fma(D[c], c_q1_aff[c * 36 + k], v);
+        K[k] = v;
+    }
+    const double dw = det * w;
+#pragma unroll
+    for (int q = 0; q < 8; q++) detw[q] = dw;
+#pragma unroll
+    for (int a = 0; a < 8; a++) bf[a] = dw * c_q1_Nsum[a];
+    return true;
+}
+
 // MATRIX = true : stiffness matrix + Dirichlet lift (+ fused body force when p.body)
 // MATRIX = false: body force only
-template <int NT, bool MATRIX, int MINB>
+template <int NT, bool MATRIX, int MINB, bool AFF = false>
 __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
     extern __shared__ double smem[];
     double* acc = smem;                                            // [acc_cap]
@@ -443,7 +498,10 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_patch(const PatchParams p) {
             ISL_TICK(2);
             if (MATRIX) {
                 if (p.dbg & 4) { for (int k = 0; k < 36; k++) K[k] = X[k & 7][k % 3]; for (int q = 0; q < 8; q++) detw[q] = 1.; }
-                else if (p.fast) { q1_K_fast(X, p.factor, K, detw, bf, p.body != 0); have_bf = p.body != 0; } else q1_K_naive(X, p.factor, K, detw);
+                else if (p.fast) {
+                    if (!(AFF && q1_K_affine(X, p.factor, K, detw, bf))) q1_K_fast(X, p.factor, K, detw, bf, p.body != 0);
+                    have_bf = p.body != 0;
+                } else q1_K_naive(X, p.factor, K, detw);
             } else q1_detw(X, detw);
             ISL_TICK(3);
             // Dirichlet lift: rhs[a] -= g_b K_ab for CONSTRAINED b (assembleMatrix.hpp:56-130).  A node without a
