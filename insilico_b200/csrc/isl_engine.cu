@@ -695,6 +695,8 @@ struct isl_engine {
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
     int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
+    int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
+    int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
 
@@ -1076,6 +1078,22 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
     const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
+    if (MATRIX && h->affine_kernel && (h->q1_fast & 2) && !h->patch_ws && h->patch_ctas_per_sm == 2 && h->shape == ISL_HEX) {
+        if (h->affine_state < 0) {  // once per coordinate set
+            DevBuf<int> flag; flag.alloc(1);
+            ISL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), h->stream));
+            if (h->n_owned > 0) ISL_LAUNCH(h, k_check_affine, h->grid_for(h->n_owned, 256), 256, 0, h->coords.p, h->conn.p, h->n_owned, flag.p);
+            int na = 0;
+            ISL_CUDA(cudaMemcpyAsync(&na, flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            h->affine_state = na ? 0 : 1;
+        }
+        if (h->affine_state == 1) {
+            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_affine<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ISL_LAUNCH(h, k_q1hex_patch_affine<256>, ps->n_patches, 256, smem, p);
+            return;
+        }
+    }
     if (MATRIX && h->patch_ws) {
         const size_t smem_ws = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 +
                                (size_t)2 * WS_STAGE_DOUBLES * 128 * 8 + 4 * 8 + (size_t)(p.row_cap + 2) * 8 + 16;
@@ -1156,6 +1174,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m);  // 0 reference order, 1 sum factorisation, 3 + affine shortcut
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
@@ -1243,7 +1262,7 @@ int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes
         ISL_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
         const isl::Basis G(shape, geom_deg);
         h->shape = shape; h->geom_deg = geom_deg; h->dim = dim; h->npe = G.nfun;
-        h->n_nodes = n_nodes; h->n_elems = n_elems; h->n_owned = n_elems;
+        h->n_nodes = n_nodes; h->n_elems = n_elems; h->n_owned = n_elems; h->affine_state = -1;
         upload(h, h->coords, coords, (size_t)n_nodes * dim);
         upload(h, h->conn, conn, (size_t)n_elems * h->npe);
         for (auto& f : h->fields) f.reset();
@@ -1256,7 +1275,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
     return guarded([&] {
         flush_pending(h);
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
-        h->n_owned = n_owned;
+        h->n_owned = n_owned; h->affine_state = -1;
         h->slotmaps.clear();
         h->patchsets.clear();
     });
@@ -1265,6 +1284,7 @@ int isl_mesh_update_coords(isl_handle h, const double* coords) {
     return guarded([&] {
         flush_pending(h);
         ISL_REQUIRE(h->n_nodes > 0, "mesh not set");
+        h->affine_state = -1;
         ISL_CUDA(cudaMemcpyAsync(h->coords.p, coords, (size_t)h->n_nodes * h->dim * sizeof(double), cudaMemcpyDefault, h->stream));
     });
 }

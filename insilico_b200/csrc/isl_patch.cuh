@@ -818,6 +818,187 @@ __global__ void __launch_bounds__(256, 1) k_q1hex_patch_ws(const PatchParams p) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Patch kernel for meshes whose elements are ALL affine (checked once per coordinate set by k_check_affine).  The local
+// matrix is never stored: in phase a the eight entries of local row a are formed from the six numbers D_c and the
+// constant tables (48 FMAs with constant-bank operands) right before they are added to the accumulator.  The thread
+// state is a few dozen registers, so a CTA has 256 threads at two CTAs per SM: twice the warps of the general kernel
+// for hiding the shared-memory and barrier latencies.
+__global__ void k_check_affine(const double* coords, const int32_t* conn, int64_t n, int* not_affine) {
+    constexpr int H[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        double X[8][3];
+        for (int a = 0; a < 8; a++) { const double* c = coords + (size_t)conn[e * 8 + a] * 3; X[a][0] = c[0]; X[a][1] = c[1]; X[a][2] = c[2]; }
+        bool affine = true;
+        for (int d = 0; d < 3; d++) {
+            const double ex = X[H[1]][d] - X[H[0]][d], ey = X[H[2]][d] - X[H[0]][d], ez = X[H[4]][d] - X[H[0]][d];
+            affine &= (X[H[3]][d] - X[H[2]][d] == ex) & (X[H[5]][d] - X[H[4]][d] == ex) & (X[H[7]][d] - X[H[6]][d] == ex);
+            affine &= (X[H[3]][d] - X[H[1]][d] == ey) & (X[H[6]][d] - X[H[4]][d] == ey) & (X[H[7]][d] - X[H[5]][d] == ey);
+            affine &= (X[H[5]][d] - X[H[1]][d] == ez) & (X[H[6]][d] - X[H[2]][d] == ez) & (X[H[7]][d] - X[H[3]][d] == ez);
+        }
+        if (!affine) *not_affine = 1;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) k_q1hex_patch_affine(const PatchParams p) {
+    extern __shared__ double smem[];
+    double* acc = smem;
+    double* sX = acc + p.acc_cap;
+    double* srhs = sX + (size_t)p.node_cap * 3;
+    int64_t* srun = reinterpret_cast<int64_t*>(srhs + p.row_cap);
+    uint32_t* ssoff = reinterpret_cast<uint32_t*>(srun + p.row_cap);
+    uint32_t* srsoff = ssoff + p.row_cap + 2;
+    const int tid = threadIdx.x;
+    const int pid = blockIdx.x;
+    const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
+    const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
+    const int e0 = p.p_inst_off[pid], e1 = p.p_inst_off[pid + 1];
+    const int u0 = p.p_run_off[pid], nruns = p.p_run_off[pid + 1] - u0;
+    for (int r = tid; r <= nrows; r += NT) ssoff[r] = p.soff[r0 + pid + r];
+    for (int r = tid; r < nrows; r += NT) srhs[r] = 0.;
+    for (int u = tid; u <= nruns; u += NT) {
+        srsoff[u] = p.run_soff[u0 + pid + u];
+        if (u < nruns) srun[u] = p.run_start[u0 + u];
+    }
+    {
+        constexpr int U = 4;
+        for (int nb = 0; nb < nnodes; nb += U * NT) {
+            int32_t g[U];
+#pragma unroll
+            for (int i = 0; i < U; i++) { const int n = nb + i * NT + tid; g[i] = (n < nnodes) ? __ldg(p.nodes + n0 + n) : 0; }
+            double x[U][3];
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const double* c = p.coords + (size_t)g[i] * 3;
+                x[i][0] = __ldg(c); x[i][1] = __ldg(c + 1); x[i][2] = __ldg(c + 2);
+            }
+#pragma unroll
+            for (int i = 0; i < U; i++) {
+                const int n = nb + i * NT + tid;
+                if (n < nnodes) { sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int nent = (int)ssoff[nrows];
+        for (int k = tid; k < nent; k += NT) acc[k] = 0.;
+    }
+    __syncthreads();
+
+    for (int eb = e0; eb < e1; eb += NT) {
+        const int e = eb + tid;
+        const bool have = e < e1;
+        int lrow[8];
+        uint32_t posw[16];
+        double D[6], gv[8];
+        double dw = 0.;
+        bool anyc = false;
+#pragma unroll
+        for (int a = 0; a < 8; a++) { lrow[a] = 0xffff; gv[a] = 0.; }
+#pragma unroll
+        for (int c = 0; c < 6; c++) D[c] = 0.;
+        if (have) {
+            int ln[8];
+            {
+                const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)e * 8));
+                ln[0] = l4.x & 0xffff; ln[1] = (unsigned)l4.x >> 16; ln[2] = l4.y & 0xffff; ln[3] = (unsigned)l4.y >> 16;
+                ln[4] = l4.z & 0xffff; ln[5] = (unsigned)l4.z >> 16; ln[6] = l4.w & 0xffff; ln[7] = (unsigned)l4.w >> 16;
+                const int4 r4 = __ldg(reinterpret_cast<const int4*>(p.i_lrow + (size_t)e * 8));
+                lrow[0] = r4.x & 0xffff; lrow[1] = (unsigned)r4.x >> 16; lrow[2] = r4.y & 0xffff; lrow[3] = (unsigned)r4.y >> 16;
+                lrow[4] = r4.z & 0xffff; lrow[5] = (unsigned)r4.z >> 16; lrow[6] = r4.w & 0xffff; lrow[7] = (unsigned)r4.w >> 16;
+            }
+            const int4* p4 = reinterpret_cast<const int4*>(p.i_pos + (size_t)e * 64);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int4 v = __ldg(p4 + i);
+                posw[i * 4] = v.x; posw[i * 4 + 1] = v.y; posw[i * 4 + 2] = v.z; posw[i * 4 + 3] = v.w;
+            }
+            // constant Jacobian from the three edges at hierarchic node 0: nodes 1 (xi), 3 (eta), 4 (zeta)
+            double J[3][3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double x0 = sX[ln[0] * 3 + d];
+                J[d][0] = sX[ln[1] * 3 + d] - x0; J[d][1] = sX[ln[3] * 3 + d] - x0; J[d][2] = sX[ln[4] * 3 + d] - x0;
+            }
+            double co[3][3];
+            co[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            co[0][1] = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+            co[0][2] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            co[1][0] = J[0][2] * J[2][1] - J[0][1] * J[2][2];
+            co[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+            co[1][2] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+            co[2][0] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+            co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
+            co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
+            const double w = c_q1_w[0];
+            const double s = (p.factor * w) / det;
+            dw = det * w;
+            D[0] = s * (co[0][0] * co[0][0] + co[1][0] * co[1][0] + co[2][0] * co[2][0]);
+            D[1] = s * (co[0][1] * co[0][1] + co[1][1] * co[1][1] + co[2][1] * co[2][1]);
+            D[2] = s * (co[0][2] * co[0][2] + co[1][2] * co[1][2] + co[2][2] * co[2][2]);
+            D[3] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
+            D[4] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
+            D[5] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
+#pragma unroll
+            for (int b = 0; b < 8; b++) anyc |= (((posw[(b * 8 + b) >> 2] >> (((b * 8 + b) & 3) * 8)) & 0xff) == 0xff);
+            if (anyc) {
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const int32_t g = __ldg(p.nodes + n0 + ln[b]);
+                    if (p.status[g] == ISL_CONSTRAINED) gv[b] = p.incremental ? p.presc[g] - p.values[g] : p.presc[g];
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            if (lrow[a] != 0xffff) {
+                double* row = acc + ssoff[lrow[a]];
+                double kv[8], t[8];
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                    double v = D[0] * c_q1_aff[sym_idx(a, b)];
+#pragma unroll
+                    for (int c = 1; c < 6; c++) v = fma(D[c], c_q1_aff[c * 36 + sym_idx(a, b)], v);
+                    kv[b] = v;
+                    t[b] = (pos != 0xff) ? row[pos] : 0.;
+                }
+                double lift = 0.;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                    if (pos != 0xff) row[pos] = t[b] + kv[b];
+                    lift = fma(gv[b], kv[b], lift);
+                }
+                if (p.body) lift -= p.f0 * (dw * c_q1_Nsum[a]);
+                if (anyc || p.body) srhs[lrow[a]] -= lift;
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = tid; r < nrows; r += NT) {
+        const double v = srhs[r];
+        if (v != 0.) { const int32_t g = p.rows[r0 + r]; p.rhs[g] += v; }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int u = warp; u < nruns; u += NT / 32) {
+        const int64_t gstart = srun[u];
+        const int s0 = (int)srsoff[u], len = (int)srsoff[u + 1] - s0;
+        double* dst = p.val + gstart;
+        const double* src = acc + s0;
+        if (p.store_mode) {
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) dst[k] = src[k];
+        } else {
+#pragma unroll 4
+            for (int k = lane; k < len; k += 32) dst[k] += src[k];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // preprocessing
 // per element instance: uint8 position of column b inside row a (0xff when row or column is not ACTIVE)
 __global__ void k_inst_pos(const int32_t* inst_elem, const int32_t* elem_eqn, int64_t n_inst, const int64_t* rowptr,
