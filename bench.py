@@ -310,7 +310,7 @@ def main():
                        "register_fields_ms": t_register * 1e3,
                        "ms_per_step_perturbed_mesh": ms_step_perturbed},
             "achieved_hbm_gbs": ALGO_BYTES_PER_ELEM * value / world / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "k_q1hex_patch (stiffness + Dirichlet lift + body force, one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_q1hex_patch_affine (stiffness + Dirichlet lift + body force, one launch; k_q1hex_patch on non-affine meshes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}

@@ -696,6 +696,8 @@ struct isl_engine {
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
     int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
+    int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
+    int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
@@ -1007,7 +1009,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     // shared memory per CTA: accumulator (27 entries per row on a hex lattice) + coordinates of the patch's nodes
     // (owned + halo) + row metadata.  R is shrunk until the estimate fits the budget; if the real patches still
     // overflow (irregular boxes) the partition is redone with a smaller R.
-    const int smem_budget = (h->patch_ctas_per_sm >= 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024 -
+    const int smem_budget = (h->patch_ctas_per_sm >= 4 ? 55 : h->patch_ctas_per_sm == 3 ? 74 : h->patch_ctas_per_sm == 2 ? 112 : 224) * 1024 -
                             (h->patch_ws ? 2 * WS_STAGE_DOUBLES * 128 * 8 + 64 : 0);
     int rows_per_patch = h->patch_rows, cap_nodes = 0, cap_entries = 0;
     PatchHost P;
@@ -1055,6 +1057,26 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         fprintf(stderr, "[isl] patches: %d (<= %d rows), max entries %d (cap %d), max nodes %d (cap %d), element instances %.3fx, lattice %d%s\n",
                 (int)P.inst_off.size() - 1, rows_per_patch, P.max_entries, cap_entries, P.max_nodes, cap_nodes,
                 n ? (double)P.inst_elem.size() / (double)n : 0., (int)P.lattice, fits ? "" : " -> atomic fallback");
+    {
+        // CTA size of the all-affine kernel: the one whose element batches leave the fewest idle thread slots
+        double best = -1.;
+        for (int nt : {256, 288, 320}) {
+            int64_t slots = 0;
+            for (size_t q = 0; q + 1 < P.inst_off.size(); q++) slots += ((P.inst_off[q + 1] - P.inst_off[q] + nt - 1) / nt) * nt;
+            const double u = slots ? (double)P.inst_elem.size() / (double)slots : 0.;
+            if (u > best + 0.02) { best = u; ps->aff_nt = nt; }
+        }
+    }
+    if (getenv("ISL_VERBOSE")) {
+        // slot utilisation of the element batches for the CTA sizes the all-affine kernel is built for
+        fprintf(stderr, "[isl] batch slot utilisation:");
+        for (int nt : {128, 160, 192, 224, 256, 288, 320, 384, 512}) {
+            int64_t slots = 0;
+            for (size_t q = 0; q + 1 < P.inst_off.size(); q++) slots += ((P.inst_off[q + 1] - P.inst_off[q] + nt - 1) / nt) * nt;
+            fprintf(stderr, " %d:%.3f", nt, slots ? (double)P.inst_elem.size() / (double)slots : 0.);
+        }
+        fprintf(stderr, "\n");
+    }
     h->patchsets[field] = std::move(ps);
     return out;
 }
@@ -1078,7 +1100,7 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
     const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
-    if (MATRIX && h->affine_kernel && (h->q1_fast & 2) && !h->patch_ws && h->patch_ctas_per_sm == 2 && h->shape == ISL_HEX) {
+    if (MATRIX && h->affine_kernel && (h->q1_fast & 2) && !h->patch_ws && h->shape == ISL_HEX) {
         if (h->affine_state < 0) {  // once per coordinate set
             DevBuf<int> flag; flag.alloc(1);
             ISL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), h->stream));
@@ -1089,8 +1111,40 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
             h->affine_state = na ? 0 : 1;
         }
         if (h->affine_state == 1) {
-            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_affine<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ISL_LAUNCH(h, k_q1hex_patch_affine<256>, ps->n_patches, 256, smem, p);
+#define ISL_AFF_LAUNCH(NT, MINB)                                                                                        \
+    do {                                                                                                               \
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_affine<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ISL_LAUNCH(h, (k_q1hex_patch_affine<NT, MINB>), ps->n_patches, NT, smem, p);                                   \
+    } while (0)
+#define ISL_AFF_LAUNCH_S(NT, MINB)                                                                                      \
+    do {                                                                                                               \
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_affine<NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ISL_LAUNCH(h, (k_q1hex_patch_affine<NT, MINB, true>), ps->n_patches, NT, smem, p);                             \
+    } while (0)
+            const int nt = h->patch_threads_aff ? h->patch_threads_aff : ps->aff_nt;
+            switch (h->patch_ctas_per_sm) {
+                case 1: ISL_AFF_LAUNCH(512, 1); break;
+                case 2:
+                    if (nt == 192) ISL_AFF_LAUNCH(192, 2);
+                    else if (nt == 224) ISL_AFF_LAUNCH(224, 2);
+                    else if (nt == 288 && h->aff_split) ISL_AFF_LAUNCH_S(288, 2);
+                    else if (nt == 320 && h->aff_split) ISL_AFF_LAUNCH_S(320, 2);
+                    else if (nt == 288) ISL_AFF_LAUNCH(288, 2);
+                    else if (nt == 320) ISL_AFF_LAUNCH(320, 2);
+                    else if (nt == 384) ISL_AFF_LAUNCH(384, 2);
+                    else if (h->aff_split) ISL_AFF_LAUNCH_S(256, 2);
+                    else ISL_AFF_LAUNCH(256, 2);
+                    break;
+                case 3:
+                    if (nt == 256) ISL_AFF_LAUNCH(256, 3);
+                    else if (nt == 160) ISL_AFF_LAUNCH(160, 3);
+                    else if (nt == 224) ISL_AFF_LAUNCH(224, 3);
+                    else ISL_AFF_LAUNCH(192, 3);
+                    break;
+                default: ISL_AFF_LAUNCH(128, 4); break;
+            }
+#undef ISL_AFF_LAUNCH
+#undef ISL_AFF_LAUNCH_S
             return;
         }
     }
@@ -1175,10 +1229,12 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m);  // 0 reference order, 1 sum factorisation, 3 + affine shortcut
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
+        if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
-        if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(3, atoi(m)));
+        if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(4, atoi(m)));
         *out = h.release();
     });
 }

@@ -839,9 +839,19 @@ __global__ void k_check_affine(const double* coords, const int32_t* conn, int64_
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2) k_q1hex_patch_affine(const PatchParams p) {
+// SPLIT: the barrier after every phase is an mbarrier arrive / wait pair with the next local row's eight entries
+// computed in between, so the wait for the slowest warp overlaps FP64 work.
+// (register cap left to __launch_bounds__: with 9 or 10 warps per CTA the per-scheduler register file, not the SM
+// total, decides whether two CTAs fit - 96 registers, which the compiler derives itself)
+template <int NT, int MINB, bool SPLIT = false>
+__global__ void __launch_bounds__(NT, MINB) k_q1hex_patch_affine(const PatchParams p) {
     extern __shared__ double smem[];
+    __shared__ uint64_t sbar;
+    int par = 0;
+    if (SPLIT && threadIdx.x == 0) {
+        mbar_init(&sbar, NT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     double* acc = smem;
     double* sX = acc + p.acc_cap;
     double* srhs = sX + (size_t)p.node_cap * 3;
@@ -854,6 +864,19 @@ __global__ void __launch_bounds__(NT, 2) k_q1hex_patch_affine(const PatchParams 
     const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
     const int e0 = p.p_inst_off[pid], e1 = p.p_inst_off[pid + 1];
     const int u0 = p.p_run_off[pid], nruns = p.p_run_off[pid + 1] - u0;
+    if (!(p.dbg & 8)) {
+        // the patch's element instances are contiguous: pull their rows/positions into L2 while the prologue runs
+        const char* b0 = reinterpret_cast<const char*>(p.i_pos + (size_t)e0 * 64);
+        const size_t nb0 = (size_t)(e1 - e0) * 64;
+        for (size_t o = (size_t)tid * 128; o < nb0; o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
+        const char* b1 = reinterpret_cast<const char*>(p.i_lnode + (size_t)e0 * 8);
+        const char* b2 = reinterpret_cast<const char*>(p.i_lrow + (size_t)e0 * 8);
+        const size_t nb1 = (size_t)(e1 - e0) * 16;
+        for (size_t o = (size_t)tid * 128; o < nb1; o += (size_t)NT * 128) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
+        }
+    }
     for (int r = tid; r <= nrows; r += NT) ssoff[r] = p.soff[r0 + pid + r];
     for (int r = tid; r < nrows; r += NT) srhs[r] = 0.;
     for (int u = tid; u <= nruns; u += NT) {
@@ -951,31 +974,59 @@ __global__ void __launch_bounds__(NT, 2) k_q1hex_patch_affine(const PatchParams 
                 }
             }
         }
+        auto krow = [&](int a, double (&kv)[8]) {
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-            if (lrow[a] != 0xffff) {
-                double* row = acc + ssoff[lrow[a]];
-                double kv[8], t[8];
+            for (int b = 0; b < 8; b++) {
+                double v = D[0] * c_q1_aff[sym_idx(a, b)];
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
-                    double v = D[0] * c_q1_aff[sym_idx(a, b)];
+                for (int c = 1; c < 6; c++) v = fma(D[c], c_q1_aff[c * 36 + sym_idx(a, b)], v);
+                kv[b] = v;
+            }
+        };
+        auto add_row = [&](int a, const double (&kv)[8]) {
+            double* row = acc + ssoff[lrow[a]];
+            double t[8];
 #pragma unroll
-                    for (int c = 1; c < 6; c++) v = fma(D[c], c_q1_aff[c * 36 + sym_idx(a, b)], v);
-                    kv[b] = v;
-                    t[b] = (pos != 0xff) ? row[pos] : 0.;
-                }
+            for (int b = 0; b < 8; b++) {
+                const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                t[b] = (pos != 0xff) ? row[pos] : 0.;
+            }
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
+                if (pos != 0xff) row[pos] = t[b] + kv[b];
+            }
+            if (anyc || p.body) {
                 double lift = 0.;
+                if (anyc) {
 #pragma unroll
-                for (int b = 0; b < 8; b++) {
-                    const int pos = (posw[(a * 8 + b) >> 2] >> (((a * 8 + b) & 3) * 8)) & 0xff;
-                    if (pos != 0xff) row[pos] = t[b] + kv[b];
-                    lift = fma(gv[b], kv[b], lift);
+                    for (int b = 0; b < 8; b++) lift = fma(gv[b], kv[b], lift);
                 }
                 if (p.body) lift -= p.f0 * (dw * c_q1_Nsum[a]);
-                if (anyc || p.body) srhs[lrow[a]] -= lift;
+                srhs[lrow[a]] -= lift;
             }
-            __syncthreads();
+        };
+        if (SPLIT) {
+            double kv[8];
+            if (lrow[0] != 0xffff) krow(0, kv);
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                if (lrow[a] != 0xffff) add_row(a, kv);
+                mbar_arrive(&sbar);
+                if (a < 7) { if (lrow[a + 1] != 0xffff) krow(a + 1, kv); }
+                mbar_wait(&sbar, par);
+                par ^= 1;
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                if (lrow[a] != 0xffff) {
+                    double kv[8];
+                    krow(a, kv);
+                    add_row(a, kv);
+                }
+                __syncthreads();
+            }
         }
     }
     for (int r = tid; r < nrows; r += NT) {
@@ -1019,6 +1070,7 @@ __global__ void k_inst_pos(const int32_t* inst_elem, const int32_t* elem_eqn, in
 }
 
 struct PatchSet {
+    int aff_nt = 256;  // CTA size chosen for the all-affine kernel
     bool usable = false;  // false: the mesh does not fit the patch kernel (atomic fallback)
     int n_patches = 0, max_entries = 0, max_rows = 0, max_nodes = 0;
     int64_t n_inst = 0, n_elems = 0;

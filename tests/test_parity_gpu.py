@@ -158,7 +158,8 @@ def test_large_mesh_properties(eng):
                                  {"ISL_PATCH_ROWS": "200", "ISL_PATCH_THREADS": "256"}, {"ISL_PATCH_ROWS": "360"},
                                  {"ISL_PATCH_ROWS": "512", "ISL_PATCH_THREADS": "256", "ISL_PATCH_CTAS": "1"},
                                  {"ISL_PATCH_WS": "1"}, {"ISL_PATCH_WS": "1", "ISL_PATCH_ROWS": "120"}, {"ISL_Q1_FAST": "3"},
-                                 {"ISL_AFFINE_KERNEL": "0"}])
+                                 {"ISL_AFFINE_KERNEL": "0"}, {"ISL_AFF_SPLIT": "1", "ISL_AFF_THREADS": "288"},
+                                 {"ISL_AFF_THREADS": "320"}, {"ISL_PATCH_CTAS": "3", "ISL_PATCH_ROWS": "260"}])
 @pytest.mark.parametrize("name,n,permute", [("laplace_q1_hex", 13, False), ("laplace_q1_hex_values", 9, True)])
 def test_q1_hot_path_variants(monkeypatch, env, name, n, permute):
     """one-thread-per-element atomic kernel and shared-memory patch kernel (several patch sizes, Morton ordering of a
