@@ -648,6 +648,7 @@ __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const d
 }
 
 #include "isl_patch.cuh"
+#include "isl_rowgather.cuh"
 
 // ---------------------------------------------------------------------------------------------
 struct FieldDev {
@@ -696,6 +697,8 @@ struct isl_engine {
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
     int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
+    int q1_rows = 0;            // ISL_Q1_ROWS=1: row-gather kernel on all-affine meshes (isl_rowgather.cuh; not yet default)
+    int rows_threads = 256;     // its CTA size (ISL_ROWS_THREADS)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1027,6 +1030,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         bounds[n_leaves] = (int64_t)perm_try.size();
         if (!perm_try.empty()) rcb_split(perm_try.data(), rowxyz.data(), 0, (int64_t)perm_try.size(), (int)n_leaves, 0, bounds.data(), 0);
         P = PatchHost();
+        P.want_slots = h->q1_rows != 0;
         form_patches(perm_try, bounds, heqn, hconn, hrowptr, h->n_eqn, h->n_nodes, cap_entries, cap_nodes, P);
         if (!P.lattice || (P.max_entries <= cap_entries && P.max_nodes <= cap_nodes) || rows_per_patch <= 16) break;
         rows_per_patch = (int)(rows_per_patch * 0.88);
@@ -1052,6 +1056,30 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         if (!err) { ps->usable = true; out = ps.get(); } else ps->n_patches = 0;
+        if (!err && h->q1_rows && P.lattice && ps->n_patches > 0) {
+            // row-gather tables (isl_rowgather.cuh): slots from the host, positions / eligibility on the device
+            DevBuf<uint16_t> rslot; upload_vec(h, rslot, P.rslot);
+            const size_t nr = P.rows.size();
+            ps->r_meta.alloc(nr * sizeof(RowMeta)); ps->r_rowstart.alloc(nr);
+            DevBuf<int> cnt; cnt.alloc(2);
+            ISL_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int), h->stream));
+            ISL_LAUNCH(h, k_row_meta, ps->n_patches, 128, 0, 0, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p,
+                       h->conn.p, f.eqn.p, f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p),
+                       ps->r_rowstart.p, (int32_t*)nullptr, cnt.p, cnt.p + 1);
+            int hc[2] = {0, 0};
+            ISL_CUDA(cudaMemcpyAsync(hc, cnt.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            if (!hc[1]) {
+                ps->lift_nodes.alloc((size_t)std::max(1, hc[0]) * 27);
+                if (hc[0] > 0)
+                    ISL_LAUNCH(h, k_row_meta, ps->n_patches, 128, 0, 1, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p,
+                               h->conn.p, f.eqn.p, f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p),
+                               ps->r_rowstart.p, ps->lift_nodes.p, cnt.p, cnt.p + 1);
+                ISL_CUDA(cudaStreamSynchronize(h->stream));
+                ps->rows_ok = true; ps->max_inst = P.max_inst;
+            }
+            if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] row-gather tables: %s, %d rows next to constrained nodes\n", ps->rows_ok ? "ok" : "not eligible", hc[0]);
+        }
     }
     if (getenv("ISL_VERBOSE"))
         fprintf(stderr, "[isl] patches: %d (<= %d rows), max entries %d (cap %d), max nodes %d (cap %d), element instances %.3fx, lattice %d%s\n",
@@ -1100,7 +1128,7 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
     const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
-    if (MATRIX && h->affine_kernel && (h->q1_fast & 2) && !h->patch_ws && h->shape == ISL_HEX) {
+    if (MATRIX && (h->affine_kernel || h->q1_rows) && (h->q1_fast & 2) && !h->patch_ws && h->shape == ISL_HEX) {
         if (h->affine_state < 0) {  // once per coordinate set
             DevBuf<int> flag; flag.alloc(1);
             ISL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), h->stream));
@@ -1110,7 +1138,31 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
             ISL_CUDA(cudaStreamSynchronize(h->stream));
             h->affine_state = na ? 0 : 1;
         }
-        if (h->affine_state == 1) {
+        if (h->affine_state == 1 && h->q1_rows && ps->rows_ok) {
+            RowsParams q;
+            q.coords = h->coords.p; q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
+            q.rows = ps->rows.p; q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
+            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.rowstart = ps->r_rowstart.p; q.lift_nodes = ps->lift_nodes.p;
+            q.status = p.status; q.presc = p.presc; q.values = p.values; q.val = p.val; q.rhs = p.rhs;
+            q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
+            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 1) & ~1;
+            const int nt = h->rows_threads;
+            const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
+#define ISL_ROWS_LAUNCH(NT, MINB)                                                                                       \
+    do {                                                                                                               \
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
+        ISL_LAUNCH(h, (k_q1hex_rows_affine<NT, MINB>), ps->n_patches, NT, smem_r, q);                                 \
+    } while (0)
+            if (nt == 128) ISL_ROWS_LAUNCH(128, 4);
+            else if (nt == 192) ISL_ROWS_LAUNCH(192, 2);
+            else if (nt == 320) ISL_ROWS_LAUNCH(320, 2);
+            else if (nt == 384) ISL_ROWS_LAUNCH(384, 1);
+            else if (nt == 512) ISL_ROWS_LAUNCH(512, 1);
+            else ISL_ROWS_LAUNCH(256, 2);
+#undef ISL_ROWS_LAUNCH
+            return;
+        }
+        if (h->affine_state == 1 && h->affine_kernel) {
 #define ISL_AFF_LAUNCH(NT, MINB)                                                                                        \
     do {                                                                                                               \
         ISL_CUDA(cudaFuncSetAttribute(k_q1hex_patch_affine<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1232,6 +1284,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
         if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
+        if (const char* m = getenv("ISL_Q1_ROWS")) { h->q1_rows = atoi(m) ? 1 : 0; if (h->q1_rows) h->patch_rows = 256; }
+        if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
         if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(4, atoi(m)));

@@ -1,0 +1,172 @@
+// Host emulation of the row-gather kernel (insilico_b200/csrc/isl_rowgather.cuh) -- TEST INFRASTRUCTURE ONLY.
+// Compiles the kernel's per-thread routines (rg_instance, rg_add_slot, rg_row_tables) and the host preprocessing
+// (isl_patch_host.hpp) with g++ and replays k_row_meta / k_q1hex_rows_affine patch by patch, thread by thread, including
+// the per-warp staging (segmented shuffle scan, sixteen rows per round), so that the algorithm, its tables and its
+// index arithmetic can be checked against the oracle on a machine without a GPU (tests/test_rowgather_emu.py).
+// Nothing in the product links or loads this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/insilico_b200.h"
+#include "../../insilico_b200/csrc/isl_tables.hpp"
+
+namespace {
+constexpr int sym_idx(int a, int b) {
+    return (a < b) ? (a * 8 - (a * (a - 1)) / 2 + (b - a)) : (b * 8 - (b * (b - 1)) / 2 + (a - b));
+}
+#include "../../insilico_b200/csrc/isl_patch_host.hpp"
+#include "../../insilico_b200/csrc/isl_rowgather.cuh"
+
+double g_w0 = 0.;
+void fill_tables() {
+    // same construction as load_q1_tables (isl_engine.cu): C_c[a][b] and sum_q N_a(q) on the 8-point rule
+    const isl::Rule R = isl::make_rule(ISL_HEX, 3);
+    const isl::Basis B(ISL_HEX, 1);
+    std::vector<double> dN(8 * 8 * 3), N(8), Nq(64);
+    for (int q = 0; q < 8; q++) { B.eval(&R.p[q * 3], N.data(), &dN[q * 24]); for (int a = 0; a < 8; a++) Nq[q * 8 + a] = N[a]; }
+    const int al[6] = {0, 1, 2, 0, 0, 1}, be[6] = {0, 1, 2, 1, 2, 2};
+    for (int c = 0; c < 6; c++)
+        for (int a = 0; a < 8; a++)
+            for (int b = a; b < 8; b++) {
+                double v = 0.;
+                for (int q = 0; q < 8; q++) {
+                    v += dN[q * 24 + a * 3 + al[c]] * dN[q * 24 + b * 3 + be[c]];
+                    if (al[c] != be[c]) v += dN[q * 24 + a * 3 + be[c]] * dN[q * 24 + b * 3 + al[c]];
+                }
+                rg_host_aff[c * 36 + sym_idx(a, b)] = v;
+            }
+    for (int a = 0; a < 8; a++) { rg_host_nsum[a] = 0.; for (int q = 0; q < 8; q++) rg_host_nsum[a] += Nq[q * 8 + a]; }
+    g_w0 = R.w[0];
+}
+
+template <int A>
+void gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
+    const int s = m.slot[A];
+    if (s != 0xffff) {
+        double D[6];
+        for (int c = 0; c < 6; c++) D[c] = sD[c * cap + s];
+        rg_add_slot<A>(D, sD[6 * cap + s], acc, body);
+    }
+}
+}  // namespace
+
+extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coords, const int32_t* conn,
+                             const int32_t* node_eqn, const uint8_t* status, const double* presc, const double* values,
+                             int64_t n_eqn, const int64_t* rowptr, const int32_t* col, double factor, double f0, int body,
+                             int incremental, int store_mode, int rows_per_patch, int NT, double* val, double* rhs,
+                             int64_t* stats /* [patches, instances, flagged rows] */) {
+    fill_tables();
+    std::vector<int32_t> heqn((size_t)n_elems * 8), hconn(conn, conn + (size_t)n_elems * 8);
+    for (int64_t k = 0; k < n_elems * 8; k++) heqn[k] = node_eqn[conn[k]];
+    std::vector<int64_t> hrowptr(rowptr, rowptr + n_eqn + 1);
+    std::vector<double> rowxyz((size_t)n_eqn * 3, 0.);
+    std::vector<int32_t> perm;
+    for (int64_t nd = 0; nd < n_nodes; nd++) {
+        const int32_t r = node_eqn[nd];
+        if (r < 0) continue;
+        for (int d = 0; d < 3; d++) rowxyz[(size_t)r * 3 + d] = coords[(size_t)nd * 3 + d];
+        perm.push_back(r);
+    }
+    const int64_t n_leaves = std::max<int64_t>(1, ((int64_t)perm.size() + rows_per_patch - 1) / rows_per_patch);
+    std::vector<int64_t> bounds(n_leaves + 1, 0);
+    bounds[n_leaves] = (int64_t)perm.size();
+    if (!perm.empty()) rcb_split(perm.data(), rowxyz.data(), 0, (int64_t)perm.size(), (int)n_leaves, 0, bounds.data(), 0);
+    PatchHost P;
+    P.want_slots = true;
+    form_patches(perm, bounds, heqn, hconn, hrowptr, n_eqn, n_nodes, 1 << 30, 1 << 30, P);
+    if (!P.lattice) return 1;
+    const int n_patches = (int)P.inst_off.size() - 1;
+    const size_t nr = P.rows.size();
+    // k_row_meta, pass 0 and 1
+    std::vector<RowMeta> meta(nr);
+    std::vector<int64_t> rowstart(nr);
+    std::vector<int32_t> lift_nodes;
+    int counter = 0;
+    for (int pid = 0; pid < n_patches; pid++) {
+        const int r0 = P.row_off[pid], nrows = P.row_off[pid + 1] - r0;
+        const int32_t* ie = P.inst_elem.data() + P.inst_off[pid];
+        for (int r = 0; r < nrows; r++) {
+            const int32_t g = P.rows[r0 + r];
+            RowMeta m; int32_t nbn[27]; bool cnb = false;
+            if (!rg_row_tables(g, P.rslot.data() + (size_t)(r0 + r) * 8, ie, conn, node_eqn, status, rowptr, col, m, nbn, cnb)) return 1;
+            if (cnb) { m.lift = counter++; lift_nodes.insert(lift_nodes.end(), nbn, nbn + 27); }
+            meta[r0 + r] = m;
+            rowstart[r0 + r] = rowptr[g];
+        }
+    }
+    stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter;
+    const int inst_cap = (P.max_inst + 1) & ~1;
+    std::vector<double> sD((size_t)7 * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
+    for (int pid = 0; pid < n_patches; pid++) {
+        const int r0 = P.row_off[pid], nrows = P.row_off[pid + 1] - r0;
+        const int n0 = P.node_off[pid], nnodes = P.node_off[pid + 1] - n0;
+        const int e0 = P.inst_off[pid], ninst = P.inst_off[pid + 1] - e0;
+        for (int n = 0; n < nnodes; n++) for (int d = 0; d < 3; d++) sX[n * 3 + d] = coords[(size_t)P.nodes[n0 + n] * 3 + d];
+        // phase 1
+        for (int i = 0; i < ninst; i++) {
+            const uint16_t* ln = P.lnode.data() + (size_t)(e0 + i) * 8;
+            double D[6], dw;
+            rg_instance(&sX[ln[0] * 3], &sX[ln[1] * 3], &sX[ln[3] * 3], &sX[ln[4] * 3], factor, g_w0, D, dw);
+            for (int c = 0; c < 6; c++) sD[c * inst_cap + i] = D[c];
+            sD[6 * inst_cap + i] = dw;
+        }
+        // phase 2, warp by warp (32 lanes in lock step)
+        for (int rb = 0; rb < nrows; rb += NT) {
+            for (int warp = 0; warp < NT / 32; warp++) {
+                double* st = stage.data() + (size_t)warp * 16 * 27;
+                RowMeta m[32]; int64_t rs[32]; double acc[32][27]; int myn[32]; bool act[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    const int tid = warp * 32 + lane, r = rb + tid;
+                    act[lane] = r < nrows; rs[lane] = 0; myn[lane] = 0;
+                    for (int k = 0; k < 27; k++) acc[lane][k] = 0.;
+                    if (!act[lane]) continue;
+                    m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz;
+                    double bsum = 0.;
+                    gather_slot<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    gather_slot<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    gather_slot<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    gather_slot<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    double lift = 0.;
+                    if (m[lane].lift >= 0) {
+                        const int32_t* ln = lift_nodes.data() + (size_t)m[lane].lift * 27;
+                        for (int k = 0; k < 27; k++) {
+                            const int32_t nd = ln[k];
+                            if (nd >= 0 && m[lane].pos[k] == 0xff && status[nd] == ISL_CONSTRAINED) {
+                                const double gv = incremental ? presc[nd] - values[nd] : presc[nd];
+                                lift = std::fma(gv, acc[lane][k], lift);
+                            }
+                        }
+                    }
+                    const double v = (body ? f0 * bsum : 0.) - lift;
+                    if (v != 0.) rhs[P.rows[r0 + r]] += v;
+                }
+                for (int h = 0; h < 2; h++) {
+                    int incl[32], off[32];
+                    for (int lane = 0; lane < 32; lane++) incl[lane] = ((lane >> 4) == h) ? myn[lane] : 0;
+                    for (int d = 1; d < 16; d <<= 1) {  // __shfl_up_sync(.., d, 16): segments of 16 lanes
+                        int v[32];
+                        for (int lane = 0; lane < 32; lane++) v[lane] = ((lane & 15) >= d) ? incl[lane - d] : incl[lane];
+                        for (int lane = 0; lane < 32; lane++) if ((lane & 15) >= d) incl[lane] += v[lane];
+                    }
+                    for (int lane = 0; lane < 32; lane++) off[lane] = incl[lane] - (((lane >> 4) == h) ? myn[lane] : 0);
+                    for (int lane = 0; lane < 32; lane++)
+                        if ((lane >> 4) == h && act[lane])
+                            for (int k = 0; k < 27; k++) if (m[lane].pos[k] != 0xff) st[off[lane] + m[lane].pos[k]] = acc[lane][k];
+                    for (int j = 0; j < 16; j++) {
+                        const int src = h * 16 + j;
+                        for (int lane = 0; lane < 32; lane++)
+                            if (lane < myn[src]) {
+                                if (store_mode) val[rs[src] + lane] = st[off[src] + lane];
+                                else val[rs[src] + lane] += st[off[src] + lane];
+                            }
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}

@@ -250,3 +250,46 @@ def test_inactive_dofs_are_skipped(eng):
     r = flows.compare(ref, out)
     assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
     assert c.n_eqn < 4 ** 3
+
+
+def test_affine_kernel_multi_patch_equals_general_kernel(monkeypatch):
+    """unperturbed 40^3 mesh (all elements affine, ~160 patches): the all-affine kernel and the general patch kernel
+    (ISL_AFFINE_KERNEL=0) produce the same system; a permuted 14^3 mesh is also compared with the oracle."""
+    c = flows.build_case("laplace_q1_hex", 14, False, True)
+    ref = c.run_oracle()
+    big = flows.build_case("laplace_q1_hex", 40, False, False)
+    outs = []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("ISL_AFFINE_KERNEL", knob)
+        e = E.Engine(0)
+        try:
+            r = flows.compare(ref, c.run_engine(eng=e))
+            assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+            outs.append(big.run_engine(eng=e))
+        finally:
+            e.close()
+    r = flows.compare(outs[0], outs[1])
+    assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("ISL_TEST_EXPERIMENTAL"),
+                    reason="row-gather kernel (ISL_Q1_ROWS=1) is not the default yet: set ISL_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("threads", ["256", "320", "128"])
+def test_rowgather_kernel_equals_oracle(monkeypatch, threads):
+    """isl_rowgather.cuh on the device (the same routines pass tests/test_rowgather_emu.py on the host)."""
+    monkeypatch.setenv("ISL_Q1_ROWS", "1")
+    monkeypatch.setenv("ISL_ROWS_THREADS", threads)
+    monkeypatch.setenv("ISL_PATCH_ROWS", "100")
+    e = E.Engine(0)
+    try:
+        for name, n, permute in [("laplace_q1_hex", 13, False), ("laplace_q1_hex_values", 9, True)]:
+            c = flows.build_case(name, n, False, permute)
+            ref = c.run_oracle()
+            r = flows.compare(ref, c.run_engine(eng=e))
+            assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+            ops = c.ops
+            c.ops = [ops[0], ops[0]]     # second assembly accumulates into complete rows
+            r2 = flows.compare(c.run_oracle(), c.run_engine(eng=e))
+            assert r2["pattern_equal"] and r2["val_diff"] <= TOL and r2["rhs_diff"] <= TOL, r2
+    finally:
+        e.close()
