@@ -46,33 +46,23 @@ inline void rcb_split(int32_t* idx, const double* xyz, int64_t lo, int64_t hi, i
     }
 }
 
-inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector<int64_t>& leaf_bounds,
-                         const std::vector<int32_t>& eqn /* [n][8] */,
-                         const std::vector<int32_t>& conn /* [n][8] */, const std::vector<int64_t>& rowptr, int64_t n_eqn,
-                         int64_t n_nodes, int cap_entries, int cap_nodes, PatchHost& P) {
-    const int64_t n = (int64_t)eqn.size() / 8;
-    // row -> incident (element, local index) lists
-    std::vector<int64_t> adj_ptr(n_eqn + 1, 0);
-    for (int64_t k = 0; k < n * 8; k++) if (eqn[k] >= 0) adj_ptr[eqn[k] + 1]++;
-    for (int64_t r = 0; r < n_eqn; r++) adj_ptr[r + 1] += adj_ptr[r];
-    std::vector<int32_t> adj(adj_ptr[n_eqn]);
-    {
-        std::vector<int64_t> cur(adj_ptr.begin(), adj_ptr.end() - 1);
-        for (int64_t e = 0; e < n; e++)
-            for (int a = 0; a < 8; a++) { const int32_t g = eqn[e * 8 + a]; if (g >= 0) adj[cur[g]++] = (int32_t)e; }
-    }
-    std::vector<int32_t> row_stamp(n_eqn, -1), row_l(n_eqn, 0), el_stamp(n, -1), node_stamp(n_nodes, -1), node_l(n_nodes, 0);
+// patches of the leaves [leaf_lo, leaf_hi) appended to P (offsets relative to P); no global scratch arrays, so several
+// ranges can be formed concurrently: candidate elements are deduplicated by sort + unique, nodes get their local index
+// (order of first appearance over the sorted elements) through a small open-addressing table, rows by binary search
+// in the patch's sorted row list
+inline void form_patch_range(int64_t leaf_lo, int64_t leaf_hi, const std::vector<int32_t>& row_perm,
+                             const std::vector<int64_t>& leaf_bounds, const std::vector<int32_t>& eqn,
+                             const std::vector<int32_t>& conn, const std::vector<int64_t>& rowptr,
+                             const std::vector<int64_t>& adj_ptr, const std::vector<int32_t>& adj, PatchHost& P) {
     std::vector<uint8_t> amask;
-    int pid = 0;
-    const int64_t n_leaves = (int64_t)leaf_bounds.size() - 1;
-    for (int64_t leaf = 0; leaf < n_leaves; leaf++) {
+    std::vector<int32_t> hkey, hval;
+    for (int64_t leaf = leaf_lo; leaf < leaf_hi; leaf++) {
         // rows of this patch
         const size_t rbase = P.rows.size();
         int entries = 0, nrows = 0;
         for (int64_t k = leaf_bounds[leaf]; k < leaf_bounds[leaf + 1]; k++) {
             const int32_t g = row_perm[k];
             const int nnz = (int)(rowptr[g + 1] - rowptr[g]);
-            row_stamp[g] = pid; row_l[g] = nrows;
             P.rows.push_back(g); P.soff.push_back((uint32_t)entries);
             entries += nnz; nrows++;
         }
@@ -95,24 +85,28 @@ inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector
         const size_t ibase = P.inst_elem.size();
         for (int r = 0; r < nrows; r++) {
             const int32_t g = P.rows[rbase + r];
-            for (int64_t j = adj_ptr[g]; j < adj_ptr[g + 1]; j++) {
-                const int32_t e = adj[j];
-                if (el_stamp[e] == pid) continue;
-                el_stamp[e] = pid;
-                P.inst_elem.push_back(e);
-            }
+            P.inst_elem.insert(P.inst_elem.end(), adj.begin() + adj_ptr[g], adj.begin() + adj_ptr[g + 1]);
         }
         std::sort(P.inst_elem.begin() + ibase, P.inst_elem.end());
+        P.inst_elem.erase(std::unique(P.inst_elem.begin() + ibase, P.inst_elem.end()), P.inst_elem.end());
+        const size_t ninst = P.inst_elem.size() - ibase;
+        size_t hcap = 64;
+        while (hcap < ninst * 16) hcap <<= 1;  // <= 8 ninst distinct nodes: load factor <= 1/2
+        hkey.assign(hcap, -1); hval.resize(hcap);
+        const int32_t* prow = P.rows.data() + rbase;
         int nnodes = 0;
         for (size_t ii = ibase; ii < P.inst_elem.size(); ii++) {
             const int32_t e = P.inst_elem[ii];
             for (int a = 0; a < 8; a++) {
                 const int32_t nd = conn[(size_t)e * 8 + a];
-                if (node_stamp[nd] != pid) { node_stamp[nd] = pid; node_l[nd] = nnodes++; P.nodes.push_back(nd); }
-                P.lnode.push_back((uint16_t)node_l[nd]);
+                size_t hq = ((uint32_t)nd * 2654435761u) & (hcap - 1);
+                while (hkey[hq] != -1 && hkey[hq] != nd) hq = (hq + 1) & (hcap - 1);
+                if (hkey[hq] == -1) { hkey[hq] = nd; hval[hq] = nnodes++; P.nodes.push_back(nd); }
+                P.lnode.push_back((uint16_t)hval[hq]);
                 const int32_t ge = eqn[(size_t)e * 8 + a];
-                if (ge >= 0 && row_stamp[ge] == pid) {
-                    const int l = row_l[ge];
+                const int32_t* it = ge >= 0 ? std::lower_bound(prow, prow + nrows, ge) : prow + nrows;
+                if (it != prow + nrows && *it == ge) {
+                    const int l = (int)(it - prow);
                     P.lrow.push_back((uint16_t)l);
                     if (amask[l] & (1u << a)) P.lattice = false;  // two elements see this row as local row a
                     amask[l] |= (uint8_t)(1u << a);
@@ -126,8 +120,95 @@ inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector
         P.max_entries = std::max(P.max_entries, entries);
         P.max_rows = std::max(P.max_rows, nrows);
         P.max_nodes = std::max(P.max_nodes, nnodes);
-        P.max_inst = std::max(P.max_inst, (int)(P.inst_elem.size() - ibase));
-        pid++;
+        P.max_inst = std::max(P.max_inst, (int)ninst);
     }
-    (void)cap_nodes; (void)cap_entries;
+}
+
+inline void form_patches(const std::vector<int32_t>& row_perm, const std::vector<int64_t>& leaf_bounds,
+                         const std::vector<int32_t>& eqn /* [n][8] */,
+                         const std::vector<int32_t>& conn /* [n][8] */, const std::vector<int64_t>& rowptr, int64_t n_eqn,
+                         int64_t n_nodes, int cap_entries, int cap_nodes, PatchHost& P) {
+    const int64_t n = (int64_t)eqn.size() / 8;
+#ifdef ISL_PREP_TIMING
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tt0 = tnow();
+#endif
+    // row -> incident element lists; every host thread scans all elements and keeps the rows of its own range
+    const int64_t n_leaves = (int64_t)leaf_bounds.size() - 1;
+    const int T = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), std::max<int64_t>(1, n_leaves / 64));
+    auto run_threads = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (int t = 0; t + 1 < T; t++) th.emplace_back([&fn, t] { fn(t); });
+        fn(T - 1);
+        for (auto& x : th) x.join();
+    };
+    std::vector<int64_t> adj_ptr(n_eqn + 1, 0);
+    run_threads([&](int t) {
+        const int64_t lo = n_eqn * t / T, hi = n_eqn * (t + 1) / T;
+        for (int64_t k = 0; k < n * 8; k++) { const int64_t g = eqn[k]; if (g >= lo && g < hi) adj_ptr[g + 1]++; }
+    });
+    for (int64_t r = 0; r < n_eqn; r++) adj_ptr[r + 1] += adj_ptr[r];
+    std::vector<int32_t> adj(adj_ptr[n_eqn]);
+    {
+        std::vector<int64_t> cur(adj_ptr.begin(), adj_ptr.end() - 1);
+        run_threads([&](int t) {
+            const int64_t lo = n_eqn * t / T, hi = n_eqn * (t + 1) / T;
+            for (int64_t k = 0; k < n * 8; k++) { const int64_t g = eqn[k]; if (g >= lo && g < hi) adj[cur[g]++] = (int32_t)(k >> 3); }
+        });
+    }
+#ifdef ISL_PREP_TIMING
+    const double tt1 = tnow();
+#endif
+    // contiguous ranges of leaves on the host threads, concatenated in leaf order
+    std::vector<PatchHost> part(T);
+    run_threads([&](int t) {
+        part[t].want_slots = P.want_slots;
+        const int64_t lo = n_leaves * t / T, hi = n_leaves * (t + 1) / T;
+        const size_t nr = (size_t)(leaf_bounds[hi] - leaf_bounds[lo]), ni = nr * 2 + 1024;  // ~1.5 instances per row
+        PatchHost& Q = part[t];
+        Q.rows.reserve(nr); Q.soff.reserve(nr + (size_t)(hi - lo)); Q.inst_elem.reserve(ni); Q.nodes.reserve(ni * 2);
+        Q.lnode.reserve(ni * 8); Q.lrow.reserve(ni * 8);
+        if (Q.want_slots) Q.rslot.reserve(nr * 8);
+        form_patch_range(lo, hi, row_perm, leaf_bounds, eqn, conn, rowptr, adj_ptr, adj, Q);
+    });
+#ifdef ISL_PREP_TIMING
+    const double tt2 = tnow();
+#endif
+    {
+        // offsets of every part in the concatenation, then the large arrays are copied by the threads
+        std::vector<size_t> bi(T + 1, P.inst_elem.size()), br(T + 1, P.rows.size()), bn(T + 1, P.nodes.size()), bu(T + 1, P.run_start.size()),
+            bs(T + 1, P.soff.size()), bq(T + 1, P.run_soff.size());
+        for (int t = 0; t < T; t++) {
+            const PatchHost& Q = part[t];
+            bi[t + 1] = bi[t] + Q.inst_elem.size(); br[t + 1] = br[t] + Q.rows.size(); bn[t + 1] = bn[t] + Q.nodes.size();
+            bu[t + 1] = bu[t] + Q.run_start.size(); bs[t + 1] = bs[t] + Q.soff.size(); bq[t + 1] = bq[t] + Q.run_soff.size();
+            for (size_t k = 1; k < Q.inst_off.size(); k++) {
+                P.inst_off.push_back(Q.inst_off[k] + (int32_t)bi[t]); P.row_off.push_back(Q.row_off[k] + (int32_t)br[t]);
+                P.node_off.push_back(Q.node_off[k] + (int32_t)bn[t]); P.run_off.push_back(Q.run_off[k] + (int32_t)bu[t]);
+            }
+            P.max_entries = std::max(P.max_entries, Q.max_entries); P.max_rows = std::max(P.max_rows, Q.max_rows);
+            P.max_nodes = std::max(P.max_nodes, Q.max_nodes); P.max_inst = std::max(P.max_inst, Q.max_inst);
+            P.lattice = P.lattice && Q.lattice;
+        }
+        P.inst_elem.resize(bi[T]); P.rows.resize(br[T]); P.nodes.resize(bn[T]); P.run_start.resize(bu[T]); P.soff.resize(bs[T]);
+        P.run_soff.resize(bq[T]); P.lnode.resize(bi[T] * 8); P.lrow.resize(bi[T] * 8);
+        if (P.want_slots) P.rslot.resize(br[T] * 8);
+        run_threads([&](int t) {
+            PatchHost& Q = part[t];
+            std::copy(Q.inst_elem.begin(), Q.inst_elem.end(), P.inst_elem.begin() + bi[t]);
+            std::copy(Q.rows.begin(), Q.rows.end(), P.rows.begin() + br[t]);
+            std::copy(Q.nodes.begin(), Q.nodes.end(), P.nodes.begin() + bn[t]);
+            std::copy(Q.run_start.begin(), Q.run_start.end(), P.run_start.begin() + bu[t]);
+            std::copy(Q.soff.begin(), Q.soff.end(), P.soff.begin() + bs[t]);
+            std::copy(Q.run_soff.begin(), Q.run_soff.end(), P.run_soff.begin() + bq[t]);
+            std::copy(Q.lnode.begin(), Q.lnode.end(), P.lnode.begin() + bi[t] * 8);
+            std::copy(Q.lrow.begin(), Q.lrow.end(), P.lrow.begin() + bi[t] * 8);
+            if (P.want_slots) std::copy(Q.rslot.begin(), Q.rslot.end(), P.rslot.begin() + br[t] * 8);
+            Q = PatchHost();
+        });
+    }
+#ifdef ISL_PREP_TIMING
+    fprintf(stderr, "[prep] adjacency %.3f s, patches (%d threads) %.3f s, merge %.3f s\n", tt1 - tt0, T, tt2 - tt1, tnow() - tt2);
+#endif
+    (void)cap_nodes; (void)cap_entries; (void)n_nodes;
 }

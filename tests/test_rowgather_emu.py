@@ -69,7 +69,8 @@ def sheared(n, permute):
 
 
 @pytest.mark.parametrize("n,permute,rows_per_patch,nt", [(5, False, 400, 64), (7, True, 40, 64), (9, False, 100, 128),
-                                                          (8, True, 37, 32)])
+                                                          (8, True, 37, 32),
+                                                          (20, True, 16, 32)])  # 428 patches: threaded preprocessing
 def test_rowgather_equals_oracle(emu, n, permute, rows_per_patch, nt):
     c = flows.build_case("laplace_q1_hex", n, False, permute)   # stiffness (incremental) + body force f = 1
     ref = c.run_oracle()
