@@ -1162,6 +1162,28 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
 #undef ISL_ROWS_LAUNCH
             return;
         }
+        if (h->affine_state == 0 && h->q1_rows && ps->rows_ok) {
+            // general elements: 44 doubles per instance in shared memory; falls through to the patch kernel when a patch does not fit
+            RowsParams q;
+            q.coords = h->coords.p; q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
+            q.rows = ps->rows.p; q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
+            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.rowstart = ps->r_rowstart.p; q.lift_nodes = ps->lift_nodes.p;
+            q.status = p.status; q.presc = p.presc; q.values = p.values; q.val = p.val; q.rhs = p.rhs;
+            q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
+            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 1) & ~1;
+            const int nt = h->rows_threads == 128 ? 128 : 256;
+            const size_t smem_g = (size_t)44 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
+            if (smem_g <= (size_t)227 * 1024) {
+                if (nt == 128) {
+                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_general<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+                    ISL_LAUNCH(h, (k_q1hex_rows_general<128, 2>), ps->n_patches, 128, smem_g, q);
+                } else {
+                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_general<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+                    ISL_LAUNCH(h, (k_q1hex_rows_general<256, 1>), ps->n_patches, 256, smem_g, q);
+                }
+                return;
+            }
+        }
         if (h->affine_state == 1 && h->affine_kernel) {
 #define ISL_AFF_LAUNCH(NT, MINB)                                                                                        \
     do {                                                                                                               \

@@ -105,6 +105,17 @@ RG_HD void rg_add_slot(const double (&D)[6], double dw, double (&acc)[27], doubl
     body = fma(dw, RG_NSUM(A), body);
 }
 
+// general (non-affine) elements: the element's symmetric local matrix (36 numbers) and its body-force integrals
+// sum_q N_a w det J (8 numbers) are taken from the patch's instance table instead of being formed from D
+template <int A, class LoadK>
+RG_HD void rg_add_slot_general(LoadK&& ld, double (&acc)[27], double& body) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int b = 0; b < 8; b++) acc[rg_kidx(A, b)] += ld(sym_idx(A, b));
+    body += ld(36 + A);
+}
+
 // binary search of column c in CSR row r; -1 when absent
 RG_HD int64_t rg_find(const int64_t* rowptr, const int32_t* col, int32_t r, int32_t c) {
     int64_t lo = rowptr[r], hi = rowptr[r + 1];
@@ -304,6 +315,128 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
         }
         // matrix: sixteen rows at a time through the warp's staging buffer into CSR order, then row-contiguous stores
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const bool mine = (lane >> 4) == h;
+            int incl = mine ? myn : 0;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
+                if ((lane & 15) >= d) incl += v;
+            }
+            const int off = incl - (mine ? myn : 0);
+            if (mine && act) {
+#pragma unroll
+                for (int k = 0; k < 27; k++)
+                    if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j < 16; j++) {
+                const int src = h * 16 + j;
+                const int64_t rsj = __shfl_sync(0xffffffffu, rs, src);
+                const int nj = __shfl_sync(0xffffffffu, myn, src);
+                const int oj = __shfl_sync(0xffffffffu, off, src);
+                if (lane < nj) {
+                    if (p.store_mode) p.val[rsj + lane] = st[oj + lane];
+                    else p.val[rsj + lane] += st[oj + lane];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same row-gather scheme for general (non-affine) elements: phase 1 computes the symmetric local matrix with the
+// sum-factorised q1_K_fast (isl_patch.cuh) and keeps it in shared memory, 44 doubles per element instance
+// (sK[44][inst_cap]); phase 2 only adds.  Shared memory: sK | (sX aliased after phase 1 by the staging buffer).
+template <int A>
+__device__ __forceinline__ void rg_gather_slot_general(const RowMeta& m, const double* sK, int cap, double (&acc)[27], double& body) {
+    const int s = m.slot[A];
+    if (s != 0xffff) rg_add_slot_general<A>([&](int i) { return sK[i * cap + s]; }, acc, body);
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParams p) {
+    extern __shared__ double smem[];
+    double* sK = smem;
+    double* sX = sK + (size_t)44 * p.inst_cap;
+    double* stage = sX;
+    const int tid = threadIdx.x;
+    const int pid = blockIdx.x;
+    const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
+    const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
+    const int e0 = p.p_inst_off[pid], ninst = p.p_inst_off[pid + 1] - e0;
+    {
+        const char* b1 = reinterpret_cast<const char*>(p.i_lnode + (size_t)e0 * 8);
+        for (size_t o = (size_t)tid * 128; o < (size_t)ninst * 16; o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
+        const char* b2 = reinterpret_cast<const char*>(p.meta + r0);
+        for (size_t o = (size_t)tid * 128; o < (size_t)nrows * sizeof(RowMeta); o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
+    }
+    for (int n = tid; n < nnodes; n += NT) {
+        const double* c = p.coords + (size_t)__ldg(p.nodes + n0 + n) * 3;
+        sX[n * 3] = __ldg(c); sX[n * 3 + 1] = __ldg(c + 1); sX[n * 3 + 2] = __ldg(c + 2);
+    }
+    __syncthreads();
+    // phase 1: local matrices of the element instances
+    for (int i = tid; i < ninst; i += NT) {
+        const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8));
+        const int ln[8] = {l4.x & 0xffff, (int)((unsigned)l4.x >> 16), l4.y & 0xffff, (int)((unsigned)l4.y >> 16),
+                           l4.z & 0xffff, (int)((unsigned)l4.z >> 16), l4.w & 0xffff, (int)((unsigned)l4.w >> 16)};
+        double X[8][3];
+#pragma unroll
+        for (int a = 0; a < 8; a++) { X[a][0] = sX[ln[a] * 3]; X[a][1] = sX[ln[a] * 3 + 1]; X[a][2] = sX[ln[a] * 3 + 2]; }
+        double K[36], detw[8], bf[8];
+        q1_K_fast(X, p.factor, K, detw, bf, true);
+#pragma unroll
+        for (int k = 0; k < 36; k++) sK[k * p.inst_cap + i] = K[k];
+#pragma unroll
+        for (int a = 0; a < 8; a++) sK[(36 + a) * p.inst_cap + i] = bf[a];
+    }
+    __syncthreads();  // sK complete; sX is dead from here on (stage aliases it)
+    // phase 2: owned rows (identical to k_q1hex_rows_affine apart from the slot routine)
+    const int lane = tid & 31, warp = tid >> 5;
+    double* st = stage + (size_t)warp * (16 * 27);
+    for (int rb = 0; rb < nrows; rb += NT) {
+        const int r = rb + tid;
+        const bool act = r < nrows;
+        RowMeta m;
+        int64_t rs = 0;
+        double acc[27];
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] = 0.;
+        int myn = 0;
+        if (act) {
+            const int4* mp = reinterpret_cast<const int4*>(p.meta + r0 + r);
+            int4* md = reinterpret_cast<int4*>(&m);
+            md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2);
+            rs = __ldg(p.rowstart + r0 + r);
+            myn = m.nnz;
+            double body = 0.;
+            rg_gather_slot_general<0>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<1>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<2>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<3>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<4>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<5>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<6>(m, sK, p.inst_cap, acc, body);
+            rg_gather_slot_general<7>(m, sK, p.inst_cap, acc, body);
+            double lift = 0.;
+            if (m.lift >= 0) {
+                const int32_t* ln = p.lift_nodes + (size_t)m.lift * 27;
+#pragma unroll
+                for (int k = 0; k < 27; k++) {
+                    const int32_t nd = __ldg(ln + k);
+                    if (nd >= 0 && m.pos[k] == 0xff && p.status[nd] == ISL_CONSTRAINED) {
+                        const double gv = p.incremental ? p.presc[nd] - p.values[nd] : p.presc[nd];
+                        lift = fma(gv, acc[k], lift);
+                    }
+                }
+            }
+            const double v = (p.body ? p.f0 * body : 0.) - lift;
+            if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
+        }
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const bool mine = (lane >> 4) == h;

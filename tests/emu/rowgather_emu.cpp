@@ -22,6 +22,34 @@ constexpr int sym_idx(int a, int b) {
 #include "../../insilico_b200/csrc/isl_rowgather.cuh"
 
 double g_w0 = 0.;
+double g_dN[8 * 8 * 3], g_Nq[64], g_w[8];
+// local matrix and body-force integrals of a general trilinear element in plain quadrature order (stands in for the
+// device's q1_K_fast, which the gpu tests cover): K_ab = sum_q factor w_q det J_q grad N_a . grad N_b
+void host_K(const double (&X)[8][3], double factor, double (&K)[36], double (&bf)[8]) {
+    for (int k = 0; k < 36; k++) K[k] = 0.;
+    for (int a = 0; a < 8; a++) bf[a] = 0.;
+    for (int q = 0; q < 8; q++) {
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int a = 0; a < 8; a++)
+            for (int d = 0; d < 3; d++)
+                for (int e = 0; e < 3; e++) J[d][e] += X[a][d] * g_dN[q * 24 + a * 3 + e];
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        double inv[3][3];
+        inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det;
+        inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det; inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det;
+        inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det;
+        inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        double G[8][3];
+        for (int a = 0; a < 8; a++)
+            for (int d = 0; d < 3; d++) { G[a][d] = 0.; for (int e = 0; e < 3; e++) G[a][d] += inv[e][d] * g_dN[q * 24 + a * 3 + e]; }
+        for (int a = 0; a < 8; a++) {
+            for (int b = a; b < 8; b++) K[sym_idx(a, b)] += factor * g_w[q] * det * (G[a][0] * G[b][0] + G[a][1] * G[b][1] + G[a][2] * G[b][2]);
+            bf[a] += g_Nq[q * 8 + a] * g_w[q] * det;
+        }
+    }
+}
 void fill_tables() {
     // same construction as load_q1_tables (isl_engine.cu): C_c[a][b] and sum_q N_a(q) on the 8-point rule
     const isl::Rule R = isl::make_rule(ISL_HEX, 3);
@@ -41,6 +69,15 @@ void fill_tables() {
             }
     for (int a = 0; a < 8; a++) { rg_host_nsum[a] = 0.; for (int q = 0; q < 8; q++) rg_host_nsum[a] += Nq[q * 8 + a]; }
     g_w0 = R.w[0];
+    for (int k = 0; k < 192; k++) g_dN[k] = dN[k];
+    for (int k = 0; k < 64; k++) g_Nq[k] = Nq[k];
+    for (int q = 0; q < 8; q++) g_w[q] = R.w[q];
+}
+
+template <int A>
+void gather_slot_general(const RowMeta& m, const double* sK, int cap, double (&acc)[27], double& body) {
+    const int s = m.slot[A];
+    if (s != 0xffff) rg_add_slot_general<A>([&](int i) { return sK[i * cap + s]; }, acc, body);
 }
 
 template <int A>
@@ -57,7 +94,7 @@ void gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27],
 extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coords, const int32_t* conn,
                              const int32_t* node_eqn, const uint8_t* status, const double* presc, const double* values,
                              int64_t n_eqn, const int64_t* rowptr, const int32_t* col, double factor, double f0, int body,
-                             int incremental, int store_mode, int rows_per_patch, int NT, double* val, double* rhs,
+                             int incremental, int store_mode, int rows_per_patch, int NT, int general, double* val, double* rhs,
                              int64_t* stats /* [patches, instances, flagged rows] */) {
     fill_tables();
     std::vector<int32_t> heqn((size_t)n_elems * 8), hconn(conn, conn + (size_t)n_elems * 8);
@@ -100,7 +137,7 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
     }
     stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter;
     const int inst_cap = (P.max_inst + 1) & ~1;
-    std::vector<double> sD((size_t)7 * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
+    std::vector<double> sD((size_t)(general ? 44 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
     for (int pid = 0; pid < n_patches; pid++) {
         const int r0 = P.row_off[pid], nrows = P.row_off[pid + 1] - r0;
         const int n0 = P.node_off[pid], nnodes = P.node_off[pid + 1] - n0;
@@ -109,6 +146,14 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
         // phase 1
         for (int i = 0; i < ninst; i++) {
             const uint16_t* ln = P.lnode.data() + (size_t)(e0 + i) * 8;
+            if (general) {  // k_q1hex_rows_general
+                double X[8][3], K[36], bf[8];
+                for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) X[a][d] = sX[ln[a] * 3 + d];
+                host_K(X, factor, K, bf);
+                for (int k = 0; k < 36; k++) sD[k * inst_cap + i] = K[k];
+                for (int a = 0; a < 8; a++) sD[(36 + a) * inst_cap + i] = bf[a];
+                continue;
+            }
             double D[6], dw;
             rg_instance(&sX[ln[0] * 3], &sX[ln[1] * 3], &sX[ln[3] * 3], &sX[ln[4] * 3], factor, g_w0, D, dw);
             for (int c = 0; c < 6; c++) sD[c * inst_cap + i] = D[c];
@@ -126,10 +171,17 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                     if (!act[lane]) continue;
                     m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz;
                     double bsum = 0.;
+                    if (general) {
+                        gather_slot_general<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_general<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_general<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_general<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    } else {
                     gather_slot<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                     gather_slot<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                     gather_slot<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                     gather_slot<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    }
                     double lift = 0.;
                     if (m[lane].lift >= 0) {
                         const int32_t* ln = lift_nodes.data() + (size_t)m[lane].lift * 27;

@@ -282,8 +282,9 @@ def test_rowgather_kernel_equals_oracle(monkeypatch, threads):
     monkeypatch.setenv("ISL_PATCH_ROWS", "100")
     e = E.Engine(0)
     try:
-        for name, n, permute in [("laplace_q1_hex", 13, False), ("laplace_q1_hex_values", 9, True)]:
-            c = flows.build_case(name, n, False, permute)
+        for name, n, perturb, permute in [("laplace_q1_hex", 13, False, False), ("laplace_q1_hex_values", 9, False, True),
+                                          ("laplace_q1_hex", 11, True, True)]:   # perturbed: k_q1hex_rows_general
+            c = flows.build_case(name, n, perturb, permute)
             ref = c.run_oracle()
             r = flows.compare(ref, c.run_engine(eng=e))
             assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r

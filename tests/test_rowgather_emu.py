@@ -34,7 +34,7 @@ def emu():
     return lib
 
 
-def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, nt, ref):
+def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, nt, ref, general=0):
     f = c.fields[0]
     rp, col = ref[0].astype(np.int64), ref[1].astype(np.int32)
     val = np.zeros(len(col)) if store_mode else np.full(len(col), 0.5)
@@ -51,7 +51,8 @@ def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, n
     rc = lib.emu_rowgather(ctypes.c_int64(len(coords)), ctypes.c_int64(len(conn)), arr(coords), arr(conn), arr(eqn),
                            arr(status), arr(presc), arr(values), ctypes.c_int64(c.n_eqn), arr(rp), arr(col),
                            ctypes.c_double(factor), ctypes.c_double(f0), ctypes.c_int(body), ctypes.c_int(incremental),
-                           ctypes.c_int(store_mode), ctypes.c_int(rows_per_patch), ctypes.c_int(nt), arr(val), arr(rhs),
+                           ctypes.c_int(store_mode), ctypes.c_int(rows_per_patch), ctypes.c_int(nt), ctypes.c_int(general), arr(val),
+                           arr(rhs),
                            arr(stats))
     return rc, val, rhs, stats
 
@@ -92,6 +93,17 @@ def test_rowgather_sheared_mesh_lift_and_accumulate(emu, incremental):
     # accumulate into a non-empty matrix (second assembly into the same solver)
     rc, val2, rhs2, _ = run_emu(emu, c, 2.5, 0.0, 0, int(incremental), 0, 48, 64, ref)
     assert rc == 0 and H.csr_rel_diff(ref[0], ref[2] + 0.5, val2) <= 1e-12
+
+
+@pytest.mark.parametrize("n,permute,rows_per_patch", [(6, False, 400), (9, True, 50)])
+def test_rowgather_general_elements_equal_oracle(emu, n, permute, rows_per_patch):
+    """perturbed mesh (no element affine): phase 1 keeps the full symmetric local matrix per element instance, phase 2
+    gathers it (k_q1hex_rows_general)."""
+    c = flows.build_case("laplace_q1_hex", n, True, permute)
+    ref = c.run_oracle()
+    rc, val, rhs, _ = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, rows_per_patch, 64, ref, general=1)
+    assert rc == 0 and not np.isnan(val).any()
+    assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
 
 
 def test_rowgather_rejects_non_lattice_connectivity(emu):
