@@ -23,7 +23,8 @@
 //
 // Eligibility (checked per row when the tables are built, otherwise the patch kernels are used): lattice property,
 // the same neighbour reached through different elements gets the same offset, every CSR entry of the row is a
-// stencil neighbour (so a complete row is written and the lazily-zeroed matrix needs no memset).
+// stencil neighbour or the row is marked partial and zero-filled first (so a complete row is written and the
+// lazily-zeroed matrix needs no memset).
 // =============================================================================
 #pragma once
 
@@ -46,7 +47,7 @@ RG_HD constexpr int rg_kidx(int a, int b) {
 struct alignas(16) RowMeta {
     uint16_t slot[8];  // patch-local element instance that has this row as local node a (0xffff: none)
     uint8_t pos[27];   // position of stencil neighbour k inside the CSR row (0xff: no entry)
-    uint8_t nnz;       // entries of the row
+    uint8_t nnz;       // entries of the row (bits 0-6); bit 7: partial row, has entries that are no stencil neighbours
     int32_t lift;      // row next to CONSTRAINED nodes: index into the table of neighbour node ids, else -1
 };
 static_assert(sizeof(RowMeta) == 48, "RowMeta is read as three 16-byte words");
@@ -153,8 +154,12 @@ RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_el
             cnt++;
         } else if (status[nbn[k]] == ISL_CONSTRAINED) constrained_nb = true;
     }
-    if ((int64_t)cnt != rowptr[g + 1] - rowptr[g] || cnt > 27) return false;  // the row has entries outside the stencil
-    m.nnz = (uint8_t)cnt;
+    // A row may have MORE entries than stencil neighbours found through the owned elements (columns that only the
+    // pattern-only halo elements of another partition contribute, isl_mesh_set_owned): such a row is "partial", the
+    // kernel zero-fills it before it scatters.  More than 27 entries do not fit the staging buffer.
+    const int64_t rn = rowptr[g + 1] - rowptr[g];
+    if ((int64_t)cnt > rn || rn > 27) return false;
+    m.nnz = (uint8_t)(rn | (cnt < rn ? 0x80 : 0));
     m.lift = -1;
     return true;
 }
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             int4* md = reinterpret_cast<int4*>(&m);
             md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2);
             rs = __ldg(p.rowstart + r0 + r);
-            myn = m.nnz;
+            myn = m.nnz & 0x7f;
             double body = 0.;
             rg_gather_slot<0>(m, sD, p.inst_cap, acc, body);
             rg_gather_slot<1>(m, sD, p.inst_cap, acc, body);
@@ -326,6 +331,11 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             }
             const int off = incl - (mine ? myn : 0);
             if (mine && act) {
+                if (m.nnz & 0x80) {
+#pragma unroll
+                    for (int k = 0; k < 27; k++)
+                        if (k < myn) st[off + k] = 0.;
+                }
 #pragma unroll
                 for (int k = 0; k < 27; k++)
                     if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
             int4* md = reinterpret_cast<int4*>(&m);
             md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2);
             rs = __ldg(p.rowstart + r0 + r);
-            myn = m.nnz;
+            myn = m.nnz & 0x7f;
             double body = 0.;
             rg_gather_slot_general<0>(m, sK, p.inst_cap, acc, body);
             rg_gather_slot_general<1>(m, sK, p.inst_cap, acc, body);
@@ -448,6 +458,11 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
             }
             const int off = incl - (mine ? myn : 0);
             if (mine && act) {
+                if (m.nnz & 0x80) {
+#pragma unroll
+                    for (int k = 0; k < 27; k++)
+                        if (k < myn) st[off + k] = 0.;
+                }
 #pragma unroll
                 for (int k = 0; k < 27; k++)
                     if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];

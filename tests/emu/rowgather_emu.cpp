@@ -91,6 +91,7 @@ void gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27],
 }
 }  // namespace
 
+// conn lists the OWNED elements only; the pattern (rowptr, col) may contain more columns (pattern-only halo elements)
 extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coords, const int32_t* conn,
                              const int32_t* node_eqn, const uint8_t* status, const double* presc, const double* values,
                              int64_t n_eqn, const int64_t* rowptr, const int32_t* col, double factor, double f0, int body,
@@ -169,7 +170,7 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                     act[lane] = r < nrows; rs[lane] = 0; myn[lane] = 0;
                     for (int k = 0; k < 27; k++) acc[lane][k] = 0.;
                     if (!act[lane]) continue;
-                    m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz;
+                    m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz & 0x7f;
                     double bsum = 0.;
                     if (general) {
                         gather_slot_general<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
@@ -206,8 +207,10 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                     }
                     for (int lane = 0; lane < 32; lane++) off[lane] = incl[lane] - (((lane >> 4) == h) ? myn[lane] : 0);
                     for (int lane = 0; lane < 32; lane++)
-                        if ((lane >> 4) == h && act[lane])
+                        if ((lane >> 4) == h && act[lane]) {
+                            if (m[lane].nnz & 0x80) for (int k = 0; k < 27; k++) if (k < myn[lane]) st[off[lane] + k] = 0.;
                             for (int k = 0; k < 27; k++) if (m[lane].pos[k] != 0xff) st[off[lane] + m[lane].pos[k]] = acc[lane][k];
+                        }
                     for (int j = 0; j < 16; j++) {
                         const int src = h * 16 + j;
                         for (int lane = 0; lane < 32; lane++)

@@ -34,17 +34,21 @@ def emu():
     return lib
 
 
-def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, nt, ref, general=0):
+def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, nt, ref, general=0, elems=None,
+            val=None, rhs=None):
     f = c.fields[0]
     rp, col = ref[0].astype(np.int64), ref[1].astype(np.int32)
-    val = np.zeros(len(col)) if store_mode else np.full(len(col), 0.5)
-    if store_mode:
-        val[:] = np.nan  # lazily-zeroed matrix: every entry must be WRITTEN
-    rhs = np.zeros(c.n_eqn)
+    if val is None:
+        val = np.zeros(len(col)) if store_mode else np.full(len(col), 0.5)
+        if store_mode:
+            val[:] = np.nan  # lazily-zeroed matrix: every entry must be WRITTEN
+    if rhs is None:
+        rhs = np.zeros(c.n_eqn)
     stats = np.zeros(3, dtype=np.int64)
     P = ctypes.c_void_p
     arr = lambda a: a.ctypes.data_as(P)
-    coords = np.ascontiguousarray(c.coords); conn = np.ascontiguousarray(c.conn, dtype=np.int32)
+    coords = np.ascontiguousarray(c.coords)
+    conn = np.ascontiguousarray(c.conn if elems is None else c.conn[elems], dtype=np.int32)
     eqn = np.ascontiguousarray(f["eqn"].reshape(-1), dtype=np.int32)
     status = np.ascontiguousarray(f["status"].reshape(-1), dtype=np.uint8)
     presc = np.ascontiguousarray(f["presc"].reshape(-1)); values = np.ascontiguousarray(f["values"].reshape(-1))
@@ -103,6 +107,24 @@ def test_rowgather_general_elements_equal_oracle(emu, n, permute, rows_per_patch
     ref = c.run_oracle()
     rc, val, rhs, _ = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, rows_per_patch, 64, ref, general=1)
     assert rc == 0 and not np.isnan(val).any()
+    assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
+
+
+@pytest.mark.parametrize("general", [0, 1])
+def test_rowgather_partial_rows_of_a_partition(emu, general):
+    """multi-GPU layout: the pattern holds the columns of the neighbour's (pattern-only) elements as well.  Assembling
+    the first part of the elements in store mode into a NaN-filled matrix and the rest in accumulate mode must give the
+    oracle's full system: rows at the cut are partial (zero-filled before the scatter), rows without any owned element
+    are written as zeros."""
+    c = flows.build_case("laplace_q1_hex", 8, bool(general), False)
+    ref = c.run_oracle()
+    ne = len(c.conn)
+    first, second = np.arange(0, (3 * ne) // 8), np.arange((3 * ne) // 8, ne)
+    rc, val, rhs, _ = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, 60, 64, ref, general=general, elems=first)
+    assert rc == 0 and not np.isnan(val).any()
+    assert (val == 0.0).sum() > 0
+    rc, val, rhs, _ = run_emu(emu, c, 1.0, 1.0, 1, 1, 0, 60, 64, ref, general=general, elems=second, val=val, rhs=rhs)
+    assert rc == 0
     assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
 
 
