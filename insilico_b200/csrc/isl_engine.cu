@@ -699,6 +699,7 @@ struct isl_engine {
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
     int q1_rows = 0;            // ISL_Q1_ROWS=1: row-gather kernel on all-affine meshes (isl_rowgather.cuh; not yet default)
     int rows_threads = 256;     // its CTA size (ISL_ROWS_THREADS)
+    int rows_ss = 0;            // ISL_ROWS_SS=1: signed-sum form of the entries (15 numbers per element, no constant tables)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1147,18 +1148,26 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
             q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
             q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 1) & ~1;
             const int nt = h->rows_threads;
-            const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
-#define ISL_ROWS_LAUNCH(NT, MINB)                                                                                       \
+            const size_t smem_r = (size_t)(h->rows_ss ? 16 : 7) * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
+#define ISL_ROWS_LAUNCH(NT, MINB, SS)                                                                                   \
     do {                                                                                                               \
-        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
-        ISL_LAUNCH(h, (k_q1hex_rows_affine<NT, MINB>), ps->n_patches, NT, smem_r, q);                                 \
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<NT, MINB, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
+        ISL_LAUNCH(h, (k_q1hex_rows_affine<NT, MINB, SS>), ps->n_patches, NT, smem_r, q);                             \
     } while (0)
-            if (nt == 128) ISL_ROWS_LAUNCH(128, 4);
-            else if (nt == 192) ISL_ROWS_LAUNCH(192, 2);
-            else if (nt == 320) ISL_ROWS_LAUNCH(320, 2);
-            else if (nt == 384) ISL_ROWS_LAUNCH(384, 1);
-            else if (nt == 512) ISL_ROWS_LAUNCH(512, 1);
-            else ISL_ROWS_LAUNCH(256, 2);
+            if (h->rows_ss) {
+                if (nt == 128) ISL_ROWS_LAUNCH(128, 4, true);
+                else if (nt == 192) ISL_ROWS_LAUNCH(192, 2, true);
+                else if (nt == 320) ISL_ROWS_LAUNCH(320, 2, true);
+                else if (nt == 384) ISL_ROWS_LAUNCH(384, 1, true);
+                else ISL_ROWS_LAUNCH(256, 2, true);
+            } else {
+                if (nt == 128) ISL_ROWS_LAUNCH(128, 4, false);
+                else if (nt == 192) ISL_ROWS_LAUNCH(192, 2, false);
+                else if (nt == 320) ISL_ROWS_LAUNCH(320, 2, false);
+                else if (nt == 384) ISL_ROWS_LAUNCH(384, 1, false);
+                else if (nt == 512) ISL_ROWS_LAUNCH(512, 1, false);
+                else ISL_ROWS_LAUNCH(256, 2, false);
+            }
 #undef ISL_ROWS_LAUNCH
             return;
         }
@@ -1308,6 +1317,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_Q1_ROWS")) { h->q1_rows = atoi(m) ? 1 : 0; if (h->q1_rows) h->patch_rows = 256; }
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
+        if (const char* m = getenv("ISL_ROWS_SS")) h->rows_ss = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
         if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(4, atoi(m)));

@@ -106,6 +106,66 @@ RG_HD void rg_add_slot(const double (&D)[6], double dw, double (&acc)[27], doubl
     body = fma(dw, RG_NSUM(A), body);
 }
 
+// Signed-sum form of the same entries (SS variant).  On the reference cube the trilinear integrals are exact rationals:
+//   int d_x N_a d_x N_b = s_x(a) s_x(b) m_y m_z,  m = 1/3 (a, b on the same side of that axis) or 1/6,  s = -1 / +1,
+//   int (d_x N_a d_y N_b + d_y N_a d_x N_b) = +- (1/2) m_z s_x(a) s_y(a)  when a, b agree on both or differ on both
+//                                              of x, y (+ / -), else 0
+// (the 2x2x2 Gauss rule integrates them exactly, so this equals the quadrature of the reference up to rounding).
+// Phase 1 stores, per element, E_c {1/9, 1/18, 1/36} (c = xx, yy, zz) and E_c {1/6, 1/12} (c = xy, xz, yz) with
+// E_c = (kappa / det J) (cof^T cof)_c: 15 numbers; every matrix entry is then a signed sum of 3 to 6 of them with
+// compile-time signs and selections: 288 additions per row instead of 384 fused multiply-adds + 64 additions, and no
+// constant-table loads.
+RG_HD void rg_instance_ss(const double* x0, const double* x1, const double* x3, const double* x4, double factor, double w,
+                          double (&T)[15], double& dw) {
+    double D[6];
+    rg_instance(x0, x1, x3, x4, factor, w, D, dw);   // D_c = (factor w / det) (cof^T cof)_c with w = 1/8
+    const double inv_w = 1.0 / w;
+    for (int c = 0; c < 3; c++) {
+        const double e = D[c] * inv_w;
+        T[c * 3] = e * (1.0 / 9.0); T[c * 3 + 1] = e * (1.0 / 18.0); T[c * 3 + 2] = e * (1.0 / 36.0);
+    }
+    for (int c = 3; c < 6; c++) {
+        const double e = D[c] * inv_w;
+        T[9 + (c - 3) * 2] = e * (1.0 / 6.0); T[9 + (c - 3) * 2 + 1] = e * (1.0 / 12.0);
+    }
+}
+RG_HD constexpr int rg_bit(int axis, int a) { return axis == 0 ? rg_bx(a) : axis == 1 ? rg_by(a) : rg_bz(a); }
+RG_HD constexpr bool rg_same(int axis, int a, int b) { return rg_bit(axis, a) == rg_bit(axis, b); }
+RG_HD constexpr int rg_sgn(int axis, int a) { return rg_bit(axis, a) ? 1 : -1; }
+template <int A>
+RG_HD void rg_add_slot_ss(const double (&T)[15], double dw, double (&acc)[27], double& body) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int b = 0; b < 8; b++) {
+        double v = acc[rg_kidx(A, b)];
+        // diagonal terms c = 0 (xx), 1 (yy), 2 (zz): sign s_c(a) s_c(b), magnitude by the two other axes
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int c = 0; c < 3; c++) {
+            const int o1 = (c + 1) % 3, o2 = (c + 2) % 3;
+            const int mi = (rg_same(o1, A, b) ? 0 : 1) + (rg_same(o2, A, b) ? 0 : 1);
+            const double t = T[c * 3 + mi];
+            v = (rg_sgn(c, A) * rg_sgn(c, b) > 0) ? v + t : v - t;
+        }
+        // cross terms c = 3 (xy), 4 (xz), 5 (yz)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int c = 3; c < 6; c++) {
+            const int p = (c == 5) ? 1 : 0, q = (c == 3) ? 1 : 2, r = 3 - p - q;
+            const bool ep = rg_same(p, A, b), eq = rg_same(q, A, b);
+            if (ep == eq) {
+                const double t = T[9 + (c - 3) * 2 + (rg_same(r, A, b) ? 0 : 1)];
+                v = ((rg_sgn(p, A) * rg_sgn(q, A) > 0) == ep) ? v + t : v - t;
+            }
+        }
+        acc[rg_kidx(A, b)] = v;
+    }
+    body = fma(dw, RG_NSUM(A), body);
+}
+
 // general (non-affine) elements: the element's symmetric local matrix (36 numbers) and its body-force integrals
 // sum_q N_a w det J (8 numbers) are taken from the patch's instance table instead of being formed from D
 template <int A, class LoadK>
@@ -224,12 +284,23 @@ __device__ __forceinline__ void rg_gather_slot(const RowMeta& m, const double* s
     }
 }
 
-// one CTA per patch.  Shared memory: sD[7][inst_cap] | (sX[node_cap][3]  aliased after phase 1 by  stage[NT/32][16*27])
-template <int NT, int MINB>
+template <int A>
+__device__ __forceinline__ void rg_gather_slot_ss(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
+    const int s = m.slot[A];
+    if (s != 0xffff) {
+        double T[15];
+#pragma unroll
+        for (int c = 0; c < 15; c++) T[c] = sD[c * cap + s];
+        rg_add_slot_ss<A>(T, sD[15 * cap + s], acc, body);
+    }
+}
+
+// one CTA per patch.  Shared memory: sD[7 (SS: 16)][inst_cap] | (sX[node_cap][3]  aliased after phase 1 by  stage[NT/32][16*27])
+template <int NT, int MINB, bool SS = false>
 __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams p) {
     extern __shared__ double smem[];
     double* sD = smem;
-    double* sX = sD + (size_t)7 * p.inst_cap;
+    double* sX = sD + (size_t)(SS ? 16 : 7) * p.inst_cap;
     double* stage = sX;
     const int tid = threadIdx.x;
     const int pid = blockIdx.x;
@@ -269,11 +340,19 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
     for (int i = tid; i < ninst; i += NT) {
         const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8));
         const int n0l = l4.x & 0xffff, n1l = (unsigned)l4.x >> 16, n3l = (unsigned)l4.y >> 16, n4l = l4.z & 0xffff;
-        double D[6], dw;
-        rg_instance(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, D, dw);
+        if (SS) {
+            double T[15], dw;
+            rg_instance_ss(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, T, dw);
 #pragma unroll
-        for (int c = 0; c < 6; c++) sD[c * p.inst_cap + i] = D[c];
-        sD[6 * p.inst_cap + i] = dw;
+            for (int c = 0; c < 15; c++) sD[c * p.inst_cap + i] = T[c];
+            sD[15 * p.inst_cap + i] = dw;
+        } else {
+            double D[6], dw;
+            rg_instance(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, D, dw);
+#pragma unroll
+            for (int c = 0; c < 6; c++) sD[c * p.inst_cap + i] = D[c];
+            sD[6 * p.inst_cap + i] = dw;
+        }
     }
     __syncthreads();  // sD complete; sX is dead from here on (stage aliases it)
     // phase 2: owned rows
@@ -295,14 +374,25 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             rs = __ldg(p.rowstart + r0 + r);
             myn = m.nnz & 0x7f;
             double body = 0.;
-            rg_gather_slot<0>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<1>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<2>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<3>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<4>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<5>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<6>(m, sD, p.inst_cap, acc, body);
-            rg_gather_slot<7>(m, sD, p.inst_cap, acc, body);
+            if (SS) {
+                rg_gather_slot_ss<0>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<1>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<2>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<3>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<4>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<5>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<6>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot_ss<7>(m, sD, p.inst_cap, acc, body);
+            } else {
+                rg_gather_slot<0>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<1>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<2>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<3>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<4>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<5>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<6>(m, sD, p.inst_cap, acc, body);
+                rg_gather_slot<7>(m, sD, p.inst_cap, acc, body);
+            }
             // right-hand side: Dirichlet lift of CONSTRAINED stencil neighbours (assembleMatrix.hpp:56-130), body force
             double lift = 0.;
             if (m.lift >= 0) {

@@ -75,6 +75,16 @@ void fill_tables() {
 }
 
 template <int A>
+void gather_slot_ss(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
+    const int s = m.slot[A];
+    if (s != 0xffff) {
+        double T[15];
+        for (int c = 0; c < 15; c++) T[c] = sD[c * cap + s];
+        rg_add_slot_ss<A>(T, sD[15 * cap + s], acc, body);
+    }
+}
+
+template <int A>
 void gather_slot_general(const RowMeta& m, const double* sK, int cap, double (&acc)[27], double& body) {
     const int s = m.slot[A];
     if (s != 0xffff) rg_add_slot_general<A>([&](int i) { return sK[i * cap + s]; }, acc, body);
@@ -138,7 +148,7 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
     }
     stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter;
     const int inst_cap = (P.max_inst + 1) & ~1;
-    std::vector<double> sD((size_t)(general ? 44 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
+    std::vector<double> sD((size_t)(general == 1 ? 44 : general == 2 ? 16 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
     for (int pid = 0; pid < n_patches; pid++) {
         const int r0 = P.row_off[pid], nrows = P.row_off[pid + 1] - r0;
         const int n0 = P.node_off[pid], nnodes = P.node_off[pid + 1] - n0;
@@ -147,7 +157,14 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
         // phase 1
         for (int i = 0; i < ninst; i++) {
             const uint16_t* ln = P.lnode.data() + (size_t)(e0 + i) * 8;
-            if (general) {  // k_q1hex_rows_general
+            if (general == 2) {  // k_q1hex_rows_affine<.., SS = true>
+                double T[15], dw;
+                rg_instance_ss(&sX[ln[0] * 3], &sX[ln[1] * 3], &sX[ln[3] * 3], &sX[ln[4] * 3], factor, g_w0, T, dw);
+                for (int c = 0; c < 15; c++) sD[c * inst_cap + i] = T[c];
+                sD[15 * inst_cap + i] = dw;
+                continue;
+            }
+            if (general == 1) {  // k_q1hex_rows_general
                 double X[8][3], K[36], bf[8];
                 for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) X[a][d] = sX[ln[a] * 3 + d];
                 host_K(X, factor, K, bf);
@@ -172,7 +189,12 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                     if (!act[lane]) continue;
                     m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz & 0x7f;
                     double bsum = 0.;
-                    if (general) {
+                    if (general == 2) {
+                        gather_slot_ss<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_ss<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_ss<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        gather_slot_ss<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                    } else if (general == 1) {
                         gather_slot_general<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                         gather_slot_general<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                         gather_slot_general<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);

@@ -274,10 +274,11 @@ def test_affine_kernel_multi_patch_equals_general_kernel(monkeypatch):
 
 @pytest.mark.skipif(not __import__("os").environ.get("ISL_TEST_EXPERIMENTAL"),
                     reason="row-gather kernel (ISL_Q1_ROWS=1) is not the default yet: set ISL_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("threads", ["256", "320", "128"])
-def test_rowgather_kernel_equals_oracle(monkeypatch, threads):
+@pytest.mark.parametrize("threads,ss", [("256", "0"), ("320", "0"), ("128", "0"), ("256", "1"), ("320", "1")])
+def test_rowgather_kernel_equals_oracle(monkeypatch, threads, ss):
     """isl_rowgather.cuh on the device (the same routines pass tests/test_rowgather_emu.py on the host)."""
     monkeypatch.setenv("ISL_Q1_ROWS", "1")
+    monkeypatch.setenv("ISL_ROWS_SS", ss)
     monkeypatch.setenv("ISL_ROWS_THREADS", threads)
     monkeypatch.setenv("ISL_PATCH_ROWS", "100")
     e = E.Engine(0)

@@ -79,23 +79,25 @@ def sheared(n, permute):
 def test_rowgather_equals_oracle(emu, n, permute, rows_per_patch, nt):
     c = flows.build_case("laplace_q1_hex", n, False, permute)   # stiffness (incremental) + body force f = 1
     ref = c.run_oracle()
-    rc, val, rhs, stats = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, rows_per_patch, nt, ref)
-    assert rc == 0
-    assert not np.isnan(val).any()
-    assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
+    for variant in (0, 2):
+        rc, val, rhs, stats = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, rows_per_patch, nt, ref, general=variant)
+        assert rc == 0
+        assert not np.isnan(val).any()
+        assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
     assert stats[0] >= (n - 1) ** 3 // rows_per_patch and stats[2] > 0
 
 
+@pytest.mark.parametrize("variant", [0, 2])   # 0: constant tables, 2: signed sums of 15 numbers per element (SS)
 @pytest.mark.parametrize("incremental", [True, False])
-def test_rowgather_sheared_mesh_lift_and_accumulate(emu, incremental):
+def test_rowgather_sheared_mesh_lift_and_accumulate(emu, incremental, variant):
     c = sheared(6, True)
     c.ops = [("matrix", E.K_LAPLACE, [2.5], 3, 0, 0, incremental)]
     ref = c.run_oracle()
-    rc, val, rhs, _ = run_emu(emu, c, 2.5, 0.0, 0, int(incremental), 1, 48, 64, ref)
+    rc, val, rhs, _ = run_emu(emu, c, 2.5, 0.0, 0, int(incremental), 1, 48, 64, ref, general=variant)
     assert rc == 0
     assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
     # accumulate into a non-empty matrix (second assembly into the same solver)
-    rc, val2, rhs2, _ = run_emu(emu, c, 2.5, 0.0, 0, int(incremental), 0, 48, 64, ref)
+    rc, val2, rhs2, _ = run_emu(emu, c, 2.5, 0.0, 0, int(incremental), 0, 48, 64, ref, general=variant)
     assert rc == 0 and H.csr_rel_diff(ref[0], ref[2] + 0.5, val2) <= 1e-12
 
 
