@@ -695,6 +695,7 @@ struct isl_engine {
     struct PendingQ1 { bool active = false; int field = 0; double factor = 1.; int incremental = 1; } pending_q1;
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
     int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
+    double patch_stretch = 1.0;  // ISL_PATCH_STRETCH: boxes this many times longer along the axis of consecutive equation numbers
     int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
     int q1_rows = 0;            // ISL_Q1_ROWS=1: row-gather kernel on all-affine meshes (isl_rowgather.cuh; not yet default)
@@ -1009,6 +1010,25 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         for (int d = 0; d < 3; d++) rowxyz[(size_t)r * 3 + d] = hcoords[(size_t)nd * 3 + d] / hmean[d];
         hperm.push_back(r);
     }
+    if (h->patch_stretch != 1.0 && nrow > 1) {
+        // longer runs of consecutive rows per box (longer contiguous pieces of the CSR arrays per patch): find the axis
+        // along which consecutive equation numbers advance and shrink it before the bisection
+        int64_t votes[3] = {0, 0, 0};
+        const int64_t stride = std::max<int64_t>(1, nrow / 100000);
+        for (int64_t r = 0; r + 1 < nrow; r += stride) {
+            int best = -1, nz = 0;
+            for (int d = 0; d < 3; d++) {
+                const double dd = std::fabs(rowxyz[(size_t)(r + 1) * 3 + d] - rowxyz[(size_t)r * 3 + d]);
+                if (dd > 0.25) { nz++; best = d; }
+            }
+            if (nz == 1) votes[best]++;
+        }
+        int ax = 0;
+        if (votes[1] > votes[ax]) ax = 1;
+        if (votes[2] > votes[ax]) ax = 2;
+        if (votes[ax] > 0)
+            for (int64_t r = 0; r < nrow; r++) rowxyz[(size_t)r * 3 + ax] /= h->patch_stretch;
+    }
     hcoords.clear(); hcoords.shrink_to_fit();
     // shared memory per CTA: accumulator (27 entries per row on a hex lattice) + coordinates of the patch's nodes
     // (owned + halo) + row metadata.  R is shrunk until the estimate fits the budget; if the real patches still
@@ -1319,6 +1339,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
         if (const char* m = getenv("ISL_ROWS_SS")) h->rows_ss = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
+        if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
         if (const char* m = getenv("ISL_PATCH_CTAS")) h->patch_ctas_per_sm = std::max(1, std::min(4, atoi(m)));
         *out = h.release();

@@ -273,6 +273,62 @@ __global__ void k_row_meta(int pass, const int32_t* p_row_off, const int32_t* p_
     }
 }
 
+
+// matrix write-out of a warp's 32 rows: sixteen rows at a time through the warp's staging buffer into CSR order, then
+// stores along the rows.  When the sixteen rows are consecutive in the CSR arrays (the usual case: consecutive
+// equation numbers) the staged block is one contiguous piece of the value array and is streamed with all 32 lanes.
+__device__ __forceinline__ void rg_write_rows(const RowsParams& p, const RowMeta& m, const double (&acc)[27], bool act, int myn,
+                                              int64_t rs, double* st, int lane) {
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const bool mine = (lane >> 4) == h;
+        int incl = mine ? myn : 0;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
+            if ((lane & 15) >= d) incl += v;
+        }
+        const int off = incl - (mine ? myn : 0);
+        if (mine && act) {
+            if (m.nnz & 0x80) {
+#pragma unroll
+                for (int k = 0; k < 27; k++)
+                    if (k < myn) st[off + k] = 0.;
+            }
+#pragma unroll
+            for (int k = 0; k < 27; k++)
+                if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
+        }
+        const int64_t rs_next = __shfl_down_sync(0xffffffffu, rs, 1);
+        const int n_next = __shfl_down_sync(0xffffffffu, myn, 1);
+        const bool ok = !mine || (lane & 15) == 15 || n_next == 0 || rs_next == rs + myn;
+        const bool contiguous = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        if (contiguous) {
+            const int total = __shfl_sync(0xffffffffu, incl, h * 16 + 15);
+            const int64_t rs0 = __shfl_sync(0xffffffffu, rs, h * 16);
+            if (p.store_mode) {
+                for (int q = lane; q < total; q += 32) p.val[rs0 + q] = st[q];
+            } else {
+                for (int q = lane; q < total; q += 32) p.val[rs0 + q] += st[q];
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < 16; j++) {
+                const int src = h * 16 + j;
+                const int64_t rsj = __shfl_sync(0xffffffffu, rs, src);
+                const int nj = __shfl_sync(0xffffffffu, myn, src);
+                const int oj = __shfl_sync(0xffffffffu, off, src);
+                if (lane < nj) {
+                    if (p.store_mode) p.val[rsj + lane] = st[oj + lane];
+                    else p.val[rsj + lane] += st[oj + lane];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int A>
 __device__ __forceinline__ void rg_gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
     const int s = m.slot[A];
@@ -410,40 +466,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
         }
         // matrix: sixteen rows at a time through the warp's staging buffer into CSR order, then row-contiguous stores
-#pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const bool mine = (lane >> 4) == h;
-            int incl = mine ? myn : 0;
-#pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
-                if ((lane & 15) >= d) incl += v;
-            }
-            const int off = incl - (mine ? myn : 0);
-            if (mine && act) {
-                if (m.nnz & 0x80) {
-#pragma unroll
-                    for (int k = 0; k < 27; k++)
-                        if (k < myn) st[off + k] = 0.;
-                }
-#pragma unroll
-                for (int k = 0; k < 27; k++)
-                    if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int j = 0; j < 16; j++) {
-                const int src = h * 16 + j;
-                const int64_t rsj = __shfl_sync(0xffffffffu, rs, src);
-                const int nj = __shfl_sync(0xffffffffu, myn, src);
-                const int oj = __shfl_sync(0xffffffffu, off, src);
-                if (lane < nj) {
-                    if (p.store_mode) p.val[rsj + lane] = st[oj + lane];
-                    else p.val[rsj + lane] += st[oj + lane];
-                }
-            }
-            __syncwarp();
-        }
+        rg_write_rows(p, m, acc, act, myn, rs, st, lane);
     }
 }
 
@@ -537,40 +560,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
             const double v = (p.body ? p.f0 * body : 0.) - lift;
             if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
         }
-#pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const bool mine = (lane >> 4) == h;
-            int incl = mine ? myn : 0;
-#pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
-                if ((lane & 15) >= d) incl += v;
-            }
-            const int off = incl - (mine ? myn : 0);
-            if (mine && act) {
-                if (m.nnz & 0x80) {
-#pragma unroll
-                    for (int k = 0; k < 27; k++)
-                        if (k < myn) st[off + k] = 0.;
-                }
-#pragma unroll
-                for (int k = 0; k < 27; k++)
-                    if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
-            }
-            __syncwarp();
-#pragma unroll 1
-            for (int j = 0; j < 16; j++) {
-                const int src = h * 16 + j;
-                const int64_t rsj = __shfl_sync(0xffffffffu, rs, src);
-                const int nj = __shfl_sync(0xffffffffu, myn, src);
-                const int oj = __shfl_sync(0xffffffffu, off, src);
-                if (lane < nj) {
-                    if (p.store_mode) p.val[rsj + lane] = st[oj + lane];
-                    else p.val[rsj + lane] += st[oj + lane];
-                }
-            }
-            __syncwarp();
-        }
+        rg_write_rows(p, m, acc, act, myn, rs, st, lane);
     }
 }
 #endif  // __CUDACC__

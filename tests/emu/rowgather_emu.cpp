@@ -106,7 +106,7 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                              const int32_t* node_eqn, const uint8_t* status, const double* presc, const double* values,
                              int64_t n_eqn, const int64_t* rowptr, const int32_t* col, double factor, double f0, int body,
                              int incremental, int store_mode, int rows_per_patch, int NT, int general, double* val, double* rhs,
-                             int64_t* stats /* [patches, instances, flagged rows] */) {
+                             int64_t* stats /* [patches, instances, flagged rows, contiguous blocks, row-by-row blocks] */) {
     fill_tables();
     std::vector<int32_t> heqn((size_t)n_elems * 8), hconn(conn, conn + (size_t)n_elems * 8);
     for (int64_t k = 0; k < n_elems * 8; k++) heqn[k] = node_eqn[conn[k]];
@@ -146,7 +146,7 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
             rowstart[r0 + r] = rowptr[g];
         }
     }
-    stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter;
+    stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter; stats[3] = stats[4] = 0;
     const int inst_cap = (P.max_inst + 1) & ~1;
     std::vector<double> sD((size_t)(general == 1 ? 44 : general == 2 ? 16 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
     for (int pid = 0; pid < n_patches; pid++) {
@@ -233,13 +233,33 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                             if (m[lane].nnz & 0x80) for (int k = 0; k < 27; k++) if (k < myn[lane]) st[off[lane] + k] = 0.;
                             for (int k = 0; k < 27; k++) if (m[lane].pos[k] != 0xff) st[off[lane] + m[lane].pos[k]] = acc[lane][k];
                         }
-                    for (int j = 0; j < 16; j++) {
-                        const int src = h * 16 + j;
+                    // rg_write_rows: contiguity vote (__shfl_down_sync by 1, __all_sync), then one streamed block or row by row
+                    bool contiguous = true;
+                    for (int lane = 0; lane < 32; lane++) {
+                        const bool mine = (lane >> 4) == h;
+                        const int64_t rs_next = lane < 31 ? rs[lane + 1] : rs[lane];
+                        const int n_next = lane < 31 ? myn[lane + 1] : myn[lane];
+                        const bool ok = !mine || (lane & 15) == 15 || n_next == 0 || rs_next == rs[lane] + myn[lane];
+                        contiguous = contiguous && ok;
+                    }
+                    if (contiguous) {
+                        const int total = incl[h * 16 + 15];
+                        const int64_t rs0 = rs[h * 16];
                         for (int lane = 0; lane < 32; lane++)
-                            if (lane < myn[src]) {
-                                if (store_mode) val[rs[src] + lane] = st[off[src] + lane];
-                                else val[rs[src] + lane] += st[off[src] + lane];
+                            for (int q = lane; q < total; q += 32) {
+                                if (store_mode) val[rs0 + q] = st[q]; else val[rs0 + q] += st[q];
                             }
+                        stats[3]++;
+                    } else {
+                        for (int j = 0; j < 16; j++) {
+                            const int src = h * 16 + j;
+                            for (int lane = 0; lane < 32; lane++)
+                                if (lane < myn[src]) {
+                                    if (store_mode) val[rs[src] + lane] = st[off[src] + lane];
+                                    else val[rs[src] + lane] += st[off[src] + lane];
+                                }
+                        }
+                        stats[4]++;
                     }
                 }
             }

@@ -44,7 +44,7 @@ def run_emu(lib, c, factor, f0, body, incremental, store_mode, rows_per_patch, n
             val[:] = np.nan  # lazily-zeroed matrix: every entry must be WRITTEN
     if rhs is None:
         rhs = np.zeros(c.n_eqn)
-    stats = np.zeros(3, dtype=np.int64)
+    stats = np.zeros(5, dtype=np.int64)
     P = ctypes.c_void_p
     arr = lambda a: a.ctypes.data_as(P)
     coords = np.ascontiguousarray(c.coords)
@@ -85,6 +85,8 @@ def test_rowgather_equals_oracle(emu, n, permute, rows_per_patch, nt):
         assert not np.isnan(val).any()
         assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
     assert stats[0] >= (n - 1) ** 3 // rows_per_patch and stats[2] > 0
+    # write-out paths: one patch holding all rows streams contiguous blocks, boxes of a larger mesh go row by row
+    assert stats[3] > 0 if rows_per_patch >= (n - 1) ** 3 else stats[4] > 0
 
 
 @pytest.mark.parametrize("variant", [0, 2])   # 0: constant tables, 2: signed sums of 15 numbers per element (SS)
