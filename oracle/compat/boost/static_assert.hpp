@@ -1,0 +1,6 @@
+// Test infrastructure — NOT product code, NOT the Boost library: a std-only stand-in for the few Boost 1.55 names the
+// reference headers use, so that the unmodified headers under /root/reference compile here (see oracle/compat/README.md).
+#ifndef BOOST_STATIC_ASSERT
+#define BOOST_STATIC_ASSERT(x) static_assert(x, #x)
+#define BOOST_STATIC_ASSERT_MSG(x, m) static_assert(x, m)
+#endif

@@ -1,0 +1,376 @@
+// Test infrastructure — NOT product code.
+//
+// Drives the UNMODIFIED inSilico headers under /root/reference (compiled against the std-only Boost/Eigen stand-ins
+// of oracle/compat) through the reference's own public API for the assembly hot path and dumps what the parity
+// tests compare: DoF numbering (element -> DoF ids, status, equation numbers) and the assembled system of
+// base::solver::Eigen3 (finishAssembly -> debugLHS / debugRHS, reference base/solver/Eigen3.hpp:140-153,307-322).
+// The call sequence per case is the reference applications':
+//   reference/04-heat/dirichlet.cpp:99-167, reference/06-elastic/compressible.cpp:163-288,
+//   reference/07-drivenCavity/drivenCavity.cpp:176-275.
+// Built only where /root/reference exists (oracle/Makefile target `ref`), output into oracle/_ref/.
+//
+// usage: ref_driver <job file>          (see tools/make_ref_goldens.py for the job format)
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include <base/shape.hpp>
+#include <base/Unstructured.hpp>
+#include <base/mesh/MeshBoundary.hpp>
+#include <base/Quadrature.hpp>
+#include <base/io/smf/Reader.hpp>
+#include <base/fe/Basis.hpp>
+#include <base/Field.hpp>
+#include <base/dof/numbering.hpp>
+#include <base/dof/generate.hpp>
+#include <base/dof/constrainBoundary.hpp>
+#include <base/asmb/FieldBinder.hpp>
+#include <base/asmb/StiffnessMatrix.hpp>
+#include <base/asmb/ForceIntegrator.hpp>
+#include <base/asmb/BodyForce.hpp>
+#include <base/solver/Eigen3.hpp>
+#include <heat/Laplace.hpp>
+#include <fluid/Stokes.hpp>
+#include <mat/Lame.hpp>
+#include <mat/hypel/StVenant.hpp>
+#include <mat/hypel/NeoHookeanCompressible.hpp>
+#include <solid/HyperElastic.hpp>
+
+namespace drv {
+
+struct Op {
+    std::string what, kernel;  // matrix | residual | body
+    int test = 0, trial = 0, incremental = 1;
+    std::vector<double> p;
+};
+struct FieldSpec {
+    std::string presc, values;  // raw f64 files [n_obj][ds] ("-" = none)
+    int boundary = 0;           // constrain the whole boundary through dof::constrainBoundary
+    long pin = -1;              // constrainValue(0, 0.) on this DoF object
+};
+struct Job {
+    std::string type, mesh, out;
+    int registerFields = 0, repeat = 1, dump = 1;
+    std::map<int, FieldSpec> fields;
+    std::vector<Op> ops;
+};
+
+static std::vector<double> readF64(const std::string& f) {
+    std::vector<double> v;
+    if (f == "-" || f.empty()) return v;
+    std::ifstream in(f.c_str(), std::ios::binary);
+    VERIFY_MSG(in.is_open(), "cannot open " + f);
+    in.seekg(0, std::ios::end);
+    const std::size_t n = static_cast<std::size_t>(in.tellg()) / sizeof(double);
+    in.seekg(0);
+    v.resize(n);
+    in.read(reinterpret_cast<char*>(v.data()), static_cast<std::streamsize>(n * sizeof(double)));
+    return v;
+}
+
+static Job readJob(const char* file) {
+    Job j;
+    std::ifstream in(file);
+    VERIFY_MSG(in.is_open(), "cannot open job file");
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream s(line);
+        std::string key;
+        if (!(s >> key) || key[0] == '#') continue;
+        if (key == "type") s >> j.type;
+        else if (key == "mesh") s >> j.mesh;
+        else if (key == "out") s >> j.out;
+        else if (key == "register") s >> j.registerFields;
+        else if (key == "repeat") s >> j.repeat;
+        else if (key == "dump") s >> j.dump;
+        else if (key == "field") {
+            int i;
+            FieldSpec f;
+            s >> i >> f.boundary >> f.pin >> f.presc >> f.values;
+            j.fields[i] = f;
+        } else if (key == "op") {
+            Op o;
+            s >> o.what >> o.kernel >> o.test >> o.trial >> o.incremental;
+            double v;
+            while (s >> v) o.p.push_back(v);
+            j.ops.push_back(o);
+        }
+    }
+    return j;
+}
+
+// Dirichlet callback handed to dof::constrainBoundary: the value comes from a table indexed by the DoF id, so that
+// WHICH DoFs get constrained is decided by the reference's boundary extraction alone.
+template <typename DOF, typename VEC>
+void prescribeFromTable(const VEC&, DOF* doF, const std::vector<double>* table) {
+    const std::size_t id = doF->getID();
+    for (unsigned d = 0; d < DOF::size; d++)
+        if (doF->isActive(d)) doF->constrainValue(d, (*table)[id * DOF::size + d]);
+}
+
+template <unsigned DS>
+struct ConstantForce {
+    typedef typename base::Vector<DS>::Type result_type;
+    result_type f;
+    template <typename X>
+    result_type operator()(const X&) const { return f; }
+};
+
+template <typename MESH, typename FEBASIS, typename FIELD>
+void setUpField(const MESH& mesh, FIELD& field, const FieldSpec& spec, const base::mesh::MeshBoundary& boundary) {
+    typedef typename FIELD::DegreeOfFreedom DoF;
+    base::dof::generate<FEBASIS>(mesh, field);
+    const std::vector<double> presc = readF64(spec.presc), values = readF64(spec.values);
+    if (spec.boundary) {
+        typedef typename base::Vector<MESH::Node::dim>::Type VecDim;
+        base::dof::constrainBoundary<FEBASIS>(boundary.begin(), boundary.end(), mesh, field,
+                                              boost::bind(&prescribeFromTable<DoF, VecDim>, _1, _2, &presc));
+    }
+    if (spec.pin >= 0) {
+        typename FIELD::DoFPtrIter it = field.doFsBegin();
+        std::advance(it, spec.pin);
+        (*it)->constrainValue(0, 0.0);
+    }
+    if (!values.empty()) {
+        for (typename FIELD::DoFPtrIter it = field.doFsBegin(); it != field.doFsEnd(); ++it)
+            for (unsigned d = 0; d < DoF::size; d++) (*it)->setValue(d, values[(*it)->getID() * DoF::size + d]);
+    }
+}
+
+template <typename FIELD>
+void dumpField(const FIELD& field, const std::string& prefix) {
+    typedef typename FIELD::DegreeOfFreedom DoF;
+    {
+        std::ofstream o((prefix + ".elemdof.txt").c_str());
+        for (typename FIELD::ElementPtrConstIter e = field.elementsBegin(); e != field.elementsEnd(); ++e) {
+            for (typename FIELD::Element::DoFPtrConstIter d = (*e)->doFsBegin(); d != (*e)->doFsEnd(); ++d)
+                o << (*d)->getID() << " ";
+            o << "\n";
+        }
+    }
+    {
+        std::ofstream o((prefix + ".dofs.txt").c_str());
+        o << std::setprecision(17);
+        for (typename FIELD::DoFPtrConstIter d = field.doFsBegin(); d != field.doFsEnd(); ++d) {
+            o << (*d)->getID();
+            for (unsigned c = 0; c < DoF::size; c++) {
+                const bool act = (*d)->isActive(c), con = (*d)->isConstrained(c);
+                std::vector<double> pv(DoF::size);
+                o << " " << (act ? 0 : (con ? 1 : 2)) << " " << (act ? static_cast<long>((*d)->getIndex(c)) : -1L);
+            }
+            o << "\n";
+        }
+    }
+}
+
+template <typename SOLVER>
+void dumpSystem(const SOLVER& solver, const std::string& prefix) {
+    std::ofstream a((prefix + ".lhs.txt").c_str());
+    a << std::setprecision(17);
+    solver.debugLHS(a);
+    std::ofstream b((prefix + ".rhs.txt").c_str());
+    b << std::setprecision(17);
+    solver.debugRHS(b);
+}
+
+static double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+enum Kind { SCALAR, VECTOR, SOLID };
+
+// ---- one field (Bubnov) cases: scalar Laplace, vector Laplace, hyperelastic solids --------------------------------
+template <base::Shape SHAPE, unsigned FDEG, unsigned DS, unsigned QDEG, unsigned QDEGBODY, Kind KIND>
+int runSingle(const Job& job) {
+    typedef base::Unstructured<SHAPE, 1> Mesh;
+    typedef base::fe::Basis<SHAPE, FDEG> FEBasis;
+    typedef base::Field<FEBasis, DS> Field;
+    typedef base::asmb::FieldBinder<Mesh, Field> FieldBinder;
+    typedef typename FieldBinder::template TupleBinder<1, 1>::Type FTB;
+    typedef base::Quadrature<QDEG, SHAPE> Quadrature;
+    typedef base::Quadrature<QDEGBODY, SHAPE> QuadratureBody;
+    typedef base::solver::Eigen3 Solver;
+
+    Mesh mesh;
+    {
+        std::ifstream smf(job.mesh.c_str());
+        VERIFY_MSG(smf.is_open(), "cannot open mesh");
+        base::io::smf::readMesh(smf, mesh);
+    }
+    base::mesh::MeshBoundary boundary;
+    boundary.create(mesh.elementsBegin(), mesh.elementsEnd());
+    Field field;
+    setUpField<Mesh, FEBasis>(mesh, field, job.fields.at(0), boundary);
+    const std::size_t numDoFs = base::dof::numberDoFsConsecutively(field.doFsBegin(), field.doFsEnd());
+    if (job.dump) dumpField(field, job.out + ".f0");
+
+    FieldBinder fieldBinder(mesh, field);
+    Quadrature quadrature;
+    QuadratureBody quadratureBody;
+
+    double best = 1e300;
+    for (int rep = 0; rep < job.repeat; rep++) {
+        const double t0 = now();
+        Solver solver(numDoFs);
+        if (job.registerFields) solver.template registerFields<FTB>(fieldBinder);
+        const double t1 = now();
+        for (const Op& op : job.ops) {
+            if (op.what == "body") {
+                ConstantForce<DS> f;
+                for (unsigned d = 0; d < DS; d++) f.f[d] = op.p[d];
+                base::asmb::bodyForceComputation<FTB>(quadratureBody, solver, fieldBinder, f);
+                continue;
+            }
+            if constexpr (KIND == SCALAR) {
+                heat::Laplace<typename FTB::Tuple> kernel(op.p[0]);
+                if (op.what == "matrix")
+                    base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                else
+                    base::asmb::computeResidualForces<FTB>(quadrature, solver, fieldBinder, kernel);
+            } else if constexpr (KIND == VECTOR) {
+                fluid::VectorLaplace<typename FTB::Tuple> kernel(op.p[0]);
+                if (op.what == "matrix")
+                    base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                else
+                    base::asmb::computeResidualForces<FTB>(quadrature, solver, fieldBinder, kernel);
+            } else {
+                if (op.kernel == "stvenant") {
+                    typedef mat::hypel::StVenant Material;
+                    Material material(op.p[0], op.p[1]);
+                    solid::HyperElastic<Material, typename FTB::Tuple> kernel(material);
+                    if (op.what == "matrix")
+                        base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                    else
+                        base::asmb::computeResidualForces<FTB>(quadrature, solver, fieldBinder, kernel);
+                } else {
+                    typedef mat::hypel::NeoHookeanCompressible Material;
+                    Material material(op.p[0], op.p[1]);
+                    solid::HyperElastic<Material, typename FTB::Tuple> kernel(material);
+                    if (op.what == "matrix")
+                        base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                    else
+                        base::asmb::computeResidualForces<FTB>(quadrature, solver, fieldBinder, kernel);
+                }
+            }
+        }
+        const double t2 = now();
+        solver.finishAssembly();
+        const double t3 = now();
+        best = std::min(best, t2 - t1);
+        std::printf("rep %d  elements %zu  dofs %zu  register %.6f s  assemble %.6f s  finish %.6f s\n", rep,
+                    static_cast<std::size_t>(std::distance(mesh.elementsBegin(), mesh.elementsEnd())), numDoFs, t1 - t0,
+                    t2 - t1, t3 - t2);
+        if (job.dump && rep == 0) dumpSystem(solver, job.out);
+    }
+    std::printf("best_assemble_seconds %.9f\n", best);
+    return 0;
+}
+
+// ---- Taylor-Hood Stokes blocks (velocity FDEG x dim, pressure FDEG-1 x 1) -----------------------------------------
+template <base::Shape SHAPE, unsigned FDEG, unsigned QDEG>
+int runStokes(const Job& job) {
+    typedef base::Unstructured<SHAPE, 1> Mesh;
+    static const unsigned dim = Mesh::Node::dim;
+    typedef base::fe::Basis<SHAPE, FDEG> FEBasisU;
+    typedef base::fe::Basis<SHAPE, FDEG - 1> FEBasisP;
+    typedef base::Field<FEBasisU, dim> Velocity;
+    typedef base::Field<FEBasisP, 1> Pressure;
+    typedef base::asmb::FieldBinder<Mesh, Velocity, Pressure> Binder;
+    typedef typename Binder::template TupleBinder<1, 1>::Type UU;
+    typedef typename Binder::template TupleBinder<1, 2>::Type UP;
+    typedef typename Binder::template TupleBinder<2, 1>::Type PU;
+    typedef base::Quadrature<QDEG, SHAPE> Quadrature;
+    typedef base::solver::Eigen3 Solver;
+
+    Mesh mesh;
+    {
+        std::ifstream smf(job.mesh.c_str());
+        VERIFY_MSG(smf.is_open(), "cannot open mesh");
+        base::io::smf::readMesh(smf, mesh);
+    }
+    base::mesh::MeshBoundary boundary;
+    boundary.create(mesh.elementsBegin(), mesh.elementsEnd());
+    Velocity velocity;
+    Pressure pressure;
+    setUpField<Mesh, FEBasisU>(mesh, velocity, job.fields.at(0), boundary);
+    setUpField<Mesh, FEBasisP>(mesh, pressure, job.fields.at(1), boundary);
+    const std::size_t nU = base::dof::numberDoFsConsecutively(velocity.doFsBegin(), velocity.doFsEnd());
+    const std::size_t nP = base::dof::numberDoFsConsecutively(pressure.doFsBegin(), pressure.doFsEnd(), nU);
+    if (job.dump) {
+        dumpField(velocity, job.out + ".f0");
+        dumpField(pressure, job.out + ".f1");
+    }
+    Binder binder(mesh, velocity, pressure);
+    Quadrature quadrature;
+    double best = 1e300;
+    for (int rep = 0; rep < job.repeat; rep++) {
+        Solver solver(nU + nP);
+        if (job.registerFields) {
+            solver.template registerFields<UU>(binder);
+            solver.template registerFields<UP>(binder);
+            solver.template registerFields<PU>(binder);
+        }
+        const double t1 = now();
+        for (const Op& op : job.ops) {
+            const bool matrix = (op.what == "matrix"), incr = (op.incremental != 0);
+            if (op.kernel == "vector_laplace") {
+                fluid::VectorLaplace<typename UU::Tuple> k(op.p[0]);
+                if (matrix) base::asmb::stiffnessMatrixComputation<UU>(quadrature, solver, binder, k, incr);
+                else base::asmb::computeResidualForces<UU>(quadrature, solver, binder, k);
+            } else if (op.kernel == "pressure_gradient") {
+                fluid::PressureGradient<typename UP::Tuple> k;
+                if (matrix) base::asmb::stiffnessMatrixComputation<UP>(quadrature, solver, binder, k, incr);
+                else base::asmb::computeResidualForces<UP>(quadrature, solver, binder, k);
+            } else if (op.kernel == "velocity_divergence") {
+                fluid::VelocityDivergence<typename PU::Tuple> k(!op.p.empty() && op.p[0] != 0.0);
+                if (matrix) base::asmb::stiffnessMatrixComputation<PU>(quadrature, solver, binder, k, incr);
+                else base::asmb::computeResidualForces<PU>(quadrature, solver, binder, k);
+            } else {
+                VERIFY_MSG(false, "unknown kernel " + op.kernel);
+            }
+        }
+        const double t2 = now();
+        solver.finishAssembly();
+        best = std::min(best, t2 - t1);
+        std::printf("rep %d  elements %zu  dofs %zu  assemble %.6f s\n", rep,
+                    static_cast<std::size_t>(std::distance(mesh.elementsBegin(), mesh.elementsEnd())), nU + nP, t2 - t1);
+        if (job.dump && rep == 0) dumpSystem(solver, job.out);
+    }
+    std::printf("best_assemble_seconds %.9f\n", best);
+    return 0;
+}
+
+}  // namespace drv
+
+int main(int argc, char* argv[]) {
+    if (argc != 2) {
+        std::cerr << "usage: " << argv[0] << " job.txt\n";
+        return 2;
+    }
+    using namespace drv;
+    const Job job = readJob(argv[1]);
+    const std::string& t = job.type;
+    //                                   shape      fdeg ds qdeg qbody kind
+    if (t == "laplace_q1_hex") return runSingle<base::HEX, 1, 1, 3, 3, SCALAR>(job);
+    if (t == "laplace_q2_hex") return runSingle<base::HEX, 2, 1, 4, 4, SCALAR>(job);
+    if (t == "laplace_p1_tet") return runSingle<base::TET, 1, 1, 3, 2, SCALAR>(job);
+    if (t == "laplace_q1_quad") return runSingle<base::QUAD, 1, 1, 3, 3, SCALAR>(job);
+    if (t == "laplace_p2_tri") return runSingle<base::TRI, 2, 1, 4, 4, SCALAR>(job);
+    if (t == "vector_laplace_q1_hex") return runSingle<base::HEX, 1, 3, 3, 3, VECTOR>(job);
+    if (t == "solid_q1_hex") return runSingle<base::HEX, 1, 3, 3, 3, SOLID>(job);
+    if (t == "solid_q2_hex") return runSingle<base::HEX, 2, 3, 4, 4, SOLID>(job);
+    if (t == "solid_q1_quad") return runSingle<base::QUAD, 1, 2, 3, 3, SOLID>(job);
+    if (t == "solid_p2_tet") return runSingle<base::TET, 2, 3, 4, 4, SOLID>(job);
+    if (t == "stokes_p2p1_tet") return runStokes<base::TET, 2, 4>(job);
+    if (t == "stokes_q2q1_hex") return runStokes<base::HEX, 2, 4>(job);
+    if (t == "stokes_q2q1_quad") return runStokes<base::QUAD, 2, 4>(job);
+    std::cerr << "unknown case type '" << t << "'\n";
+    return 2;
+}

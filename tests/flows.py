@@ -67,7 +67,7 @@ class Case:
         if values is not None:
             vals = np.asarray(values(self.dof_positions(fe_deg, ed, nobj)), dtype=np.float64).reshape(nobj, ds)
         self.fields.append(dict(fe_deg=fe_deg, ds=ds, n_obj=nobj, elem_dof=ed, status=status, presc=presc, eqn=eqn,
-                                values=vals))
+                                values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1))
         return len(self.fields) - 1
 
     def dof_positions(self, fe_deg, ed, nobj):
