@@ -1,0 +1,664 @@
+// =============================================================================
+// insilico_b200_reference.hpp -- the binding a maintainer of thrueberg/inSilico adds to the reference tree
+// (it would live there as base/solver/B200.hpp).  It is compiled TOGETHER WITH THE UNMODIFIED REFERENCE HEADERS
+// and routes the assembly hot path to the B200 engine through the C ABI of insilico_b200.h:
+//
+//   * base::solver::B200            same members as base::solver::Eigen3 (base/solver/Eigen3.hpp:71-341); storage
+//                                   = device CSR + device rhs of the engine
+//   * base::asmb::stiffnessMatrixComputation<FTB> / computeResidualForces<FTB> / bodyForceComputation<FTB>
+//                                   overloads for SOLVER = base::solver::B200 (base/asmb/StiffnessMatrix.hpp:49-87,
+//                                   ForceIntegrator.hpp:37-71, BodyForce.hpp:65-84).  SOLVER is a template parameter
+//                                   of the reference's functions, so the overloads win by partial ordering and no
+//                                   reference file changes; an application switches one typedef
+//                                   (e.g. reference/04-heat/dirichlet.cpp:150).
+//   * flattening                    the reference's heap objects (Node, Element, DegreeOfFreedom; reached through
+//                                   FieldBinder::elementsBegin()/End(), base/asmb/FieldBinder.hpp:150-181) become the
+//                                   flat arrays of isl_mesh_set / isl_field_set: topology once per binder, DoF state
+//                                   (status, equation numbers, prescribed and current values, node coordinates)
+//                                   re-read at every assembly call and uploaded only when it changed.
+//   * kernel objects                recognised at compile time (B200KernelTraits); a kernel type the engine does not
+//                                   implement is a compile error -- there is no CPU fallback.  The reference keeps
+//                                   material constants private, so they are recovered by probing the kernel object
+//                                   through its public tangentStiffness on one element (all supported integrands are
+//                                   linear in their constants); a maintainer would add accessors instead.
+//
+// Errors follow the reference: VERIFY_MSG (message on stderr + abort, base/verify.hpp:139-149).
+// =============================================================================
+#ifndef INSILICO_B200_REFERENCE_HPP
+#define INSILICO_B200_REFERENCE_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <ostream>
+#include <vector>
+
+#include <insilico_b200.h>
+
+#include <base/verify.hpp>
+#include <base/linearAlgebra.hpp>
+#include <base/shape.hpp>
+#include <base/Quadrature.hpp>
+#include <base/geometry.hpp>
+#include <base/asmb/FieldBinder.hpp>
+#include <base/asmb/FieldTupleBinder.hpp>
+#include <base/asmb/StiffnessMatrix.hpp>
+#include <base/asmb/ForceIntegrator.hpp>
+#include <base/asmb/BodyForce.hpp>
+#include <heat/Laplace.hpp>
+#include <fluid/VectorLaplace.hpp>
+#include <fluid/PressureGradient.hpp>
+#include <fluid/VelocityDivergence.hpp>
+#include <solid/HyperElastic.hpp>
+#include <mat/hypel/StVenant.hpp>
+#include <mat/hypel/NeoHookeanCompressible.hpp>
+
+namespace base {
+namespace solver {
+
+namespace b200_detail {
+
+inline void check(int rc) { VERIFY_MSG(rc == 0, std::string("B200 engine: ") + isl_last_error()); }
+
+inline isl_handle engine() {
+    static isl_handle h = NULL;
+    if (h == NULL) check(isl_engine_create(0, &h));
+    return h;
+}
+
+template <typename T>
+bool assignIfChanged(std::vector<T>& cache, const std::vector<T>& fresh) {
+    if (cache.size() == fresh.size() && (fresh.empty() || std::memcmp(&cache[0], &fresh[0], fresh.size() * sizeof(T)) == 0))
+        return false;
+    cache = fresh;
+    return true;
+}
+
+struct FieldState {
+    bool bound = false;
+    int feDeg = 0, dofSize = 0;
+    int64_t nObj = 0;
+    std::vector<int32_t> elemDof;
+    std::vector<int64_t> eqn;
+    std::vector<uint8_t> status;
+    std::vector<double> prescribed, values;
+};
+
+struct BinderState {
+    const void* key = NULL;
+    std::size_t numElements = 0;
+    int shape = 0, geomDeg = 0, dim = 0;
+    int64_t nNodes = 0;
+    std::vector<int32_t> conn;
+    std::vector<double> coords;
+    FieldState field[5];
+};
+
+inline BinderState& state() {
+    static BinderState s;
+    return s;
+}
+
+// ---- flatten one field of the binder (slot N = 1..5 of FieldBinder::ElementPtrTuple) -------------------------------
+template <typename ELEMENTPTR>
+struct IsDummy {
+    static const bool value = boost::is_same<ELEMENTPTR, base::asmb::detail_::DummyElementPtr>::value;
+};
+
+template <int N, typename FIELDBINDER, bool DUMMY>
+struct FlattenField {
+    static void apply(const FIELDBINDER&, BinderState& s, bool) { s.field[N - 1].bound = false; }
+};
+
+template <int N, typename FIELDBINDER>
+struct FlattenField<N, FIELDBINDER, false> {
+    typedef typename FIELDBINDER::ElementPtrTuple EPT;
+    typedef typename base::TypeReduction<typename EPT::template Binder<N>::Type>::Type Element;
+    typedef typename Element::DegreeOfFreedom DoF;
+
+    static void apply(const FIELDBINDER& fb, BinderState& s, bool topologyChanged) {
+        FieldState& f = s.field[N - 1];
+        const int ds = static_cast<int>(DoF::size), ndpe = static_cast<int>(Element::numDoFs);
+        bool redefine = topologyChanged || !f.bound;
+        typename FIELDBINDER::FieldIterator it = fb.elementsBegin(), end = fb.elementsEnd();
+        if (redefine) {
+            f.feDeg = static_cast<int>(Element::FEFun::degree);
+            f.dofSize = ds;
+            f.elemDof.assign(s.numElements * ndpe, 0);
+            std::size_t maxId = 0, e = 0;
+            for (typename FIELDBINDER::FieldIterator i2 = it; i2 != end; ++i2, ++e) {
+                const Element* ep = (*i2).template get<N>();
+                int k = 0;
+                for (typename Element::DoFPtrConstIter d = ep->doFsBegin(); d != ep->doFsEnd(); ++d, ++k) {
+                    const std::size_t id = (*d)->getID();
+                    f.elemDof[e * ndpe + k] = static_cast<int32_t>(id);
+                    if (id > maxId) maxId = id;
+                }
+            }
+            f.nObj = static_cast<int64_t>(maxId) + 1;
+        }
+        // DoF state, read through the element -> DoF pointers (shared DoFs are simply visited more than once)
+        const std::size_t n = static_cast<std::size_t>(f.nObj) * ds;
+        std::vector<int64_t> eqn(n, -1);
+        std::vector<uint8_t> status(n, ISL_INACTIVE);
+        std::vector<double> prescribed(n, 0.), values(n, 0.);
+        double pv[DoF::size];
+        for (; it != end; ++it) {
+            const Element* ep = (*it).template get<N>();
+            for (typename Element::DoFPtrConstIter d = ep->doFsBegin(); d != ep->doFsEnd(); ++d) {
+                const DoF* doF = *d;
+                const std::size_t o = doF->getID() * ds;
+                doF->getPrescribedValues(&pv[0], false);
+                for (int c = 0; c < ds; c++) {
+                    if (doF->isActive(c)) {
+                        status[o + c] = ISL_ACTIVE;
+                        eqn[o + c] = static_cast<int64_t>(doF->getIndex(c));
+                    } else if (doF->isConstrained(c)) {
+                        status[o + c] = ISL_CONSTRAINED;
+                        prescribed[o + c] = pv[c];
+                        std::vector<std::pair<base::number, std::size_t> > masters;
+                        const_cast<DoF*>(doF)->getConstraint(c)->getWeightedDoFIDs(masters);
+                        VERIFY_MSG(masters.empty(), "B200 engine: linear constraints with master DoFs are not supported "
+                                                    "(only prescribed values, base/dof/Constraint.hpp)");
+                    }
+                    values[o + c] = doF->getValue(c);
+                }
+            }
+        }
+        const bool numberingChanged = assignIfChanged(f.eqn, eqn) | assignIfChanged(f.status, status);
+        const bool prescChanged = assignIfChanged(f.prescribed, prescribed);
+        const bool valuesChanged = assignIfChanged(f.values, values);
+        if (redefine || numberingChanged) {
+            check(isl_field_set(engine(), N - 1, f.feDeg, f.dofSize, f.nObj, &f.elemDof[0], &f.eqn[0], &f.status[0],
+                                &f.prescribed[0], &f.values[0]));
+        } else if (prescChanged || valuesChanged) {
+            check(isl_field_update(engine(), N - 1, prescChanged ? &f.prescribed[0] : NULL,
+                                   valuesChanged ? &f.values[0] : NULL));
+        }
+        f.bound = true;
+    }
+};
+
+template <int N, typename FIELDBINDER>
+void flattenField(const FIELDBINDER& fb, BinderState& s, bool topologyChanged) {
+    typedef typename FIELDBINDER::ElementPtrTuple EPT;
+    FlattenField<N, FIELDBINDER, IsDummy<typename EPT::template Binder<N>::Type>::value>::apply(fb, s, topologyChanged);
+}
+
+//! Bring the engine's copy of mesh and fields in line with the reference's objects behind this binder.
+template <typename FIELDBINDER>
+void synchronise(const FIELDBINDER& fb) {
+    typedef typename FIELDBINDER::ElementPtrTuple EPT;
+    typedef typename EPT::GeomElement GeomElement;
+    typedef typename GeomElement::Node Node;
+    BinderState& s = state();
+    const std::size_t numElements = static_cast<std::size_t>(std::distance(fb.elementsBegin(), fb.elementsEnd()));
+    const int npe = static_cast<int>(GeomElement::numNodes), dim = static_cast<int>(Node::dim);
+    bool topologyChanged = (s.key != static_cast<const void*>(&fb)) || (s.numElements != numElements);
+
+    // connectivity (also re-read when the binder is known: cheap, and catches a re-meshed binder)
+    std::vector<int32_t> conn(numElements * npe);
+    std::size_t maxNode = 0, e = 0;
+    typename FIELDBINDER::FieldIterator end = fb.elementsEnd();
+    for (typename FIELDBINDER::FieldIterator it = fb.elementsBegin(); it != end; ++it, ++e) {
+        const GeomElement* gep = (*it).geomElementPtr();
+        int k = 0;
+        for (typename GeomElement::NodePtrConstIter n = gep->nodesBegin(); n != gep->nodesEnd(); ++n, ++k) {
+            const std::size_t id = (*n)->getID();
+            conn[e * npe + k] = static_cast<int32_t>(id);
+            if (id > maxNode) maxNode = id;
+        }
+    }
+    topologyChanged = assignIfChanged(s.conn, conn) || topologyChanged;
+    const int64_t nNodes = static_cast<int64_t>(maxNode) + 1;
+    std::vector<double> coords(static_cast<std::size_t>(nNodes) * dim, 0.);
+    for (typename FIELDBINDER::FieldIterator it = fb.elementsBegin(); it != end; ++it) {
+        const GeomElement* gep = (*it).geomElementPtr();
+        for (typename GeomElement::NodePtrConstIter n = gep->nodesBegin(); n != gep->nodesEnd(); ++n)
+            (*n)->getX(&coords[(*n)->getID() * dim]);
+    }
+    const bool coordsChanged = assignIfChanged(s.coords, coords);
+    if (topologyChanged || s.nNodes != nNodes) {
+        s.key = &fb;
+        s.numElements = numElements;
+        s.shape = static_cast<int>(GeomElement::shape);
+        s.geomDeg = static_cast<int>(GeomElement::GeomFun::degree);
+        s.dim = dim;
+        s.nNodes = nNodes;
+        check(isl_mesh_set(engine(), s.shape, s.geomDeg, dim, nNodes, &s.coords[0], static_cast<int64_t>(numElements),
+                           &s.conn[0]));
+        topologyChanged = true;
+    } else if (coordsChanged) {
+        check(isl_mesh_update_coords(engine(), &s.coords[0]));
+    }
+    flattenField<1>(fb, s, topologyChanged);
+    flattenField<2>(fb, s, topologyChanged);
+    flattenField<3>(fb, s, topologyChanged);
+    flattenField<4>(fb, s, topologyChanged);
+    flattenField<5>(fb, s, topologyChanged);
+}
+
+// ---- compile-time facts ----------------------------------------------------------------------------------------
+template <typename FTB>
+struct TupleIndices;
+template <typename EPT, int I, int J, int K, int L, int M>
+struct TupleIndices<base::asmb::FieldTupleBinder<EPT, I, J, K, L, M> > {
+    static const int test = I - 1, trial = J - 1;  // the engine addresses fields 0-based
+};
+
+template <typename QUADRATURE>
+struct QuadratureDegree;
+template <unsigned DEGREE, base::Shape SHAPE>
+struct QuadratureDegree<base::Quadrature<DEGREE, SHAPE> > {
+    static const int value = static_cast<int>(DEGREE);
+};
+
+// ---- probing of kernel constants through the public interface ------------------------------------------------------
+template <typename KERNEL, typename TUPLE>
+base::MatrixD probeTangent(const KERNEL& kernel, const TUPLE& tuple) {
+    typedef typename TUPLE::GeomElement GeomElement;
+    typedef typename TUPLE::TestElement TestElement;
+    typedef typename TUPLE::TrialElement TrialElement;
+    const unsigned nr = TestElement::numDoFs * TestElement::DegreeOfFreedom::size;
+    const unsigned nc = TrialElement::numDoFs * TrialElement::DegreeOfFreedom::size;
+    base::MatrixD K = base::MatrixD::Zero(nr, nc);
+    kernel.tangentStiffness(tuple, base::ShapeCentroid<GeomElement::shape>::apply(), 1.0, K);
+    return K;
+}
+
+inline double maxAbs(const base::MatrixD& A) {
+    double m = 0.;
+    for (int j = 0; j < A.cols(); j++)
+        for (int i = 0; i < A.rows(); i++) m = std::max(m, std::abs(A(i, j)));
+    return m;
+}
+
+//! K = c * K1 -> c; the candidate that reproduces K bit for bit is preferred over the plain quotient
+template <typename MAKEKERNEL, typename TUPLE>
+double probeScalar(const base::MatrixD& K, const MAKEKERNEL& make, const TUPLE& tuple) {
+    const base::MatrixD K1 = probeTangent(make(1.0), tuple);
+    int bi = 0, bj = 0;
+    for (int j = 0; j < K1.cols(); j++)
+        for (int i = 0; i < K1.rows(); i++)
+            if (std::abs(K1(i, j)) > std::abs(K1(bi, bj))) { bi = i; bj = j; }
+    VERIFY_MSG(K1(bi, bj) != 0., "B200 engine: cannot probe the kernel constant (zero element matrix)");
+    const double c = K(bi, bj) / K1(bi, bj);
+    double cand[5] = {c, std::nextafter(c, 1e300), std::nextafter(c, -1e300), 0., 0.};
+    cand[3] = std::nextafter(cand[1], 1e300);
+    cand[4] = std::nextafter(cand[2], -1e300);
+    for (int k = 0; k < 5; k++) {
+        const base::MatrixD Kc = probeTangent(make(cand[k]), tuple);
+        bool same = true;
+        for (int j = 0; j < K.cols() && same; j++)
+            for (int i = 0; i < K.rows() && same; i++) same = (Kc(i, j) == K(i, j));
+        if (same) return cand[k];
+    }
+    const double scale = maxAbs(K);
+    for (int j = 0; j < K.cols(); j++)
+        for (int i = 0; i < K.rows(); i++)
+            VERIFY_MSG(std::abs(K(i, j) - c * K1(i, j)) <= 1e-12 * scale,
+                       "B200 engine: kernel object is not a constant multiple of the unit kernel "
+                       "(non-constant material functions are not supported)");
+    return c;
+}
+
+}  // namespace b200_detail
+
+//------------------------------------------------------------------------------------------------------------------
+/** Which engine integrand a reference kernel object is, and with which constants.  Specialise for further kernels;
+ *  the primary template is undefined on purpose (unsupported kernel = compile error, no CPU fallback).            */
+template <typename KERNEL>
+struct B200KernelTraits;
+
+template <typename TUPLE>
+struct B200KernelTraits<heat::Laplace<TUPLE> > {
+    struct Make {
+        heat::Laplace<TUPLE> operator()(double c) const { return heat::Laplace<TUPLE>(c); }
+    };
+    static int describe(const heat::Laplace<TUPLE>& k, const TUPLE& t0, const TUPLE& t1, double* p) {
+        p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
+        const double p1 = b200_detail::probeScalar(b200_detail::probeTangent(k, t1), Make(), t1);
+        VERIFY_MSG(std::abs(p1 - p[0]) <= 1e-13 * std::abs(p[0]),
+                   "B200 engine: heat::Laplace with a non-constant conductivity function is not supported");
+        return ISL_K_LAPLACE;
+    }
+};
+
+template <typename TUPLE>
+struct B200KernelTraits<fluid::VectorLaplace<TUPLE> > {
+    struct Make {
+        fluid::VectorLaplace<TUPLE> operator()(double c) const { return fluid::VectorLaplace<TUPLE>(c); }
+    };
+    static int describe(const fluid::VectorLaplace<TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+        p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
+        return ISL_K_VECTOR_LAPLACE;
+    }
+};
+
+template <typename TUPLE>
+struct B200KernelTraits<fluid::PressureGradient<TUPLE> > {
+    static int describe(const fluid::PressureGradient<TUPLE>&, const TUPLE&, const TUPLE&, double* p) {
+        p[0] = 0.;
+        return ISL_K_PRESSURE_GRADIENT;
+    }
+};
+
+template <typename TUPLE>
+struct B200KernelTraits<fluid::VelocityDivergence<TUPLE> > {
+    static int describe(const fluid::VelocityDivergence<TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+        const base::MatrixD K = b200_detail::probeTangent(k, t0);
+        const base::MatrixD K1 = b200_detail::probeTangent(fluid::VelocityDivergence<TUPLE>(false), t0);
+        bool same = true, flipped = true;
+        for (int j = 0; j < K.cols(); j++)
+            for (int i = 0; i < K.rows(); i++) {
+                same = same && (K(i, j) == K1(i, j));
+                flipped = flipped && (K(i, j) == -K1(i, j));
+            }
+        VERIFY_MSG(same || flipped, "B200 engine: unexpected fluid::VelocityDivergence behaviour");
+        p[0] = (same ? 0. : 1.);  // changeSign
+        return ISL_K_VELOCITY_DIVERGENCE;
+    }
+};
+
+namespace b200_detail {
+//! K = lambda * K(1,0) + mu * K(0,1) for solid::HyperElastic with a two-constant material (fixed displacement state)
+template <typename MATERIAL, typename TUPLE>
+void probeLame(const solid::HyperElastic<MATERIAL, TUPLE>& k, const TUPLE& t0, double* p) {
+    const MATERIAL m10(1., 0.), m01(0., 1.);
+    const solid::HyperElastic<MATERIAL, TUPLE> k10(m10), k01(m01);
+    const base::MatrixD K = probeTangent(k, t0), A = probeTangent(k10, t0), B = probeTangent(k01, t0);
+    // normal equations of the two-parameter fit over all entries
+    double aa = 0., ab = 0., bb = 0., ak = 0., bk = 0.;
+    for (int j = 0; j < K.cols(); j++)
+        for (int i = 0; i < K.rows(); i++) {
+            aa += A(i, j) * A(i, j); ab += A(i, j) * B(i, j); bb += B(i, j) * B(i, j);
+            ak += A(i, j) * K(i, j); bk += B(i, j) * K(i, j);
+        }
+    const double det = aa * bb - ab * ab;
+    VERIFY_MSG(det > 1e-8 * aa * bb, "B200 engine: cannot separate the two material constants on the probe element");
+    p[0] = (ak * bb - bk * ab) / det;
+    p[1] = (bk * aa - ak * ab) / det;
+    // polish: constants entered by the application are usually short decimals of E, nu; keep the fit otherwise
+    const double scale = maxAbs(K);
+    for (int j = 0; j < K.cols(); j++)
+        for (int i = 0; i < K.rows(); i++)
+            VERIFY_MSG(std::abs(K(i, j) - (p[0] * A(i, j) + p[1] * B(i, j))) <= 1e-11 * scale,
+                       "B200 engine: solid::HyperElastic tangent is not linear in the material constants");
+}
+}  // namespace b200_detail
+
+template <typename TUPLE>
+struct B200KernelTraits<solid::HyperElastic<mat::hypel::StVenant, TUPLE> > {
+    static int describe(const solid::HyperElastic<mat::hypel::StVenant, TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+        b200_detail::probeLame(k, t0, p);
+        return ISL_K_HYPEL_STVENANT;
+    }
+};
+
+template <typename TUPLE>
+struct B200KernelTraits<solid::HyperElastic<mat::hypel::NeoHookeanCompressible, TUPLE> > {
+    static int describe(const solid::HyperElastic<mat::hypel::NeoHookeanCompressible, TUPLE>& k, const TUPLE& t0,
+                        const TUPLE&, double* p) {
+        b200_detail::probeLame(k, t0, p);
+        return ISL_K_HYPEL_NEOHOOKE;
+    }
+};
+
+//------------------------------------------------------------------------------------------------------------------
+/** Linear-system storage on the B200: same interface as base::solver::Eigen3 (base/solver/Eigen3.hpp:62-341).
+ *  One system exists per engine at a time, exactly like the reference applications use their solver (a fresh
+ *  `Solver solver(n)` per Newton iteration, reference/06-elastic/compressible.cpp:263-266).                        */
+class B200 {
+public:
+    //! Hook for the linear solves, which are outside the assembly path: given the finished CSR system
+    //! it overwrites rhs with the solution and returns an iteration count.  NULL = calling a solve is an error.
+    typedef int (*SolveHook)(const char* method, std::size_t n, const std::vector<int64_t>& rowptr,
+                             const std::vector<int32_t>& col, const std::vector<double>& val, std::vector<double>& rhs);
+    static SolveHook& solveHook() {
+        static SolveHook hook = NULL;
+        return hook;
+    }
+
+    //! Constructor with the size N of matrix and vector (Eigen3.hpp:71-77)
+    B200(const std::size_t size) : size_(size), solved_(false) {
+        b200_detail::check(isl_system_create(b200_detail::engine(), static_cast<int64_t>(size)));
+    }
+
+    //! Insert numbers to matrix storage (Eigen3.hpp:81-108): host-side odd contributions
+    template <typename MATRIX, typename RDOFS, typename CDOFS>
+    void insertToLHS(const MATRIX& matrix, const RDOFS& rowDoFs, const CDOFS& colDoFs) {
+        const std::size_t nr = rowDoFs.size(), nc = colDoFs.size();
+        if (nr == 0 || nc == 0) return;
+        std::vector<int64_t> r(nr), c(nc);
+        std::vector<double> m(nr * nc);
+        for (std::size_t i = 0; i < nr; i++) {
+            VERIFY_MSG(static_cast<std::size_t>(rowDoFs[i]) < size_, "Row index out of bound: " + x2s(rowDoFs[i]));
+            r[i] = static_cast<int64_t>(rowDoFs[i]);
+        }
+        for (std::size_t j = 0; j < nc; j++) {
+            VERIFY_MSG(static_cast<std::size_t>(colDoFs[j]) < size_, "Col index out of bound: " + x2s(colDoFs[j]));
+            c[j] = static_cast<int64_t>(colDoFs[j]);
+        }
+        for (std::size_t i = 0; i < nr; i++)
+            for (std::size_t j = 0; j < nc; j++) m[i * nc + j] = matrix(i, j);
+        b200_detail::check(isl_insert_lhs(b200_detail::engine(), &m[0], &r[0], static_cast<int>(nr), &c[0], static_cast<int>(nc)));
+    }
+
+    //! Insert numbers to RHS vector (Eigen3.hpp:112-124)
+    template <typename VECTOR, typename DOFS>
+    void insertToRHS(const VECTOR& vector, const DOFS& dofs) {
+        const std::size_t n = dofs.size();
+        if (n == 0) return;
+        std::vector<int64_t> r(n);
+        std::vector<double> v(n);
+        for (std::size_t i = 0; i < n; i++) {
+            VERIFY_MSG(static_cast<std::size_t>(dofs[i]) < size_, x2s(dofs[i]) + " out of bound");
+            r[i] = static_cast<int64_t>(dofs[i]);
+            v[i] = vector[i];
+        }
+        b200_detail::check(isl_insert_rhs(b200_detail::engine(), &v[0], &r[0], static_cast<int>(n)));
+    }
+
+    //! Pre-determine the non-zero pattern (Eigen3.hpp:329-336, TripletContainer.hpp:158-301)
+    template <typename FIELDTUPLEBINDER, typename FIELDBINDER>
+    void registerFields(const FIELDBINDER& fieldBinder) {
+        b200_detail::synchronise(fieldBinder);
+        typedef b200_detail::TupleIndices<FIELDTUPLEBINDER> TI;
+        b200_detail::check(isl_pattern_register(b200_detail::engine(), TI::test, TI::trial));
+    }
+
+    //! Finish the assembly (Eigen3.hpp:142-153): waits for the device
+    void finishAssembly(const bool = true) {
+        int64_t n = 0, nnz = 0;
+        b200_detail::check(isl_finish(b200_detail::engine(), &n, &nnz));
+        nnz_ = static_cast<std::size_t>(nnz);
+    }
+
+    //! Norm of the rhs/solution vector; like the reference divided by the length (Eigen3.hpp:128-138)
+    double norm() const {
+        if (solved_) return this->norm(0, size_);
+        double v = 0.;
+        b200_detail::check(isl_rhs_norm(b200_detail::engine(), &v));
+        return v;
+    }
+    double norm(const std::size_t first, const std::size_t last) const {
+        const std::vector<double>& b = this->hostRhs_();
+        double s = 0.;
+        for (std::size_t i = first; i < last; i++) s += b[i] * b[i];
+        return std::sqrt(s) / static_cast<double>(last - first);
+    }
+
+    //! Direct access to an entry in the RHS/solution vector (Eigen3.hpp:293-296)
+    number getValue(const std::size_t index) const {
+        if (solved_) return x_[index];
+        double v = 0.;
+        b200_detail::check(isl_rhs_value(b200_detail::engine(), static_cast<int64_t>(index), &v));
+        return v;
+    }
+
+    //! @name Hand-off of the finished system (canonical CSR: rows and columns ascending, explicit zeros kept)
+    //@{
+    void getCSR(std::vector<int64_t>& rowptr, std::vector<int32_t>& col, std::vector<double>& val,
+                std::vector<double>& rhs) const {
+        int64_t n = 0, nnz = 0;
+        b200_detail::check(isl_finish(b200_detail::engine(), &n, &nnz));
+        rowptr.assign(static_cast<std::size_t>(n) + 1, 0);
+        col.assign(static_cast<std::size_t>(nnz), 0);
+        val.assign(static_cast<std::size_t>(nnz), 0.);
+        rhs.assign(static_cast<std::size_t>(n), 0.);
+        b200_detail::check(isl_get_csr(b200_detail::engine(), &rowptr[0], nnz ? &col[0] : NULL, nnz ? &val[0] : NULL,
+                                       n ? &rhs[0] : NULL));
+    }
+    //! device pointers for a device-resident solver (valid until the next solver is constructed)
+    void getDeviceCSR(int64_t** rowptr, int32_t** col, double** val, double** rhs) const {
+        b200_detail::check(isl_get_device_csr(b200_detail::engine(), rowptr, col, val, rhs));
+    }
+    //@}
+
+    //! @name Linear solves: outside the assembly path, delegated to the hook (host) -- Eigen3.hpp:157-289
+    //@{
+    void choleskySolve() { this->solve_("cholesky"); }
+    void luSolve() { this->solve_("lu"); }
+    void superLUSolve() { this->solve_("superlu"); }
+    int cgSolve() { return this->solve_("cg"); }
+    int biCGStabSolve() { return this->solve_("bicgstab"); }
+    //@}
+
+    //! @name Debug routines for printing (Eigen3.hpp:298-327); the matrix is written column by column like Eigen's
+    //@{
+    void systemInfo(std::ostream& out) const {
+        int64_t n = 0, nnz = 0;
+        b200_detail::check(isl_finish(b200_detail::engine(), &n, &nnz));
+        out << n << " X " << n << " sparse matrix with " << nnz << " non-zero entries \n";
+    }
+    void debugLHS(std::ostream& out) const {
+        std::vector<int64_t> rowptr;
+        std::vector<int32_t> col;
+        std::vector<double> val, rhs;
+        this->getCSR(rowptr, col, val, rhs);
+        const std::size_t n = rhs.size();
+        std::vector<std::size_t> start(n + 1, 0);
+        for (std::size_t k = 0; k < col.size(); k++) start[col[k] + 1]++;
+        for (std::size_t j = 0; j < n; j++) start[j + 1] += start[j];
+        std::vector<int64_t> r(col.size());
+        std::vector<double> v(col.size());
+        std::vector<std::size_t> pos(start.begin(), start.end() - 1);
+        for (std::size_t i = 0; i < n; i++)
+            for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) {
+                const std::size_t q = pos[col[k]]++;
+                r[q] = static_cast<int64_t>(i);
+                v[q] = val[k];
+            }
+        for (std::size_t j = 0; j < n; j++)
+            for (std::size_t q = start[j]; q < start[j + 1]; q++) out << r[q] << " " << j << " " << v[q] << "\n";
+    }
+    void debugRHS(std::ostream& out) const {
+        const std::vector<double>& b = this->hostRhs_();
+        for (std::size_t i = 0; i < b.size(); i++) out << i << " " << b[i] << "\n";
+    }
+    //@}
+
+private:
+    const std::vector<double>& hostRhs_() const {
+        if (!solved_) {
+            x_.assign(size_, 0.);
+            if (size_) b200_detail::check(isl_get_csr(b200_detail::engine(), NULL, NULL, NULL, &x_[0]));
+        }
+        return x_;
+    }
+    int solve_(const char* method) {
+        VERIFY_MSG(solveHook() != NULL, std::string("B200 solver: linear solve '") + method +
+                                            "' requested but no solve hook installed (the engine covers the assembly path)");
+        std::vector<int64_t> rowptr;
+        std::vector<int32_t> col;
+        std::vector<double> val;
+        this->getCSR(rowptr, col, val, x_);
+        const int it = solveHook()(method, size_, rowptr, col, val, x_);
+        solved_ = true;
+        return it;
+    }
+
+    std::size_t size_, nnz_ = 0;
+    mutable std::vector<double> x_;  //!< host copy of rhs / the solution after a solve
+    bool solved_;
+};
+
+}  // namespace solver
+
+//------------------------------------------------------------------------------------------------------------------
+namespace asmb {
+
+namespace b200_detail {
+template <typename FIELDTUPLEBINDER, typename FIELDBINDER>
+typename FIELDTUPLEBINDER::Tuple probeTuple(const FIELDBINDER& fb, bool last) {
+    typename FIELDBINDER::FieldIterator it = fb.elementsBegin();
+    if (last) std::advance(it, std::distance(fb.elementsBegin(), fb.elementsEnd()) - 1);
+    return FIELDTUPLEBINDER::makeTuple(*it);
+}
+}  // namespace b200_detail
+
+//! base/asmb/StiffnessMatrix.hpp:49-87 for SOLVER = base::solver::B200
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
+void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder,
+                                const KERNEL& kernelObj, const bool incremental = true) {
+    namespace D = base::solver::b200_detail;
+    if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
+    D::synchronise(fieldBinder);
+    double params[4] = {0., 0., 0., 0.};
+    const int id = base::solver::B200KernelTraits<KERNEL>::describe(
+        kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
+        b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
+    typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
+    D::check(isl_assemble_matrix(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
+                                 incremental ? 1 : 0));
+}
+
+//! base/asmb/ForceIntegrator.hpp:37-71 for SOLVER = base::solver::B200 (forces enter the rhs with factor -1)
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
+void computeResidualForces(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder,
+                           const KERNEL& kernelObj) {
+    namespace D = base::solver::b200_detail;
+    if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
+    D::synchronise(fieldBinder);
+    double params[4] = {0., 0., 0., 0.};
+    const int id = base::solver::B200KernelTraits<KERNEL>::describe(
+        kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
+        b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
+    typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
+    D::check(isl_assemble_residual(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
+                                   -1.0));
+}
+
+//! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200; the engine integrates constant body forces
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
+void bodyForceComputation(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder, const FUN& forceFun) {
+    namespace D = base::solver::b200_detail;
+    typedef typename FIELDTUPLEBINDER::Tuple Tuple;
+    typedef typename Tuple::GeomElement GeomElement;
+    typedef typename Tuple::TestElement TestElement;
+    if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
+    D::synchronise(fieldBinder);
+    const unsigned ds = TestElement::DegreeOfFreedom::size;
+    double f[3] = {0., 0., 0.};
+    // sample the force function at the centroids of the first, middle and last element: it has to be constant
+    const std::size_t n = static_cast<std::size_t>(std::distance(fieldBinder.elementsBegin(), fieldBinder.elementsEnd()));
+    const std::size_t probes[3] = {0, n / 2, n - 1};
+    for (int k = 0; k < 3; k++) {
+        typename FIELDBINDER::FieldIterator it = fieldBinder.elementsBegin();
+        std::advance(it, probes[k]);
+        const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*it).geomElementPtr();
+        const typename FUN::result_type v =
+            forceFun(base::Geometry<GeomElement>()(gep, base::ShapeCentroid<GeomElement::shape>::apply()));
+        for (unsigned d = 0; d < ds; d++) {
+            if (k == 0) f[d] = v[d];
+            else VERIFY_MSG(v[d] == f[d], "B200 engine: only constant body forces are supported");
+        }
+    }
+    typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
+    D::check(isl_assemble_bodyforce(D::engine(), f, D::QuadratureDegree<QUADRATURE>::value, TI::test));
+}
+
+}  // namespace asmb
+}  // namespace base
+
+#endif

@@ -1,0 +1,139 @@
+// Test infrastructure — NOT product code.
+//
+// A CPU stand-in for the subset of the C ABI (include/insilico_b200.h) that include/insilico_b200_reference.hpp
+// calls, implemented on the CPU oracle (oracle/insilico_oracle.cpp).  It exists so that the binding header can be
+// exercised in the `-m "not gpu"` suite: the unmodified reference applications, compiled against the binding and
+// linked with THIS file instead of libinsilico_b200.so, must print what they print with base::solver::Eigen3.
+// On the GPU the same applications link the real library.  Never shipped, never linked by the product.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <insilico_b200.h>
+
+extern "C" {
+void* orc_problem_new();
+void orc_problem_free(void*);
+void orc_set_mesh(void*, int, int, int, int64_t, const double*, int64_t, const int64_t*);
+void orc_set_field(void*, int, int, int, int64_t, const int64_t*, const int64_t*, const uint8_t*, const double*, const double*);
+void* orc_system_new(int64_t);
+void orc_system_free(void*);
+void orc_register_fields(void*, void*, int, int);
+int orc_stiffness(void*, void*, int, const double*, int, int, int, int, int);
+int orc_residual(void*, void*, int, const double*, int, int, int);
+int orc_bodyforce(void*, void*, const double*, int, int);
+void orc_finish(void*);
+int64_t orc_nnz(void*);
+void orc_get_csr(void*, int64_t*, int32_t*, double*, double*);
+const char* orc_system_error(void*);
+double orc_rhs_norm(void*);
+}
+
+struct isl_engine {
+    void* prob = nullptr;
+    void* sys = nullptr;
+    int64_t n = 0;
+    bool finished = false;
+    int shape = 0, npe = 0;
+    int64_t nElems = 0;
+    struct F { int deg = 0, ds = 0; int64_t nObj = 0; std::vector<int64_t> elemDof, eqn; std::vector<uint8_t> status;
+               std::vector<double> presc, values; } f[5];
+    std::vector<std::vector<double> > pendingRows;
+};
+static std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+
+extern "C" {
+const char* isl_last_error(void) { return g_err.c_str(); }
+int isl_engine_create(int, isl_handle* out) { *out = new isl_engine(); (*out)->prob = orc_problem_new(); return 0; }
+int isl_engine_destroy(isl_handle h) { delete h; return 0; }
+int isl_mesh_set(isl_handle h, int shape, int gdeg, int dim, int64_t nn, const double* x, int64_t ne, const int32_t* conn) {
+    const int npeTab[6] = {1, 0, 0, 0, 0, 0};
+    (void)npeTab;
+    // nodes per element from the sizes handed in by the caller: conn has ne*npe entries; geometry degree 1 only here
+    const int npe = (shape == ISL_TRI ? 3 : shape == ISL_QUAD ? 4 : shape == ISL_TET ? 4 : shape == ISL_HEX ? 8 : 2);
+    if (gdeg != 1) return fail("mock ABI: geometry degree 1 only");
+    std::vector<int64_t> c(conn, conn + ne * npe);
+    orc_set_mesh(h->prob, shape, gdeg, dim, nn, x, ne, c.data());
+    h->shape = shape; h->npe = npe; h->nElems = ne;
+    return 0;
+}
+int isl_mesh_update_coords(isl_handle, const double*) { return fail("mock ABI: isl_mesh_update_coords not provided"); }
+static void push_field(isl_handle h, int i) {
+    isl_engine::F& f = h->f[i];
+    orc_set_field(h->prob, i, f.deg, f.ds, f.nObj, f.elemDof.data(), f.eqn.data(), f.status.data(), f.presc.data(),
+                  f.values.data());
+}
+int isl_field_set(isl_handle h, int i, int deg, int ds, int64_t nObj, const int32_t* ed, const int64_t* eqn,
+                  const uint8_t* status, const double* presc, const double* values) {
+    isl_engine::F& f = h->f[i];
+    f.deg = deg; f.ds = ds; f.nObj = nObj;
+    const int64_t ndpe = [&] {  // DoF objects per element of a Lagrange element (base/fe/LagrangeElement.hpp:96-111)
+        const int d = deg;
+        switch (h->shape) {
+            case ISL_TRI: return (int64_t)(d + 1) * (d + 2) / 2;
+            case ISL_QUAD: return (int64_t)(d + 1) * (d + 1);
+            case ISL_TET: return (int64_t)(d + 1) * (d + 2) * (d + 3) / 6;
+            default: return (int64_t)(d + 1) * (d + 1) * (d + 1);
+        }
+    }();
+    f.elemDof.assign(ed, ed + h->nElems * ndpe);
+    const size_t n = (size_t)nObj * ds;
+    f.eqn.assign(eqn, eqn + n);
+    for (size_t k = 0; k < n; k++) if (status[k] != ISL_ACTIVE) f.eqn[k] = -1;
+    f.status.assign(status, status + n);
+    f.presc.assign(presc, presc + n);
+    f.values.assign(values, values + n);
+    push_field(h, i);
+    return 0;
+}
+int isl_field_update(isl_handle h, int i, const double* presc, const double* values) {
+    isl_engine::F& f = h->f[i];
+    const size_t n = (size_t)f.nObj * f.ds;
+    if (presc) f.presc.assign(presc, presc + n);
+    if (values) f.values.assign(values, values + n);
+    push_field(h, i);
+    return 0;
+}
+int isl_system_create(isl_handle h, int64_t n) {
+    if (h->sys) orc_system_free(h->sys);
+    h->sys = orc_system_new(n);
+    h->n = n; h->finished = false;
+    return 0;
+}
+int isl_pattern_register(isl_handle h, int t, int c) { orc_register_fields(h->sys, h->prob, t, c); return 0; }
+int isl_assemble_matrix(isl_handle h, int kid, const double* p, int q, int t, int c, int incr) {
+    return orc_stiffness(h->sys, h->prob, kid, p, q, t, c, incr, 1) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_residual(isl_handle h, int kid, const double* p, int q, int t, int c, double factor) {
+    if (factor != -1.0) return fail("mock ABI: residual factor must be -1");
+    return orc_residual(h->sys, h->prob, kid, p, q, t, c) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_bodyforce(isl_handle h, const double* f, int q, int t) {
+    return orc_bodyforce(h->sys, h->prob, f, q, t) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_insert_lhs(isl_handle, const double*, const int64_t*, int, const int64_t*, int) {
+    return fail("mock ABI: isl_insert_lhs not provided");
+}
+int isl_insert_rhs(isl_handle, const double*, const int64_t*, int) { return fail("mock ABI: isl_insert_rhs not provided"); }
+int isl_finish(isl_handle h, int64_t* n, int64_t* nnz) {
+    if (!h->finished) { orc_finish(h->sys); h->finished = true; }
+    if (n) *n = h->n;
+    if (nnz) *nnz = orc_nnz(h->sys);
+    return 0;
+}
+int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs) {
+    if (!h->finished) { orc_finish(h->sys); h->finished = true; }
+    orc_get_csr(h->sys, rowptr, col, val, rhs);
+    return 0;
+}
+int isl_get_device_csr(isl_handle, int64_t**, int32_t**, double**, double**) { return fail("mock ABI: no device"); }
+int isl_rhs_value(isl_handle h, int64_t i, double* v) {
+    std::vector<double> b((size_t)h->n);
+    orc_get_csr(h->sys, nullptr, nullptr, nullptr, b.data());
+    *v = b[(size_t)i];
+    return 0;
+}
+int isl_rhs_norm(isl_handle h, double* v) { *v = orc_rhs_norm(h->sys); return 0; }
+}

@@ -135,3 +135,45 @@ def test_reference_app_compressible_newton_history_golden(tmp_path):
                 assert x == y, (a, b)
                 compared += 1
     assert compared >= 30
+
+
+# ---- the reference's applications, unmodified, on the B200 binding --------------------------------------------------
+# oracle/_ref/apps_b200/<app>       = application + include/insilico_b200_reference.hpp + libinsilico_b200.so (GPU)
+# oracle/_ref/apps_b200/<app>_mock  = same object file + the oracle-backed mock of the C ABI (CPU check of the binding)
+# expected output = what the application prints with the reference's own base::solver::Eigen3
+# (tests/golden/refrun_apps, tools/make_ref_app_goldens.py)
+from tests import ref_apps_cases as RA  # noqa: E402
+
+APPS_B200 = os.path.join(ROOT, "oracle", "_ref", "apps_b200")
+
+
+def _run_binding_app(name, suffix, tmp_path):
+    exe, args = RA.prepare(name, str(tmp_path))
+    path = os.path.join(APPS_B200, exe + suffix)
+    p = subprocess.run([path] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    expected = open(os.path.join(ROOT, "tests", "golden", "refrun_apps", name + ".out")).read()
+    assert RA.same_output(p.stdout, expected), "\n" + p.stdout + "\n--- expected ---\n" + expected
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(RA.CASES))
+def test_unmodified_reference_app_on_binding_with_mock_abi(tmp_path, name):
+    _run_binding_app(name, "_mock", tmp_path)
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_binding_app_without_gpu_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe, args = RA.prepare("dirichlet_tet6", str(tmp_path))
+    p = subprocess.run([os.path.join(APPS_B200, exe)] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(RA.CASES))
+def test_unmodified_reference_app_on_b200_engine(tmp_path, name):
+    _run_binding_app(name, "", tmp_path)
