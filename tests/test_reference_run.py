@@ -177,3 +177,39 @@ def test_binding_app_without_gpu_fails_loudly(tmp_path):
 @pytest.mark.parametrize("name", sorted(RA.CASES))
 def test_unmodified_reference_app_on_b200_engine(tmp_path, name):
     _run_binding_app(name, "", tmp_path)
+
+
+# ---- every fixture case through the binding: reference API -> flattening -> C ABI -----------------------------------
+def _driver_on_binding(path, exe, tmp_path):
+    from tools import make_ref_goldens as G
+    g = np.load(path, allow_pickle=False)
+    spec = [c for c in G.CASES if c[0] == os.path.basename(path)[:-4]][0]
+    case = flows.build_case(spec[1], spec[3], spec[4], spec[5])
+    old = G.DRIVER
+    G.DRIVER = os.path.join(APPS_B200, exe)
+    try:
+        r = G.run_reference(case, spec[2], spec[6], str(tmp_path))
+    finally:
+        G.DRIVER = old
+    for i in range(len(case.fields)):
+        assert np.array_equal(r["elem_dof%d" % i], g["elem_dof%d" % i])
+        assert np.array_equal(r["status%d" % i], g["status%d" % i])
+    res = flows.compare((g["rowptr"], g["col"], g["val"], g["rhs"]), (r["rowptr"], r["col"], r["val"], r["rhs"]))
+    assert res["pattern_equal"], "CSR pattern differs from the reference's finished matrix"
+    # material constants are recovered by probing (1e-15), hence 1e-13 instead of bit-level agreement
+    assert res["val_diff"] <= 1e-12 and res["rhs_diff"] <= 1e-12, res
+    return res
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_reference_api_on_binding_with_mock_abi(tmp_path, path):
+    res = _driver_on_binding(path, "ref_driver_mock", tmp_path)
+    assert res["val_diff"] <= 1e-13 and res["rhs_diff"] <= 1e-13, res
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_reference_api_on_b200_engine(tmp_path, path):
+    _driver_on_binding(path, "ref_driver", tmp_path)
