@@ -1441,6 +1441,19 @@ int orc_bodyforce(void* s, void* h, const double* f, int quadDeg, int test) {
     for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, f, test, test, 1.0, true, e);
     return sys.error.empty() ? 0 : -1;
 }
+// solver::Eigen3::insertToLHS / insertToRHS (Eigen3.hpp:81-124) for contributions computed by the caller
+// (e.g. the reference's surface terms); mat is row-major [nRows*nCols]
+int orc_insert_lhs(void* s, const double* mat, const int64_t* rows, int nRows, const int64_t* cols, int nCols) {
+    System& sys = *(System*)s;
+    for (int i = 0; i < nRows; i++)
+        for (int j = 0; j < nCols; j++) sys.insert((int)rows[i], (int)cols[j], mat[(size_t)i * nCols + j]);
+    return sys.error.empty() ? 0 : -1;
+}
+int orc_insert_rhs(void* s, const double* vec, const int64_t* rows, int nRows) {
+    System& sys = *(System*)s;
+    for (int i = 0; i < nRows; i++) sys.b[(size_t)rows[i]] += vec[i];
+    return 0;
+}
 void orc_finish(void* s) { ((System*)s)->finishAssembly(); }
 int64_t orc_nnz(void* s) { return (int64_t)((System*)s)->col.size(); }
 void orc_get_csr(void* s, int64_t* rowptr, int32_t* col, double* val, double* rhs) {

@@ -23,6 +23,8 @@ void orc_register_fields(void*, void*, int, int);
 int orc_stiffness(void*, void*, int, const double*, int, int, int, int, int);
 int orc_residual(void*, void*, int, const double*, int, int, int);
 int orc_bodyforce(void*, void*, const double*, int, int);
+int orc_insert_lhs(void*, const double*, const int64_t*, int, const int64_t*, int);
+int orc_insert_rhs(void*, const double*, const int64_t*, int);
 void orc_finish(void*);
 int64_t orc_nnz(void*);
 void orc_get_csr(void*, int64_t*, int32_t*, double*, double*);
@@ -49,9 +51,7 @@ const char* isl_last_error(void) { return g_err.c_str(); }
 int isl_engine_create(int, isl_handle* out) { *out = new isl_engine(); (*out)->prob = orc_problem_new(); return 0; }
 int isl_engine_destroy(isl_handle h) { delete h; return 0; }
 int isl_mesh_set(isl_handle h, int shape, int gdeg, int dim, int64_t nn, const double* x, int64_t ne, const int32_t* conn) {
-    const int npeTab[6] = {1, 0, 0, 0, 0, 0};
-    (void)npeTab;
-    // nodes per element from the sizes handed in by the caller: conn has ne*npe entries; geometry degree 1 only here
+    // geometry degree 1 only here
     const int npe = (shape == ISL_TRI ? 3 : shape == ISL_QUAD ? 4 : shape == ISL_TET ? 4 : shape == ISL_HEX ? 8 : 2);
     if (gdeg != 1) return fail("mock ABI: geometry degree 1 only");
     std::vector<int64_t> c(conn, conn + ne * npe);
@@ -113,10 +113,10 @@ int isl_assemble_residual(isl_handle h, int kid, const double* p, int q, int t, 
 int isl_assemble_bodyforce(isl_handle h, const double* f, int q, int t) {
     return orc_bodyforce(h->sys, h->prob, f, q, t) ? fail(orc_system_error(h->sys)) : 0;
 }
-int isl_insert_lhs(isl_handle, const double*, const int64_t*, int, const int64_t*, int) {
-    return fail("mock ABI: isl_insert_lhs not provided");
+int isl_insert_lhs(isl_handle h, const double* m, const int64_t* r, int nr, const int64_t* c, int nc) {
+    return orc_insert_lhs(h->sys, m, r, nr, c, nc) ? fail(orc_system_error(h->sys)) : 0;
 }
-int isl_insert_rhs(isl_handle, const double*, const int64_t*, int) { return fail("mock ABI: isl_insert_rhs not provided"); }
+int isl_insert_rhs(isl_handle h, const double* v, const int64_t* r, int nr) { return orc_insert_rhs(h->sys, v, r, nr); }
 int isl_finish(isl_handle h, int64_t* n, int64_t* nnz) {
     if (!h->finished) { orc_finish(h->sys); h->finished = true; }
     if (n) *n = h->n;
