@@ -370,7 +370,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         line["cpu_baseline"], _ = reference_baseline(args.cpu_sample, 2, 1, cores)
     print(json.dumps(line))
     if world > 1:

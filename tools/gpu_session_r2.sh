@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU call of round 2 (round 1 ended without GPU minutes for the last session):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session_r2.sh'
+# Everything lands in gpurun_out/r2/.  Steps are independent: a failing one does not stop the others.
+mkdir -p gpurun_out/r2
+O=gpurun_out/r2
+export PYTHONUNBUFFERED=1
+{
+echo "== 1. GPU test suite"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+echo "== 2. experimental row-gather kernels"; ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -k rowgather 2>&1 | tail -8
+echo "== 3. default bench"; timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_default.json 2> $O/bench_default.err; tail -c 1500 $O/bench_default.json
+echo "== 4. row-gather sweep (kernel only)"
+for ss in 0 1; do for nt in 256 320 192 128; do for pr in 192 256 320; do for st in 1 2 4; do
+  echo -n "ROWS ss=$ss threads=$nt patch_rows=$pr stretch=$st : "
+  ISL_Q1_ROWS=1 ISL_ROWS_SS=$ss ISL_ROWS_THREADS=$nt ISL_PATCH_ROWS=$pr ISL_PATCH_STRETCH=$st timeout 300 \
+    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('%.3f ms/step  frac %.3f  perturbed %.3f ms' % (d['ms_per_step'], d['roofline']['frac'], d['config'].get('ms_per_step_perturbed_mesh') or -1))
+"
+done; done; done; done
+echo "== 5. other configs (generic kernels)"; timeout 900 python tools/bench_configs.py 2>&1 | tail -12
+echo "== 6. launch list of the default bench"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_default.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launch.log 2>&1; tail -3 $O/ncu_launch.log
+} > $O/session.log 2>&1
+tail -60 $O/session.log

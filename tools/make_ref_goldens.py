@@ -88,7 +88,10 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
     job = os.path.join(workdir, "job.txt")
     with open(job, "w") as f:
         f.write("\n".join(lines) + "\n")
-    log = subprocess.run([DRIVER, job], check=True, capture_output=True, text=True).stdout
+    proc = subprocess.run([DRIVER, job], capture_output=True, text=True, timeout=1800)
+    if proc.returncode != 0:
+        raise RuntimeError("%s failed (exit %d):\n%s" % (DRIVER, proc.returncode, proc.stderr[-3000:]))
+    log = proc.stdout
     res = dict(log=log)
     if not dump:
         return res
