@@ -104,6 +104,14 @@ int isl_mesh_update_coords(isl_handle h, const double* coords);
  * value (dof::Constraint rhs, base/dof/Constraint.hpp) / current value                                      */
 int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_obj, const int32_t* elem_dof,
                   const int64_t* eqn, const uint8_t* status, const double* prescribed, const double* values);
+/* general linear constraints (base/dof/Constraint.hpp:57-140, collected per element by asmb::collectFromDoFs,
+ * base/asmb/collectFromDoFs.hpp:112-131, applied by asmb::assembleMatrix / assembleForces,
+ * base/asmb/assembleMatrix.hpp:212-338, assembleForces.hpp:58-139): DoF component con_dof[k] = obj*dof_size+comp
+ * (status CONSTRAINED) is  u = prescribed + sum_j weight[j] * u_master[j],  j in [con_ptr[k], con_ptr[k+1]), with
+ * master_eqn[j] the equation number of the (ACTIVE) master.  HOST arrays.  Call after isl_field_set (which drops
+ * earlier constraints); n_con = 0 removes them.  Fields with such slaves use the generic kernels.              */
+int isl_field_set_constraints(isl_handle h, int field, int64_t n_con, const int64_t* con_dof, const int64_t* con_ptr,
+                              const int64_t* master_eqn, const double* weight);
 /* new Newton state / new Dirichlet values, numbering unchanged (either pointer may be NULL) */
 int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values);
 

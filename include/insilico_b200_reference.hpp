@@ -14,8 +14,9 @@
 //   * flattening                    the reference's heap objects (Node, Element, DegreeOfFreedom; reached through
 //                                   FieldBinder::elementsBegin()/End(), base/asmb/FieldBinder.hpp:150-181) become the
 //                                   flat arrays of isl_mesh_set / isl_field_set: topology once per binder, DoF state
-//                                   (status, equation numbers, prescribed and current values, node coordinates)
-//                                   re-read at every assembly call and uploaded only when it changed.
+//                                   (status, equation numbers, prescribed and current values, linear constraints
+//                                   with their master DoFs and weights, node coordinates) re-read at every
+//                                   assembly call and uploaded only when it changed.
 //   * kernel objects                recognised at compile time (B200KernelTraits); a kernel type the engine does not
 //                                   implement is a compile error -- there is no CPU fallback.  The reference keeps
 //                                   material constants private, so they are recovered by probing the kernel object
@@ -82,6 +83,9 @@ struct FieldState {
     std::vector<int64_t> eqn;
     std::vector<uint8_t> status;
     std::vector<double> prescribed, values;
+    // linear constraints with master DoFs (base/dof/Constraint.hpp): flat form of isl_field_set_constraints
+    std::vector<int64_t> conDof, conPtr, masterEqn;
+    std::vector<double> weight;
 };
 
 struct BinderState {
@@ -142,6 +146,9 @@ struct FlattenField<N, FIELDBINDER, false> {
         std::vector<int64_t> eqn(n, -1);
         std::vector<uint8_t> status(n, ISL_INACTIVE);
         std::vector<double> prescribed(n, 0.), values(n, 0.);
+        std::vector<int64_t> conDof, conPtr(1, 0), masterEqn;
+        std::vector<double> weight;
+        std::vector<uint8_t> seen(n, 0);
         double pv[DoF::size];
         for (; it != end; ++it) {
             const Element* ep = (*it).template get<N>();
@@ -156,11 +163,20 @@ struct FlattenField<N, FIELDBINDER, false> {
                     } else if (doF->isConstrained(c)) {
                         status[o + c] = ISL_CONSTRAINED;
                         prescribed[o + c] = pv[c];
-                        std::vector<std::pair<base::number, std::size_t> > masters;
-                        const_cast<DoF*>(doF)->getConstraint(c)->getWeightedDoFIDs(masters);
-                        VERIFY_MSG(masters.empty(), "B200 engine: linear constraints with master DoFs are not supported "
-                                                    "(only prescribed values, base/dof/Constraint.hpp)");
+                        if (!seen[o + c]) {  // masters of a slave DoF (base/dof/Constraint.hpp:118-136), once per DoF
+                            std::vector<std::pair<base::number, std::size_t> > masters;
+                            const_cast<DoF*>(doF)->getConstraint(c)->getWeightedDoFIDs(masters);
+                            if (!masters.empty()) {
+                                conDof.push_back(static_cast<int64_t>(o + c));
+                                for (std::size_t m = 0; m < masters.size(); m++) {
+                                    weight.push_back(masters[m].first);
+                                    masterEqn.push_back(static_cast<int64_t>(masters[m].second));
+                                }
+                                conPtr.push_back(static_cast<int64_t>(masterEqn.size()));
+                            }
+                        }
                     }
+                    seen[o + c] = 1;
                     values[o + c] = doF->getValue(c);
                 }
             }
@@ -168,9 +184,21 @@ struct FlattenField<N, FIELDBINDER, false> {
         const bool numberingChanged = assignIfChanged(f.eqn, eqn) | assignIfChanged(f.status, status);
         const bool prescChanged = assignIfChanged(f.prescribed, prescribed);
         const bool valuesChanged = assignIfChanged(f.values, values);
+        const bool constraintsChanged = assignIfChanged(f.conDof, conDof) | assignIfChanged(f.conPtr, conPtr) |
+                                        assignIfChanged(f.masterEqn, masterEqn) | assignIfChanged(f.weight, weight);
         if (redefine || numberingChanged) {
             check(isl_field_set(engine(), N - 1, f.feDeg, f.dofSize, f.nObj, &f.elemDof[0], &f.eqn[0], &f.status[0],
                                 &f.prescribed[0], &f.values[0]));
+            if (!f.conDof.empty())
+                check(isl_field_set_constraints(engine(), N - 1, static_cast<int64_t>(f.conDof.size()), &f.conDof[0],
+                                                &f.conPtr[0], &f.masterEqn[0], &f.weight[0]));
+        } else if (constraintsChanged) {
+            check(isl_field_set_constraints(engine(), N - 1, static_cast<int64_t>(f.conDof.size()),
+                                            f.conDof.empty() ? NULL : &f.conDof[0], &f.conPtr[0],
+                                            f.masterEqn.empty() ? NULL : &f.masterEqn[0], f.weight.empty() ? NULL : &f.weight[0]));
+            if (prescChanged || valuesChanged)
+                check(isl_field_update(engine(), N - 1, prescChanged ? &f.prescribed[0] : NULL,
+                                       valuesChanged ? &f.values[0] : NULL));
         } else if (prescChanged || valuesChanged) {
             check(isl_field_update(engine(), N - 1, prescChanged ? &f.prescribed[0] : NULL,
                                    valuesChanged ? &f.values[0] : NULL));

@@ -43,6 +43,7 @@
 #include "../../include/insilico_b200.h"
 #include "isl_dof.hpp"
 #include "isl_tables.hpp"
+#include "isl_constraints.hpp"
 
 namespace {
 
@@ -106,6 +107,11 @@ struct AsmParams {
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
     int body; double f[3];
+    // linear constraints with master DoFs (nullptr when the field has none): per DoF component k the masters
+    // [cptr[k], cptr[k+1]) as equation numbers cm[] with weights cw[]; CSR pattern for the entries they reach
+    const int32_t* cptr_t; const int32_t* cm_t; const double* cw_t;
+    const int32_t* cptr_c; const int32_t* cm_c; const double* cw_c;
+    const int64_t* rowptr; const int32_t* col;
 };
 
 __device__ __forceinline__ int voigt_idx(int i, int j) {
@@ -267,16 +273,34 @@ __device__ void deformation_gradient(const AsmParams& p, const Stage<DIM>& s, in
     for (int i = 0; i < p.dsc; i++) for (int J = 0; J < DIM; J++) F[i][J] += GradU[J][i];
 }
 
+__device__ __forceinline__ int64_t find_in_row(const int64_t* rowptr, const int32_t* col, int32_t r, int32_t c) {
+    return isl_find_in_row(rowptr, col, r, c);
+}
+struct DeviceAdd {
+    __device__ static void add(double* target, double value) { atomicAdd(target, value); }
+};
+
+// entry (kr, k) of an element whose row and/or column DoF is not ACTIVE while the field has slaves of master DoFs:
+// isl_constraints.hpp (positions are looked up in the CSR row; the slot map only holds ACTIVE x ACTIVE); rare path
+__device__ __noinline__ void scatter_constrained(const AsmParams& p, size_t kr, int32_t r, size_t k, double v) {
+    const bool c_con = (p.st_c[k] == ISL_CONSTRAINED);
+    const double g = c_con ? (p.incremental ? p.presc_c[k] - p.val_c[k] : p.presc_c[k]) : 0.;
+    const IslMasters mt{p.cptr_t, p.cm_t, p.cw_t}, mc{p.cptr_c, p.cm_c, p.cw_c};
+    isl_scatter_constrained<DeviceAdd>(mt, mc, p.rowptr, p.col, p.val, p.rhs, kr, r, k, p.eqn_c[k], c_con, g, v);
+}
+
 // scatter one local matrix entry: ACTIVE x ACTIVE -> CSR value,
-// ACTIVE row x CONSTRAINED column -> rhs -= g * K
+// ACTIVE row x CONSTRAINED column -> rhs -= g * K; slaves of master DoFs -> scatter_constrained
 __device__ __forceinline__ void scatter_entry(const AsmParams& p, int64_t e, int i, int j, int nr, int ncl, double v) {
     const int32_t sl = p.slot[((size_t)e * nr + i) * ncl + j];
     if (sl >= 0) { atomicAdd(p.val + sl, v); return; }
     const int M = i / p.dst, ci = i % p.dst;
-    const int32_t r = p.eqn_t[(size_t)p.ed_t[e * p.nt + M] * p.dst + ci];
-    if (r < 0) return;
+    const size_t kr = (size_t)p.ed_t[e * p.nt + M] * p.dst + ci;
+    const int32_t r = p.eqn_t[kr];
     const int N = j / p.dsc, cj = j % p.dsc;
     const size_t k = (size_t)p.ed_c[e * p.nc + N] * p.dsc + cj;
+    if (p.cptr_t != nullptr || p.cptr_c != nullptr) { scatter_constrained(p, kr, r, k, v); return; }
+    if (r < 0) return;
     if (p.st_c[k] == ISL_CONSTRAINED) {
         const double g = p.incremental ? p.presc_c[k] - p.val_c[k] : p.presc_c[k];
         atomicAdd(p.rhs + r, -(g * v));
@@ -448,8 +472,11 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
                     } break;
                 }
             }
-            const int32_t r = p.eqn_t[(size_t)p.ed_t[e * p.nt + M] * p.dst + ci];
+            const size_t kr = (size_t)p.ed_t[e * p.nt + M] * p.dst + ci;
+            const int32_t r = p.eqn_t[kr];
             if (r >= 0) atomicAdd(p.rhs + r, p.factor * acc);
+            else if (p.cptr_t != nullptr)  // slave of master DoFs (asmb/assembleForces.hpp:118-131)
+                isl_scatter_force_to_masters<DeviceAdd>(IslMasters{p.cptr_t, p.cm_t, p.cw_t}, p.rhs, kr, p.factor * acc);
         }
         __syncthreads();
     }
@@ -595,11 +622,6 @@ __global__ void k_cols_from_keys(const uint64_t* keys, int64_t nnz, int32_t* col
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
         col[k] = (int32_t)(keys[k] & 0xffffffffu);
 }
-__device__ __forceinline__ int64_t find_in_row(const int64_t* rowptr, const int32_t* col, int32_t r, int32_t c) {
-    int64_t lo = rowptr[r], hi = rowptr[r + 1];
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (col[mid] < c) lo = mid + 1; else hi = mid; }
-    return (lo < rowptr[r + 1] && col[lo] == c) ? lo : -1;
-}
 __global__ void k_slotmap(const int32_t* er, const int32_t* ec, int64_t n_elems, int nr, int ncl, const int64_t* rowptr,
                           const int32_t* col, int32_t* slot) {
     const int64_t n = n_elems * nr * ncl;
@@ -657,9 +679,19 @@ struct FieldDev {
     int deg = 0, ds = 0, ndpe = 0; int64_t n_obj = 0;
     DevBuf<int32_t> elem_dof, eqn; DevBuf<uint8_t> status; DevBuf<double> presc, values;
     DevBuf<int32_t> elem_eqn;  // [n_elems][ndpe*ds]
+    // linear constraints with master DoFs (isl_field_set_constraints): dense pointer array [n_obj*ds+1], masters as
+    // equation numbers; host copies feed the extra pattern keys in build_pattern
+    bool has_masters = false;
+    DevBuf<int32_t> cptr, cmaster; DevBuf<double> cweight;
+    std::vector<int32_t> h_cptr, h_cmaster, h_elem_dof, h_eqn;
+    void reset_constraints() {
+        has_masters = false; cptr.release(); cmaster.release(); cweight.release();
+        h_cptr.clear(); h_cmaster.clear();
+    }
     void reset() {
         set = false; dof_is_node = false; deg = ds = ndpe = 0; n_obj = 0;
         elem_dof.release(); eqn.release(); status.release(); presc.release(); values.release(); elem_eqn.release();
+        reset_constraints(); h_elem_dof.clear(); h_eqn.clear();
     }
 };
 
@@ -766,9 +798,41 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
         ISL_REQUIRE(t.set && c.set, "pattern registration on a field that was not set");
         total += h->n_elems * (int64_t)(t.ndpe * t.ds) * (c.ndpe * c.ds);
     }
+    // pairs whose test or trial field has slaves of master DoFs reach further entries: effective rows x effective
+    // columns (ACTIVE ids ++ master ids) of every element holding such a slave (solver/TripletContainer.hpp:229-262);
+    // few, formed on the host
+    std::vector<uint64_t> extra;
+    for (auto& pr : pairs) {
+        FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
+        if (!t.has_masters && !c.has_masters) continue;
+        auto host_copy = [&](FieldDev& f) {
+            if (!f.h_elem_dof.empty()) return;
+            f.h_elem_dof.resize((size_t)h->n_elems * f.ndpe); f.h_eqn.resize((size_t)f.n_obj * f.ds);
+            ISL_CUDA(cudaMemcpyAsync(f.h_elem_dof.data(), f.elem_dof.p, f.h_elem_dof.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaMemcpyAsync(f.h_eqn.data(), f.eqn.p, f.h_eqn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+        };
+        host_copy(t); host_copy(c);
+        auto effective = [&](const FieldDev& f, int64_t e, std::vector<int32_t>& eff) {
+            return isl_effective_ids(f.h_elem_dof.data(), f.ndpe, f.ds, f.h_eqn.data(), f.has_masters ? f.h_cptr.data() : nullptr,
+                                     f.h_cmaster.data(), e, eff);
+        };
+        std::vector<int32_t> er, ec;
+        for (int64_t e = 0; e < h->n_elems; e++) {
+            const bool sr = effective(t, e, er), sc = effective(c, e, ec);
+            if (!sr && !sc) continue;
+            for (int32_t r : er) for (int32_t cc : ec) extra.push_back(((uint64_t)(uint32_t)r << 32) | (uint32_t)cc);
+        }
+    }
+    total += (int64_t)extra.size();
     DevBuf<uint64_t> keys, keys2;
     keys.alloc(total + 1);
     int64_t off = 0;
+    if (!extra.empty()) {
+        ISL_CUDA(cudaMemcpyAsync(keys.p, extra.data(), extra.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        off = (int64_t)extra.size();
+    }
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
         build_elem_eqn(h, t); build_elem_eqn(h, c);
@@ -887,6 +951,9 @@ void fill_common(isl_engine* h, AsmParams& p, int quad_deg, int t, int c) {
     p.ed_t = ft.elem_dof.p; p.ed_c = fc.elem_dof.p; p.eqn_t = ft.eqn.p; p.eqn_c = fc.eqn.p;
     p.st_c = fc.status.p; p.presc_c = fc.presc.p; p.val_c = fc.values.p;
     p.val = h->val.p; p.rhs = h->rhs.p;
+    p.cptr_t = ft.has_masters ? ft.cptr.p : nullptr; p.cm_t = ft.cmaster.p; p.cw_t = ft.cweight.p;
+    p.cptr_c = fc.has_masters ? fc.cptr.p : nullptr; p.cm_c = fc.cmaster.p; p.cw_c = fc.cweight.p;
+    p.rowptr = h->rowptr.p; p.col = h->col.p;
 }
 
 template <class K>
@@ -964,7 +1031,8 @@ void load_q1_tables(isl_engine* h) {
 
 bool qualifies_q1(const isl_engine* h, int t, int c) {
     const FieldDev& ft = h->fields[t];
-    return h->shape == ISL_HEX && h->geom_deg == 1 && t == c && ft.set && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node;
+    return h->shape == ISL_HEX && h->geom_deg == 1 && t == c && ft.set && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node &&
+           !ft.has_masters;  // slaves of master DoFs take the generic kernels
 }
 
 // build (or fetch) the patch decomposition of a scalar Q1-hex field; returns nullptr when the mesh does not fit
@@ -1495,6 +1563,44 @@ int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_o
         ISL_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
+int isl_field_set_constraints(isl_handle h, int field, int64_t n_con, const int64_t* con_dof, const int64_t* con_ptr,
+                              const int64_t* master_eqn, const double* weight) {
+    return guarded([&] {
+        flush_pending(h);
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
+        FieldDev& f = h->fields[field];
+        f.reset_constraints();
+        invalidate_pattern(h);
+        if (n_con <= 0) return;
+        const size_t n = (size_t)f.n_obj * f.ds;
+        // status and equation numbers on the host: slaves must be CONSTRAINED, masters must be equation numbers
+        std::vector<uint8_t> st(n);
+        ISL_CUDA(cudaMemcpyAsync(st.data(), f.status.p, n, cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        std::vector<int32_t> cnt(n + 1, 0);
+        for (int64_t k = 0; k < n_con; k++) {
+            ISL_REQUIRE(con_dof[k] >= 0 && (size_t)con_dof[k] < n, "constraint on a DoF component that does not exist");
+            ISL_REQUIRE(st[con_dof[k]] == ISL_CONSTRAINED, "a DoF component with master DoFs must have status CONSTRAINED");
+            ISL_REQUIRE(con_ptr[k + 1] >= con_ptr[k], "con_ptr must be non-decreasing");
+            ISL_REQUIRE(cnt[con_dof[k] + 1] == 0, "DoF component constrained twice");
+            cnt[con_dof[k] + 1] = (int32_t)(con_ptr[k + 1] - con_ptr[k]);
+        }
+        for (size_t k = 0; k < n; k++) cnt[k + 1] += cnt[k];
+        std::vector<int32_t> cm((size_t)cnt[n]);
+        std::vector<double> cw((size_t)cnt[n]);
+        for (int64_t k = 0; k < n_con; k++)
+            for (int64_t j = con_ptr[k]; j < con_ptr[k + 1]; j++) {
+                ISL_REQUIRE(master_eqn[j] >= 0 && master_eqn[j] < ((int64_t)1 << 31), "master DoFs must be ACTIVE (equation number >= 0)");
+                const size_t q = (size_t)cnt[con_dof[k]] + (size_t)(j - con_ptr[k]);
+                cm[q] = (int32_t)master_eqn[j]; cw[q] = weight[j];
+            }
+        f.has_masters = !cm.empty();
+        if (!f.has_masters) return;
+        upload_vec(h, f.cptr, cnt); upload_vec(h, f.cmaster, cm); upload_vec(h, f.cweight, cw);
+        f.h_cptr = cnt; f.h_cmaster = cm;
+    });
+}
 int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values) {
     return guarded([&] {
         flush_pending(h);
@@ -1599,7 +1705,7 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
         {
             const FieldDev& ft = h->fields[t];
             if (h->q1_mode == 1 && h->shape == ISL_HEX && h->geom_deg == 1 && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node &&
-                (quad_deg == 2 || quad_deg == 3) && h->pattern_pairs.count({t, t})) {
+                !ft.has_masters && (quad_deg == 2 || quad_deg == 3) && h->pattern_pairs.count({t, t})) {
                 load_q1_tables(h);
                 if (h->pending_q1.active && h->pending_q1.field == t) { flush_pending(h, 1, f[0]); return; }
                 flush_pending(h);

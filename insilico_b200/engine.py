@@ -33,7 +33,8 @@ EXPORTED = [
     "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_synchronize", "isl_engine_stream",
     "isl_kernel_launches", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
-    "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_update", "isl_system_create", "isl_pattern_register",
+    "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
+    "isl_system_create", "isl_pattern_register",
     "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_insert_lhs", "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_pack_entries",
     "isl_unpack_add_entries",
@@ -235,6 +236,14 @@ class Engine:
         status, prescribed, values = conv(status, np.uint8), conv(prescribed, np.float64), conv(values, np.float64)
         _chk(lib().isl_field_set(self.h, fid, fe_deg, dof_size, _i64(n_obj), _ptr(elem_dof), _ptr(eqn), _ptr(status),
                                  _ptr(prescribed), _ptr(values)))
+
+    def set_field_constraints(self, fid, con_dof, con_ptr, master_eqn, weight):
+        """linear constraints with master DoFs (base/dof/Constraint.hpp:57-140): component con_dof[k] = obj*ds+comp is
+        u = prescribed + sum_j weight[j] u(master_eqn[j]), j in [con_ptr[k], con_ptr[k+1]).  Host arrays."""
+        con_dof = np.ascontiguousarray(con_dof, dtype=np.int64); con_ptr = np.ascontiguousarray(con_ptr, dtype=np.int64)
+        master_eqn = np.ascontiguousarray(master_eqn, dtype=np.int64); weight = np.ascontiguousarray(weight, dtype=np.float64)
+        _chk(lib().isl_field_set_constraints(self.h, fid, _i64(len(con_dof)), _ptr(con_dof), _ptr(con_ptr),
+                                             _ptr(master_eqn), _ptr(weight)))
 
     def update_field(self, fid, prescribed=None, values=None):
         _chk(lib().isl_field_update(self.h, fid, _ptr(prescribed), _ptr(values)))

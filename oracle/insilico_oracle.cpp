@@ -575,6 +575,10 @@ struct Field {
     std::vector<uint8_t> status;    // [nObj*dofSize]
     std::vector<double> prescribed; // constraint rhs (valid where CONSTRAINED)
     std::vector<double> values;     // current values (history 0)
+    // linear constraints with master DoFs (base/dof/Constraint.hpp:57-140): component k = obj*dofSize+comp is
+    // u_k = prescribed_k + sum_j cweight[j] u(cmaster[j]), j in [cptr[k], cptr[k+1]); cptr empty = none
+    std::vector<int64_t> cptr, cmaster;  // cmaster = equation numbers of the (ACTIVE) masters
+    std::vector<double> cweight;
     SFun feFun;
 };
 
@@ -904,7 +908,11 @@ static void deformationGradient(const Tuple& t, const double* xi, double F[3][3]
 }
 
 // K is row-major [nRow][nCol] here (the reference MatrixXd is column-major; storage only)
-struct LocalMat { int nr, nc; std::vector<double> a; double& operator()(int r, int c) { return a[(size_t)r * nc + c]; } };
+struct LocalMat {
+    int nr, nc; std::vector<double> a;
+    double& operator()(int r, int c) { return a[(size_t)r * nc + c]; }
+    double operator()(int r, int c) const { return a[(size_t)r * nc + c]; }
+};
 
 // base/kernel/Laplace.hpp:100-151 (via heat/Laplace.hpp:113-126, fluid/VectorLaplace.hpp:40-59)
 static void laplaceTangent(const Tuple& t, double factor, const double* xi, double weight, LocalMat& K) {
@@ -1171,44 +1179,83 @@ struct System {
     }
 };
 
-// asmb/collectFromDoFs.hpp:82-136 (plain Dirichlet constraints: empty weighted-DoF lists)
+// (local DoF index, [(weight, master equation number)]) as built by asmb/collectFromDoFs.hpp:112-131
+typedef std::vector<std::pair<unsigned, std::vector<std::pair<double, size_t> > > > Constraints;
+
+// asmb/collectFromDoFs.hpp:82-136
 static bool collectFromDoFs(const Field& f, int64_t e, std::vector<uint8_t>& status, std::vector<size_t>& ids,
-                            std::vector<double>& values, bool incremental) {
+                            std::vector<double>& values, Constraints& constraints, bool incremental) {
     bool allInactive = true;
+    unsigned local = 0;
     for (int d = 0; d < f.ndpe; d++) {
         const int64_t obj = f.elemDof[e * f.ndpe + d];
-        for (int s = 0; s < f.dofSize; s++) {
+        for (int s = 0; s < f.dofSize; s++, local++) {
             const size_t k = obj * f.dofSize + s;
             status.push_back(f.status[k]);
             ids.push_back((size_t)f.eqn[k]);
-            // DegreeOfFreedom.hpp:248-264
-            if (f.status[k] == CONSTRAINED) values.push_back(incremental ? f.prescribed[k] - f.values[k] : f.prescribed[k]);
-            else values.push_back(std::numeric_limits<double>::max());
+            // DegreeOfFreedom.hpp:248-264: the constraint's rhs term (minus the current value if incremental)
+            if (f.status[k] == CONSTRAINED) {
+                values.push_back(incremental ? f.prescribed[k] - f.values[k] : f.prescribed[k]);
+                std::vector<std::pair<double, size_t> > weighted;  // Constraint::getWeightedDoFIDs, Constraint.hpp:118-136
+                if (!f.cptr.empty())
+                    for (int64_t j = f.cptr[k]; j < f.cptr[k + 1]; j++) weighted.push_back({f.cweight[j], (size_t)f.cmaster[j]});
+                constraints.push_back({local, weighted});
+            } else values.push_back(std::numeric_limits<double>::max());
             if (f.status[k] != INACTIVE) allInactive = false;
         }
     }
     return !allInactive;
 }
 
-// asmb/assembleMatrix.hpp:212-338 with detail_::assembleRow :56-130 (no master DoFs)
+// effective IDs = [ACTIVE ids in local order] ++ [master ids of the constraints in local order]
+// (asmb/assembleMatrix.hpp:247-277, asmb/assembleForces.hpp:78-92, solver/TripletContainer.hpp:229-256)
+static std::vector<size_t> effectiveIDs(const std::vector<uint8_t>& st, const std::vector<size_t>& ids, const Constraints& con) {
+    std::vector<size_t> eff;
+    for (size_t d = 0; d < ids.size(); d++) if (st[d] == ACTIVE) eff.push_back(ids[d]);
+    for (const auto& c : con) for (const auto& wm : c.second) eff.push_back(wm.second);
+    return eff;
+}
+
+// asmb/assembleMatrix.hpp:56-130 (detail_::assembleRow): one (possibly weighted) row of the element matrix
+static void assembleRow(const LocalMat& K, size_t r, unsigned rowCtr, double rowWeight, size_t numActiveCols,
+                        const std::vector<uint8_t>& cS, const std::vector<double>& cVal, const Constraints& cCon,
+                        LocalMat& sys, std::vector<double>& vec) {
+    unsigned activeCol = 0, colCstr = 0, extraCol = 0;
+    for (size_t c = 0; c < cS.size(); c++) {
+        if (cS[c] == ACTIVE) { sys((int)rowCtr, (int)activeCol) = rowWeight * K((int)r, (int)c); activeCol++; }
+        else if (cS[c] == CONSTRAINED) {
+            vec[rowCtr] -= cVal[c] * rowWeight * K((int)r, (int)c);
+            for (const auto& wm : cCon[colCstr].second) {
+                sys((int)rowCtr, (int)(numActiveCols + extraCol)) = rowWeight * wm.first * K((int)r, (int)c);
+                extraCol++;
+            }
+            colCstr++;
+        }
+    }
+}
+
+// asmb/assembleMatrix.hpp:212-338
 static void assembleMatrix(LocalMat& K, const std::vector<uint8_t>& rS, const std::vector<uint8_t>& cS,
                            const std::vector<size_t>& rID, const std::vector<size_t>& cID,
-                           const std::vector<double>& cVal, System& solver) {
-    std::vector<size_t> effR, effC;
-    for (size_t r = 0; r < rID.size(); r++) if (rS[r] == ACTIVE) effR.push_back(rID[r]);
-    for (size_t c = 0; c < cID.size(); c++) if (cS[c] == ACTIVE) effC.push_back(cID[c]);
+                           const std::vector<double>& cVal, const Constraints& rCon, const Constraints& cCon,
+                           System& solver) {
+    const size_t numActiveRows = (size_t)std::count(rS.begin(), rS.end(), (uint8_t)ACTIVE);
+    const size_t numActiveCols = (size_t)std::count(cS.begin(), cS.end(), (uint8_t)ACTIVE);
+    const std::vector<size_t> effR = effectiveIDs(rS, rID, rCon), effC = effectiveIDs(cS, cID, cCon);
     LocalMat sys; sys.nr = (int)effR.size(); sys.nc = (int)effC.size(); sys.a.assign((size_t)sys.nr * sys.nc, 0.);
     std::vector<double> vec(effR.size(), 0.);
-    unsigned activeRow = 0;
+    unsigned activeRow = 0, rowCstr = 0, extraRow = 0;
     for (size_t r = 0; r < rID.size(); r++) {
-        if (rS[r] != ACTIVE) continue;  // CONSTRAINED rows without masters contribute nothing
-        unsigned activeCol = 0;
-        const double rowWeight = 1.0;
-        for (size_t c = 0; c < cID.size(); c++) {
-            if (cS[c] == ACTIVE) { sys(activeRow, activeCol) = rowWeight * K((int)r, (int)c); activeCol++; }
-            else if (cS[c] == CONSTRAINED) vec[activeRow] -= cVal[c] * rowWeight * K((int)r, (int)c);
+        if (rS[r] == ACTIVE) {
+            assembleRow(K, r, activeRow, 1.0, numActiveCols, cS, cVal, cCon, sys, vec);
+            activeRow++;
+        } else if (rS[r] == CONSTRAINED) {
+            for (const auto& wm : rCon[rowCstr].second) {  // one additional row per master of the constrained row
+                assembleRow(K, r, (unsigned)(numActiveRows + extraRow), wm.first, numActiveCols, cS, cVal, cCon, sys, vec);
+                extraRow++;
+            }
+            rowCstr++;
         }
-        activeRow++;
     }
     solver.insertToLHS(sys, effR, effC);
     solver.insertToRHS(vec, effR);
@@ -1216,9 +1263,18 @@ static void assembleMatrix(LocalMat& K, const std::vector<uint8_t>& rS, const st
 
 // asmb/assembleForces.hpp:58-139
 static void assembleForces(const std::vector<double>& f, const std::vector<uint8_t>& st, const std::vector<size_t>& ids,
-                           System& solver) {
-    std::vector<size_t> eff; std::vector<double> v;
-    for (size_t d = 0; d < ids.size(); d++) if (st[d] == ACTIVE) { eff.push_back(ids[d]); v.push_back(f[d]); }
+                           const Constraints& con, System& solver) {
+    const std::vector<size_t> eff = effectiveIDs(st, ids, con);
+    const size_t numActive = (size_t)std::count(st.begin(), st.end(), (uint8_t)ACTIVE);
+    std::vector<double> v(eff.size(), 0.);
+    unsigned active = 0, cstr = 0, extra = 0;
+    for (size_t d = 0; d < ids.size(); d++) {
+        if (st[d] == ACTIVE) v[active++] = f[d];
+        else if (st[d] == CONSTRAINED) {
+            for (const auto& wm : con[cstr].second) v[numActive + extra++] = wm.first * f[d];
+            cstr++;
+        }
+    }
     solver.insertToRHS(v, eff);
 }
 
@@ -1228,14 +1284,15 @@ static void stiffnessElement(const Problem& p, System& solver, const Quad& q, in
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
     std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
-    bool doSomething = collectFromDoFs(test, e, rS, rID, rV, incremental);
+    Constraints rCon, cCon;
+    bool doSomething = collectFromDoFs(test, e, rS, rID, rV, rCon, incremental);
     if (!doSomething) return;
-    if (t.bubnov()) { cS = rS; cID = rID; cV = rV; }
-    else doSomething = collectFromDoFs(trial, e, cS, cID, cV, incremental);
+    if (t.bubnov()) { cS = rS; cID = rID; cV = rV; cCon = rCon; }
+    else doSomething = collectFromDoFs(trial, e, cS, cID, cV, cCon, incremental);
     if (!doSomething) return;
     LocalMat K; K.nr = (int)rID.size(); K.nc = (int)cID.size(); K.a.assign((size_t)K.nr * K.nc, 0.);
     for (int g = 0; g < q.n; g++) tangentKernel(kid, params, t, &q.p[g * q.dim], q.w[g], K);  // Quadrature.hpp:132-141
-    assembleMatrix(K, rS, cS, rID, cID, cV, solver);
+    assembleMatrix(K, rS, cS, rID, cID, cV, rCon, cCon, solver);
 }
 
 // asmb/ForceIntegrator.hpp:126-160
@@ -1244,14 +1301,15 @@ static void forceElement(const Problem& p, System& solver, const Quad& q, int ki
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
     std::vector<uint8_t> st; std::vector<size_t> ids; std::vector<double> pv;
-    if (!collectFromDoFs(test, e, st, ids, pv, false)) return;
+    Constraints con;
+    if (!collectFromDoFs(test, e, st, ids, pv, con, false)) return;
     std::vector<double> f(ids.size(), 0.);
     for (int g = 0; g < q.n; g++) {
         if (body) bodyForceKernel(t, params, &q.p[g * q.dim], q.w[g], f);
         else residualKernel(kid, params, t, &q.p[g * q.dim], q.w[g], f);
     }
     for (auto& x : f) x *= factor;
-    assembleForces(f, st, ids, solver);
+    assembleForces(f, st, ids, con, solver);
 }
 
 // solver/TripletContainer.hpp:158-301
@@ -1260,12 +1318,11 @@ static void registerFields(const Problem& p, System& solver, int testId, int tri
     const bool bubnov = (&test == &trial);
     for (int64_t e = 0; e < p.mesh.nElems; e++) {
         std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
-        if (!collectFromDoFs(test, e, rS, rID, rV, false)) continue;
-        if (bubnov) { cS = rS; cID = rID; }
-        else if (!collectFromDoFs(trial, e, cS, cID, cV, false)) continue;
-        std::vector<size_t> effR, effC;
-        for (size_t r = 0; r < rID.size(); r++) if (rS[r] == ACTIVE) effR.push_back(rID[r]);
-        for (size_t c = 0; c < cID.size(); c++) if (cS[c] == ACTIVE) effC.push_back(cID[c]);
+        Constraints rCon, cCon;
+        if (!collectFromDoFs(test, e, rS, rID, rV, rCon, false)) continue;
+        if (bubnov) { cS = rS; cID = rID; cCon = rCon; }
+        else if (!collectFromDoFs(trial, e, cS, cID, cV, cCon, false)) continue;
+        const std::vector<size_t> effR = effectiveIDs(rS, rID, rCon), effC = effectiveIDs(cS, cID, cCon);
         for (size_t r : effR) for (size_t c : effC) solver.tmp.insert(Triplet{(int)r, (int)c, 0.});
     }
     const size_t cur = solver.trip.size();
@@ -1392,6 +1449,25 @@ void orc_set_field(void* h, int id, int feDeg, int dofSize, int64_t nObj, const 
     f.status.assign(status, status + n);
     f.prescribed.assign(prescribed, prescribed + n);
     f.values.assign(values, values + n);
+}
+// linear constraints with master DoFs: conDof[k] = obj*dofSize+comp of a CONSTRAINED component, masters/weights in
+// [conPtr[k], conPtr[k+1]); replaces previous ones (nCon = 0 removes them)
+void orc_set_field_constraints(void* h, int id, int64_t nCon, const int64_t* conDof, const int64_t* conPtr,
+                               const int64_t* masterEqn, const double* weight) {
+    Field& f = ((Problem*)h)->fields[id];
+    f.cptr.clear(); f.cmaster.clear(); f.cweight.clear();
+    if (nCon <= 0) return;
+    const size_t n = (size_t)f.nObj * f.dofSize;
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (int64_t k = 0; k < nCon; k++) cnt[conDof[k] + 1] = conPtr[k + 1] - conPtr[k];
+    for (size_t k = 0; k < n; k++) cnt[k + 1] += cnt[k];
+    f.cptr = cnt;
+    f.cmaster.resize((size_t)cnt[n]); f.cweight.resize((size_t)cnt[n]);
+    for (int64_t k = 0; k < nCon; k++)
+        for (int64_t j = conPtr[k]; j < conPtr[k + 1]; j++) {
+            const size_t q = (size_t)(cnt[conDof[k]] + (j - conPtr[k]));
+            f.cmaster[q] = masterEqn[j]; f.cweight[q] = weight[j];
+        }
 }
 void orc_set_field_values(void* h, int id, const double* values) {
     Field& f = ((Problem*)h)->fields[id];

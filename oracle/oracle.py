@@ -174,6 +174,13 @@ class Problem:
         lib().orc_set_field(self.h, fid, fe_deg, dof_size, C.c_int64(n_obj), _p(a["elem_dof"]), _p(a["eqn"]),
                             _p(a["status"]), _p(a["prescribed"]), _p(a["values"]))
 
+    def set_field_constraints(self, fid, con_dof, con_ptr, master_eqn, weight):
+        """linear constraints with master DoFs (base/dof/Constraint.hpp): see orc_set_field_constraints"""
+        con_dof = np.ascontiguousarray(con_dof, dtype=np.int64); con_ptr = np.ascontiguousarray(con_ptr, dtype=np.int64)
+        master_eqn = np.ascontiguousarray(master_eqn, dtype=np.int64); weight = np.ascontiguousarray(weight, dtype=np.float64)
+        lib().orc_set_field_constraints(self.h, fid, C.c_int64(len(con_dof)), _p(con_dof), _p(con_ptr), _p(master_eqn),
+                                        _p(weight))
+
     def set_field_values(self, fid, values):
         v = np.ascontiguousarray(values, dtype=np.float64)
         lib().orc_set_field_values(self.h, fid, _p(v))

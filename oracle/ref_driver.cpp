@@ -50,10 +50,19 @@ struct Op {
     int test = 0, trial = 0, incremental = 1;
     std::vector<double> p;
 };
+struct LinearConstraint {       // base/dof/Constraint.hpp: u(obj,comp) = rhs + sum weight * u(master obj, master comp)
+    long obj = 0;
+    unsigned comp = 0;
+    double rhs = 0.;
+    std::vector<long> mobj;
+    std::vector<unsigned> mcomp;
+    std::vector<double> weight;
+};
 struct FieldSpec {
     std::string presc, values;  // raw f64 files [n_obj][ds] ("-" = none)
     int boundary = 0;           // constrain the whole boundary through dof::constrainBoundary
     long pin = -1;              // constrainValue(0, 0.) on this DoF object
+    std::vector<LinearConstraint> linear;
 };
 struct Job {
     std::string type, mesh, out;
@@ -95,6 +104,13 @@ static Job readJob(const char* file) {
             FieldSpec f;
             s >> i >> f.boundary >> f.pin >> f.presc >> f.values;
             j.fields[i] = f;
+        } else if (key == "constraint") {
+            int i, nm;
+            LinearConstraint c;
+            s >> i >> c.obj >> c.comp >> c.rhs >> nm;
+            c.mobj.resize(nm); c.mcomp.resize(nm); c.weight.resize(nm);
+            for (int k = 0; k < nm; k++) s >> c.mobj[k] >> c.mcomp[k] >> c.weight[k];
+            j.fields[i].linear.push_back(c);
         } else if (key == "op") {
             Op o;
             s >> o.what >> o.kernel >> o.test >> o.trial >> o.incremental;
@@ -137,6 +153,17 @@ void setUpField(const MESH& mesh, FIELD& field, const FieldSpec& spec, const bas
         typename FIELD::DoFPtrIter it = field.doFsBegin();
         std::advance(it, spec.pin);
         (*it)->constrainValue(0, 0.0);
+    }
+    for (const LinearConstraint& c : spec.linear) {
+        typename FIELD::DoFPtrIter slave = field.doFsBegin();
+        std::advance(slave, c.obj);
+        (*slave)->makeConstraint(c.comp);
+        (*slave)->getConstraint(c.comp)->setValue(c.rhs);
+        for (std::size_t k = 0; k < c.mobj.size(); k++) {
+            typename FIELD::DoFPtrIter master = field.doFsBegin();
+            std::advance(master, c.mobj[k]);
+            (*slave)->getConstraint(c.comp)->addWeightedDoF(*master, c.mcomp[k], c.weight[k]);
+        }
     }
     if (!values.empty()) {
         for (typename FIELD::DoFPtrIter it = field.doFsBegin(); it != field.doFsEnd(); ++it)

@@ -48,7 +48,7 @@ class Case:
         self.ops = []
         self.n_eqn = 0
 
-    def add_field(self, fe_deg, ds, dirichlet=None, values=None, pin_first=False):
+    def add_field(self, fe_deg, ds, dirichlet=None, values=None, pin_first=False, linear=None):
         """dirichlet: fun(x)->[n,ds] applied on the whole boundary (dof::constrainBoundary);
         values: fun(x_support)->[n_obj,ds] current field state; pin_first: constrain component 0 of DoF 0 to 0
         (drivenCavity.cpp:199-202)."""
@@ -61,14 +61,33 @@ class Case:
         if pin_first:
             status[0, 0] = E.CONSTRAINED
             presc[0, 0] = 0.0
+        # linear constraints with master DoFs (base/dof/Constraint.hpp): linear(status) -> [(obj, comp, rhs,
+        # [(master obj, master comp, weight), ...]), ...]; applied after the Dirichlet boundary, before the numbering
+        lin = linear(status) if linear is not None else []
+        for obj, comp, rhs, _ in lin:
+            status[obj, comp] = E.CONSTRAINED
+            presc[obj, comp] = rhs
         eqn, n = E.number_dofs_consecutively(status, init=self.n_eqn)
         self.n_eqn += n
         vals = np.zeros((nobj, ds))
         if values is not None:
             vals = np.asarray(values(self.dof_positions(fe_deg, ed, nobj)), dtype=np.float64).reshape(nobj, ds)
         self.fields.append(dict(fe_deg=fe_deg, ds=ds, n_obj=nobj, elem_dof=ed, status=status, presc=presc, eqn=eqn,
-                                values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1))
+                                values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1, linear=lin))
         return len(self.fields) - 1
+
+    @staticmethod
+    def constraint_arrays(f):
+        """flat form of f["linear"] for set_field_constraints (masters as equation numbers)"""
+        con_dof, con_ptr, meq, w = [], [0], [], []
+        for obj, comp, _, masters in f["linear"]:
+            con_dof.append(obj * f["ds"] + comp)
+            for mo, mc, wt in masters:
+                assert f["status"][mo, mc] == E.ACTIVE, "master DoFs must be ACTIVE"
+                meq.append(int(f["eqn"][mo, mc])); w.append(wt)
+            con_ptr.append(len(meq))
+        return (np.array(con_dof, dtype=np.int64), np.array(con_ptr, dtype=np.int64), np.array(meq, dtype=np.int64),
+                np.array(w, dtype=np.float64))
 
     def dof_positions(self, fe_deg, ed, nobj):
         """physical position of every DoF object (support point mapped through the geometry)."""
@@ -86,6 +105,8 @@ class Case:
         for i, f in enumerate(self.fields):
             prob.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"].astype(np.int64), f["eqn"], f["status"],
                            f["presc"], f["values"])
+            if f["linear"]:
+                prob.set_field_constraints(i, *self.constraint_arrays(f))
         s = orc.System(self.n_eqn)
         if register:
             for op in self.ops:
@@ -109,6 +130,8 @@ class Case:
         for i, f in enumerate(self.fields):
             eng.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"],
                           f["values"])
+            if f["linear"]:
+                eng.set_field_constraints(i, *self.constraint_arrays(f))
         eng.new_solver(self.n_eqn)
         if register:
             for op in self.ops:
@@ -125,6 +148,26 @@ class Case:
         if own:
             eng.close()
         return out
+
+
+def linear_constraints(status, ds, count=4):
+    """deterministic set of linear constraints on ACTIVE DoF components: slave k gets 2 or 3 ACTIVE masters (never a
+    slave, possibly another component of the slave's own DoF object or a DoF of the same element) and an rhs term"""
+    free = [(int(o), int(cmp)) for o, cmp in np.argwhere(status == E.ACTIVE)]
+    rng = np.random.default_rng(2024 + ds)
+    picks = rng.permutation(len(free))
+    nslave = min(count, len(free) // 5)
+    slaves = [free[k] for k in picks[:nslave]]
+    pool = [free[k] for k in picks[nslave:]]
+    out = []
+    for k, (o, cmp) in enumerate(slaves):
+        nm = 2 + (k % 2)
+        masters = [pool[(3 * k + 7 * j) % len(pool)] for j in range(nm)]
+        if ds > 1 and k == 0 and (o, (cmp + 1) % ds) in pool:
+            masters[0] = (o, (cmp + 1) % ds)
+        w = [0.5, 0.25, -0.75][:nm] if k % 2 else [0.6, 0.4]
+        out.append((o, cmp, 0.05 * (k + 1), [(m[0], m[1], w[j]) for j, m in enumerate(masters)]))
+    return out
 
 
 def smooth_u(dim, amp=0.02):
@@ -191,6 +234,32 @@ def build_case(name, n=4, perturb=True, permute=False):
         lid = lambda x: np.stack([(x[:, dim - 1] > 1 - 1e-9) * 1.0] + [0 * x[:, 0]] * (dim - 1), axis=1)
         u = c.add_field(2, dim, dirichlet=lid, values=smooth_u(dim))
         p = c.add_field(1, 1, pin_first=True, values=lambda x: x[:, :1] - 0.5)
+        c.ops = [("matrix", E.K_VECTOR_LAPLACE, [1.0], 4, u, u, True), ("matrix", E.K_PRESSURE_GRADIENT, None, 4, u, p, True),
+                 ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
+                 ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),
+                 ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
+    elif name in ("laplace_q1_hex_linear", "laplace_q2_hex_linear", "laplace_p1_tet_linear"):
+        # general linear constraints: some interior DoFs are slaves of two / three ACTIVE masters with an rhs term
+        shape = E.TET if "tet" in name else E.HEX
+        deg = 2 if "q2" in name else 1
+        c = Case(shape, 1, *make_mesh(shape, n, perturb, permute))
+        c.add_field(deg, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), values=lambda x: 0.3 * x[:, :1] + 0.1,
+                    linear=lambda st: linear_constraints(st, 1))
+        q = 4 if deg == 2 else 3
+        c.ops = [("matrix", E.K_LAPLACE, [1.5], q, 0, 0, True), ("residual", E.K_LAPLACE, [1.5], q, 0, 0),
+                 ("body", [1.0], q, 0)]
+    elif name == "stvenant_q1_hex_linear":
+        lam, mu = lame(1000.0, 0.25)
+        y0 = np.full(3, -0.1); d = np.array([0., 1., 0.])
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 3, dirichlet=lambda x: H.fund_sol_elastostatic(x, y0, d, lam, mu), values=smooth_u(3),
+                    linear=lambda st: linear_constraints(st, 3))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0, True), ("residual", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0)]
+    elif name == "stokes_p2p1_tet_linear":
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        lid = lambda x: np.stack([(x[:, 2] > 1 - 1e-9) * 1.0, 0 * x[:, 0], 0 * x[:, 0]], axis=1)
+        u = c.add_field(2, 3, dirichlet=lid, values=smooth_u(3), linear=lambda st: linear_constraints(st, 3))
+        p = c.add_field(1, 1, pin_first=True, values=lambda x: x[:, :1] - 0.5, linear=lambda st: linear_constraints(st, 1, 2))
         c.ops = [("matrix", E.K_VECTOR_LAPLACE, [1.0], 4, u, u, True), ("matrix", E.K_PRESSURE_GRADIENT, None, 4, u, p, True),
                  ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
                  ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),

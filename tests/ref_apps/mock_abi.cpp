@@ -17,6 +17,7 @@ void* orc_problem_new();
 void orc_problem_free(void*);
 void orc_set_mesh(void*, int, int, int, int64_t, const double*, int64_t, const int64_t*);
 void orc_set_field(void*, int, int, int, int64_t, const int64_t*, const int64_t*, const uint8_t*, const double*, const double*);
+void orc_set_field_constraints(void*, int, int64_t, const int64_t*, const int64_t*, const int64_t*, const double*);
 void* orc_system_new(int64_t);
 void orc_system_free(void*);
 void orc_register_fields(void*, void*, int, int);
@@ -40,7 +41,8 @@ struct isl_engine {
     int shape = 0, npe = 0;
     int64_t nElems = 0;
     struct F { int deg = 0, ds = 0; int64_t nObj = 0; std::vector<int64_t> elemDof, eqn; std::vector<uint8_t> status;
-               std::vector<double> presc, values; } f[5];
+               std::vector<double> presc, values;
+               std::vector<int64_t> conDof, conPtr, masterEqn; std::vector<double> weight; } f[5];
     std::vector<std::vector<double> > pendingRows;
 };
 static std::string g_err;
@@ -64,6 +66,8 @@ static void push_field(isl_handle h, int i) {
     isl_engine::F& f = h->f[i];
     orc_set_field(h->prob, i, f.deg, f.ds, f.nObj, f.elemDof.data(), f.eqn.data(), f.status.data(), f.presc.data(),
                   f.values.data());
+    orc_set_field_constraints(h->prob, i, (int64_t)f.conDof.size(), f.conDof.data(), f.conPtr.data(), f.masterEqn.data(),
+                              f.weight.data());
 }
 int isl_field_set(isl_handle h, int i, int deg, int ds, int64_t nObj, const int32_t* ed, const int64_t* eqn,
                   const uint8_t* status, const double* presc, const double* values) {
@@ -85,6 +89,19 @@ int isl_field_set(isl_handle h, int i, int deg, int ds, int64_t nObj, const int3
     f.status.assign(status, status + n);
     f.presc.assign(presc, presc + n);
     f.values.assign(values, values + n);
+    f.conDof.clear(); f.conPtr.assign(1, 0); f.masterEqn.clear(); f.weight.clear();  // isl_field_set drops constraints
+    push_field(h, i);
+    return 0;
+}
+int isl_field_set_constraints(isl_handle h, int i, int64_t nCon, const int64_t* conDof, const int64_t* conPtr,
+                              const int64_t* masterEqn, const double* weight) {
+    isl_engine::F& f = h->f[i];
+    f.conDof.assign(conDof, conDof + nCon);
+    f.conPtr.assign(1, 0);
+    if (nCon > 0) f.conPtr.assign(conPtr, conPtr + nCon + 1);
+    const int64_t nm = nCon > 0 ? conPtr[nCon] : 0;
+    f.masterEqn.assign(masterEqn, masterEqn + nm);
+    f.weight.assign(weight, weight + nm);
     push_field(h, i);
     return 0;
 }

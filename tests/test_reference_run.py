@@ -24,7 +24,10 @@ import pytest
 from tests import flows
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refrun", "*.npz")))
+ALL_GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refrun", "*.npz")))
+# the cases with general linear constraints live in tests/test_zz_linear_constraints.py
+GOLD = [p for p in ALL_GOLD if "_linear" not in os.path.basename(p)]
+GOLD_LINEAR = [p for p in ALL_GOLD if "_linear" in os.path.basename(p)]
 REFERENCE = "/root/reference"
 APPS = os.path.join(ROOT, "oracle", "_ref", "apps")
 

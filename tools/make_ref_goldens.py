@@ -47,6 +47,13 @@ CASES = [
     ("stokes_p2p1_tet_n3", "stokes_p2p1_tet", "stokes_p2p1_tet", 3, True, False, True),
     ("stokes_q2q1_hex_n2", "stokes_q2q1_hex", "stokes_q2q1_hex", 2, True, False, False),
     ("stokes_q2q1_quad_n4", "stokes_q2q1_quad", "stokes_q2q1_quad", 4, True, False, True),
+    # general linear constraints (slave DoFs with weighted ACTIVE masters, asmb/assembleMatrix.hpp:212-338)
+    ("laplace_q1_hex_linear_n5", "laplace_q1_hex_linear", "laplace_q1_hex", 5, True, False, False),
+    ("laplace_q1_hex_linear_n4_reg", "laplace_q1_hex_linear", "laplace_q1_hex", 4, False, False, True),
+    ("laplace_q2_hex_linear_n2", "laplace_q2_hex_linear", "laplace_q2_hex", 2, True, False, False),
+    ("laplace_p1_tet_linear_n4", "laplace_p1_tet_linear", "laplace_p1_tet", 4, True, False, True),
+    ("stvenant_q1_hex_linear_n4", "stvenant_q1_hex_linear", "solid_q1_hex", 4, True, False, False),
+    ("stokes_p2p1_tet_linear_n2", "stokes_p2p1_tet_linear", "stokes_p2p1_tet", 2, True, False, True),
 ]
 
 
@@ -76,6 +83,9 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
         np.ascontiguousarray(f["presc"], dtype=np.float64).tofile(pf)
         np.ascontiguousarray(f["values"], dtype=np.float64).tofile(vf)
         lines.append("field %d %d %d %s %s" % (i, boundary, pin, pf, vf))
+        for obj, comp, rhs, masters in f["linear"]:
+            lines.append("constraint %d %d %d %.17g %d %s" % (i, obj, comp, rhs, len(masters), " ".join(
+                "%d %d %.17g" % m for m in masters)))
     for op in case.ops:
         if op[0] == "matrix":
             lines.append("op matrix %s %d %d %d %s" % (KERNEL_NAME[op[1]], op[4], op[5], int(op[6]),
