@@ -80,3 +80,34 @@ def test_engine_full_size_structured_system_equals_scaled_oracle_stencil(n):
         eng.close()
     del wl
     SC.check_structured_system(n, rp, col, val, rhs, bench_dirichlet, S0, body0, n0)
+
+
+def _perturbed_workload(n):
+    from insilico_b200 import engine as E
+    from insilico_b200 import meshgen
+    coords, conn, _ = meshgen.unit_cube_hex(n, n, n)
+    coords = meshgen.perturb_interior(coords, 1.0 / n, 0.15)
+    c = flows.Case(E.HEX, 1, coords, conn)
+    c.add_field(1, 1, dirichlet=lambda x: 1.0 + 0 * x[:, :1])
+    c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True)]
+    return c
+
+
+def test_sub_box_argument_holds_for_the_oracle():
+    """CPU: the perturbed-mesh checker (pattern, A 1 = rhs, symmetry, oracle on sub-boxes) accepts the oracle's system"""
+    n = 12
+    c = _perturbed_workload(n)
+    rp, col, val, rhs = c.run_oracle()
+    err = SC.check_perturbed_system(n, c.coords, rp, col, val, rhs, boxes=4, box=4)
+    assert err <= 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [24, 256])
+def test_engine_full_size_perturbed_mesh_properties_and_sub_box_oracle_parity(n):
+    import psutil
+    if n == 256 and psutil.virtual_memory().available < 48e9:
+        pytest.skip("needs about 40 GB of host memory")
+    c = _perturbed_workload(n)
+    rp, col, val, rhs = c.run_engine()
+    SC.check_perturbed_system(n, c.coords, rp, col, val, rhs)
