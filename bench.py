@@ -117,13 +117,17 @@ def cpu_reference(n_sample, steps, warmup, threads):
 REF_DRIVER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "ref_driver_omp")
 
 
-def cpu_reference_real(n_sample, steps):
+BINDING_DRIVER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "apps_b200", "ref_driver")
+
+
+def cpu_reference_real(n_sample, steps, driver=None):
     """The UNMODIFIED reference (headers of thrueberg/inSilico compiled here against the std-only Boost/Eigen stand-ins
     of oracle/compat, binary oracle/_ref/ref_driver_omp built by `make -C oracle ref` with the reference's release
     flags -O3 -fopenmp -DNDEBUG, NTHREADS=0 = all cores) on an n_sample^3 mesh of the same workload: per step a fresh
     base::solver::Eigen3, registerFields (untimed, like our cached pattern), stiffnessMatrixComputation +
     bodyForceComputation (timed).  Returns None when the binary is not there."""
-    if not os.access(REF_DRIVER, os.X_OK):
+    driver = driver or REF_DRIVER
+    if not os.access(driver, os.X_OK):
         return None
     import subprocess
     import tempfile
@@ -143,16 +147,41 @@ def cpu_reference_real(n_sample, steps):
                     "field 0 1 -1 %s/presc.bin -\nop matrix laplace 0 0 1 1.0\nop body body 0 0 1 1.0\n"
                     % (smf, wd, max(1, steps), wd))
         try:
-            out = subprocess.run([REF_DRIVER, job], check=True, capture_output=True, text=True, timeout=1500).stdout
+            out = subprocess.run([driver, job], check=True, capture_output=True, text=True, timeout=1500).stdout
         except Exception as e:  # noqa: BLE001  (fall back to the port, say so in the sample text)
             sys.stderr.write("reference driver failed: %r\n" % (e,))
             return None
     reps = [l.split() for l in out.splitlines() if l.startswith("rep ")]
-    t_asm = [float(r[r.index("assemble") + 1]) for r in reps]
+    if driver != REF_DRIVER and len(reps) > 1:
+        reps = reps[1:]   # the first pass uploads the mesh and builds the pattern (untimed for the CPU arm as well)
+    t_asm = [float(r[r.index("assemble") + 1]) + (float(r[r.index("finish") + 1]) if driver != REF_DRIVER else 0.0) for r in reps]
     t_reg = [float(r[r.index("register") + 1]) for r in reps]
     ne = conn.shape[0]
     t = sum(t_asm) / len(t_asm)
     return ne / t, t * 1e3, sum(t_reg) / len(t_reg) * 1e3, ne
+
+
+def reference_api_on_engine(ns, steps):
+    """The SAME job as the CPU baseline (reference objects in host memory, the reference's own API calls) with
+    base::solver::Eigen3 replaced by the binding's base::solver::B200 (include/insilico_b200_reference.hpp): per step a
+    fresh solver, registerFields (untimed, pattern cached), then stiffnessMatrixComputation + bodyForceComputation +
+    finishAssembly -- i.e. re-reading the reference's heap objects, host->device copies of what changed, the kernels,
+    the wait for the device.  The finished system stays on the device (getDeviceCSR), like a device solver would use it.
+    None when the prebuilt application is missing or fails."""
+    try:
+        r = cpu_reference_real(ns, steps + 1, driver=BINDING_DRIVER)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("reference API on the engine failed: %r\n" % (e,))
+        return None
+    if r is None:
+        return None
+    v, ms, ms_reg, ne = r
+    return {"value": v, "unit": "elements/s", "ms_per_step": ms,
+            "sample": "%d^3 Q1 hex mesh (%d elements), the CPU baseline's job through the reference API on the B200 "
+                      "binding; registerFields %.0f ms excluded" % (ns, ne, ms_reg),
+            "what": "unmodified reference headers + include/insilico_b200_reference.hpp + libinsilico_b200.so: host scan "
+                    "of the reference's Node/Element/DegreeOfFreedom objects, isl_assemble_matrix + isl_assemble_bodyforce, "
+                    "isl_finish; the system stays on the device"}
 
 
 def reference_baseline(ns, steps, warmup, cores):
@@ -372,6 +401,9 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         line["cpu_baseline"], _ = reference_baseline(args.cpu_sample, 2, 1, cores)
+        api = reference_api_on_engine(args.cpu_sample, 3)   # separate process with its own engine on the same device
+        if api is not None:
+            line["e2e_reference_api"] = api
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
