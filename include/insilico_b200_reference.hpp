@@ -448,13 +448,19 @@ public:
     }
 
     //! Constructor with the size N of matrix and vector (Eigen3.hpp:71-77)
-    B200(const std::size_t size) : size_(size), solved_(false) {
+    B200(const std::size_t size) : size_(size), solved_(false), id_(++latest_()) {
         b200_detail::check(isl_system_create(b200_detail::engine(), static_cast<int64_t>(size)));
+    }
+
+    //! The engine holds ONE system at a time: using a solver after a newer one was constructed is an error
+    void verifyCurrent() const {
+        VERIFY_MSG(id_ == latest_(), "base::solver::B200: a newer solver object exists; the engine holds one system at a time");
     }
 
     //! Insert numbers to matrix storage (Eigen3.hpp:81-108): host-side odd contributions
     template <typename MATRIX, typename RDOFS, typename CDOFS>
     void insertToLHS(const MATRIX& matrix, const RDOFS& rowDoFs, const CDOFS& colDoFs) {
+        this->verifyCurrent();
         const std::size_t nr = rowDoFs.size(), nc = colDoFs.size();
         if (nr == 0 || nc == 0) return;
         std::vector<int64_t> r(nr), c(nc);
@@ -475,6 +481,7 @@ public:
     //! Insert numbers to RHS vector (Eigen3.hpp:112-124)
     template <typename VECTOR, typename DOFS>
     void insertToRHS(const VECTOR& vector, const DOFS& dofs) {
+        this->verifyCurrent();
         const std::size_t n = dofs.size();
         if (n == 0) return;
         std::vector<int64_t> r(n);
@@ -490,6 +497,7 @@ public:
     //! Pre-determine the non-zero pattern (Eigen3.hpp:329-336, TripletContainer.hpp:158-301)
     template <typename FIELDTUPLEBINDER, typename FIELDBINDER>
     void registerFields(const FIELDBINDER& fieldBinder) {
+        this->verifyCurrent();
         b200_detail::synchronise(fieldBinder);
         typedef b200_detail::TupleIndices<FIELDTUPLEBINDER> TI;
         b200_detail::check(isl_pattern_register(b200_detail::engine(), TI::test, TI::trial));
@@ -497,6 +505,7 @@ public:
 
     //! Finish the assembly (Eigen3.hpp:142-153): waits for the device
     void finishAssembly(const bool = true) {
+        this->verifyCurrent();
         int64_t n = 0, nnz = 0;
         b200_detail::check(isl_finish(b200_detail::engine(), &n, &nnz));
         nnz_ = static_cast<std::size_t>(nnz);
@@ -505,6 +514,7 @@ public:
     //! Norm of the rhs/solution vector; like the reference divided by the length (Eigen3.hpp:128-138)
     double norm() const {
         if (solved_) return this->norm(0, size_);
+        this->verifyCurrent();
         double v = 0.;
         b200_detail::check(isl_rhs_norm(b200_detail::engine(), &v));
         return v;
@@ -519,6 +529,7 @@ public:
     //! Direct access to an entry in the RHS/solution vector (Eigen3.hpp:293-296)
     number getValue(const std::size_t index) const {
         if (solved_) return x_[index];
+        this->verifyCurrent();
         double v = 0.;
         b200_detail::check(isl_rhs_value(b200_detail::engine(), static_cast<int64_t>(index), &v));
         return v;
@@ -528,6 +539,7 @@ public:
     //@{
     void getCSR(std::vector<int64_t>& rowptr, std::vector<int32_t>& col, std::vector<double>& val,
                 std::vector<double>& rhs) const {
+        this->verifyCurrent();
         int64_t n = 0, nnz = 0;
         b200_detail::check(isl_finish(b200_detail::engine(), &n, &nnz));
         rowptr.assign(static_cast<std::size_t>(n) + 1, 0);
@@ -589,6 +601,7 @@ public:
 private:
     const std::vector<double>& hostRhs_() const {
         if (!solved_) {
+            this->verifyCurrent();
             x_.assign(size_, 0.);
             if (size_) b200_detail::check(isl_get_csr(b200_detail::engine(), NULL, NULL, NULL, &x_[0]));
         }
@@ -606,9 +619,15 @@ private:
         return it;
     }
 
+    static unsigned long& latest_() {
+        static unsigned long n = 0;
+        return n;
+    }
+
     std::size_t size_, nnz_ = 0;
     mutable std::vector<double> x_;  //!< host copy of rhs / the solution after a solve
     bool solved_;
+    unsigned long id_;
 };
 
 }  // namespace solver
@@ -627,9 +646,10 @@ typename FIELDTUPLEBINDER::Tuple probeTuple(const FIELDBINDER& fb, bool last) {
 
 //! base/asmb/StiffnessMatrix.hpp:49-87 for SOLVER = base::solver::B200
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
-void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder,
+void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
                                 const KERNEL& kernelObj, const bool incremental = true) {
     namespace D = base::solver::b200_detail;
+    solver.verifyCurrent();
     if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
     D::synchronise(fieldBinder);
     double params[4] = {0., 0., 0., 0.};
@@ -643,9 +663,10 @@ void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200&, const FI
 
 //! base/asmb/ForceIntegrator.hpp:37-71 for SOLVER = base::solver::B200 (forces enter the rhs with factor -1)
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
-void computeResidualForces(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder,
+void computeResidualForces(const QUADRATURE&, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
                            const KERNEL& kernelObj) {
     namespace D = base::solver::b200_detail;
+    solver.verifyCurrent();
     if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
     D::synchronise(fieldBinder);
     double params[4] = {0., 0., 0., 0.};
@@ -659,8 +680,9 @@ void computeResidualForces(const QUADRATURE&, base::solver::B200&, const FIELDBI
 
 //! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200; the engine integrates constant body forces
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
-void bodyForceComputation(const QUADRATURE&, base::solver::B200&, const FIELDBINDER& fieldBinder, const FUN& forceFun) {
+void bodyForceComputation(const QUADRATURE&, base::solver::B200& solver, const FIELDBINDER& fieldBinder, const FUN& forceFun) {
     namespace D = base::solver::b200_detail;
+    solver.verifyCurrent();
     typedef typename FIELDTUPLEBINDER::Tuple Tuple;
     typedef typename Tuple::GeomElement GeomElement;
     typedef typename Tuple::TestElement TestElement;
