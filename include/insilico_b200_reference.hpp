@@ -596,6 +596,16 @@ public:
         const std::vector<double>& b = this->hostRhs_();
         for (std::size_t i = 0; i < b.size(); i++) out << i << " " << b[i] << "\n";
     }
+    //! Eigen3.hpp:324-327 / TripletContainer.hpp:390-400: "row col value" sorted by (row, col)
+    std::ostream& debugTriplet(std::ostream& out) const {
+        std::vector<int64_t> rowptr;
+        std::vector<int32_t> col;
+        std::vector<double> val, rhs;
+        this->getCSR(rowptr, col, val, rhs);
+        for (std::size_t i = 0; i + 1 < rowptr.size(); i++)
+            for (int64_t k = rowptr[i]; k < rowptr[i + 1]; k++) out << i << " " << col[k] << " " << val[k] << std::endl;
+        return out;
+    }
     //@}
 
 private:
