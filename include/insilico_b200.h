@@ -148,6 +148,12 @@ int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** v
 int isl_rhs_value(isl_handle h, int64_t index, double* value);
 int isl_rhs_norm(isl_handle h, double* norm);
 
+/* solver.cgSolve() (base/solver/Eigen3.hpp:263-275: Eigen::ConjugateGradient, diagonal preconditioner, zero initial
+ * guess): solves A x = rhs on the device for the finished s.p.d. system, rhs is replaced by x.  tol <= 0 = machine
+ * epsilon, max_iter <= 0 = 2 n (Eigen's defaults); *error = |r| / |b| at exit.  First row of SURVEY 8(f); not on the
+ * benchmarked path.                                                                                            */
+int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations, double* error);
+
 /* ---- multi-GPU interface exchange helpers (element blocks per GPU, owned row ranges) -------------------- */
 /* gather val[idx[k]] (or rhs when which = 1) into a packed device buffer / scatter-add a packed buffer      */
 int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev);

@@ -557,6 +557,11 @@ public:
 
     //! @name Linear solves: outside the assembly path, delegated to the hook (host) -- Eigen3.hpp:157-289
     //@{
+    //! cgSolve() runs on the device (isl_solve_cg) unless a solve hook is installed and nativeCG() is false
+    static bool& nativeCG() {
+        static bool flag = true;
+        return flag;
+    }
     void choleskySolve() { this->solve_("cholesky"); }
     void luSolve() { this->solve_("lu"); }
     void superLUSolve() { this->solve_("superlu"); }
@@ -618,6 +623,16 @@ private:
         return x_;
     }
     int solve_(const char* method) {
+        if (std::string(method) == "cg" && (nativeCG() || solveHook() == NULL)) {
+            this->verifyCurrent();
+            int64_t iterations = 0;
+            double error = 0.;
+            b200_detail::check(isl_solve_cg(b200_detail::engine(), 0., 0, &iterations, &error));
+            x_.assign(size_, 0.);
+            if (size_) b200_detail::check(isl_get_csr(b200_detail::engine(), NULL, NULL, NULL, &x_[0]));
+            solved_ = true;
+            return static_cast<int>(iterations);
+        }
         VERIFY_MSG(solveHook() != NULL, std::string("B200 solver: linear solve '") + method +
                                             "' requested but no solve hook installed (the engine covers the assembly path)");
         std::vector<int64_t> rowptr;

@@ -1371,6 +1371,8 @@ void flush_pending(isl_engine* h, int fuse_body, double f0) {
     h->val_is_zero = false;
 }
 
+#include "isl_solver.cuh"
+
 }  // namespace
 
 // =============================================================================
@@ -1810,6 +1812,16 @@ int isl_rhs_norm(isl_handle h, double* norm) {
         ISL_CUDA(cudaMemcpyAsync(&s, h->scratch_d.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         *norm = std::sqrt(s) / (double)h->n_eqn;  // Eigen3.hpp:133-138 divides by the segment length
+    });
+}
+
+int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations, double* error) {
+    return guarded([&] {
+        flush_pending(h);
+        materialize_zero(h);
+        ISL_CUDA(cudaSetDevice(h->device));
+        const int64_t it = solve_cg(h, tol, max_iter, error);
+        if (iterations) *iterations = it;
     });
 }
 

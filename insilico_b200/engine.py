@@ -36,7 +36,7 @@ EXPORTED = [
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
     "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_insert_lhs", "isl_insert_rhs",
-    "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_pack_entries",
+    "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
     "isl_unpack_add_entries",
 ]
 
@@ -295,6 +295,12 @@ class Engine:
             rhs = np.zeros(n)
         _chk(lib().isl_get_csr(self.h, _ptr(rowptr), _ptr(col), _ptr(val), _ptr(rhs)))
         return rowptr, col, val, rhs
+
+    def cg_solve(self, tol=0.0, max_iter=0):
+        """solver.cgSolve() on the device (base/solver/Eigen3.hpp:263-275): rhs <- A^-1 rhs; returns (iterations, error)"""
+        it, err = C.c_int64(0), C.c_double(0.0)
+        _chk(lib().isl_solve_cg(self.h, C.c_double(tol), _i64(max_iter), C.byref(it), C.byref(err)))
+        return it.value, err.value
 
     def device_csr(self):
         p = [C.c_void_p() for _ in range(4)]

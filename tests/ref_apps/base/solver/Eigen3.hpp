@@ -8,6 +8,7 @@
 #ifndef base_solver_eigen3_hpp
 #define base_solver_eigen3_hpp
 
+#include <cstdlib>
 #include <Eigen/Sparse>
 #include <base/io/Format.hpp>
 #include <insilico_b200_reference.hpp>
@@ -49,7 +50,10 @@ inline int hostSolve(const char* method, std::size_t n, const std::vector<int64_
     return iterations;
 }
 struct InstallHook {
-    InstallHook() { B200::solveHook() = &hostSolve; }
+    InstallHook() {
+        B200::solveHook() = &hostSolve;
+        B200::nativeCG() = (std::getenv("ISL_NATIVE_CG") != NULL);   // default: the host stand-in, like the CPU reference run
+    }
 };
 static InstallHook installHook;
 }  // namespace shadow_detail

@@ -6,6 +6,7 @@
 // linked with THIS file instead of libinsilico_b200.so, must print what they print with base::solver::Eigen3.
 // On the GPU the same applications link the real library.  Never shipped, never linked by the product.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,7 +44,7 @@ struct isl_engine {
     struct F { int deg = 0, ds = 0; int64_t nObj = 0; std::vector<int64_t> elemDof, eqn; std::vector<uint8_t> status;
                std::vector<double> presc, values;
                std::vector<int64_t> conDof, conPtr, masterEqn; std::vector<double> weight; } f[5];
-    std::vector<std::vector<double> > pendingRows;
+    std::vector<double> solution;  // rhs after isl_solve_cg
 };
 static std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -116,7 +117,7 @@ int isl_field_update(isl_handle h, int i, const double* presc, const double* val
 int isl_system_create(isl_handle h, int64_t n) {
     if (h->sys) orc_system_free(h->sys);
     h->sys = orc_system_new(n);
-    h->n = n; h->finished = false;
+    h->n = n; h->finished = false; h->solution.clear();
     return 0;
 }
 int isl_pattern_register(isl_handle h, int t, int c) { orc_register_fields(h->sys, h->prob, t, c); return 0; }
@@ -143,6 +144,7 @@ int isl_finish(isl_handle h, int64_t* n, int64_t* nnz) {
 int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs) {
     if (!h->finished) { orc_finish(h->sys); h->finished = true; }
     orc_get_csr(h->sys, rowptr, col, val, rhs);
+    if (rhs && !h->solution.empty()) std::memcpy(rhs, h->solution.data(), h->solution.size() * sizeof(double));
     return 0;
 }
 int isl_get_device_csr(isl_handle, int64_t**, int32_t**, double**, double**) { return fail("mock ABI: no device"); }
@@ -152,5 +154,41 @@ int isl_rhs_value(isl_handle h, int64_t i, double* v) {
     *v = b[(size_t)i];
     return 0;
 }
-int isl_rhs_norm(isl_handle h, double* v) { *v = orc_rhs_norm(h->sys); return 0; }
+int isl_rhs_norm(isl_handle h, double* v) {
+    if (!h->solution.empty()) { double a = 0.; for (double x : h->solution) a += x * x; *v = std::sqrt(a) / (double)h->n; return 0; }
+    *v = orc_rhs_norm(h->sys);
+    return 0;
+}
+// Jacobi-preconditioned CG as in Eigen 3.2's ConjugateGradient.h (what isl_solve_cg does on the device)
+int isl_solve_cg(isl_handle h, double tol, int64_t maxIter, int64_t* iterations, double* error) {
+    int64_t n = 0, nnz = 0;
+    isl_finish(h, &n, &nnz);
+    std::vector<int64_t> rp(n + 1); std::vector<int32_t> col(nnz); std::vector<double> val(nnz), b(n);
+    orc_get_csr(h->sys, rp.data(), col.data(), val.data(), b.data());
+    if (tol <= 0.) tol = 2.220446049250313e-16;
+    if (maxIter <= 0) maxIter = 2 * n;
+    std::vector<double> x(n, 0.), r(b), p(n), Ap(n), dinv(n, 1.);
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t k = rp[i]; k < rp[i + 1]; k++) if (col[k] == i && val[k] != 0.) dinv[i] = 1. / val[k];
+    double bb = 0., rr = 0., rz = 0.;
+    for (int64_t i = 0; i < n; i++) { bb += b[i] * b[i]; p[i] = dinv[i] * r[i]; rz += r[i] * p[i]; }
+    rr = bb;
+    int64_t it = 0;
+    if (bb > 0.)
+        while (rr >= tol * tol * bb && it < maxIter) {
+            double pAp = 0.;
+            for (int64_t i = 0; i < n; i++) { double s = 0.; for (int64_t k = rp[i]; k < rp[i + 1]; k++) s += val[k] * p[col[k]]; Ap[i] = s; pAp += p[i] * s; }
+            const double alpha = rz / pAp;
+            rr = 0.; double rzn = 0.;
+            for (int64_t i = 0; i < n; i++) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rr += r[i] * r[i]; rzn += r[i] * dinv[i] * r[i]; }
+            if (rr < tol * tol * bb) break;
+            const double beta = rzn / rz; rz = rzn;
+            for (int64_t i = 0; i < n; i++) p[i] = dinv[i] * r[i] + beta * p[i];
+            it++;
+        }
+    h->solution = x;
+    if (iterations) *iterations = it;
+    if (error) *error = bb > 0. ? std::sqrt(rr / bb) : 0.;
+    return 0;
+}
 }

@@ -95,3 +95,65 @@ def test_constraint_argument_checks_on_engine():
         eng.set_field_constraints(0, con_dof, con_ptr, meq, w)
     finally:
         eng.close()
+
+
+# ---- device conjugate gradients (isl_solve_cg) -----------------------------------------------------------
+# written without GPU minutes: the GPU variants are gated until they have run once (ISL_TEST_EXPERIMENTAL=1)
+experimental = pytest.mark.skipif(not os.environ.get("ISL_TEST_EXPERIMENTAL"), reason="set ISL_TEST_EXPERIMENTAL=1")
+
+
+def _run_app_native_cg(suffix, tmp_path):
+    import subprocess
+    from tests import ref_apps_cases as RA
+    from tests.test_reference_run import ROOT
+    exe, args = RA.prepare("compressible_quad010", str(tmp_path))
+    p = subprocess.run([os.path.join(APPS_B200, exe + suffix)] + args, cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, ISL_NATIVE_CG="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    expected = open(os.path.join(ROOT, "tests", "golden", "refrun_apps", "compressible_quad010.out")).read()
+    assert RA.same_output(p.stdout, expected), "\n" + p.stdout + "\n--- expected ---\n" + expected
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_newton_application_with_cg_behind_the_abi_mock(tmp_path):
+    """B200::cgSolve -> isl_solve_cg -> solution back into the DoFs; the mock ABI runs the same algorithm on the host"""
+    _run_app_native_cg("_mock", tmp_path)
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_newton_application_with_device_cg(tmp_path):
+    _run_app_native_cg("", tmp_path)
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize("name,n", [("laplace_q1_hex", 12), ("stvenant_q1_hex", 6), ("laplace_p1_tet", 8)])
+def test_device_cg_equals_sparse_direct_solve(name, n):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from insilico_b200 import engine as E
+    c = flows.build_case(name, n, True, False)
+    c.ops = [op for op in c.ops if op[0] != "residual" or True]
+    eng = E.Engine(0)
+    try:
+        eng.set_mesh(c.shape, c.geom_deg, c.coords, c.conn)
+        for i, f in enumerate(c.fields):
+            eng.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+        eng.new_solver(c.n_eqn)
+        for op in c.ops:
+            if op[0] == "matrix":
+                eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+            elif op[0] == "residual":
+                eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5])
+            elif op[0] == "body":
+                eng.body_force_computation(op[1], op[2], op[3])
+        rp, col, val, rhs = eng.get_csr()
+        it, err = eng.cg_solve()
+        x = eng.get_csr(rhs=np.zeros(c.n_eqn))[3]
+    finally:
+        eng.close()
+    ref = spla.spsolve(sp.csr_matrix((val, col, rp)).tocsc(), rhs)
+    assert 0 < it <= 2 * c.n_eqn and err < 1e-12
+    assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
