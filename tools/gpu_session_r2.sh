@@ -7,7 +7,8 @@ O=gpurun_out/r2
 export PYTHONUNBUFFERED=1
 {
 echo "== 1. GPU test suite"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
-echo "== 2. experimental row-gather kernels"; ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -k rowgather 2>&1 | tail -8
+echo "== 2. experimental: row-gather kernels, device CG"; ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -k rowgather 2>&1 | tail -8
+ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_linear_constraints.py -q -m gpu -k "cg" 2>&1 | tail -8
 echo "== 3. default bench"; timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_default.json 2> $O/bench_default.err; tail -c 1500 $O/bench_default.json
 echo "== 4. row-gather sweep (kernel only)"
 for ss in 0 1; do for nt in 256 320 192 128; do for pr in 192 256 320; do for st in 1 2 4; do
