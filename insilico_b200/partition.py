@@ -209,3 +209,190 @@ class DistributedAssembly:
     def exchange(self):
         with torch.cuda.stream(self.stream):
             self.plan.exchange(self.val, self.rhs, add_fn=self._add)
+
+
+# =====================================================================================================================
+# General element-block partition (unstructured case): any mesh, any number of fields.
+# Every rank computes the same partition from the global description; one process per GPU assembles its element block
+# into a local CSR over (owned rows | ghost rows | halo-only ids) and ships the ghost rows to their owners.
+# =====================================================================================================================
+def morton_order(coords, conn, bits=10):
+    """element order along a Z-curve of the centroids: contiguous blocks of it are compact element blocks"""
+    cen = coords[conn].mean(axis=1)
+    lo, hi = cen.min(axis=0), cen.max(axis=0)
+    q = np.minimum(((cen - lo) / np.maximum(hi - lo, 1e-300) * (1 << bits)).astype(np.int64), (1 << bits) - 1)
+    key = np.zeros(len(conn), dtype=np.int64)
+    dim = coords.shape[1]
+    for b in range(bits):
+        for d in range(dim):
+            key |= ((q[:, d] >> b) & 1) << (b * dim + d)
+    return np.argsort(key, kind="stable")
+
+
+def general_partition(coords, conn, fields, n_eqn, rank, world, order=None):
+    """Local workload of `rank`.
+
+    coords [n_nodes, dim], conn [n_elems, npe]; fields: list of dicts with elem_dof [n_elems, ndpe], eqn [n_obj, ds]
+    (global equation numbers, < 0 where not ACTIVE), status, presc, values [n_obj, ds]; n_eqn: global system size.
+    order: element permutation whose contiguous blocks become the element blocks (default: Morton order).
+
+    Returns a dict: local mesh (owned elements first, then halo elements that only shape the pattern of owned rows),
+    local fields with LOCAL equation numbers, l2g (local -> global equation), n_owned_rows, ghost segments per owner."""
+    ne = len(conn)
+    order = morton_order(coords, conn) if order is None else np.asarray(order)
+    elem_owner = np.empty(ne, dtype=np.int64)
+    elem_owner[order] = np.arange(ne, dtype=np.int64) * world // ne
+    # row owner = lowest rank among the elements touching the row
+    row_owner = np.full(n_eqn, world, dtype=np.int64)
+    elem_rows = []
+    for f in fields:
+        er = f["eqn"][f["elem_dof"]].reshape(ne, -1)            # [ne, ndpe*ds] global equation numbers (or < 0)
+        elem_rows.append(er)
+        ok = er >= 0
+        np.minimum.at(row_owner, er[ok], np.broadcast_to(elem_owner[:, None], er.shape)[ok])
+    assert n_eqn == 0 or row_owner.max() < world, "an equation is touched by no element"
+    rows_all = np.concatenate(elem_rows, axis=1)
+    owned_e = np.nonzero(elem_owner == rank)[0]
+    touches_owned = ((rows_all >= 0) & (row_owner[np.maximum(rows_all, 0)] == rank)).any(axis=1)
+    halo_e = np.nonzero(touches_owned & (elem_owner != rank))[0]
+    local_e = np.concatenate([owned_e, halo_e])
+    # local nodes
+    nodes = np.unique(conn[local_e])
+    g2l_node = np.full(len(coords), -1, dtype=np.int64); g2l_node[nodes] = np.arange(len(nodes))
+    out = dict(coords=np.ascontiguousarray(coords[nodes]), conn=np.ascontiguousarray(g2l_node[conn[local_e]].astype(np.int32)),
+               n_owned_elems=len(owned_e), elements=local_e, fields=[])
+    # local equation numbering: owned rows (ascending), ghost rows grouped by owner (ascending), halo-only ids
+    touched_by_owned = np.unique(rows_all[owned_e][rows_all[owned_e] >= 0])
+    touched_local = np.unique(rows_all[local_e][rows_all[local_e] >= 0])
+    owned_rows = np.nonzero(row_owner == rank)[0]
+    assert np.isin(owned_rows, touched_local).all()
+    ghost = touched_by_owned[row_owner[touched_by_owned] != rank]
+    ghost = ghost[np.lexsort((ghost, row_owner[ghost]))]
+    rest = np.setdiff1d(touched_local, np.concatenate([owned_rows, ghost]))
+    l2g = np.concatenate([owned_rows, ghost, rest]).astype(np.int64)
+    g2l = np.full(n_eqn, -1, dtype=np.int64); g2l[l2g] = np.arange(len(l2g))
+    for f, er in zip(fields, elem_rows):
+        objs = np.unique(f["elem_dof"][local_e])
+        g2l_obj = np.full(len(f["eqn"]), -1, dtype=np.int64); g2l_obj[objs] = np.arange(len(objs))
+        eq = f["eqn"][objs]
+        leq = np.where(eq >= 0, g2l[np.maximum(eq, 0)], -1)
+        out["fields"].append(dict(fe_deg=f["fe_deg"], ds=f["ds"], n_obj=len(objs),
+                                  elem_dof=np.ascontiguousarray(g2l_obj[f["elem_dof"][local_e]].astype(np.int32)),
+                                  eqn=np.ascontiguousarray(leq.astype(np.int64)), status=np.ascontiguousarray(f["status"][objs]),
+                                  presc=np.ascontiguousarray(f["presc"][objs]), values=np.ascontiguousarray(f["values"][objs])))
+    owners = row_owner[ghost]
+    out.update(l2g=l2g, n_eqn_local=len(l2g), n_owned_rows=len(owned_rows), n_ghost_rows=len(ghost),
+               ghost_segments=[(int(r), int(np.searchsorted(owners, r, "left")) + len(owned_rows),
+                                int(np.searchsorted(owners, r, "right")) + len(owned_rows)) for r in np.unique(owners)],
+               n_eqn_global=int(n_eqn))
+    return out
+
+
+class GeneralExchange:
+    """Ghost rows -> owners for general_partition(): every rank sends, per owner, one contiguous slice of its CSR values
+    and of its rhs; the owner adds them at positions found once from the (global row, global column) keys.
+    Point-to-point (batch_isend_irecv), so it runs on gloo (CPU tensors) and nccl (CUDA tensors)."""
+
+    def __init__(self, rank, world, wl):
+        self.rank, self.world, self.wl = rank, world, wl
+        self.send = []   # (dst, val slice, row slice)
+        self.recv = []   # (src, positions in val, local rows)
+
+    def setup(self, rowptr, col):
+        dev = rowptr.device
+        l2g = torch.from_numpy(self.wl["l2g"]).to(dev)
+        g2l = torch.full((self.wl["n_eqn_global"],), -1, dtype=torch.int64, device=dev)
+        g2l[l2g] = torch.arange(len(l2g), device=dev)
+        # who sends to whom, and how much: exchange (n_entries, n_rows) for every ordered pair via all_gather
+        mine = torch.zeros(self.world, 2, dtype=torch.int64, device=dev)
+        keys = {}
+        for dst, lo, hi in self.wl["ghost_segments"]:
+            a, b = int(rowptr[lo]), int(rowptr[hi])
+            counts = rowptr[lo + 1:hi + 1] - rowptr[lo:hi]
+            rows = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int64), counts)
+            keys[dst] = torch.stack([l2g[rows], l2g[col[a:b].to(torch.int64)]])
+            mine[dst, 0], mine[dst, 1] = b - a, hi - lo
+            self.send.append((dst, (a, b), (lo, hi)))
+        table = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(table, mine)
+        ops, rbuf = [], {}
+        for dst, _, (lo, hi) in self.send:
+            ops.append(dist.P2POp(dist.isend, keys[dst].contiguous(), dst))
+            ops.append(dist.P2POp(dist.isend, l2g[lo:hi].contiguous(), dst))
+        for src in range(self.world):
+            n_ent, n_rows = int(table[src][self.rank, 0]), int(table[src][self.rank, 1])
+            if src == self.rank or n_rows == 0:
+                continue
+            rbuf[src] = (torch.zeros(2, n_ent, dtype=torch.int64, device=dev), torch.zeros(n_rows, dtype=torch.int64, device=dev))
+            ops.append(dist.P2POp(dist.irecv, rbuf[src][0], src))
+            ops.append(dist.P2POp(dist.irecv, rbuf[src][1], src))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for src, (k, grows) in rbuf.items():
+            r, c = g2l[k[0]], g2l[k[1]]
+            if bool((r < 0).any()) or bool((r >= self.wl["n_owned_rows"]).any()):
+                raise RuntimeError("received a row this rank does not own")
+            start, end = rowptr[r], rowptr[r + 1]
+            pos = torch.full_like(r, -1)
+            width = int((end - start).max()) if r.numel() else 0
+            for j in range(width):
+                idx = start + j
+                ok = (idx < end) & (pos < 0)
+                hit = ok & (col[torch.where(ok, idx, start)].to(torch.int64) == c)
+                pos = torch.where(hit, idx, pos)
+            if bool((pos < 0).any()):
+                raise RuntimeError("ghost entry missing in the owner's pattern (halo elements not registered?)")
+            self.recv.append((src, pos.contiguous(), g2l[grows].contiguous()))
+        return self
+
+    def exchange(self, val, rhs, add_fn=None):
+        ops, bufs = [], []
+        for dst, (a, b), (lo, hi) in self.send:
+            ops += [dist.P2POp(dist.isend, val[a:b], dst), dist.P2POp(dist.isend, rhs[lo:hi], dst)]
+        for src, pos, rows in self.recv:
+            bv = torch.empty(pos.numel(), dtype=val.dtype, device=val.device)
+            br = torch.empty(rows.numel(), dtype=val.dtype, device=val.device)
+            bufs.append((pos, rows, bv, br))
+            ops += [dist.P2POp(dist.irecv, bv, src), dist.P2POp(dist.irecv, br, src)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for pos, rows, bv, br in bufs:
+            if add_fn is not None:
+                add_fn(pos, bv, rows, br)
+            else:
+                val.index_add_(0, pos, bv)
+                rhs.index_add_(0, rows, br)
+
+
+class GeneralDistributedAssembly:
+    """general_partition() bound to an Engine (one process per GPU): local mesh / fields on the device, ghost-row
+    exchange with the engine's scatter-add kernels on the engine stream"""
+
+    def __init__(self, eng, wl, rank, world, shape, geom_deg):
+        self.eng, self.wl = eng, wl
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.ExternalStream(eng.stream, device=self.device)
+        self.plan = GeneralExchange(rank, world, wl)
+        eng.set_mesh(shape, geom_deg, wl["coords"], wl["conn"])
+        eng.set_owned_elements(wl["n_owned_elems"])
+        for i, f in enumerate(wl["fields"]):
+            eng.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+
+    def setup_exchange(self):
+        with torch.cuda.stream(self.stream):
+            n, nnz = self.eng.finish_assembly()
+            rp, col, val, rhs = self.eng.device_csr()
+            self.val = wrap_device(val, nnz, torch.float64, self.device)
+            self.rhs = wrap_device(rhs, n, torch.float64, self.device)
+            self.plan.setup(wrap_device(rp, n + 1, torch.int64, self.device), wrap_device(col, nnz, torch.int32, self.device))
+            self.stream.synchronize()
+
+    def _add(self, pos, bv, rows, br):
+        self.eng.unpack_add_entries(0, pos.data_ptr(), pos.numel(), bv.data_ptr())
+        self.eng.unpack_add_entries(1, rows.data_ptr(), rows.numel(), br.data_ptr())
+
+    def exchange(self):
+        with torch.cuda.stream(self.stream):
+            self.plan.exchange(self.val, self.rhs, add_fn=self._add)

@@ -18,3 +18,16 @@ def test_two_gpu_slab_assembly_matches_single_gpu():
            "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_check.py"), "12"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 4), ("laplace_q1_hex", 10)])
+def test_two_gpu_general_partition_matches_oracle(name, n):
+    """general element-block partition (Morton blocks of a permuted mesh, several fields, all-to-all ghost exchange)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(root, "tests", "dist_check_general.py"), name, str(n)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "DIST_CHECK_GENERAL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -1,5 +1,6 @@
-"""Multi-GPU host logic on CPU: world_size-2 gloo run of the slab partition + ghost-row exchange, with the oracle
-standing in for the device assembly.  The owned rows of both ranks must equal the global single-process assembly."""
+"""Multi-GPU host logic on CPU: gloo runs (world 2 and 3) of the slab partition and of the general element-block
+partition (any mesh, several fields, Stokes blocks) with their ghost-row exchange, the oracle standing in for the device
+assembly.  The owned rows of all ranks must equal the global single-process assembly."""
 import os
 import socket
 
@@ -74,3 +75,75 @@ def test_slab_partition_matches_global_assembly(world, e):
         assert np.abs(o["val"] - val[rp[lo]:rp[hi]]).max() <= 1e-13 * scale
         assert np.abs(o["rhs"] - rhs[lo:hi]).max() <= 1e-13 * max(np.abs(rhs).max(), 1e-300)
     assert rows_seen == len(rhs)
+
+
+# ---- general element-block partition (any mesh, several fields, all-to-all ghost exchange) ---------------------------
+def _general_local_system(case, wl):
+    """local CSR of one rank with the oracle: pattern from owned + halo elements, values from the owned elements"""
+    conn = wl["conn"].astype(np.int64)
+    no = wl["n_owned_elems"]
+    full = orc.Problem(case.shape, case.geom_deg, wl["coords"], conn)
+    own = orc.Problem(case.shape, case.geom_deg, wl["coords"], conn[:no])
+    for i, f in enumerate(wl["fields"]):
+        ed = f["elem_dof"].astype(np.int64)
+        full.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], ed, f["eqn"], f["status"], f["presc"], f["values"])
+        own.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], ed[:no], f["eqn"], f["status"], f["presc"], f["values"])
+    s = orc.System(wl["n_eqn_local"])
+    for op in case.ops:
+        if op[0] == "matrix":
+            s.register_fields(full, op[4], op[5])
+    for op in case.ops:
+        if op[0] == "matrix":
+            s.stiffness(own, op[1], op[2], op[3], op[4], op[5], incremental=op[6], nthreads=1)
+        elif op[0] == "residual":
+            s.residual(own, op[1], op[2], op[3], op[4], op[5])
+        elif op[0] == "body":
+            s.bodyforce(own, op[1], op[2], op[3])
+    return s.finish()
+
+
+def _general_worker(rank, world, port, name, n, out):
+    from tests import flows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = flows.build_case(name, n, True, True)     # perturbed nodes, permuted element order
+    wl = partition.general_partition(case.coords, case.conn, case.fields, case.n_eqn, rank, world)
+    rp, col, val, rhs = _general_local_system(case, wl)
+    t = [torch.from_numpy(a) for a in (rp, col, val, rhs)]
+    plan = partition.GeneralExchange(rank, world, wl).setup(t[0], t[1])
+    plan.exchange(t[2], t[3])
+    no, l2g = wl["n_owned_rows"], wl["l2g"]
+    out[rank] = dict(rows=l2g[:no].copy(), rowptr=rp[:no + 1].copy(), gcol=l2g[col[:rp[no]]].copy(),
+                     val=t[2].numpy()[:rp[no]].copy(), rhs=t[3].numpy()[:no].copy(), n_halo=len(wl["elements"]) - wl["n_owned_elems"],
+                     n_ghost=wl["n_ghost_rows"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,name,n", [(2, "laplace_q1_hex", 4), (3, "laplace_p1_tet", 4), (3, "stvenant_q1_hex", 3),
+                                          (2, "stokes_p2p1_tet", 2)])
+def test_general_partition_matches_global_assembly(world, name, n):
+    from tests import flows
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_general_worker, args=(world, port, name, n, out), nprocs=world, join=True)
+    case = flows.build_case(name, n, True, True)
+    rp, col, val, rhs = case.run_oracle(register=True)
+    seen = np.zeros(case.n_eqn, dtype=int)
+    scale, rscale = np.abs(val).max(), max(np.abs(rhs).max(), 1e-300)
+    assert sum(out[r]["n_ghost"] for r in range(world)) > 0 and sum(out[r]["n_halo"] for r in range(world)) > 0
+    for r in range(world):
+        o = out[r]
+        for k, g in enumerate(o["rows"]):
+            seen[g] += 1
+            a, b = o["rowptr"][k], o["rowptr"][k + 1]
+            order = np.argsort(o["gcol"][a:b])
+            assert np.array_equal(o["gcol"][a:b][order], col[rp[g]:rp[g + 1]]), "pattern of an owned row differs"
+            if b > a:  # (rows that only couple to constrained DoFs are empty)
+                assert np.abs(o["val"][a:b][order] - val[rp[g]:rp[g + 1]]).max() <= 1e-13 * scale
+            assert abs(o["rhs"][k] - rhs[g]) <= 1e-13 * rscale
+    assert np.all(seen == 1), "every equation must be owned by exactly one rank"
