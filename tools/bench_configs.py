@@ -79,8 +79,32 @@ def run(name, n, steps, warmup, perturb=True):
                     "booked to the following call"}
 
 
+DRIVER_TYPE = {"laplace_q1_hex": "laplace_q1_hex", "stvenant_q2_hex": "solid_q2_hex", "neohooke_p2_tet": "solid_p2_tet",
+               "stokes_p2p1_tet": "stokes_p2p1_tet", "vector_laplace_q1_hex": "vector_laplace_q1_hex",
+               "neohooke_q1_hex": "solid_q1_hex", "stvenant_q1_hex": "solid_q1_hex", "laplace_q2_hex": "laplace_q2_hex",
+               "laplace_p1_tet": "laplace_p1_tet", "stokes_q2q1_hex": "stokes_q2q1_hex"}
+
+
+def run_cpu_reference(name, n, steps, perturb=True):
+    """the same case assembled by the UNMODIFIED reference on the host cores (oracle/_ref/ref_driver_omp: OpenMP,
+    pre-structured triplets; residual / body-force loops are serial in the reference)"""
+    import tempfile
+    from tests import flows
+    from tools import make_ref_goldens as G
+    G.DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver_omp")
+    c = flows.build_case(name, n, perturb, False)
+    with tempfile.TemporaryDirectory() as wd:
+        log = G.run_reference(c, DRIVER_TYPE[name], True, wd, repeat=steps, dump=False)["log"]
+    reps = [l.split() for l in log.splitlines() if l.startswith("rep ")]
+    t = [float(r[r.index("assemble") + 1]) for r in reps]
+    ne = int(c.conn.shape[0])
+    return {"case": name, "n": n, "impl": "reference (unmodified headers + oracle/compat stand-ins)", "cores": os.cpu_count(),
+            "n_elems": ne, "n_eqn": int(c.n_eqn), "ms_per_step": 1e3 * sum(t) / len(t), "elements_per_s": ne / (sum(t) / len(t))}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--cpu-reference", action="store_true", help="time the reference on the host cores instead of the engine")
     ap.add_argument("--case", default=None)
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
@@ -89,7 +113,10 @@ def main():
     args = ap.parse_args()
     cases = DEFAULT if args.case is None else [(args.case, args.n or 16)]
     for name, n in cases:
-        print(json.dumps(run(name, args.n or n, args.steps, args.warmup, not args.structured)), flush=True)
+        if args.cpu_reference:
+            print(json.dumps(run_cpu_reference(name, args.n or n, max(1, min(args.steps, 3)), not args.structured)), flush=True)
+        else:
+            print(json.dumps(run(name, args.n or n, args.steps, args.warmup, not args.structured)), flush=True)
 
 
 if __name__ == "__main__":
