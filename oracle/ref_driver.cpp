@@ -395,6 +395,8 @@ int main(int argc, char* argv[]) {
     if (t == "solid_q2_hex") return runSingle<base::HEX, 2, 3, 4, 4, SOLID>(job);
     if (t == "solid_q1_quad") return runSingle<base::QUAD, 1, 2, 3, 3, SOLID>(job);
     if (t == "solid_p2_tet") return runSingle<base::TET, 2, 3, 4, 4, SOLID>(job);
+    if (t == "solid_q2_quad") return runSingle<base::QUAD, 2, 2, 3, 3, SOLID>(job);
+    if (t == "laplace_p1_tri") return runSingle<base::TRI, 1, 1, 2, 2, SCALAR>(job);
     if (t == "stokes_p2p1_tet") return runStokes<base::TET, 2, 4>(job);
     if (t == "stokes_q2q1_hex") return runStokes<base::HEX, 2, 4>(job);
     if (t == "stokes_q2q1_quad") return runStokes<base::QUAD, 2, 4>(job);

@@ -221,6 +221,23 @@ def build_case(name, n=4, perturb=True, permute=False):
         c.add_field(1, 2, dirichlet=lambda x: H.fund_sol_elastostatic(x, y0, d, lam, mu), values=smooth_u(2))
         c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0, True),
                  ("residual", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0)]
+    elif name == "stvenant_q2_quad":   # the element of reference/06-elastic/compressible.cpp (Q2 quads on Q1 geometry)
+        lam, mu = lame(1000.0, 0.25)
+        y0 = np.full(2, -0.1); d = np.array([0., 1.])
+        c = Case(E.QUAD, 1, *make_mesh(E.QUAD, n, perturb, permute))
+        c.add_field(2, 2, dirichlet=lambda x: H.fund_sol_elastostatic(x, y0, d, lam, mu), values=smooth_u(2))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0, True),
+                 ("residual", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0)]
+    elif name == "laplace_p1_tri":
+        c = Case(E.TRI, 1, *make_mesh(E.TRI, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, np.full(2, -0.5)), values=lambda x: 0.2 * x[:, 1:2])
+        c.ops = [("matrix", E.K_LAPLACE, [0.5], 2, 0, 0, False), ("residual", E.K_LAPLACE, [0.5], 2, 0, 0), ("body", [2.0], 2, 0)]
+    elif name == "stvenant_p2_tet":
+        lam, mu = lame(1000.0, 0.3)
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, values=lambda x: 0.03 * np.sin(np.pi * x))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0, True), ("residual", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0),
+                 ("body", [0.0, 0.0, -9.81], 4, 0)]
     elif name == "neohooke_p2_tet":
         lam, mu = lame(1000.0, 0.3)
         c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))

@@ -47,6 +47,9 @@ CASES = [
     ("stokes_p2p1_tet_n3", "stokes_p2p1_tet", "stokes_p2p1_tet", 3, True, False, True),
     ("stokes_q2q1_hex_n2", "stokes_q2q1_hex", "stokes_q2q1_hex", 2, True, False, False),
     ("stokes_q2q1_quad_n4", "stokes_q2q1_quad", "stokes_q2q1_quad", 4, True, False, True),
+    ("stvenant_q2_quad_n4", "stvenant_q2_quad", "solid_q2_quad", 4, True, False, True),
+    ("laplace_p1_tri_n6", "laplace_p1_tri", "laplace_p1_tri", 6, True, True, False),
+    ("stvenant_p2_tet_n3", "stvenant_p2_tet", "solid_p2_tet", 3, True, False, False),
     # general linear constraints (slave DoFs with weighted ACTIVE masters, asmb/assembleMatrix.hpp:212-338)
     ("laplace_q1_hex_linear_n5", "laplace_q1_hex_linear", "laplace_q1_hex", 5, True, False, False),
     ("laplace_q1_hex_linear_n4_reg", "laplace_q1_hex_linear", "laplace_q1_hex", 4, False, False, True),
