@@ -482,6 +482,8 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
     }
 }
 
+#include "isl_tangent_tiled.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // specialised hot path: Q1 hex geometry, Q1 scalar field, Laplace, 2x2x2 Gauss rule (BASELINE config 2).
 // One thread per element; symmetric 8x8 local matrix (36 accumulators) in registers; scatter through the
@@ -738,6 +740,7 @@ struct isl_engine {
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
+    int tangent_tiled = 0;      // ISL_TANGENT_TILED=1: register-tiled hyperelastic tangent (isl_tangent_tiled.cuh; not yet default)
 
     int grid_for(int64_t n, int block) const {
         const int64_t g = (n + block - 1) / block;
@@ -1401,6 +1404,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_MODE")) h->q1_mode = (std::string(m) == "atomic") ? 0 : 1;
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m);  // 0 reference order, 1 sum factorisation, 3 + affine shortcut
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
         if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
@@ -1678,6 +1682,10 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT);
         p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : 0;
+        if (h->tangent_tiled && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == h->dim) {
+            if (h->dim == 3) launch_staged(h, k_tangent_hypel_tiled<3>, p); else launch_staged(h, k_tangent_hypel_tiled<2>, p);
+            return;
+        }
         if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
     });
 }

@@ -105,3 +105,25 @@ def test_engine_constraint_scatter_equals_reference_semantics(emu, name, n, incr
         scale = max(np.abs(vals).max(), 1.0)
         assert np.abs(val[:nnz] - vals).max() <= 1e-13 * scale
         assert np.abs(rhs - b).max() <= 1e-13 * max(np.abs(b).max(), 1.0)
+
+
+# ---- register-tiled hyperelastic tangent (isl_tangent_tiled.cuh), per-thread routine replayed on the host ------------
+@pytest.mark.parametrize("dim,nq,nt,nc", [(3, 27, 27, 27), (3, 11, 10, 10), (3, 8, 8, 8), (2, 4, 9, 9), (3, 5, 7, 4)])
+def test_tiled_hyperelastic_tangent_equals_defining_formula(dim, nq, nt, nc):
+    src = os.path.join(ROOT, "tests", "emu", "tangent_tiled_emu.cpp")
+    lib_path = os.path.join(ROOT, "tests", "emu", "_build", "libtangent_tiled_emu.so")
+    deps = [src, os.path.join(ROOT, "insilico_b200", "csrc", "isl_tangent_tiled.cuh")]
+    os.makedirs(os.path.dirname(lib_path), exist_ok=True)
+    if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", "-Wall",
+                        "-o", lib_path, src], check=True)
+    lib = ctypes.CDLL(lib_path)
+    rng = np.random.default_rng(dim * 100 + nt)
+    Gt, Gc = rng.standard_normal((nq, nt, dim)), rng.standard_normal((nq, nc, dim))
+    Q = rng.standard_normal((nq, 3, 3, 3, 3))            # Ceff[i, J, k, L], stride 3 also in 2-D
+    det, w = rng.random(nq) + 0.5, rng.random(nq)
+    K = np.zeros((nt * dim, nc * dim))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib.emu_hypel_tile(dim, P(Gt), P(Gc), P(np.ascontiguousarray(Q)), P(det), P(w), nq, nt, nc, P(K))
+    ref = np.einsum("q,qmJ,qiJkL,qnL->mink", det * w, Gt, Q[:, :dim, :dim, :dim, :dim], Gc).reshape(nt * dim, nc * dim)
+    assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max()

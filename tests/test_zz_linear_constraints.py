@@ -157,3 +157,14 @@ def test_device_cg_equals_sparse_direct_solve(name, n):
     ref = spla.spsolve(sp.csr_matrix((val, col, rp)).tocsc(), rhs)
     assert 0 < it <= 2 * c.n_eqn and err < 1e-12
     assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@experimental
+@pytest.mark.parametrize("name,n", [("stvenant_q2_hex", 3), ("neohooke_p2_tet", 3), ("neohooke_q1_hex", 5), ("stvenant_q1_quad", 6),
+                                    ("stvenant_q1_hex_linear", 4)])
+def test_register_tiled_hyperelastic_tangent_equals_oracle(monkeypatch, name, n):
+    """k_tangent_hypel_tiled (ISL_TANGENT_TILED=1, csrc/isl_tangent_tiled.cuh)"""
+    monkeypatch.setenv("ISL_TANGENT_TILED", "1")
+    res = flows.run_case(name, n=n, perturb=True)
+    assert res["pattern_equal"] and res["val_diff"] <= 1e-12 and res["rhs_diff"] <= 1e-12, res

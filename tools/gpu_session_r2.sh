@@ -8,7 +8,7 @@ export PYTHONUNBUFFERED=1
 {
 echo "== 1. GPU test suite"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
 echo "== 2. experimental: row-gather kernels, device CG"; ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -k rowgather 2>&1 | tail -8
-ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_linear_constraints.py -q -m gpu -k "cg" 2>&1 | tail -8
+ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_linear_constraints.py -q -m gpu -k "cg or tiled" 2>&1 | tail -8
 echo "== 3. default bench"; timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_default.json 2> $O/bench_default.err; tail -c 1500 $O/bench_default.json
 echo "== 4. row-gather sweep (kernel only)"
 for ss in 0 1; do for nt in 256 320 192 128; do for pr in 192 256 320; do for st in 1 2 4; do
@@ -21,7 +21,9 @@ for l in sys.stdin:
         d = json.loads(l); print('%.3f ms/step  frac %.3f  perturbed %.3f ms' % (d['ms_per_step'], d['roofline']['frac'], d['config'].get('ms_per_step_perturbed_mesh') or -1))
 "
 done; done; done; done
-echo "== 5. other configs (generic kernels)"; timeout 900 python tools/bench_configs.py 2>&1 | tail -12
+echo "== 5. other configs (generic kernels), then with the register-tiled hyperelastic tangent"; timeout 900 python tools/bench_configs.py 2>&1 | tail -12
+ISL_TANGENT_TILED=1 timeout 600 python tools/bench_configs.py --case stvenant_q2_hex --n 24 2>&1 | tail -2
+ISL_TANGENT_TILED=1 timeout 600 python tools/bench_configs.py --case neohooke_p2_tet --n 24 2>&1 | tail -2
 echo "== 6. launch list of the default bench"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_default.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launch.log 2>&1; tail -3 $O/ncu_launch.log
