@@ -20,6 +20,8 @@ def test_two_gpu_slab_assembly_matches_single_gpu():
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+@pytest.mark.skipif(not os.environ.get("ISL_TEST_EXPERIMENTAL"),
+                    reason="general partition on GPUs has not run yet (CPU/gloo-verified); set ISL_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 4), ("laplace_q1_hex", 10)])
 def test_two_gpu_general_partition_matches_oracle(name, n):
     """general element-block partition (Morton blocks of a permuted mesh, several fields, all-to-all ghost exchange)"""

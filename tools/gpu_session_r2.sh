@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2 (round 1 ended without GPU minutes for the last session):
 #   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session_r2.sh'
+# With 2 GPUs (gpurun --gpus 2) also: ISL_TEST_EXPERIMENTAL=1 python -m pytest tests/test_multigpu.py -q   (general partition)
 # Everything lands in gpurun_out/r2/.  Steps are independent: a failing one does not stop the others.
 mkdir -p gpurun_out/r2
 O=gpurun_out/r2
