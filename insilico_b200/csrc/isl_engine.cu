@@ -1429,6 +1429,22 @@ int isl_engine_destroy(isl_handle h) {
         cudaStreamDestroy(s);
     });
 }
+int isl_engine_set_option(isl_handle h, const char* name, double value) {
+    return guarded([&] {
+        flush_pending(h);
+        const std::string n(name ? name : "");
+        const int v = (int)value;
+        if (n == "q1_rows") h->q1_rows = v ? 1 : 0;               // only useful when the engine was created with ISL_Q1_ROWS=1
+        else if (n == "rows_threads") h->rows_threads = v;
+        else if (n == "rows_ss") h->rows_ss = v ? 1 : 0;
+        else if (n == "affine_kernel") h->affine_kernel = v ? 1 : 0;
+        else if (n == "aff_split") h->aff_split = v ? 1 : 0;
+        else if (n == "aff_threads") h->patch_threads_aff = v;
+        else if (n == "tangent_tiled") h->tangent_tiled = v ? 1 : 0;
+        else if (n == "defer") h->defer_launch = v ? 1 : 0;
+        else throw IslError("unknown option '" + n + "'");
+    });
+}
 int isl_synchronize(isl_handle h) { return guarded([&] { flush_pending(h); ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
 void* isl_engine_stream(isl_handle h) { return (void*)h->stream; }
 int64_t isl_kernel_launches(isl_handle h) { return h->launches; }

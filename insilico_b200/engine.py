@@ -30,7 +30,8 @@ SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
 
 # every symbol include/insilico_b200.h declares (checked by tests/test_cabi.py)
 EXPORTED = [
-    "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_synchronize", "isl_engine_stream",
+    "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_engine_set_option", "isl_synchronize",
+    "isl_engine_stream",
     "isl_kernel_launches", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
@@ -188,6 +189,10 @@ class Engine:
         self.h = C.c_void_p()
         _chk(lib().isl_engine_create(int(device), C.byref(self.h)))
         self.n_eqn = 0
+
+    def set_option(self, name, value):
+        """kernel-selection knob (see isl_engine_set_option)"""
+        _chk(lib().isl_engine_set_option(self.h, name.encode(), C.c_double(float(value))))
 
     def close(self):
         if self.h:

@@ -11,17 +11,9 @@ echo "== 1. GPU test suite"; timeout 1500 python -m pytest tests -m gpu -q -x 2>
 echo "== 2. experimental: row-gather kernels, device CG"; ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_parity_gpu.py -q -k rowgather 2>&1 | tail -8
 ISL_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_linear_constraints.py -q -m gpu -k "cg or tiled" 2>&1 | tail -8
 echo "== 3. default bench"; timeout 600 python bench.py --steps 10 --warmup 3 > $O/bench_default.json 2> $O/bench_default.err; tail -c 1500 $O/bench_default.json
-echo "== 4. row-gather sweep (kernel only)"
-for ss in 0 1; do for nt in 256 320 192 128; do for pr in 192 256 320; do for st in 1 2 4; do
-  echo -n "ROWS ss=$ss threads=$nt patch_rows=$pr stretch=$st : "
-  ISL_Q1_ROWS=1 ISL_ROWS_SS=$ss ISL_ROWS_THREADS=$nt ISL_PATCH_ROWS=$pr ISL_PATCH_STRETCH=$st timeout 300 \
-    python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d = json.loads(l); print('%.3f ms/step  frac %.3f  perturbed %.3f ms' % (d['ms_per_step'], d['roofline']['frac'], d['config'].get('ms_per_step_perturbed_mesh') or -1))
-"
-done; done; done; done
+echo "== 4. row-gather sweep in one process (structured, then perturbed mesh)"
+timeout 900 python tools/sweep_rows.py --n 256 --steps 10 2>&1 | tail -90
+timeout 600 python tools/sweep_rows.py --n 256 --steps 10 --perturbed --patch-rows 192,256 --stretch 1,2 --threads 256,128 2>&1 | tail -40
 echo "== 5. other configs (generic kernels), then with the register-tiled hyperelastic tangent"; timeout 900 python tools/bench_configs.py 2>&1 | tail -12
 ISL_TANGENT_TILED=1 timeout 600 python tools/bench_configs.py --case stvenant_q2_hex --n 24 2>&1 | tail -2
 ISL_TANGENT_TILED=1 timeout 600 python tools/bench_configs.py --case neohooke_p2_tet --n 24 2>&1 | tail -2
