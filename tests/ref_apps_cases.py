@@ -13,6 +13,10 @@ CASES = {
     "linearElastic3D_cube008": ("linearElastic3D", ["cube.008.smf"], ["cube.008.smf"]),
     "compressible_quad010": ("compressible", ["quad.010.smf", "inputCompRefD.dat"],       # 06-elastic/compressible.cpp
                              ["quad.010.smf", "inputCompRefD.dat"]),
+    # the same problem through the reference's driver facade (solid/CompressibleDriver.hpp, base/BoundaryValueProblem.hpp):
+    # prints the number of Newton iterations per load step
+    "compressibleWithDriver_quad010": ("compressibleWithDriver", ["quad.010.smf", "inputCompRefD.dat"],
+                                       ["quad.010.smf", "inputCompRefD.dat"]),
     # traction controlled: asmb::neumannForceComputation runs in the reference's own code and reaches the solver
     # through insertToRHS (the host-side "odd contribution" interface)
     "compressible_neumann_quad010": ("compressible", ["quad.010.smf", "inputCompRefN.dat"],
