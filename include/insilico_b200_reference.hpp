@@ -660,6 +660,20 @@ private:
 //------------------------------------------------------------------------------------------------------------------
 namespace asmb {
 
+/** Guard against a silent host path.  The overloads below must be VISIBLE WHERE THE CALL IS WRITTEN: the reference
+ *  calls `base::asmb::stiffnessMatrixComputation<FTB>(...)` with a qualified name, so inside its own templates
+ *  (base/BoundaryValueProblem.hpp:271, the drivers) only overloads declared before that header are considered.  If this
+ *  binding is included too late, the reference's generic version would run its element loop on the host and feed the
+ *  engine through insertToLHS -- correct numbers, but a CPU assembly.  The generic version instantiates this functor, so
+ *  the misuse is a compile error instead: include this header first (e.g. `g++ -include insilico_b200_reference.hpp`). */
+template <typename QUAD, typename FIELDTUPLE>
+class StiffnessMatrix<QUAD, base::solver::B200, FIELDTUPLE> {
+    static_assert(sizeof(QUAD) == 0,
+                  "base::asmb::StiffnessMatrix<..., base::solver::B200, ...>: the reference's host element loop was selected for "
+                  "the B200 solver. Include insilico_b200_reference.hpp BEFORE the reference headers that call "
+                  "stiffnessMatrixComputation (compile with -include insilico_b200_reference.hpp); the engine has no CPU fallback.");
+};
+
 namespace b200_detail {
 template <typename FIELDTUPLEBINDER, typename FIELDBINDER>
 typename FIELDTUPLEBINDER::Tuple probeTuple(const FIELDBINDER& fb, bool last) {

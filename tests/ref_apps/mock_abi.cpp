@@ -7,6 +7,8 @@
 // On the GPU the same applications link the real library.  Never shipped, never linked by the product.
 #include <cstdint>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,6 +49,15 @@ struct isl_engine {
     std::vector<double> solution;  // rhs after isl_solve_cg
 };
 static std::string g_err;
+// ISL_MOCK_TRACE=1: count the ABI calls and print them at exit (which path did the application take?)
+static long g_calls[6] = {0, 0, 0, 0, 0, 0};  // assemble_matrix, assemble_residual, assemble_bodyforce, insert_lhs, insert_rhs, solve_cg
+static struct TraceAtExit {
+    ~TraceAtExit() {
+        if (std::getenv("ISL_MOCK_TRACE"))
+            std::fprintf(stderr, "[mock abi] assemble_matrix %ld  assemble_residual %ld  assemble_bodyforce %ld  insert_lhs %ld  insert_rhs %ld  solve_cg %ld\n",
+                         g_calls[0], g_calls[1], g_calls[2], g_calls[3], g_calls[4], g_calls[5]);
+    }
+} g_trace;
 static int fail(const std::string& m) { g_err = m; return 1; }
 
 extern "C" {
@@ -122,19 +133,23 @@ int isl_system_create(isl_handle h, int64_t n) {
 }
 int isl_pattern_register(isl_handle h, int t, int c) { orc_register_fields(h->sys, h->prob, t, c); return 0; }
 int isl_assemble_matrix(isl_handle h, int kid, const double* p, int q, int t, int c, int incr) {
+    g_calls[0]++;
     return orc_stiffness(h->sys, h->prob, kid, p, q, t, c, incr, 1) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_assemble_residual(isl_handle h, int kid, const double* p, int q, int t, int c, double factor) {
+    g_calls[1]++;
     if (factor != -1.0) return fail("mock ABI: residual factor must be -1");
     return orc_residual(h->sys, h->prob, kid, p, q, t, c) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_assemble_bodyforce(isl_handle h, const double* f, int q, int t) {
+    g_calls[2]++;
     return orc_bodyforce(h->sys, h->prob, f, q, t) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_insert_lhs(isl_handle h, const double* m, const int64_t* r, int nr, const int64_t* c, int nc) {
+    g_calls[3]++;
     return orc_insert_lhs(h->sys, m, r, nr, c, nc) ? fail(orc_system_error(h->sys)) : 0;
 }
-int isl_insert_rhs(isl_handle h, const double* v, const int64_t* r, int nr) { return orc_insert_rhs(h->sys, v, r, nr); }
+int isl_insert_rhs(isl_handle h, const double* v, const int64_t* r, int nr) { g_calls[4]++; return orc_insert_rhs(h->sys, v, r, nr); }
 int isl_finish(isl_handle h, int64_t* n, int64_t* nnz) {
     if (!h->finished) { orc_finish(h->sys); h->finished = true; }
     if (n) *n = h->n;
@@ -161,6 +176,7 @@ int isl_rhs_norm(isl_handle h, double* v) {
 }
 // Jacobi-preconditioned CG as in Eigen 3.2's ConjugateGradient.h (what isl_solve_cg does on the device)
 int isl_solve_cg(isl_handle h, double tol, int64_t maxIter, int64_t* iterations, double* error) {
+    g_calls[5]++;
     int64_t n = 0, nnz = 0;
     isl_finish(h, &n, &nnz);
     std::vector<int64_t> rp(n + 1); std::vector<int32_t> col(nnz); std::vector<double> val(nnz), b(n);

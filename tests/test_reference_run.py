@@ -216,3 +216,34 @@ def test_reference_api_on_binding_with_mock_abi(tmp_path, path):
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_reference_api_on_b200_engine(tmp_path, path):
     _driver_on_binding(path, "ref_driver", tmp_path)
+
+
+# ---- no silent host path: the applications must reach the engine's assembly entry points -----------------------------
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["dirichlet_tet6", "linearElastic3D_cube004", "compressible_quad010", "compressibleWithDriver_quad010"])
+def test_applications_use_the_assembly_entry_points_not_insert(tmp_path, name):
+    """ISL_MOCK_TRACE counts the ABI calls: the element matrices must come from isl_assemble_matrix; isl_insert_lhs
+    (the reference's own host element loop feeding the solver) must not be used at all."""
+    import re
+    exe, args = RA.prepare(name, str(tmp_path))
+    p = subprocess.run([os.path.join(APPS_B200, exe + "_mock")] + args, cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, ISL_MOCK_TRACE="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    m = re.search(r"assemble_matrix (\d+)\s+assemble_residual (\d+)\s+assemble_bodyforce (\d+)\s+insert_lhs (\d+)\s+insert_rhs (\d+)", p.stderr)
+    assert m, p.stderr[-500:]
+    n_matrix, n_res, n_body, n_ins_lhs, n_ins_rhs = map(int, m.groups())
+    assert n_matrix >= 1 and n_ins_lhs == 0 and n_ins_rhs == 0, m.group(0)
+
+
+@needs_ref
+def test_binding_included_too_late_is_a_compile_error(tmp_path):
+    """without `-include insilico_b200_reference.hpp` the reference's driver facade would select the reference's generic
+    host element loop for the B200 solver: the guard turns that into a compile error"""
+    src = os.path.join(REFERENCE, "reference", "06-elastic", "compressibleWithDriver.cpp")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-DNDEBUG", "-w", "-fsyntax-only", "-DSPACEDIM=2",
+           "-I" + os.path.join(ROOT, "tests", "ref_apps"), "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "oracle", "compat"), "-I" + REFERENCE, "-I" + os.path.dirname(src), src]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+    p = subprocess.run(cmd[:-1] + ["-include", "insilico_b200_reference.hpp", src], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
