@@ -137,6 +137,11 @@ int isl_assemble_residual(isl_handle h, int kernel_id, const double* params, int
 /* asmb::bodyForceComputation<FTB>(quad, solver, binder, f) with constant f[dof_size]
  * (base/asmb/BodyForce.hpp:65-84,172-205)                                                                   */
 int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int test_field);
+/* the same with a general f(x) (BodyForce.hpp:172-205 evaluates the caller's function at every quadrature point):
+ * values[n_elems * nq * dof_size] = f at the physical location x(xi_q) of every (owned) element and quadrature point
+ * of Quadrature<quad_deg> (isl_quadrature gives xi_q; x = sum_a N_a(xi_q) x_a), host or device pointer.  The caller's
+ * function runs on the host, the integration on the device.                                                       */
+int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_deg, int test_field);
 /* solver.insertToLHS / insertToRHS (Eigen3.hpp:81-124) for host-side odd contributions:
  * mat is row-major [n_rows*n_cols]; entries must exist in the registered pattern                            */
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols,

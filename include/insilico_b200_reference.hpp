@@ -47,6 +47,8 @@
 #include <base/asmb/ForceIntegrator.hpp>
 #include <base/asmb/BodyForce.hpp>
 #include <heat/Laplace.hpp>
+#include <heat/Static.hpp>
+#include <mat/thermal/IsotropicConstant.hpp>
 #include <fluid/VectorLaplace.hpp>
 #include <fluid/PressureGradient.hpp>
 #include <fluid/VelocityDivergence.hpp>
@@ -348,6 +350,27 @@ struct B200KernelTraits<heat::Laplace<TUPLE> > {
         const double p1 = b200_detail::probeScalar(b200_detail::probeTangent(k, t1), Make(), t1);
         VERIFY_MSG(std::abs(p1 - p[0]) <= 1e-13 * std::abs(p[0]),
                    "B200 engine: heat::Laplace with a non-constant conductivity function is not supported");
+        return ISL_K_LAPLACE;
+    }
+};
+
+//! heat::Static with the constant isotropic material (heat/Static.hpp:60-118, mat/thermal/IsotropicConstant.hpp) is the
+//! Laplace operator with conductivity kappa; used by heat::PoissonDriver
+template <typename TUPLE>
+struct B200KernelTraits<heat::Static<mat::thermal::IsotropicConstant, TUPLE> > {
+    struct Unit {   // kernel + the material it refers to
+        mat::thermal::IsotropicConstant material;
+        heat::Static<mat::thermal::IsotropicConstant, TUPLE> kernel;
+        explicit Unit(double c) : material(c), kernel(material) {}
+        Unit(const Unit& o) : material(o.material), kernel(material) {}
+        template <typename XI>
+        void tangentStiffness(const TUPLE& t, const XI& xi, double w, base::MatrixD& K) const { kernel.tangentStiffness(t, xi, w, K); }
+    };
+    struct Make {
+        Unit operator()(double c) const { return Unit(c); }
+    };
+    static int describe(const heat::Static<mat::thermal::IsotropicConstant, TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+        p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         return ISL_K_LAPLACE;
     }
 };
@@ -717,9 +740,12 @@ void computeResidualForces(const QUADRATURE&, base::solver::B200& solver, const 
                                    -1.0));
 }
 
-//! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200; the engine integrates constant body forces
+//! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200.  The caller's function f(x) runs on the host, once per
+//! element and quadrature point (as in BodyForce.hpp:172-205); the integration runs on the device.  A force that turns
+//! out to be the same at every point takes the constant entry point (fused with the stiffness launch on the Q1 path).
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
-void bodyForceComputation(const QUADRATURE&, base::solver::B200& solver, const FIELDBINDER& fieldBinder, const FUN& forceFun) {
+void bodyForceComputation(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                          const FUN& forceFun) {
     namespace D = base::solver::b200_detail;
     solver.verifyCurrent();
     typedef typename FIELDTUPLEBINDER::Tuple Tuple;
@@ -728,23 +754,31 @@ void bodyForceComputation(const QUADRATURE&, base::solver::B200& solver, const F
     if (fieldBinder.elementsBegin() == fieldBinder.elementsEnd()) return;
     D::synchronise(fieldBinder);
     const unsigned ds = TestElement::DegreeOfFreedom::size;
-    double f[3] = {0., 0., 0.};
-    // sample the force function at the centroids of the first, middle and last element: it has to be constant
     const std::size_t n = static_cast<std::size_t>(std::distance(fieldBinder.elementsBegin(), fieldBinder.elementsEnd()));
-    const std::size_t probes[3] = {0, n / 2, n - 1};
-    for (int k = 0; k < 3; k++) {
-        typename FIELDBINDER::FieldIterator it = fieldBinder.elementsBegin();
-        std::advance(it, probes[k]);
+    const std::size_t nq = static_cast<std::size_t>(std::distance(quadrature.begin(), quadrature.end()));
+    std::vector<double> values(n * nq * ds);
+    bool constant = true;
+    std::size_t e = 0;
+    typename FIELDBINDER::FieldIterator end = fieldBinder.elementsEnd();
+    for (typename FIELDBINDER::FieldIterator it = fieldBinder.elementsBegin(); it != end; ++it, ++e) {
         const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*it).geomElementPtr();
-        const typename FUN::result_type v =
-            forceFun(base::Geometry<GeomElement>()(gep, base::ShapeCentroid<GeomElement::shape>::apply()));
-        for (unsigned d = 0; d < ds; d++) {
-            if (k == 0) f[d] = v[d];
-            else VERIFY_MSG(v[d] == f[d], "B200 engine: only constant body forces are supported");
+        std::size_t q = 0;
+        for (typename QUADRATURE::Iter qIter = quadrature.begin(); qIter != quadrature.end(); ++qIter, ++q) {
+            const typename FUN::result_type v = forceFun(base::Geometry<GeomElement>()(gep, qIter->second));
+            for (unsigned d = 0; d < ds; d++) {
+                values[(e * nq + q) * ds + d] = v[d];
+                constant = constant && (v[d] == values[d]);
+            }
         }
     }
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
-    D::check(isl_assemble_bodyforce(D::engine(), f, D::QuadratureDegree<QUADRATURE>::value, TI::test));
+    if (constant) {
+        double f[3] = {0., 0., 0.};
+        for (unsigned d = 0; d < ds; d++) f[d] = values[d];
+        D::check(isl_assemble_bodyforce(D::engine(), f, D::QuadratureDegree<QUADRATURE>::value, TI::test));
+    } else {
+        D::check(isl_assemble_bodyforce_sampled(D::engine(), &values[0], D::QuadratureDegree<QUADRATURE>::value, TI::test));
+    }
 }
 
 }  // namespace asmb

@@ -107,6 +107,7 @@ struct AsmParams {
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
     int body; double f[3];
+    const double* fq;   // body == 2: force sampled at the quadrature points, [n_elems][nq][dst]
     // linear constraints with master DoFs (nullptr when the field has none): per DoF component k the masters
     // [cptr[k], cptr[k+1]) as equation numbers cm[] with weights cw[]; CSR pattern for the entries they reach
     const int32_t* cptr_t; const int32_t* cm_t; const double* cw_t;
@@ -441,7 +442,8 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
                 const double detJ = s.sDet[eq], w = p.w[q];
                 const double* qd = s.sQ + (size_t)eq * 9;
                 if (p.body) {
-                    acc += p.f[ci] * p.Nt[q * p.nt + M] * w * detJ;
+                    const double fc = (p.body == 2) ? p.fq[((size_t)e * p.nq + q) * p.dst + ci] : p.f[ci];
+                    acc += fc * p.Nt[q * p.nt + M] * w * detJ;
                     continue;
                 }
                 const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
@@ -1745,6 +1747,24 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
         for (int d = 0; d < h->fields[t].ds; d++) p.f[d] = f[d];
         p.need_gt = 0; p.need_gc = 0; p.nqdata = 0;
         if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
+    });
+}
+
+int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_deg, int t) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ISL_REQUIRE(t >= 0 && t < 5 && h->fields[t].set, "field not set");
+        ISL_REQUIRE(values != nullptr, "no force values");
+        flush_pending(h);
+        AsmParams p; std::memset(&p, 0, sizeof(p));
+        fill_common(h, p, quad_deg, t, t);
+        DevBuf<double> fq;   // host or device pointer
+        upload(h, fq, values, (size_t)h->n_owned * p.nq * h->fields[t].ds);
+        p.body = 2; p.factor = 1.0; p.fq = fq.p;
+        p.need_gt = 0; p.need_gc = 0; p.nqdata = 0;
+        if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
+        ISL_CUDA(cudaStreamSynchronize(h->stream));   // fq is released when this function returns
     });
 }
 

@@ -36,7 +36,8 @@ EXPORTED = [
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
-    "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_insert_lhs", "isl_insert_rhs",
+    "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
+    "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
     "isl_unpack_add_entries",
 ]
@@ -272,6 +273,11 @@ class Engine:
     def body_force_computation(self, f, quad_deg, test):
         f = np.ascontiguousarray(f, dtype=np.float64)
         _chk(lib().isl_assemble_bodyforce(self.h, _ptr(f), quad_deg, test))
+
+    def body_force_computation_sampled(self, values, quad_deg, test):
+        """asmb::bodyForceComputation<FTB> with a general f(x): values [n_elems, nq, ds] = f at the quadrature points"""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        _chk(lib().isl_assemble_bodyforce_sampled(self.h, _ptr(values), quad_deg, test))
 
     def insert_to_lhs(self, mat, rows, cols):
         mat = np.ascontiguousarray(mat, dtype=np.float64)

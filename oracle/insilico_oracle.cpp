@@ -1295,9 +1295,9 @@ static void stiffnessElement(const Problem& p, System& solver, const Quad& q, in
     assembleMatrix(K, rS, cS, rID, cID, cV, rCon, cCon, solver);
 }
 
-// asmb/ForceIntegrator.hpp:126-160
+// asmb/ForceIntegrator.hpp:126-160 ; body = 2: params holds f(x) sampled at the quadrature points, [nElems][nq][dofSize]
 static void forceElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
-                         int trialId, double factor, bool body, int64_t e) {
+                         int trialId, double factor, int body, int64_t e) {
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
     std::vector<uint8_t> st; std::vector<size_t> ids; std::vector<double> pv;
@@ -1305,7 +1305,8 @@ static void forceElement(const Problem& p, System& solver, const Quad& q, int ki
     if (!collectFromDoFs(test, e, st, ids, pv, con, false)) return;
     std::vector<double> f(ids.size(), 0.);
     for (int g = 0; g < q.n; g++) {
-        if (body) bodyForceKernel(t, params, &q.p[g * q.dim], q.w[g], f);
+        if (body == 2) bodyForceKernel(t, params + ((size_t)e * q.n + g) * test.dofSize, &q.p[g * q.dim], q.w[g], f);
+        else if (body) bodyForceKernel(t, params, &q.p[g * q.dim], q.w[g], f);
         else residualKernel(kid, params, t, &q.p[g * q.dim], q.w[g], f);
     }
     for (auto& x : f) x *= factor;
@@ -1507,14 +1508,14 @@ int orc_stiffness(void* s, void* h, int kid, const double* params, int quadDeg, 
 int orc_residual(void* s, void* h, int kid, const double* params, int quadDeg, int test, int trial) {
     Problem& p = *(Problem*)h; System& sys = *(System*)s;
     Quad q = makeQuadrature(p.mesh.shape, quadDeg);
-    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, kid, params, test, trial, -1.0, false, e);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, kid, params, test, trial, -1.0, 0, e);
     return sys.error.empty() ? 0 : -1;
 }
 // asmb/BodyForce.hpp:65-84 with f(x) = const vector f[dofSize]
 int orc_bodyforce(void* s, void* h, const double* f, int quadDeg, int test) {
     Problem& p = *(Problem*)h; System& sys = *(System*)s;
     Quad q = makeQuadrature(p.mesh.shape, quadDeg);
-    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, f, test, test, 1.0, true, e);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, f, test, test, 1.0, 1, e);
     return sys.error.empty() ? 0 : -1;
 }
 // solver::Eigen3::insertToLHS / insertToRHS (Eigen3.hpp:81-124) for contributions computed by the caller
@@ -1529,6 +1530,29 @@ int orc_insert_rhs(void* s, const double* vec, const int64_t* rows, int nRows) {
     System& sys = *(System*)s;
     for (int i = 0; i < nRows; i++) sys.b[(size_t)rows[i]] += vec[i];
     return 0;
+}
+// asmb/BodyForce.hpp:65-84 with a general f(x): values = f at x(xi_q) of every element and quadrature point
+int orc_bodyforce_sampled(void* s, void* h, const double* values, int quadDeg, int test) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, values, test, test, 1.0, 2, e);
+    return sys.error.empty() ? 0 : -1;
+}
+// physical coordinates of the quadrature points, [nElems][nq][dim] (base::Geometry, geometry.hpp:105-135)
+void orc_quadrature_points(void* h, int quadDeg, double* x) {
+    Problem& p = *(Problem*)h;
+    const Mesh& m = p.mesh;
+    Quad q = makeQuadrature(m.shape, quadDeg);
+    std::vector<double> N(m.npe);
+    for (int64_t e = 0; e < m.nElems; e++)
+        for (int g = 0; g < q.n; g++) {
+            m.geomFun.fun(&q.p[g * q.dim], N.data());
+            for (int d = 0; d < m.dim; d++) {
+                double v = 0.;
+                for (int a = 0; a < m.npe; a++) v += N[a] * m.X[(size_t)m.conn[e * m.npe + a] * m.dim + d];
+                x[((size_t)e * q.n + g) * m.dim + d] = v;
+            }
+        }
 }
 void orc_finish(void* s) { ((System*)s)->finishAssembly(); }
 int64_t orc_nnz(void* s) { return (int64_t)((System*)s)->col.size(); }

@@ -174,6 +174,13 @@ class Problem:
         lib().orc_set_field(self.h, fid, fe_deg, dof_size, C.c_int64(n_obj), _p(a["elem_dof"]), _p(a["eqn"]),
                             _p(a["status"]), _p(a["prescribed"]), _p(a["values"]))
 
+    def quadrature_points(self, quad_deg):
+        """physical coordinates of the quadrature points [n_elems, nq, dim]"""
+        w, _ = quadrature(self.shape, quad_deg)
+        x = np.zeros((self.n_elems, len(w), self.dim))
+        lib().orc_quadrature_points(self.h, quad_deg, _p(x))
+        return x
+
     def set_field_constraints(self, fid, con_dof, con_ptr, master_eqn, weight):
         """linear constraints with master DoFs (base/dof/Constraint.hpp): see orc_set_field_constraints"""
         con_dof = np.ascontiguousarray(con_dof, dtype=np.int64); con_ptr = np.ascontiguousarray(con_ptr, dtype=np.int64)
@@ -223,6 +230,12 @@ class System:
         params = np.ascontiguousarray(params, dtype=np.float64)
         self._check(lib().orc_stiffness(self.h, prob.h, kid, _p(params), quad_deg, test, trial, int(incremental),
                                         nthreads))
+
+    def bodyforce_sampled(self, prob, values, quad_deg, test):
+        """asmb::bodyForceComputation with a general f(x): values [n_elems, nq, ds] = f at the quadrature points"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if lib().orc_bodyforce_sampled(self.h, prob.h, _p(v), quad_deg, test):
+            raise RuntimeError(lib().orc_system_error(self.h).decode())
 
     def residual(self, prob, kid, params, quad_deg, test, trial):
         params = np.ascontiguousarray(params, dtype=np.float64)

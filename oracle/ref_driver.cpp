@@ -139,6 +139,22 @@ struct ConstantForce {
     result_type operator()(const X&) const { return f; }
 };
 
+// the non-constant body forces of tests/flows.py ("bodyfun" operations), by name
+template <unsigned DS, unsigned DIM>
+struct NamedForce {
+    typedef typename base::Vector<DS>::Type result_type;
+    std::string name;
+    result_type operator()(const typename base::Vector<DIM>::Type& x) const {
+        result_type f = base::constantVector<DS>(0.);
+        const double X = x[0], Y = x[1], Z = (DIM > 2 ? x[DIM - 1] : 0.);
+        if (name == "hex_scalar") f[0] = std::exp(X) * std::sin(2.0 * Y) + Z * Z;
+        else if (name == "tri_scalar") f[0] = std::sin(3.0 * X) * (1.0 + Y * Y);
+        else if (name == "hex_vector") { f[0] = Y * Z; f[DS > 1 ? 1 : 0] = std::cos(X); f[DS - 1] = 1.0 + X * Y * Z; }
+        else VERIFY_MSG(false, "unknown force function " + name);
+        return f;
+    }
+};
+
 template <typename MESH, typename FEBASIS, typename FIELD>
 void setUpField(const MESH& mesh, FIELD& field, const FieldSpec& spec, const base::mesh::MeshBoundary& boundary) {
     typedef typename FIELD::DegreeOfFreedom DoF;
@@ -249,6 +265,12 @@ int runSingle(const Job& job) {
         if (job.registerFields) solver.template registerFields<FTB>(fieldBinder);
         const double t1 = now();
         for (const Op& op : job.ops) {
+            if (op.what == "bodyfun") {
+                NamedForce<DS, Mesh::Node::dim> f;
+                f.name = op.kernel;
+                base::asmb::bodyForceComputation<FTB>(quadratureBody, solver, fieldBinder, f);
+                continue;
+            }
             if (op.what == "body") {
                 ConstantForce<DS> f;
                 for (unsigned d = 0; d < DS; d++) f.f[d] = op.p[d];

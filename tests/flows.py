@@ -76,6 +76,15 @@ class Case:
                                 values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1, linear=lin))
         return len(self.fields) - 1
 
+    def sampled_force(self, op):
+        """f(x) of a ("bodyfun", fun, quad_deg, field) operation at the quadrature points of every element
+        [n_elems, nq, ds]; x(xi_q) = sum_a N_a(xi_q) x_a like base::Geometry (base/geometry.hpp:105-135)"""
+        w, xi = E.quadrature(self.shape, op[2])
+        Ng = np.array([E.shape_eval(self.shape, self.geom_deg, p)[0] for p in xi])     # [nq, npe]
+        x = np.einsum("qa,ead->eqd", Ng, self.coords[self.conn])
+        ds = self.fields[op[3]]["ds"]
+        return np.ascontiguousarray(np.asarray(op[1](x.reshape(-1, self.dim)), dtype=np.float64).reshape(len(self.conn), len(w), ds))
+
     @staticmethod
     def constraint_arrays(f):
         """flat form of f["linear"] for set_field_constraints (masters as equation numbers)"""
@@ -119,6 +128,8 @@ class Case:
                 s.residual(prob, op[1], op[2], op[3], op[4], op[5])
             elif op[0] == "body":
                 s.bodyforce(prob, op[1], op[2], op[3])
+            elif op[0] == "bodyfun":
+                s.bodyforce_sampled(prob, self.sampled_force(op), op[2], op[3])
         return s.finish()
 
     # ---- run on the CUDA engine ----------------------------------------------------------------------
@@ -144,6 +155,8 @@ class Case:
                 eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5])
             elif op[0] == "body":
                 eng.body_force_computation(op[1], op[2], op[3])
+            elif op[0] == "bodyfun":
+                eng.body_force_computation_sampled(self.sampled_force(op), op[2], op[3])
         out = eng.get_csr()
         if own:
             eng.close()
@@ -255,6 +268,23 @@ def build_case(name, n=4, perturb=True, permute=False):
                  ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
                  ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),
                  ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
+    elif name in ("laplace_q1_hex_bodyfun", "laplace_p2_tri_bodyfun", "vector_laplace_q1_hex_bodyfun"):
+        # general (non-constant) body force f(x): BodyForce.hpp:172-205 evaluates the caller's function per point
+        if "tri" in name:
+            c = Case(E.TRI, 1, *make_mesh(E.TRI, n, perturb, permute))
+            c.add_field(2, 1, dirichlet=lambda x: H.fund_sol_laplace(x, np.full(2, -0.5)))
+            c.ops = [("matrix", E.K_LAPLACE, [1.0], 4, 0, 0, True),
+                     ("bodyfun", lambda x: (np.sin(3.0 * x[:, 0]) * (1.0 + x[:, 1] ** 2))[:, None], 4, 0)]
+        elif "vector" in name:
+            c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+            c.add_field(1, 3, dirichlet=lambda x: np.stack([x[:, 0], 0 * x[:, 1], -x[:, 2]], axis=1))
+            c.ops = [("matrix", E.K_VECTOR_LAPLACE, [0.7], 3, 0, 0, True),
+                     ("bodyfun", lambda x: np.stack([x[:, 1] * x[:, 2], np.cos(x[:, 0]), 1.0 + x[:, 0] * x[:, 1] * x[:, 2]], axis=1), 3, 0)]
+        else:
+            c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+            c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3))
+            c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True),
+                     ("bodyfun", lambda x: (np.exp(x[:, 0]) * np.sin(2.0 * x[:, 1]) + x[:, 2] ** 2)[:, None], 3, 0)]
     elif name in ("laplace_q1_hex_linear", "laplace_q2_hex_linear", "laplace_p1_tet_linear"):
         # general linear constraints: some interior DoFs are slaves of two / three ACTIVE masters with an rhs term
         shape = E.TET if "tet" in name else E.HEX
@@ -283,6 +313,7 @@ def build_case(name, n=4, perturb=True, permute=False):
                  ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
     else:
         raise ValueError(name)
+    c.name = name
     for i, op in enumerate(c.ops):  # normalise params
         if op[0] in ("matrix", "residual") and op[2] is None:
             c.ops[i] = (op[0], op[1], [0.0]) + tuple(op[3:])

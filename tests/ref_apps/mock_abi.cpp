@@ -27,6 +27,7 @@ void orc_register_fields(void*, void*, int, int);
 int orc_stiffness(void*, void*, int, const double*, int, int, int, int, int);
 int orc_residual(void*, void*, int, const double*, int, int, int);
 int orc_bodyforce(void*, void*, const double*, int, int);
+int orc_bodyforce_sampled(void*, void*, const double*, int, int);
 int orc_insert_lhs(void*, const double*, const int64_t*, int, const int64_t*, int);
 int orc_insert_rhs(void*, const double*, const int64_t*, int);
 void orc_finish(void*);
@@ -144,6 +145,10 @@ int isl_assemble_residual(isl_handle h, int kid, const double* p, int q, int t, 
 int isl_assemble_bodyforce(isl_handle h, const double* f, int q, int t) {
     g_calls[2]++;
     return orc_bodyforce(h->sys, h->prob, f, q, t) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_bodyforce_sampled(isl_handle h, const double* v, int q, int t) {
+    g_calls[2]++;
+    return orc_bodyforce_sampled(h->sys, h->prob, v, q, t) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_insert_lhs(isl_handle h, const double* m, const int64_t* r, int nr, const int64_t* c, int nc) {
     g_calls[3]++;

@@ -17,6 +17,11 @@ CASES = {
     # prints the number of Newton iterations per load step
     "compressibleWithDriver_quad010": ("compressibleWithDriver", ["quad.010.smf", "inputCompRefD.dat"],
                                        ["quad.010.smf", "inputCompRefD.dat"]),
+    # reference/05-mixedPoisson: heat::Laplace + a body force f(x) (sampled on the host, integrated on the device) +
+    # element-wise force and Neumann terms that reach the solver through insertToRHS; prints L2 / H1 errors
+    "mixedPoisson_square020": ("mixedPoisson", ["square_020.smf"], ["square_020.smf"]),
+    # the same through heat::PoissonDriver (kernel heat::Static<mat::thermal::IsotropicConstant>); writes test.vtk
+    "mixedPoissonWithDriver_square020": ("mixedPoissonWithDriver", ["square_020.smf"], ["square_020.smf"], "test.vtk"),
     # traction controlled: asmb::neumannForceComputation runs in the reference's own code and reaches the solver
     # through insertToRHS (the host-side "odd contribution" interface)
     "compressible_neumann_quad010": ("compressible", ["quad.010.smf", "inputCompRefN.dat"],
@@ -24,8 +29,13 @@ CASES = {
 }
 
 
+def output_file(name):
+    """file written by the application whose content belongs to the compared output (or None)"""
+    return CASES[name][3] if len(CASES[name]) > 3 else None
+
+
 def prepare(name, workdir):
-    exe, files, args = CASES[name]
+    exe, files, args = CASES[name][:3]
     for f in files:
         shutil.copy(os.path.join(REF, f), os.path.join(workdir, f))
     if name == "dirichlet_tet6":

@@ -25,9 +25,11 @@ from tests import flows
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ALL_GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "refrun", "*.npz")))
-# the cases with general linear constraints live in tests/test_zz_linear_constraints.py
-GOLD = [p for p in ALL_GOLD if "_linear" not in os.path.basename(p)]
-GOLD_LINEAR = [p for p in ALL_GOLD if "_linear" in os.path.basename(p)]
+# the cases with general linear constraints and with general body forces f(x) live in tests/test_zz_linear_constraints.py
+# (engine entry points written without GPU minutes: they run last)
+_late = lambda p: "_linear" in os.path.basename(p) or "_bodyfun" in os.path.basename(p)
+GOLD = [p for p in ALL_GOLD if not _late(p)]
+GOLD_LINEAR = [p for p in ALL_GOLD if _late(p)]
 REFERENCE = "/root/reference"
 APPS = os.path.join(ROOT, "oracle", "_ref", "apps")
 
@@ -155,8 +157,11 @@ def _run_binding_app(name, suffix, tmp_path):
     path = os.path.join(APPS_B200, exe + suffix)
     p = subprocess.run([path] + args, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
+    out = p.stdout
+    if RA.output_file(name):
+        out += open(os.path.join(str(tmp_path), RA.output_file(name))).read()
     expected = open(os.path.join(ROOT, "tests", "golden", "refrun_apps", name + ".out")).read()
-    assert RA.same_output(p.stdout, expected), "\n" + p.stdout + "\n--- expected ---\n" + expected
+    assert RA.same_output(out, expected), "\n" + out[-3000:] + "\n--- expected ---\n" + expected[-3000:]
 
 
 @pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
@@ -247,3 +252,13 @@ def test_binding_included_too_late_is_a_compile_error(tmp_path):
     assert p.returncode != 0 and "no CPU fallback" in p.stderr
     p = subprocess.run(cmd[:-1] + ["-include", "insilico_b200_reference.hpp", src], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
+
+
+@needs_ref
+def test_reference_app_mixed_poisson_golden(tmp_path):
+    """reference/05-mixedPoisson (appTest.mk): stdout equals `ref`, the VTK output equals `ref.vtk`"""
+    d = os.path.join(REFERENCE, "reference", "05-mixedPoisson")
+    out = _run(str(tmp_path), "mixedPoisson", ["square_020.smf"], [os.path.join(d, "square_020.smf")])
+    assert RA.same_output(out, open(os.path.join(d, "ref")).read(), rel=1e-6, noise=0.0)
+    mine = open(os.path.join(str(tmp_path), "square_020.vtk")).read()
+    assert RA.same_output(mine, open(os.path.join(d, "ref.vtk")).read(), rel=2e-5, noise=1e-9)

@@ -1,4 +1,10 @@
-"""General linear constraints: slave DoF components u = rhs + sum_j w_j u_master_j (base/dof/Constraint.hpp:57-140),
+"""General linear constraints and general body forces f(x).
+
+General body forces: asmb::bodyForceComputation with a caller-supplied function evaluated at every quadrature point
+(base/asmb/BodyForce.hpp:172-205) -> isl_assemble_bodyforce_sampled (function on the host, integration on the device);
+fixtures *_bodyfun_*.npz.
+
+General linear constraints: slave DoF components u = rhs + sum_j w_j u_master_j (base/dof/Constraint.hpp:57-140),
 collected by asmb::collectFromDoFs (base/asmb/collectFromDoFs.hpp:112-131) and applied by asmb::assembleMatrix /
 assembleForces (base/asmb/assembleMatrix.hpp:56-130,212-338, assembleForces.hpp:58-139): weighted extra rows and
 columns for the masters, prescribed part lifted to the rhs.
@@ -18,9 +24,12 @@ IDS = [os.path.basename(p)[:-4] for p in GOLD_LINEAR]
 
 
 def test_fixtures_hold_master_slave_constraints():
-    assert len(GOLD_LINEAR) >= 6
+    assert len([p for p in GOLD_LINEAR if "_linear" in p]) >= 6 and len([p for p in GOLD_LINEAR if "_bodyfun" in p]) >= 3
     for p in GOLD_LINEAR:
         _, case = _load(p)
+        if "_bodyfun" in p:
+            assert any(op[0] == "bodyfun" for op in case.ops)
+            continue
         assert any(f["linear"] for f in case.fields)
         for f in case.fields:
             for obj, comp, rhs, masters in f["linear"]:
@@ -63,7 +72,8 @@ def test_engine_reproduces_reference_run_with_linear_constraints(path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,n", [("laplace_q1_hex_linear", 7), ("laplace_q2_hex_linear", 3), ("laplace_p1_tet_linear", 6),
-                                    ("stvenant_q1_hex_linear", 5), ("stokes_p2p1_tet_linear", 3)])
+                                    ("stvenant_q1_hex_linear", 5), ("stokes_p2p1_tet_linear", 3), ("laplace_q1_hex_bodyfun", 7),
+                                    ("laplace_p2_tri_bodyfun", 6), ("vector_laplace_q1_hex_bodyfun", 5)])
 def test_engine_equals_oracle_with_linear_constraints(name, n):
     for register in (False, True):
         res = flows.run_case(name, n=n, perturb=True, register=register)

@@ -25,6 +25,8 @@ def main():
             exe, args = C.prepare(name, wd)
             out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "apps", exe)] + args, cwd=wd, check=True,
                                  capture_output=True, text=True, timeout=900).stdout
+            if C.output_file(name):
+                out += open(os.path.join(wd, C.output_file(name))).read()
         with open(os.path.join(OUT, name + ".out"), "w") as f:
             f.write(out)
         print(name, "->", len(out.splitlines()), "lines")

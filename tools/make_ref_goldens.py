@@ -50,6 +50,10 @@ CASES = [
     ("stvenant_q2_quad_n4", "stvenant_q2_quad", "solid_q2_quad", 4, True, False, True),
     ("laplace_p1_tri_n6", "laplace_p1_tri", "laplace_p1_tri", 6, True, True, False),
     ("stvenant_p2_tet_n3", "stvenant_p2_tet", "solid_p2_tet", 3, True, False, False),
+    # general body forces f(x) (the caller's function evaluated per quadrature point, BodyForce.hpp:172-205)
+    ("laplace_q1_hex_bodyfun_n4", "laplace_q1_hex_bodyfun", "laplace_q1_hex", 4, True, False, False),
+    ("laplace_p2_tri_bodyfun_n4", "laplace_p2_tri_bodyfun", "laplace_p2_tri", 4, True, False, False),
+    ("vector_laplace_q1_hex_bodyfun_n3", "vector_laplace_q1_hex_bodyfun", "vector_laplace_q1_hex", 3, True, True, False),
     # general linear constraints (slave DoFs with weighted ACTIVE masters, asmb/assembleMatrix.hpp:212-338)
     ("laplace_q1_hex_linear_n5", "laplace_q1_hex_linear", "laplace_q1_hex", 5, True, False, False),
     ("laplace_q1_hex_linear_n4_reg", "laplace_q1_hex_linear", "laplace_q1_hex", 4, False, False, True),
@@ -58,6 +62,14 @@ CASES = [
     ("stvenant_q1_hex_linear_n4", "stvenant_q1_hex_linear", "solid_q1_hex", 4, True, False, False),
     ("stokes_p2p1_tet_linear_n2", "stokes_p2p1_tet_linear", "stokes_p2p1_tet", 2, True, False, True),
 ]
+
+
+BODYFUN_NAME = {"laplace_q1_hex_bodyfun": "hex_scalar", "laplace_p2_tri_bodyfun": "tri_scalar",
+                "vector_laplace_q1_hex_bodyfun": "hex_vector"}
+
+
+def case_name(case):
+    return getattr(case, "name", None)
 
 
 def write_smf(path, shape, coords, conn):
@@ -96,6 +108,8 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
         elif op[0] == "residual":
             lines.append("op residual %s %d %d 1 %s" % (KERNEL_NAME[op[1]], op[4], op[5],
                                                         " ".join("%.17g" % p for p in op[2])))
+        elif op[0] == "bodyfun":
+            lines.append("op bodyfun %s %d %d 1" % (BODYFUN_NAME[case_name(case)], op[3], op[3]))
         elif op[0] == "body":
             lines.append("op body body %d %d 1 %s" % (op[3], op[3], " ".join("%.17g" % p for p in op[1])))
     job = os.path.join(workdir, "job.txt")
