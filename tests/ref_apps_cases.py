@@ -29,6 +29,11 @@ CASES = {
 }
 
 
+# applications that need engine entry points written without GPU minutes (isl_assemble_bodyforce_sampled): their GPU
+# test lives in tests/test_zz_linear_constraints.py so that it runs after the established suites
+LATE = ("mixedPoisson_square020", "mixedPoissonWithDriver_square020")
+
+
 def output_file(name):
     """file written by the application whose content belongs to the compared output (or None)"""
     return CASES[name][3] if len(CASES[name]) > 3 else None

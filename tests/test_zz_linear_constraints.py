@@ -88,6 +88,15 @@ def test_reference_api_on_b200_engine_linear_constraints(tmp_path, path):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["mixedPoisson_square020", "mixedPoissonWithDriver_square020"])
+def test_unmodified_mixed_poisson_applications_on_b200_engine(tmp_path, name):
+    """reference/05-mixedPoisson: body force f(x) sampled on the host and integrated by isl_assemble_bodyforce_sampled"""
+    from tests.test_reference_run import _run_binding_app
+    _run_binding_app(name, "", tmp_path)
+
+
+@pytest.mark.gpu
 def test_constraint_argument_checks_on_engine():
     from insilico_b200 import engine as E
     c = flows.build_case("laplace_q1_hex_linear", 4, True, False)
