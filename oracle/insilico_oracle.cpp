@@ -27,7 +27,7 @@
 //      reference/06-elastic/compRefOutD.dat (6 digits)
 //    * HierarchicOrder tables + worked numbering example of
 //      base/dof/generateDoFIndicesFromFaces.hpp:141-160
-//    * entry-wise: DoF numbering, CSR pattern (exact) and every matrix / rhs entry (<= 5.1e-16) of 26 cases
+//    * entry-wise: DoF numbering, CSR pattern (exact) and every matrix / rhs entry (<= 5.1e-16) of 29 cases
 //      assembled by the unmodified reference run here: tests/golden/refrun/*.npz,
 //      tests/test_reference_run.py::test_oracle_reproduces_reference_run
 // =============================================================================

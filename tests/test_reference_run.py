@@ -4,7 +4,7 @@ tests/golden/refrun/*.npz were produced by tools/make_ref_goldens.py from oracle
 headers of /root/reference (base::asmb::stiffnessMatrixComputation / computeResidualForces / bodyForceComputation into
 base::solver::Eigen3, finishAssembly, debugLHS/debugRHS) compiled against the std-only Boost/Eigen stand-ins of
 oracle/compat.  They hold the reference's DoF numbering (element -> DoF ids, status, equation numbers) and its
-finished system for 26 cases (6 of them with general linear constraints, see test_zz_linear_constraints.py).
+finished system for 29 cases (6 with general linear constraints and 3 with body forces f(x): see test_zz_linear_constraints.py).
 
   * CPU (`not gpu`): the oracle restatement reproduces them (numbering/pattern exact, values 1e-13) -> the oracle is
     pinned entry-wise, not only by the reference's 6-digit goldens.
