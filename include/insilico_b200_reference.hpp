@@ -336,9 +336,15 @@ double probeScalar(const base::MatrixD& K, const MAKEKERNEL& make, const TUPLE& 
 
 //------------------------------------------------------------------------------------------------------------------
 /** Which engine integrand a reference kernel object is, and with which constants.  Specialise for further kernels;
- *  the primary template is undefined on purpose (unsupported kernel = compile error, no CPU fallback).            */
+ *  the primary template is a static_assert (unsupported kernel = compile error, no CPU fallback).                 */
 template <typename KERNEL>
-struct B200KernelTraits;
+struct B200KernelTraits {
+    static_assert(sizeof(KERNEL) == 0,
+                  "this kernel object has no implementation in the B200 assembly engine (supported: heat::Laplace, "
+                  "heat::Static<mat::thermal::IsotropicConstant>, fluid::VectorLaplace, fluid::PressureGradient, "
+                  "fluid::VelocityDivergence, solid::HyperElastic<mat::hypel::StVenant | NeoHookeanCompressible>); "
+                  "there is no CPU fallback");
+};
 
 template <typename TUPLE>
 struct B200KernelTraits<heat::Laplace<TUPLE> > {

@@ -262,3 +262,14 @@ def test_reference_app_mixed_poisson_golden(tmp_path):
     assert RA.same_output(out, open(os.path.join(d, "ref")).read(), rel=1e-6, noise=0.0)
     mine = open(os.path.join(str(tmp_path), "square_020.vtk")).read()
     assert RA.same_output(mine, open(os.path.join(d, "ref.vtk")).read(), rel=2e-5, noise=1e-9)
+
+
+@needs_ref
+def test_unsupported_kernel_is_a_compile_error(tmp_path):
+    """reference/04-heat/convection.cpp uses heat::Convection, which the engine does not implement: no CPU fallback"""
+    src = os.path.join(REFERENCE, "reference", "04-heat", "convection.cpp")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-DNDEBUG", "-w", "-fsyntax-only", "-I" + os.path.join(ROOT, "tests", "ref_apps"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "compat"), "-I" + REFERENCE,
+           "-include", "insilico_b200_reference.hpp", src]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode != 0 and "has no implementation in the B200 assembly engine" in p.stderr
