@@ -749,9 +749,10 @@ void computeResidualForces(const QUADRATURE&, base::solver::B200& solver, const 
 //! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200.  The caller's function f(x) runs on the host, once per
 //! element and quadrature point (as in BodyForce.hpp:172-205); the integration runs on the device.  A force that turns
 //! out to be the same at every point takes the constant entry point (fused with the stiffness launch on the Q1 path).
-template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
-void bodyForceComputation(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
-                          const FUN& forceFun) {
+namespace b200_detail {
+//! shared by bodyForceComputation (f(x)) and bodyForceComputation2 (f(element, xi)): EVAL(gep, xi) -> force vector
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename EVAL>
+void sampledBodyForce(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder, const EVAL& eval) {
     namespace D = base::solver::b200_detail;
     solver.verifyCurrent();
     typedef typename FIELDTUPLEBINDER::Tuple Tuple;
@@ -770,7 +771,7 @@ void bodyForceComputation(const QUADRATURE& quadrature, base::solver::B200& solv
         const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*it).geomElementPtr();
         std::size_t q = 0;
         for (typename QUADRATURE::Iter qIter = quadrature.begin(); qIter != quadrature.end(); ++qIter, ++q) {
-            const typename FUN::result_type v = forceFun(base::Geometry<GeomElement>()(gep, qIter->second));
+            const typename EVAL::result_type v = eval(gep, qIter->second);
             for (unsigned d = 0; d < ds; d++) {
                 values[(e * nq + q) * ds + d] = v[d];
                 constant = constant && (v[d] == values[d]);
@@ -785,6 +786,38 @@ void bodyForceComputation(const QUADRATURE& quadrature, base::solver::B200& solv
     } else {
         D::check(isl_assemble_bodyforce_sampled(D::engine(), &values[0], D::QuadratureDegree<QUADRATURE>::value, TI::test));
     }
+}
+template <typename GEOMELEMENT, typename FUN>
+struct AtPhysicalPoint {   // f(x), x = x(xi) like base::auxi::EvaluateDirectly (base/auxi/FunEvaluationPolicy.hpp:47-59)
+    typedef typename FUN::result_type result_type;
+    const FUN& fun;
+    template <typename XI>
+    result_type operator()(const GEOMELEMENT* gep, const XI& xi) const { return fun(base::Geometry<GEOMELEMENT>()(gep, xi)); }
+};
+template <typename GEOMELEMENT, typename FUN>
+struct AtElementPoint {    // f(element, xi) like base::auxi::EvaluateViaElement (FunEvaluationPolicy.hpp:74-86)
+    typedef typename FUN::result_type result_type;
+    const FUN& fun;
+    template <typename XI>
+    result_type operator()(const GEOMELEMENT* gep, const XI& xi) const { return fun(gep, xi); }
+};
+}  // namespace b200_detail
+
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
+void bodyForceComputation(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                          const FUN& forceFun) {
+    typedef typename FIELDTUPLEBINDER::Tuple::GeomElement GeomElement;
+    const b200_detail::AtPhysicalPoint<GeomElement, FUN> eval = {forceFun};
+    b200_detail::sampledBodyForce<FIELDTUPLEBINDER>(quadrature, solver, fieldBinder, eval);
+}
+
+//! base/asmb/BodyForce.hpp:92-111 (force function of an element pointer and a local coordinate) for SOLVER = B200
+template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename FUN>
+void bodyForceComputation2(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                           const FUN& forceFun) {
+    typedef typename FIELDTUPLEBINDER::Tuple::GeomElement GeomElement;
+    const b200_detail::AtElementPoint<GeomElement, FUN> eval = {forceFun};
+    b200_detail::sampledBodyForce<FIELDTUPLEBINDER>(quadrature, solver, fieldBinder, eval);
 }
 
 }  // namespace asmb
