@@ -215,9 +215,27 @@ void flattenField(const FIELDBINDER& fb, BinderState& s, bool topologyChanged) {
     FlattenField<N, FIELDBINDER, IsDummy<typename EPT::template Binder<N>::Type>::value>::apply(fb, s, topologyChanged);
 }
 
+//! Rescan policy: by default the reference's objects are re-read at EVERY assembly call (what the reference's element
+//! loop does).  An application that changes DoFs, constraints and nodes only between solver instances (the reference's
+//! Newton loops do) can set rescanOncePerSolver() = true: the scan then runs at the first assembly call of each solver.
+inline bool& rescanOncePerSolver() {
+    static bool flag = false;
+    return flag;
+}
+inline unsigned long& scannedForSolver() {
+    static unsigned long id = 0;
+    return id;
+}
+inline unsigned long& currentSolver() {
+    static unsigned long id = 0;
+    return id;
+}
+
 //! Bring the engine's copy of mesh and fields in line with the reference's objects behind this binder.
 template <typename FIELDBINDER>
 void synchronise(const FIELDBINDER& fb) {
+    if (rescanOncePerSolver() && state().key == static_cast<const void*>(&fb) && scannedForSolver() == currentSolver()) return;
+    scannedForSolver() = currentSolver();
     typedef typename FIELDBINDER::ElementPtrTuple EPT;
     typedef typename EPT::GeomElement GeomElement;
     typedef typename GeomElement::Node Node;
@@ -478,6 +496,7 @@ public:
 
     //! Constructor with the size N of matrix and vector (Eigen3.hpp:71-77)
     B200(const std::size_t size) : size_(size), solved_(false), id_(++latest_()) {
+        b200_detail::currentSolver() = id_;
         b200_detail::check(isl_system_create(b200_detail::engine(), static_cast<int64_t>(size)));
     }
 

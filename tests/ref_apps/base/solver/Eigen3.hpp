@@ -53,6 +53,7 @@ struct InstallHook {
     InstallHook() {
         B200::solveHook() = &hostSolve;
         B200::nativeCG() = (std::getenv("ISL_NATIVE_CG") != NULL);   // default: the host stand-in, like the CPU reference run
+        b200_detail::rescanOncePerSolver() = (std::getenv("ISL_RESCAN_PER_SOLVER") != NULL);
     }
 };
 static InstallHook installHook;

@@ -273,3 +273,15 @@ def test_unsupported_kernel_is_a_compile_error(tmp_path):
            "-include", "insilico_b200_reference.hpp", src]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode != 0 and "has no implementation in the B200 assembly engine" in p.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_rescan_once_per_solver_policy_gives_the_same_newton_history(tmp_path):
+    """b200_detail::rescanOncePerSolver(): the reference's objects are scanned at the first assembly call of each solver
+    only (the reference's Newton loops change DoFs between solver instances)"""
+    exe, args = RA.prepare("compressible_quad010", str(tmp_path))
+    p = subprocess.run([os.path.join(APPS_B200, exe + "_mock")] + args, cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, ISL_RESCAN_PER_SOLVER="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    expected = open(os.path.join(ROOT, "tests", "golden", "refrun_apps", "compressible_quad010.out")).read()
+    assert RA.same_output(p.stdout, expected)
