@@ -67,6 +67,10 @@ void* isl_engine_stream(isl_handle h);
 /* number of the engine's own kernels launched since creation (bench.py "gpu_launches") */
 int64_t isl_kernel_launches(isl_handle h);
 
+/* measured FP64 peak of this device (independent DFMA chains in registers, CUDA events on the engine stream):
+ * the denominator of the FP64-pipe roofline fraction SURVEY 8(d) asks for; nothing comparable in the reference */
+int isl_measure_fp64_peak(isl_handle h, double* tflops);
+
 /* ---- host-side tables (no GPU needed) ------------------------------------ */
 /* base::Quadrature<DEG,SHAPE> (base/Quadrature.hpp:113-143): returns #points; weights[n], points[n*dim] */
 int isl_quadrature(int shape, int degree, double* weights, double* points);

@@ -1377,6 +1377,7 @@ void flush_pending(isl_engine* h, int fuse_body, double f0) {
 }
 
 #include "isl_solver.cuh"
+#include "isl_microbench.cuh"
 
 }  // namespace
 
@@ -1866,6 +1867,31 @@ int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations
         ISL_CUDA(cudaSetDevice(h->device));
         const int64_t it = solve_cg(h, tol, max_iter, error);
         if (iterations) *iterations = it;
+    });
+}
+
+int isl_measure_fp64_peak(isl_handle h, double* tflops) {
+    return guarded([&] {
+        ISL_REQUIRE(tflops, "null output");
+        flush_pending(h);
+        DevBuf<double> out; out.alloc(1);
+        cudaEvent_t a, b;
+        ISL_CUDA(cudaEventCreate(&a)); ISL_CUDA(cudaEventCreate(&b));
+        constexpr int CH = 8;
+        const int grid = h->n_sm * 8, iters = 2048;
+        double best = 0.;
+        for (int rep = 0; rep < 4; rep++) {
+            ISL_CUDA(cudaEventRecord(a, h->stream));
+            ISL_LAUNCH(h, k_dfma_peak<CH>, grid, 256, 0, out.p, iters, 0.999999, 1e-9);
+            ISL_CUDA(cudaEventRecord(b, h->stream));
+            ISL_CUDA(cudaEventSynchronize(b));
+            float ms = 0.f;
+            ISL_CUDA(cudaEventElapsedTime(&ms, a, b));
+            const double fl = 2.0 * CH * 16.0 * iters * 256.0 * grid;
+            if (rep > 0 && ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        *tflops = best;
     });
 }
 
