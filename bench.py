@@ -202,17 +202,257 @@ def reference_baseline(ns, steps, warmup, cores):
                       % (ns, ne, cores, ms, ms_reg, v_dyn)}, ms
 
 
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs 1, 3, 4, 5 (insilico_b200/workloads.py): python bench.py --config C3 [--n 64]
+DEFAULT_N = {"C1": 32, "C3": 64, "C4": 64, "C5": 64}
+CPU_SAMPLE_N = {"C1": 32, "C3": 10, "C4": 14, "C5": 16}
+BOUND = {"C1": "hbm", "C3": "fp64", "C4": "fp64", "C5": "hbm"}
+DRIVER_TYPE = {"C1": "laplace_q1_hex", "C2": "laplace_q1_hex", "C3": "solid_q2_hex", "C4": "solid_p2_tet", "C5": "stokes_p2p1_tet"}
+KERNEL_NAME = {1: "laplace", 2: "stvenant", 3: "neohooke", 4: "pressure_gradient", 5: "velocity_divergence", 6: "vector_laplace"}
+SHAPE_NAME = {2: "triangle", 3: "quadrilateral", 4: "tetrahedron", 5: "hexahedron"}
+
+
+def cpu_reference_config(w, steps):
+    """one workload (insilico_b200.workloads.Workload) assembled by the UNMODIFIED reference on the host cores
+    (oracle/_ref/ref_driver_omp, OpenMP over all cores, pre-structured triplets; registerFields untimed).
+    Returns (elements/s, ms per step) or None."""
+    if not os.access(REF_DRIVER, os.X_OK):
+        return None
+    import tempfile
+    with tempfile.TemporaryDirectory() as wd:
+        smf = os.path.join(wd, "mesh.smf")
+        c3 = np.zeros((len(w.coords), 3)); c3[:, :w.dim] = w.coords
+        with open(smf, "w") as f:
+            f.write("! elementShape %s\n! elementNumPoints %d\n%d %d\n" % (SHAPE_NAME[w.shape], w.conn.shape[1], len(c3), len(w.conn)))
+            np.savetxt(f, c3, fmt="%.17g")
+            np.savetxt(f, w.conn, fmt="%d")
+        lines = ["type %s" % DRIVER_TYPE[w.name], "mesh %s" % smf, "out %s/out" % wd, "register 1", "repeat %d" % max(1, steps), "dump 0"]
+        for i, fl in enumerate(w.fields):
+            for nm, arr in (("presc", fl["presc"]), ("values", fl["values"]), ("status", fl["status"].astype(np.float64))):
+                np.ascontiguousarray(arr, dtype=np.float64).tofile(os.path.join(wd, "%s%d.bin" % (nm, i)))
+            lines.append("field %d 2 -1 %s/presc%d.bin %s/values%d.bin %s/status%d.bin" % (i, wd, i, wd, i, wd, i))
+        for op in w.ops:
+            if op[0] == "matrix":
+                lines.append("op matrix %s %d %d %d %s" % (KERNEL_NAME[op[1]], op[4], op[5], int(op[6]), " ".join("%.17g" % v for v in op[2])))
+            elif op[0] == "residual":
+                lines.append("op residual %s %d %d 1 %s" % (KERNEL_NAME[op[1]], op[4], op[5], " ".join("%.17g" % v for v in op[2])))
+            else:
+                lines.append("op body body %d %d 1 %s" % (op[3], op[3], " ".join("%.17g" % v for v in op[1])))
+        job = os.path.join(wd, "job.txt")
+        with open(job, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        try:
+            out = subprocess.run([REF_DRIVER, job], check=True, capture_output=True, text=True, timeout=1500).stdout
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("reference driver failed: %r\n" % (e,))
+            return None
+    reps = [l.split() for l in out.splitlines() if l.startswith("rep ")]
+    t = [float(r[r.index("assemble") + 1]) for r in reps]
+    if not t:
+        return None
+    dt = sum(t) / len(t)
+    return len(w.conn) / dt, dt * 1e3
+
+
+def config_cpu_baseline(cfg, ns, steps, cores):
+    from insilico_b200 import workloads
+    ws = workloads.build(cfg, ns)
+    r = cpu_reference_config(ws, steps)
+    if r is None:
+        return None, None
+    return {"value": r[0], "unit": "elements/s", "cores": cores, "kind": "reference",
+            "sample": "%s at n = %d (%d elements) per step, UNMODIFIED reference headers (stiffnessMatrixComputation / "
+                      "computeResidualForces into base::solver::Eigen3, pre-structured triplets, OpenMP parallel for over %d "
+                      "threads) compiled against std-only Boost/Eigen stand-ins (oracle/compat): %.0f ms/step, registerFields "
+                      "excluded" % (ws.description.split(":")[0], ns, len(ws.conn), cores, r[1])}, r[1]
+
+
+def bench_config(args, rank, world, local_rank, cores):
+    """one JSON line for BASELINE config C1 / C3 / C4 / C5 on the generic kernels (same keys as the C2 line)"""
+    import torch
+    import torch.distributed as dist
+    from insilico_b200 import engine as E
+    from insilico_b200 import partition, workloads
+    cfg = args.config
+    n = args.n if args.n_given else DEFAULT_N[cfg]
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = E.Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.stream, device=local_rank)
+    extra = {}
+    if cfg == "C1":   # dirichlet.cpp on unitCube N N N, N in {8, 16, 32}: the smaller ones are timed first
+        for ns in (8, 16):
+            ws = workloads.build("C1", ns)
+            ws.upload(eng); eng.new_solver(ws.n_eqn); ws.register(eng)
+            for _ in range(3):
+                ws.step(eng)
+            eng.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(args.steps):
+                ws.step(eng)
+            b.record(stream)
+            eng.synchronize(); torch.cuda.synchronize()
+            extra["ms_per_step_n%d" % ns] = a.elapsed_time(b) / args.steps
+    w = workloads.build(cfg, n)
+    ne_global = len(w.conn)
+    part = None
+    if world > 1:
+        wl = partition.general_partition(w.coords, w.conn, w.fields, w.n_eqn, rank, world)
+        part = partition.GeneralDistributedAssembly(eng, wl, rank, world, w.shape, w.geom_deg)
+        n_eqn, ne_rank = wl["n_eqn_local"], wl["n_owned_elems"]
+    else:
+        w.upload(eng)
+        n_eqn, ne_rank = w.n_eqn, ne_global
+    eng.new_solver(n_eqn)
+    t0 = time.perf_counter()
+    w.register(eng)
+    if part is not None:
+        part.setup_exchange()
+    eng.synchronize()
+    t_register = time.perf_counter() - t0
+
+    def step(ev=None):
+        eng.new_solver(n_eqn)
+        for k, op in enumerate(w.ops):
+            if ev is not None:
+                ev[k][0].record(stream)
+            if op[0] == "matrix":
+                eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+            elif op[0] == "residual":
+                eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5])
+            else:
+                eng.body_force_computation(op[1], op[2], op[3])
+            if ev is not None:
+                eng.flush()
+                ev[k][1].record(stream)
+        if part is not None:
+            part.exchange()
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in w.ops] for _ in range(args.steps)]
+    a.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    b.record(stream)
+    barrier()
+    launches = eng.kernel_launches - l0
+    ms_total = a.elapsed_time(b)
+    per_op = [sum(evs[s][k][0].elapsed_time(evs[s][k][1]) for s in range(args.steps)) / args.steps for k in range(len(w.ops))]
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = ne_global / (ms_step * 1e-3)
+    nnz = eng.finish_assembly()[1]
+    fp64_peak = eng.measure_fp64_peak()
+
+    e2e = None
+    if not args.no_e2e and world == 1:
+        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
+        h_coords = pin(w.coords)
+        h_f = [(pin(f["presc"]), pin(f["values"])) for f in w.fields]
+        h_val = torch.empty(nnz, dtype=torch.float64).pin_memory().numpy()
+        h_rhs = torch.empty(n_eqn, dtype=torch.float64).pin_memory().numpy()
+
+        def e2e_step():
+            eng.update_coords(h_coords)
+            for i, (hp, hv) in enumerate(h_f):
+                eng.update_field(i, prescribed=hp, values=hv)
+            step()
+            eng.get_csr(None, None, h_val, h_rhs)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(2, min(args.steps, 5))
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / ke
+        e2e = {"value": ne_global / dt, "unit": "elements/s",
+               "h2d_bytes_per_step": int(h_coords.nbytes + sum(x.nbytes + y.nbytes for x, y in h_f)),
+               "d2h_bytes_per_step": int(h_val.nbytes + h_rhs.nbytes), "ms_per_step": dt * 1e3,
+               "what": "isl_mesh_update_coords + isl_field_update (pinned H2D), isl_system_create, the assembly calls of the step, "
+                       "isl_finish, isl_get_csr values+rhs (pinned D2H); pattern cached"}
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    hbm_peak, peak_src = peaks()
+    flops = w.algorithmic_flops_per_element()
+    nbytes = w.algorithmic_bytes_per_element(nnz if world == 1 else nnz * world)
+    k_dom = int(np.argmax(per_op))
+    t_asm = sum(per_op) * 1e-3   # device time of the assembly kernels of one step
+    hbm = {"achieved": nbytes * ne_rank / t_asm / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+           "algorithmic_bytes_per_element": nbytes}
+    hbm["frac"] = hbm["achieved"] / hbm_peak
+    f64 = {"achieved": flops * ne_rank / t_asm / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+           "peak_source": "measured (isl_measure_fp64_peak: DFMA chains, CUDA events, this run)",
+           "algorithmic_flops_per_element": flops}
+    f64["frac"] = f64["achieved"] / fp64_peak if fp64_peak else None
+    main_r = dict(f64 if BOUND[cfg] == "fp64" else hbm)
+    op = w.ops[k_dom]
+    roof = {"bound": BOUND[cfg], "kernel": "%s %s (k_tangent / k_force family)" % (op[0], KERNEL_NAME.get(op[1], "bodyforce") if op[0] != "body" else "bodyforce"),
+            "achieved": main_r["achieved"], "peak": main_r["peak"], "unit": main_r["unit"], "frac": main_r["frac"], "traffic": None,
+            "kernel_ms": t_asm * 1e3, "per_op_ms": [{"op": o[0], "kernel": KERNEL_NAME.get(o[1], "body") if o[0] != "body" else "body", "ms": t} for o, t in zip(w.ops, per_op)],
+            "hbm": hbm, "fp64": f64}
+    cfgd = {"workload": w.description, "n": n, "n_elems": int(ne_global), "n_eqn": int(w.n_eqn), "nnz_per_gpu": int(nnz),
+            "partition": "element blocks along a Z-curve, owned rows, NCCL ghost-row exchange" if world > 1 else "single GPU",
+            "l2": "arrays touched per step: %.2f GB (%s L2)" % (nbytes * ne_rank / 1e9, "larger than" if nbytes * ne_rank > 126e6 else "inside"),
+            "register_fields_ms": t_register * 1e3}
+    cfgd.update(extra)
+    line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfgd, "roofline": roof, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "e2e": e2e}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb, _ = config_cpu_baseline(cfg, args.cpu_sample if args.cpu_sample_given else CPU_SAMPLE_N[cfg], 2, cores)
+            if cb is not None:
+                line["cpu_baseline"] = cb
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("cpu_baseline failed: %r\n" % (e,))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="elements per direction per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="edge length of the CPU-baseline sample mesh")
+    ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="BASELINE.json config; C2 (default) is the headline, the others run the generic kernels")
+    ap.add_argument("--n", type=int, default=None, help="elements per direction (C2: per GPU; default 256)")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="edge length of the CPU-baseline sample mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    args.n_given, args.cpu_sample_given = args.n is not None, args.cpu_sample is not None
+    if args.n is None:
+        args.n = 256
+    if args.cpu_sample is None:
+        args.cpu_sample = 64
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +465,17 @@ def main():
         if rank != 0:
             return
         ns = args.cpu_sample
+        if args.config != "C2":
+            cb, ms = config_cpu_baseline(args.config, ns if args.cpu_sample_given else CPU_SAMPLE_N[args.config], max(1, min(args.steps, 3)), cores)
+            if cb is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
+                return
+            print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "elements/s", "n_gpus": args.gpus,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": cb["sample"]},
+                              "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
         cb, ms = reference_baseline(ns, max(1, min(args.steps, 5)), min(args.warmup, 1), cores)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "elements/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -236,6 +487,9 @@ def main():
         return
 
     # ------------------------------------------------------------------------------------------------------ our arm
+    if args.config != "C2":
+        bench_config(args, rank, world, local_rank, cores)
+        return
     import torch
     import torch.distributed as dist
     from insilico_b200 import engine as E

@@ -58,6 +58,8 @@ int isl_version(void);
 int isl_engine_create(int device, isl_handle* out);
 int isl_engine_destroy(isl_handle h);
 int isl_synchronize(isl_handle h);
+/* launches deferred work (the Q1 stiffness kernel waits one call for a body force to fuse) without waiting */
+int isl_flush(isl_handle h);
 /* kernel-selection knobs that can change between launches without new preprocessing (tuning sweeps; the same knobs
  * are read from ISL_* environment variables when the engine is created): "q1_rows", "rows_threads", "rows_ss",
  * "affine_kernel", "aff_split", "aff_threads", "tangent_tiled", "defer"                                        */

@@ -736,7 +736,6 @@ struct isl_engine {
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
     int q1_rows = 0;            // ISL_Q1_ROWS=1: row-gather kernel on all-affine meshes (isl_rowgather.cuh; not yet default)
     int rows_threads = 256;     // its CTA size (ISL_ROWS_THREADS)
-    int rows_ss = 0;            // ISL_ROWS_SS=1: signed-sum form of the entries (15 numbers per element, no constant tables)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1154,12 +1153,12 @@ PatchSet* get_patchset(isl_engine* h, int field) {
             // row-gather tables (isl_rowgather.cuh): slots from the host, positions / eligibility on the device
             DevBuf<uint16_t> rslot; upload_vec(h, rslot, P.rslot);
             const size_t nr = P.rows.size();
-            ps->r_meta.alloc(nr * sizeof(RowMeta)); ps->r_rowstart.alloc(nr);
+            ps->r_meta.alloc(nr * sizeof(RowMeta));
             DevBuf<int> cnt; cnt.alloc(2);
             ISL_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int), h->stream));
             ISL_LAUNCH(h, k_row_meta, ps->n_patches, 128, 0, 0, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p,
                        h->conn.p, f.eqn.p, f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p),
-                       ps->r_rowstart.p, (int32_t*)nullptr, cnt.p, cnt.p + 1);
+                       (int32_t*)nullptr, cnt.p, cnt.p + 1);
             int hc[2] = {0, 0};
             ISL_CUDA(cudaMemcpyAsync(hc, cnt.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             ISL_CUDA(cudaStreamSynchronize(h->stream));
@@ -1168,7 +1167,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
                 if (hc[0] > 0)
                     ISL_LAUNCH(h, k_row_meta, ps->n_patches, 128, 0, 1, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p,
                                h->conn.p, f.eqn.p, f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p),
-                               ps->r_rowstart.p, ps->lift_nodes.p, cnt.p, cnt.p + 1);
+                               ps->lift_nodes.p, cnt.p, cnt.p + 1);
                 ISL_CUDA(cudaStreamSynchronize(h->stream));
                 ps->rows_ok = true; ps->max_inst = P.max_inst;
             }
@@ -1232,50 +1231,33 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
             ISL_CUDA(cudaStreamSynchronize(h->stream));
             h->affine_state = na ? 0 : 1;
         }
-        if (h->affine_state == 1 && h->q1_rows && ps->rows_ok) {
+        if (h->q1_rows && ps->rows_ok && h->affine_state >= 0) {
             RowsParams q;
             q.coords = h->coords.p; q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
-            q.rows = ps->rows.p; q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
-            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.rowstart = ps->r_rowstart.p; q.lift_nodes = ps->lift_nodes.p;
+            q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
+            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.lift_nodes = ps->lift_nodes.p;
             q.status = p.status; q.presc = p.presc; q.values = p.values; q.val = p.val; q.rhs = p.rhs;
             q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
-            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 1) & ~1;
-            const int nt = h->rows_threads;
-            const size_t smem_r = (size_t)(h->rows_ss ? 16 : 7) * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
-#define ISL_ROWS_LAUNCH(NT, MINB, SS)                                                                                   \
-    do {                                                                                                               \
-        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<NT, MINB, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r)); \
-        ISL_LAUNCH(h, (k_q1hex_rows_affine<NT, MINB, SS>), ps->n_patches, NT, smem_r, q);                             \
-    } while (0)
-            if (h->rows_ss) {
-                if (nt == 128) ISL_ROWS_LAUNCH(128, 4, true);
-                else if (nt == 192) ISL_ROWS_LAUNCH(192, 2, true);
-                else if (nt == 320) ISL_ROWS_LAUNCH(320, 2, true);
-                else if (nt == 384) ISL_ROWS_LAUNCH(384, 1, true);
-                else ISL_ROWS_LAUNCH(256, 2, true);
-            } else {
-                if (nt == 128) ISL_ROWS_LAUNCH(128, 4, false);
-                else if (nt == 192) ISL_ROWS_LAUNCH(192, 2, false);
-                else if (nt == 320) ISL_ROWS_LAUNCH(320, 2, false);
-                else if (nt == 384) ISL_ROWS_LAUNCH(384, 1, false);
-                else if (nt == 512) ISL_ROWS_LAUNCH(512, 1, false);
-                else ISL_ROWS_LAUNCH(256, 2, false);
+            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 2) & ~1; q.n_patches = ps->n_patches;
+            if (h->affine_state == 1) {
+                const int nt = h->rows_threads == 256 ? 256 : 128;
+                const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
+                int per_sm = (int)std::min<size_t>(nt == 256 ? 2 : 4, (size_t)(227 * 1024) / (smem_r + 1024));
+                q.resident = h->n_sm * std::max(1, per_sm);
+                if (nt == 256) {
+                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                    ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), ps->n_patches, 256, smem_r, q);
+                } else {
+                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                    ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), ps->n_patches, 128, smem_r, q);
+                }
+                return;
             }
-#undef ISL_ROWS_LAUNCH
-            return;
-        }
-        if (h->affine_state == 0 && h->q1_rows && ps->rows_ok) {
             // general elements: 44 doubles per instance in shared memory; falls through to the patch kernel when a patch does not fit
-            RowsParams q;
-            q.coords = h->coords.p; q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
-            q.rows = ps->rows.p; q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
-            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.rowstart = ps->r_rowstart.p; q.lift_nodes = ps->lift_nodes.p;
-            q.status = p.status; q.presc = p.presc; q.values = p.values; q.val = p.val; q.rhs = p.rhs;
-            q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
-            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 1) & ~1;
             const int nt = h->rows_threads == 128 ? 128 : 256;
-            const size_t smem_g = (size_t)44 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)nt * 108);
+            const size_t smem_g = (size_t)44 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
             if (smem_g <= (size_t)227 * 1024) {
+                q.resident = h->n_sm * std::max<int>(1, (int)((size_t)(227 * 1024) / (smem_g + 1024)));
                 if (nt == 128) {
                     ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_general<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
                     ISL_LAUNCH(h, (k_q1hex_rows_general<128, 2>), ps->n_patches, 128, smem_g, q);
@@ -1414,7 +1396,6 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
         if (const char* m = getenv("ISL_Q1_ROWS")) { h->q1_rows = atoi(m) ? 1 : 0; if (h->q1_rows) h->patch_rows = 256; }
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
-        if (const char* m = getenv("ISL_ROWS_SS")) h->rows_ss = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
@@ -1439,7 +1420,7 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         const int v = (int)value;
         if (n == "q1_rows") h->q1_rows = v ? 1 : 0;               // only useful when the engine was created with ISL_Q1_ROWS=1
         else if (n == "rows_threads") h->rows_threads = v;
-        else if (n == "rows_ss") h->rows_ss = v ? 1 : 0;
+        else if (n == "rows_ss") (void)v;   // retired variant; accepted for old sweep scripts
         else if (n == "affine_kernel") h->affine_kernel = v ? 1 : 0;
         else if (n == "aff_split") h->aff_split = v ? 1 : 0;
         else if (n == "aff_threads") h->patch_threads_aff = v;
@@ -1449,6 +1430,7 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
     });
 }
 int isl_synchronize(isl_handle h) { return guarded([&] { flush_pending(h); ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
+int isl_flush(isl_handle h) { return guarded([&] { flush_pending(h); }); }
 void* isl_engine_stream(isl_handle h) { return (void*)h->stream; }
 int64_t isl_kernel_launches(isl_handle h) { return h->launches; }
 

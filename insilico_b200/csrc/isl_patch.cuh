@@ -1079,8 +1079,8 @@ struct PatchSet {
     DevBuf<int64_t> run_start;
     DevBuf<uint16_t> i_lnode, i_lrow;
     DevBuf<uint8_t> i_pos;
-    // row-gather kernel (isl_rowgather.cuh): per owned row 48-byte RowMeta, CSR start, neighbour nodes of rows next to CONSTRAINED nodes
-    DevBuf<unsigned char> r_meta; DevBuf<int64_t> r_rowstart; DevBuf<int32_t> lift_nodes;
+    // row-gather kernel (isl_rowgather.cuh): per owned row 64-byte RowMeta (slots, CSR positions, row id and start), neighbour nodes of rows next to CONSTRAINED nodes
+    DevBuf<unsigned char> r_meta; DevBuf<int32_t> lift_nodes;
     bool rows_ok = false; int max_inst = 0;
     double redundancy = 0.;
 };

@@ -49,23 +49,24 @@ struct alignas(16) RowMeta {
     uint8_t pos[27];   // position of stencil neighbour k inside the CSR row (0xff: no entry)
     uint8_t nnz;       // entries of the row (bits 0-6); bit 7: partial row, has entries that are no stencil neighbours
     int32_t lift;      // row next to CONSTRAINED nodes: index into the table of neighbour node ids, else -1
+    int32_t grow;      // global row (equation number)
+    int32_t pad;
+    int64_t rowstart;  // rowptr[grow]
 };
-static_assert(sizeof(RowMeta) == 48, "RowMeta is read as three 16-byte words");
+static_assert(sizeof(RowMeta) == 64, "RowMeta is read as four 16-byte words");
 
 // tables: device = the engine's constant memory, host emulation = plain arrays filled by the test harness
 #ifdef __CUDA_ARCH__
-#define RG_AFF(i) c_q1_aff[i]
 #define RG_NSUM(i) c_q1_Nsum[i]
 #else
-static double rg_host_aff[6 * 36];
 static double rg_host_nsum[8];
-#define RG_AFF(i) rg_host_aff[i]
 #define RG_NSUM(i) rg_host_nsum[i]
 #endif
 
-// phase 1: the six numbers D_c and det J w of an affine element from its hierarchic nodes 0, 1 (xi), 3 (eta), 4 (zeta)
+// phase 1: the six numbers E_c = (kappa / det J) (cof^T cof)_c, c = xx yy zz xy xz yz, and det J w of an affine
+// element from its hierarchic nodes 0, 1 (xi), 3 (eta), 4 (zeta)
 RG_HD void rg_instance(const double* x0, const double* x1, const double* x3, const double* x4, double factor, double w,
-                       double (&D)[6], double& dw) {
+                       double (&E)[6], double& dw) {
     double J[3][3];
     for (int d = 0; d < 3; d++) { J[d][0] = x1[d] - x0[d]; J[d][1] = x3[d] - x0[d]; J[d][2] = x4[d] - x0[d]; }
     double co[3][3];
@@ -79,91 +80,109 @@ RG_HD void rg_instance(const double* x0, const double* x1, const double* x3, con
     co[2][1] = J[0][2] * J[1][0] - J[0][0] * J[1][2];
     co[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
     const double det = J[0][0] * co[0][0] + (J[0][1] * co[0][1] + J[0][2] * co[0][2]);
-    const double s = (factor * w) / det;
+    const double s = factor / det;
     dw = det * w;
-    D[0] = s * (co[0][0] * co[0][0] + co[1][0] * co[1][0] + co[2][0] * co[2][0]);
-    D[1] = s * (co[0][1] * co[0][1] + co[1][1] * co[1][1] + co[2][1] * co[2][1]);
-    D[2] = s * (co[0][2] * co[0][2] + co[1][2] * co[1][2] + co[2][2] * co[2][2]);
-    D[3] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
-    D[4] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
-    D[5] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
+    E[0] = s * (co[0][0] * co[0][0] + co[1][0] * co[1][0] + co[2][0] * co[2][0]);
+    E[1] = s * (co[0][1] * co[0][1] + co[1][1] * co[1][1] + co[2][1] * co[2][1]);
+    E[2] = s * (co[0][2] * co[0][2] + co[1][2] * co[1][2] + co[2][2] * co[2][2]);
+    E[3] = s * (co[0][0] * co[0][1] + co[1][0] * co[1][1] + co[2][0] * co[2][1]);
+    E[4] = s * (co[0][0] * co[0][2] + co[1][0] * co[1][2] + co[2][0] * co[2][2]);
+    E[5] = s * (co[0][1] * co[0][2] + co[1][1] * co[1][2] + co[2][1] * co[2][2]);
 }
 
-// phase 2: the eight entries that the element with the row node as local node A contributes (A compile-time)
-template <int A>
-RG_HD void rg_add_slot(const double (&D)[6], double dw, double (&acc)[27], double& body) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int b = 0; b < 8; b++) {
-        double v = D[0] * RG_AFF(sym_idx(A, b));
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-        for (int c = 1; c < 6; c++) v = fma(D[c], RG_AFF(c * 36 + sym_idx(A, b)), v);
-        acc[rg_kidx(A, b)] += v;
-    }
-    body = fma(dw, RG_NSUM(A), body);
-}
-
-// Signed-sum form of the same entries (SS variant).  On the reference cube the trilinear integrals are exact rationals:
-//   int d_x N_a d_x N_b = s_x(a) s_x(b) m_y m_z,  m = 1/3 (a, b on the same side of that axis) or 1/6,  s = -1 / +1,
-//   int (d_x N_a d_y N_b + d_y N_a d_x N_b) = +- (1/2) m_z s_x(a) s_y(a)  when a, b agree on both or differ on both
-//                                              of x, y (+ / -), else 0
-// (the 2x2x2 Gauss rule integrates them exactly, so this equals the quadrature of the reference up to rounding).
-// Phase 1 stores, per element, E_c {1/9, 1/18, 1/36} (c = xx, yy, zz) and E_c {1/6, 1/12} (c = xy, xz, yz) with
-// E_c = (kappa / det J) (cof^T cof)_c: 15 numbers; every matrix entry is then a signed sum of 3 to 6 of them with
-// compile-time signs and selections: 288 additions per row instead of 384 fused multiply-adds + 64 additions, and no
-// constant-table loads.
-RG_HD void rg_instance_ss(const double* x0, const double* x1, const double* x3, const double* x4, double factor, double w,
-                          double (&T)[15], double& dw) {
-    double D[6];
-    rg_instance(x0, x1, x3, x4, factor, w, D, dw);   // D_c = (factor w / det) (cof^T cof)_c with w = 1/8
-    const double inv_w = 1.0 / w;
-    for (int c = 0; c < 3; c++) {
-        const double e = D[c] * inv_w;
-        T[c * 3] = e * (1.0 / 9.0); T[c * 3 + 1] = e * (1.0 / 18.0); T[c * 3 + 2] = e * (1.0 / 36.0);
-    }
-    for (int c = 3; c < 6; c++) {
-        const double e = D[c] * inv_w;
-        T[9 + (c - 3) * 2] = e * (1.0 / 6.0); T[9 + (c - 3) * 2 + 1] = e * (1.0 / 12.0);
-    }
-}
+// phase 2 for affine elements: the 27 stencil entries of one row from the E_c of the (up to) eight elements around its
+// node.  On the reference cube the trilinear integrals are exact rationals (the 2x2x2 Gauss rule of the reference
+// integrates them exactly, so this equals its quadrature up to rounding):
+//   int d_x N_a d_x N_b = s_x(a) s_x(b) m_y m_z,   m = 1/3 (a, b on the same side of that axis) or 1/6,  s = -1 / +1,
+//   int (d_x N_a d_y N_b + d_y N_a d_x N_b) = +-(1/2) m_z s_x(a) s_y(a)  when a, b agree on both or differ on both of
+//                                              x, y (+ / -), else 0.
+// For a FIXED stencil offset d = bits(b) - bits(a) these factors do not depend on the element any more, only on d (and,
+// for the mixed terms, on the signs s(a) of the row node inside the element), so
+//   A[i, i+d] = sum_c coef_c(d) * S_c(d),   S_c(d) = (signed) sum of E_c over the elements that contain both nodes.
+// The 27 sums S_c(d) are a tensor product of {element on the - side, both, element on the + side} per axis and are
+// formed by a three-level tree: 19 additions per diagonal component, 11 per mixed component (only the offsets with
+// d_p = d_q = 0 or both non-zero are needed), then one multiply-add per non-zero coefficient: about 215 FP64
+// operations per row and ten distinct constants, instead of 448 operations and 216 constant-table entries when the
+// eight 8-entry local rows are formed one by one.
+//   ld(A, c): E_c (c < 6) or det J w (c = 6) of the element that has the row as local node A, 0 when there is none.
 RG_HD constexpr int rg_bit(int axis, int a) { return axis == 0 ? rg_bx(a) : axis == 1 ? rg_by(a) : rg_bz(a); }
-RG_HD constexpr bool rg_same(int axis, int a, int b) { return rg_bit(axis, a) == rg_bit(axis, b); }
-RG_HD constexpr int rg_sgn(int axis, int a) { return rg_bit(axis, a) ? 1 : -1; }
-template <int A>
-RG_HD void rg_add_slot_ss(const double (&T)[15], double dw, double (&acc)[27], double& body) {
+// hierarchic vertex with the given (x, y, z) bits
+RG_HD constexpr int rg_vertex(int bx, int by, int bz) {
+    for (int a = 0; a < 8; a++)
+        if (rg_bx(a) == bx && rg_by(a) == by && rg_bz(a) == bz) return a;
+    return -1;
+}
+// one tree level along an axis: t = 0 (offset -1: the row node is on the element's + side, bit 1), t = 1 (offset 0:
+// both elements), t = 2 (offset +1: bit 0).  sgn: weight the elements with the sign s(a) = -1 (bit 0) / +1 (bit 1).
+RG_HD void rg_level(double e0, double e1, bool sgn, double& tm, double& t0, double& tp) {
+    tm = e1;
+    tp = sgn ? -e0 : e0;
+    t0 = sgn ? e1 - e0 : e0 + e1;
+}
+template <class LD>
+RG_HD void rg_row_affine(LD&& ld, double (&acc)[27], double& body) {
+    constexpr double mu[3] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 6.0};   // by offset index t = d + 1
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int b = 0; b < 8; b++) {
-        double v = acc[rg_kidx(A, b)];
-        // diagonal terms c = 0 (xx), 1 (yy), 2 (zz): sign s_c(a) s_c(b), magnitude by the two other axes
+    for (int c = 0; c < 6; c++) {
+        // axes: diagonal component c < 3 -> (c, c); mixed 3 -> (0,1), 4 -> (0,2), 5 -> (1,2)
+        const int p = (c < 3) ? c : (c == 5 ? 1 : 0), q = (c < 3) ? c : (c == 3 ? 1 : 2);
+        const bool mixed = c >= 3;
+        const bool sg[3] = {mixed && (p == 0 || q == 0), mixed && (p == 1 || q == 1), mixed && (p == 2 || q == 2)};
+        double X[2][2][3];   // [bz][by][tx]
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int c = 0; c < 3; c++) {
-            const int o1 = (c + 1) % 3, o2 = (c + 2) % 3;
-            const int mi = (rg_same(o1, A, b) ? 0 : 1) + (rg_same(o2, A, b) ? 0 : 1);
-            const double t = T[c * 3 + mi];
-            v = (rg_sgn(c, A) * rg_sgn(c, b) > 0) ? v + t : v - t;
-        }
-        // cross terms c = 3 (xy), 4 (xz), 5 (yz)
+        for (int bz = 0; bz < 2; bz++)
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int c = 3; c < 6; c++) {
-            const int p = (c == 5) ? 1 : 0, q = (c == 3) ? 1 : 2, r = 3 - p - q;
-            const bool ep = rg_same(p, A, b), eq = rg_same(q, A, b);
-            if (ep == eq) {
-                const double t = T[9 + (c - 3) * 2 + (rg_same(r, A, b) ? 0 : 1)];
-                v = ((rg_sgn(p, A) * rg_sgn(q, A) > 0) == ep) ? v + t : v - t;
+            for (int by = 0; by < 2; by++)
+                rg_level(ld(rg_vertex(0, by, bz), c), ld(rg_vertex(1, by, bz), c), sg[0], X[bz][by][0], X[bz][by][1], X[bz][by][2]);
+        double Y[2][3][3];   // [bz][ty][tx]
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int bz = 0; bz < 2; bz++)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int tx = 0; tx < 3; tx++)
+                rg_level(X[bz][0][tx], X[bz][1][tx], sg[1], Y[bz][0][tx], Y[bz][1][tx], Y[bz][2][tx]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int ty = 0; ty < 3; ty++)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int tx = 0; tx < 3; tx++) {
+                double Z[3];
+                rg_level(Y[0][ty][tx], Y[1][ty][tx], sg[2], Z[0], Z[1], Z[2]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+                for (int tz = 0; tz < 3; tz++) {
+                    const int t[3] = {tx, ty, tz};
+                    double coef;
+                    if (!mixed) {
+                        const int o1 = (c + 1) % 3, o2 = (c + 2) % 3;
+                        coef = (t[c] == 1 ? 1.0 : -1.0) * mu[t[o1]] * mu[t[o2]];
+                    } else {
+                        const int r = 3 - p - q;
+                        const bool zp = t[p] == 1, zq = t[q] == 1;
+                        if (zp != zq) continue;   // the mixed integrals vanish when a, b agree on exactly one of the two axes
+                        coef = (zp ? 0.5 : -0.5) * mu[t[r]];
+                    }
+                    acc[tz * 9 + ty * 3 + tx] = fma(coef, Z[tz], acc[tz * 9 + ty * 3 + tx]);
+                }
             }
-        }
-        acc[rg_kidx(A, b)] = v;
     }
-    body = fma(dw, RG_NSUM(A), body);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int a = 0; a < 8; a++) body = fma(ld(a, 6), RG_NSUM(a), body);
 }
 
 // general (non-affine) elements: the element's symmetric local matrix (36 numbers) and its body-force integrals
@@ -221,7 +240,43 @@ RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_el
     if ((int64_t)cnt > rn || rn > 27) return false;
     m.nnz = (uint8_t)(rn | (cnt < rn ? 0x80 : 0));
     m.lift = -1;
+    m.grow = g; m.pad = 0; m.rowstart = rowptr[g];
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// write-out of a warp's (up to) 32 rows, shared by the device kernels and the host emulation.
+// The rows of a patch are sorted by equation number, so consecutive lanes often hold consecutive CSR rows; a maximal
+// piece of consecutive rows inside the warp is a SEGMENT: one contiguous piece of the value array.  The rows are put
+// into the warp's staging buffer in CSR order (position bytes of RowMeta), segment after segment; the start of every
+// segment is shifted by 0 or 1 doubles so that staging address and global address have the same 16-byte phase, which is
+// what the bulk copy (cp.async.bulk shared -> global, SASS UBLKCP) needs.  Offsets of lane l:
+//   off  = exclusive prefix sum of the row lengths,  seg = number of segment heads at lanes <= l, minus one,
+//   fix  = (rowstart(head) ^ (off(head) + 2 seg)) & 1,  staging offset = off + 2 seg + fix.
+constexpr int RG_STAGE = 32 * 27 + 2 * 32 + 2;   // doubles per warp
+
+struct RgLane { int n, off, seg, fix, head_lane, next_head; bool head; };
+
+// lock-step evaluation for one warp on the host (the device kernel does the same with shuffles and ballots)
+inline void rg_segments_host(const int (&n)[32], const int64_t (&rs)[32], RgLane (&L)[32], int& total) {
+    int run = 0; uint32_t headmask = 0;
+    for (int l = 0; l < 32; l++) {
+        L[l].n = n[l]; L[l].off = run; run += n[l];
+        L[l].head = n[l] > 0 && (l == 0 || rs[l] != rs[l - 1] + n[l - 1]);
+        if (L[l].head) headmask |= 1u << l;
+    }
+    total = run;
+    for (int l = 0; l < 32; l++) {
+        const uint32_t le = headmask & (0xffffffffu >> (31 - l));
+        L[l].seg = __builtin_popcount(le) - 1;
+        L[l].head_lane = le ? 31 - __builtin_clz(le) : 0;
+        const uint32_t above = (l < 31) ? (headmask >> (l + 1)) : 0u;
+        L[l].next_head = above ? l + 1 + __builtin_ctz(above) : 32;
+    }
+    for (int l = 0; l < 32; l++) {
+        const int hl = L[l].head_lane;
+        L[l].fix = (int)((rs[hl] ^ (int64_t)(L[hl].off + 2 * L[l].seg)) & 1);
+    }
 }
 
 #ifdef __CUDACC__
@@ -230,25 +285,23 @@ RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_el
 struct RowsParams {
     const double* coords;
     const int32_t* p_inst_off; const int32_t* p_row_off; const int32_t* p_node_off;
-    const int32_t* rows;       // global row id of every owned local row
     const int32_t* nodes;      // global node id of every local node
     const uint16_t* i_lnode;   // [inst][8] local node index
-    const RowMeta* meta;       // per owned row (same index as rows)
-    const int64_t* rowstart;   // per owned row: rowptr[row]
+    const RowMeta* meta;       // per owned row, patch after patch
     const int32_t* lift_nodes; // [flagged rows][27] neighbour node ids
     const uint8_t* status; const double* presc; const double* values;
     double* val; double* rhs;
     double factor; int incremental; int store_mode;
     int body; double f0;
-    int node_cap, inst_cap;
+    int node_cap, inst_cap, n_patches, resident;
 };
 
-// preprocessing: one CTA per patch, threads over its rows.  pass 0 fills meta / rowstart and numbers the rows that
+// preprocessing: one CTA per patch, threads over its rows.  pass 0 fills meta and numbers the rows that
 // have CONSTRAINED neighbours (counter[0]); pass 1 writes their neighbour node ids.  err[0] != 0: some row is not eligible.
 __global__ void k_row_meta(int pass, const int32_t* p_row_off, const int32_t* p_inst_off, const int32_t* rows,
                            const uint16_t* rslot, const int32_t* inst_elem, const int32_t* conn, const int32_t* node_eqn,
                            const uint8_t* status, const int64_t* rowptr, const int32_t* col, RowMeta* meta,
-                           int64_t* rowstart, int32_t* lift_nodes, int* counter, int* err) {
+                           int32_t* lift_nodes, int* counter, int* err) {
     const int pid = blockIdx.x;
     const int r0 = p_row_off[pid], nrows = p_row_off[pid + 1] - r0;
     const int32_t* ie = inst_elem + p_inst_off[pid];
@@ -261,7 +314,6 @@ __global__ void k_row_meta(int pass, const int32_t* p_row_off, const int32_t* p_
             if (!rg_row_tables(g, rslot + (size_t)(r0 + r) * 8, ie, conn, node_eqn, status, rowptr, col, m, nbn, cnb)) { *err = 1; continue; }
             if (cnb) m.lift = atomicAdd(counter, 1);
             meta[r0 + r] = m;
-            rowstart[r0 + r] = rowptr[g];
         } else if (meta[r0 + r].lift >= 0) {
             RowMeta m;
             int32_t nbn[27];
@@ -273,201 +325,207 @@ __global__ void k_row_meta(int pass, const int32_t* p_row_off, const int32_t* p_
     }
 }
 
+__device__ __forceinline__ void rg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// matrix write-out of a warp's 32 rows: sixteen rows at a time through the warp's staging buffer into CSR order, then
-// stores along the rows.  When the sixteen rows are consecutive in the CSR arrays (the usual case: consecutive
-// equation numbers) the staged block is one contiguous piece of the value array and is streamed with all 32 lanes.
-__device__ __forceinline__ void rg_write_rows(const RowsParams& p, const RowMeta& m, const double (&acc)[27], bool act, int myn,
-                                              int64_t rs, double* st, int lane) {
-#pragma unroll 1
-    for (int h = 0; h < 2; h++) {
-        const bool mine = (lane >> 4) == h;
-        int incl = mine ? myn : 0;
+// matrix write-out of a warp's 32 rows (see the comment at RG_STAGE): staging in CSR order, then one bulk copy
+// (store mode) or bulk reduction (accumulate mode: cp.reduce.async.bulk .add.f64, SASS UBLKRED) per segment, issued
+// by the segment's head lane; an odd first / last element of a segment goes out as a plain store / atomic add.
+__device__ __forceinline__ void rg_write_rows(const RowsParams& p, const RowMeta& m, const double (&acc)[27], bool act, double* st,
+                                              int lane) {
+    const int n = act ? (m.nnz & 0x7f) : 0;
+    const int64_t rs = act ? m.rowstart : 0;
+    int incl = n;
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d, 16);
-            if ((lane & 15) >= d) incl += v;
-        }
-        const int off = incl - (mine ? myn : 0);
-        if (mine && act) {
-            if (m.nnz & 0x80) {
-#pragma unroll
-                for (int k = 0; k < 27; k++)
-                    if (k < myn) st[off + k] = 0.;
-            }
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int off = incl - n;
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int64_t rs_prev = __shfl_up_sync(0xffffffffu, rs, 1);
+    const int n_prev = __shfl_up_sync(0xffffffffu, n, 1);
+    const bool head = n > 0 && (lane == 0 || rs != rs_prev + n_prev);
+    const uint32_t headmask = __ballot_sync(0xffffffffu, head);
+    const uint32_t le = headmask & (0xffffffffu >> (31 - lane));
+    const int seg = __popc(le) - 1;
+    const int head_lane = le ? 31 - __clz(le) : 0;
+    const uint32_t above = (lane < 31) ? (headmask >> (lane + 1)) : 0u;
+    const int next_head = above ? lane + __ffs(above) : 32;
+    const int head_off = __shfl_sync(0xffffffffu, off, head_lane);
+    const int64_t head_rs = __shfl_sync(0xffffffffu, rs, head_lane);
+    const int fix = (int)((head_rs ^ (int64_t)(head_off + 2 * seg)) & 1);
+    const int so = off + 2 * seg + fix;
+    const int end_off = __shfl_sync(0xffffffffu, off, next_head & 31);
+    const int seg_len = (next_head < 32 ? end_off : total) - off;   // meaningful on head lanes
+    if (n > 0) {
+        if (m.nnz & 0x80) {
 #pragma unroll
             for (int k = 0; k < 27; k++)
-                if (m.pos[k] != 0xff) st[off + m.pos[k]] = acc[k];
+                if (k < n) st[so + k] = 0.;
         }
-        const int64_t rs_next = __shfl_down_sync(0xffffffffu, rs, 1);
-        const int n_next = __shfl_down_sync(0xffffffffu, myn, 1);
-        const bool ok = !mine || (lane & 15) == 15 || n_next == 0 || rs_next == rs + myn;
-        const bool contiguous = __all_sync(0xffffffffu, ok);
-        __syncwarp();
-        if (contiguous) {
-            const int total = __shfl_sync(0xffffffffu, incl, h * 16 + 15);
-            const int64_t rs0 = __shfl_sync(0xffffffffu, rs, h * 16);
-            if (p.store_mode) {
-                for (int q = lane; q < total; q += 32) p.val[rs0 + q] = st[q];
-            } else {
-                for (int q = lane; q < total; q += 32) p.val[rs0 + q] += st[q];
-            }
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < 16; j++) {
-                const int src = h * 16 + j;
-                const int64_t rsj = __shfl_sync(0xffffffffu, rs, src);
-                const int nj = __shfl_sync(0xffffffffu, myn, src);
-                const int oj = __shfl_sync(0xffffffffu, off, src);
-                if (lane < nj) {
-                    if (p.store_mode) p.val[rsj + lane] = st[oj + lane];
-                    else p.val[rsj + lane] += st[oj + lane];
-                }
+#pragma unroll
+        for (int k = 0; k < 27; k++)
+            if (m.pos[k] != 0xff) st[so + m.pos[k]] = acc[k];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (head) {
+        int64_t g0 = rs;
+        int s0 = so, len = seg_len;
+        if (g0 & 1) {
+            if (p.store_mode) p.val[g0] = st[s0]; else atomicAdd(p.val + g0, st[s0]);
+            g0++; s0++; len--;
+        }
+        if (len & 1) {
+            if (p.store_mode) p.val[g0 + len - 1] = st[s0 + len - 1]; else atomicAdd(p.val + g0 + len - 1, st[s0 + len - 1]);
+            len--;
+        }
+        if (len > 0) {
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(st + s0);
+            if (p.store_mode)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.val + g0), "r"(sa), "r"(len * 8) : "memory");
+            else
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(p.val + g0), "r"(sa), "r"(len * 8) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+
+// right-hand side of one row: Dirichlet lift of CONSTRAINED stencil neighbours (assembleMatrix.hpp:56-130) and body
+// force; added with a reduction (no round trip: every row is owned by exactly one thread of one CTA)
+__device__ __forceinline__ void rg_rhs(const RowsParams& p, const RowMeta& m, const double (&acc)[27], double body) {
+    double lift = 0.;
+    if (m.lift >= 0) {
+        const int32_t* ln = p.lift_nodes + (size_t)m.lift * 27;
+#pragma unroll
+        for (int k = 0; k < 27; k++) {
+            const int32_t nd = __ldg(ln + k);
+            if (nd >= 0 && m.pos[k] == 0xff && p.status[nd] == ISL_CONSTRAINED) {
+                const double gv = p.incremental ? p.presc[nd] - p.values[nd] : p.presc[nd];
+                lift = fma(gv, acc[k], lift);
             }
         }
-        __syncwarp();
     }
+    const double v = (p.body ? p.f0 * body : 0.) - lift;
+    if (v != 0.) atomicAdd(p.rhs + m.grow, v);
 }
 
-template <int A>
-__device__ __forceinline__ void rg_gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
-    const int s = m.slot[A];
-    if (s != 0xffff) {
-        double D[6];
+__device__ __forceinline__ void rg_load_meta(RowMeta& m, const RowMeta* src) {
+    const int4* mp = reinterpret_cast<const int4*>(src);
+    int4* md = reinterpret_cast<int4*>(&m);
+    md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2); md[3] = __ldg(mp + 3);
+}
+
+// the patch that will run on this CTA's slot next is about `resident` patches ahead: pull its row tables, instance
+// nodes and node list into L2 (cp.async.bulk.prefetch.L2, SASS UBLKPF) so that its prologue hits L2 instead of DRAM
+__device__ __forceinline__ void rg_prefetch_patch(const RowsParams& p, int pid) {
+    if (pid >= p.n_patches) return;
+    const int r0 = p.p_row_off[pid], r1 = p.p_row_off[pid + 1];
+    const int e0 = p.p_inst_off[pid], e1 = p.p_inst_off[pid + 1];
+    const int n0 = p.p_node_off[pid], n1 = p.p_node_off[pid + 1];
+    const char* b0 = reinterpret_cast<const char*>(p.meta + r0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0), "r"((r1 - r0) * 64) : "memory");
+    const char* b1 = reinterpret_cast<const char*>(p.i_lnode + (size_t)e0 * 8);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b1), "r"((e1 - e0) * 16) : "memory");
+    const size_t a2 = reinterpret_cast<size_t>(p.nodes + n0) & ~(size_t)15;
+    const int nb2 = (int)((reinterpret_cast<size_t>(p.nodes + n1) + 15 - a2) & ~(size_t)15);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a2), "r"(nb2) : "memory");
+}
+
+// nodal coordinates of the patch -> shared memory (two dependent global loads: node id, then its coordinates)
+template <int NT>
+__device__ __forceinline__ void rg_load_coords(const RowsParams& p, double* sX, int n0, int nnodes, int tid) {
+    constexpr int U = 4;
+    for (int nb = 0; nb < nnodes; nb += U * NT) {
+        int32_t g[U];
 #pragma unroll
-        for (int c = 0; c < 6; c++) D[c] = sD[c * cap + s];
-        rg_add_slot<A>(D, sD[6 * cap + s], acc, body);
-    }
-}
-
-template <int A>
-__device__ __forceinline__ void rg_gather_slot_ss(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
-    const int s = m.slot[A];
-    if (s != 0xffff) {
-        double T[15];
+        for (int i = 0; i < U; i++) { const int n = nb + i * NT + tid; g[i] = (n < nnodes) ? __ldg(p.nodes + n0 + n) : 0; }
+        double x[U][3];
 #pragma unroll
-        for (int c = 0; c < 15; c++) T[c] = sD[c * cap + s];
-        rg_add_slot_ss<A>(T, sD[15 * cap + s], acc, body);
+        for (int i = 0; i < U; i++) {
+            const double* c = p.coords + (size_t)g[i] * 3;
+            x[i][0] = __ldg(c); x[i][1] = __ldg(c + 1); x[i][2] = __ldg(c + 2);
+        }
+#pragma unroll
+        for (int i = 0; i < U; i++) {
+            const int n = nb + i * NT + tid;
+            if (n < nnodes) { sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
+        }
     }
 }
 
-// one CTA per patch.  Shared memory: sD[7 (SS: 16)][inst_cap] | (sX[node_cap][3]  aliased after phase 1 by  stage[NT/32][16*27])
-template <int NT, int MINB, bool SS = false>
+// one CTA per patch.  Shared memory: sD[7][inst_cap] | (sX[node_cap][3]  aliased after phase 1 by  stage[NT/32][RG_STAGE]);
+// instance inst_cap-1 is a zero element (rows with fewer than eight elements around them)
+template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams p) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double* sD = smem;
-    double* sX = sD + (size_t)(SS ? 16 : 7) * p.inst_cap;
+    double* sX = sD + (size_t)7 * p.inst_cap;
     double* stage = sX;
     const int tid = threadIdx.x;
     const int pid = blockIdx.x;
     const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
     const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
     const int e0 = p.p_inst_off[pid], ninst = p.p_inst_off[pid + 1] - e0;
-    {
-        // the patch's element instances and row tables are contiguous: pull them into L2 while the coordinates load
-        const char* b1 = reinterpret_cast<const char*>(p.i_lnode + (size_t)e0 * 8);
-        for (size_t o = (size_t)tid * 128; o < (size_t)ninst * 16; o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
-        const char* b2 = reinterpret_cast<const char*>(p.meta + r0);
-        for (size_t o = (size_t)tid * 128; o < (size_t)nrows * sizeof(RowMeta); o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
+    // everything that does not depend on other threads is requested first: instance nodes, the row table of the first row
+    constexpr int UI = 4;
+    int4 ln4[UI];
+#pragma unroll
+    for (int u = 0; u < UI; u++) {
+        const int i = u * NT + tid;
+        ln4[u] = (i < ninst) ? __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8)) : make_int4(0, 0, 0, 0);
     }
-    // nodal coordinates of the patch -> shared memory
-    {
-        constexpr int U = 4;
-        for (int nb = 0; nb < nnodes; nb += U * NT) {
-            int32_t g[U];
-#pragma unroll
-            for (int i = 0; i < U; i++) { const int n = nb + i * NT + tid; g[i] = (n < nnodes) ? __ldg(p.nodes + n0 + n) : 0; }
-            double x[U][3];
-#pragma unroll
-            for (int i = 0; i < U; i++) {
-                const double* c = p.coords + (size_t)g[i] * 3;
-                x[i][0] = __ldg(c); x[i][1] = __ldg(c + 1); x[i][2] = __ldg(c + 2);
-            }
-#pragma unroll
-            for (int i = 0; i < U; i++) {
-                const int n = nb + i * NT + tid;
-                if (n < nnodes) { sX[n * 3] = x[i][0]; sX[n * 3 + 1] = x[i][1]; sX[n * 3 + 2] = x[i][2]; }
-            }
-        }
-    }
+    RowMeta m;
+    if (tid < nrows) rg_load_meta(m, p.meta + r0 + tid);
+    rg_load_coords<NT>(p, sX, n0, nnodes, tid);
+    if (tid < 7) sD[tid * p.inst_cap + p.inst_cap - 1] = 0.;
+    if (tid == NT - 1) rg_prefetch_patch(p, pid + p.resident);
     __syncthreads();
     // phase 1: element instances
     const double w = c_q1_w[0];
-    for (int i = tid; i < ninst; i += NT) {
-        const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8));
+    auto instance = [&](int i, const int4& l4) {
         const int n0l = l4.x & 0xffff, n1l = (unsigned)l4.x >> 16, n3l = (unsigned)l4.y >> 16, n4l = l4.z & 0xffff;
-        if (SS) {
-            double T[15], dw;
-            rg_instance_ss(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, T, dw);
+        double E[6], dw;
+        rg_instance(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, E, dw);
 #pragma unroll
-            for (int c = 0; c < 15; c++) sD[c * p.inst_cap + i] = T[c];
-            sD[15 * p.inst_cap + i] = dw;
-        } else {
-            double D[6], dw;
-            rg_instance(sX + n0l * 3, sX + n1l * 3, sX + n3l * 3, sX + n4l * 3, p.factor, w, D, dw);
+        for (int c = 0; c < 6; c++) sD[c * p.inst_cap + i] = E[c];
+        sD[6 * p.inst_cap + i] = dw;
+    };
 #pragma unroll
-            for (int c = 0; c < 6; c++) sD[c * p.inst_cap + i] = D[c];
-            sD[6 * p.inst_cap + i] = dw;
-        }
+    for (int u = 0; u < UI; u++) {
+        const int i = u * NT + tid;
+        if (i < ninst) instance(i, ln4[u]);
     }
+    for (int i = UI * NT + tid; i < ninst; i += NT)
+        instance(i, __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8)));
     __syncthreads();  // sD complete; sX is dead from here on (stage aliases it)
     // phase 2: owned rows
     const int lane = tid & 31, warp = tid >> 5;
-    double* st = stage + (size_t)warp * (16 * 27);
+    double* st = stage + (size_t)warp * RG_STAGE;
+    const int zs = p.inst_cap - 1;
     for (int rb = 0; rb < nrows; rb += NT) {
         const int r = rb + tid;
         const bool act = r < nrows;
-        RowMeta m;
-        int64_t rs = 0;
+        if (rb > 0) {
+            if (act) rg_load_meta(m, p.meta + r0 + r);
+            rg_bulk_wait_read();   // the bulk copies of the previous round have read the staging buffer
+            __syncwarp();
+        }
+        if (r + NT < nrows) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.meta + r0 + r + NT));
         double acc[27];
 #pragma unroll
         for (int k = 0; k < 27; k++) acc[k] = 0.;
-        int myn = 0;
         if (act) {
-            const int4* mp = reinterpret_cast<const int4*>(p.meta + r0 + r);
-            int4* md = reinterpret_cast<int4*>(&m);
-            md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2);
-            rs = __ldg(p.rowstart + r0 + r);
-            myn = m.nnz & 0x7f;
-            double body = 0.;
-            if (SS) {
-                rg_gather_slot_ss<0>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<1>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<2>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<3>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<4>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<5>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<6>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot_ss<7>(m, sD, p.inst_cap, acc, body);
-            } else {
-                rg_gather_slot<0>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<1>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<2>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<3>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<4>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<5>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<6>(m, sD, p.inst_cap, acc, body);
-                rg_gather_slot<7>(m, sD, p.inst_cap, acc, body);
-            }
-            // right-hand side: Dirichlet lift of CONSTRAINED stencil neighbours (assembleMatrix.hpp:56-130), body force
-            double lift = 0.;
-            if (m.lift >= 0) {
-                const int32_t* ln = p.lift_nodes + (size_t)m.lift * 27;
+            int sl[8];
 #pragma unroll
-                for (int k = 0; k < 27; k++) {
-                    const int32_t nd = __ldg(ln + k);
-                    if (nd >= 0 && m.pos[k] == 0xff && p.status[nd] == ISL_CONSTRAINED) {
-                        const double gv = p.incremental ? p.presc[nd] - p.values[nd] : p.presc[nd];
-                        lift = fma(gv, acc[k], lift);
-                    }
-                }
-            }
-            const double v = (p.body ? p.f0 * body : 0.) - lift;
-            if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
+            for (int a = 0; a < 8; a++) sl[a] = min((int)m.slot[a], zs);
+            double body = 0.;
+            rg_row_affine([&](int a, int c) { return sD[c * p.inst_cap + sl[a]]; }, acc, body);
+            rg_rhs(p, m, acc, body);
         }
-        // matrix: sixteen rows at a time through the warp's staging buffer into CSR order, then row-contiguous stores
-        rg_write_rows(p, m, acc, act, myn, rs, st, lane);
+        rg_write_rows(p, m, acc, act, st, lane);
     }
+    rg_bulk_wait_read();   // shared memory must stay valid until the bulk copies have read it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -482,7 +540,7 @@ __device__ __forceinline__ void rg_gather_slot_general(const RowMeta& m, const d
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParams p) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     double* sK = smem;
     double* sX = sK + (size_t)44 * p.inst_cap;
     double* stage = sX;
@@ -491,20 +549,18 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
     const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
     const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
     const int e0 = p.p_inst_off[pid], ninst = p.p_inst_off[pid + 1] - e0;
-    {
-        const char* b1 = reinterpret_cast<const char*>(p.i_lnode + (size_t)e0 * 8);
-        for (size_t o = (size_t)tid * 128; o < (size_t)ninst * 16; o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
-        const char* b2 = reinterpret_cast<const char*>(p.meta + r0);
-        for (size_t o = (size_t)tid * 128; o < (size_t)nrows * sizeof(RowMeta); o += (size_t)NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + o));
+    constexpr int UI = 2;
+    int4 ln4[UI];
+#pragma unroll
+    for (int u = 0; u < UI; u++) {
+        const int i = u * NT + tid;
+        ln4[u] = (i < ninst) ? __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8)) : make_int4(0, 0, 0, 0);
     }
-    for (int n = tid; n < nnodes; n += NT) {
-        const double* c = p.coords + (size_t)__ldg(p.nodes + n0 + n) * 3;
-        sX[n * 3] = __ldg(c); sX[n * 3 + 1] = __ldg(c + 1); sX[n * 3 + 2] = __ldg(c + 2);
-    }
+    rg_load_coords<NT>(p, sX, n0, nnodes, tid);
+    if (tid == NT - 1) rg_prefetch_patch(p, pid + p.resident);
     __syncthreads();
     // phase 1: local matrices of the element instances
-    for (int i = tid; i < ninst; i += NT) {
-        const int4 l4 = __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8));
+    auto instance = [&](int i, const int4& l4) {
         const int ln[8] = {l4.x & 0xffff, (int)((unsigned)l4.x >> 16), l4.y & 0xffff, (int)((unsigned)l4.y >> 16),
                            l4.z & 0xffff, (int)((unsigned)l4.z >> 16), l4.w & 0xffff, (int)((unsigned)l4.w >> 16)};
         double X[8][3];
@@ -516,26 +572,29 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
         for (int k = 0; k < 36; k++) sK[k * p.inst_cap + i] = K[k];
 #pragma unroll
         for (int a = 0; a < 8; a++) sK[(36 + a) * p.inst_cap + i] = bf[a];
+    };
+#pragma unroll 1
+    for (int u = 0; u < UI; u++) {
+        const int i = u * NT + tid;
+        if (i < ninst) instance(i, ln4[u]);
     }
+#pragma unroll 1
+    for (int i = UI * NT + tid; i < ninst; i += NT)
+        instance(i, __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8)));
     __syncthreads();  // sK complete; sX is dead from here on (stage aliases it)
     // phase 2: owned rows (identical to k_q1hex_rows_affine apart from the slot routine)
     const int lane = tid & 31, warp = tid >> 5;
-    double* st = stage + (size_t)warp * (16 * 27);
+    double* st = stage + (size_t)warp * RG_STAGE;
     for (int rb = 0; rb < nrows; rb += NT) {
         const int r = rb + tid;
         const bool act = r < nrows;
         RowMeta m;
-        int64_t rs = 0;
+        if (act) rg_load_meta(m, p.meta + r0 + r);
+        if (rb > 0) { rg_bulk_wait_read(); __syncwarp(); }
         double acc[27];
 #pragma unroll
         for (int k = 0; k < 27; k++) acc[k] = 0.;
-        int myn = 0;
         if (act) {
-            const int4* mp = reinterpret_cast<const int4*>(p.meta + r0 + r);
-            int4* md = reinterpret_cast<int4*>(&m);
-            md[0] = __ldg(mp); md[1] = __ldg(mp + 1); md[2] = __ldg(mp + 2);
-            rs = __ldg(p.rowstart + r0 + r);
-            myn = m.nnz & 0x7f;
             double body = 0.;
             rg_gather_slot_general<0>(m, sK, p.inst_cap, acc, body);
             rg_gather_slot_general<1>(m, sK, p.inst_cap, acc, body);
@@ -545,22 +604,10 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
             rg_gather_slot_general<5>(m, sK, p.inst_cap, acc, body);
             rg_gather_slot_general<6>(m, sK, p.inst_cap, acc, body);
             rg_gather_slot_general<7>(m, sK, p.inst_cap, acc, body);
-            double lift = 0.;
-            if (m.lift >= 0) {
-                const int32_t* ln = p.lift_nodes + (size_t)m.lift * 27;
-#pragma unroll
-                for (int k = 0; k < 27; k++) {
-                    const int32_t nd = __ldg(ln + k);
-                    if (nd >= 0 && m.pos[k] == 0xff && p.status[nd] == ISL_CONSTRAINED) {
-                        const double gv = p.incremental ? p.presc[nd] - p.values[nd] : p.presc[nd];
-                        lift = fma(gv, acc[k], lift);
-                    }
-                }
-            }
-            const double v = (p.body ? p.f0 * body : 0.) - lift;
-            if (v != 0.) { const int32_t g = __ldg(p.rows + r0 + r); p.rhs[g] += v; }
+            rg_rhs(p, m, acc, body);
         }
-        rg_write_rows(p, m, acc, act, myn, rs, st, lane);
+        rg_write_rows(p, m, acc, act, st, lane);
     }
+    rg_bulk_wait_read();
 }
 #endif  // __CUDACC__

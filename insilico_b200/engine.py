@@ -30,7 +30,7 @@ SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
 
 # every symbol include/insilico_b200.h declares (checked by tests/test_cabi.py)
 EXPORTED = [
-    "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_engine_set_option", "isl_synchronize",
+    "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_engine_set_option", "isl_synchronize", "isl_flush",
     "isl_engine_stream",
     "isl_kernel_launches", "isl_measure_fp64_peak", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
@@ -216,6 +216,11 @@ class Engine:
 
     def synchronize(self):
         _chk(lib().isl_synchronize(self.h))
+
+    def flush(self):
+        """launch what the engine has deferred (the Q1 stiffness launch waits one call for a body force to fuse), without
+        waiting for the device"""
+        _chk(lib().isl_flush(self.h))
 
     def measure_fp64_peak(self):
         """measured DFMA peak of the device in TFLOP/s (denominator of the FP64-pipe roofline fraction)"""

@@ -60,7 +60,9 @@ struct LinearConstraint {       // base/dof/Constraint.hpp: u(obj,comp) = rhs + 
 };
 struct FieldSpec {
     std::string presc, values;  // raw f64 files [n_obj][ds] ("-" = none)
-    int boundary = 0;           // constrain the whole boundary through dof::constrainBoundary
+    int boundary = 0;           // 1: constrain the whole boundary through dof::constrainBoundary; 2: constrain exactly
+                                // the DoF components whose entry in the `status` table (raw f64 [n_obj][ds]) is 1
+    std::string status;
     long pin = -1;              // constrainValue(0, 0.) on this DoF object
     std::vector<LinearConstraint> linear;
 };
@@ -103,6 +105,7 @@ static Job readJob(const char* file) {
             int i;
             FieldSpec f;
             s >> i >> f.boundary >> f.pin >> f.presc >> f.values;
+            if (f.boundary == 2) s >> f.status;
             j.fields[i] = f;
         } else if (key == "constraint") {
             int i, nm;
@@ -160,7 +163,12 @@ void setUpField(const MESH& mesh, FIELD& field, const FieldSpec& spec, const bas
     typedef typename FIELD::DegreeOfFreedom DoF;
     base::dof::generate<FEBASIS>(mesh, field);
     const std::vector<double> presc = readF64(spec.presc), values = readF64(spec.values);
-    if (spec.boundary) {
+    if (spec.boundary == 2) {
+        const std::vector<double> st = readF64(spec.status);
+        for (typename FIELD::DoFPtrIter it = field.doFsBegin(); it != field.doFsEnd(); ++it)
+            for (unsigned d = 0; d < DoF::size; d++)
+                if (st[(*it)->getID() * DoF::size + d] == 1.0) (*it)->constrainValue(d, presc[(*it)->getID() * DoF::size + d]);
+    } else if (spec.boundary) {
         typedef typename base::Vector<MESH::Node::dim>::Type VecDim;
         base::dof::constrainBoundary<FEBASIS>(boundary.begin(), boundary.end(), mesh, field,
                                               boost::bind(&prescribeFromTable<DoF, VecDim>, _1, _2, &presc));

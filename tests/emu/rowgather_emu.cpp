@@ -1,7 +1,7 @@
 // Host emulation of the row-gather kernel (insilico_b200/csrc/isl_rowgather.cuh) -- TEST INFRASTRUCTURE ONLY.
-// Compiles the kernel's per-thread routines (rg_instance, rg_add_slot, rg_row_tables) and the host preprocessing
+// Compiles the kernel's per-thread routines (rg_instance, rg_row_affine, rg_add_slot_general, rg_row_tables, the segment arithmetic of the write-out) and the host preprocessing
 // (isl_patch_host.hpp) with g++ and replays k_row_meta / k_q1hex_rows_affine patch by patch, thread by thread, including
-// the per-warp staging (segmented shuffle scan, sixteen rows per round), so that the algorithm, its tables and its
+// the per-warp staging (segments of consecutive rows, 16-byte phase of the bulk copies), so that the algorithm, its tables and its
 // index arithmetic can be checked against the oracle on a machine without a GPU (tests/test_rowgather_emu.py).
 // Nothing in the product links or loads this file.
 #include <algorithm>
@@ -56,17 +56,6 @@ void fill_tables() {
     const isl::Basis B(ISL_HEX, 1);
     std::vector<double> dN(8 * 8 * 3), N(8), Nq(64);
     for (int q = 0; q < 8; q++) { B.eval(&R.p[q * 3], N.data(), &dN[q * 24]); for (int a = 0; a < 8; a++) Nq[q * 8 + a] = N[a]; }
-    const int al[6] = {0, 1, 2, 0, 0, 1}, be[6] = {0, 1, 2, 1, 2, 2};
-    for (int c = 0; c < 6; c++)
-        for (int a = 0; a < 8; a++)
-            for (int b = a; b < 8; b++) {
-                double v = 0.;
-                for (int q = 0; q < 8; q++) {
-                    v += dN[q * 24 + a * 3 + al[c]] * dN[q * 24 + b * 3 + be[c]];
-                    if (al[c] != be[c]) v += dN[q * 24 + a * 3 + be[c]] * dN[q * 24 + b * 3 + al[c]];
-                }
-                rg_host_aff[c * 36 + sym_idx(a, b)] = v;
-            }
     for (int a = 0; a < 8; a++) { rg_host_nsum[a] = 0.; for (int q = 0; q < 8; q++) rg_host_nsum[a] += Nq[q * 8 + a]; }
     g_w0 = R.w[0];
     for (int k = 0; k < 192; k++) g_dN[k] = dN[k];
@@ -75,30 +64,11 @@ void fill_tables() {
 }
 
 template <int A>
-void gather_slot_ss(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
-    const int s = m.slot[A];
-    if (s != 0xffff) {
-        double T[15];
-        for (int c = 0; c < 15; c++) T[c] = sD[c * cap + s];
-        rg_add_slot_ss<A>(T, sD[15 * cap + s], acc, body);
-    }
-}
-
-template <int A>
 void gather_slot_general(const RowMeta& m, const double* sK, int cap, double (&acc)[27], double& body) {
     const int s = m.slot[A];
     if (s != 0xffff) rg_add_slot_general<A>([&](int i) { return sK[i * cap + s]; }, acc, body);
 }
 
-template <int A>
-void gather_slot(const RowMeta& m, const double* sD, int cap, double (&acc)[27], double& body) {
-    const int s = m.slot[A];
-    if (s != 0xffff) {
-        double D[6];
-        for (int c = 0; c < 6; c++) D[c] = sD[c * cap + s];
-        rg_add_slot<A>(D, sD[6 * cap + s], acc, body);
-    }
-}
 }  // namespace
 
 // conn lists the OWNED elements only; the pattern (rowptr, col) may contain more columns (pattern-only halo elements)
@@ -131,7 +101,6 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
     const size_t nr = P.rows.size();
     // k_row_meta, pass 0 and 1
     std::vector<RowMeta> meta(nr);
-    std::vector<int64_t> rowstart(nr);
     std::vector<int32_t> lift_nodes;
     int counter = 0;
     for (int pid = 0; pid < n_patches; pid++) {
@@ -143,12 +112,11 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
             if (!rg_row_tables(g, P.rslot.data() + (size_t)(r0 + r) * 8, ie, conn, node_eqn, status, rowptr, col, m, nbn, cnb)) return 1;
             if (cnb) { m.lift = counter++; lift_nodes.insert(lift_nodes.end(), nbn, nbn + 27); }
             meta[r0 + r] = m;
-            rowstart[r0 + r] = rowptr[g];
         }
     }
     stats[0] = n_patches; stats[1] = (int64_t)P.inst_elem.size(); stats[2] = counter; stats[3] = stats[4] = 0;
-    const int inst_cap = (P.max_inst + 1) & ~1;
-    std::vector<double> sD((size_t)(general == 1 ? 44 : general == 2 ? 16 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * 16 * 27);
+    const int inst_cap = (P.max_inst + 2) & ~1;
+    std::vector<double> sD((size_t)(general == 1 ? 44 : 7) * inst_cap), sX((size_t)P.max_nodes * 3), stage((size_t)(NT / 32) * RG_STAGE);
     for (int pid = 0; pid < n_patches; pid++) {
         const int r0 = P.row_off[pid], nrows = P.row_off[pid + 1] - r0;
         const int n0 = P.node_off[pid], nnodes = P.node_off[pid + 1] - n0;
@@ -157,13 +125,6 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
         // phase 1
         for (int i = 0; i < ninst; i++) {
             const uint16_t* ln = P.lnode.data() + (size_t)(e0 + i) * 8;
-            if (general == 2) {  // k_q1hex_rows_affine<.., SS = true>
-                double T[15], dw;
-                rg_instance_ss(&sX[ln[0] * 3], &sX[ln[1] * 3], &sX[ln[3] * 3], &sX[ln[4] * 3], factor, g_w0, T, dw);
-                for (int c = 0; c < 15; c++) sD[c * inst_cap + i] = T[c];
-                sD[15 * inst_cap + i] = dw;
-                continue;
-            }
             if (general == 1) {  // k_q1hex_rows_general
                 double X[8][3], K[36], bf[8];
                 for (int a = 0; a < 8; a++) for (int d = 0; d < 3; d++) X[a][d] = sX[ln[a] * 3 + d];
@@ -177,33 +138,29 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
             for (int c = 0; c < 6; c++) sD[c * inst_cap + i] = D[c];
             sD[6 * inst_cap + i] = dw;
         }
+        if (general != 1) for (int c = 0; c < 7; c++) sD[c * inst_cap + inst_cap - 1] = 0.;   // the zero element
         // phase 2, warp by warp (32 lanes in lock step)
         for (int rb = 0; rb < nrows; rb += NT) {
             for (int warp = 0; warp < NT / 32; warp++) {
-                double* st = stage.data() + (size_t)warp * 16 * 27;
+                double* st = stage.data() + (size_t)warp * RG_STAGE;
                 RowMeta m[32]; int64_t rs[32]; double acc[32][27]; int myn[32]; bool act[32];
                 for (int lane = 0; lane < 32; lane++) {
                     const int tid = warp * 32 + lane, r = rb + tid;
                     act[lane] = r < nrows; rs[lane] = 0; myn[lane] = 0;
                     for (int k = 0; k < 27; k++) acc[lane][k] = 0.;
                     if (!act[lane]) continue;
-                    m[lane] = meta[r0 + r]; rs[lane] = rowstart[r0 + r]; myn[lane] = m[lane].nnz & 0x7f;
+                    m[lane] = meta[r0 + r]; rs[lane] = m[lane].rowstart; myn[lane] = m[lane].nnz & 0x7f;
+                    if (m[lane].grow != P.rows[r0 + r] || m[lane].rowstart != rowptr[m[lane].grow]) return 2;
                     double bsum = 0.;
-                    if (general == 2) {
-                        gather_slot_ss<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                        gather_slot_ss<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                        gather_slot_ss<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                        gather_slot_ss<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_ss<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                    } else if (general == 1) {
+                    if (general == 1) {
                         gather_slot_general<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                         gather_slot_general<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                         gather_slot_general<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                         gather_slot_general<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot_general<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
                     } else {
-                    gather_slot<0>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<1>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                    gather_slot<2>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<3>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                    gather_slot<4>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<5>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
-                    gather_slot<6>(m[lane], sD.data(), inst_cap, acc[lane], bsum); gather_slot<7>(m[lane], sD.data(), inst_cap, acc[lane], bsum);
+                        int sl[8];
+                        for (int a = 0; a < 8; a++) sl[a] = std::min((int)m[lane].slot[a], inst_cap - 1);
+                        rg_row_affine([&](int a, int c) { return sD[(size_t)c * inst_cap + sl[a]]; }, acc[lane], bsum);
                     }
                     double lift = 0.;
                     if (m[lane].lift >= 0) {
@@ -217,50 +174,35 @@ extern "C" int emu_rowgather(int64_t n_nodes, int64_t n_elems, const double* coo
                         }
                     }
                     const double v = (body ? f0 * bsum : 0.) - lift;
-                    if (v != 0.) rhs[P.rows[r0 + r]] += v;
+                    if (v != 0.) rhs[m[lane].grow] += v;
                 }
-                for (int h = 0; h < 2; h++) {
-                    int incl[32], off[32];
-                    for (int lane = 0; lane < 32; lane++) incl[lane] = ((lane >> 4) == h) ? myn[lane] : 0;
-                    for (int d = 1; d < 16; d <<= 1) {  // __shfl_up_sync(.., d, 16): segments of 16 lanes
-                        int v[32];
-                        for (int lane = 0; lane < 32; lane++) v[lane] = ((lane & 15) >= d) ? incl[lane - d] : incl[lane];
-                        for (int lane = 0; lane < 32; lane++) if ((lane & 15) >= d) incl[lane] += v[lane];
-                    }
-                    for (int lane = 0; lane < 32; lane++) off[lane] = incl[lane] - (((lane >> 4) == h) ? myn[lane] : 0);
-                    for (int lane = 0; lane < 32; lane++)
-                        if ((lane >> 4) == h && act[lane]) {
-                            if (m[lane].nnz & 0x80) for (int k = 0; k < 27; k++) if (k < myn[lane]) st[off[lane] + k] = 0.;
-                            for (int k = 0; k < 27; k++) if (m[lane].pos[k] != 0xff) st[off[lane] + m[lane].pos[k]] = acc[lane][k];
-                        }
-                    // rg_write_rows: contiguity vote (__shfl_down_sync by 1, __all_sync), then one streamed block or row by row
-                    bool contiguous = true;
-                    for (int lane = 0; lane < 32; lane++) {
-                        const bool mine = (lane >> 4) == h;
-                        const int64_t rs_next = lane < 31 ? rs[lane + 1] : rs[lane];
-                        const int n_next = lane < 31 ? myn[lane + 1] : myn[lane];
-                        const bool ok = !mine || (lane & 15) == 15 || n_next == 0 || rs_next == rs[lane] + myn[lane];
-                        contiguous = contiguous && ok;
-                    }
-                    if (contiguous) {
-                        const int total = incl[h * 16 + 15];
-                        const int64_t rs0 = rs[h * 16];
-                        for (int lane = 0; lane < 32; lane++)
-                            for (int q = lane; q < total; q += 32) {
-                                if (store_mode) val[rs0 + q] = st[q]; else val[rs0 + q] += st[q];
-                            }
+                // rg_write_rows: segments of consecutive rows, staged with the 16-byte phase of their global address, one
+                // bulk copy per segment (an odd first / last element leaves as a plain store)
+                RgLane L[32]; int total = 0;
+                rg_segments_host(myn, rs, L, total);
+                std::vector<double> poison(RG_STAGE, std::nan(""));
+                std::copy(poison.begin(), poison.end(), st);
+                for (int lane = 0; lane < 32; lane++) {
+                    if (myn[lane] == 0) continue;
+                    const int so = L[lane].off + 2 * L[lane].seg + L[lane].fix;
+                    if (so + myn[lane] > RG_STAGE) return 3;
+                    if (m[lane].nnz & 0x80) for (int k = 0; k < myn[lane]; k++) st[so + k] = 0.;
+                    for (int k = 0; k < 27; k++) if (m[lane].pos[k] != 0xff) st[so + m[lane].pos[k]] = acc[lane][k];
+                }
+                for (int lane = 0; lane < 32; lane++) {
+                    if (!L[lane].head) continue;
+                    int64_t g0 = rs[lane];
+                    int s0 = L[lane].off + 2 * L[lane].seg + L[lane].fix;
+                    int len = (L[lane].next_head < 32 ? L[L[lane].next_head].off : total) - L[lane].off;
+                    auto put = [&](int64_t g, int si) { if (store_mode) val[g] = st[si]; else val[g] += st[si]; };
+                    if (g0 & 1) { put(g0, s0); g0++; s0++; len--; }
+                    if (len & 1) { put(g0 + len - 1, s0 + len - 1); len--; }
+                    if (len > 0) {
+                        if ((g0 & 1) || (s0 & 1) || (len & 1)) return 4;   // the bulk copy needs 16-byte aligned ends
+                        for (int q = 0; q < len; q++) put(g0 + q, s0 + q);
                         stats[3]++;
-                    } else {
-                        for (int j = 0; j < 16; j++) {
-                            const int src = h * 16 + j;
-                            for (int lane = 0; lane < 32; lane++)
-                                if (lane < myn[src]) {
-                                    if (store_mode) val[rs[src] + lane] = st[off[src] + lane];
-                                    else val[rs[src] + lane] += st[off[src] + lane];
-                                }
-                        }
-                        stats[4]++;
                     }
+                    stats[4]++;
                 }
             }
         }

@@ -272,15 +272,13 @@ def test_affine_kernel_multi_patch_equals_general_kernel(monkeypatch):
     assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("ISL_TEST_EXPERIMENTAL"),
-                    reason="row-gather kernel (ISL_Q1_ROWS=1) is not the default yet: set ISL_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("threads,ss", [("256", "0"), ("320", "0"), ("128", "0"), ("256", "1"), ("320", "1")])
-def test_rowgather_kernel_equals_oracle(monkeypatch, threads, ss):
-    """isl_rowgather.cuh on the device (the same routines pass tests/test_rowgather_emu.py on the host)."""
+@pytest.mark.parametrize("threads,rows", [("128", "100"), ("256", "100"), ("128", "256"), ("256", "37")])
+def test_rowgather_kernel_equals_oracle(monkeypatch, threads, rows):
+    """isl_rowgather.cuh on the device (the same routines pass tests/test_rowgather_emu.py on the host): stencil-sum
+    kernel on affine meshes, gathered local matrices on perturbed ones, store and accumulate mode of the bulk write-out."""
     monkeypatch.setenv("ISL_Q1_ROWS", "1")
-    monkeypatch.setenv("ISL_ROWS_SS", ss)
     monkeypatch.setenv("ISL_ROWS_THREADS", threads)
-    monkeypatch.setenv("ISL_PATCH_ROWS", "100")
+    monkeypatch.setenv("ISL_PATCH_ROWS", rows)
     e = E.Engine(0)
     try:
         for name, n, perturb, permute in [("laplace_q1_hex", 13, False, False), ("laplace_q1_hex_values", 9, False, True),

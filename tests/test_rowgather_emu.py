@@ -79,17 +79,17 @@ def sheared(n, permute):
 def test_rowgather_equals_oracle(emu, n, permute, rows_per_patch, nt):
     c = flows.build_case("laplace_q1_hex", n, False, permute)   # stiffness (incremental) + body force f = 1
     ref = c.run_oracle()
-    for variant in (0, 2):
+    for variant in (0,):
         rc, val, rhs, stats = run_emu(emu, c, 1.0, 1.0, 1, 1, 1, rows_per_patch, nt, ref, general=variant)
         assert rc == 0
         assert not np.isnan(val).any()
         assert H.csr_rel_diff(ref[0], ref[2], val) <= 1e-12 and H.vec_rel_diff(ref[3], rhs) <= 1e-12
     assert stats[0] >= (n - 1) ** 3 // rows_per_patch and stats[2] > 0
-    # write-out paths: one patch holding all rows streams contiguous blocks, boxes of a larger mesh go row by row
-    assert stats[3] > 0 if rows_per_patch >= (n - 1) ** 3 else stats[4] > 0
+    # write-out: every segment of consecutive rows leaves as one bulk copy (stats[3]) plus at most two odd elements
+    assert stats[4] > 0 and stats[3] > 0
 
 
-@pytest.mark.parametrize("variant", [0, 2])   # 0: constant tables, 2: signed sums of 15 numbers per element (SS)
+@pytest.mark.parametrize("variant", [0])   # stencil sums (rg_row_affine)
 @pytest.mark.parametrize("incremental", [True, False])
 def test_rowgather_sheared_mesh_lift_and_accumulate(emu, incremental, variant):
     c = sheared(6, True)

@@ -54,8 +54,7 @@ def main():
             eng.body_force_computation([1.0], 3, 0)
             eng.finish_assembly()
 
-        configs = [dict(q1_rows=0)] + [dict(q1_rows=1, rows_threads=t, rows_ss=ss)
-                                       for ss in (0, 1) for t in [int(x) for x in args.threads.split(",")]]
+        configs = [dict(q1_rows=1, rows_threads=t) for t in [int(x) for x in args.threads.split(",")]]
         for cfg in configs:
             for k, v in cfg.items():
                 eng.set_option(k, v)
