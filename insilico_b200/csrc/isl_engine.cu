@@ -675,6 +675,7 @@ __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const d
 
 #include "isl_patch.cuh"
 #include "isl_rowgather.cuh"
+#include "isl_rows_fromk.cuh"
 
 // ---------------------------------------------------------------------------------------------
 struct FieldDev {
@@ -726,22 +727,42 @@ struct isl_engine {
     DevBuf<double> scratch_d; DevBuf<int> scratch_i;
     // patch assembly (isl_patch.cuh)
     std::map<int, std::unique_ptr<PatchSet>> patchsets;  // per field
+    std::map<int, std::unique_ptr<FromKSet>> fromk_sets; // per field: two-kernel path for general (non-affine) Q1 elements
     bool val_is_zero = false;   // matrix values known to be zero (fresh solver): complete rows may be stored
     bool val_zero_pending = false;  // the memset of val has been postponed (a store-mode patch launch makes it unnecessary)
     struct PendingQ1 { bool active = false; int field = 0; double factor = 1.; int incremental = 1; } pending_q1;
     int q1_mode = 1;            // 0 = one thread per element + atomics, 1 = shared-memory patches
-    int patch_rows = 400, patch_threads = 128, patch_ctas_per_sm = 2;
-    double patch_stretch = 1.0;  // ISL_PATCH_STRETCH: boxes this many times longer along the axis of consecutive equation numbers
+    int patch_rows = 256, patch_threads = 128, patch_ctas_per_sm = 2;
+    double patch_stretch = 3.0;  // ISL_PATCH_STRETCH: boxes this many times longer along the axis of consecutive equation numbers
     int q1_fast = 3;            // bit0: sum-factorised local matrix, bit1: affine-element shortcut
     int affine_kernel = 1;      // all-affine meshes: low-register kernel with 256 threads per CTA
-    int q1_rows = 0;            // ISL_Q1_ROWS=1: row-gather kernel on all-affine meshes (isl_rowgather.cuh; not yet default)
-    int rows_threads = 256;     // its CTA size (ISL_ROWS_THREADS)
+    int q1_rows = 1;            // row kernels (isl_rowgather.cuh: all-affine meshes; isl_rows_fromk.cuh: general elements);
+                                // ISL_Q1_ROWS=0 selects the round-1 shared-memory patch kernels
+    int rows_threads = 128;     // CTA size of the affine row kernel (ISL_ROWS_THREADS)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
+    DevBuf<unsigned long long> profbuf;
+    bool sys_touched = false;   // something has been assembled / inserted into the current system
+    bool sys_stale = false;     // mesh or field arrays were replaced after that: the system's entries are gone
     int tangent_tiled = 0;      // ISL_TANGENT_TILED=1: register-tiled hyperelastic tangent (isl_tangent_tiled.cuh; not yet default)
+
+    // staging of isl_insert_lhs / isl_insert_rhs operands: a ring of slices so that a copy never overwrites operands a
+    // queued kernel still reads only after the stream has passed them (stream order) -- one arena, grown on demand
+    DevBuf<char> ins_buf; size_t ins_off = 0; DevBuf<int> ins_err;
+    char* insert_arena(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!ins_err.p) { ins_err.alloc(1); cudaMemsetAsync(ins_err.p, 0, sizeof(int), stream); }
+        if (bytes > ins_buf.n || !ins_buf.p) {
+            cudaStreamSynchronize(stream);
+            ins_buf.alloc(std::max<size_t>(bytes * 4, (size_t)1 << 20)); ins_off = 0;
+        }
+        if (ins_off + bytes > ins_buf.n) ins_off = 0;   // wrap: everything in the arena is consumed in stream order
+        char* p = ins_buf.p + ins_off; ins_off += bytes;
+        return p;
+    }
 
     int grid_for(int64_t n, int block) const {
         const int64_t g = (n + block - 1) / block;
@@ -776,10 +797,21 @@ void upload_vec(isl_engine* h, DevBuf<T>& dst, const std::vector<T>& v) {
     }
 }
 
+// replacing mesh / field arrays drops the pattern and with it the values: if the current system already holds
+// contributions it becomes unusable (a second FieldBinder on the same solver, a binder rebuilt between two assembly
+// calls); later calls on it fail instead of silently continuing on an empty matrix
+void mark_stale_if_touched(isl_engine* h) { if (h->sys_touched) h->sys_stale = true; }
+void require_live_system(isl_engine* h) {
+    ISL_REQUIRE(!h->sys_stale, "mesh or field arrays were replaced after assembly into this system had started, so its entries "
+                               "are gone: create a new solver first (one FieldBinder per solver is supported)");
+    h->sys_touched = true;
+}
+
 void invalidate_pattern(isl_engine* h) {
     h->pattern_pairs.clear();
     h->slotmaps.clear();
     h->patchsets.clear();
+    h->fromk_sets.clear();
     h->nnz = 0;
     h->rowptr.release(); h->col.release(); h->val.release();
 }
@@ -885,6 +917,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     h->pattern_pairs = pairs;
     h->slotmaps.clear();
     h->patchsets.clear();
+    h->fromk_sets.clear();
 }
 
 void ensure_pair(isl_engine* h, int t, int c) {
@@ -1111,6 +1144,7 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     PatchHost P;
     for (int attempt = 0; attempt < 4; attempt++) {
         for (;; rows_per_patch -= 8) {
+            if (h->q1_rows) { cap_nodes = 65534; cap_entries = 1 << 30; break; }   // the row kernels keep no accumulator
             const double c = std::cbrt((double)rows_per_patch) + 2.0;
             cap_nodes = (int)(c * c * c * 1.35) + 32;
             cap_entries = (smem_budget - cap_nodes * 24 - rows_per_patch * 24 - 256) / 8;
@@ -1125,29 +1159,42 @@ PatchSet* get_patchset(isl_engine* h, int field) {
         P = PatchHost();
         P.want_slots = h->q1_rows != 0;
         form_patches(perm_try, bounds, heqn, hconn, hrowptr, h->n_eqn, h->n_nodes, cap_entries, cap_nodes, P);
+        if (h->q1_rows) {
+            // row kernel: 7 doubles per element instance + max(coordinates, write-out staging); four CTAs per SM want <= 56 KB
+            const size_t sm = (size_t)7 * ((P.max_inst + 2) & ~1) * 8 + std::max((size_t)((P.max_nodes + 1) & ~1) * 24, (size_t)4 * RG_STAGE * 8);
+            if (!P.lattice || sm <= (size_t)56 * 1024 || rows_per_patch <= 32 || attempt == 3) break;
+            rows_per_patch = (int)(rows_per_patch * 0.85);
+            continue;
+        }
         if (!P.lattice || (P.max_entries <= cap_entries && P.max_nodes <= cap_nodes) || rows_per_patch <= 16) break;
         rows_per_patch = (int)(rows_per_patch * 0.88);
     }
     rowxyz.clear(); rowxyz.shrink_to_fit();
-    const bool fits = P.lattice && P.max_entries <= cap_entries && P.max_nodes <= cap_nodes && P.max_nodes < 65535 && cap_entries > 0;
+    bool fits = P.lattice && P.max_entries <= cap_entries && P.max_nodes <= cap_nodes && P.max_nodes < 65535 && cap_entries > 0;
+    if (h->q1_rows)
+        fits = fits && P.max_inst < 65534 &&
+               (size_t)7 * ((P.max_inst + 2) & ~1) * 8 + std::max((size_t)((P.max_nodes + 1) & ~1) * 24, (size_t)4 * RG_STAGE * 8) <= (size_t)226 * 1024;
     if (fits) {
         ps->n_patches = (int)P.inst_off.size() - 1;
         ps->max_entries = P.max_entries; ps->max_rows = P.max_rows; ps->max_nodes = P.max_nodes;
         ps->n_inst = (int64_t)P.inst_elem.size(); ps->n_elems = n;
         ps->redundancy = n ? (double)ps->n_inst / (double)n : 0.;
         upload_vec(h, ps->p_inst_off, P.inst_off); upload_vec(h, ps->p_row_off, P.row_off); upload_vec(h, ps->p_node_off, P.node_off);
-        upload_vec(h, ps->rows, P.rows); upload_vec(h, ps->soff, P.soff); upload_vec(h, ps->nodes, P.nodes);
-        upload_vec(h, ps->i_lnode, P.lnode); upload_vec(h, ps->i_lrow, P.lrow);
-        upload_vec(h, ps->p_run_off, P.run_off); upload_vec(h, ps->run_start, P.run_start); upload_vec(h, ps->run_soff, P.run_soff);
+        upload_vec(h, ps->rows, P.rows); upload_vec(h, ps->nodes, P.nodes);
+        upload_vec(h, ps->i_lnode, P.lnode);
         DevBuf<int32_t> inst_elem; upload_vec(h, inst_elem, P.inst_elem);
-        ps->i_pos.alloc((size_t)ps->n_inst * 64);
-        DevBuf<int> derr; derr.alloc(1);
-        ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
-        ISL_LAUNCH(h, k_inst_pos, h->grid_for(ps->n_inst * 64, 256), 256, 0, inst_elem.p, f.elem_eqn.p, ps->n_inst, h->rowptr.p, h->col.p,
-                   ps->i_pos.p, derr.p);
         int err = 0;
-        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        if (!h->q1_rows) {   // tables of the round-1 patch kernels only (64 position bytes per element instance)
+            upload_vec(h, ps->soff, P.soff); upload_vec(h, ps->i_lrow, P.lrow);
+            upload_vec(h, ps->p_run_off, P.run_off); upload_vec(h, ps->run_start, P.run_start); upload_vec(h, ps->run_soff, P.run_soff);
+            ps->i_pos.alloc((size_t)ps->n_inst * 64);
+            DevBuf<int> derr; derr.alloc(1);
+            ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
+            ISL_LAUNCH(h, k_inst_pos, h->grid_for(ps->n_inst * 64, 256), 256, 0, inst_elem.p, f.elem_eqn.p, ps->n_inst, h->rowptr.p, h->col.p,
+                       ps->i_pos.p, derr.p);
+            ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+        }
         if (!err) { ps->usable = true; out = ps.get(); } else ps->n_patches = 0;
         if (!err && h->q1_rows && P.lattice && ps->n_patches > 0) {
             // row-gather tables (isl_rowgather.cuh): slots from the host, positions / eligibility on the device
@@ -1202,6 +1249,127 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     return out;
 }
 
+// every owned element affine?  (exact test on the edge vectors, once per coordinate set)
+void ensure_affine_state(isl_engine* h) {
+    if (h->affine_state >= 0) return;
+    DevBuf<int> flag; flag.alloc(1);
+    ISL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), h->stream));
+    if (h->n_owned > 0) ISL_LAUNCH(h, k_check_affine, h->grid_for(h->n_owned, 256), 256, 0, h->coords.p, h->conn.p, h->n_owned, flag.p);
+    int na = 0;
+    ISL_CUDA(cudaMemcpyAsync(&na, flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    h->affine_state = na ? 0 : 1;
+}
+
+// tables of the two-kernel path for general Q1 elements (isl_rows_fromk.cuh), built on the device: locality-sorted
+// element order (cub radix sort of the smallest equation number), row -> element table with the lattice check, per-row
+// CSR positions.  ok = false: the mesh is not lattice-like (a row is local node a of two elements) -> generic kernels.
+FromKSet* get_fromk(isl_engine* h, int field) {
+    auto it = h->fromk_sets.find(field);
+    if (it != h->fromk_sets.end()) return it->second->ok ? it->second.get() : nullptr;
+    auto fk = std::make_unique<FromKSet>();
+    FieldDev& f = h->fields[field];
+    const int64_t n = h->n_owned, nr = h->n_eqn;
+    build_elem_eqn(h, f);
+    fk->n_rows = nr; fk->n_elems = n; fk->built = true;
+    if (n > 0 && nr > 0 && n < ((int64_t)1 << 31)) {
+        DevBuf<int32_t> key, key2, idx;
+        key.alloc(n); key2.alloc(n); idx.alloc(n); fk->eorder.alloc(n);
+        ISL_LAUNCH(h, k_fromk_elem_key, h->grid_for(n, 256), 256, 0, f.elem_eqn.p, n, key.p, idx.p);
+        size_t tb = 0;
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, fk->eorder.p, n, 0, 32, h->stream));
+        DevBuf<char> tmp; tmp.alloc(tb);
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, fk->eorder.p, n, 0, 32, h->stream));
+        h->launches += 4;
+        fk->row_pos.alloc((size_t)nr * 8);
+        ISL_CUDA(cudaMemsetAsync(fk->row_pos.p, 0xff, (size_t)nr * 8 * sizeof(int32_t), h->stream));
+        DevBuf<int> cnt; cnt.alloc(2);
+        ISL_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_fromk_row_pos, h->grid_for(n, 256), 256, 0, fk->eorder.p, f.elem_eqn.p, n, fk->row_pos.p, cnt.p + 1);
+        fk->meta.alloc((size_t)nr * sizeof(RowMeta));
+        ISL_LAUNCH(h, k_fromk_row_meta, h->grid_for(nr, 128), 128, 0, 0, nr, fk->row_pos.p, fk->eorder.p, h->conn.p, f.eqn.p, f.status.p,
+                   h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(fk->meta.p), (int32_t*)nullptr, cnt.p, cnt.p + 1);
+        int hc[2] = {0, 0};
+        ISL_CUDA(cudaMemcpyAsync(hc, cnt.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        if (!hc[1]) {
+            fk->lift_nodes.alloc((size_t)std::max(1, hc[0]) * 27);
+            if (hc[0] > 0)
+                ISL_LAUNCH(h, k_fromk_row_meta, h->grid_for(nr, 128), 128, 0, 1, nr, fk->row_pos.p, fk->eorder.p, h->conn.p, f.eqn.p,
+                           f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(fk->meta.p), fk->lift_nodes.p, cnt.p, cnt.p + 1);
+            fk->K.alloc((size_t)44 * n);
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            fk->ok = true;
+        }
+        if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] two-kernel general path: %s, %d rows next to constrained nodes\n", fk->ok ? "ok" : "not eligible", hc[0]);
+    }
+    FromKSet* out = fk->ok ? fk.get() : nullptr;
+    h->fromk_sets[field] = std::move(fk);
+    return out;
+}
+
+PatchSet* get_patchset(isl_engine* h, int field);
+
+// is one of the Q1 fast paths available for this field?  (builds its tables on first use)
+bool q1_ready(isl_engine* h, int field) {
+    if (!h->q1_rows) return get_patchset(h, field) != nullptr;
+    ensure_affine_state(h);
+    if (h->affine_state == 1) { PatchSet* ps = get_patchset(h, field); if (ps && ps->rows_ok) return true; }
+    return get_fromk(h, field) != nullptr;   // also serves affine meshes whose patches are not eligible
+}
+
+template <bool MATRIX>
+void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor, int incremental, int body, double f0);
+
+// one launch (affine row kernel) or two (general elements) of the Q1 hot path: stiffness + Dirichlet lift (matrix != 0)
+// and / or body force
+void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremental, int body, double f0) {
+    const FieldDev& ft = h->fields[field];
+    if (!h->q1_rows) {
+        PatchSet* ps = get_patchset(h, field);
+        ISL_REQUIRE(ps, "internal: Q1 patch launch without a patch set");
+        if (matrix) launch_patch<true>(h, ps, ft, factor, incremental, body, f0); else launch_patch<false>(h, ps, ft, 0., 0, body, f0);
+        return;
+    }
+    ensure_affine_state(h);
+    RowsParams q;
+    std::memset(&q, 0, sizeof(q));
+    q.coords = h->coords.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p; q.val = h->val.p; q.rhs = h->rhs.p;
+    q.factor = factor; q.incremental = incremental; q.store_mode = h->val_is_zero ? 1 : 0; q.body = body; q.f0 = f0; q.matrix = matrix;
+    PatchSet* ps = (h->affine_state == 1) ? get_patchset(h, field) : nullptr;
+    if (ps && ps->rows_ok) {
+        if (ps->n_patches == 0) return;
+        q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
+        q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
+        q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.lift_nodes = ps->lift_nodes.p;
+        q.node_cap = (ps->max_nodes + 1) & ~1; q.inst_cap = (ps->max_inst + 2) & ~1; q.n_patches = ps->n_patches;
+        const int nt = h->rows_threads == 256 ? 256 : 128;
+        const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
+        const int per_sm = (int)std::min<size_t>(nt == 256 ? 2 : 4, (size_t)(227 * 1024) / (smem_r + 1024));
+        q.resident = h->n_sm * std::max(1, per_sm);
+        if (nt == 256) {
+            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), ps->n_patches, 256, smem_r, q);
+        } else {
+            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+            ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), ps->n_patches, 128, smem_r, q);
+        }
+        return;
+    }
+    FromKSet* fk = get_fromk(h, field);
+    ISL_REQUIRE(fk, "internal: Q1 row launch without tables");
+    FromKParams k;
+    k.coords = h->coords.p; k.conn = h->conn.p; k.eorder = fk->eorder.p; k.n_elems = fk->n_elems;
+    k.row_pos = fk->row_pos.p; k.meta = reinterpret_cast<const RowMeta*>(fk->meta.p); k.n_rows = fk->n_rows; k.K = fk->K.p;
+    q.lift_nodes = fk->lift_nodes.p;
+    k.r = q; k.matrix = matrix;
+    ISL_LAUNCH(h, k_q1hex_elemK, (unsigned)((fk->n_elems + 127) / 128), 128, 0, k);
+    constexpr int NT = 128;
+    const size_t smem_k = (size_t)(NT / 32) * RG_STAGE * 8;
+    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_fromK<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+    ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((fk->n_rows + NT - 1) / NT), NT, smem_k, k);
+}
+
 template <bool MATRIX>
 void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor, int incremental, int body, double f0) {
     if (ps->n_patches == 0) return;  // no ACTIVE row: nothing to assemble
@@ -1217,57 +1385,12 @@ void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor
     p.acc_cap = MATRIX ? ((ps->max_entries + 1) & ~1) : 0; p.row_cap = (ps->max_rows + 1) & ~1; p.node_cap = (ps->max_nodes + 1) & ~1;
     p.body = body; p.f0 = f0; p.fast = h->q1_fast; p.dbg = getenv("ISL_DBG") ? atoi(getenv("ISL_DBG")) : 0;
     p.prof = nullptr;
-    static DevBuf<unsigned long long> profbuf;
+    DevBuf<unsigned long long>& profbuf = h->profbuf;   // per engine (ISL_PROF=1 cycle counters)
     const bool prof = MATRIX && getenv("ISL_PROF");
     if (prof) { profbuf.alloc(8); ISL_CUDA(cudaMemsetAsync(profbuf.p, 0, 64, h->stream)); p.prof = profbuf.p; }
     const size_t smem = (size_t)p.acc_cap * 8 + (size_t)p.node_cap * 24 + (size_t)p.row_cap * 16 + (size_t)(p.row_cap + 2) * 8 + 16;
-    if (MATRIX && (h->affine_kernel || h->q1_rows) && (h->q1_fast & 2) && !h->patch_ws && h->shape == ISL_HEX) {
-        if (h->affine_state < 0) {  // once per coordinate set
-            DevBuf<int> flag; flag.alloc(1);
-            ISL_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), h->stream));
-            if (h->n_owned > 0) ISL_LAUNCH(h, k_check_affine, h->grid_for(h->n_owned, 256), 256, 0, h->coords.p, h->conn.p, h->n_owned, flag.p);
-            int na = 0;
-            ISL_CUDA(cudaMemcpyAsync(&na, flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            ISL_CUDA(cudaStreamSynchronize(h->stream));
-            h->affine_state = na ? 0 : 1;
-        }
-        if (h->q1_rows && ps->rows_ok && h->affine_state >= 0) {
-            RowsParams q;
-            q.coords = h->coords.p; q.p_inst_off = ps->p_inst_off.p; q.p_row_off = ps->p_row_off.p; q.p_node_off = ps->p_node_off.p;
-            q.nodes = ps->nodes.p; q.i_lnode = ps->i_lnode.p;
-            q.meta = reinterpret_cast<const RowMeta*>(ps->r_meta.p); q.lift_nodes = ps->lift_nodes.p;
-            q.status = p.status; q.presc = p.presc; q.values = p.values; q.val = p.val; q.rhs = p.rhs;
-            q.factor = p.factor; q.incremental = p.incremental; q.store_mode = p.store_mode; q.body = p.body; q.f0 = p.f0;
-            q.node_cap = p.node_cap; q.inst_cap = (ps->max_inst + 2) & ~1; q.n_patches = ps->n_patches;
-            if (h->affine_state == 1) {
-                const int nt = h->rows_threads == 256 ? 256 : 128;
-                const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
-                int per_sm = (int)std::min<size_t>(nt == 256 ? 2 : 4, (size_t)(227 * 1024) / (smem_r + 1024));
-                q.resident = h->n_sm * std::max(1, per_sm);
-                if (nt == 256) {
-                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-                    ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), ps->n_patches, 256, smem_r, q);
-                } else {
-                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-                    ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), ps->n_patches, 128, smem_r, q);
-                }
-                return;
-            }
-            // general elements: 44 doubles per instance in shared memory; falls through to the patch kernel when a patch does not fit
-            const int nt = h->rows_threads == 128 ? 128 : 256;
-            const size_t smem_g = (size_t)44 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
-            if (smem_g <= (size_t)227 * 1024) {
-                q.resident = h->n_sm * std::max<int>(1, (int)((size_t)(227 * 1024) / (smem_g + 1024)));
-                if (nt == 128) {
-                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_general<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-                    ISL_LAUNCH(h, (k_q1hex_rows_general<128, 2>), ps->n_patches, 128, smem_g, q);
-                } else {
-                    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_general<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-                    ISL_LAUNCH(h, (k_q1hex_rows_general<256, 1>), ps->n_patches, 256, smem_g, q);
-                }
-                return;
-            }
-        }
+    if (MATRIX && h->affine_kernel && (h->q1_fast & 2) && !h->patch_ws && h->shape == ISL_HEX) {
+        ensure_affine_state(h);
         if (h->affine_state == 1 && h->affine_kernel) {
 #define ISL_AFF_LAUNCH(NT, MINB)                                                                                        \
     do {                                                                                                               \
@@ -1349,12 +1472,10 @@ void flush_pending(isl_engine* h, int fuse_body, double f0) {
     if (!h->pending_q1.active) return;
     h->pending_q1.active = false;
     const int t = h->pending_q1.field;
-    PatchSet* ps = get_patchset(h, t);
-    ISL_REQUIRE(ps, "internal: deferred patch launch without a patch set");
     const bool full_store = h->val_is_zero && h->pattern_pairs.size() == 1;
     if (full_store) h->val_zero_pending = false;  // every entry is written by a plain store
     else materialize_zero(h);
-    launch_patch<true>(h, ps, h->fields[t], h->pending_q1.factor, h->pending_q1.incremental, fuse_body, f0);
+    launch_q1(h, t, 1, h->pending_q1.factor, h->pending_q1.incremental, fuse_body, f0);
     h->val_is_zero = false;
 }
 
@@ -1394,7 +1515,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
         if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PATCH_WS")) { h->patch_ws = atoi(m) ? 1 : 0; if (h->patch_ws) { h->patch_ctas_per_sm = 1; h->patch_threads = 256; if (!getenv("ISL_PATCH_ROWS")) h->patch_rows = 448; } }
-        if (const char* m = getenv("ISL_Q1_ROWS")) { h->q1_rows = atoi(m) ? 1 : 0; if (h->q1_rows) h->patch_rows = 256; }
+        if (const char* m = getenv("ISL_Q1_ROWS")) h->q1_rows = atoi(m) ? 1 : 0;
+        if (!h->q1_rows) { h->patch_rows = 400; h->patch_stretch = 1.0; }   // geometry of the round-1 patch kernels
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
@@ -1505,6 +1627,7 @@ int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes
         upload(h, h->conn, conn, (size_t)n_elems * h->npe);
         for (auto& f : h->fields) f.reset();
         h->tables.clear();
+        mark_stale_if_touched(h);
         invalidate_pattern(h);
         ISL_CUDA(cudaStreamSynchronize(h->stream));
     });
@@ -1516,6 +1639,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         h->n_owned = n_owned; h->affine_state = -1;
         h->slotmaps.clear();
         h->patchsets.clear();
+        h->fromk_sets.clear();
     });
 }
 int isl_mesh_update_coords(isl_handle h, const double* coords) {
@@ -1563,6 +1687,7 @@ int isl_field_set(isl_handle h, int field, int fe_deg, int dof_size, int64_t n_o
             ISL_CUDA(cudaStreamSynchronize(h->stream));
             f.dof_is_node = (ndiff == 0);
         }
+        mark_stale_if_touched(h);
         invalidate_pattern(h);
         // tables depend on the field degrees only, but drop those that refer to this field id
         for (auto it = h->tables.begin(); it != h->tables.end();)
@@ -1578,6 +1703,7 @@ int isl_field_set_constraints(isl_handle h, int field, int64_t n_con, const int6
         ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
         FieldDev& f = h->fields[field];
         f.reset_constraints();
+        mark_stale_if_touched(h);
         invalidate_pattern(h);
         if (n_con <= 0) return;
         const size_t n = (size_t)f.n_obj * f.ds;
@@ -1630,6 +1756,8 @@ int isl_system_create(isl_handle h, int64_t n_eqn) {
         if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
         h->val_zero_pending = true;   // memset of the matrix values postponed, see materialize_zero()
         h->val_is_zero = true;
+        h->sys_touched = false; h->sys_stale = false;
+        if (h->ins_err.p) ISL_CUDA(cudaMemsetAsync(h->ins_err.p, 0, sizeof(int), h->stream));
     });
 }
 int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
@@ -1637,7 +1765,7 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
         flush_pending(h);
         ISL_CUDA(cudaSetDevice(h->device));
         ensure_pair(h, test_field, trial_field);
-        if (qualifies_q1(h, test_field, trial_field) && h->q1_mode == 1 && get_patchset(h, test_field)) return;
+        if (qualifies_q1(h, test_field, trial_field) && h->q1_mode == 1 && q1_ready(h, test_field)) return;
         get_slotmap(h, test_field, trial_field);
     });
 }
@@ -1646,6 +1774,8 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ISL_REQUIRE(t >= 0 && t < 5 && c >= 0 && c < 5, "field index out of range");
+        require_live_system(h);
         flush_pending(h);
         ensure_pair(h, t, c);
         check_kernel_fields(h, kid, t, c, true);
@@ -1655,7 +1785,7 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
             load_q1_tables(h);
             const double factor = params ? params[0] : 1.0;
             if (h->q1_mode == 1) {
-                if (get_patchset(h, t)) {
+                if (q1_ready(h, t)) {
                     h->pending_q1.active = true; h->pending_q1.field = t; h->pending_q1.factor = factor;
                     h->pending_q1.incremental = incremental;
                     if (!h->defer_launch) flush_pending(h);
@@ -1695,6 +1825,8 @@ int isl_assemble_residual(isl_handle h, int kid, const double* params, int quad_
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ISL_REQUIRE(t >= 0 && t < 5 && c >= 0 && c < 5, "field index out of range");
+        require_live_system(h);
         flush_pending(h);
         check_kernel_fields(h, kid, t, c, false);
         AsmParams p; std::memset(&p, 0, sizeof(p));
@@ -1713,6 +1845,7 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
         ISL_REQUIRE(t >= 0 && t < 5 && h->fields[t].set, "field not set");
+        require_live_system(h);
         {
             const FieldDev& ft = h->fields[t];
             if (h->q1_mode == 1 && h->shape == ISL_HEX && h->geom_deg == 1 && ft.deg == 1 && ft.ds == 1 && ft.dof_is_node &&
@@ -1720,7 +1853,7 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int t) {
                 load_q1_tables(h);
                 if (h->pending_q1.active && h->pending_q1.field == t) { flush_pending(h, 1, f[0]); return; }
                 flush_pending(h);
-                if (PatchSet* ps = get_patchset(h, t)) { launch_patch<false>(h, ps, ft, 0., 0, 1, f[0]); return; }
+                if (q1_ready(h, t)) { launch_q1(h, t, 0, 0., 0, 1, f[0]); return; }
             }
         }
         flush_pending(h);
@@ -1739,6 +1872,7 @@ int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
         ISL_REQUIRE(t >= 0 && t < 5 && h->fields[t].set, "field not set");
         ISL_REQUIRE(values != nullptr, "no force values");
+        require_live_system(h);
         flush_pending(h);
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, t);
@@ -1751,44 +1885,59 @@ int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_
     });
 }
 
+// host-side odd contributions (Neumann terms of the reference's own loops come through here element by element):
+// no allocation and no wait per call; the operands are staged in a small arena that the stream reuses in order, a
+// missing pattern entry is recorded on the device and reported by isl_finish
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols, int n_cols) {
     return guarded([&] {
+        require_live_system(h);
         flush_pending(h);
         materialize_zero(h);
         h->val_is_zero = false;
         ISL_REQUIRE(h->nnz > 0, "no pattern registered");
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, "Row index out of bound: " + std::to_string(rows[i]));
         for (int j = 0; j < n_cols; j++) ISL_REQUIRE(cols[j] >= 0 && cols[j] < h->n_eqn, "Col index out of bound: " + std::to_string(cols[j]));
-        DevBuf<double> dm; DevBuf<int64_t> dr, dc; DevBuf<int> derr;
-        upload(h, dm, mat, (size_t)n_rows * n_cols); upload(h, dr, rows, n_rows); upload(h, dc, cols, n_cols);
-        derr.alloc(1); ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
-        const int n = n_rows * n_cols;
-        ISL_LAUNCH(h, k_insert_lhs, (n + 127) / 128, 128, 0, dm.p, dr.p, n_rows, dc.p, n_cols, h->rowptr.p, h->col.p, h->val.p, derr.p);
-        int err = 0;
-        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        ISL_CUDA(cudaStreamSynchronize(h->stream));
-        ISL_REQUIRE(!err, "TripletContainer had not been properly set up");
+        const size_t nm = (size_t)n_rows * n_cols;
+        char* a = h->insert_arena(nm * 8 + (size_t)(n_rows + n_cols) * 8);
+        double* dm = reinterpret_cast<double*>(a);
+        int64_t* dr = reinterpret_cast<int64_t*>(a + nm * 8);
+        int64_t* dc = dr + n_rows;
+        ISL_CUDA(cudaMemcpyAsync(dm, mat, nm * 8, cudaMemcpyDefault, h->stream));
+        ISL_CUDA(cudaMemcpyAsync(dr, rows, (size_t)n_rows * 8, cudaMemcpyDefault, h->stream));
+        ISL_CUDA(cudaMemcpyAsync(dc, cols, (size_t)n_cols * 8, cudaMemcpyDefault, h->stream));
+        const int n = (int)nm;
+        ISL_LAUNCH(h, k_insert_lhs, (n + 127) / 128, 128, 0, dm, dr, n_rows, dc, n_cols, h->rowptr.p, h->col.p, h->val.p, h->ins_err.p);
     });
 }
 int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_rows) {
     return guarded([&] {
+        require_live_system(h);
         flush_pending(h);
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, std::to_string(rows[i]) + " out of bound");
-        DevBuf<double> dv; DevBuf<int64_t> dr;
-        upload(h, dv, vec, n_rows); upload(h, dr, rows, n_rows);
-        ISL_LAUNCH(h, k_insert_rhs, (n_rows + 127) / 128, 128, 0, dv.p, dr.p, n_rows, h->rhs.p);
-        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        char* a = h->insert_arena((size_t)n_rows * 16);
+        double* dv = reinterpret_cast<double*>(a);
+        int64_t* dr = reinterpret_cast<int64_t*>(a + (size_t)n_rows * 8);
+        ISL_CUDA(cudaMemcpyAsync(dv, vec, (size_t)n_rows * 8, cudaMemcpyDefault, h->stream));
+        ISL_CUDA(cudaMemcpyAsync(dr, rows, (size_t)n_rows * 8, cudaMemcpyDefault, h->stream));
+        ISL_LAUNCH(h, k_insert_rhs, (n_rows + 127) / 128, 128, 0, dv, dr, n_rows, h->rhs.p);
     });
 }
 
 int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz) {
     return guarded([&] {
+        ISL_REQUIRE(!h->sys_stale, "mesh or field arrays were replaced after assembly into this system had started: create a new solver first");
         flush_pending(h);
         materialize_zero(h);
         ISL_CUDA(cudaSetDevice(h->device));
         if (h->sys_pairs != h->pattern_pairs && !h->sys_pairs.empty()) {
             // the cached pattern holds blocks this system never registered: rebuild exactly
             build_pattern(h, h->sys_pairs);
+        }
+        if (h->ins_err.p) {
+            int err = 0;
+            ISL_CUDA(cudaMemcpyAsync(&err, h->ins_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            ISL_REQUIRE(!err, "TripletContainer had not been properly set up");
         }
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         if (n_eqn) *n_eqn = h->n_eqn;

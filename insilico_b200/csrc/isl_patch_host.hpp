@@ -97,6 +97,11 @@ inline void form_patch_range(int64_t leaf_lo, int64_t leaf_hi, const std::vector
         int nnodes = 0;
         for (size_t ii = ibase; ii < P.inst_elem.size(); ii++) {
             const int32_t e = P.inst_elem[ii];
+            // two local nodes with the same equation (tied / periodic numbering): the phase scatter and the row gather
+            // assume distinct columns per local row -> generic (atomic) kernels
+            for (int a = 1; a < 8; a++)
+                for (int b = 0; b < a; b++)
+                    if (eqn[(size_t)e * 8 + a] >= 0 && eqn[(size_t)e * 8 + a] == eqn[(size_t)e * 8 + b]) P.lattice = false;
             for (int a = 0; a < 8; a++) {
                 const int32_t nd = conn[(size_t)e * 8 + a];
                 size_t hq = ((uint32_t)nd * 2654435761u) & (hcap - 1);

@@ -204,16 +204,15 @@ RG_HD int64_t rg_find(const int64_t* rowptr, const int32_t* col, int32_t r, int3
 }
 
 // tables of one owned row: stencil neighbours through the (up to) eight elements around the row node, their CSR
-// positions, whether a neighbour is CONSTRAINED.  inst_elem points at the patch's instance list.  Returns false when
-// the row is not eligible (see header).  nbn[k] = global node of stencil neighbour k or -1.
-RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_elem, const int32_t* conn,
-                         const int32_t* node_eqn, const uint8_t* status, const int64_t* rowptr, const int32_t* col,
-                         RowMeta& m, int32_t (&nbn)[27], bool& constrained_nb) {
+// positions, whether a neighbour is CONSTRAINED.  el[a] = element that has the row node as local node a (-1: none).
+// Returns false when the row is not eligible (see header).  nbn[k] = global node of stencil neighbour k or -1.
+RG_HD bool rg_row_tables_el(int32_t g, const int32_t (&el)[8], const int32_t* conn,
+                            const int32_t* node_eqn, const uint8_t* status, const int64_t* rowptr, const int32_t* col,
+                            RowMeta& m, int32_t (&nbn)[27], bool& constrained_nb) {
     for (int k = 0; k < 27; k++) { nbn[k] = -1; m.pos[k] = 0xff; }
     for (int a = 0; a < 8; a++) {
-        m.slot[a] = slot[a];
-        if (slot[a] == 0xffff) continue;
-        const int32_t* ce = conn + (size_t)inst_elem[slot[a]] * 8;
+        if (el[a] < 0) continue;
+        const int32_t* ce = conn + (size_t)el[a] * 8;
         for (int b = 0; b < 8; b++) {
             const int k = rg_kidx(a, b);
             if (nbn[k] >= 0 && nbn[k] != ce[b]) return false;  // two elements disagree about the neighbour at this offset
@@ -242,6 +241,14 @@ RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_el
     m.lift = -1;
     m.grow = g; m.pad = 0; m.rowstart = rowptr[g];
     return true;
+}
+// the same for a row of a patch: slot[a] = patch-local element instance (0xffff: none), inst_elem = the patch's instance list
+RG_HD bool rg_row_tables(int32_t g, const uint16_t* slot, const int32_t* inst_elem, const int32_t* conn,
+                         const int32_t* node_eqn, const uint8_t* status, const int64_t* rowptr, const int32_t* col,
+                         RowMeta& m, int32_t (&nbn)[27], bool& constrained_nb) {
+    int32_t el[8];
+    for (int a = 0; a < 8; a++) { m.slot[a] = slot[a]; el[a] = (slot[a] == 0xffff) ? -1 : inst_elem[slot[a]]; }
+    return rg_row_tables_el(g, el, conn, node_eqn, status, rowptr, col, m, nbn, constrained_nb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -294,6 +301,7 @@ struct RowsParams {
     double factor; int incremental; int store_mode;
     int body; double f0;
     int node_cap, inst_cap, n_patches, resident;
+    int matrix;   // 0: right-hand side only (body force without a stiffness call before it)
 };
 
 // preprocessing: one CTA per patch, threads over its rows.  pass 0 fills meta and numbers the rows that
@@ -395,7 +403,7 @@ __device__ __forceinline__ void rg_write_rows(const RowsParams& p, const RowMeta
 // force; added with a reduction (no round trip: every row is owned by exactly one thread of one CTA)
 __device__ __forceinline__ void rg_rhs(const RowsParams& p, const RowMeta& m, const double (&acc)[27], double body) {
     double lift = 0.;
-    if (m.lift >= 0) {
+    if (m.lift >= 0 && p.matrix) {
         const int32_t* ln = p.lift_nodes + (size_t)m.lift * 27;
 #pragma unroll
         for (int k = 0; k < 27; k++) {
@@ -523,7 +531,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
             rg_row_affine([&](int a, int c) { return sD[c * p.inst_cap + sl[a]]; }, acc, body);
             rg_rhs(p, m, acc, body);
         }
-        rg_write_rows(p, m, acc, act, st, lane);
+        if (p.matrix) rg_write_rows(p, m, acc, act, st, lane);
     }
     rg_bulk_wait_read();   // shared memory must stay valid until the bulk copies have read it
 }

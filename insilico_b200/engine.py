@@ -244,6 +244,8 @@ class Engine:
         _chk(lib().isl_mesh_set_owned(self.h, _i64(n_owned)))
 
     def update_coords(self, coords):
+        if not isinstance(coords, (int, np.integer)):
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
         _chk(lib().isl_mesh_update_coords(self.h, _ptr(coords)))
 
     # base::Field<FEBasis,DOFSIZE>
@@ -263,6 +265,8 @@ class Engine:
                                              _ptr(master_eqn), _ptr(weight)))
 
     def update_field(self, fid, prescribed=None, values=None):
+        conv = lambda a: a if a is None or isinstance(a, (int, np.integer)) else np.ascontiguousarray(a, dtype=np.float64)
+        prescribed, values = conv(prescribed), conv(values)
         _chk(lib().isl_field_update(self.h, fid, _ptr(prescribed), _ptr(values)))
 
     # base::solver::Eigen3
@@ -273,12 +277,20 @@ class Engine:
     def register_fields(self, test, trial):
         _chk(lib().isl_pattern_register(self.h, test, trial))
 
+    @staticmethod
+    def _params(kernel_id, params):
+        need = 2 if kernel_id in (K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE) else 1
+        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64).reshape(-1)
+        if len(params) < need:
+            raise EngineError("kernel %d needs %d parameters (lambda, mu), got %d" % (kernel_id, need, len(params)))
+        return params
+
     def stiffness_matrix_computation(self, kernel_id, params, quad_deg, test, trial, incremental=True):
-        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        params = self._params(kernel_id, params)
         _chk(lib().isl_assemble_matrix(self.h, kernel_id, _ptr(params), quad_deg, test, trial, int(incremental)))
 
     def compute_residual_forces(self, kernel_id, params, quad_deg, test, trial, factor=-1.0):
-        params = np.ascontiguousarray(params if params is not None else [0.0], dtype=np.float64)
+        params = self._params(kernel_id, params)
         _chk(lib().isl_assemble_residual(self.h, kernel_id, _ptr(params), quad_deg, test, trial, C.c_double(factor)))
 
     def body_force_computation(self, f, quad_deg, test):

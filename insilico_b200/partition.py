@@ -207,6 +207,9 @@ class DistributedAssembly:
         self.eng.unpack_add_entries(1, self._rows.data_ptr(), rr.numel(), rr.data_ptr())
 
     def exchange(self):
+        # a Q1 stiffness launch may still be deferred inside the engine (it waits one call for a body force to fuse):
+        # the ghost rows must be in memory before they are sent
+        self.eng.flush()
         with torch.cuda.stream(self.stream):
             self.plan.exchange(self.val, self.rhs, add_fn=self._add)
 
@@ -394,5 +397,6 @@ class GeneralDistributedAssembly:
         self.eng.unpack_add_entries(1, rows.data_ptr(), rows.numel(), br.data_ptr())
 
     def exchange(self):
+        self.eng.flush()   # see DistributedAssembly.exchange
         with torch.cuda.stream(self.stream):
             self.plan.exchange(self.val, self.rhs, add_fn=self._add)

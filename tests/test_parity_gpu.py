@@ -114,9 +114,28 @@ def test_solver_interface_odd_contributions_and_norm(eng):
     assert rhs2[0] == rhs[0] + 0.25 and rhs2[1] == rhs[1] + 0.5
     with pytest.raises(E.EngineError, match="not been properly set up"):
         far = np.array([c.n_eqn - 1])
-        eng.insert_to_lhs(np.array([[1.0]]), rows[:1], far)
+        eng.insert_to_lhs(np.array([[1.0]]), rows[:1], far)   # recorded on the device (no wait per call) ...
+        eng.finish_assembly()                                  # ... and reported when the assembly is finished
     with pytest.raises(E.EngineError, match="out of bound"):
         eng.insert_to_rhs(np.array([1.0]), np.array([c.n_eqn]))
+
+
+def test_fields_replaced_during_assembly_is_an_error(eng):
+    """isl_field_set / isl_mesh_set drop the pattern and the values; when that happens between two assembly
+    calls on one solver (a second FieldBinder, a rebuilt binder) the system must not silently continue empty"""
+    c = flows.build_case("laplace_q1_hex", 3)
+    c.run_engine(eng=eng)
+    f = c.fields[0]
+    eng.set_field(0, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+    with pytest.raises(E.EngineError, match="create a new solver"):
+        eng.body_force_computation([1.0], 3, 0)
+    with pytest.raises(E.EngineError, match="create a new solver"):
+        eng.finish_assembly()
+    eng.new_solver(c.n_eqn)                      # a fresh solver is fine again
+    eng.body_force_computation([1.0], 3, 0)
+    eng.finish_assembly()
+    with pytest.raises(E.EngineError, match="field index out of range"):
+        eng.compute_residual_forces(E.K_LAPLACE, [1.0], 3, 0, 7)
 
 
 def test_error_behaviour(eng):
