@@ -169,7 +169,23 @@ int isl_rhs_norm(isl_handle h, double* norm);
  * benchmarked path.                                                                                            */
 int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations, double* error);
 
-/* ---- multi-GPU interface exchange helpers (element blocks per GPU, owned row ranges) -------------------- */
+/* ---- multi-GPU: one engine per process and GPU, NCCL inside the engine (the reference's only parallel
+ * construct is the OpenMP loop of base/auxi/parallel.hpp:25-60) ----------------------------------------------- */
+/* rank 0 makes the 128-byte NCCL id, the caller hands it to the other processes (file, socket, MPI, torch ...) */
+int isl_comm_unique_id(void* id128);
+int isl_comm_init(isl_handle h, const void* id128, int rank, int world);
+int isl_comm_destroy(isl_handle h);
+/* exchange plan, collective, after the pattern is registered.  l2g[n_local]: global equation of every local one;
+ * rows [own_lo, own_hi) are owned here (l2g ascending on that range); the ghost rows [seg_lo[k], seg_hi[k]) are
+ * assembled here but owned by rank seg_owner[k] (at most one segment per owner).  The (global row, global column)
+ * keys of the ghost entries go to the owners once, which locate them in their CSR.                            */
+int isl_exchange_setup(isl_handle h, int64_t n_local, const int64_t* l2g, int64_t own_lo, int64_t own_hi, int n_seg,
+                       const int* seg_owner, const int64_t* seg_lo, const int64_t* seg_hi);
+/* after the local assembly calls of a step: ghost values and rhs rows -> owners (ncclSend / ncclRecv on a second
+ * stream), added there; overlaps the interior patches of the Q1 row kernel, which launches interface patches first */
+int isl_exchange(isl_handle h);
+
+/* ---- helpers of the round-1 exchange driven from Python (kept for the torch.distributed / gloo path) ------- */
 /* gather val[idx[k]] (or rhs when which = 1) into a packed device buffer / scatter-add a packed buffer      */
 int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev);
 int isl_unpack_add_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, const double* in_dev);

@@ -113,6 +113,10 @@ struct AsmParams {
     const int32_t* cptr_t; const int32_t* cm_t; const double* cw_t;
     const int32_t* cptr_c; const int32_t* cm_c; const double* cw_c;
     const int64_t* rowptr; const int32_t* col;
+    // elements are processed in a locality-sorted order (smallest equation number of the element): neighbouring
+    // batches scatter into neighbouring CSR rows whatever the caller's element order is (nullptr: as given)
+    const int32_t* eorder;
+    __device__ __forceinline__ int64_t eid(int64_t k) const { return eorder ? (int64_t)eorder[k] : k; }
 };
 
 __device__ __forceinline__ int voigt_idx(int i, int j) {
@@ -201,7 +205,7 @@ __device__ void stage_batch(const AsmParams& p, const Stage<DIM>& s, int64_t bas
     for (int t = tid; t < nb * p.npe * DIM; t += nth) {
         const int eb = t / (p.npe * DIM), r = t % (p.npe * DIM);
         const int a = r / DIM, d = r % DIM;
-        s.sX[t] = p.coords[(size_t)p.conn[(base + eb) * p.npe + a] * DIM + d];
+        s.sX[t] = p.coords[(size_t)p.conn[(p.eid(base + eb)) * p.npe + a] * DIM + d];
     }
     __syncthreads();
     for (int t = tid; t < nb * p.nq; t += nth) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
             for (int t = tid; t < nb * p.nq; t += nth) {
                 const int eb = t / p.nq;
                 double F[3][3], S[3][3], C[6][6];
-                deformation_gradient<DIM>(p, s, base + eb, t, F);
+                deformation_gradient<DIM>(p, s, p.eid(base + eb), t, F);
                 material_eval(p.kernel_id, p.p0, p.p1, F, S, C, true);
                 double* ce = s.sQ + (size_t)t * 81;
                 for (int i = 0; i < DIM; i++)
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         for (int L = 0; L < DIM; L++) sum += gM[J] * ce[J * 9 + L] * gN[L];
                     acc += sum * (s.sDet[eq] * p.w[q]);
                 }
-                scatter_entry(p, base + eb, i, j, nr, ncl, acc);
+                scatter_entry(p, p.eid(base + eb), i, j, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_LAPLACE || p.kernel_id == ISL_K_VECTOR_LAPLACE) {
             for (int t = tid; t < nb * p.nt * p.nc; t += nth) {
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     for (int k = 1; k < DIM; k++) dot += gM[k] * gN[k];
                     acc += dot * (p.p0 * s.sDet[eq] * p.w[q]);
                 }
-                for (int c = 0; c < p.dsc; c++) scatter_entry(p, base + eb, M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
             // B(M d + i, N) = -detJ w g_M[i] psi_N
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGt[((size_t)eq * p.nt + M) * DIM + d] * p.Nc[q * p.nc + N];
                     }
-                scatter_entry(p, base + eb, i, N, nr, ncl, acc);
+                scatter_entry(p, p.eid(base + eb), i, N, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_VELOCITY_DIVERGENCE) {
             // transpose of the pressure-gradient block on the transposed tuple, optional sign change
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGc[((size_t)eq * p.nc + N) * DIM + d] * p.Nt[q * p.nt + Mp];
                     }
-                scatter_entry(p, base + eb, Mp, j, nr, ncl, sgn * acc);
+                scatter_entry(p, p.eid(base + eb), Mp, j, nr, ncl, sgn * acc);
             }
         }
         __syncthreads();
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
         if (!p.body) {
             for (int t = tid; t < nb * p.nq; t += nth) {
                 const int eb = t / p.nq, q = t % p.nq;
-                const int64_t e = base + eb;
+                const int64_t e = p.eid(base + eb);
                 double* qd = s.sQ + (size_t)t * 9;
                 if (p.kernel_id == ISL_K_HYPEL_STVENANT || p.kernel_id == ISL_K_HYPEL_NEOHOOKE) {
                     double F[3][3], S[3][3], C[6][6];
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
         }
         for (int t = tid; t < nb * nr; t += nth) {
             const int eb = t / nr, i = t % nr, M = i / p.dst, ci = i % p.dst;
-            const int64_t e = base + eb;
+            const int64_t e = p.eid(base + eb);
             double acc = 0.;
             for (int q = 0; q < p.nq; q++) {
                 const int eq = eb * p.nq + q;
@@ -606,6 +610,13 @@ __global__ void k_elem_eqn(const int32_t* ed, const int32_t* eqn, int64_t n_elem
         out[t] = eqn[(size_t)ed[ef] * ds + c];
     }
 }
+__global__ void k_elem_min_eqn(const int32_t* elem_eqn, int64_t n, int per, int32_t* key, int32_t* idx) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int32_t m = 0x7fffffff;
+        for (int a = 0; a < per; a++) { const int32_t q = elem_eqn[e * per + a]; if (q >= 0 && q < m) m = q; }
+        key[e] = m; idx[e] = (int32_t)e;
+    }
+}
 __global__ void k_make_keys(const int32_t* er, const int32_t* ec, int64_t n_elems, int nr, int ncl, uint64_t* keys) {
     const int64_t n = n_elems * nr * ncl;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -673,6 +684,7 @@ __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const d
         atomicAdd(dst + idx[i], in[i]);
 }
 
+#include "isl_comm.cuh"
 #include "isl_patch.cuh"
 #include "isl_rowgather.cuh"
 #include "isl_rows_fromk.cuh"
@@ -684,6 +696,7 @@ struct FieldDev {
     int deg = 0, ds = 0, ndpe = 0; int64_t n_obj = 0;
     DevBuf<int32_t> elem_dof, eqn; DevBuf<uint8_t> status; DevBuf<double> presc, values;
     DevBuf<int32_t> elem_eqn;  // [n_elems][ndpe*ds]
+    DevBuf<int32_t> eorder;    // locality-sorted element order of the generic kernels (get_eorder)
     // linear constraints with master DoFs (isl_field_set_constraints): dense pointer array [n_obj*ds+1], masters as
     // equation numbers; host copies feed the extra pattern keys in build_pattern
     bool has_masters = false;
@@ -695,7 +708,7 @@ struct FieldDev {
     }
     void reset() {
         set = false; dof_is_node = false; deg = ds = ndpe = 0; n_obj = 0;
-        elem_dof.release(); eqn.release(); status.release(); presc.release(); values.release(); elem_eqn.release();
+        elem_dof.release(); eqn.release(); status.release(); presc.release(); values.release(); elem_eqn.release(); eorder.release();
         reset_constraints(); h_elem_dof.clear(); h_eqn.clear();
     }
 };
@@ -745,8 +758,11 @@ struct isl_engine {
     int patch_ws = 0;           // warp-specialised patch kernel (compute warps + scatter warps, one CTA per SM)
     int defer_launch = 1;       // fuse stiffness + body force of the Q1 hot path into one launch
     DevBuf<unsigned long long> profbuf;
-    bool sys_touched = false;   // something has been assembled / inserted into the current system
-    bool sys_stale = false;     // mesh or field arrays were replaced after that: the system's entries are gone
+    std::unique_ptr<CommState> comm;   // NCCL communicator + interface-row exchange plan (isl_comm.cuh)
+    DevBuf<int64_t> l2g;               // local -> global equation (exchange plan)
+    bool sys_stale = false;     // mesh or field arrays were replaced while the system held matrix entries: they are gone
+    int tangent_sym = 1;        // symmetric register-tiled hyperelastic tangent (k_tangent_hypel_sym); ISL_TANGENT_SYM=0: k_tangent
+    int elem_order = 1;         // generic kernels walk the elements in a locality-sorted order (ISL_ELEM_ORDER=0: as given)
     int tangent_tiled = 0;      // ISL_TANGENT_TILED=1: register-tiled hyperelastic tangent (isl_tangent_tiled.cuh; not yet default)
 
     // staging of isl_insert_lhs / isl_insert_rhs operands: a ring of slices so that a copy never overwrites operands a
@@ -797,14 +813,14 @@ void upload_vec(isl_engine* h, DevBuf<T>& dst, const std::vector<T>& v) {
     }
 }
 
-// replacing mesh / field arrays drops the pattern and with it the values: if the current system already holds
-// contributions it becomes unusable (a second FieldBinder on the same solver, a binder rebuilt between two assembly
+// replacing mesh / field arrays drops the pattern and with it the matrix values: if the current system already holds
+// matrix contributions it becomes unusable (a second FieldBinder on the same solver, a binder rebuilt between two assembly
 // calls); later calls on it fail instead of silently continuing on an empty matrix
-void mark_stale_if_touched(isl_engine* h) { if (h->sys_touched) h->sys_stale = true; }
+void mark_stale_if_touched(isl_engine* h) { if (!h->val_is_zero && h->nnz > 0) h->sys_stale = true; }   // rhs survives, the matrix does not
 void require_live_system(isl_engine* h) {
     ISL_REQUIRE(!h->sys_stale, "mesh or field arrays were replaced after assembly into this system had started, so its entries "
                                "are gone: create a new solver first (one FieldBinder per solver is supported)");
-    h->sys_touched = true;
+    if (h->comm) h->comm->iface_event_valid = false;   // set again by the split launch of the Q1 row kernel only
 }
 
 void invalidate_pattern(isl_engine* h) {
@@ -977,6 +993,8 @@ size_t stage_doubles_per_elem(const AsmParams& p, int dim) {
     return n;
 }
 
+const int32_t* get_eorder(isl_engine* h, int field);
+
 void fill_common(isl_engine* h, AsmParams& p, int quad_deg, int t, int c) {
     ISL_REQUIRE(h->n_elems > 0, "mesh not set");
     FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
@@ -991,6 +1009,59 @@ void fill_common(isl_engine* h, AsmParams& p, int quad_deg, int t, int c) {
     p.cptr_t = ft.has_masters ? ft.cptr.p : nullptr; p.cm_t = ft.cmaster.p; p.cw_t = ft.cweight.p;
     p.cptr_c = fc.has_masters ? fc.cptr.p : nullptr; p.cm_c = fc.cmaster.p; p.cw_c = fc.cweight.p;
     p.rowptr = h->rowptr.p; p.col = h->col.p;
+    p.eorder = get_eorder(h, t);
+}
+
+// locality-sorted element order of a field (smallest equation number of the element), built once per numbering
+const int32_t* get_eorder(isl_engine* h, int field) {
+    if (!h->elem_order) return nullptr;
+    FieldDev& f = h->fields[field];
+    if (f.eorder.p && (int64_t)f.eorder.n == h->n_owned) return f.eorder.p;
+    const int64_t n = h->n_owned;
+    if (n <= 0 || n >= ((int64_t)1 << 31)) return nullptr;
+    build_elem_eqn(h, f);
+    DevBuf<int32_t> key, key2, idx;
+    key.alloc(n); key2.alloc(n); idx.alloc(n); f.eorder.alloc(n);
+    ISL_LAUNCH(h, k_elem_min_eqn, h->grid_for(n, 256), 256, 0, f.elem_eqn.p, n, f.ndpe * f.ds, key.p, idx.p);
+    size_t tb = 0;
+    ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, f.eorder.p, n, 0, 32, h->stream));
+    DevBuf<char> tmp; tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, f.eorder.p, n, 0, 32, h->stream));
+    h->launches += 4;
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    return f.eorder.p;
+}
+
+void launch_hypel_sym(isl_engine* h, AsmParams& p) {
+    const int nt = p.nt;
+    const int MC = (nt <= 10) ? 5 : 6;
+    int ntiles = 0;
+    for (int N = 0; N < nt; N++) ntiles += N / MC + 1;
+    ISL_REQUIRE(ntiles <= 160, "element too large for the tile table");
+    const HypelSymLayout L(p.npe, p.nq, nt);
+    const size_t per = (size_t)L.per_elem * sizeof(double);
+    ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
+    int EB = (int)std::max<size_t>(1, std::min<size_t>((size_t)(100 * 1024) / per, 16));
+    // CTA size: the multiple of 32 up to 256 that leaves the fewest idle thread slots in the tile phase
+    int best_nt = 256; double best_u = -1.;
+    for (int eb = EB; eb >= std::max(1, EB - 1); eb--)
+        for (int ntc = 256; ntc >= 96; ntc -= 32) {
+            const int items = eb * ntiles;
+            const double u = (double)items / (double)(((items + ntc - 1) / ntc) * ntc);
+            if (u > best_u + 0.03) { best_u = u; best_nt = ntc; EB = eb; }
+        }
+    p.EB = EB;
+    const size_t smem = per * EB;
+    auto launch = [&](auto kernel) {
+        ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t nbatch = (h->n_owned + EB - 1) / EB;
+        if (nbatch == 0) return;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
+        kernel<<<grid, best_nt, smem, h->stream>>>(p, ntiles);
+        h->launches++;
+        ISL_CUDA(cudaGetLastError());
+    };
+    if (MC == 5) launch(k_tangent_hypel_sym<5>); else launch(k_tangent_hypel_sym<6>);
 }
 
 template <class K>
@@ -1321,6 +1392,25 @@ bool q1_ready(isl_engine* h, int field) {
 template <bool MATRIX>
 void launch_patch(isl_engine* h, PatchSet* ps, const FieldDev& ft, double factor, int incremental, int body, double f0);
 
+// launch order of a patch set for the current exchange plan: interface patches first (built once per plan)
+bool comm_patch_order(isl_engine* h, PatchSet* ps) {
+    if (ps->perm_built) return ps->perm.p != nullptr;
+    ps->perm_built = true;
+    CommState& c = *h->comm;
+    if (!c.iface_row.p || ps->n_patches == 0) return false;
+    DevBuf<int32_t> flag; flag.alloc(ps->n_patches);
+    ISL_LAUNCH(h, k_comm_patch_flags, ps->n_patches, 64, 0, ps->p_row_off.p, ps->rows.p, c.iface_row.p, ps->n_patches, flag.p);
+    std::vector<int32_t> hf(ps->n_patches), perm; perm.reserve(ps->n_patches);
+    ISL_CUDA(cudaMemcpyAsync(hf.data(), flag.p, hf.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < ps->n_patches; k++) if (hf[k]) perm.push_back(k);
+    ps->n_iface = (int)perm.size();
+    for (int k = 0; k < ps->n_patches; k++) if (!hf[k]) perm.push_back(k);
+    upload_vec(h, ps->perm, perm);
+    if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] exchange overlap: %d of %d patches own interface rows and are launched first\n", ps->n_iface, ps->n_patches);
+    return true;
+}
+
 // one launch (affine row kernel) or two (general elements) of the Q1 hot path: stiffness + Dirichlet lift (matrix != 0)
 // and / or body force
 void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremental, int body, double f0) {
@@ -1347,12 +1437,27 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
         const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
         const int per_sm = (int)std::min<size_t>(nt == 256 ? 2 : 4, (size_t)(227 * 1024) / (smem_r + 1024));
         q.resident = h->n_sm * std::max(1, per_sm);
-        if (nt == 256) {
-            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-            ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), ps->n_patches, 256, smem_r, q);
+        auto launch_range = [&](int base, int count) {
+            if (count <= 0) return;
+            q.patch_base = base;
+            if (nt == 256) {
+                ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), count, 256, smem_r, q);
+            } else {
+                ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+                ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), count, 128, smem_r, q);
+            }
+        };
+        // multi-GPU: the patches that own interface rows first; the exchange starts when they are done and runs on the
+        // communication stream while the interior patches are assembled (isl_comm.cuh)
+        if (h->comm && h->comm->plan && comm_patch_order(h, ps) && ps->n_iface > 0 && ps->n_iface < ps->n_patches) {
+            q.perm = ps->perm.p;
+            launch_range(0, ps->n_iface);
+            ISL_CUDA(cudaEventRecord(h->comm->ev_iface, h->stream));
+            h->comm->iface_event_valid = true;
+            launch_range(ps->n_iface, ps->n_patches - ps->n_iface);
         } else {
-            ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-            ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), ps->n_patches, 128, smem_r, q);
+            launch_range(0, ps->n_patches);
         }
         return;
     }
@@ -1511,6 +1616,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_FAST")) h->q1_fast = atoi(m);  // 0 reference order, 1 sum factorisation, 3 + affine shortcut
         if (const char* m = getenv("ISL_DEFER")) h->defer_launch = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
         if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
@@ -1547,6 +1654,8 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else if (n == "aff_split") h->aff_split = v ? 1 : 0;
         else if (n == "aff_threads") h->patch_threads_aff = v;
         else if (n == "tangent_tiled") h->tangent_tiled = v ? 1 : 0;
+        else if (n == "tangent_sym") h->tangent_sym = v ? 1 : 0;
+        else if (n == "elem_order") h->elem_order = v ? 1 : 0;
         else if (n == "defer") h->defer_launch = v ? 1 : 0;
         else throw IslError("unknown option '" + n + "'");
     });
@@ -1637,6 +1746,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         flush_pending(h);
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned; h->affine_state = -1;
+        for (auto& f : h->fields) f.eorder.release();
         h->slotmaps.clear();
         h->patchsets.clear();
         h->fromk_sets.clear();
@@ -1756,7 +1866,7 @@ int isl_system_create(isl_handle h, int64_t n_eqn) {
         if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
         h->val_zero_pending = true;   // memset of the matrix values postponed, see materialize_zero()
         h->val_is_zero = true;
-        h->sys_touched = false; h->sys_stale = false;
+        h->sys_stale = false;
         if (h->ins_err.p) ISL_CUDA(cudaMemsetAsync(h->ins_err.p, 0, sizeof(int), h->stream));
     });
 }
@@ -1813,6 +1923,11 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT);
         p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : 0;
+        if (h->tangent_sym && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == 3 && h->dim == 3 && t == c &&
+            !ft.has_masters && ft.ndpe <= 27) {
+            launch_hypel_sym(h, p);
+            return;
+        }
         if (h->tangent_tiled && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == h->dim) {
             if (h->dim == 3) launch_staged(h, k_tangent_hypel_tiled<3>, p); else launch_staged(h, k_tangent_hypel_tiled<2>, p);
             return;
@@ -2023,6 +2138,167 @@ int isl_measure_fp64_peak(isl_handle h, double* tflops) {
         }
         cudaEventDestroy(a); cudaEventDestroy(b);
         *tflops = best;
+    });
+}
+
+// ---- multi-GPU: communicator and interface-row exchange inside the engine (isl_comm.cuh) ----
+int isl_comm_unique_id(void* id128) {
+    return guarded([&] {
+        ISL_REQUIRE(id128, "null id buffer");
+        nccl_dyn::ncclUniqueId id;
+        ISL_NCCL(nccl_dyn::api().GetUniqueId(&id));
+        std::memcpy(id128, &id, sizeof(id));
+    });
+}
+int isl_comm_init(isl_handle h, const void* id128, int rank, int world) {
+    return guarded([&] {
+        ISL_REQUIRE(id128 && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+        ISL_CUDA(cudaSetDevice(h->device));
+        flush_pending(h);
+        auto c = std::make_unique<CommState>();
+        c->rank = rank; c->world = world;
+        nccl_dyn::ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        ISL_NCCL(nccl_dyn::api().CommInitRank(&c->comm, world, id, rank));
+        ISL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        ISL_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+        ISL_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+        ISL_CUDA(cudaEventCreateWithFlags(&c->ev_iface, cudaEventDisableTiming));
+        h->comm = std::move(c);
+    });
+}
+int isl_comm_destroy(isl_handle h) {
+    return guarded([&] {
+        if (!h->comm) return;
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->comm->stream));
+        h->comm.reset();
+    });
+}
+int isl_exchange_setup(isl_handle h, int64_t n_local, const int64_t* l2g, int64_t own_lo, int64_t own_hi, int n_seg,
+                       const int* seg_owner, const int64_t* seg_lo, const int64_t* seg_hi) {
+    return guarded([&] {
+        ISL_REQUIRE(h->comm, "isl_comm_init must be called first");
+        ISL_REQUIRE(n_local == h->n_eqn, "l2g must cover the local system");
+        ISL_REQUIRE(h->nnz > 0 && h->rowptr.p, "register the pattern before the exchange plan");
+        ISL_CUDA(cudaSetDevice(h->device));
+        flush_pending(h);
+        CommState& c = *h->comm;
+        auto& N = nccl_dyn::api();
+        const int W = c.world;
+        c.plan = false; c.sends.clear(); c.recvs.clear(); c.iface_event_valid = false;
+        upload(h, h->l2g, l2g, (size_t)n_local);
+        c.iface_row.alloc((size_t)std::max<int64_t>(n_local, 1));
+        ISL_CUDA(cudaMemsetAsync(c.iface_row.p, 0, (size_t)std::max<int64_t>(n_local, 1), h->stream));
+        // what I send to whom: (entries, rows) per destination; everybody learns the whole table
+        std::vector<int64_t> mine((size_t)W * 2, 0);
+        for (int k = 0; k < n_seg; k++) {
+            ISL_REQUIRE(seg_owner[k] >= 0 && seg_owner[k] < W && seg_owner[k] != c.rank, "bad ghost segment owner");
+            ISL_REQUIRE(seg_lo[k] >= 0 && seg_lo[k] <= seg_hi[k] && seg_hi[k] <= n_local, "bad ghost segment");
+            ISL_REQUIRE(mine[(size_t)seg_owner[k] * 2 + 1] == 0, "one ghost segment per owner");
+            int64_t rp[2];
+            ISL_CUDA(cudaMemcpyAsync(&rp[0], h->rowptr.p + seg_lo[k], sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaMemcpyAsync(&rp[1], h->rowptr.p + seg_hi[k], sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            if (seg_hi[k] == seg_lo[k]) continue;
+            c.sends.push_back(CommSend{seg_owner[k], rp[0], rp[1] - rp[0], seg_lo[k], seg_hi[k] - seg_lo[k]});
+            mine[(size_t)seg_owner[k] * 2] = rp[1] - rp[0]; mine[(size_t)seg_owner[k] * 2 + 1] = seg_hi[k] - seg_lo[k];
+            ISL_LAUNCH(h, k_comm_mark, h->grid_for(seg_hi[k] - seg_lo[k], 256), 256, 0, c.iface_row.p, seg_lo[k], seg_hi[k]);
+        }
+        DevBuf<int64_t> dmine, dtable;
+        upload_vec(h, dmine, mine); dtable.alloc((size_t)W * W * 2);
+        ISL_NCCL(N.AllGather(dmine.p, dtable.p, (size_t)W * 2, nccl_dyn::ncclInt64, c.comm, h->stream));
+        std::vector<int64_t> table((size_t)W * W * 2);
+        ISL_CUDA(cudaMemcpyAsync(table.data(), dtable.p, table.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        // keys of my ghost entries, global ids of my ghost rows
+        std::vector<std::unique_ptr<DevBuf<uint64_t>>> skeys;
+        for (const CommSend& sd : c.sends) {
+            auto kb = std::make_unique<DevBuf<uint64_t>>(); kb->alloc((size_t)std::max<int64_t>(sd.n_val, 1));
+            ISL_LAUNCH(h, k_comm_keys, (unsigned)std::min<int64_t>(sd.n_rows, 65535), 32, 0, h->rowptr.p, h->col.p, h->l2g.p, sd.row_lo,
+                       sd.row_lo + sd.n_rows, kb->p);
+            skeys.push_back(std::move(kb));
+        }
+        std::vector<std::unique_ptr<DevBuf<uint64_t>>> rkeys;
+        std::vector<std::unique_ptr<DevBuf<int64_t>>> rrows;
+        for (int src = 0; src < W; src++) {
+            const int64_t ne = table[((size_t)src * W + c.rank) * 2], nr = table[((size_t)src * W + c.rank) * 2 + 1];
+            if (src == c.rank || nr == 0) continue;
+            auto rv = std::make_unique<CommRecv>();
+            rv->src = src; rv->n_val = ne; rv->n_rows = nr;
+            rv->pos.alloc((size_t)std::max<int64_t>(ne, 1)); rv->rows.alloc((size_t)nr);
+            rv->bval.alloc((size_t)std::max<int64_t>(ne, 1)); rv->brhs.alloc((size_t)nr);
+            auto kb = std::make_unique<DevBuf<uint64_t>>(); kb->alloc((size_t)std::max<int64_t>(ne, 1));
+            auto rb = std::make_unique<DevBuf<int64_t>>(); rb->alloc((size_t)nr);
+            rkeys.push_back(std::move(kb)); rrows.push_back(std::move(rb));
+            c.recvs.push_back(std::move(rv));
+        }
+        ISL_NCCL(N.GroupStart());
+        for (size_t k = 0; k < c.sends.size(); k++) {
+            const CommSend& sd = c.sends[k];
+            ISL_NCCL(N.Send(skeys[k]->p, (size_t)sd.n_val, nccl_dyn::ncclUint64, sd.dst, c.comm, h->stream));
+            ISL_NCCL(N.Send(h->l2g.p + sd.row_lo, (size_t)sd.n_rows, nccl_dyn::ncclInt64, sd.dst, c.comm, h->stream));
+        }
+        for (size_t k = 0; k < c.recvs.size(); k++) {
+            ISL_NCCL(N.Recv(rkeys[k]->p, (size_t)c.recvs[k]->n_val, nccl_dyn::ncclUint64, c.recvs[k]->src, c.comm, h->stream));
+            ISL_NCCL(N.Recv(rrows[k]->p, (size_t)c.recvs[k]->n_rows, nccl_dyn::ncclInt64, c.recvs[k]->src, c.comm, h->stream));
+        }
+        ISL_NCCL(N.GroupEnd());
+        DevBuf<int> derr; derr.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
+        for (size_t k = 0; k < c.recvs.size(); k++) {
+            CommRecv& rv = *c.recvs[k];
+            if (rv.n_val) ISL_LAUNCH(h, k_comm_locate, h->grid_for(rv.n_val, 128), 128, 0, rkeys[k]->p, rv.n_val, h->l2g.p, own_lo, own_hi,
+                                     h->rowptr.p, h->col.p, rv.pos.p, derr.p);
+            ISL_LAUNCH(h, k_comm_locate_rows, h->grid_for(rv.n_rows, 128), 128, 0, rrows[k]->p, rv.n_rows, h->l2g.p, own_lo, own_hi, rv.rows.p,
+                       c.iface_row.p, derr.p);
+        }
+        int err = 0;
+        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        ISL_REQUIRE(!err, "ghost entry missing in the owner's pattern (halo elements not registered?) or row not owned");
+        c.plan = true; c.plan_nnz = h->nnz;
+        for (auto& kv : h->patchsets) { kv.second->perm_built = false; kv.second->perm.release(); kv.second->n_iface = 0; }
+    });
+}
+int isl_exchange(isl_handle h) {
+    return guarded([&] {
+        ISL_REQUIRE(h->comm && h->comm->plan, "isl_exchange_setup must be called first");
+        ISL_REQUIRE(h->comm->plan_nnz == h->nnz, "the pattern changed after isl_exchange_setup");
+        ISL_CUDA(cudaSetDevice(h->device));
+        flush_pending(h);     // may be the split launch that records ev_iface
+        materialize_zero(h);
+        CommState& c = *h->comm;
+        auto& N = nccl_dyn::api();
+        if (c.iface_event_valid) {
+            ISL_CUDA(cudaStreamWaitEvent(c.stream, c.ev_iface, 0));
+        } else {
+            ISL_CUDA(cudaEventRecord(c.ev_ready, h->stream));
+            ISL_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
+        }
+        c.iface_event_valid = false;
+        ISL_NCCL(N.GroupStart());
+        for (const CommSend& sd : c.sends) {
+            if (sd.n_val) ISL_NCCL(N.Send(h->val.p + sd.val_lo, (size_t)sd.n_val, nccl_dyn::ncclFloat64, sd.dst, c.comm, c.stream));
+            ISL_NCCL(N.Send(h->rhs.p + sd.row_lo, (size_t)sd.n_rows, nccl_dyn::ncclFloat64, sd.dst, c.comm, c.stream));
+        }
+        for (auto& rv : c.recvs) {
+            if (rv->n_val) ISL_NCCL(N.Recv(rv->bval.p, (size_t)rv->n_val, nccl_dyn::ncclFloat64, rv->src, c.comm, c.stream));
+            ISL_NCCL(N.Recv(rv->brhs.p, (size_t)rv->n_rows, nccl_dyn::ncclFloat64, rv->src, c.comm, c.stream));
+        }
+        ISL_NCCL(N.GroupEnd());
+        for (auto& rv : c.recvs) {
+            if (rv->n_val) {
+                k_unpack_add<<<h->grid_for(rv->n_val, 256), 256, 0, c.stream>>>(h->val.p, rv->pos.p, rv->n_val, rv->bval.p);
+                h->launches++;
+            }
+            k_unpack_add<<<h->grid_for(rv->n_rows, 256), 256, 0, c.stream>>>(h->rhs.p, rv->rows.p, rv->n_rows, rv->brhs.p);
+            h->launches++;
+            ISL_CUDA(cudaGetLastError());
+        }
+        ISL_CUDA(cudaEventRecord(c.ev_done, c.stream));
+        ISL_CUDA(cudaStreamWaitEvent(h->stream, c.ev_done, 0));
+        h->val_is_zero = false;
     });
 }
 

@@ -1082,6 +1082,8 @@ struct PatchSet {
     // row-gather kernel (isl_rowgather.cuh): per owned row 64-byte RowMeta (slots, CSR positions, row id and start), neighbour nodes of rows next to CONSTRAINED nodes
     DevBuf<unsigned char> r_meta; DevBuf<int32_t> lift_nodes;
     bool rows_ok = false; int max_inst = 0;
+    // multi-GPU: launch order with the patches that own interface rows first (isl_comm.cuh), n_iface of them
+    DevBuf<int32_t> perm; int n_iface = 0; bool perm_built = false;
     double redundancy = 0.;
 };
 

@@ -302,6 +302,7 @@ struct RowsParams {
     int body; double f0;
     int node_cap, inst_cap, n_patches, resident;
     int matrix;   // 0: right-hand side only (body force without a stiffness call before it)
+    const int32_t* perm; int patch_base;   // launch order: patch = perm[blockIdx.x + patch_base] (perm may be null)
 };
 
 // preprocessing: one CTA per patch, threads over its rows.  pass 0 fills meta and numbers the rows that
@@ -471,7 +472,8 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
     double* sX = sD + (size_t)7 * p.inst_cap;
     double* stage = sX;
     const int tid = threadIdx.x;
-    const int pid = blockIdx.x;
+    const int slot_id = blockIdx.x + p.patch_base;
+    const int pid = p.perm ? p.perm[slot_id] : slot_id;
     const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
     const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
     const int e0 = p.p_inst_off[pid], ninst = p.p_inst_off[pid + 1] - e0;
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_affine(const RowsParams
     if (tid < nrows) rg_load_meta(m, p.meta + r0 + tid);
     rg_load_coords<NT>(p, sX, n0, nnodes, tid);
     if (tid < 7) sD[tid * p.inst_cap + p.inst_cap - 1] = 0.;
-    if (tid == NT - 1) rg_prefetch_patch(p, pid + p.resident);
+    if (tid == NT - 1 && slot_id + p.resident < p.n_patches) rg_prefetch_patch(p, p.perm ? p.perm[slot_id + p.resident] : slot_id + p.resident);
     __syncthreads();
     // phase 1: element instances
     const double w = c_q1_w[0];
@@ -553,7 +555,8 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
     double* sX = sK + (size_t)44 * p.inst_cap;
     double* stage = sX;
     const int tid = threadIdx.x;
-    const int pid = blockIdx.x;
+    const int slot_id = blockIdx.x + p.patch_base;
+    const int pid = p.perm ? p.perm[slot_id] : slot_id;
     const int r0 = p.p_row_off[pid], nrows = p.p_row_off[pid + 1] - r0;
     const int n0 = p.p_node_off[pid], nnodes = p.p_node_off[pid + 1] - n0;
     const int e0 = p.p_inst_off[pid], ninst = p.p_inst_off[pid + 1] - e0;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_general(const RowsParam
         ln4[u] = (i < ninst) ? __ldg(reinterpret_cast<const int4*>(p.i_lnode + (size_t)(e0 + i) * 8)) : make_int4(0, 0, 0, 0);
     }
     rg_load_coords<NT>(p, sX, n0, nnodes, tid);
-    if (tid == NT - 1) rg_prefetch_patch(p, pid + p.resident);
+    if (tid == NT - 1 && slot_id + p.resident < p.n_patches) rg_prefetch_patch(p, p.perm ? p.perm[slot_id + p.resident] : slot_id + p.resident);
     __syncthreads();
     // phase 1: local matrices of the element instances
     auto instance = [&](int i, const int4& l4) {

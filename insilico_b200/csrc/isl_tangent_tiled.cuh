@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_tiled(const AsmParams p) 
         for (int t = tid; t < nb * p.nq; t += nth) {
             const int eb = t / p.nq;
             double F[3][3], S[3][3], C[6][6];
-            deformation_gradient<DIM>(p, s, base + eb, t, F);
+            deformation_gradient<DIM>(p, s, p.eid(base + eb), t, F);
             material_eval(p.kernel_id, p.p0, p.p1, F, S, C, true);
             double* ce = s.sQ + (size_t)t * 81;
             for (int i = 0; i < DIM; i++)
@@ -97,11 +97,179 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_tiled(const AsmParams p) 
                     for (int i = 0; i < DIM; i++)
 #pragma unroll
                         for (int k = 0; k < DIM; k++)
-                            scatter_entry(p, base + eb, M * DIM + i, N * DIM + k, nr, ncl, acc[m][i * DIM + k]);
+                            scatter_entry(p, p.eid(base + eb), M * DIM + i, N * DIM + k, nr, ncl, acc[m][i * DIM + k]);
                 }
             }
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_tangent_hypel_sym<MC>: the hyperelastic tangent with
+//   * the effective elasticity per quadrature point formed by ALL threads in two contraction steps,
+//       D[A,J,k,L] = sum_B C[V(A,J),V(B,L)] F[k,B],   Ceff[i,J,k,L] = delta_ik S[J,L] + sum_A F[i,A] D[A,J,k,L]
+//     (2 x 243 multiply-adds per point, one thread per (point, J, k, L); k_tangent / the tiled kernel above give a
+//     whole point to one thread, 2187 x 2 multiplies, while the other threads of the CTA wait),
+//   * symmetry: Ceff[i,J,k,L] = Ceff[k,L,i,J] (S symmetric, C with major symmetry), hence K[(M,i),(N,k)] =
+//     K[(N,k),(M,i)]: only node pairs M <= N are integrated and every block is scattered together with its transpose
+//     (Q2 hex: 378 instead of 729 node pairs),
+//   * register tiles: a thread owns trial node N and up to MC test nodes M <= N; per point it contracts Ceff with
+//     det J w g_N once (81 multiply-adds, the 81 numbers are the same for all lanes of a warp working on one element:
+//     broadcast 16-byte loads) and spends 27 multiply-adds per test node on 3 loads; 9 MC results stay in registers.
+// Multiply-adds per Q2-hex element and point: 75 x 81 + 378 x 27 = 16.3 k (k_tangent: 59 k, the tiled kernel: 32.8 k;
+// the algorithmic count of SURVEY 8(d) without symmetry: 21.9 k).
+// Shared memory per element (doubles): X npe*3 | contra nq*9 | det nq | G nq*nt*3 | Ceff nq*82 | F,S,C nq*54.
+constexpr int HS_QSTRIDE = 82;   // 81 numbers of Ceff per point, padded to a 16-byte multiple
+
+struct HypelSymLayout {
+    int per_elem;   // doubles
+    int oX, oCon, oDet, oG, oQ, oM;
+    __host__ __device__ HypelSymLayout(int npe, int nq, int nt) {
+        oX = 0; oCon = oX + npe * 3; oDet = oCon + nq * 9; oG = oDet + nq; oG += (oG & 1);
+        oQ = oG + nq * nt * 3; oQ += (oQ & 1); oM = oQ + nq * HS_QSTRIDE; per_elem = oM + nq * 54; per_elem += (per_elem & 1);
+    }
+};
+
+template <int MC>
+__global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, int ntiles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ unsigned char sTileN[160], sTileM0[160];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nt = p.nt, nq = p.nq, npe = p.npe;
+    const HypelSymLayout L(npe, nq, nt);
+    // tiles of one element: for every trial node N the test nodes 0..N in chunks of MC
+    if (tid == 0) {
+        int t = 0;
+        for (int N = 0; N < nt; N++)
+            for (int M0 = 0; M0 <= N; M0 += MC) { sTileN[t] = (unsigned char)N; sTileM0[t] = (unsigned char)M0; t++; }
+    }
+    for (int64_t base = (int64_t)blockIdx.x * p.EB; base < p.n_elems; base += (int64_t)gridDim.x * p.EB) {
+        const int nb = (int)min((int64_t)p.EB, p.n_elems - base);
+        __syncthreads();   // previous batch done with the staging area
+        // coordinates
+        for (int t = tid; t < nb * npe * 3; t += nth) {
+            const int eb = t / (npe * 3), r = t % (npe * 3);
+            smem[(size_t)eb * L.per_elem + L.oX + r] = p.coords[(size_t)p.conn[p.eid(base + eb) * npe + r / 3] * 3 + r % 3];
+        }
+        __syncthreads();
+        // J^-T and det J per point (base/geometry.hpp:142-177,419-445)
+        for (int t = tid; t < nb * nq; t += nth) {
+            const int eb = t / nq, q = t % nq;
+            double* E = smem + (size_t)eb * L.per_elem;
+            const double* dN = p.dNg + (size_t)q * npe * 3;
+            double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int n = 0; n < npe; n++)
+                for (int i = 0; i < 3; i++)
+                    for (int a = 0; a < 3; a++) J[i][a] += E[L.oX + n * 3 + i] * dN[n * 3 + a];
+            double aux[3][3], inv[3][3];
+            for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) aux[i][a] = J[a][i];
+            E[L.oDet + q] = inv3(aux, inv);
+            for (int i = 0; i < 3; i++) for (int a = 0; a < 3; a++) E[L.oCon + q * 9 + i * 3 + a] = inv[i][a];
+        }
+        __syncthreads();
+        // physical gradients g_a = J^-T grad_xi phi_a
+        for (int t = tid; t < nb * nq * nt; t += nth) {
+            const int eb = t / (nq * nt), r = t % (nq * nt), q = r / nt;
+            double* E = smem + (size_t)eb * L.per_elem;
+            const double* con = E + L.oCon + q * 9;
+            const double* dN = p.dNt + (size_t)r * 3;
+#pragma unroll
+            for (int c = 0; c < 3; c++) E[L.oG + r * 3 + c] = con[c * 3] * dN[0] + con[c * 3 + 1] * dN[1] + con[c * 3 + 2] * dN[2];
+        }
+        __syncthreads();
+        // F, S, C per point (solid/Deformation.hpp:25-46, mat/hypel/*.hpp)
+        for (int t = tid; t < nb * nq; t += nth) {
+            const int eb = t / nq, q = t % nq;
+            double* E = smem + (size_t)eb * L.per_elem;
+            const int64_t e = p.eid(base + eb);
+            double GradU[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            const double* g = E + L.oG + (size_t)q * nt * 3;
+            for (int f = 0; f < nt; f++) {
+                const int32_t obj = p.ed_c[e * nt + f];
+                for (int J = 0; J < 3; J++)
+                    for (int i = 0; i < 3; i++) GradU[J][i] += g[f * 3 + J] * p.val_c[(size_t)obj * 3 + i];
+            }
+            double F[3][3], S[3][3], C[6][6];
+            for (int i = 0; i < 3; i++) for (int J = 0; J < 3; J++) F[i][J] = (i == J ? 1. : 0.) + GradU[J][i];
+            material_eval(p.kernel_id, p.p0, p.p1, F, S, C, true);
+            double* m = E + L.oM + q * 54;
+            for (int i = 0; i < 3; i++) for (int J = 0; J < 3; J++) { m[i * 3 + J] = F[i][J]; m[9 + i * 3 + J] = S[i][J]; }
+            for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) m[18 + a * 6 + b] = C[a][b];
+        }
+        __syncthreads();
+        // effective elasticity, one thread per (point, J, k, L)
+        for (int t = tid; t < nb * nq * 27; t += nth) {
+            const int eb = t / (nq * 27), r = t % (nq * 27), q = r / 27, jkl = r % 27, J = jkl / 9, k = (jkl / 3) % 3, Lx = jkl % 3;
+            double* E = smem + (size_t)eb * L.per_elem;
+            const double* m = E + L.oM + q * 54;
+            double D[3];
+#pragma unroll
+            for (int A = 0; A < 3; A++) {
+                double d = 0.;
+#pragma unroll
+                for (int B = 0; B < 3; B++) d = fma(m[18 + voigt_idx(A, J) * 6 + voigt_idx(B, Lx)], m[k * 3 + B], d);
+                D[A] = d;
+            }
+            double* ce = E + L.oQ + q * HS_QSTRIDE;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                double v = (i == k) ? m[9 + J * 3 + Lx] : 0.;
+#pragma unroll
+                for (int A = 0; A < 3; A++) v = fma(m[i * 3 + A], D[A], v);
+                ce[((i * 3 + J) * 3 + k) * 3 + Lx] = v;
+            }
+        }
+        __syncthreads();
+        // register tiles
+        const int items = nb * ntiles;
+        for (int t = tid; t < items; t += nth) {
+            const int eb = t / ntiles, tl = t % ntiles;
+            const int N = sTileN[tl], M0 = sTileM0[tl];
+            const double* E = smem + (size_t)eb * L.per_elem;
+            const double* G = E + L.oG;
+            double acc[MC][9];
+#pragma unroll
+            for (int m = 0; m < MC; m++)
+#pragma unroll
+                for (int x = 0; x < 9; x++) acc[m][x] = 0.;
+            for (int q = 0; q < nq; q++) {
+                const double wd = E[L.oDet + q] * p.w[q];
+                const double* gN = G + ((size_t)q * nt + N) * 3;
+                const double g0 = gN[0] * wd, g1 = gN[1] * wd, g2 = gN[2] * wd;
+                const double* c = E + L.oQ + q * HS_QSTRIDE;   // the same address in all lanes working on this element: broadcast
+                double T[27];   // [i][J][k]
+#pragma unroll
+                for (int x = 0; x < 27; x++) T[x] = fma(c[x * 3 + 2], g2, fma(c[x * 3 + 1], g1, c[x * 3] * g0));
+#pragma unroll
+                for (int m = 0; m < MC; m++) {
+                    const int M = min(M0 + m, N);
+                    const double* gM = G + ((size_t)q * nt + M) * 3;
+                    const double h0 = gM[0], h1 = gM[1], h2 = gM[2];
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            acc[m][i * 3 + k] = fma(h2, T[(i * 3 + 2) * 3 + k], fma(h1, T[(i * 3 + 1) * 3 + k], fma(h0, T[(i * 3 + 0) * 3 + k], acc[m][i * 3 + k])));
+                }
+            }
+            const int64_t e = p.eid(base + eb);
+            const int nr = nt * 3;
+#pragma unroll
+            for (int m = 0; m < MC; m++) {
+                const int M = M0 + m;
+                if (M <= N) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++)
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const double v = acc[m][i * 3 + k];
+                            scatter_entry(p, e, M * 3 + i, N * 3 + k, nr, nr, v);
+                            if (M != N) scatter_entry(p, e, N * 3 + k, M * 3 + i, nr, nr, v);
+                        }
+                }
+            }
+        }
     }
 }
 #endif

@@ -39,7 +39,7 @@ EXPORTED = [
     "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
-    "isl_unpack_add_entries",
+    "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange",
 ]
 
 
@@ -350,6 +350,31 @@ class Engine:
         v = C.c_double()
         _chk(lib().isl_rhs_norm(self.h, C.byref(v)))
         return v.value
+
+    # multi-GPU exchange inside the engine (NCCL, isl_comm.cuh)
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _chk(lib().isl_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        _chk(lib().isl_comm_init(self.h, C.c_char_p(unique_id), int(rank), int(world)))
+
+    def comm_destroy(self):
+        _chk(lib().isl_comm_destroy(self.h))
+
+    def exchange_setup(self, l2g, own_lo, own_hi, segments):
+        """segments: [(owner rank, row_lo, row_hi), ...] ghost rows in local numbering"""
+        l2g = np.ascontiguousarray(l2g, dtype=np.int64)
+        own = np.array([s[0] for s in segments], dtype=np.int32)
+        lo = np.array([s[1] for s in segments], dtype=np.int64)
+        hi = np.array([s[2] for s in segments], dtype=np.int64)
+        _chk(lib().isl_exchange_setup(self.h, _i64(len(l2g)), _ptr(l2g), _i64(own_lo), _i64(own_hi), len(segments),
+                                      _ptr(own), _ptr(lo), _ptr(hi)))
+
+    def exchange(self):
+        _chk(lib().isl_exchange(self.h))
 
     def pack_entries(self, which, idx_dev, n, out_dev):
         _chk(lib().isl_pack_entries(self.h, which, _ptr(idx_dev), _i64(n), _ptr(out_dev)))

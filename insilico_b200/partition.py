@@ -69,6 +69,30 @@ def structured_laplace_slab(e1, e2, e3_total, rank, world, dirichlet_fun):
                 ghost_source=rank - 1 if rank > 0 else -1)
 
 
+def _run_p2p(ops):
+    """ops: [("send" | "recv", tensor, peer), ...].  nccl moves CUDA tensors directly; gloo has no point-to-point
+    operations on CUDA tensors, so they are staged through the host (used by the two-process test on ONE GPU, where
+    NCCL refuses two ranks on the same device)."""
+    if not ops:
+        return
+    stage = dist.get_backend() == "gloo"
+    real, back = [], []
+    for kind, t, peer in ops:
+        if stage and t.is_cuda:
+            if kind == "send":
+                c = t.detach().cpu().contiguous()
+            else:
+                c = torch.empty(t.shape, dtype=t.dtype)
+                back.append((t, c))
+            real.append(dist.P2POp(dist.isend if kind == "send" else dist.irecv, c, peer))
+        else:
+            real.append(dist.P2POp(dist.isend if kind == "send" else dist.irecv, t, peer))
+    for w in dist.batch_isend_irecv(real):
+        w.wait()
+    for t, c in back:
+        t.copy_(c)
+
+
 class GhostExchange:
     """Static exchange plan for ghost rows that form one contiguous local row range sent to a single owner
     (z-slabs).  Works on CPU tensors (gloo) and CUDA tensors (nccl)."""
@@ -126,12 +150,10 @@ class GhostExchange:
     def _sendrecv(self, send, recv):
         ops = []
         if self.dst >= 0:
-            ops.append(dist.P2POp(dist.isend, send, self.dst))
+            ops.append(("send", send, self.dst))
         if self.src >= 0:
-            ops.append(dist.P2POp(dist.irecv, recv, self.src))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            ops.append(("recv", recv, self.src))
+        _run_p2p(ops)
 
     def exchange(self, val, rhs, add_fn=None):
         """one assembly step: ghost values and ghost rhs rows go to the owner and are added there"""
@@ -144,12 +166,10 @@ class GhostExchange:
             self._rr = torch.empty(self.n_recv_rows if self.src >= 0 else 0, dtype=val.dtype, device=dev)
         ops = []
         if self.dst >= 0:
-            ops += [dist.P2POp(dist.isend, send_v, self.dst), dist.P2POp(dist.isend, send_r, self.dst)]
+            ops += [("send", send_v, self.dst), ("send", send_r, self.dst)]
         if self.src >= 0:
-            ops += [dist.P2POp(dist.irecv, self._rv, self.src), dist.P2POp(dist.irecv, self._rr, self.src)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            ops += [("recv", self._rv, self.src), ("recv", self._rr, self.src)]
+        _run_p2p(ops)
         if self.src >= 0:
             if add_fn is not None:
                 add_fn(self.pos, self._rv, self.recv_row_lo, self._rr)
@@ -173,6 +193,18 @@ def wrap_device(ptr, n, dtype, device):
     return torch.as_tensor(_DevArray(ptr, n, typestr), device=device)
 
 
+def engine_comm_init(eng, rank, world):
+    """NCCL communicator inside the engine (isl_comm_init): rank 0 makes the id, torch.distributed only carries the
+    128 bytes to the other ranks.  ISL_TORCH_EXCHANGE=1 keeps the round-1 exchange through torch point-to-point calls."""
+    import os
+    if os.environ.get("ISL_TORCH_EXCHANGE") or not dist.is_initialized() or dist.get_backend() != "nccl":
+        return False
+    box = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    eng.comm_init(box[0], rank, world)
+    return True
+
+
 class DistributedAssembly:
     """binds a GhostExchange to an Engine: device CSR wrapped as torch tensors, all work on the engine's stream"""
 
@@ -181,6 +213,7 @@ class DistributedAssembly:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.ExternalStream(eng.stream, device=self.device)
         self.plan = GhostExchange(rank, world, wl)
+        self.native = engine_comm_init(eng, rank, world)
 
     def setup_fields(self):
         wl = self.wl
@@ -194,6 +227,13 @@ class DistributedAssembly:
                 wrap_device(val, nnz, torch.float64, self.device), wrap_device(rhs, n, torch.float64, self.device))
 
     def setup_exchange(self):
+        if self.native:
+            wl = self.wl
+            self.eng.finish_assembly()
+            l2g = np.arange(wl["n_eqn_local"], dtype=np.int64) + wl["eqn_offset"]
+            segs = [(wl["ghost_owner"],) + tuple(wl["ghost_rows"])] if wl["ghost_owner"] >= 0 else []
+            self.eng.exchange_setup(l2g, wl["owned_rows"][0], wl["owned_rows"][1], segs)
+            return
         with torch.cuda.stream(self.stream):
             rp, col, self.val, self.rhs = self._tensors()
             self.plan.setup(rp, col)
@@ -207,6 +247,9 @@ class DistributedAssembly:
         self.eng.unpack_add_entries(1, self._rows.data_ptr(), rr.numel(), rr.data_ptr())
 
     def exchange(self):
+        if self.native:
+            self.eng.exchange()    # isl_exchange: NCCL on the engine's communication stream, overlapped with interior patches
+            return
         # a Q1 stiffness launch may still be deferred inside the engine (it waits one call for a body force to fuse):
         # the ghost rows must be in memory before they are sent
         self.eng.flush()
@@ -316,22 +359,26 @@ class GeneralExchange:
             keys[dst] = torch.stack([l2g[rows], l2g[col[a:b].to(torch.int64)]])
             mine[dst, 0], mine[dst, 1] = b - a, hi - lo
             self.send.append((dst, (a, b), (lo, hi)))
-        table = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(table, mine)
+        if dist.get_backend() == "gloo" and mine.is_cuda:   # no CUDA collectives in gloo: through the host
+            mc = mine.cpu()
+            tc = [torch.zeros_like(mc) for _ in range(self.world)]
+            dist.all_gather(tc, mc)
+            table = [t.to(dev) for t in tc]
+        else:
+            table = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(table, mine)
         ops, rbuf = [], {}
         for dst, _, (lo, hi) in self.send:
-            ops.append(dist.P2POp(dist.isend, keys[dst].contiguous(), dst))
-            ops.append(dist.P2POp(dist.isend, l2g[lo:hi].contiguous(), dst))
+            ops.append(("send", keys[dst].contiguous(), dst))
+            ops.append(("send", l2g[lo:hi].contiguous(), dst))
         for src in range(self.world):
             n_ent, n_rows = int(table[src][self.rank, 0]), int(table[src][self.rank, 1])
             if src == self.rank or n_rows == 0:
                 continue
             rbuf[src] = (torch.zeros(2, n_ent, dtype=torch.int64, device=dev), torch.zeros(n_rows, dtype=torch.int64, device=dev))
-            ops.append(dist.P2POp(dist.irecv, rbuf[src][0], src))
-            ops.append(dist.P2POp(dist.irecv, rbuf[src][1], src))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            ops.append(("recv", rbuf[src][0], src))
+            ops.append(("recv", rbuf[src][1], src))
+        _run_p2p(ops)
         for src, (k, grows) in rbuf.items():
             r, c = g2l[k[0]], g2l[k[1]]
             if bool((r < 0).any()) or bool((r >= self.wl["n_owned_rows"]).any()):
@@ -352,15 +399,13 @@ class GeneralExchange:
     def exchange(self, val, rhs, add_fn=None):
         ops, bufs = [], []
         for dst, (a, b), (lo, hi) in self.send:
-            ops += [dist.P2POp(dist.isend, val[a:b], dst), dist.P2POp(dist.isend, rhs[lo:hi], dst)]
+            ops += [("send", val[a:b], dst), ("send", rhs[lo:hi], dst)]
         for src, pos, rows in self.recv:
             bv = torch.empty(pos.numel(), dtype=val.dtype, device=val.device)
             br = torch.empty(rows.numel(), dtype=val.dtype, device=val.device)
             bufs.append((pos, rows, bv, br))
-            ops += [dist.P2POp(dist.irecv, bv, src), dist.P2POp(dist.irecv, br, src)]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            ops += [("recv", bv, src), ("recv", br, src)]
+        _run_p2p(ops)
         for pos, rows, bv, br in bufs:
             if add_fn is not None:
                 add_fn(pos, bv, rows, br)
@@ -378,12 +423,18 @@ class GeneralDistributedAssembly:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.ExternalStream(eng.stream, device=self.device)
         self.plan = GeneralExchange(rank, world, wl)
+        self.native = engine_comm_init(eng, rank, world)
         eng.set_mesh(shape, geom_deg, wl["coords"], wl["conn"])
         eng.set_owned_elements(wl["n_owned_elems"])
         for i, f in enumerate(wl["fields"]):
             eng.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
 
     def setup_exchange(self):
+        if self.native:
+            wl = self.wl
+            self.eng.finish_assembly()
+            self.eng.exchange_setup(wl["l2g"], 0, wl["n_owned_rows"], wl["ghost_segments"])
+            return
         with torch.cuda.stream(self.stream):
             n, nnz = self.eng.finish_assembly()
             rp, col, val, rhs = self.eng.device_csr()
@@ -397,6 +448,9 @@ class GeneralDistributedAssembly:
         self.eng.unpack_add_entries(1, rows.data_ptr(), rows.numel(), br.data_ptr())
 
     def exchange(self):
+        if self.native:
+            self.eng.exchange()
+            return
         self.eng.flush()   # see DistributedAssembly.exchange
         with torch.cuda.stream(self.stream):
             self.plan.exchange(self.val, self.rhs, add_fn=self._add)

@@ -18,6 +18,9 @@ def fun(x):
     return (1.0 / (4.0 * np.pi)) / d
 
 
+MATRIX_ONLY = len(sys.argv) > 2 and sys.argv[2] == "matrix_only"   # the Q1 stiffness launch is the LAST call before the exchange
+
+
 def assemble(eng, wl, part=None):
     eng.set_mesh(E.HEX, 1, wl["coords"], wl["conn"])
     if part is not None:
@@ -30,8 +33,12 @@ def assemble(eng, wl, part=None):
         part.setup_exchange()
     for _ in range(2):  # second pass exercises the cached plan
         eng.new_solver(wl["n_eqn_local"])
-        eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
-        eng.body_force_computation([1.0], 3, 0)
+        if MATRIX_ONLY:
+            eng.body_force_computation([1.0], 3, 0)
+            eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)   # deferred inside the engine
+        else:
+            eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
+            eng.body_force_computation([1.0], 3, 0)
         if part is not None:
             part.exchange()
     return eng.get_csr()
@@ -41,8 +48,14 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     e = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+    backend = os.environ.get("ISL_DIST_BACKEND", "nccl")
+    if os.environ.get("ISL_DIST_SAME_GPU"):   # two processes on ONE GPU (gloo carries the exchange through the host)
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
     wl = partition.structured_laplace_slab(e, e, e * world, rank, world, fun)
     eng = E.Engine(local)
     part = partition.DistributedAssembly(eng, wl, rank, world)

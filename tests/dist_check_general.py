@@ -23,8 +23,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     name = sys.argv[1] if len(sys.argv) > 1 else "stokes_p2p1_tet"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    backend = os.environ.get("ISL_DIST_BACKEND", "nccl")
+    if os.environ.get("ISL_DIST_SAME_GPU"):   # two processes on ONE GPU (gloo carries the exchange through the host)
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group(backend)
     case = flows.build_case(name, n, True, True)
     wl = partition.general_partition(case.coords, case.conn, case.fields, case.n_eqn, rank, world)
     eng = E.Engine(local)

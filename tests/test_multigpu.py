@@ -20,8 +20,33 @@ def test_two_gpu_slab_assembly_matches_single_gpu():
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
-@pytest.mark.skipif(not os.environ.get("ISL_TEST_EXPERIMENTAL"),
-                    reason="general partition on GPUs has not run yet (CPU/gloo-verified); set ISL_TEST_EXPERIMENTAL=1")
+def _torchrun(script, args, port, env_extra=None, nproc=2, timeout=900):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", script)] + [str(a) for a in args]
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+ONE_GPU = {"ISL_DIST_BACKEND": "gloo", "ISL_DIST_SAME_GPU": "1"}
+
+
+@pytest.mark.parametrize("mode", ["", "matrix_only"])
+def test_two_ranks_on_one_gpu_slab_assembly(mode):
+    """the N > 1 path on a box with ONE GPU: two processes share the device, every one with its own engine, element
+    block, owned rows and pattern-only halo elements; gloo carries the ghost rows through the host (NCCL refuses two
+    ranks per device).  matrix_only: the deferred Q1 stiffness launch is the last call before the exchange."""
+    out = _torchrun("dist_check.py", [10] + ([mode] if mode else []), 29541, ONE_GPU)
+    assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 3), ("laplace_q1_hex", 8)])
+def test_two_ranks_on_one_gpu_general_partition(name, n):
+    out = _torchrun("dist_check_general.py", [name, n], 29542, ONE_GPU)
+    assert out.returncode == 0 and "DIST_CHECK_GENERAL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 @pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 4), ("laplace_q1_hex", 10)])
 def test_two_gpu_general_partition_matches_oracle(name, n):
     """general element-block partition (Morton blocks of a permuted mesh, several fields, all-to-all ghost exchange)"""

@@ -132,7 +132,9 @@ def test_fields_replaced_during_assembly_is_an_error(eng):
     with pytest.raises(E.EngineError, match="create a new solver"):
         eng.finish_assembly()
     eng.new_solver(c.n_eqn)                      # a fresh solver is fine again
-    eng.body_force_computation([1.0], 3, 0)
+    eng.body_force_computation([1.0], 3, 0)      # right-hand side only: replacing the fields now loses nothing
+    eng.set_field(0, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+    eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
     eng.finish_assembly()
     with pytest.raises(E.EngineError, match="field index out of range"):
         eng.compute_residual_forces(E.K_LAPLACE, [1.0], 3, 0, 7)
