@@ -106,9 +106,13 @@ __global__ void __launch_bounds__(128) k_q1hex_elemK(const FromKParams p) {
     }
     double K[36], detw[8], bf[8];
     q1_K_fast(X, p.r.factor, K, detw, bf, true);
+    // the diagonal entries are not stored: the local matrix of the Laplace operator has zero row sums, the row kernel
+    // recovers the diagonal of the assembled row from its off-diagonal entries (8 of 44 arrays less to write and read)
     double* out = p.K + t;
 #pragma unroll
-    for (int k = 0; k < 36; k++) out[(size_t)k * p.n_elems] = K[k];
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = a + 1; b < 8; b++) out[(size_t)sym_idx(a, b) * p.n_elems] = K[sym_idx(a, b)];
 #pragma unroll
     for (int a = 0; a < 8; a++) out[(size_t)(36 + a) * p.n_elems] = bf[a];
 }
@@ -130,19 +134,34 @@ __global__ void __launch_bounds__(NT) k_q1hex_rows_fromK(const FromKParams p) {
         const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.row_pos + r * 8) + 1);
         const int pos[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         double body = 0.;
-        // all loads of a slot are issued before they are used: 9 independent coalesced loads per slot
+        // four slots at a time: 32 independent coalesced loads are in flight before the first is used (rows without an
+        // element in a slot read column 0 with weight zero, so that no load hides behind a branch)
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-            if (pos[a] < 0) continue;
-            const double* kc = p.K + pos[a];
-            double v[8];
+        for (int h4 = 0; h4 < 2; h4++) {
+            double v[4][8];
 #pragma unroll
-            for (int b = 0; b < 8; b++) v[b] = __ldg(kc + (size_t)sym_idx(a, b) * p.n_elems);
-            const double bv = __ldg(kc + (size_t)(36 + a) * p.n_elems);
+            for (int u = 0; u < 4; u++) {
+                const int a = h4 * 4 + u;
+                const double* kc = p.K + max(pos[a], 0);
 #pragma unroll
-            for (int b = 0; b < 8; b++) acc[rg_kidx(a, b)] += v[b];
-            body += bv;
+                for (int b = 0; b < 8; b++) v[u][b] = __ldg(kc + (size_t)(b == a ? 36 + a : sym_idx(a, b)) * p.n_elems);   // slot b == a: body force
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int a = h4 * 4 + u;
+                const double wgt = pos[a] >= 0 ? 1.0 : 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    if (b == a) body = fma(wgt, v[u][b], body);
+                    else acc[rg_kidx(a, b)] = fma(wgt, v[u][b], acc[rg_kidx(a, b)]);
+                }
+            }
         }
+        // diagonal of the row: minus the sum of the 26 other stencil entries (zero row sums of every local matrix)
+        double dsum = 0.;
+#pragma unroll
+        for (int k = 0; k < 27; k++) if (k != 13) dsum += acc[k];
+        acc[13] = -dsum;
         rg_rhs(p.r, m, acc, body);
     }
     if (p.matrix) {

@@ -54,6 +54,7 @@ struct InstallHook {
         B200::solveHook() = &hostSolve;
         B200::nativeCG() = (std::getenv("ISL_NATIVE_CG") != NULL);   // default: the host stand-in, like the CPU reference run
         b200_detail::rescanOncePerSolver() = (std::getenv("ISL_RESCAN_PER_SOLVER") != NULL);
+        b200_detail::rescanEveryCall() = (std::getenv("ISL_RESCAN_EVERY_CALL") != NULL);
     }
 };
 static InstallHook installHook;

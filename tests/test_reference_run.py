@@ -285,3 +285,8 @@ def test_rescan_once_per_solver_policy_gives_the_same_newton_history(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     expected = open(os.path.join(ROOT, "tests", "golden", "refrun_apps", "compressible_quad010.out")).read()
     assert RA.same_output(p.stdout, expected)
+    # the reference's own semantics (every assembly call re-reads the objects) gives the same history as well; the
+    # default is in between: full scan per solver + sampled comparison at the other calls
+    p = subprocess.run([os.path.join(APPS_B200, exe + "_mock")] + args, cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, ISL_RESCAN_EVERY_CALL="1"))
+    assert p.returncode == 0 and RA.same_output(p.stdout, expected), p.stderr[-2000:]
