@@ -169,6 +169,14 @@ int isl_rhs_norm(isl_handle h, double* norm);
  * benchmarked path.                                                                                            */
 int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations, double* error);
 
+/* base::dof::setDoFsFromSolver (add = 0) / addToDoFsFromSolver (add != 0) (base/dof/Distribute.hpp:35-56,139-215) on the
+ * device: after a solve the rhs holds the solution; ACTIVE components of the field take / add their entry, CONSTRAINED
+ * ones are set to their constraint value (prescribed + weighted masters).  With isl_solve_cg this closes a Newton
+ * iteration without the matrix or the field leaving the GPU (solid/CompressibleDriver.hpp:179-210).            */
+int isl_distribute(isl_handle h, int field, int add);
+/* current values of a field [n_obj * dof_size] -> host or device buffer */
+int isl_field_get_values(isl_handle h, int field, double* values);
+
 /* ---- multi-GPU: one engine per process and GPU, NCCL inside the engine (the reference's only parallel
  * construct is the OpenMP loop of base/auxi/parallel.hpp:25-60) ----------------------------------------------- */
 /* rank 0 makes the 128-byte NCCL id, the caller hands it to the other processes (file, socket, MPI, torch ...) */

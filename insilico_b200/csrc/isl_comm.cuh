@@ -14,9 +14,10 @@
 //   owner; the owner finds the position of every key in its own CSR (k_comm_locate) and keeps the position list.
 // Step (isl_exchange): the ghost values go out as ONE contiguous slice of the value array per owner (the local
 // numbering puts the ghost rows of one owner next to each other), the rhs rows likewise; the owner adds what it
-// receives with k_unpack_add.  All of it runs on a second stream that waits for the event recorded after the
-// INTERFACE patches of the Q1 row kernel (launched first), so the transfer and the additions run while the interior
-// patches are still being assembled (launch_q1).
+// receives with k_unpack_add.  The patches of the Q1 row kernel that own INTERFACE rows are launched on a second,
+// high-priority stream and the exchange is queued right behind them on that stream, while the interior patches run
+// on the engine stream at the same time (the two sets write disjoint rows); comm_join() brings the streams together
+// (launch_q1 in isl_engine.cu).  Other kernels (generic elements, general Q1 elements) exchange after their launch.
 // =============================================================================
 #pragma once
 
@@ -71,7 +72,7 @@ struct CommState {
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_iface = nullptr;
-    bool plan = false, iface_event_valid = false;
+    bool plan = false, iface_event_valid = false, join_pending = false;
     std::vector<CommSend> sends;
     std::vector<std::unique_ptr<CommRecv>> recvs;
     DevBuf<uint8_t> iface_row;   // [n_local] 1: the row is sent to or received from another rank

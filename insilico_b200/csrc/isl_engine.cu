@@ -679,6 +679,34 @@ __global__ void k_sumsq(const double* x, int64_t n, double* out) {
 __global__ void k_pack(const double* src, const int64_t* idx, int64_t n, double* out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = src[idx[i]];
 }
+// base/dof/Distribute.hpp:163-210 on the device: ACTIVE components take (SET) or add (ADD) the solver's value
+__global__ void k_distribute_active(const int32_t* eqn, const double* x, double* values, int64_t n, int add) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t q = eqn[k];
+        if (q >= 0) values[k] = add ? values[k] + x[q] : x[q];
+    }
+}
+__global__ void k_eqn2dof(const int32_t* eqn, int64_t n, int32_t* map) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        if (eqn[k] >= 0) map[eqn[k]] = (int32_t)k;
+}
+// ... then CONSTRAINED components are set to their constraint value: prescribed + sum_j weight_j * (value of master j)
+__global__ void k_distribute_constrained(const uint8_t* status, const double* presc, const int32_t* cptr, const int32_t* cm,
+                                         const double* cw, const int32_t* eqn2dof, int32_t eqn_lo, int32_t eqn_hi, double* values,
+                                         int64_t n, int* err) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        if (status[k] != ISL_CONSTRAINED) continue;
+        double v = presc[k];
+        if (cptr)
+            for (int32_t j = cptr[k]; j < cptr[k + 1]; j++) {
+                const int32_t q = cm[j];
+                const int32_t d = (q >= eqn_lo && q < eqn_hi) ? eqn2dof[q - eqn_lo] : -1;
+                if (d < 0) { *err = 1; continue; }   // master in another field: not supported on the device
+                v = fma(cw[j], values[d], v);
+            }
+        values[k] = v;
+    }
+}
 __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const double* in) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(dst + idx[i], in[i]);
@@ -796,6 +824,7 @@ namespace {
     } while (0)
 
 void materialize_zero(isl_engine* h);
+void comm_join(isl_engine* h);
 void flush_pending(isl_engine* h, int fuse_body, double f0);
 inline void flush_pending(isl_engine* h) { flush_pending(h, 0, 0.); }
 
@@ -1437,27 +1466,32 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
         const size_t smem_r = (size_t)7 * q.inst_cap * 8 + std::max((size_t)q.node_cap * 24, (size_t)(nt / 32) * RG_STAGE * 8);
         const int per_sm = (int)std::min<size_t>(nt == 256 ? 2 : 4, (size_t)(227 * 1024) / (smem_r + 1024));
         q.resident = h->n_sm * std::max(1, per_sm);
-        auto launch_range = [&](int base, int count) {
+        auto launch_range = [&](int base, int count, cudaStream_t st) {
             if (count <= 0) return;
             q.patch_base = base;
             if (nt == 256) {
                 ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-                ISL_LAUNCH(h, (k_q1hex_rows_affine<256, 2>), count, 256, smem_r, q);
+                k_q1hex_rows_affine<256, 2><<<count, 256, smem_r, st>>>(q);
             } else {
                 ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_affine<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-                ISL_LAUNCH(h, (k_q1hex_rows_affine<128, 4>), count, 128, smem_r, q);
+                k_q1hex_rows_affine<128, 4><<<count, 128, smem_r, st>>>(q);
             }
+            h->launches++;
+            ISL_CUDA(cudaGetLastError());
         };
-        // multi-GPU: the patches that own interface rows first; the exchange starts when they are done and runs on the
-        // communication stream while the interior patches are assembled (isl_comm.cuh)
-        if (h->comm && h->comm->plan && comm_patch_order(h, ps) && ps->n_iface > 0 && ps->n_iface < ps->n_patches) {
+        // multi-GPU: the patches that own interface rows run on the (high-priority) communication stream, the exchange
+        // is queued right behind them there, and the interior patches run on the engine stream at the same time; the
+        // two sets write disjoint rows (isl_comm.cuh).  comm_join() brings the streams together again.
+        if (h->comm && h->comm->plan && matrix && comm_patch_order(h, ps) && ps->n_iface > 0 && ps->n_iface < ps->n_patches) {
+            CommState& c = *h->comm;
             q.perm = ps->perm.p;
-            launch_range(0, ps->n_iface);
-            ISL_CUDA(cudaEventRecord(h->comm->ev_iface, h->stream));
-            h->comm->iface_event_valid = true;
-            launch_range(ps->n_iface, ps->n_patches - ps->n_iface);
+            ISL_CUDA(cudaEventRecord(c.ev_ready, h->stream));
+            ISL_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
+            launch_range(0, ps->n_iface, c.stream);
+            c.iface_event_valid = true; c.join_pending = true;
+            launch_range(ps->n_iface, ps->n_patches - ps->n_iface, h->stream);
         } else {
-            launch_range(0, ps->n_patches);
+            launch_range(0, ps->n_patches, h->stream);
         }
         return;
     }
@@ -1573,7 +1607,16 @@ void materialize_zero(isl_engine* h) {
 
 // launch of the Q1 patch matrix kernel is deferred by one call so that an immediately following body force on the same
 // field is fused into the same pass over the elements (the reference application order: stiffness, then body force)
+// work queued on the communication stream (interface patches, exchange) becomes visible to the engine stream
+void comm_join(isl_engine* h) {
+    if (!h->comm || !h->comm->join_pending) return;
+    ISL_CUDA(cudaEventRecord(h->comm->ev_done, h->comm->stream));
+    ISL_CUDA(cudaStreamWaitEvent(h->stream, h->comm->ev_done, 0));
+    h->comm->join_pending = false;
+}
+
 void flush_pending(isl_engine* h, int fuse_body, double f0) {
+    comm_join(h);
     if (!h->pending_q1.active) return;
     h->pending_q1.active = false;
     const int t = h->pending_q1.field;
@@ -2116,6 +2159,44 @@ int isl_solve_cg(isl_handle h, double tol, int64_t max_iter, int64_t* iterations
     });
 }
 
+/* base::dof::setDoFsFromSolver / addToDoFsFromSolver (base/dof/Distribute.hpp:35-56,139-215) on the device */
+int isl_distribute(isl_handle h, int field, int add) {
+    return guarded([&] {
+        ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
+        ISL_REQUIRE(h->n_eqn >= 0 && h->rhs.p, "no system");
+        ISL_CUDA(cudaSetDevice(h->device));
+        flush_pending(h);
+        FieldDev& f = h->fields[field];
+        const int64_t n = f.n_obj * f.ds;
+        if (n == 0) return;
+        ISL_LAUNCH(h, k_distribute_active, h->grid_for(n, 256), 256, 0, f.eqn.p, h->rhs.p, f.values.p, n, add ? 1 : 0);
+        DevBuf<int32_t> map; DevBuf<int> derr;
+        derr.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), h->stream));
+        if (f.has_masters) {
+            map.alloc((size_t)std::max<int64_t>(h->n_eqn, 1));
+            ISL_CUDA(cudaMemsetAsync(map.p, 0xff, map.n * sizeof(int32_t), h->stream));
+            ISL_LAUNCH(h, k_eqn2dof, h->grid_for(n, 256), 256, 0, f.eqn.p, n, map.p);
+        }
+        ISL_LAUNCH(h, k_distribute_constrained, h->grid_for(n, 256), 256, 0, f.status.p, f.presc.p, f.has_masters ? f.cptr.p : nullptr,
+                   f.cmaster.p, f.cweight.p, map.p, 0, (int32_t)h->n_eqn, f.values.p, n, derr.p);
+        int err = 0;
+        ISL_CUDA(cudaMemcpyAsync(&err, derr.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        ISL_REQUIRE(!err, "a master DoF of a linear constraint belongs to another field (not supported by isl_distribute)");
+    });
+}
+int isl_field_get_values(isl_handle h, int field, double* values) {
+    return guarded([&] {
+        ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
+        ISL_REQUIRE(values, "null output");
+        flush_pending(h);
+        FieldDev& f = h->fields[field];
+        ISL_CUDA(cudaMemcpyAsync(values, f.values.p, (size_t)f.n_obj * f.ds * sizeof(double), cudaMemcpyDefault, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
 int isl_measure_fp64_peak(isl_handle h, double* tflops) {
     return guarded([&] {
         ISL_REQUIRE(tflops, "null output");
@@ -2160,7 +2241,9 @@ int isl_comm_init(isl_handle h, const void* id128, int rank, int world) {
         nccl_dyn::ncclUniqueId id;
         std::memcpy(&id, id128, sizeof(id));
         ISL_NCCL(nccl_dyn::api().CommInitRank(&c->comm, world, id, rank));
-        ISL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        ISL_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        ISL_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));   // its blocks are dispatched first
         ISL_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
         ISL_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
         ISL_CUDA(cudaEventCreateWithFlags(&c->ev_iface, cudaEventDisableTiming));
@@ -2271,7 +2354,7 @@ int isl_exchange(isl_handle h) {
         CommState& c = *h->comm;
         auto& N = nccl_dyn::api();
         if (c.iface_event_valid) {
-            ISL_CUDA(cudaStreamWaitEvent(c.stream, c.ev_iface, 0));
+            // the interface patches were launched on the communication stream itself: stream order is enough
         } else {
             ISL_CUDA(cudaEventRecord(c.ev_ready, h->stream));
             ISL_CUDA(cudaStreamWaitEvent(c.stream, c.ev_ready, 0));
@@ -2296,8 +2379,8 @@ int isl_exchange(isl_handle h) {
             h->launches++;
             ISL_CUDA(cudaGetLastError());
         }
-        ISL_CUDA(cudaEventRecord(c.ev_done, c.stream));
-        ISL_CUDA(cudaStreamWaitEvent(h->stream, c.ev_done, 0));
+        c.join_pending = true;
+        comm_join(h);
         h->val_is_zero = false;
     });
 }

@@ -39,7 +39,7 @@ EXPORTED = [
     "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
-    "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange",
+    "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange", "isl_distribute", "isl_field_get_values",
 ]
 
 
@@ -335,6 +335,15 @@ class Engine:
         it, err = C.c_int64(0), C.c_double(0.0)
         _chk(lib().isl_solve_cg(self.h, C.c_double(tol), _i64(max_iter), C.byref(it), C.byref(err)))
         return it.value, err.value
+
+    def distribute(self, fid, add=False):
+        """base::dof::setDoFsFromSolver / addToDoFsFromSolver on the device (the rhs holds the solution after cg_solve)"""
+        _chk(lib().isl_distribute(self.h, int(fid), int(bool(add))))
+
+    def get_field_values(self, fid, n_obj, ds):
+        out = np.zeros((n_obj, ds))
+        _chk(lib().isl_field_get_values(self.h, int(fid), _ptr(out)))
+        return out
 
     def device_csr(self):
         p = [C.c_void_p() for _ in range(4)]
