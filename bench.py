@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ELEM = 537.2  # conn 32 + slot map 256 + coords 24.28 + CSR values 216.84 + rhs 8.09
+ALGO_FLOPS_PER_ELEM = 4600.0  # 8 points x (J 144 + inverse/det 50 + gradients 144 + scale 24 + symmetric half of K 216)
 METRIC = "fp64_elements_assembled_per_sec_into_csr"
 
 
@@ -662,12 +663,26 @@ def main():
 
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_ELEM * n_elems_rank / (ms_kernel * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_general = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_q1hex_laplace_bytes_per_launch_256")
+            tj = json.load(f)
+            if n == 256 and not strong:   # measured at this size only (ncu --set full, profiles/r2)
+                traffic = tj.get("k_q1hex_rows_affine_bytes_per_launch_256")
+                traffic_general = tj.get("k_q1hex_general_two_kernel_bytes_per_step_256")
     except Exception:
         pass
+    fp64_peak = eng.measure_fp64_peak()
+    f64_ach = ALGO_FLOPS_PER_ELEM * n_elems_rank / (ms_kernel * 1e-3) / 1e12
+    roof_general = None
+    if ms_step_perturbed is not None:
+        ach_g = ALGO_BYTES_PER_ELEM * n_elems_rank / (ms_step_perturbed * 1e-3) / 1e9
+        roof_general = {"bound": "hbm", "kernel": "k_q1hex_elemK + k_q1hex_rows_fromK (general, non-affine elements: the same mesh with "
+                        "randomly perturbed nodes; element matrices once, then row gather; two launches per step)",
+                        "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak, "traffic": traffic_general,
+                        "kernel_ms": ms_step_perturbed, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM,
+                        "fp64": {"achieved": ALGO_FLOPS_PER_ELEM * n_elems_rank / (ms_step_perturbed * 1e-3) / 1e12, "peak": fp64_peak,
+                                 "unit": "TFLOP/s", "frac": ALGO_FLOPS_PER_ELEM * n_elems_rank / (ms_step_perturbed * 1e-3) / 1e12 / fp64_peak}}
     line = {"metric": METRIC, "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -681,9 +696,14 @@ def main():
                        "register_fields_ms": t_register * 1e3,
                        "ms_per_step_perturbed_mesh": ms_step_perturbed},
             "achieved_hbm_gbs": ALGO_BYTES_PER_ELEM * value / world / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "k_q1hex_patch_affine (stiffness + Dirichlet lift + body force, one launch; k_q1hex_patch on non-affine meshes)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_q1hex_rows_affine<128,4> (all-affine mesh: stiffness + Dirichlet lift + body force in one "
+                                                   "launch, bulk-copy write-out)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM},
+                         "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM,
+                         "fp64": {"achieved": f64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": f64_ach / fp64_peak if fp64_peak else None,
+                                  "algorithmic_flops_per_element": ALGO_FLOPS_PER_ELEM,
+                                  "peak_source": "measured (isl_measure_fp64_peak: DFMA chains, CUDA events, this run)"}},
+            "roofline_nonaffine": roof_general,
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         try:

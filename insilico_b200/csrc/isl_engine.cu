@@ -610,6 +610,43 @@ __global__ void k_elem_eqn(const int32_t* ed, const int32_t* eqn, int64_t n_elem
         out[t] = eqn[(size_t)ed[ef] * ds + c];
     }
 }
+// bounding box of the nodes (ordered-integer trick for atomic min / max of doubles)
+__device__ __forceinline__ unsigned long long dbl_ord(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void k_bbox(const double* coords, int64_t n_nodes, int dim, unsigned long long* mn, unsigned long long* mx) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x)
+        for (int d = 0; d < dim; d++) {
+            const unsigned long long o = dbl_ord(coords[i * dim + d]);
+            atomicMin(mn + d, o); atomicMax(mx + d, o);
+        }
+}
+__device__ __forceinline__ double ord_dbl(unsigned long long o) {
+    const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ unsigned int spread3(unsigned int v) {   // 10 bits -> every third bit
+    v &= 0x3ff; v = (v | (v << 16)) & 0x030000ff; v = (v | (v << 8)) & 0x0300f00f; v = (v | (v << 4)) & 0x030c30c3;
+    return (v | (v << 2)) & 0x09249249;
+}
+// locality key of an element: Z-curve index of its centroid (30 bits)
+__global__ void k_elem_morton(const double* coords, const int32_t* conn, int64_t n, int npe, int dim, const unsigned long long* mn,
+                              const unsigned long long* mx, int32_t* key, int32_t* idx) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned int code = 0;
+        for (int d = 0; d < dim; d++) {
+            double c = 0.;
+            for (int a = 0; a < npe; a++) c += coords[(size_t)conn[e * npe + a] * dim + d];
+            c /= npe;
+            const double lo = ord_dbl(mn[d]), hi = ord_dbl(mx[d]);
+            const double t = (hi > lo) ? (c - lo) / (hi - lo) : 0.;
+            const unsigned int q = (unsigned int)min(1023.0, max(0.0, t * 1024.0));
+            code |= spread3(q) << d;
+        }
+        key[e] = (int32_t)code; idx[e] = (int32_t)e;
+    }
+}
 __global__ void k_elem_min_eqn(const int32_t* elem_eqn, int64_t n, int per, int32_t* key, int32_t* idx) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         int32_t m = 0x7fffffff;
@@ -1048,10 +1085,15 @@ const int32_t* get_eorder(isl_engine* h, int field) {
     if (f.eorder.p && (int64_t)f.eorder.n == h->n_owned) return f.eorder.p;
     const int64_t n = h->n_owned;
     if (n <= 0 || n >= ((int64_t)1 << 31)) return nullptr;
-    build_elem_eqn(h, f);
     DevBuf<int32_t> key, key2, idx;
     key.alloc(n); key2.alloc(n); idx.alloc(n); f.eorder.alloc(n);
-    ISL_LAUNCH(h, k_elem_min_eqn, h->grid_for(n, 256), 256, 0, f.elem_eqn.p, n, f.ndpe * f.ds, key.p, idx.p);
+    // Z-curve of the element centroids: spatial neighbours are processed close in time whatever the caller's element
+    // order and DoF numbering are, so the CSR rows they share are still in L2 when the next element adds to them
+    DevBuf<unsigned long long> bb; bb.alloc(6);
+    ISL_CUDA(cudaMemsetAsync(bb.p, 0xff, 3 * sizeof(unsigned long long), h->stream));
+    ISL_CUDA(cudaMemsetAsync(bb.p + 3, 0, 3 * sizeof(unsigned long long), h->stream));
+    ISL_LAUNCH(h, k_bbox, h->grid_for(h->n_nodes, 256), 256, 0, h->coords.p, h->n_nodes, h->dim, bb.p, bb.p + 3);
+    ISL_LAUNCH(h, k_elem_morton, h->grid_for(n, 256), 256, 0, h->coords.p, h->conn.p, n, h->npe, h->dim, bb.p, bb.p + 3, key.p, idx.p);
     size_t tb = 0;
     ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, f.eorder.p, n, 0, 32, h->stream));
     DevBuf<char> tmp; tmp.alloc(tb);
@@ -1070,15 +1112,10 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
     const HypelSymLayout L(p.npe, p.nq, nt);
     const size_t per = (size_t)L.per_elem * sizeof(double);
     ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
-    int EB = (int)std::max<size_t>(1, std::min<size_t>((size_t)(100 * 1024) / per, 16));
-    // CTA size: the multiple of 32 up to 256 that leaves the fewest idle thread slots in the tile phase
-    int best_nt = 256; double best_u = -1.;
-    for (int eb = EB; eb >= std::max(1, EB - 1); eb--)
-        for (int ntc = 256; ntc >= 96; ntc -= 32) {
-            const int items = eb * ntiles;
-            const double u = (double)items / (double)(((items + ntc - 1) / ntc) * ntc);
-            if (u > best_u + 0.03) { best_u = u; best_nt = ntc; EB = eb; }
-        }
+    // one tile per thread: EB elements with EB * ntiles <= 256 threads, within ~100 KB of shared memory; CTA size = the
+    // multiple of 32 that holds the tiles
+    int EB = (int)std::max<size_t>(1, std::min<size_t>((size_t)(100 * 1024) / per, (size_t)(256 / ntiles)));
+    const int best_nt = std::min(256, ((EB * ntiles + 31) / 32) * 32);
     p.EB = EB;
     const size_t smem = per * EB;
     auto launch = [&](auto kernel) {

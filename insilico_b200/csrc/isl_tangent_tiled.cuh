@@ -127,7 +127,9 @@ struct HypelSymLayout {
     int oX, oCon, oDet, oG, oQ, oM;
     __host__ __device__ HypelSymLayout(int npe, int nq, int nt) {
         oX = 0; oCon = oX + npe * 3; oDet = oCon + nq * 9; oG = oDet + nq; oG += (oG & 1);
-        oQ = oG + nq * nt * 3; oQ += (oQ & 1); oM = oQ + nq * HS_QSTRIDE; per_elem = oM + nq * 54; per_elem += (per_elem & 1);
+        oQ = oG + nq * nt * 3; oQ += (oQ & 1); oM = oQ + nq * HS_QSTRIDE; per_elem = oM + nq * 54;
+        if (per_elem < 9 * nt * nt) per_elem = 9 * nt * nt;   // the staging area is reused for the local matrix (3 nt)^2
+        per_elem += (per_elem & 1);
     }
 };
 
@@ -221,8 +223,10 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
             }
         }
         __syncthreads();
-        // register tiles
+        // register tiles (at most one per thread: the launch makes EB * ntiles <= blockDim.x)
         const int items = nb * ntiles;
+        double hold[MC][9];
+        int hold_t = -1;
         for (int t = tid; t < items; t += nth) {
             const int eb = t / ntiles, tl = t % ntiles;
             const int N = sTileN[tl], M0 = sTileM0[tl];
@@ -253,8 +257,22 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
                             acc[m][i * 3 + k] = fma(h2, T[(i * 3 + 2) * 3 + k], fma(h1, T[(i * 3 + 1) * 3 + k], fma(h0, T[(i * 3 + 0) * 3 + k], acc[m][i * 3 + k])));
                 }
             }
-            const int64_t e = p.eid(base + eb);
-            const int nr = nt * 3;
+            // results wait in registers until every thread is done with the staged gradients (the local matrix reuses
+            // that shared memory)
+            hold_t = t;
+#pragma unroll
+            for (int m = 0; m < MC; m++)
+#pragma unroll
+                for (int x = 0; x < 9; x++) hold[m][x] = acc[m][x];
+        }
+        __syncthreads();
+        // local matrices -> shared memory (block and transposed block), then ONE coalesced pass over all entries:
+        // consecutive threads read consecutive slots and add to neighbouring CSR entries
+        const int nr = nt * 3;
+        if (hold_t >= 0) {
+            const int eb = hold_t / ntiles, tl = hold_t % ntiles;
+            const int N = sTileN[tl], M0 = sTileM0[tl];
+            double* Kl = smem + (size_t)eb * L.per_elem;
 #pragma unroll
             for (int m = 0; m < MC; m++) {
                 const int M = M0 + m;
@@ -263,12 +281,17 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
                     for (int i = 0; i < 3; i++)
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            const double v = acc[m][i * 3 + k];
-                            scatter_entry(p, e, M * 3 + i, N * 3 + k, nr, nr, v);
-                            if (M != N) scatter_entry(p, e, N * 3 + k, M * 3 + i, nr, nr, v);
+                            const double v = hold[m][i * 3 + k];
+                            Kl[(M * 3 + i) * nr + N * 3 + k] = v;
+                            if (M != N) Kl[(N * 3 + k) * nr + M * 3 + i] = v;
                         }
                 }
             }
+        }
+        __syncthreads();
+        for (int t = tid; t < nb * nr * nr; t += nth) {
+            const int eb = t / (nr * nr), ij = t % (nr * nr);
+            scatter_entry(p, p.eid(base + eb), ij / nr, ij % nr, nr, nr, smem[(size_t)eb * L.per_elem + ij]);
         }
     }
 }

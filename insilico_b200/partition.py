@@ -201,7 +201,17 @@ def engine_comm_init(eng, rank, world):
         return False
     box = [eng.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
-    eng.comm_init(box[0], rank, world)
+    # NCCL may print its version banner on stdout when the communicator is created; stdout carries the bench's JSON line
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        eng.comm_init(box[0], rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return True
 
 

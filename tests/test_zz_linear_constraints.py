@@ -249,4 +249,5 @@ def test_device_resident_newton_loop(name, n):
         vals = new
     scale = np.abs(vals).max()
     assert np.abs(u_dev - vals).max() <= 1e-8 * scale, (np.abs(u_dev - vals).max(), scale, norms, hn)
-    assert norms[-1] < 1e-6 * norms[0] or norms[-1] < 1e-12
+    # the residual norms the application reads per iteration (solver.norm(), Eigen3.hpp:133-138) follow the host loop
+    assert np.allclose(norms, hn, rtol=1e-6, atol=1e-12 * max(hn)), (norms, hn)
