@@ -652,6 +652,30 @@ def main():
                "d2h_bytes_per_step": int(h_val.nbytes + h_rhs.nbytes), "ms_per_step": dt * 1e3,
                "what": "isl_mesh_update_coords + isl_field_update (pinned H2D), isl_system_create, isl_assemble_matrix, "
                        "isl_assemble_bodyforce, isl_finish, isl_get_csr values+rhs (pinned D2H); pattern cached"}
+    # ---- one device-resident Newton-type iteration (solid/CompressibleDriver.hpp:179-210 order of calls): assembly, Jacobi
+    # preconditioned CG on the device (isl_solve_cg = Eigen3::cgSolve), update of the field on the device (isl_distribute =
+    # dof::addToDoFsFromSolver); the matrix never leaves the GPU, only the updated field values cross PCIe
+    e2e_newton = None
+    if not args.no_e2e and world == 1:
+        h_u = torch.empty(wl["n_obj"], dtype=torch.float64).pin_memory().numpy()
+        step(); barrier()
+        t0 = time.perf_counter()
+        step()
+        eng.finish_assembly()
+        t1 = time.perf_counter()
+        cg_it, cg_err = eng.cg_solve(tol=1e-8, max_iter=400)
+        eng.synchronize()
+        t2 = time.perf_counter()
+        eng.distribute(0, add=True)
+        _chk_vals = E.lib().isl_field_get_values(eng.h, 0, h_u.ctypes.data_as(__import__("ctypes").c_void_p))
+        t3 = time.perf_counter()
+        eng.update_field(0, values=wl["values"])   # back to the benchmark state
+        e2e_newton = {"value": n_elems_total / (t3 - t0), "unit": "elements/s", "ms_per_step": (t3 - t0) * 1e3,
+                      "assemble_ms": (t1 - t0) * 1e3, "cg_ms": (t2 - t1) * 1e3, "cg_iterations": int(cg_it), "cg_relative_residual": float(cg_err),
+                      "cg_tolerance": 1e-8, "cg_max_iter": 400, "update_and_copy_ms": (t3 - t2) * 1e3,
+                      "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(h_u.nbytes),
+                      "what": "isl_system_create + isl_assemble_matrix + isl_assemble_bodyforce + isl_finish, isl_solve_cg (capped at 400 "
+                              "iterations), isl_distribute(add), isl_field_get_values -> pinned host: the CSR stays on the device"}
     if rank == 0:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -702,9 +726,16 @@ def main():
                          "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALGO_BYTES_PER_ELEM,
                          "fp64": {"achieved": f64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": f64_ach / fp64_peak if fp64_peak else None,
                                   "algorithmic_flops_per_element": ALGO_FLOPS_PER_ELEM,
+                                  "note": "algorithmic flops of the general element (SURVEY 8d) over the kernel time; the all-affine kernel "
+                                          "executes ~215 FP64 operations per matrix row instead (stencil sums), so this can exceed 1; "
+                                          "roofline_nonaffine is the like-for-like figure",
                                   "peak_source": "measured (isl_measure_fp64_peak: DFMA chains, CUDA events, this run)"}},
             "roofline_nonaffine": roof_general,
             "gpu_launches": int(launches), "clocks": sampler.summary(), "e2e": e2e}
+    if e2e_newton is not None:
+        line["e2e_newton"] = e2e_newton
+    if numa_node is not None:
+        line["config"]["numa_node"] = numa_node
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         try:
             line["cpu_baseline"], _ = reference_baseline(args.cpu_sample, 2, 1, cores)

@@ -882,20 +882,23 @@ void sampledBodyForce(const QUADRATURE& quadrature, base::solver::B200& solver, 
     const std::size_t n = static_cast<std::size_t>(std::distance(fieldBinder.elementsBegin(), fieldBinder.elementsEnd()));
     const std::size_t nq = static_cast<std::size_t>(std::distance(quadrature.begin(), quadrature.end()));
     std::vector<double> values(n * nq * ds);
-    bool constant = true;
-    std::size_t e = 0;
-    typename FIELDBINDER::FieldIterator end = fieldBinder.elementsEnd();
-    for (typename FIELDBINDER::FieldIterator it = fieldBinder.elementsBegin(); it != end; ++it, ++e) {
-        const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*it).geomElementPtr();
-        std::size_t q = 0;
-        for (typename QUADRATURE::Iter qIter = quadrature.begin(); qIter != quadrature.end(); ++qIter, ++q) {
-            const typename EVAL::result_type v = eval(gep, qIter->second);
-            for (unsigned d = 0; d < ds; d++) {
-                values[(e * nq + q) * ds + d] = v[d];
-                constant = constant && (v[d] == values[d]);
-            }
+    // the caller's function is evaluated at every quadrature point of every element by all host threads (it is taken by
+    // const reference and called concurrently, like the kernel objects in the reference's own OpenMP element loop,
+    // base/auxi/parallel.hpp:37-57)
+    const typename FIELDBINDER::FieldIterator it0 = fieldBinder.elementsBegin();
+    const long numE = static_cast<long>(n);
+    std::vector<typename QUADRATURE::Iter> qpts;
+    for (typename QUADRATURE::Iter qIter = quadrature.begin(); qIter != quadrature.end(); ++qIter) qpts.push_back(qIter);
+#pragma omp parallel for schedule(static)
+    for (long e = 0; e < numE; e++) {
+        const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*(it0 + e)).geomElementPtr();
+        for (std::size_t q = 0; q < nq; q++) {
+            const typename EVAL::result_type v = eval(gep, qpts[q]->second);
+            for (unsigned d = 0; d < ds; d++) values[(e * nq + q) * ds + d] = v[d];
         }
     }
+    bool constant = true;
+    for (std::size_t k = ds; k < values.size() && constant; k++) constant = (values[k] == values[k % ds]);
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
     if (constant) {
         double f[3] = {0., 0., 0.};

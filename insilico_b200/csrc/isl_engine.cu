@@ -817,6 +817,7 @@ struct isl_engine {
     int q1_rows = 1;            // row kernels (isl_rowgather.cuh: all-affine meshes; isl_rows_fromk.cuh: general elements);
                                 // ISL_Q1_ROWS=0 selects the round-1 shared-memory patch kernels
     int rows_threads = 128;     // CTA size of the affine row kernel (ISL_ROWS_THREADS)
+    int fromk_chunks = 16;      // software-pipeline depth of the two-kernel general path (ISL_FROMK_CHUNKS)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1418,6 +1419,24 @@ FromKSet* get_fromk(isl_engine* h, int field) {
         DevBuf<char> tmp; tmp.alloc(tb);
         ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, fk->eorder.p, n, 0, 32, h->stream));
         h->launches += 4;
+        {   // chunks of the software pipeline (launch_q1): equal row ranges, element ranges by the sorted keys
+            const int NC = (int)std::max<int64_t>(1, std::min<int64_t>(h->fromk_chunks, nr / 65536));
+            std::vector<int64_t> rb(NC + 1);
+            for (int c = 0; c <= NC; c++) rb[c] = (nr * c / NC) & ~(int64_t)127;   // whole CTAs of the row kernel
+            rb[NC] = nr;
+            DevBuf<int64_t> db, de;
+            upload_vec(h, db, rb); de.alloc(NC + 1);
+            ISL_LAUNCH(h, k_fromk_bounds, 1, 64 > NC + 1 ? 64 : ((NC + 1 + 31) / 32) * 32, 0, key2.p, n, db.p, NC + 1, de.p);
+            std::vector<int64_t> eb(NC + 1);
+            ISL_CUDA(cudaMemcpyAsync(eb.data(), de.p, (NC + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            eb[0] = 0;   // (row boundary 0: every key >= 0)
+            fk->row_b = rb; fk->elem_b = eb;   // elements past elem_b[NC] touch no ACTIVE row
+            fk->ev.resize(NC);
+            for (auto& e : fk->ev) ISL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ISL_CUDA(cudaEventCreateWithFlags(&fk->ev_start, cudaEventDisableTiming));
+            ISL_CUDA(cudaStreamCreateWithFlags(&fk->aux, cudaStreamNonBlocking));
+        }
         fk->row_pos.alloc((size_t)nr * 8);
         ISL_CUDA(cudaMemsetAsync(fk->row_pos.p, 0xff, (size_t)nr * 8 * sizeof(int32_t), h->stream));
         DevBuf<int> cnt; cnt.alloc(2);
@@ -1539,11 +1558,28 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
     k.row_pos = fk->row_pos.p; k.meta = reinterpret_cast<const RowMeta*>(fk->meta.p); k.n_rows = fk->n_rows; k.K = fk->K.p;
     q.lift_nodes = fk->lift_nodes.p;
     k.r = q; k.matrix = matrix;
-    ISL_LAUNCH(h, k_q1hex_elemK, (unsigned)((fk->n_elems + 127) / 128), 128, 0, k);
+    // software pipeline over chunks: the element kernel (FP64-bound) of chunk c+1 runs on a second stream while the row
+    // kernel (memory-bound) of chunk c runs on the engine stream; rows of chunk c only read elements of chunks <= c
     constexpr int NT = 128;
     const size_t smem_k = (size_t)(NT / 32) * RG_STAGE * 8;
     ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_fromK<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
-    ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((fk->n_rows + NT - 1) / NT), NT, smem_k, k);
+    const int NC = (int)fk->row_b.size() - 1;
+    ISL_CUDA(cudaEventRecord(fk->ev_start, h->stream));
+    ISL_CUDA(cudaStreamWaitEvent(fk->aux, fk->ev_start, 0));
+    for (int c = 0; c < NC; c++) {
+        k.e_lo = fk->elem_b[c]; k.e_hi = fk->elem_b[c + 1];
+        if (k.e_hi > k.e_lo) {
+            k_q1hex_elemK<<<(unsigned)((k.e_hi - k.e_lo + 127) / 128), 128, 0, fk->aux>>>(k);
+            h->launches++;
+        }
+        ISL_CUDA(cudaEventRecord(fk->ev[c], fk->aux));
+    }
+    for (int c = 0; c < NC; c++) {
+        k.r_lo = fk->row_b[c]; k.r_hi = fk->row_b[c + 1];
+        ISL_CUDA(cudaStreamWaitEvent(h->stream, fk->ev[c], 0));
+        if (k.r_hi > k.r_lo) ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((k.r_hi - k.r_lo + NT - 1) / NT), NT, smem_k, k);
+    }
+    ISL_CUDA(cudaGetLastError());
 }
 
 template <bool MATRIX>
@@ -1705,6 +1741,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_ROWS")) h->q1_rows = atoi(m) ? 1 : 0;
         if (!h->q1_rows) { h->patch_rows = 400; h->patch_stretch = 1.0; }   // geometry of the round-1 patch kernels
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
+        if (const char* m = getenv("ISL_FROMK_CHUNKS")) h->fromk_chunks = std::max(1, std::min(512, atoi(m)));
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;

@@ -29,6 +29,16 @@ struct FromKSet {
     DevBuf<unsigned char> meta; // RowMeta per row (slot[] unused)
     DevBuf<int32_t> lift_nodes;
     DevBuf<double> K;           // [44][n_elems]: 36 symmetric entries (sym_idx), 8 body-force integrals
+    // software pipeline: chunk c = rows [row_b[c], row_b[c+1]) and the elements whose smallest equation lies in that
+    // range, sorted positions [elem_b[c], elem_b[c+1]); rows of chunk c only need elements of chunks <= c
+    std::vector<int64_t> row_b, elem_b;
+    std::vector<cudaEvent_t> ev;
+    cudaStream_t aux = nullptr; cudaEvent_t ev_start = nullptr;
+    ~FromKSet() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (aux) cudaStreamDestroy(aux);
+    }
 };
 
 struct FromKParams {
@@ -37,7 +47,17 @@ struct FromKParams {
     double* K;
     RowsParams r;   // val, rhs, lift tables, flags (patch arrays unused)
     int matrix;     // 0: right-hand side only (body force without a preceding stiffness call)
+    int64_t e_lo, e_hi, r_lo, r_hi;   // this launch: sorted element positions [e_lo, e_hi) / rows [r_lo, r_hi)
 };
+
+// first sorted position whose key is >= bound[c], for every chunk boundary
+__global__ void k_fromk_bounds(const int32_t* sorted_key, int64_t n, const int64_t* bound, int nb, int64_t* out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)sorted_key[mid] < bound[c]) lo = mid + 1; else hi = mid; }
+    out[c] = lo;
+}
 
 // locality key of an element: its smallest equation number (rows of one warp then read neighbouring K columns)
 __global__ void k_fromk_elem_key(const int32_t* elem_eqn, int64_t n, int32_t* key, int32_t* idx) {
@@ -92,8 +112,8 @@ __global__ void k_fromk_row_meta(int pass, int64_t n_rows, const int32_t* row_po
 }
 
 __global__ void __launch_bounds__(128) k_q1hex_elemK(const FromKParams p) {
-    const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (t >= p.n_elems) return;
+    const int64_t t = p.e_lo + (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= p.e_hi) return;
     const int64_t e = __ldg(p.eorder + t);
     const int4 c0 = __ldg(reinterpret_cast<const int4*>(p.conn + e * 8));
     const int4 c1 = __ldg(reinterpret_cast<const int4*>(p.conn + e * 8) + 1);
@@ -122,8 +142,8 @@ __global__ void __launch_bounds__(NT) k_q1hex_rows_fromK(const FromKParams p) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* st = smem + (size_t)warp * RG_STAGE;
-    const int64_t r = (int64_t)blockIdx.x * NT + tid;
-    const bool act = r < p.n_rows;
+    const int64_t r = p.r_lo + (int64_t)blockIdx.x * NT + tid;
+    const bool act = r < p.r_hi;
     RowMeta m;
     double acc[27];
 #pragma unroll

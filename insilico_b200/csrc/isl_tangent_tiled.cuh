@@ -134,7 +134,7 @@ struct HypelSymLayout {
 };
 
 template <int MC>
-__global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, int ntiles) {
+__global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p, int ntiles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ unsigned char sTileN[160], sTileM0[160];
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -223,20 +223,19 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
             }
         }
         __syncthreads();
-        // register tiles (at most one per thread: the launch makes EB * ntiles <= blockDim.x)
+        // register tiles: exactly one per thread (the launch makes EB * ntiles <= blockDim.x)
         const int items = nb * ntiles;
-        double hold[MC][9];
-        int hold_t = -1;
-        for (int t = tid; t < items; t += nth) {
-            const int eb = t / ntiles, tl = t % ntiles;
-            const int N = sTileN[tl], M0 = sTileM0[tl];
-            const double* E = smem + (size_t)eb * L.per_elem;
+        const bool has = tid < items;
+        const int teb = has ? tid / ntiles : 0, tl = has ? tid % ntiles : 0;
+        const int N = sTileN[tl], M0 = sTileM0[tl];
+        double acc[MC][9];
+#pragma unroll
+        for (int m = 0; m < MC; m++)
+#pragma unroll
+            for (int x = 0; x < 9; x++) acc[m][x] = 0.;
+        if (has) {
+            const double* E = smem + (size_t)teb * L.per_elem;
             const double* G = E + L.oG;
-            double acc[MC][9];
-#pragma unroll
-            for (int m = 0; m < MC; m++)
-#pragma unroll
-                for (int x = 0; x < 9; x++) acc[m][x] = 0.;
             for (int q = 0; q < nq; q++) {
                 const double wd = E[L.oDet + q] * p.w[q];
                 const double* gN = G + ((size_t)q * nt + N) * 3;
@@ -257,22 +256,13 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
                             acc[m][i * 3 + k] = fma(h2, T[(i * 3 + 2) * 3 + k], fma(h1, T[(i * 3 + 1) * 3 + k], fma(h0, T[(i * 3 + 0) * 3 + k], acc[m][i * 3 + k])));
                 }
             }
-            // results wait in registers until every thread is done with the staged gradients (the local matrix reuses
-            // that shared memory)
-            hold_t = t;
-#pragma unroll
-            for (int m = 0; m < MC; m++)
-#pragma unroll
-                for (int x = 0; x < 9; x++) hold[m][x] = acc[m][x];
         }
-        __syncthreads();
+        __syncthreads();   // every thread is done with the staged gradients: the local matrix reuses that shared memory
         // local matrices -> shared memory (block and transposed block), then ONE coalesced pass over all entries:
         // consecutive threads read consecutive slots and add to neighbouring CSR entries
-        const int nr = nt * 3;
-        if (hold_t >= 0) {
-            const int eb = hold_t / ntiles, tl = hold_t % ntiles;
-            const int N = sTileN[tl], M0 = sTileM0[tl];
-            double* Kl = smem + (size_t)eb * L.per_elem;
+        const int nr = nt * 3, nn = nr * nr;
+        if (has) {
+            double* Kl = smem + (size_t)teb * L.per_elem;
 #pragma unroll
             for (int m = 0; m < MC; m++) {
                 const int M = M0 + m;
@@ -281,7 +271,7 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
                     for (int i = 0; i < 3; i++)
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            const double v = hold[m][i * 3 + k];
+                            const double v = acc[m][i * 3 + k];
                             Kl[(M * 3 + i) * nr + N * 3 + k] = v;
                             if (M != N) Kl[(N * 3 + k) * nr + M * 3 + i] = v;
                         }
@@ -289,9 +279,23 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_sym(const AsmParams p, in
             }
         }
         __syncthreads();
-        for (int t = tid; t < nb * nr * nr; t += nth) {
-            const int eb = t / (nr * nr), ij = t % (nr * nr);
-            scatter_entry(p, p.eid(base + eb), ij / nr, ij % nr, nr, nr, smem[(size_t)eb * L.per_elem + ij]);
+        for (int eb = 0; eb < nb; eb++) {
+            const int64_t e = p.eid(base + eb);
+            const int32_t* sl = p.slot + (size_t)e * nn;
+            const double* Kl = smem + (size_t)eb * L.per_elem;
+            constexpr int U = 4;   // slot loads in flight per thread
+            for (int t0 = tid; t0 < nn; t0 += U * nth) {
+                int32_t s4[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { const int t = t0 + u * nth; s4[u] = (t < nn) ? __ldg(sl + t) : 0; }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int t = t0 + u * nth;
+                    if (t >= nn) continue;
+                    if (s4[u] >= 0) atomicAdd(p.val + s4[u], Kl[t]);
+                    else scatter_entry(p, e, t / nr, t % nr, nr, nr, Kl[t]);   // constrained row / column: lift or nothing
+                }
+            }
         }
     }
 }

@@ -190,7 +190,7 @@ def test_register_tiled_hyperelastic_tangent_equals_oracle(monkeypatch, name, n)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,n", [("neohooke_p2_tet", 3), ("neohooke_q1_hex", 4), ("stvenant_q1_hex_linear", 4)])
+@pytest.mark.parametrize("name,n", [("stvenant_q1_hex", 4), ("neohooke_q1_hex", 4), ("stvenant_q1_hex_linear", 4)])
 def test_device_resident_newton_loop(name, n):
     """solid/CompressibleDriver.hpp:179-210 without the matrix or the field leaving the GPU: per iteration a fresh solver,
     residual + tangent (incremental), isl_solve_cg, isl_distribute(add) (base/dof/Distribute.hpp:139-215); only the
