@@ -78,6 +78,11 @@ bool assignIfChanged(std::vector<T>& cache, const std::vector<T>& fresh) {
     return true;
 }
 
+//! meshes below this size are scanned by one thread (measured: 10 ms for 262 k hexahedra; waking the OpenMP team costs more)
+#ifndef ISL_B200_PARALLEL_SCAN_MIN
+#define ISL_B200_PARALLEL_SCAN_MIN 400000
+#endif
+
 //! store into an array that several scanning threads may write with the SAME value (shared nodes / DoFs)
 template <typename T>
 inline void storeShared(T& dst, T v) { __atomic_store(&dst, &v, __ATOMIC_RELAXED); }
@@ -138,7 +143,7 @@ struct FlattenField<N, FIELDBINDER, false> {
             f.dofSize = ds;
             f.elemDof.assign(s.numElements * ndpe, 0);
             long maxId = 0;
-#pragma omp parallel for schedule(static) reduction(max : maxId)
+#pragma omp parallel for schedule(static) reduction(max : maxId) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
             for (long e = 0; e < numE; e++) {
                 const Element* ep = (*(it + e)).template get<N>();
                 int k = 0;
@@ -159,7 +164,7 @@ struct FlattenField<N, FIELDBINDER, false> {
         std::vector<uint8_t> seen(n, 0);
         struct Slave { int64_t dof; std::vector<std::pair<base::number, std::size_t> > masters; };
         std::vector<Slave> slaves;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
         for (long e = 0; e < numE; e++) {
             const Element* ep = (*(it + e)).template get<N>();
             double pv[DoF::size];
@@ -342,7 +347,7 @@ void synchronise(const FIELDBINDER& fb) {
     std::vector<int32_t> conn(numElements * npe);
     long maxNode = 0;
     const typename FIELDBINDER::FieldIterator it0 = fb.elementsBegin();
-#pragma omp parallel for schedule(static) reduction(max : maxNode)
+#pragma omp parallel for schedule(static) reduction(max : maxNode) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
     for (long e = 0; e < numE; e++) {
         const GeomElement* gep = (*(it0 + e)).geomElementPtr();
         int k = 0;
@@ -355,7 +360,7 @@ void synchronise(const FIELDBINDER& fb) {
     topologyChanged = assignIfChanged(s.conn, conn) || topologyChanged;
     const int64_t nNodes = static_cast<int64_t>(maxNode) + 1;
     std::vector<double> coords(static_cast<std::size_t>(nNodes) * dim, 0.);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
     for (long e = 0; e < numE; e++) {
         const GeomElement* gep = (*(it0 + e)).geomElementPtr();
         double x[3];
@@ -889,7 +894,7 @@ void sampledBodyForce(const QUADRATURE& quadrature, base::solver::B200& solver, 
     const long numE = static_cast<long>(n);
     std::vector<typename QUADRATURE::Iter> qpts;
     for (typename QUADRATURE::Iter qIter = quadrature.begin(); qIter != quadrature.end(); ++qIter) qpts.push_back(qIter);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
     for (long e = 0; e < numE; e++) {
         const GeomElement* gep = FIELDTUPLEBINDER::makeTuple(*(it0 + e)).geomElementPtr();
         for (std::size_t q = 0; q < nq; q++) {

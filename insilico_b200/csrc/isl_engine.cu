@@ -817,7 +817,7 @@ struct isl_engine {
     int q1_rows = 1;            // row kernels (isl_rowgather.cuh: all-affine meshes; isl_rows_fromk.cuh: general elements);
                                 // ISL_Q1_ROWS=0 selects the round-1 shared-memory patch kernels
     int rows_threads = 128;     // CTA size of the affine row kernel (ISL_ROWS_THREADS)
-    int fromk_chunks = 16;      // software-pipeline depth of the two-kernel general path (ISL_FROMK_CHUNKS)
+    int fromk_chunks = 1;       // software-pipeline depth of the two-kernel general path (ISL_FROMK_CHUNKS)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
