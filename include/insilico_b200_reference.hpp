@@ -474,6 +474,11 @@ struct B200KernelTraits<heat::Laplace<TUPLE> > {
         heat::Laplace<TUPLE> operator()(double c) const { return heat::Laplace<TUPLE>(c); }
     };
     static int describe(const heat::Laplace<TUPLE>& k, const TUPLE& t0, const TUPLE& t1, double* p) {
+#ifdef ISL_B200_HAVE_KERNEL_ACCESSORS   // the maintainer added `double conductivity() const`
+        (void)t0; (void)t1;
+        p[0] = k.conductivity();
+        return ISL_K_LAPLACE;
+#endif
         p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         const double p1 = b200_detail::probeScalar(b200_detail::probeTangent(k, t1), Make(), t1);
         VERIFY_MSG(std::abs(p1 - p[0]) <= 1e-13 * std::abs(p[0]),
@@ -509,6 +514,11 @@ struct B200KernelTraits<fluid::VectorLaplace<TUPLE> > {
         fluid::VectorLaplace<TUPLE> operator()(double c) const { return fluid::VectorLaplace<TUPLE>(c); }
     };
     static int describe(const fluid::VectorLaplace<TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+#ifdef ISL_B200_HAVE_KERNEL_ACCESSORS   // `double viscosity() const`
+        (void)t0;
+        p[0] = k.viscosity();
+        return ISL_K_VECTOR_LAPLACE;
+#endif
         p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         return ISL_K_VECTOR_LAPLACE;
     }
@@ -543,6 +553,11 @@ namespace b200_detail {
 //! K = lambda * K(1,0) + mu * K(0,1) for solid::HyperElastic with a two-constant material (fixed displacement state)
 template <typename MATERIAL, typename TUPLE>
 void probeLame(const solid::HyperElastic<MATERIAL, TUPLE>& k, const TUPLE& t0, double* p) {
+#ifdef ISL_B200_HAVE_KERNEL_ACCESSORS   // `const MATERIAL& material() const`, `double lambda() const`, `double mu() const`
+    (void)t0;
+    p[0] = k.material().lambda(); p[1] = k.material().mu();
+    return;
+#endif
     const MATERIAL m10(1., 0.), m01(0., 1.);
     const solid::HyperElastic<MATERIAL, TUPLE> k10(m10), k01(m01);
     const base::MatrixD K = probeTangent(k, t0), A = probeTangent(k10, t0), B = probeTangent(k01, t0);
