@@ -261,6 +261,7 @@ int runSingle(const Job& job) {
     setUpField<Mesh, FEBasis>(mesh, field, job.fields.at(0), boundary);
     const std::size_t numDoFs = base::dof::numberDoFsConsecutively(field.doFsBegin(), field.doFsEnd());
     if (job.dump) dumpField(field, job.out + ".f0");
+    if (job.dump == 2) return 0;   // numbering fixtures of large meshes: no assembly
 
     FieldBinder fieldBinder(mesh, field);
     Quadrature quadrature;
@@ -324,7 +325,7 @@ int runSingle(const Job& job) {
         std::printf("rep %d  elements %zu  dofs %zu  register %.6f s  assemble %.6f s  finish %.6f s\n", rep,
                     static_cast<std::size_t>(std::distance(mesh.elementsBegin(), mesh.elementsEnd())), numDoFs, t1 - t0,
                     t2 - t1, t3 - t2);
-        if (job.dump && rep == 0) dumpSystem(solver, job.out);
+        if (job.dump == 1 && rep == 0) dumpSystem(solver, job.out);   // dump 2: numbering only
     }
     std::printf("best_assemble_seconds %.9f\n", best);
     return 0;
@@ -364,6 +365,7 @@ int runStokes(const Job& job) {
         dumpField(velocity, job.out + ".f0");
         dumpField(pressure, job.out + ".f1");
     }
+    if (job.dump == 2) return 0;
     Binder binder(mesh, velocity, pressure);
     Quadrature quadrature;
     double best = 1e300;
@@ -398,7 +400,7 @@ int runStokes(const Job& job) {
         best = std::min(best, t2 - t1);
         std::printf("rep %d  elements %zu  dofs %zu  assemble %.6f s\n", rep,
                     static_cast<std::size_t>(std::distance(mesh.elementsBegin(), mesh.elementsEnd())), nU + nP, t2 - t1);
-        if (job.dump && rep == 0) dumpSystem(solver, job.out);
+        if (job.dump == 1 && rep == 0) dumpSystem(solver, job.out);   // dump 2: numbering only
     }
     std::printf("best_assemble_seconds %.9f\n", best);
     return 0;

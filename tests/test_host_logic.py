@@ -159,3 +159,30 @@ def test_cpp_facade_example_builds_and_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     out = subprocess.run([exe, "4"], capture_output=True, text=True)
     assert out.returncode != 0 and "no CUDA device available" in out.stderr
+
+
+# ---- numbering at larger sizes against the reference itself (tools/make_ref_numbering.py) -----------------------------
+def _digest(a, dtype):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=dtype).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("key", ["stvenant_q2_hex_n16", "neohooke_p2_tet_n16", "stokes_p2p1_tet_n12", "laplace_q2_hex_n16"])
+def test_numbering_at_size_equals_reference_run(key):
+    """DoF ids per element, status and equation numbers of Q2 hexahedra / P2 tetrahedra / the Taylor-Hood pair on meshes
+    with 16 (12) elements per direction, perturbed, in permuted element order: the product's restatement of base/dof
+    (isl_dof_generate, isl_mesh_boundary, isl_boundary_dofs, isl_number_dofs through flows.build_case) AND the oracle's
+    reproduce what the unmodified reference produced (SHA-256 of the arrays, tests/golden/refrun/numbering_digests.json)"""
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(H.REF), "refrun", "numbering_digests.json")))[key]
+    name, n = key.rsplit("_n", 1)
+    c = flows.build_case(name, int(n), gold["perturb"], gold["permute"])
+    assert len(c.conn) == gold["n_elems"]
+    prob = orc.Problem(c.shape, 1, c.coords, c.conn.astype(np.int64))
+    for f, g in zip(c.fields, gold["fields"]):
+        assert f["n_obj"] == g["n_obj"] and int((f["eqn"] >= 0).sum()) == g["n_active"]
+        assert _digest(f["elem_dof"], np.int32) == g["elem_dof"], "element -> DoF table differs from the reference's"
+        assert _digest(f["status"], np.uint8) == g["status"]
+        assert _digest(np.where(f["eqn"] >= 0, f["eqn"], -1), np.int64) == g["eqn"], "equation numbers differ from the reference's"
+        ed0, nobj0 = prob.dof_generate(f["fe_deg"])
+        assert nobj0 == g["n_obj"] and _digest(ed0, np.int32) == g["elem_dof"]

@@ -111,3 +111,57 @@ def test_engine_full_size_perturbed_mesh_properties_and_sub_box_oracle_parity(n)
     c = _perturbed_workload(n)
     rp, col, val, rhs = c.run_engine()
     SC.check_perturbed_system(n, c.coords, rp, col, val, rhs)
+
+
+# ---- BASELINE configs 3 and 4 at their benchmark sizes: oracle parity on sampled sub-meshes ---------------------------
+def _oracle_system(w):
+    from oracle import oracle as orc
+    prob = orc.Problem(w.shape, w.geom_deg, w.coords, w.conn.astype(np.int64))
+    for i, f in enumerate(w.fields):
+        prob.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"].astype(np.int64), f["eqn"], f["status"], f["presc"], f["values"])
+    s = orc.System(w.n_eqn)
+    for op in w.ops:
+        if op[0] == "matrix":
+            s.stiffness(prob, op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+    return s.finish()
+
+
+@pytest.mark.parametrize("cfg,n,hw", [("C3", 4, 0.3), ("C4", 4, 0.3), ("C5", 4, 0.3)])
+def test_sub_mesh_argument_holds_for_the_oracle(cfg, n, hw):
+    """CPU: the sub-mesh checker accepts the oracle's own full system (and so checks nothing but the argument)"""
+    from insilico_b200 import workloads
+    from tests import subbox_check as SB
+    w = workloads.build(cfg, n)
+    rp, col, val, rhs = _oracle_system(w)
+    err, compared = SB.check_subboxes(w, rp, col, val, n_boxes=2, half_width=hw)
+    assert err <= 1e-14 and compared > 50
+    val2 = val.copy()
+    val2[len(val2) // 2] += 1e-6 * np.abs(val).max()     # the checker can fail: some box must see a perturbed entry
+    with pytest.raises(AssertionError):
+        for seed in range(40):
+            SB.check_subboxes(w, rp, col, val2, n_boxes=2, half_width=hw, seed=seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n,hw", [("C3", 12, 0.13), ("C4", 12, 0.1), ("C5", 12, 0.1), ("C3", 64, 0.025), ("C4", 64, 0.02)])
+def test_engine_config_sizes_sub_mesh_oracle_parity(cfg, n, hw):
+    """bench.py --config C3 / C4 (/ C5) workloads on the engine, at the benchmark size for C3 and C4: entries between DoFs
+    that only the elements of a sampled box touch equal the oracle's assembly of that box"""
+    import psutil
+    from insilico_b200 import engine as E
+    from insilico_b200 import workloads
+    from tests import subbox_check as SB
+    if n >= 64 and psutil.virtual_memory().available < 64e9:
+        pytest.skip("needs about 50 GB of host memory")
+    w = workloads.build(cfg, n)
+    eng = E.Engine(0)
+    try:
+        w.upload(eng)
+        eng.new_solver(w.n_eqn)
+        w.register(eng)
+        w.step(eng)
+        rp, col, val, rhs = eng.get_csr()
+    finally:
+        eng.close()
+    err, compared = SB.check_subboxes(w, rp, col, val, n_boxes=3, half_width=hw)
+    assert compared > 100
