@@ -46,7 +46,9 @@ enum {
     ISL_K_PRESSURE_GRADIENT = 4,   /* fluid::PressureGradient (fluid/PressureGradient.hpp:76-155); no params */
     ISL_K_VELOCITY_DIVERGENCE = 5, /* fluid::VelocityDivergence (fluid/VelocityDivergence.hpp:67-124);
                                       params = {changeSign != 0}                                       */
-    ISL_K_VECTOR_LAPLACE = 6       /* fluid::VectorLaplace (fluid/VectorLaplace.hpp:40-112); {viscosity}   */
+    ISL_K_VECTOR_LAPLACE = 6,      /* fluid::VectorLaplace (fluid/VectorLaplace.hpp:40-112); {viscosity}   */
+    ISL_K_MASS = 7                 /* base::kernel::Mass (base/kernel/Mass.hpp:88-138), matrix only; {factor}: entry =
+                                      factor detJ w phi_M psi_N on every DoF component (time stepping, L2 projections) */
 };
 
 typedef struct isl_engine* isl_handle;

@@ -39,6 +39,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/insilico_b200.h"
 #include "isl_dof.hpp"
@@ -370,6 +372,15 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     for (int k = 1; k < DIM; k++) dot += gM[k] * gN[k];
                     acc += dot * (p.p0 * s.sDet[eq] * p.w[q]);
                 }
+                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+            }
+        } else if (p.kernel_id == ISL_K_MASS) {
+            // base/kernel/Mass.hpp:88-138: (factor detJ w) phi_M psi_N on every DoF component
+            for (int t = tid; t < nb * p.nt * p.nc; t += nth) {
+                const int eb = t / (p.nt * p.nc), mn = t % (p.nt * p.nc), M = mn / p.nc, N = mn % p.nc;
+                double acc = 0.;
+                for (int q = 0; q < p.nq; q++)
+                    acc += (p.p0 * s.sDet[eb * p.nq + q] * p.w[q]) * p.Nt[q * p.nt + M] * p.Nc[q * p.nc + N];
                 for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
@@ -753,6 +764,7 @@ __global__ void k_unpack_add(double* dst, const int64_t* idx, int64_t n, const d
 #include "isl_patch.cuh"
 #include "isl_rowgather.cuh"
 #include "isl_rows_fromk.cuh"
+#include "isl_patch_dev.cuh"
 
 // ---------------------------------------------------------------------------------------------
 struct FieldDev {
@@ -1151,6 +1163,10 @@ void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
 void check_kernel_fields(isl_engine* h, int kid, int t, int c, bool tangent) {
     const FieldDev& ft = h->fields[t]; const FieldDev& fc = h->fields[c];
     switch (kid) {
+        case ISL_K_MASS:
+            ISL_REQUIRE(ft.ds == fc.ds, "Mass kernel: test and trial DoF sizes differ");
+            ISL_REQUIRE(tangent, "base::kernel::Mass: only the matrix is implemented (no residual)");
+            break;
         case ISL_K_LAPLACE:
         case ISL_K_VECTOR_LAPLACE:
             ISL_REQUIRE(ft.ds == fc.ds, "Laplace kernel: test and trial DoF sizes differ");
@@ -1210,6 +1226,189 @@ bool qualifies_q1(const isl_engine* h, int t, int c) {
            !ft.has_masters;  // slaves of master DoFs take the generic kernels
 }
 
+
+// patch tables of the Q1 row kernel built on the device (isl_patch_dev.cuh); false: not eligible (caller falls back)
+bool form_patches_device(isl_engine* h, FieldDev& f, PatchSet* ps) {
+    const int64_t n = h->n_owned, nr = h->n_eqn, nn = h->n_nodes;
+    if (n <= 0 || nr <= 0 || n * 8 >= ((int64_t)1 << 31) || h->dim != 3) return false;
+    build_elem_eqn(h, f);
+    cudaStream_t st = h->stream;
+    // 1. row -> node, mean element extents, bounding box, numbering axis
+    DevBuf<int32_t> row_node; row_node.alloc(nr);
+    ISL_CUDA(cudaMemsetAsync(row_node.p, 0xff, nr * sizeof(int32_t), st));
+    ISL_LAUNCH(h, k_pd_row_node, h->grid_for(nn, 256), 256, 0, f.eqn.p, nn, row_node.p);
+    DevBuf<double> sums; sums.alloc(4);
+    ISL_CUDA(cudaMemsetAsync(sums.p, 0, 4 * sizeof(double), st));
+    const int64_t stride = std::max<int64_t>(1, n / 200000);
+    ISL_LAUNCH(h, k_pd_extent, h->grid_for((n + stride - 1) / stride, 128), 128, 0, h->coords.p, h->conn.p, n, stride, sums.p);
+    DevBuf<unsigned long long> bb; bb.alloc(9);
+    ISL_CUDA(cudaMemsetAsync(bb.p, 0xff, 3 * sizeof(unsigned long long), st));
+    ISL_CUDA(cudaMemsetAsync(bb.p + 3, 0, 6 * sizeof(unsigned long long), st));
+    ISL_LAUNCH(h, k_bbox, h->grid_for(nn, 256), 256, 0, h->coords.p, nn, 3, bb.p, bb.p + 3);
+    double hs[4];
+    unsigned long long hb[9];
+    ISL_CUDA(cudaMemcpyAsync(hs, sums.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    PdGrid g;
+    for (int d = 0; d < 3; d++) g.h[d] = (hs[3] > 0 && hs[d] > 0) ? hs[d] / hs[3] : 1.0;
+    DevBuf<double> dh; dh.alloc(3);
+    ISL_CUDA(cudaMemcpyAsync(dh.p, g.h, 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int64_t vstride = std::max<int64_t>(1, nr / 100000);
+    ISL_LAUNCH(h, k_pd_axis_votes, h->grid_for(nr / vstride + 1, 128), 128, 0, h->coords.p, row_node.p, nr, vstride, dh.p, bb.p + 6);
+    ISL_CUDA(cudaMemcpyAsync(hb, bb.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    auto ord2dbl = [](unsigned long long o) {
+        const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
+        double x; std::memcpy(&x, &b, sizeof(x)); return x;
+    };
+    int ax = 0;
+    if (hb[7] > hb[6 + ax]) ax = 1;
+    if (hb[8] > hb[6 + ax]) ax = 2;
+    // 2. boxes: Bs x Bo x Bo lattice cells with Bs along the numbering axis (patch_stretch > 1) and about patch_rows rows
+    const int R = std::max(16, h->patch_rows);
+    // cubes in coordinates shrunk by patch_stretch along the numbering axis: Bs = stretch * Bo, Bs * Bo^2 ~ R
+    const int Bo = std::max(1, (int)std::floor(std::cbrt((double)R / std::max(1.0, h->patch_stretch)) + 1e-9));
+    const int Bs = std::max(1, R / (Bo * Bo));
+    int64_t nb_total = 1;
+    for (int d = 0; d < 3; d++) {
+        g.lo[d] = ord2dbl(hb[d]);
+        const double ext = ord2dbl(hb[3 + d]) - g.lo[d];
+        const int64_t cells = (int64_t)std::floor(ext / g.h[d] + 0.5) + 1;
+        g.B[d] = (d == ax) ? Bs : Bo;
+        g.NB[d] = (int)std::max<int64_t>(1, (cells + g.B[d] - 1) / g.B[d]);
+        nb_total *= g.NB[d];
+    }
+    if (nb_total >= ((int64_t)1 << 31)) return false;
+    DevBuf<int32_t> key, key2, idx;
+    key.alloc(nr); key2.alloc(nr); idx.alloc(nr); ps->rows.alloc(nr);
+    ISL_LAUNCH(h, k_pd_row_keys, h->grid_for(nr, 256), 256, 0, h->coords.p, row_node.p, nr, g, key.p, idx.p);
+    int bits = 1; while (((int64_t)1 << bits) < nb_total) bits++;
+    size_t tb = 0;
+    DevBuf<char> tmp;
+    ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, ps->rows.p, nr, 0, bits, st));
+    tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, ps->rows.p, nr, 0, bits, st));
+    // run lengths of the sorted box keys = rows per patch
+    DevBuf<int32_t> ukey, ucnt; DevBuf<int> nruns;
+    ukey.alloc(nr); ucnt.alloc(nr); nruns.alloc(1);
+    tb = 0;
+    ISL_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tb, key2.p, ukey.p, ucnt.p, nruns.p, nr, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tb, key2.p, ukey.p, ucnt.p, nruns.p, nr, st));
+    int np = 0;
+    ISL_CUDA(cudaMemcpyAsync(&np, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    if (np <= 0) return false;
+    ps->p_row_off.alloc(np + 1);
+    ISL_CUDA(cudaMemsetAsync(ps->p_row_off.p, 0, sizeof(int32_t), st));
+    tb = 0;
+    ISL_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, ucnt.p, ps->p_row_off.p + 1, np, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, ucnt.p, ps->p_row_off.p + 1, np, st));
+    h->launches += 8;
+    key.release(); key2.release(); idx.release(); ukey.release(); ucnt.release();
+    DevBuf<int32_t> patch_of_row, rank_of_row;
+    patch_of_row.alloc(nr); rank_of_row.alloc(nr);
+    ISL_LAUNCH(h, k_pd_patch_of_row, np, 64, 0, ps->p_row_off.p, np, ps->rows.p, patch_of_row.p, rank_of_row.p);
+    // 3. element instances: unique (patch, element) pairs
+    const int64_t nk = n * 8;
+    DevBuf<uint64_t> k1, k2; DevBuf<int64_t> nsel;
+    k1.alloc(nk); k2.alloc(nk); nsel.alloc(1);
+    ISL_LAUNCH(h, k_pd_inst_keys, h->grid_for(nk, 256), 256, 0, f.elem_eqn.p, n, patch_of_row.p, k1.p);
+    int pbits = 1; while (((int64_t)1 << pbits) < np + 1) pbits++;
+    tb = 0;
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, k1.p, k2.p, nk, 0, 64, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, k1.p, k2.p, nk, 0, 64, st));
+    tb = 0;
+    ISL_CUDA(cub::DeviceSelect::Unique(nullptr, tb, k2.p, k1.p, nsel.p, nk, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceSelect::Unique(tmp.p, tb, k2.p, k1.p, nsel.p, nk, st));
+    int64_t n_inst = 0;
+    ISL_CUDA(cudaMemcpyAsync(&n_inst, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    {   // the invalid key (corners without an equation) sorts last
+        uint64_t last = 0;
+        if (n_inst > 0) ISL_CUDA(cudaMemcpy(&last, k1.p + n_inst - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (n_inst > 0 && last == ~0ull) n_inst--;
+    }
+    if (n_inst <= 0 || n_inst * 8 >= ((int64_t)1 << 31)) return false;
+    h->launches += 4;
+    k2.release();
+    DevBuf<uint64_t> inst_keys; inst_keys.alloc(n_inst);
+    ISL_CUDA(cudaMemcpyAsync(inst_keys.p, k1.p, n_inst * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+    k1.release();
+    ps->p_inst_off.alloc(np + 1);
+    ISL_LAUNCH(h, k_pd_segment_offsets, (np + 1 + 127) / 128, 128, 0, inst_keys.p, n_inst, np, ps->p_inst_off.p);
+    // 4. nodes of every patch: unique (patch, node) pairs of its instances
+    const int64_t nnk = n_inst * 8;
+    DevBuf<uint64_t> m1, m2; DevBuf<int32_t> inst_elem;
+    m1.alloc(nnk); m2.alloc(nnk); inst_elem.alloc(n_inst);
+    ISL_LAUNCH(h, k_pd_node_keys, h->grid_for(n_inst, 256), 256, 0, inst_keys.p, n_inst, h->conn.p, m1.p, inst_elem.p);
+    tb = 0;
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, m1.p, m2.p, nnk, 0, 64, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, m1.p, m2.p, nnk, 0, 64, st));
+    tb = 0;
+    ISL_CUDA(cub::DeviceSelect::Unique(nullptr, tb, m2.p, m1.p, nsel.p, nnk, st));
+    if (tb > tmp.n) tmp.alloc(tb);
+    ISL_CUDA(cub::DeviceSelect::Unique(tmp.p, tb, m2.p, m1.p, nsel.p, nnk, st));
+    int64_t n_pn = 0;
+    ISL_CUDA(cudaMemcpyAsync(&n_pn, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    h->launches += 4;
+    m2.release();
+    ps->nodes.alloc(n_pn); ps->p_node_off.alloc(np + 1);
+    ISL_LAUNCH(h, k_pd_nodes_from_keys, h->grid_for(n_pn, 256), 256, 0, m1.p, n_pn, ps->nodes.p);
+    ISL_LAUNCH(h, k_pd_segment_offsets, (np + 1 + 127) / 128, 128, 0, m1.p, n_pn, np, ps->p_node_off.p);
+    m1.release();
+    // 5. local node indices, slot table
+    ps->i_lnode.alloc((size_t)n_inst * 8);
+    DevBuf<uint16_t> rslot; rslot.alloc((size_t)nr * 8);
+    ISL_CUDA(cudaMemsetAsync(rslot.p, 0xff, (size_t)nr * 8 * sizeof(uint16_t), st));
+    DevBuf<int> cnt; cnt.alloc(4);
+    ISL_CUDA(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), st));
+    ISL_LAUNCH(h, k_pd_instances, h->grid_for(n_inst, 128), 128, 0, inst_keys.p, n_inst, h->conn.p, f.elem_eqn.p, ps->p_inst_off.p,
+               ps->p_node_off.p, ps->p_row_off.p, ps->nodes.p, patch_of_row.p, rank_of_row.p, ps->i_lnode.p, rslot.p, cnt.p + 2);
+    // sizes (offset arrays are small)
+    std::vector<int32_t> ho(np + 1), hn(np + 1), hr(np + 1);
+    ISL_CUDA(cudaMemcpyAsync(ho.data(), ps->p_inst_off.p, (np + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaMemcpyAsync(hn.data(), ps->p_node_off.p, (np + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaMemcpyAsync(hr.data(), ps->p_row_off.p, (np + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int herr[2] = {0, 0};
+    ISL_CUDA(cudaMemcpyAsync(herr, cnt.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    if (herr[0] || herr[1]) return false;
+    int max_inst = 0, max_nodes = 0, max_rows = 0;
+    for (int p = 0; p < np; p++) {
+        max_inst = std::max(max_inst, ho[p + 1] - ho[p]); max_nodes = std::max(max_nodes, hn[p + 1] - hn[p]);
+        max_rows = std::max(max_rows, hr[p + 1] - hr[p]);
+    }
+    const size_t sm = (size_t)7 * ((max_inst + 2) & ~1) * 8 + std::max((size_t)((max_nodes + 1) & ~1) * 24, (size_t)4 * RG_STAGE * 8);
+    if (sm > (size_t)226 * 1024 || max_nodes >= 65535 || max_inst >= 65534) return false;
+    // row tables (positions, eligibility) exactly as for host-formed patches
+    ps->r_meta.alloc((size_t)nr * sizeof(RowMeta));
+    ISL_LAUNCH(h, k_row_meta, np, 128, 0, 0, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p, h->conn.p, f.eqn.p,
+               f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p), (int32_t*)nullptr, cnt.p, cnt.p + 1);
+    int hc[2] = {0, 0};
+    ISL_CUDA(cudaMemcpyAsync(hc, cnt.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ISL_CUDA(cudaStreamSynchronize(st));
+    if (hc[1]) return false;
+    ps->lift_nodes.alloc((size_t)std::max(1, hc[0]) * 27);
+    if (hc[0] > 0)
+        ISL_LAUNCH(h, k_row_meta, np, 128, 0, 1, ps->p_row_off.p, ps->p_inst_off.p, ps->rows.p, rslot.p, inst_elem.p, h->conn.p, f.eqn.p,
+                   f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(ps->r_meta.p), ps->lift_nodes.p, cnt.p, cnt.p + 1);
+    ISL_CUDA(cudaStreamSynchronize(st));
+    ps->n_patches = np; ps->max_rows = max_rows; ps->max_nodes = max_nodes; ps->max_inst = max_inst; ps->max_entries = 0;
+    ps->n_inst = n_inst; ps->n_elems = n; ps->redundancy = (double)n_inst / (double)n;
+    ps->usable = true; ps->rows_ok = true;
+    if (getenv("ISL_VERBOSE"))
+        fprintf(stderr, "[isl] patches formed on the device: %d boxes of %d x %d x %d cells (long axis %d), max rows %d, max instances %d, "
+                        "max nodes %d, element instances %.3fx, %d rows next to constrained nodes\n",
+                np, g.B[0], g.B[1], g.B[2], ax, max_rows, max_inst, max_nodes, ps->redundancy, hc[0]);
+    return true;
+}
+
 // build (or fetch) the patch decomposition of a scalar Q1-hex field; returns nullptr when the mesh does not fit
 // the shared-memory accumulator (caller falls back to the atomic kernel)
 PatchSet* get_patchset(isl_engine* h, int field) {
@@ -1220,6 +1419,16 @@ PatchSet* get_patchset(isl_engine* h, int field) {
     FieldDev& f = h->fields[field];
     const int64_t n = h->n_owned;
     build_elem_eqn(h, f);
+    if (h->q1_rows && !getenv("ISL_PATCH_HOST")) {
+        // row kernel: everything on the device (isl_patch_dev.cuh); the host bisection below remains for the round-1 patch
+        // kernels and as a fallback
+        if (form_patches_device(h, f, ps.get())) {
+            out = ps.get();
+            h->patchsets[field] = std::move(ps);
+            return out;
+        }
+        ps = std::make_unique<PatchSet>();
+    }
     // 1. host copies: element equations / connectivity, CSR row pointer, row positions
     const int64_t nrow = h->n_eqn;
     std::vector<int32_t> heqn((size_t)n * 8), hconn((size_t)n * 8), hnode_eqn(h->n_nodes);
@@ -2037,8 +2246,8 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         h->val_is_zero = false;
         p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
-        p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
-        p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT);
+        p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
+        p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT && kid != ISL_K_MASS);
         p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : 0;
         if (h->tangent_sym && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == 3 && h->dim == 3 && t == c &&
             !ft.has_masters && ft.ndpe <= 27) {

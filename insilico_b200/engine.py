@@ -26,6 +26,7 @@ VERTEX, EDGE, FACE, CELL = range(4)
 ACTIVE, CONSTRAINED, INACTIVE = range(3)
 K_LAPLACE, K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE, K_PRESSURE_GRADIENT, K_VELOCITY_DIVERGENCE, K_VECTOR_LAPLACE = (
     1, 2, 3, 4, 5, 6)
+K_MASS = 7
 SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
 
 # every symbol include/insilico_b200.h declares (checked by tests/test_cabi.py)

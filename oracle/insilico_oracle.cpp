@@ -798,7 +798,8 @@ enum KernelId {
     K_HYPEL_NEOHOOKE = 3,    // solid::HyperElastic<mat::hypel::NeoHookeanCompressible>
     K_PRESSURE_GRADIENT = 4, // fluid::PressureGradient
     K_VELOCITY_DIVERGENCE = 5, // fluid::VelocityDivergence (params[0] != 0 : changeSign)
-    K_VECTOR_LAPLACE = 6     // fluid::VectorLaplace (tangent == K_LAPLACE; own residual)
+    K_VECTOR_LAPLACE = 6,    // fluid::VectorLaplace (tangent == K_LAPLACE; own residual)
+    K_MASS = 7               // base::kernel::Mass (params[0] = factor, e.g. the density)
 };
 
 struct Tuple {  // asmb/FieldElementPointerTuple.hpp : (geom, test, trial)
@@ -928,6 +929,23 @@ static void laplaceTangent(const Tuple& t, double factor, const double* xi, doub
             double entry = 0.;
             for (int k = 0; k < dim; k++) entry += testG[M * dim + k] * trialG[N * dim + k];
             entry *= scalar;
+            for (int d = 0; d < ds; d++) K(M * ds + d, N * ds + d) += entry;
+        }
+}
+
+// base/kernel/Mass.hpp:88-138: entry = (factor detJ w) * testFun[M] * trialFun[N] on every DoF component
+static void massTangent(const Tuple& t, double factor, const double* xi, double weight, LocalMat& K) {
+    const Mesh& m = t.p->mesh;
+    std::vector<double> trialFun(t.trial->ndpe), testFun(t.test->ndpe);
+    t.trial->feFun.fun(xi, trialFun.data());
+    if (t.bubnov()) testFun = trialFun;
+    else t.test->feFun.fun(xi, testFun.data());
+    const double detJ = jacobian(m, t.e, xi);
+    const int nRB = t.test->ndpe, nCB = t.trial->ndpe, ds = t.trial->dofSize;
+    const double scalar = factor * detJ * weight;
+    for (int M = 0; M < nRB; M++)
+        for (int N = 0; N < nCB; N++) {
+            const double entry = scalar * testFun[M] * trialFun[N];
             for (int d = 0; d < ds; d++) K(M * ds + d, N * ds + d) += entry;
         }
 }
@@ -1087,6 +1105,7 @@ static void tangentKernel(int kid, const double* params, const Tuple& t, const d
         } break;
         case K_PRESSURE_GRADIENT: pressureGradientTangent(*t.p, t.e, *t.test, *t.trial, xi, w, K); break;
         case K_VELOCITY_DIVERGENCE: velocityDivergenceTangent(t, params[0] != 0., xi, w, K); break;
+        case K_MASS: massTangent(t, params[0], xi, w, K); break;
         default: std::abort();
     }
 }

@@ -16,6 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 POINT, LINE, TRI, QUAD, TET, HEX = range(6)
 VERTEX, EDGE, FACE, CELL = range(4)
 ACTIVE, CONSTRAINED, INACTIVE = range(3)
+K_MASS = 7
 K_LAPLACE, K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE, K_PRESSURE_GRADIENT, K_VELOCITY_DIVERGENCE, K_VECTOR_LAPLACE = (
     1, 2, 3, 4, 5, 6)
 SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}

@@ -36,6 +36,7 @@
 #include <base/asmb/ForceIntegrator.hpp>
 #include <base/asmb/BodyForce.hpp>
 #include <base/solver/Eigen3.hpp>
+#include <base/kernel/Mass.hpp>
 #include <heat/Laplace.hpp>
 #include <fluid/Stokes.hpp>
 #include <mat/Lame.hpp>
@@ -284,6 +285,11 @@ int runSingle(const Job& job) {
                 ConstantForce<DS> f;
                 for (unsigned d = 0; d < DS; d++) f.f[d] = op.p[d];
                 base::asmb::bodyForceComputation<FTB>(quadratureBody, solver, fieldBinder, f);
+                continue;
+            }
+            if (op.kernel == "mass") {   // base::kernel::Mass (base/kernel/Mass.hpp), matrix only
+                base::kernel::Mass<typename FTB::Tuple> kernel(op.p[0]);
+                base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
                 continue;
             }
             if constexpr (KIND == SCALAR) {

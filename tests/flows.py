@@ -268,6 +268,15 @@ def build_case(name, n=4, perturb=True, permute=False):
                  ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
                  ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),
                  ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
+    elif name == "mass_q1_hex":       # M/dt + K of an implicit heat step: base::kernel::Mass + heat::Laplace into one matrix
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), values=lambda x: 0.3 * x[:, :1] + 0.1)
+        c.ops = [("matrix", E.K_MASS, [12.5], 3, 0, 0, True), ("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True), ("body", [1.0], 3, 0)]
+    elif name == "mass_p2_tet_vector":  # consistent mass matrix of a P2 displacement field + St. Venant tangent
+        lam, mu = lame(1000.0, 0.3)
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, values=lambda x: 0.03 * np.sin(np.pi * x))
+        c.ops = [("matrix", E.K_MASS, [7.8], 4, 0, 0, True), ("matrix", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0, True)]
     elif name in ("laplace_q1_hex_bodyfun", "laplace_p2_tri_bodyfun", "vector_laplace_q1_hex_bodyfun"):
         # general (non-constant) body force f(x): BodyForce.hpp:172-205 evaluates the caller's function per point
         if "tri" in name:

@@ -26,7 +26,7 @@ OUT = os.path.join(ROOT, "tests", "golden", "refrun")
 SHAPE_NAME = {E.TRI: "triangle", E.QUAD: "quadrilateral", E.TET: "tetrahedron", E.HEX: "hexahedron"}
 KERNEL_NAME = {E.K_LAPLACE: "laplace", E.K_VECTOR_LAPLACE: "vector_laplace", E.K_HYPEL_STVENANT: "stvenant",
                E.K_HYPEL_NEOHOOKE: "neohooke", E.K_PRESSURE_GRADIENT: "pressure_gradient",
-               E.K_VELOCITY_DIVERGENCE: "velocity_divergence"}
+               E.K_VELOCITY_DIVERGENCE: "velocity_divergence", E.K_MASS: "mass"}
 
 # (golden name, flows case, driver type, n, perturb, permute, register)
 CASES = [
@@ -50,6 +50,9 @@ CASES = [
     ("stvenant_q2_quad_n4", "stvenant_q2_quad", "solid_q2_quad", 4, True, False, True),
     ("laplace_p1_tri_n6", "laplace_p1_tri", "laplace_p1_tri", 6, True, True, False),
     ("stvenant_p2_tet_n3", "stvenant_p2_tet", "solid_p2_tet", 3, True, False, False),
+    # base::kernel::Mass next to a stiffness matrix (the system of an implicit time step / a reaction term)
+    ("mass_q1_hex_n4", "mass_q1_hex", "laplace_q1_hex", 4, True, False, False),
+    ("mass_p2_tet_vector_n3", "mass_p2_tet_vector", "solid_p2_tet", 3, True, True, False),
     # general body forces f(x) (the caller's function evaluated per quadrature point, BodyForce.hpp:172-205)
     ("laplace_q1_hex_bodyfun_n4", "laplace_q1_hex_bodyfun", "laplace_q1_hex", 4, True, False, False),
     ("laplace_p2_tri_bodyfun_n4", "laplace_p2_tri_bodyfun", "laplace_p2_tri", 4, True, False, False),
