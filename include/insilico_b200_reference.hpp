@@ -47,6 +47,7 @@
 #include <base/asmb/StiffnessMatrix.hpp>
 #include <base/asmb/ForceIntegrator.hpp>
 #include <base/asmb/BodyForce.hpp>
+#include <base/kernel/Mass.hpp>
 #include <heat/Laplace.hpp>
 #include <heat/Static.hpp>
 #include <mat/thermal/IsotropicConstant.hpp>
@@ -101,7 +102,8 @@ struct FieldState {
 };
 
 struct BinderState {
-    const void* key = NULL;
+    const void* key = NULL;            // first geometry element behind the binder
+    const void* fieldKey[5] = {NULL, NULL, NULL, NULL, NULL};   // first element of every bound field
     std::size_t numElements = 0;
     int shape = 0, geomDeg = 0, dim = 0;
     int64_t nNodes = 0;
@@ -123,7 +125,7 @@ struct IsDummy {
 
 template <int N, typename FIELDBINDER, bool DUMMY>
 struct FlattenField {
-    static void apply(const FIELDBINDER&, BinderState& s, bool) { s.field[N - 1].bound = false; }
+    static void apply(const FIELDBINDER&, BinderState&, bool) {}   // slot not bound by this binder: the engine keeps what it has
 };
 
 template <int N, typename FIELDBINDER>
@@ -135,8 +137,10 @@ struct FlattenField<N, FIELDBINDER, false> {
     static void apply(const FIELDBINDER& fb, BinderState& s, bool topologyChanged) {
         FieldState& f = s.field[N - 1];
         const int ds = static_cast<int>(DoF::size), ndpe = static_cast<int>(Element::numDoFs);
-        bool redefine = topologyChanged || !f.bound;
         const typename FIELDBINDER::FieldIterator it = fb.elementsBegin();
+        const void* firstElement = static_cast<const void*>((*it).template get<N>());
+        bool redefine = topologyChanged || !f.bound || s.fieldKey[N - 1] != firstElement;
+        s.fieldKey[N - 1] = firstElement;
         const long numE = static_cast<long>(s.numElements);
         if (redefine) {
             f.feDeg = static_cast<int>(Element::FEFun::degree);
@@ -325,10 +329,39 @@ bool sampleUnchanged(const FIELDBINDER& fb, const BinderState& s) {
     return true;
 }
 
+//! Identity of what a binder binds: the reference builds FieldBinder objects on the fly (a new local one in every method of
+//! base::BoundaryValueProblem, BoundaryValueProblem.hpp:238-345), so the binder's own address says nothing; the first
+//! geometry element and the first element of every bound field do.
+template <int N, typename FIELDBINDER, bool DUMMY>
+struct FirstElement {
+    static const void* get(const FIELDBINDER&) { return NULL; }
+};
+template <int N, typename FIELDBINDER>
+struct FirstElement<N, FIELDBINDER, false> {
+    static const void* get(const FIELDBINDER& fb) { return static_cast<const void*>((*fb.elementsBegin()).template get<N>()); }
+};
+template <typename FIELDBINDER>
+bool sameBinding(const FIELDBINDER& fb, const BinderState& s) {
+    typedef typename FIELDBINDER::ElementPtrTuple EPT;
+    if (fb.elementsBegin() == fb.elementsEnd()) return false;
+    if (s.key != static_cast<const void*>((*fb.elementsBegin()).geomElementPtr())) return false;
+    // dummy slots give NULL, and a NULL slot of this binder is not compared: a binder over fewer fields of the same
+    // mesh does not redefine anything
+    const void* k[5] = {FirstElement<1, FIELDBINDER, IsDummy<typename EPT::template Binder<1>::Type>::value>::get(fb),
+                        FirstElement<2, FIELDBINDER, IsDummy<typename EPT::template Binder<2>::Type>::value>::get(fb),
+                        FirstElement<3, FIELDBINDER, IsDummy<typename EPT::template Binder<3>::Type>::value>::get(fb),
+                        FirstElement<4, FIELDBINDER, IsDummy<typename EPT::template Binder<4>::Type>::value>::get(fb),
+                        FirstElement<5, FIELDBINDER, IsDummy<typename EPT::template Binder<5>::Type>::value>::get(fb)};
+    for (int i = 0; i < 5; i++)
+        if (k[i] != NULL && (!s.field[i].bound || s.fieldKey[i] != k[i])) return false;
+    return true;
+}
 //! Bring the engine's copy of mesh and fields in line with the reference's objects behind this binder.
 template <typename FIELDBINDER>
 void synchronise(const FIELDBINDER& fb) {
-    if (!rescanEveryCall() && state().key == static_cast<const void*>(&fb) && scannedForSolver() == currentSolver() &&
+    if (fb.elementsBegin() == fb.elementsEnd()) return;
+    const bool known = sameBinding(fb, state());
+    if (!rescanEveryCall() && known && scannedForSolver() == currentSolver() &&
         currentSolver() != 0) {
         if (rescanOncePerSolver() || sampleUnchanged(fb, state())) return;
     }
@@ -341,7 +374,9 @@ void synchronise(const FIELDBINDER& fb) {
     const std::size_t numElements = static_cast<std::size_t>(std::distance(fb.elementsBegin(), fb.elementsEnd()));
     const long numE = static_cast<long>(numElements);
     const int npe = static_cast<int>(GeomElement::numNodes), dim = static_cast<int>(Node::dim);
-    bool topologyChanged = (s.key != static_cast<const void*>(&fb)) || (s.numElements != numElements);
+    // another mesh / other fields behind the binder: everything is redefined (whether the same mesh was rebuilt is
+    // decided below by comparing the connectivity itself)
+    bool topologyChanged = (s.key != static_cast<const void*>((*fb.elementsBegin()).geomElementPtr())) || (s.numElements != numElements);
 
     // connectivity (also re-read when the binder is known: cheap, and catches a re-meshed binder); all host threads
     std::vector<int32_t> conn(numElements * npe);
@@ -371,7 +406,6 @@ void synchronise(const FIELDBINDER& fb) {
     }
     const bool coordsChanged = assignIfChanged(s.coords, coords);
     if (topologyChanged || s.nNodes != nNodes) {
-        s.key = &fb;
         s.numElements = numElements;
         s.shape = static_cast<int>(GeomElement::shape);
         s.geomDeg = static_cast<int>(GeomElement::GeomFun::degree);
@@ -383,6 +417,7 @@ void synchronise(const FIELDBINDER& fb) {
     } else if (coordsChanged) {
         check(isl_mesh_update_coords(engine(), &s.coords[0]));
     }
+    s.key = static_cast<const void*>((*fb.elementsBegin()).geomElementPtr());
     flattenField<1>(fb, s, topologyChanged);
     flattenField<2>(fb, s, topologyChanged);
     flattenField<3>(fb, s, topologyChanged);
@@ -462,7 +497,7 @@ double probeScalar(const base::MatrixD& K, const MAKEKERNEL& make, const TUPLE& 
 template <typename KERNEL>
 struct B200KernelTraits {
     static_assert(sizeof(KERNEL) == 0,
-                  "this kernel object has no implementation in the B200 assembly engine (supported: heat::Laplace, "
+                  "this kernel object has no implementation in the B200 assembly engine (supported: heat::Laplace, base::kernel::Mass, "
                   "heat::Static<mat::thermal::IsotropicConstant>, fluid::VectorLaplace, fluid::PressureGradient, "
                   "fluid::VelocityDivergence, solid::HyperElastic<mat::hypel::StVenant | NeoHookeanCompressible>); "
                   "there is no CPU fallback");
@@ -521,6 +556,18 @@ struct B200KernelTraits<fluid::VectorLaplace<TUPLE> > {
 #endif
         p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         return ISL_K_VECTOR_LAPLACE;
+    }
+};
+
+//! base::kernel::Mass (base/kernel/Mass.hpp:88-138): factor * detJ * w * phi_M * psi_N on every DoF component
+template <typename TUPLE>
+struct B200KernelTraits<base::kernel::Mass<TUPLE> > {
+    struct Make {
+        base::kernel::Mass<TUPLE> operator()(double c) const { return base::kernel::Mass<TUPLE>(c); }
+    };
+    static int describe(const base::kernel::Mass<TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
+        p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
+        return ISL_K_MASS;
     }
 };
 

@@ -26,6 +26,10 @@ CASES = [
     ("stvenant_q1_hex", 4, True, False), ("stvenant_q2_hex", 2, True, False), ("neohooke_q1_hex", 3, True, True),
     ("stvenant_q1_quad", 7, True, False), ("neohooke_p2_tet", 3, True, True), ("stokes_p2p1_tet", 3, True, False),
     ("stokes_q2q1_hex", 2, True, False), ("stokes_q2q1_quad", 5, True, True),
+    # base::kernel::Mass + a stiffness matrix into ONE system: the Q1 row kernel then runs in accumulate mode (bulk
+    # reduction) on the structured mesh and through the two-kernel general path on the perturbed one
+    ("mass_q1_hex", 7, False, False), ("mass_q1_hex", 6, True, True), ("mass_p2_tet_vector", 3, True, True),
+    ("stvenant_q2_hex", 3, True, True), ("stvenant_p2_tet", 3, True, True),
 ]
 
 
