@@ -627,11 +627,19 @@ __device__ __forceinline__ unsigned long long dbl_ord(double x) {
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 __global__ void k_bbox(const double* coords, int64_t n_nodes, int dim, unsigned long long* mn, unsigned long long* mx) {
+    unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0ull, 0ull, 0ull};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_nodes; i += (int64_t)gridDim.x * blockDim.x)
         for (int d = 0; d < dim; d++) {
             const unsigned long long o = dbl_ord(coords[i * dim + d]);
-            atomicMin(mn + d, o); atomicMax(mx + d, o);
+            lo[d] = min(lo[d], o); hi[d] = max(hi[d], o);
         }
+    for (int d = 0; d < dim; d++) {   // one atomic per warp
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[d] = min(lo[d], __shfl_down_sync(0xffffffffu, lo[d], off));
+            hi[d] = max(hi[d], __shfl_down_sync(0xffffffffu, hi[d], off));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(mn + d, lo[d]); atomicMax(mx + d, hi[d]); }
+    }
 }
 __device__ __forceinline__ double ord_dbl(unsigned long long o) {
     const unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7fffffffffffffffull) : ~o;
@@ -829,7 +837,8 @@ struct isl_engine {
     int q1_rows = 1;            // row kernels (isl_rowgather.cuh: all-affine meshes; isl_rows_fromk.cuh: general elements);
                                 // ISL_Q1_ROWS=0 selects the round-1 shared-memory patch kernels
     int rows_threads = 128;     // CTA size of the affine row kernel (ISL_ROWS_THREADS)
-    int fromk_chunks = 1;       // software-pipeline depth of the two-kernel general path (ISL_FROMK_CHUNKS)
+    int fromk_pipeline = 1;     // general Q1 elements: one persistent producer/consumer kernel (ISL_FROMK_PIPELINE=0: two kernels through HBM)
+    int64_t pipe_rows = 65536;  // rows per pipeline chunk (ISL_PIPE_ROWS)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1105,7 +1114,7 @@ const int32_t* get_eorder(isl_engine* h, int field) {
     DevBuf<unsigned long long> bb; bb.alloc(6);
     ISL_CUDA(cudaMemsetAsync(bb.p, 0xff, 3 * sizeof(unsigned long long), h->stream));
     ISL_CUDA(cudaMemsetAsync(bb.p + 3, 0, 3 * sizeof(unsigned long long), h->stream));
-    ISL_LAUNCH(h, k_bbox, h->grid_for(h->n_nodes, 256), 256, 0, h->coords.p, h->n_nodes, h->dim, bb.p, bb.p + 3);
+    ISL_LAUNCH(h, k_bbox, std::min(h->grid_for(h->n_nodes, 256), h->n_sm * 8), 256, 0, h->coords.p, h->n_nodes, h->dim, bb.p, bb.p + 3);
     ISL_LAUNCH(h, k_elem_morton, h->grid_for(n, 256), 256, 0, h->coords.p, h->conn.p, n, h->npe, h->dim, bb.p, bb.p + 3, key.p, idx.p);
     size_t tb = 0;
     ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, f.eorder.p, n, 0, 32, h->stream));
@@ -1244,7 +1253,7 @@ bool form_patches_device(isl_engine* h, FieldDev& f, PatchSet* ps) {
     DevBuf<unsigned long long> bb; bb.alloc(9);
     ISL_CUDA(cudaMemsetAsync(bb.p, 0xff, 3 * sizeof(unsigned long long), st));
     ISL_CUDA(cudaMemsetAsync(bb.p + 3, 0, 6 * sizeof(unsigned long long), st));
-    ISL_LAUNCH(h, k_bbox, h->grid_for(nn, 256), 256, 0, h->coords.p, nn, 3, bb.p, bb.p + 3);
+    ISL_LAUNCH(h, k_bbox, std::min(h->grid_for(nn, 256), h->n_sm * 8), 256, 0, h->coords.p, nn, 3, bb.p, bb.p + 3);
     double hs[4];
     unsigned long long hb[9];
     ISL_CUDA(cudaMemcpyAsync(hs, sums.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
@@ -1628,23 +1637,17 @@ FromKSet* get_fromk(isl_engine* h, int field) {
         DevBuf<char> tmp; tmp.alloc(tb);
         ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, fk->eorder.p, n, 0, 32, h->stream));
         h->launches += 4;
-        {   // chunks of the software pipeline (launch_q1): equal row ranges, element ranges by the sorted keys
-            const int NC = (int)std::max<int64_t>(1, std::min<int64_t>(h->fromk_chunks, nr / 65536));
-            std::vector<int64_t> rb(NC + 1);
-            for (int c = 0; c <= NC; c++) rb[c] = (nr * c / NC) & ~(int64_t)127;   // whole CTAs of the row kernel
-            rb[NC] = nr;
-            DevBuf<int64_t> db, de;
-            upload_vec(h, db, rb); de.alloc(NC + 1);
-            ISL_LAUNCH(h, k_fromk_bounds, 1, 64 > NC + 1 ? 64 : ((NC + 1 + 31) / 32) * 32, 0, key2.p, n, db.p, NC + 1, de.p);
-            std::vector<int64_t> eb(NC + 1);
-            ISL_CUDA(cudaMemcpyAsync(eb.data(), de.p, (NC + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<int64_t> rb, eb;
+        {   // chunks of the producer / consumer pipeline: ~pipe_rows rows each, element ranges by the sorted keys
+            const int NC = (int)std::max<int64_t>(1, (nr + h->pipe_rows - 1) / h->pipe_rows);
+            rb.resize(NC + 1);
+            for (int c = 0; c <= NC; c++) rb[c] = std::min<int64_t>(nr, (int64_t)c * h->pipe_rows);
+            upload_vec(h, fk->d_row_b, rb); fk->d_elem_b.alloc(NC + 1);
+            ISL_LAUNCH(h, k_fromk_bounds, (NC + 1 + 127) / 128, 128, 0, key2.p, n, fk->d_row_b.p, NC + 1, fk->d_elem_b.p);
+            eb.resize(NC + 1);
+            ISL_CUDA(cudaMemcpyAsync(eb.data(), fk->d_elem_b.p, (NC + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
             ISL_CUDA(cudaStreamSynchronize(h->stream));
-            eb[0] = 0;   // (row boundary 0: every key >= 0)
-            fk->row_b = rb; fk->elem_b = eb;   // elements past elem_b[NC] touch no ACTIVE row
-            fk->ev.resize(NC);
-            for (auto& e : fk->ev) ISL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            ISL_CUDA(cudaEventCreateWithFlags(&fk->ev_start, cudaEventDisableTiming));
-            ISL_CUDA(cudaStreamCreateWithFlags(&fk->aux, cudaStreamNonBlocking));
+            fk->NC = NC;   // elements past eb[NC] touch no ACTIVE row
         }
         fk->row_pos.alloc((size_t)nr * 8);
         ISL_CUDA(cudaMemsetAsync(fk->row_pos.p, 0xff, (size_t)nr * 8 * sizeof(int32_t), h->stream));
@@ -1662,11 +1665,45 @@ FromKSet* get_fromk(isl_engine* h, int field) {
             if (hc[0] > 0)
                 ISL_LAUNCH(h, k_fromk_row_meta, h->grid_for(nr, 128), 128, 0, 1, nr, fk->row_pos.p, fk->eorder.p, h->conn.p, f.eqn.p,
                            f.status.p, h->rowptr.p, h->col.p, reinterpret_cast<RowMeta*>(fk->meta.p), fk->lift_nodes.p, cnt.p, cnt.p + 1);
-            fk->K.alloc((size_t)44 * n);
+            // pipeline tables: look-back of the rows, ring of K slots, queue segments E(0), E(1), R(0), E(2), R(1), ...
+            const int NC = fk->NC;
+            DevBuf<int> dback; dback.alloc(1);
+            ISL_CUDA(cudaMemsetAsync(dback.p, 0, sizeof(int), h->stream));
+            ISL_LAUNCH(h, k_fromk_maxback, h->grid_for(nr, 256), 256, 0, fk->row_pos.p, nr, fk->d_row_b.p, fk->d_elem_b.p, NC, dback.p);
+            ISL_CUDA(cudaMemcpyAsync(&fk->maxback, dback.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+            fk->slots = std::min(NC, std::max(4, fk->maxback + 4));
+            if (h->fromk_pipeline && NC >= 2 && fk->maxback + 2 <= fk->slots) {
+                int64_t cap = 0;
+                std::vector<int32_t> et(NC), rt(NC), sc;
+                std::vector<uint8_t> sk;
+                std::vector<int64_t> sf;
+                for (int c = 0; c < NC; c++) {
+                    cap = std::max(cap, eb[c + 1] - eb[c]);
+                    et[c] = (int32_t)((eb[c + 1] - eb[c] + 127) / 128); rt[c] = (int32_t)((rb[c + 1] - rb[c] + 127) / 128);
+                }
+                int64_t items = 0;
+                auto push = [&](int kind, int c) { sf.push_back(items); sc.push_back(c); sk.push_back((uint8_t)kind); items += kind ? rt[c] : et[c]; };
+                push(0, 0);
+                for (int c = 1; c < NC; c++) { push(0, c); push(1, c - 1); }
+                push(1, NC - 1);
+                sf.push_back(items);
+                fk->chunk_cap = (cap + 15) & ~(int64_t)15; fk->n_items = items; fk->n_seg = (int)sc.size();
+                upload_vec(h, fk->seg_first, sf); upload_vec(h, fk->seg_chunk, sc); upload_vec(h, fk->seg_kind, sk);
+                upload_vec(h, fk->e_tiles, et); upload_vec(h, fk->r_tiles, rt);
+                fk->counters.alloc((size_t)4 + 2 * NC);
+                fk->Kring.alloc((size_t)44 * fk->slots * fk->chunk_cap);
+                fk->pipe_ok = true;
+            } else {
+                fk->K.alloc((size_t)44 * n);
+            }
             ISL_CUDA(cudaStreamSynchronize(h->stream));
             fk->ok = true;
         }
-        if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] two-kernel general path: %s, %d rows next to constrained nodes\n", fk->ok ? "ok" : "not eligible", hc[0]);
+        if (getenv("ISL_VERBOSE"))
+            fprintf(stderr, "[isl] general Q1 path: %s, %d rows next to constrained nodes; %s (%d chunks, look-back %d, %d ring slots of %lld elements)\n",
+                    fk->ok ? "ok" : "not eligible", hc[0], fk->pipe_ok ? "producer/consumer pipeline through L2" : "two kernels through HBM", fk->NC,
+                    fk->maxback, fk->slots, (long long)fk->chunk_cap);
     }
     FromKSet* out = fk->ok ? fk.get() : nullptr;
     h->fromk_sets[field] = std::move(fk);
@@ -1767,28 +1804,29 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
     k.row_pos = fk->row_pos.p; k.meta = reinterpret_cast<const RowMeta*>(fk->meta.p); k.n_rows = fk->n_rows; k.K = fk->K.p;
     q.lift_nodes = fk->lift_nodes.p;
     k.r = q; k.matrix = matrix;
-    // software pipeline over chunks: the element kernel (FP64-bound) of chunk c+1 runs on a second stream while the row
-    // kernel (memory-bound) of chunk c runs on the engine stream; rows of chunk c only read elements of chunks <= c
     constexpr int NT = 128;
     const size_t smem_k = (size_t)(NT / 32) * RG_STAGE * 8;
+    if (fk->pipe_ok) {
+        // ONE persistent kernel: element tiles produce K into an L2-resident ring, row tiles consume it (isl_rows_fromk.cuh)
+        PipeParams q2;
+        k.K = fk->Kring.p;
+        q2.k = k;
+        q2.seg_first = fk->seg_first.p; q2.seg_chunk = fk->seg_chunk.p; q2.seg_kind = fk->seg_kind.p;
+        q2.row_b = fk->d_row_b.p; q2.elem_b = fk->d_elem_b.p;
+        q2.n_seg = fk->n_seg; q2.NC = fk->NC; q2.slots = fk->slots; q2.maxback = fk->maxback; q2.chunk_cap = fk->chunk_cap;
+        ISL_CUDA(cudaMemsetAsync(fk->counters.p, 0, fk->counters.n * sizeof(int), h->stream));
+        q2.next = reinterpret_cast<unsigned long long*>(fk->counters.p);
+        q2.e_prefix = fk->counters.p + 2; q2.r_prefix = fk->counters.p + 3;
+        q2.edone = fk->counters.p + 4; q2.rdone = fk->counters.p + 4 + fk->NC;
+        q2.e_tiles = fk->e_tiles.p; q2.r_tiles = fk->r_tiles.p; q2.n_items = fk->n_items;
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_pipeline, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+        ISL_LAUNCH(h, k_q1hex_pipeline, h->n_sm * 3, NT, smem_k, q2);
+        return;
+    }
     ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_fromK<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
-    const int NC = (int)fk->row_b.size() - 1;
-    ISL_CUDA(cudaEventRecord(fk->ev_start, h->stream));
-    ISL_CUDA(cudaStreamWaitEvent(fk->aux, fk->ev_start, 0));
-    for (int c = 0; c < NC; c++) {
-        k.e_lo = fk->elem_b[c]; k.e_hi = fk->elem_b[c + 1];
-        if (k.e_hi > k.e_lo) {
-            k_q1hex_elemK<<<(unsigned)((k.e_hi - k.e_lo + 127) / 128), 128, 0, fk->aux>>>(k);
-            h->launches++;
-        }
-        ISL_CUDA(cudaEventRecord(fk->ev[c], fk->aux));
-    }
-    for (int c = 0; c < NC; c++) {
-        k.r_lo = fk->row_b[c]; k.r_hi = fk->row_b[c + 1];
-        ISL_CUDA(cudaStreamWaitEvent(h->stream, fk->ev[c], 0));
-        if (k.r_hi > k.r_lo) ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((k.r_hi - k.r_lo + NT - 1) / NT), NT, smem_k, k);
-    }
-    ISL_CUDA(cudaGetLastError());
+    k.e_lo = 0; k.e_hi = fk->n_elems; k.r_lo = 0; k.r_hi = fk->n_rows;
+    ISL_LAUNCH(h, k_q1hex_elemK, (unsigned)((fk->n_elems + 127) / 128), 128, 0, k);
+    ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((fk->n_rows + NT - 1) / NT), NT, smem_k, k);
 }
 
 template <bool MATRIX>
@@ -1950,7 +1988,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_Q1_ROWS")) h->q1_rows = atoi(m) ? 1 : 0;
         if (!h->q1_rows) { h->patch_rows = 400; h->patch_stretch = 1.0; }   // geometry of the round-1 patch kernels
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
-        if (const char* m = getenv("ISL_FROMK_CHUNKS")) h->fromk_chunks = std::max(1, std::min(512, atoi(m)));
+        if (const char* m = getenv("ISL_FROMK_PIPELINE")) h->fromk_pipeline = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_PIPE_ROWS")) h->pipe_rows = std::max(1024, atoi(m));
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
