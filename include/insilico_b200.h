@@ -138,6 +138,11 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field);
  * (base/asmb/StiffnessMatrix.hpp:49-87): K scattered into CSR, Dirichlet lift into rhs                      */
 int isl_assemble_matrix(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,
                         int trial_field, int incremental);
+/* the same for heat::Laplace with a conductivity FUNCTION (heat/Laplace.hpp:85-126, setConductivityFunction): values[n_elems *
+ * nq] = conductivity at the quadrature points of Quadrature<quad_deg> of every (owned) element, host or device pointer; the
+ * caller's function runs on the host (like isl_assemble_bodyforce_sampled), the integration on the device.  Laplace kernels. */
+int isl_assemble_matrix_sampled(isl_handle h, int kernel_id, const double* values, int quad_deg, int test_field,
+                                int trial_field, int incremental);
 /* asmb::computeResidualForces<FTB>(quad, solver, binder, kernelObj) (base/asmb/ForceIntegrator.hpp:37-71):
  * rhs += factor * f_e with factor = -1 in the reference                                                     */
 int isl_assemble_residual(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,

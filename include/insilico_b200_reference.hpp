@@ -516,8 +516,9 @@ struct B200KernelTraits<heat::Laplace<TUPLE> > {
 #endif
         p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         const double p1 = b200_detail::probeScalar(b200_detail::probeTangent(k, t1), Make(), t1);
-        VERIFY_MSG(std::abs(p1 - p[0]) <= 1e-13 * std::abs(p[0]),
-                   "B200 engine: heat::Laplace with a non-constant conductivity function is not supported");
+        // a conductivity FUNCTION (setConductivityFunction): the matrix overload samples it per quadrature point
+        // (b200_detail::SampledFactor); p[3] carries the verdict of this first look
+        if (!(std::abs(p1 - p[0]) <= 1e-13 * std::abs(p[0]))) p[3] = 1.0;
         return ISL_K_LAPLACE;
     }
 };
@@ -897,9 +898,73 @@ typename FIELDTUPLEBINDER::Tuple probeTuple(const FIELDBINDER& fb, bool last) {
 }
 }  // namespace b200_detail
 
+namespace b200_detail {
+//! Material factor that varies in space: heat::Laplace with setConductivityFunction (heat/Laplace.hpp:85-126) evaluates a
+//! boost::function per quadrature point.  The function object is private, so kappa(e, q) is recovered through the public
+//! interface: K = kappa * K1 with K1 from the unit-conductivity kernel at the same point (two local matrices per point,
+//! all host threads; with ISL_B200_HAVE_KERNEL_ACCESSORS a maintainer's `conductivityFunction()` accessor is called
+//! directly).  `varies` first looks at 16 elements spread over the mesh x all points.
+template <typename KERNEL>
+struct SampledFactor {
+    template <typename FTB, typename QUADRATURE, typename FIELDBINDER>
+    static bool varies(const KERNEL&, const QUADRATURE&, const FIELDBINDER&, double) { return false; }
+    template <typename FTB, typename QUADRATURE, typename FIELDBINDER>
+    static void sample(const KERNEL&, const QUADRATURE&, const FIELDBINDER&, std::vector<double>&) {}
+};
+template <typename TUPLE>
+struct SampledFactor<heat::Laplace<TUPLE> > {
+    typedef heat::Laplace<TUPLE> Kernel;
+    template <typename FTB, typename XI>
+    static double at(const Kernel& k, const Kernel& unit, const typename FTB::Tuple& tuple, const XI& xi) {
+#ifdef ISL_B200_HAVE_KERNEL_ACCESSORS
+        (void)unit;
+        return k.conductivityFunction()(tuple.geomElementPtr(), xi);
+#else
+        typedef typename TUPLE::TestElement TestElement;
+        typedef typename TUPLE::TrialElement TrialElement;
+        const unsigned nr = TestElement::numDoFs * TestElement::DegreeOfFreedom::size;
+        const unsigned nc = TrialElement::numDoFs * TrialElement::DegreeOfFreedom::size;
+        base::MatrixD K = base::MatrixD::Zero(nr, nc), K1 = base::MatrixD::Zero(nr, nc);
+        k.tangentStiffness(tuple, xi, 1.0, K);
+        unit.tangentStiffness(tuple, xi, 1.0, K1);
+        unsigned bi = 0;
+        for (unsigned i = 1; i < std::min(nr, nc); i++) if (std::abs(K1(i, i)) > std::abs(K1(bi, bi))) bi = i;
+        return K(bi, bi) / K1(bi, bi);
+#endif
+    }
+    template <typename FTB, typename QUADRATURE, typename FIELDBINDER>
+    static bool varies(const Kernel& k, const QUADRATURE& quadrature, const FIELDBINDER& fb, double kappa0) {
+        const Kernel unit(1.0);
+        const long numE = static_cast<long>(std::distance(fb.elementsBegin(), fb.elementsEnd()));
+        const long step = std::max(1L, numE / 16);
+        for (long e = 0; e < numE; e += step)
+            for (typename QUADRATURE::Iter q = quadrature.begin(); q != quadrature.end(); ++q) {
+                const double v = at<FTB>(k, unit, FTB::makeTuple(*(fb.elementsBegin() + e)), q->second);
+                if (!(std::abs(v - kappa0) <= 1e-12 * std::abs(kappa0))) return true;
+            }
+        return false;
+    }
+    template <typename FTB, typename QUADRATURE, typename FIELDBINDER>
+    static void sample(const Kernel& k, const QUADRATURE& quadrature, const FIELDBINDER& fb, std::vector<double>& values) {
+        const Kernel unit(1.0);
+        const long numE = static_cast<long>(std::distance(fb.elementsBegin(), fb.elementsEnd()));
+        std::vector<typename QUADRATURE::Iter> qpts;
+        for (typename QUADRATURE::Iter q = quadrature.begin(); q != quadrature.end(); ++q) qpts.push_back(q);
+        const std::size_t nq = qpts.size();
+        values.assign(static_cast<std::size_t>(numE) * nq, 0.);
+        const typename FIELDBINDER::FieldIterator it0 = fb.elementsBegin();
+#pragma omp parallel for schedule(static)
+        for (long e = 0; e < numE; e++) {
+            const typename FTB::Tuple tuple = FTB::makeTuple(*(it0 + e));
+            for (std::size_t q = 0; q < nq; q++) values[e * nq + q] = at<FTB>(k, unit, tuple, qpts[q]->second);
+        }
+    }
+};
+}  // namespace b200_detail
+
 //! base/asmb/StiffnessMatrix.hpp:49-87 for SOLVER = base::solver::B200
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
-void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+void stiffnessMatrixComputation(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
                                 const KERNEL& kernelObj, const bool incremental = true) {
     namespace D = base::solver::b200_detail;
     solver.verifyCurrent();
@@ -910,6 +975,15 @@ void stiffnessMatrixComputation(const QUADRATURE&, base::solver::B200& solver, c
         kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
         b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
+    typedef b200_detail::SampledFactor<KERNEL> Sampled;
+    if (params[3] != 0. || Sampled::template varies<FIELDTUPLEBINDER>(kernelObj, quadrature, fieldBinder, params[0])) {
+        std::vector<double> values;   // the caller's material function, evaluated on the host at every quadrature point
+        Sampled::template sample<FIELDTUPLEBINDER>(kernelObj, quadrature, fieldBinder, values);
+        VERIFY_MSG(!values.empty(), "B200 engine: this kernel object has a material factor that varies in space and no sampled form");
+        D::check(isl_assemble_matrix_sampled(D::engine(), id, &values[0], D::QuadratureDegree<QUADRATURE>::value, TI::test,
+                                             TI::trial, incremental ? 1 : 0));
+        return;
+    }
     D::check(isl_assemble_matrix(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
                                  incremental ? 1 : 0));
 }
@@ -926,6 +1000,7 @@ void computeResidualForces(const QUADRATURE&, base::solver::B200& solver, const 
     const int id = base::solver::B200KernelTraits<KERNEL>::describe(
         kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
         b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
+    VERIFY_MSG(params[3] == 0., "B200 engine: residual forces with a material factor that varies in space are not supported");
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
     D::check(isl_assemble_residual(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
                                    -1.0));

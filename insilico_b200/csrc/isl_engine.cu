@@ -110,6 +110,7 @@ struct AsmParams {
     int EB; int need_gt, need_gc, nqdata;
     int body; double f[3];
     const double* fq;   // body == 2: force sampled at the quadrature points, [n_elems][nq][dst]
+    const double* kq;   // Laplace kernels: conductivity sampled at the quadrature points, [n_elems][nq] (nullptr: constant p0)
     // linear constraints with master DoFs (nullptr when the field has none): per DoF component k the masters
     // [cptr[k], cptr[k+1]) as equation numbers cm[] with weights cw[]; CSR pattern for the entries they reach
     const int32_t* cptr_t; const int32_t* cm_t; const double* cw_t;
@@ -370,7 +371,8 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     const double* gN = s.sGc + ((size_t)eq * p.nc + N) * DIM;
                     double dot = gM[0] * gN[0];
                     for (int k = 1; k < DIM; k++) dot += gM[k] * gN[k];
-                    acc += dot * (p.p0 * s.sDet[eq] * p.w[q]);
+                    const double kap = p.kq ? p.kq[(size_t)p.eid(base + eb) * p.nq + q] : p.p0;
+                    acc += dot * (kap * s.sDet[eq] * p.w[q]);
                 }
                 for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
             }
@@ -837,8 +839,9 @@ struct isl_engine {
     int q1_rows = 1;            // row kernels (isl_rowgather.cuh: all-affine meshes; isl_rows_fromk.cuh: general elements);
                                 // ISL_Q1_ROWS=0 selects the round-1 shared-memory patch kernels
     int rows_threads = 128;     // CTA size of the affine row kernel (ISL_ROWS_THREADS)
-    int fromk_pipeline = 1;     // general Q1 elements: one persistent producer/consumer kernel (ISL_FROMK_PIPELINE=0: two kernels through HBM)
+    int fromk_pipeline = 0;     // ISL_FROMK_PIPELINE=1: general Q1 elements in one persistent producer/consumer kernel (measured slower: 6.5 vs 3.8 ms)
     int64_t pipe_rows = 65536;  // rows per pipeline chunk (ISL_PIPE_ROWS)
+    int fromk_variant = 0;      // row-kernel variant of the two-kernel general path (ISL_FROMK_VARIANT)
     int aff_split = 1;          // mbarrier arrive/wait phases in the all-affine kernel (ISL_AFF_SPLIT=0: __syncthreads)
     int patch_threads_aff = 0;  // experiment knob: alternative CTA size of the all-affine kernel
     int affine_state = -1;      // -1 unknown, 0 some element is not affine, 1 every owned element is affine
@@ -1823,10 +1826,22 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
         ISL_LAUNCH(h, k_q1hex_pipeline, h->n_sm * 3, NT, smem_k, q2);
         return;
     }
-    ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_fromK<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
     k.e_lo = 0; k.e_hi = fk->n_elems; k.r_lo = 0; k.r_hi = fk->n_rows;
     ISL_LAUNCH(h, k_q1hex_elemK, (unsigned)((fk->n_elems + 127) / 128), 128, 0, k);
-    ISL_LAUNCH(h, k_q1hex_rows_fromK<NT>, (unsigned)((fk->n_rows + NT - 1) / NT), NT, smem_k, k);
+    const unsigned rgrid = (unsigned)((fk->n_rows + NT - 1) / NT);
+#define ISL_FROMK_ROWS(UU, MB)                                                                                          \
+    do {                                                                                                               \
+        ISL_CUDA(cudaFuncSetAttribute(k_q1hex_rows_fromK<NT, UU, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k)); \
+        ISL_LAUNCH(h, (k_q1hex_rows_fromK<NT, UU, MB>), rgrid, NT, smem_k, k);                                         \
+    } while (0)
+    switch (h->fromk_variant) {   // loads in flight per thread against warps per SM (ISL_FROMK_VARIANT, tuning)
+        case 1: ISL_FROMK_ROWS(2, 6); break;
+        case 2: ISL_FROMK_ROWS(1, 7); break;
+        case 3: ISL_FROMK_ROWS(2, 5); break;
+        case 4: ISL_FROMK_ROWS(8, 4); break;
+        default: ISL_FROMK_ROWS(4, 5); break;
+    }
+#undef ISL_FROMK_ROWS
 }
 
 template <bool MATRIX>
@@ -1990,6 +2005,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_ROWS_THREADS")) h->rows_threads = atoi(m);
         if (const char* m = getenv("ISL_FROMK_PIPELINE")) h->fromk_pipeline = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_PIPE_ROWS")) h->pipe_rows = std::max(1024, atoi(m));
+        if (const char* m = getenv("ISL_FROMK_VARIANT")) h->fromk_variant = atoi(m);
         if (const char* m = getenv("ISL_PATCH_ROWS")) h->patch_rows = std::max(16, atoi(m));
         if (const char* m = getenv("ISL_PATCH_STRETCH")) h->patch_stretch = std::max(0.125, std::min(64.0, atof(m)));
         if (const char* m = getenv("ISL_PATCH_THREADS")) h->patch_threads = atoi(m) == 128 ? 128 : 256;
@@ -2298,6 +2314,30 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
             return;
         }
         if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+    });
+}
+
+int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int quad_deg, int t, int c, int incremental) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+        ISL_REQUIRE(t >= 0 && t < 5 && c >= 0 && c < 5, "field index out of range");
+        ISL_REQUIRE(kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE, "sampled material factors: Laplace kernels only");
+        ISL_REQUIRE(values != nullptr, "no conductivity values");
+        require_live_system(h);
+        flush_pending(h);
+        ensure_pair(h, t, c);
+        check_kernel_fields(h, kid, t, c, true);
+        AsmParams p; std::memset(&p, 0, sizeof(p));
+        fill_common(h, p, quad_deg, t, c);
+        materialize_zero(h);
+        h->val_is_zero = false;
+        DevBuf<double> kq;   // host or device pointer
+        upload(h, kq, values, (size_t)h->n_owned * p.nq);
+        p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental; p.kq = kq.p;
+        p.need_gt = 1; p.need_gc = 1; p.nqdata = 0;
+        if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+        ISL_CUDA(cudaStreamSynchronize(h->stream));   // kq is released when this function returns
     });
 }
 

@@ -158,19 +158,19 @@ __device__ __forceinline__ void fk_element(const FromKParams& p, int64_t t, int6
 
 // the 27 stencil entries and the body-force integral of row r gathered from K; COL maps a sorted element position to its
 // column of K.  CG: loads bypass L1 (the producer CTAs of the pipelined kernel write K while this SM may hold stale lines)
-template <bool CG, class COL>
+template <bool CG, int U = 4, class COL>
 __device__ __forceinline__ void fk_gather_row(const FromKParams& p, int64_t r, int64_t kstride, COL&& col, double (&acc)[27], double& body) {
     const int4 q0 = __ldg(reinterpret_cast<const int4*>(p.row_pos + r * 8));
     const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.row_pos + r * 8) + 1);
     const int pos[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    // four slots at a time: 32 independent coalesced loads are in flight before the first is used (rows without an
+    // U slots at a time: 8 U independent coalesced loads are in flight before the first is used (rows without an
     // element in a slot read some valid column with weight zero, so that no load hides behind a branch)
 #pragma unroll
-    for (int h4 = 0; h4 < 2; h4++) {
-        double v[4][8];
+    for (int h4 = 0; h4 < 8 / U; h4++) {
+        double v[U][8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int a = h4 * 4 + u;
+        for (int u = 0; u < U; u++) {
+            const int a = h4 * U + u;
             const double* kc = p.K + col(pos[a]);
 #pragma unroll
             for (int b = 0; b < 8; b++) {
@@ -179,8 +179,8 @@ __device__ __forceinline__ void fk_gather_row(const FromKParams& p, int64_t r, i
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int a = h4 * 4 + u;
+        for (int u = 0; u < U; u++) {
+            const int a = h4 * U + u;
             const double wgt = pos[a] >= 0 ? 1.0 : 0.0;
 #pragma unroll
             for (int b = 0; b < 8; b++) {
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(128) k_q1hex_elemK(const FromKParams p) {
     fk_element<false>(p, t, t, p.n_elems);
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k_q1hex_rows_fromK(const FromKParams p) {
+template <int NT, int U = 4, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_fromK(const FromKParams p) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* st = smem + (size_t)warp * RG_STAGE;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT) k_q1hex_rows_fromK(const FromKParams p) {
     if (act) {
         rg_load_meta(m, p.meta + r);
         double body = 0.;
-        fk_gather_row<false>(p, r, p.n_elems, [](int t) { return (int64_t)max(t, 0); }, acc, body);
+        fk_gather_row<false, U>(p, r, p.n_elems, [](int t) { return (int64_t)max(t, 0); }, acc, body);
         rg_rhs(p.r, m, acc, body);
     }
     if (p.matrix) {
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(128, 3) k_q1hex_pipeline(const PipeParams q) {
                     (void)NC;
                     return (int64_t)(cc % slots) * cap + ((int64_t)t - eb[cc]);
                 };
-                fk_gather_row<true>(p, r, kstride, col, acc, body);
+                fk_gather_row<true, 4>(p, r, kstride, col, acc, body);
                 rg_rhs(p.r, m, acc, body);
             }
             if (p.matrix) {

@@ -37,7 +37,7 @@ EXPORTED = [
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
-    "isl_assemble_matrix", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
+    "isl_assemble_matrix", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
     "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange", "isl_distribute", "isl_field_get_values",
@@ -289,6 +289,11 @@ class Engine:
     def stiffness_matrix_computation(self, kernel_id, params, quad_deg, test, trial, incremental=True):
         params = self._params(kernel_id, params)
         _chk(lib().isl_assemble_matrix(self.h, kernel_id, _ptr(params), quad_deg, test, trial, int(incremental)))
+
+    def stiffness_matrix_computation_sampled(self, kernel_id, values, quad_deg, test, trial, incremental=True):
+        """asmb::stiffnessMatrixComputation with heat::Laplace + conductivity function: values [n_elems, nq] at the points"""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        _chk(lib().isl_assemble_matrix_sampled(self.h, kernel_id, _ptr(values), quad_deg, test, trial, int(incremental)))
 
     def compute_residual_forces(self, kernel_id, params, quad_deg, test, trial, factor=-1.0):
         params = self._params(kernel_id, params)

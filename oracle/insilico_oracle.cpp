@@ -1298,8 +1298,10 @@ static void assembleForces(const std::vector<double>& f, const std::vector<uint8
 }
 
 // asmb/StiffnessMatrix.hpp:159-225
+// sampled != nullptr: heat::Laplace with a conductivity function (heat/Laplace.hpp:85-126): the factor of the Laplace kernel
+// at quadrature point g of element e is sampled[e * nq + g] (the caller evaluated its function there)
 static void stiffnessElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
-                             int trialId, bool incremental, int64_t e) {
+                             int trialId, bool incremental, int64_t e, const double* sampled = nullptr) {
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
     std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
@@ -1310,7 +1312,10 @@ static void stiffnessElement(const Problem& p, System& solver, const Quad& q, in
     else doSomething = collectFromDoFs(trial, e, cS, cID, cV, cCon, incremental);
     if (!doSomething) return;
     LocalMat K; K.nr = (int)rID.size(); K.nc = (int)cID.size(); K.a.assign((size_t)K.nr * K.nc, 0.);
-    for (int g = 0; g < q.n; g++) tangentKernel(kid, params, t, &q.p[g * q.dim], q.w[g], K);  // Quadrature.hpp:132-141
+    for (int g = 0; g < q.n; g++) {  // Quadrature.hpp:132-141
+        if (sampled) { const double kq = sampled[(size_t)e * q.n + g]; tangentKernel(kid, &kq, t, &q.p[g * q.dim], q.w[g], K); }
+        else tangentKernel(kid, params, t, &q.p[g * q.dim], q.w[g], K);
+    }
     assembleMatrix(K, rS, cS, rID, cID, cV, rCon, cCon, solver);
 }
 
@@ -1521,6 +1526,14 @@ int orc_stiffness(void* s, void* h, int kid, const double* params, int quadDeg, 
 #pragma omp parallel for num_threads(nthreads)
 #endif
     for (int64_t e = 0; e < p.mesh.nElems; e++) stiffnessElement(p, sys, q, kid, params, test, trial, incremental != 0, e);
+    return sys.error.empty() ? 0 : -1;
+}
+// heat::Laplace with setConductivityFunction (heat/Laplace.hpp:85-126): values [nElems][nq] = conductivity at the points
+int orc_stiffness_sampled(void* s, void* h, int kid, const double* values, int quadDeg, int test, int trial, int incremental) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    if (kid != K_LAPLACE && kid != K_VECTOR_LAPLACE) { sys.error = "sampled factors: Laplace kernels only"; return -1; }
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) stiffnessElement(p, sys, q, kid, nullptr, test, trial, incremental != 0, e, values);
     return sys.error.empty() ? 0 : -1;
 }
 // asmb/ForceIntegrator.hpp:37-71 (factor -1, serial loop)

@@ -232,6 +232,11 @@ class System:
         self._check(lib().orc_stiffness(self.h, prob.h, kid, _p(params), quad_deg, test, trial, int(incremental),
                                         nthreads))
 
+    def stiffness_sampled(self, prob, kid, values, quad_deg, test, trial, incremental=True):
+        """heat::Laplace with a conductivity function: values [n_elems, nq] = kappa at the quadrature points"""
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        self._check(lib().orc_stiffness_sampled(self.h, prob.h, kid, _p(values), quad_deg, test, trial, int(incremental)))
+
     def bodyforce_sampled(self, prob, values, quad_deg, test):
         """asmb::bodyForceComputation with a general f(x): values [n_elems, nq, ds] = f at the quadrature points"""
         v = np.ascontiguousarray(values, dtype=np.float64)

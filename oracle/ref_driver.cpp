@@ -143,6 +143,18 @@ struct ConstantForce {
     result_type operator()(const X&) const { return f; }
 };
 
+// conductivity function of the *_kappafun cases (tests/flows.py kappa_fun), evaluated by the reference at every
+// quadrature point through heat::Laplace::setConductivityFunction (heat/Laplace.hpp:85-97)
+template <typename GEOMELEMENT>
+struct NamedConductivity {
+    typedef typename base::GeomTraits<GEOMELEMENT>::LocalVecDim LocalVecDim;
+    double operator()(const GEOMELEMENT* gep, const LocalVecDim& xi) const {
+        const typename base::GeomTraits<GEOMELEMENT>::GlobalVecDim x = base::Geometry<GEOMELEMENT>()(gep, xi);
+        const unsigned dim = base::GeomTraits<GEOMELEMENT>::globalDim;
+        return 1.0 + x[0] * x[0] + 0.5 * std::sin(3.0 * x[1]) * x[dim - 1];
+    }
+};
+
 // the non-constant body forces of tests/flows.py ("bodyfun" operations), by name
 template <unsigned DS, unsigned DIM>
 struct NamedForce {
@@ -292,6 +304,16 @@ int runSingle(const Job& job) {
                 base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
                 continue;
             }
+            if (op.what == "matrixfun") {   // heat::Laplace with a conductivity function
+                if constexpr (KIND == SCALAR) {
+                    typedef heat::Laplace<typename FTB::Tuple> Kernel;
+                    Kernel kernel(1.0);
+                    typename Kernel::ConductivityFun cf = NamedConductivity<typename Mesh::Element>();
+                    kernel.setConductivityFunction(cf);
+                    base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                }
+                continue;
+            }
             if constexpr (KIND == SCALAR) {
                 heat::Laplace<typename FTB::Tuple> kernel(op.p[0]);
                 if (op.what == "matrix")
@@ -426,6 +448,7 @@ int main(int argc, char* argv[]) {
     if (t == "laplace_q1_hex") return runSingle<base::HEX, 1, 1, 3, 3, SCALAR>(job);
     if (t == "laplace_q2_hex") return runSingle<base::HEX, 2, 1, 4, 4, SCALAR>(job);
     if (t == "laplace_p1_tet") return runSingle<base::TET, 1, 1, 3, 2, SCALAR>(job);
+    if (t == "laplace_p2_tet") return runSingle<base::TET, 2, 1, 4, 4, SCALAR>(job);
     if (t == "laplace_q1_quad") return runSingle<base::QUAD, 1, 1, 3, 3, SCALAR>(job);
     if (t == "laplace_p2_tri") return runSingle<base::TRI, 2, 1, 4, 4, SCALAR>(job);
     if (t == "vector_laplace_q1_hex") return runSingle<base::HEX, 1, 3, 3, 3, VECTOR>(job);

@@ -76,6 +76,13 @@ class Case:
                                 values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1, linear=lin))
         return len(self.fields) - 1
 
+    def sampled_factor(self, op):
+        """kappa(x) of a ("matrixfun", kid, fun, quad_deg, t, c, incremental) operation at the quadrature points [n_elems, nq]"""
+        w, xi = E.quadrature(self.shape, op[3])
+        Ng = np.array([E.shape_eval(self.shape, self.geom_deg, p)[0] for p in xi])
+        x = np.einsum("qa,ead->eqd", Ng, self.coords[self.conn])
+        return np.ascontiguousarray(np.asarray(op[2](x.reshape(-1, self.dim)), dtype=np.float64).reshape(len(self.conn), len(w)))
+
     def sampled_force(self, op):
         """f(x) of a ("bodyfun", fun, quad_deg, field) operation at the quadrature points of every element
         [n_elems, nq, ds]; x(xi_q) = sum_a N_a(xi_q) x_a like base::Geometry (base/geometry.hpp:105-135)"""
@@ -119,11 +126,13 @@ class Case:
         s = orc.System(self.n_eqn)
         if register:
             for op in self.ops:
-                if op[0] == "matrix":
+                if op[0] in ("matrix", "matrixfun"):
                     s.register_fields(prob, op[4], op[5])
         for op in self.ops:
             if op[0] == "matrix":
                 s.stiffness(prob, op[1], op[2], op[3], op[4], op[5], incremental=op[6], nthreads=nthreads)
+            elif op[0] == "matrixfun":
+                s.stiffness_sampled(prob, op[1], self.sampled_factor(op), op[3], op[4], op[5], incremental=op[6])
             elif op[0] == "residual":
                 s.residual(prob, op[1], op[2], op[3], op[4], op[5])
             elif op[0] == "body":
@@ -146,11 +155,13 @@ class Case:
         eng.new_solver(self.n_eqn)
         if register:
             for op in self.ops:
-                if op[0] == "matrix":
+                if op[0] in ("matrix", "matrixfun"):
                     eng.register_fields(op[4], op[5])
         for op in self.ops:
             if op[0] == "matrix":
                 eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+            elif op[0] == "matrixfun":
+                eng.stiffness_matrix_computation_sampled(op[1], self.sampled_factor(op), op[3], op[4], op[5], incremental=op[6])
             elif op[0] == "residual":
                 eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5])
             elif op[0] == "body":
@@ -185,6 +196,11 @@ def linear_constraints(status, ds, count=4):
 
 def smooth_u(dim, amp=0.02):
     return lambda x: amp * np.sin(np.pi * x[:, :dim]) * (1.0 + x[:, ::-1][:, :dim])
+
+
+def kappa_fun(x):
+    """the conductivity function of the *_kappafun cases (also in oracle/ref_driver.cpp, NamedConductivity "kappa1")"""
+    return 1.0 + x[:, 0] ** 2 + 0.5 * np.sin(3.0 * x[:, 1]) * x[:, x.shape[1] - 1]
 
 
 def build_case(name, n=4, perturb=True, permute=False):
@@ -268,6 +284,12 @@ def build_case(name, n=4, perturb=True, permute=False):
                  ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u, True),
                  ("residual", E.K_VECTOR_LAPLACE, [1.0], 4, u, u), ("residual", E.K_PRESSURE_GRADIENT, None, 4, u, p),
                  ("residual", E.K_VELOCITY_DIVERGENCE, [0.0], 4, p, u)]
+    elif name in ("laplace_q1_hex_kappafun", "laplace_p2_tet_kappafun"):
+        # heat::Laplace with a conductivity FUNCTION (heat/Laplace.hpp:85-126): kappa(x) evaluated per quadrature point
+        shape, deg, q = (E.HEX, 1, 3) if "hex" in name else (E.TET, 2, 4)
+        c = Case(shape, 1, *make_mesh(shape, n, perturb, permute))
+        c.add_field(deg, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), values=lambda x: 0.3 * x[:, :1] + 0.1)
+        c.ops = [("matrixfun", E.K_LAPLACE, kappa_fun, q, 0, 0, True), ("body", [1.0], q, 0)]
     elif name == "mass_q1_hex":       # M/dt + K of an implicit heat step: base::kernel::Mass + heat::Laplace into one matrix
         c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
         c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), values=lambda x: 0.3 * x[:, :1] + 0.1)

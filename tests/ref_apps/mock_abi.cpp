@@ -29,6 +29,7 @@ int orc_residual(void*, void*, int, const double*, int, int, int);
 int orc_bodyforce(void*, void*, const double*, int, int);
 int orc_bodyforce_sampled(void*, void*, const double*, int, int);
 int orc_insert_lhs(void*, const double*, const int64_t*, int, const int64_t*, int);
+int orc_stiffness_sampled(void*, void*, int, const double*, int, int, int, int);
 int orc_insert_rhs(void*, const double*, const int64_t*, int);
 void orc_finish(void*);
 int64_t orc_nnz(void*);
@@ -136,6 +137,10 @@ int isl_pattern_register(isl_handle h, int t, int c) { orc_register_fields(h->sy
 int isl_assemble_matrix(isl_handle h, int kid, const double* p, int q, int t, int c, int incr) {
     g_calls[0]++;
     return orc_stiffness(h->sys, h->prob, kid, p, q, t, c, incr, 1) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int q, int t, int c, int incr) {
+    g_calls[0]++;
+    return orc_stiffness_sampled(h->sys, h->prob, kid, values, q, t, c, incr) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_assemble_residual(isl_handle h, int kid, const double* p, int q, int t, int c, double factor) {
     g_calls[1]++;

@@ -50,6 +50,9 @@ CASES = [
     ("stvenant_q2_quad_n4", "stvenant_q2_quad", "solid_q2_quad", 4, True, False, True),
     ("laplace_p1_tri_n6", "laplace_p1_tri", "laplace_p1_tri", 6, True, True, False),
     ("stvenant_p2_tet_n3", "stvenant_p2_tet", "solid_p2_tet", 3, True, False, False),
+    # heat::Laplace with a conductivity function kappa(x) (setConductivityFunction, heat/Laplace.hpp:85-126)
+    ("laplace_q1_hex_kappafun_n4", "laplace_q1_hex_kappafun", "laplace_q1_hex", 4, True, False, False),
+    ("laplace_p2_tet_kappafun_n3", "laplace_p2_tet_kappafun", "laplace_p2_tet", 3, True, True, False),
     # base::kernel::Mass next to a stiffness matrix (the system of an implicit time step / a reaction term)
     ("mass_q1_hex_n4", "mass_q1_hex", "laplace_q1_hex", 4, True, False, False),
     ("mass_p2_tet_vector_n3", "mass_p2_tet_vector", "solid_p2_tet", 3, True, True, False),
@@ -108,6 +111,8 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
         if op[0] == "matrix":
             lines.append("op matrix %s %d %d %d %s" % (KERNEL_NAME[op[1]], op[4], op[5], int(op[6]),
                                                        " ".join("%.17g" % p for p in op[2])))
+        elif op[0] == "matrixfun":
+            lines.append("op matrixfun kappa1 %d %d %d" % (op[4], op[5], int(op[6])))
         elif op[0] == "residual":
             lines.append("op residual %s %d %d 1 %s" % (KERNEL_NAME[op[1]], op[4], op[5],
                                                         " ".join("%.17g" % p for p in op[2])))
