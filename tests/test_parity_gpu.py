@@ -30,6 +30,8 @@ CASES = [
     # reduction) on the structured mesh and through the two-kernel general path on the perturbed one
     ("mass_q1_hex", 7, False, False), ("mass_q1_hex", 6, True, True), ("mass_p2_tet_vector", 3, True, True),
     ("stvenant_q2_hex", 3, True, True), ("stvenant_p2_tet", 3, True, True),
+    # heat::Laplace with a conductivity function sampled per quadrature point (isl_assemble_matrix_sampled)
+    ("laplace_q1_hex_kappafun", 6, True, True), ("laplace_p2_tet_kappafun", 3, True, False),
 ]
 
 
