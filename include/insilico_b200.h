@@ -164,6 +164,12 @@ int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_r
 int isl_finish(isl_handle h, int64_t* n_eqn, int64_t* nnz);
 /* canonical CSR (rows ascending, columns ascending, explicit zeros kept) + rhs; NULL pointers are skipped   */
 int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double* rhs);
+/* the same hand-off without waiting: values and rhs of the finished system go to PINNED host buffers on a copy stream
+ * while the engine already assembles the next system into a second set of buffers (the caller's next call must be
+ * isl_system_create); isl_copy_wait blocks until the last such copy has arrived.  For callers that insist on a host CSR
+ * per step the device -> host copy then overlaps the next step's host -> device copies and kernels.              */
+int isl_get_csr_async(isl_handle h, double* val, double* rhs);
+int isl_copy_wait(isl_handle h);
 /* zero-copy hand-off to a device solver: device pointers valid until the next create/register call         */
 int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs);
 /* solver.getValue(i), solver.norm() (Eigen3.hpp:293-296,128-138; norm = ||b||_2 / n, quirk kept)            */

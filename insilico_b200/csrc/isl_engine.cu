@@ -820,6 +820,10 @@ struct isl_engine {
     // system
     int64_t n_eqn = -1, nnz = 0;
     DevBuf<int64_t> rowptr; DevBuf<int32_t> col; DevBuf<double> val, rhs;
+    // isl_get_csr_async: second set of value / rhs buffers and a copy stream, so that the device -> host copy of a finished
+    // system overlaps the assembly (and the host -> device copies) of the next one
+    DevBuf<double> val_alt, rhs_alt; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_asm = nullptr, ev_copy = nullptr;
+    bool copy_in_flight = false, sys_released = false;
     std::set<std::pair<int, int>> pattern_pairs, sys_pairs;
     std::map<std::pair<int, int>, std::unique_ptr<DevBuf<int32_t>>> slotmaps;
     std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
@@ -911,6 +915,7 @@ void mark_stale_if_touched(isl_engine* h) { if (!h->val_is_zero && h->nnz > 0) h
 void require_live_system(isl_engine* h) {
     ISL_REQUIRE(!h->sys_stale, "mesh or field arrays were replaced after assembly into this system had started, so its entries "
                                "are gone: create a new solver first (one FieldBinder per solver is supported)");
+    ISL_REQUIRE(!h->sys_released, "the system was handed to the host by isl_get_csr_async: create a new solver first");
     if (h->comm) h->comm->iface_event_valid = false;   // set again by the split launch of the Q1 row kernel only
 }
 
@@ -921,6 +926,8 @@ void invalidate_pattern(isl_engine* h) {
     h->fromk_sets.clear();
     h->nnz = 0;
     h->rowptr.release(); h->col.release(); h->val.release();
+    if (h->copy_in_flight && h->ev_copy) cudaEventSynchronize(h->ev_copy);
+    h->val_alt.release(); h->copy_in_flight = false;
 }
 
 void build_elem_eqn(isl_engine* h, FieldDev& f) {
@@ -1838,8 +1845,8 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
         case 1: ISL_FROMK_ROWS(2, 6); break;
         case 2: ISL_FROMK_ROWS(1, 7); break;
         case 3: ISL_FROMK_ROWS(2, 5); break;
-        case 4: ISL_FROMK_ROWS(8, 4); break;
-        default: ISL_FROMK_ROWS(4, 5); break;
+        case 5: ISL_FROMK_ROWS(4, 5); break;
+        default: ISL_FROMK_ROWS(8, 4); break;   // 64 loads in flight per thread, 16 warps per SM: 3.65 ms (4/5: 3.78, 2/6: 4.04, 1/7: 4.51)
     }
 #undef ISL_FROMK_ROWS
 }
@@ -2019,6 +2026,7 @@ int isl_engine_destroy(isl_handle h) {
         cudaSetDevice(h->device);
         cudaStreamSynchronize(h->stream);
         cudaStream_t s = h->stream;
+        if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_asm); cudaEventDestroy(h->ev_copy); }
         delete h;
         cudaStreamDestroy(s);
     });
@@ -2247,7 +2255,7 @@ int isl_system_create(isl_handle h, int64_t n_eqn) {
         if (n_eqn) ISL_CUDA(cudaMemsetAsync(h->rhs.p, 0, n_eqn * sizeof(double), h->stream));
         h->val_zero_pending = true;   // memset of the matrix values postponed, see materialize_zero()
         h->val_is_zero = true;
-        h->sys_stale = false;
+        h->sys_stale = false; h->sys_released = false;
         if (h->ins_err.p) ISL_CUDA(cudaMemsetAsync(h->ins_err.p, 0, sizeof(int), h->stream));
     });
 }
@@ -2477,6 +2485,36 @@ int isl_get_csr(isl_handle h, int64_t* rowptr, int32_t* col, double* val, double
         if (val && h->nnz) ISL_CUDA(cudaMemcpyAsync(val, h->val.p, h->nnz * sizeof(double), cudaMemcpyDefault, h->stream));
         if (rhs && h->n_eqn) ISL_CUDA(cudaMemcpyAsync(rhs, h->rhs.p, h->n_eqn * sizeof(double), cudaMemcpyDefault, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+int isl_get_csr_async(isl_handle h, double* val, double* rhs) {
+    return guarded([&] {
+        ISL_REQUIRE(!h->sys_stale && !h->sys_released, "no finished system to hand over");
+        ISL_CUDA(cudaSetDevice(h->device));
+        flush_pending(h);
+        materialize_zero(h);
+        if (!h->copy_stream) {
+            ISL_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            ISL_CUDA(cudaEventCreateWithFlags(&h->ev_asm, cudaEventDisableTiming));
+            ISL_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        }
+        if (h->val_alt.n != (size_t)h->nnz) h->val_alt.alloc((size_t)h->nnz);
+        if (h->rhs_alt.n != (size_t)h->n_eqn) h->rhs_alt.alloc((size_t)h->n_eqn);
+        // the buffers that come back into use were read by the previous asynchronous copy: the engine stream waits for it
+        if (h->copy_in_flight) ISL_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+        ISL_CUDA(cudaEventRecord(h->ev_asm, h->stream));
+        h->val.swap(h->val_alt); h->rhs.swap(h->rhs_alt);
+        ISL_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_asm, 0));
+        if (val && h->nnz) ISL_CUDA(cudaMemcpyAsync(val, h->val_alt.p, h->nnz * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (rhs && h->n_eqn) ISL_CUDA(cudaMemcpyAsync(rhs, h->rhs_alt.p, h->n_eqn * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        ISL_CUDA(cudaEventRecord(h->ev_copy, h->copy_stream));
+        h->copy_in_flight = true;
+        h->sys_released = true;   // the system now lives in the copy buffers: isl_system_create starts the next one
+    });
+}
+int isl_copy_wait(isl_handle h) {
+    return guarded([&] {
+        if (h->copy_in_flight) ISL_CUDA(cudaEventSynchronize(h->ev_copy));
     });
 }
 int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs) {

@@ -2,8 +2,8 @@
 // isl_solver.cuh -- conjugate gradients on the device for the finished CSR system (the linear-solve
 // hand-off; reference: base::solver::Eigen3::cgSolve, base/solver/Eigen3.hpp:263-275 = Eigen::ConjugateGradient with
 // its default diagonal preconditioner, tolerance = machine epsilon, at most 2 n iterations, zero initial guess).
-// Included by isl_engine.cu inside its anonymous namespace.  NOT YET RUN ON A GPU (written in a session without GPU
-// minutes): entry point isl_solve_cg, test gated by ISL_TEST_EXPERIMENTAL=1.
+// Included by isl_engine.cu inside its anonymous namespace.  Entry point isl_solve_cg; GPU-verified against a sparse direct
+// solve and inside the device-resident Newton loop (tests/test_zz_linear_constraints.py).
 //
 // HBM-bound: per iteration one pass over the matrix (12 B per non-zero + the gathered vector) and ~9 vector passes.
 // One warp per row for the product (rows hold 27..375 non-zeros), warp-shuffle reductions, one atomicAdd per warp.
@@ -19,21 +19,40 @@ __global__ void k_cg_diag_inv(const int64_t* rowptr, const int32_t* col, const d
     }
 }
 
-// y = A x and *dot += x . y ; one warp per row
+// y = A x and *dot += x . y ; LPR lanes per row (8 for short rows: four rows per warp are in flight, which is what hides
+// the three dependent loads rowptr -> col / val -> x[col]; one warp per row was measured at 5.4 ms per product of the
+// 256^3 Laplace matrix, 5x its HBM time)
+template <int LPR>
 __global__ void __launch_bounds__(256) k_cg_spmv_dot(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                      const double* __restrict__ val, const double* __restrict__ x,
                                                      double* __restrict__ y, int64_t n, double* dot) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int sub = threadIdx.x % LPR;
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / LPR;
     double acc = 0.;
-    for (int64_t r = warp; r < n; r += nwarps) {
-        double s = 0.;
-        for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) s += val[k] * x[col[k]];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) { y[r] = s; acc += x[r] * s; }
+    const int64_t trips = (n + 2 * ngrp - 1) / (2 * ngrp);   // the same for every thread: the shuffles below need whole warps
+    for (int64_t it = 0; it < trips; it++) {                 // two rows per group and trip: more loads in flight
+        const int64_t ra = grp + it * 2 * ngrp, rb = ra + ngrp;
+        double sa = 0., sb = 0.;
+        const int64_t a0 = ra < n ? rowptr[ra] : 0, a1 = ra < n ? rowptr[ra + 1] : 0;
+        const int64_t b0 = rb < n ? rowptr[rb] : 0, b1 = rb < n ? rowptr[rb + 1] : 0;
+        for (int64_t k = a0 + sub, j = b0 + sub; k < a1 || j < b1; k += LPR, j += LPR) {   // (no shuffles inside: may diverge)
+            if (k < a1) sa += val[k] * x[col[k]];
+            if (j < b1) sb += val[j] * x[col[j]];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            sa += __shfl_down_sync(0xffffffffu, sa, o, LPR);
+            sb += __shfl_down_sync(0xffffffffu, sb, o, LPR);
+        }
+        if (sub == 0) {
+            if (ra < n) { y[ra] = sa; acc += x[ra] * sa; }
+            if (rb < n) { y[rb] = sb; acc += x[rb] * sb; }
+        }
     }
-    if (lane == 0 && acc != 0.) atomicAdd(dot, acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc != 0.) atomicAdd(dot, acc);
 }
 
 // x += alpha p ; r -= alpha Ap ; out[0] += r.r ; out[1] += r.(dinv r)
@@ -67,7 +86,7 @@ int64_t solve_cg(isl_engine* h, double tol, int64_t max_iter, double* error) {
     if (max_iter <= 0) max_iter = 2 * n;
     DevBuf<double> x, r, p, Ap, dinv, sc;
     x.alloc(n); r.alloc(n); p.alloc(n); Ap.alloc(n); dinv.alloc(n); sc.alloc(2);
-    const int g = h->grid_for(n, 256), gw = h->grid_for(n * 32, 256);
+    const int g = h->grid_for(n, 256), gw = h->grid_for(n * 16, 256), gw8 = h->grid_for(n * 4, 256);
     auto scalars = [&](double* out, int cnt) {
         ISL_CUDA(cudaMemcpyAsync(out, sc.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
@@ -96,7 +115,8 @@ int64_t solve_cg(isl_engine* h, double tol, int64_t max_iter, double* error) {
         ISL_LAUNCH(h, k_cg_update_p, g, 256, 0, 0.0, dinv.p, r.p, p.p, n);   // p = z
         while (it < max_iter) {
             ISL_CUDA(cudaMemsetAsync(sc.p, 0, 2 * sizeof(double), h->stream));
-            ISL_LAUNCH(h, k_cg_spmv_dot, gw, 256, 0, h->rowptr.p, h->col.p, h->val.p, p.p, Ap.p, n, sc.p);
+            if (h->nnz / n <= 48) ISL_LAUNCH(h, k_cg_spmv_dot<8>, gw8, 256, 0, h->rowptr.p, h->col.p, h->val.p, p.p, Ap.p, n, sc.p);
+            else ISL_LAUNCH(h, k_cg_spmv_dot<32>, gw, 256, 0, h->rowptr.p, h->col.p, h->val.p, p.p, Ap.p, n, sc.p);
             double pAp;
             scalars(&pAp, 1);
             ISL_REQUIRE(pAp != 0. && pAp == pAp, "conjugate gradients broke down (p.Ap = 0 or NaN): matrix not s.p.d.?");

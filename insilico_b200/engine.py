@@ -39,7 +39,7 @@ EXPORTED = [
     "isl_system_create", "isl_pattern_register",
     "isl_assemble_matrix", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
-    "isl_finish", "isl_get_csr", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
+    "isl_finish", "isl_get_csr", "isl_get_csr_async", "isl_copy_wait", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
     "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange", "isl_distribute", "isl_field_get_values",
 ]
 
@@ -335,6 +335,13 @@ class Engine:
             rhs = np.zeros(n)
         _chk(lib().isl_get_csr(self.h, _ptr(rowptr), _ptr(col), _ptr(val), _ptr(rhs)))
         return rowptr, col, val, rhs
+
+    def get_csr_async(self, val, rhs):
+        """values / rhs of the finished system -> pinned host arrays on the copy stream; the next call must be new_solver"""
+        _chk(lib().isl_get_csr_async(self.h, _ptr(val), _ptr(rhs)))
+
+    def copy_wait(self):
+        _chk(lib().isl_copy_wait(self.h))
 
     def cg_solve(self, tol=0.0, max_iter=0):
         """solver.cgSolve() on the device (base/solver/Eigen3.hpp:263-275): rhs <- A^-1 rhs; returns (iterations, error)"""

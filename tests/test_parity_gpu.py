@@ -126,6 +126,40 @@ def test_solver_interface_odd_contributions_and_norm(eng):
         eng.insert_to_rhs(np.array([1.0]), np.array([c.n_eqn]))
 
 
+def test_asynchronous_hand_off_double_buffers_the_system(eng):
+    """isl_get_csr_async: values / rhs of step k arrive in pinned host buffers while step k+1 is assembled into the second
+    set of device buffers; results equal the blocking isl_get_csr, and the released system cannot be used any more"""
+    import torch
+    c = flows.build_case("laplace_q1_hex", 9, perturb=False)
+    f = c.fields[0]
+    eng.set_mesh(c.shape, c.geom_deg, c.coords, c.conn)
+    eng.set_field(0, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+    ref = {}
+    for kappa in (1.0, 2.5, 0.5):
+        eng.new_solver(c.n_eqn)
+        eng.stiffness_matrix_computation(E.K_LAPLACE, [kappa], 3, 0, 0, True)
+        eng.body_force_computation([kappa], 3, 0)
+        ref[kappa] = eng.get_csr()
+    nnz = len(ref[1.0][2])
+    bufs = [(torch.empty(nnz, dtype=torch.float64).pin_memory().numpy(), torch.empty(c.n_eqn, dtype=torch.float64).pin_memory().numpy())
+            for _ in range(3)]
+    for k, kappa in enumerate((1.0, 2.5, 0.5)):
+        eng.new_solver(c.n_eqn)
+        eng.stiffness_matrix_computation(E.K_LAPLACE, [kappa], 3, 0, 0, True)
+        eng.body_force_computation([kappa], 3, 0)
+        eng.get_csr_async(*bufs[k])
+    with pytest.raises(E.EngineError, match="create a new solver"):
+        eng.body_force_computation([1.0], 3, 0)
+    eng.copy_wait()
+    for k, kappa in enumerate((1.0, 2.5, 0.5)):
+        assert np.array_equal(bufs[k][0], ref[kappa][2]) and np.array_equal(bufs[k][1], ref[kappa][3])
+    eng.new_solver(c.n_eqn)
+    eng.stiffness_matrix_computation(E.K_LAPLACE, [1.0], 3, 0, 0, True)
+    eng.body_force_computation([1.0], 3, 0)
+    out = eng.get_csr()
+    assert np.array_equal(out[2], ref[1.0][2]) and np.array_equal(out[3], ref[1.0][3])
+
+
 def test_fields_replaced_during_assembly_is_an_error(eng):
     """isl_field_set / isl_mesh_set drop the pattern and the values; when that happens between two assembly
     calls on one solver (a second FieldBinder, a rebuilt binder) the system must not silently continue empty"""
