@@ -457,9 +457,31 @@ def bench_config(args, rank, world, local_rank, cores):
                 line["cpu_baseline"] = cb
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("cpu_baseline failed: %r\n" % (e,))
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries loaded later (NCCL prints its version banner on stdout when a
+    communicator or a unique id is made) must not get at it: file descriptor 1 is pointed at stderr for the whole run and
+    the result line is written to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(text):
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        sys.stdout.write(text + "\n"); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, (text + "\n").encode())
 
 
 def main():
@@ -478,6 +500,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.n_given, args.cpu_sample_given = args.n is not None, args.cpu_sample is not None
     if args.n is None:
         args.n = 256
@@ -498,9 +521,9 @@ def main():
         if args.config != "C2":
             cb, ms = config_cpu_baseline(args.config, ns if args.cpu_sample_given else CPU_SAMPLE_N[args.config], max(1, min(args.steps, 3)), cores)
             if cb is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
+                emit_line(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver_omp missing or failed"}))
                 return
-            print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "elements/s", "n_gpus": args.gpus,
+            emit_line(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "elements/s", "n_gpus": args.gpus,
                               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                               "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": cb["sample"]},
                               "cpu_baseline": cb,
@@ -513,7 +536,7 @@ def main():
                 "config": {"workload": "C2: 3D scalar Laplace Q1 hex structured mesh, stiffness + RHS (CPU sample %d^3)" % ns},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
         return
 
     # ------------------------------------------------------------------------------------------------------ our arm
@@ -768,7 +791,7 @@ def main():
         api = reference_api_on_engine(args.cpu_sample, 3)   # separate process with its own engine on the same device
         if api is not None:
             line["e2e_reference_api"] = api
-    print(json.dumps(line))
+    emit_line(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
