@@ -322,10 +322,23 @@ def bench_config(args, rank, world, local_rank, cores):
             b.record(stream)
             eng.synchronize(); torch.cuda.synchronize()
             extra["ms_per_step_n%d" % ns] = a.elapsed_time(b) / args.steps
-    w = workloads.build(cfg, n)
-    ne_global = len(w.conn)
+    slab = cfg == "C5" and world > 1 and args.partition != "blocks"
+    if slab:
+        # the mesh is generated per rank in closed form: no rank ever holds the global mesh (50 M tetrahedra would not fit
+        # the host-side numbering of workloads.build in reasonable time); the tiny workload only carries the operations
+        w = workloads.build(cfg, 2)
+        wl = partition.structured_stokes_slab(n, rank, world)
+        w.n_eqn, w.n_elems_global, w.n_nodes_global = wl["n_eqn_global"], wl["n_elems_global"], (n + 1) ** 3
+        w.description = w.description.replace("6*2^3", "6*%d^3" % n) + "; mesh and numbering generated per rank (z-slabs)"
+        ne_global = wl["n_elems_global"]
+    else:
+        w = workloads.build(cfg, n)
+        ne_global = len(w.conn)
     part = None
-    if world > 1:
+    if slab:
+        part = partition.GeneralDistributedAssembly(eng, wl, rank, world, w.shape, w.geom_deg)
+        n_eqn, ne_rank = wl["n_eqn_local"], wl["n_owned_elems"]
+    elif world > 1:
         wl = partition.general_partition(w.coords, w.conn, w.fields, w.n_eqn, rank, world)
         part = partition.GeneralDistributedAssembly(eng, wl, rank, world, w.shape, w.geom_deg)
         n_eqn, ne_rank = wl["n_eqn_local"], wl["n_owned_elems"]
@@ -442,7 +455,8 @@ def bench_config(args, rank, world, local_rank, cores):
             "kernel_ms": t_asm * 1e3, "per_op_ms": [{"op": o[0], "kernel": KERNEL_NAME.get(o[1], "body") if o[0] != "body" else "body", "ms": t} for o, t in zip(w.ops, per_op)],
             "hbm": hbm, "fp64": f64}
     cfgd = {"workload": w.description, "n": n, "n_elems": int(ne_global), "n_eqn": int(w.n_eqn), "nnz_per_gpu": int(nnz),
-            "partition": "element blocks along a Z-curve, owned rows, NCCL ghost-row exchange" if world > 1 else "single GPU",
+            "partition": ("z-slabs of cube layers generated per rank, owned rows, NCCL ghost-row exchange" if slab else
+                          "element blocks along a Z-curve, owned rows, NCCL ghost-row exchange") if world > 1 else "single GPU",
             "l2": "arrays touched per step: %.2f GB (%s L2)" % (nbytes * ne_rank / 1e9, "larger than" if nbytes * ne_rank > 126e6 else "inside"),
             "register_fields_ms": t_register * 1e3}
     cfgd.update(extra)
@@ -497,6 +511,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None, help="edge length of the CPU-baseline sample mesh")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="C2 on N GPUs: weak = n^3 elements per GPU (default, the driver's scaling run), strong = one n^3 mesh cut into N slabs")
+    ap.add_argument("--partition", default="auto", choices=["auto", "blocks", "slab"],
+                    help="C5 on N GPUs: slab (default) generates each rank's z-slab directly; blocks cuts one global mesh along a Z-curve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -464,3 +464,104 @@ class GeneralDistributedAssembly:
         self.eng.flush()   # see DistributedAssembly.exchange
         with torch.cuda.stream(self.stream):
             self.plan.exchange(self.val, self.rhs, add_fn=self._add)
+
+
+# ---- Taylor-Hood Stokes on a cube of tetrahedra, cut into z-slabs, generated per rank ---------------------------------
+def _unit_hash(ids, salt):
+    """deterministic value in [-1, 1) per integer id: every rank perturbs a shared vertex identically"""
+    x = (ids.astype(np.uint64) + np.uint64(salt)) * np.uint64(0x9E3779B97F4A7C15)
+    x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return (x >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
+
+def structured_stokes_slab(n, rank, world, perturb=0.1, permute=True, seed=54321):
+    """Local workload of `rank` for the driven-cavity blocks (reference/07-drivenCavity/drivenCavity.cpp:176-275) on
+    6 n^3 tetrahedra (every cube of the n^3 lattice split as unitCube.hpp:107-134), P2 velocity x 3 + P1 pressure, WITHOUT
+    ever building the global mesh: cube layers [z0, z1) are owned, the layer above is the halo, and the numbering is in
+    closed form (velocity DoF objects = points of the (2n+1)^3 half-step lattice, pressure DoF objects = vertices; global
+    equation = lexicographic rank among the ACTIVE DoFs, velocity block first, as numberDoFsConsecutively with the
+    drivenCavity offsets gives for that object order).  Same dict as general_partition(); rows are owned by the lowest
+    rank whose elements touch them, i.e. the slab below owns a shared plane."""
+    from . import engine as E
+    from . import meshgen
+    V, F, m = n + 1, 2 * n + 1, 2 * n - 1
+    bounds = [n * r // world for r in range(world + 1)]
+    z0, z1 = bounds[rank], bounds[rank + 1]
+    assert z1 > z0, "every rank needs at least one cube layer"
+    zc1 = z1 + (1 if rank < world - 1 else 0)        # local cube layers [z0, zc1): owned + one halo layer above
+    layer_rank = np.searchsorted(np.asarray(bounds[1:]), np.arange(n), side="right")
+
+    # vertices of the local layers, lexicographic, and their (perturbed) positions
+    kv = np.arange(z0, zc1 + 1)
+    gi, gj, gk = np.meshgrid(np.arange(V), np.arange(V), kv, indexing="ij")
+    order3 = lambda a: np.ascontiguousarray(a.transpose(2, 1, 0)).reshape(-1)     # x fastest
+    vi, vj, vk = order3(gi), order3(gj), order3(gk)
+    coords = np.stack([vi, vj, vk], axis=1).astype(np.float64) / n
+    if perturb:
+        gid = vi + V * (vj + V * vk.astype(np.int64))
+        interior = (vi > 0) & (vi < n) & (vj > 0) & (vj < n) & (vk > 0) & (vk < n)
+        d = np.stack([_unit_hash(gid, 11 + c) for c in range(3)], axis=1)
+        nrm = np.linalg.norm(d, axis=1, keepdims=True)
+        d = d / np.maximum(nrm, 1e-300) * (_unit_hash(gid, 17)[:, None] * (perturb / n))
+        coords[interior] += d[interior]
+    # tetrahedra: integer vertex coordinates [ne, 4, 3]
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(z0, zc1), indexing="ij")
+    cube = np.stack([order3(ci), order3(cj), order3(ck)], axis=1)                  # [nc, 3], layer slowest
+    corner = np.array([[c & 1, (c >> 1) & 1, c >> 2] for c in range(8)])
+    tets = corner[meshgen._H_HEX[meshgen._TETS]]                                   # [6, 4, 3] offsets inside the cube
+    vint = (cube[:, None, None, :] + tets[None]).reshape(-1, 4, 3)                 # [6 nc, 4, 3]
+    n_owned = 6 * n * n * (z1 - z0)
+    if permute:
+        rng = np.random.default_rng(seed + rank)
+        p = np.concatenate([rng.permutation(n_owned), np.arange(n_owned, len(vint))])
+        vint = vint[p]
+    conn = (vint[..., 0] + V * (vint[..., 1] + V * (vint[..., 2] - z0))).astype(np.int32)
+
+    def owner_of_plane(k, half):        # lowest cube layer touching lattice plane k (half-step lattice if half)
+        lay = np.maximum((k - 1) // 2 if half else k - 1, 0)
+        return layer_rank[np.minimum(lay, n - 1)]
+
+    fields, classes, geqs = [], [], []
+    # velocity: support points of the P2 element as combinations of its vertices -> half-step lattice coordinates
+    sp = E.support_points(E.TET, 2)
+    w2 = np.rint(2 * np.array([E.shape_eval(E.TET, 1, s)[0] for s in sp])).astype(np.int64)     # [10, 4], rows sum to 2
+    fint = np.einsum("la,ead->eld", w2, vint.astype(np.int64))                     # [ne, 10, 3]
+    ed_u = (fint[..., 0] + F * (fint[..., 1] + F * (fint[..., 2] - 2 * z0))).astype(np.int32)
+    fk_l = np.arange(2 * z0, 2 * zc1 + 1)
+    fi, fj, fk = [order3(a) for a in np.meshgrid(np.arange(F), np.arange(F), fk_l, indexing="ij")]
+    bnd = (fi == 0) | (fi == 2 * n) | (fj == 0) | (fj == 2 * n) | (fk == 0) | (fk == 2 * n)
+    st = np.zeros((len(fi), 3), dtype=np.uint8); st[bnd] = E.CONSTRAINED
+    presc = np.zeros((len(fi), 3)); presc[fk == 2 * n, 0] = 1.0
+    g = 3 * ((fi - 1) + m * ((fj - 1) + m * (fk.astype(np.int64) - 1)))
+    geq = np.where(bnd[:, None], -1, g[:, None] + np.arange(3)[None])
+    n_u = 3 * m ** 3
+    fields.append(dict(fe_deg=2, ds=3, n_obj=len(fi), elem_dof=np.ascontiguousarray(ed_u), status=st, presc=presc,
+                       values=np.zeros((len(fi), 3))))
+    geqs.append(geq)
+    classes.append(np.broadcast_to(owner_of_plane(fk, True)[:, None], geq.shape))
+    # pressure: one DoF per vertex, vertex 0 pinned
+    gidp = vi + V * (vj + V * vk.astype(np.int64))
+    stp = np.zeros((len(vi), 1), dtype=np.uint8); stp[gidp == 0] = E.CONSTRAINED
+    geqp = np.where(gidp == 0, -1, n_u + gidp - 1)[:, None]
+    fields.append(dict(fe_deg=1, ds=1, n_obj=len(vi), elem_dof=np.ascontiguousarray(conn.copy()), status=stp,
+                       presc=np.zeros((len(vi), 1)), values=np.zeros((len(vi), 1))))
+    geqs.append(geqp)
+    classes.append(owner_of_plane(vk, False)[:, None])
+    # local numbering: owned rows, ghost rows (owned by the slab below), rows only the halo layer touches
+    allg = np.concatenate([q.reshape(-1) for q in geqs])
+    own = np.concatenate([np.asarray(c).reshape(-1) for c in classes])
+    cls = np.where(own == rank, 0, np.where(own < rank, 1, 2))
+    act = np.nonzero(allg >= 0)[0]
+    act = act[np.lexsort((allg[act], cls[act]))]
+    leq = np.full(len(allg), -1, dtype=np.int64); leq[act] = np.arange(len(act))
+    l2g = allg[act]
+    n_own_rows, n_ghost = int((cls[act] == 0).sum()), int((cls[act] == 1).sum())
+    a = 0
+    for f, q in zip(fields, geqs):
+        f["eqn"] = np.ascontiguousarray(leq[a:a + q.size].reshape(q.shape)); a += q.size
+    return dict(coords=coords, conn=np.ascontiguousarray(conn), n_owned_elems=n_owned, fields=fields, l2g=l2g,
+                n_eqn_local=len(l2g), n_owned_rows=n_own_rows, n_ghost_rows=n_ghost,
+                ghost_segments=[(rank - 1, n_own_rows, n_own_rows + n_ghost)] if n_ghost else [],
+                n_eqn_global=int(n_u + V ** 3 - 1), n_elems_global=6 * n ** 3)

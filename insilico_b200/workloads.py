@@ -145,7 +145,8 @@ class Workload:
         """compulsory HBM traffic of one step per element, every array touched once: connectivity,
         element -> DoF tables, element -> CSR slot maps of the matrix operations, and per element its share of the
         unique coordinates, CSR values, right-hand side and field values"""
-        ne = len(self.conn)
+        ne = getattr(self, "n_elems_global", len(self.conn))      # (set when the mesh is generated per rank: partition.structured_stokes_slab)
+        n_nodes = getattr(self, "n_nodes_global", len(self.coords))
         b = self.conn.shape[1] * 4.0
         used = set()
         for op in self.ops:
@@ -159,7 +160,7 @@ class Workload:
                 used.add(op[3])
         for i in used:
             b += self.fields[i]["ndpe"] * 4.0
-        shared = 8.0 * self.dim * len(self.coords) + 8.0 * nnz + 8.0 * self.n_eqn
+        shared = 8.0 * self.dim * n_nodes + 8.0 * nnz + 8.0 * self.n_eqn
         if any(op[0] == "residual" for op in self.ops):
             shared += sum(8.0 * self.fields[i]["n_obj"] * self.fields[i]["ds"] for i in used)
         return b + shared / ne

@@ -18,6 +18,30 @@ from insilico_b200 import partition  # noqa: E402
 from tests import flows  # noqa: E402
 
 
+class _SlabCase:
+    """the whole cube from the same generator (one rank, identity numbering) assembled by the oracle"""
+
+    def __init__(self, n):
+        self.shape, self.geom_deg, self.n = E.TET, 1, n
+        self.ops = [("matrix", E.K_VECTOR_LAPLACE, [1.0], 4, 0, 0, True), ("matrix", E.K_PRESSURE_GRADIENT, [0.0], 4, 0, 1, True),
+                    ("matrix", E.K_VELOCITY_DIVERGENCE, [0.0], 4, 1, 0, True), ("body", [1.0, -2.0, 0.5], 4, 0)]
+        self.n_eqn = 3 * (2 * n - 1) ** 3 + (n + 1) ** 3 - 1
+
+    def run_oracle(self, register=True):
+        from oracle import oracle as orc
+        wl = partition.structured_stokes_slab(self.n, 0, 1, permute=False)
+        p = orc.Problem(self.shape, self.geom_deg, wl["coords"], wl["conn"].astype(np.int64))
+        for i, f in enumerate(wl["fields"]):
+            p.set_field(i, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"].astype(np.int64), f["eqn"], f["status"], f["presc"], f["values"])
+        s = orc.System(wl["n_eqn_local"])
+        for op in self.ops[:3]:
+            s.register_fields(p, op[4], op[5])
+        for op in self.ops[:3]:
+            s.stiffness(p, op[1], op[2], op[3], op[4], op[5], incremental=op[6])
+        s.bodyforce(p, *self.ops[3][1:])
+        return s.finish()
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -31,8 +55,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group(backend)
-    case = flows.build_case(name, n, True, True)
-    wl = partition.general_partition(case.coords, case.conn, case.fields, case.n_eqn, rank, world)
+    if name == "stokes_slab":     # driven-cavity slabs generated per rank (partition.structured_stokes_slab)
+        case = _SlabCase(n)
+        wl = partition.structured_stokes_slab(n, rank, world)
+    else:
+        case = flows.build_case(name, n, True, True)
+        wl = partition.general_partition(case.coords, case.conn, case.fields, case.n_eqn, rank, world)
     eng = E.Engine(local)
     part = partition.GeneralDistributedAssembly(eng, wl, rank, world, case.shape, case.geom_deg)
     eng.new_solver(wl["n_eqn_local"])

@@ -41,13 +41,13 @@ def test_two_ranks_on_one_gpu_slab_assembly(mode):
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
-@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 3), ("laplace_q1_hex", 8)])
+@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 3), ("laplace_q1_hex", 8), ("stokes_slab", 4)])
 def test_two_ranks_on_one_gpu_general_partition(name, n):
     out = _torchrun("dist_check_general.py", [name, n], 29542, ONE_GPU)
     assert out.returncode == 0 and "DIST_CHECK_GENERAL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
-@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 4), ("laplace_q1_hex", 10)])
+@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 4), ("laplace_q1_hex", 10), ("stokes_slab", 5)])
 def test_two_gpu_general_partition_matches_oracle(name, n):
     """general element-block partition (Morton blocks of a permuted mesh, several fields, all-to-all ghost exchange)"""
     import torch
