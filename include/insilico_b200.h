@@ -155,6 +155,40 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int quad_deg, int test
  * of Quadrature<quad_deg> (isl_quadrature gives xi_q; x = sum_a N_a(xi_q) x_a), host or device pointer.  The caller's
  * function runs on the host, the integration on the device.                                                       */
 int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_deg, int test_field);
+/* ---- surface (Neumann) terms ------------------------------------------------------------------------------------
+ * A surface element is what base::mesh::SurfaceElement (base/mesh/SurfaceElement.hpp:93-201) holds: P nodes (P = nodes of
+ * the Lagrange element of the face shape and the mesh's geometry degree) with physical coordinates surf_x[P*dim], the
+ * coordinates of the same nodes in the parameter space of the domain element surf_param[P*dim], and the domain element.
+ *
+ * isl_boundary_surface: base::mesh::generateBoundaryMesh (base/mesh/generateBoundaryMesh.hpp:279-432, no triangulation)
+ * for (element, face number) pairs as isl_mesh_boundary returns them.  Host-side; pass domain_elem = NULL to query
+ * *surf_shape / *nodes_per_surf only.                                                                              */
+int isl_boundary_surface(int shape, int geom_deg, int dim, const double* coords, const int32_t* conn, int64_t n_pairs,
+                         const int64_t* pairs, int32_t* domain_elem, double* surf_x, double* surf_param, int* surf_shape,
+                         int* nodes_per_surf);
+/* what base::asmb::NeumannForce hands to the caller's force function f(x, normal) (base/asmb/NeumannForce.hpp:152-163;
+ * base::SurfaceNormal, base/geometry.hpp:256-346): position, unit normal and surface metric at the points of
+ * SurfaceQuadrature<quad_deg> (base/Quadrature.hpp:148-151) of every surface element.  Host-side; x[n_surf*nq*dim],
+ * normal[n_surf*nq*dim], detg[n_surf*nq], any of them NULL; surf_x = NULL queries *nq only.                          */
+int isl_surface_points(int surf_shape, int geom_deg, int dim, int64_t n_surf, const double* surf_x, int quad_deg, double* x,
+                       double* normal, double* detg, int* nq);
+enum isl_neumann_mode {
+    ISL_NEUMANN_CONSTANT = 0,      /* data[dof_size]: f constant                                                      */
+    ISL_NEUMANN_NORMAL = 1,        /* data[1]: f = data[0] * normal (dof_size == dim), e.g. a pressure load            */
+    ISL_NEUMANN_SAMPLED = 2        /* data[n_surf*nq*dof_size]: f at the surface quadrature points, host or device     */
+};
+/* base::asmb::neumannForceComputation<SFTB>(surfaceQuadrature, solver, surfaceFieldBinder, f)
+ * (base/asmb/NeumannForce.hpp:33-66,140-184; SurfaceFieldBinder.hpp:81-184): rhs += int f(x, n) phi ds over the surface
+ * elements, phi = the test field's shape functions of the domain element at localDomainCoordinate(eta).  One kernel
+ * launch for all surface elements; the caller's function (mode SAMPLED) runs on the host.                              */
+int isl_assemble_neumann(isl_handle h, int64_t n_surf, const int32_t* domain_elem, const double* surf_x, const double* surf_param,
+                         int quad_deg, int test_field, int mode, const double* data);
+/* the same with the equation numbers given per surface element instead of a field index: rows[n_surf * ndpe * dof_size]
+ * (shape function major, < 0: not ACTIVE, skipped), for a caller that reads them off its own element objects (the
+ * reference-tree binding does: SurfaceFieldBinder tuples need not belong to a FieldBinder the engine has seen, so the
+ * shape and geometry degree of the domain elements are arguments and no mesh or field needs to be set)                  */
+int isl_assemble_neumann_rows(isl_handle h, int shape, int geom_deg, int64_t n_surf, const double* surf_x, const double* surf_param,
+                              int quad_deg, int fe_deg, int dof_size, const int32_t* rows, int mode, const double* data);
 /* solver.insertToLHS / insertToRHS (Eigen3.hpp:81-124) for host-side odd contributions:
  * mat is row-major [n_rows*n_cols]; entries must exist in the registered pattern                            */
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols,

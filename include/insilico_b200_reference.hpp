@@ -47,6 +47,7 @@
 #include <base/asmb/StiffnessMatrix.hpp>
 #include <base/asmb/ForceIntegrator.hpp>
 #include <base/asmb/BodyForce.hpp>
+#include <base/asmb/NeumannForce.hpp>
 #include <base/kernel/Mass.hpp>
 #include <heat/Laplace.hpp>
 #include <heat/Static.hpp>
@@ -437,6 +438,10 @@ template <typename QUADRATURE>
 struct QuadratureDegree;
 template <unsigned DEGREE, base::Shape SHAPE>
 struct QuadratureDegree<base::Quadrature<DEGREE, SHAPE> > {
+    static const int value = static_cast<int>(DEGREE);
+};
+template <unsigned DEGREE, base::Shape SHAPE>
+struct QuadratureDegree<base::SurfaceQuadrature<DEGREE, SHAPE> > {   // base/Quadrature.hpp:148-151: the rule of the face shape
     static const int value = static_cast<int>(DEGREE);
 };
 
@@ -1081,6 +1086,95 @@ void bodyForceComputation2(const QUADRATURE& quadrature, base::solver::B200& sol
     typedef typename FIELDTUPLEBINDER::Tuple::GeomElement GeomElement;
     const b200_detail::AtElementPoint<GeomElement, FUN> eval = {forceFun};
     b200_detail::sampledBodyForce<FIELDTUPLEBINDER>(quadrature, solver, fieldBinder, eval);
+}
+
+//! base/asmb/NeumannForce.hpp:33-66 for SOLVER = base::solver::B200: the terms of an applied surface force over ALL surface
+//! elements of a SurfaceFieldBinder in ONE device launch (isl_assemble_neumann_rows), instead of one insertToRHS per
+//! surface element.  Read here from the reference's own objects, per surface element (base/mesh/SurfaceElement.hpp): its
+//! nodes, their coordinates in the parameter space of the domain element, the equation numbers of the test element's
+//! DoFs; the caller's function f(x, normal) is evaluated on the host with the reference's own Geometry / SurfaceNormal
+//! functors (NeumannForce.hpp:152-163), the shape functions, the metric, the weighting and the scatter run on the device.
+//! Surface elements whose test DoFs are slaves of master DoFs take the reference's generic loop.
+namespace b200_detail {
+template <typename FIELDTUPLEBINDER, typename SURFACEQUADRATURE, typename FIELDBINDER, typename FUN>
+void neumannForces(const SURFACEQUADRATURE& surfaceQuadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                   const FUN& ff) {
+    namespace D = base::solver::b200_detail;
+    solver.verifyCurrent();
+    typedef typename FIELDTUPLEBINDER::Tuple Tuple;
+    typedef typename Tuple::GeomElement SurfaceElement;
+    typedef typename Tuple::TestElement TestElement;
+    typedef typename TestElement::DegreeOfFreedom DoF;
+    typedef base::GeomTraits<SurfaceElement> GT;
+    typedef typename NeumannForce<Tuple>::ForceFun ForceFun;
+    const unsigned dim = GT::globalDim, ds = DoF::size;
+    const std::size_t n = static_cast<std::size_t>(std::distance(fieldBinder.elementsBegin(), fieldBinder.elementsEnd()));
+    if (n == 0) return;
+    const std::size_t nq = static_cast<std::size_t>(std::distance(surfaceQuadrature.begin(), surfaceQuadrature.end()));
+    const Tuple first = FIELDTUPLEBINDER::makeTuple(*fieldBinder.elementsBegin());
+    const std::size_t P = static_cast<std::size_t>(std::distance(first.geomElementPtr()->nodesBegin(), first.geomElementPtr()->nodesEnd()));
+    const std::size_t ndpe = static_cast<std::size_t>(std::distance(first.testElementPtr()->doFsBegin(), first.testElementPtr()->doFsEnd()));
+    std::vector<double> sx(n * P * dim), sp(n * P * dim), values(n * nq * ds);
+    std::vector<int32_t> rows(n * ndpe * ds);
+    bool slaves = false;
+    std::size_t k = 0;
+    for (typename FIELDBINDER::FieldIterator it = fieldBinder.elementsBegin(); it != fieldBinder.elementsEnd(); ++it, ++k) {
+        const Tuple tuple = FIELDTUPLEBINDER::makeTuple(*it);
+        const SurfaceElement* surfEp = tuple.geomElementPtr();
+        const TestElement* testEp = tuple.testElementPtr();
+        std::size_t p = 0;
+        typename SurfaceElement::ParamConstIter par = surfEp->parametricBegin();
+        for (typename SurfaceElement::NodePtrConstIter nd = surfEp->nodesBegin(); nd != surfEp->nodesEnd(); ++nd, ++par, ++p) {
+            double x[3] = {0., 0., 0.};
+            (*nd)->getX(&x[0]);
+            for (unsigned d = 0; d < dim; d++) { sx[(k * P + p) * dim + d] = x[d]; sp[(k * P + p) * dim + d] = (*par)[d]; }
+        }
+        std::size_t s = 0;
+        for (typename TestElement::DoFPtrConstIter dp = testEp->doFsBegin(); dp != testEp->doFsEnd(); ++dp, ++s)
+            for (unsigned c = 0; c < ds; c++) {
+                rows[(k * ndpe + s) * ds + c] = (*dp)->isActive(c) ? static_cast<int32_t>((*dp)->getIndex(c)) : -1;
+                if ((*dp)->isConstrained(c) && !slaves) {
+                    std::vector<std::pair<base::number, std::size_t> > masters;
+                    const_cast<DoF*>(*dp)->getConstraint(c)->getWeightedDoFIDs(masters);
+                    slaves = !masters.empty();
+                }
+            }
+        std::size_t q = 0;
+        for (typename SURFACEQUADRATURE::Iter qIter = surfaceQuadrature.begin(); qIter != surfaceQuadrature.end(); ++qIter, ++q) {
+            const typename GT::GlobalVecDim x = base::Geometry<SurfaceElement>()(surfEp, qIter->second);
+            typename GT::GlobalVecDim normal;
+            base::SurfaceNormal<SurfaceElement>()(surfEp, qIter->second, normal);
+            const typename ForceFun::result_type f = ff(x, normal);
+            for (unsigned c = 0; c < ds; c++) values[(k * nq + q) * ds + c] = f[c];
+        }
+    }
+    if (slaves) {   // few and rare: the reference's own loop (-> insertToRHS per surface element) keeps their master weights
+        const ForceFun forceFun = ff;
+        base::asmb::neumannForceComputation<FIELDTUPLEBINDER, SURFACEQUADRATURE, base::solver::B200, FIELDBINDER>(surfaceQuadrature, solver, fieldBinder, forceFun);
+        return;
+    }
+    typedef typename SurfaceElement::DomainElement DomainElement;
+    D::check(isl_assemble_neumann_rows(D::engine(), static_cast<int>(DomainElement::shape), static_cast<int>(DomainElement::GeomFun::degree),
+                                       static_cast<int64_t>(n), &sx[0], &sp[0], D::QuadratureDegree<SURFACEQUADRATURE>::value,
+                                       static_cast<int>(TestElement::FEFun::degree), static_cast<int>(ds), &rows[0], ISL_NEUMANN_SAMPLED,
+                                       &values[0]));
+}
+}  // namespace b200_detail
+
+//! The overloads.  The reference's signature takes the force function as NeumannForce<Tuple>::ForceFun (a boost::function) in
+//! a non-deduced context, which leaves that template and these unordered; they are therefore chosen by the better
+//! conversion of the last argument: a functor or bind expression (reference/05-mixedPoisson/mixedPoisson.cpp:184-187) needs
+//! no conversion here, a non-const boost::function lvalue (base/BoundaryValueProblem.hpp:329-331) binds to the less
+//! cv-qualified reference.  (A `const` boost::function lvalue of exactly that type stays ambiguous: pass it un-const.)
+template <typename FIELDTUPLEBINDER, typename SURFACEQUADRATURE, typename FIELDBINDER, typename FUN>
+void neumannForceComputation(const SURFACEQUADRATURE& surfaceQuadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                             const FUN& ff) {
+    b200_detail::neumannForces<FIELDTUPLEBINDER>(surfaceQuadrature, solver, fieldBinder, ff);
+}
+template <typename FIELDTUPLEBINDER, typename SURFACEQUADRATURE, typename FIELDBINDER, typename FUN>
+void neumannForceComputation(const SURFACEQUADRATURE& surfaceQuadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
+                             FUN& ff) {
+    b200_detail::neumannForces<FIELDTUPLEBINDER>(surfaceQuadrature, solver, fieldBinder, ff);
 }
 
 }  // namespace asmb

@@ -198,6 +198,87 @@ inline void boundary_dofs(int shape, int geom_deg, int dim, const double* coords
     }
 }
 
+// ---- surface elements of boundary faces ------------------------------------------------------------------------------
+// shape of the faces of a shape (base/shape.hpp FaceShape)
+inline int face_shape(int shape) { return shape == HEX ? QUAD : (shape == TET ? TRI : LINE); }
+
+// base::mesh::generateBoundaryMesh (base/mesh/generateBoundaryMesh.hpp:279-432, without the optional triangulation): one
+// surface element per (element, face number) pair.  Its nodes are the geometry nodes of the domain element that
+// FaceExtraction lists for the face, in that order (= the order the Lagrange shape functions of the face shape expect);
+// with every node it keeps the node's coordinate in the parameter space of the domain element (base/mesh/SurfaceElement.hpp).
+// domain_elem[n_pairs], surf_x[n_pairs * P * dim], surf_param[n_pairs * P * dim]; returns P.
+inline int boundary_surface(int shape, int geom_deg, int dim, const double* coords, const int32_t* conn, int64_t n_pairs,
+                            const int64_t* pairs, int32_t* domain_elem, double* surf_x, double* surf_param) {
+    const Basis geom(shape, geom_deg);
+    std::vector<double> sp((size_t)geom.nfun * geom.dim);
+    geom.support(sp.data());
+    const int surf = shape_dim(shape) - 1;
+    std::vector<int> loc;
+    face_local_dofs(shape, geom_deg, surf, 0, loc);
+    const int P = (int)loc.size();
+    if (!domain_elem) return P;
+    for (int64_t b = 0; b < n_pairs; b++) {
+        const int64_t e = pairs[2 * b];
+        face_local_dofs(shape, geom_deg, surf, (int)pairs[2 * b + 1], loc);
+        domain_elem[b] = (int32_t)e;
+        for (int p = 0; p < P; p++) {
+            const int32_t node = conn[e * geom.nfun + loc[p]];
+            for (int d = 0; d < dim; d++) {
+                surf_x[((size_t)b * P + p) * dim + d] = coords[(size_t)node * dim + d];
+                surf_param[((size_t)b * P + p) * dim + d] = sp[(size_t)loc[p] * dim + d];
+            }
+        }
+    }
+    return P;
+}
+
+// un-normalised normal of a surface element at a point: cross product of the columns of its Jacobi matrix
+// (base/geometry.hpp:256-273, base/linearAlgebra.hpp:75-99); J[d][a] = sum_p x_p[d] dN_p/deta_a
+inline void surface_normal_raw(int dim, int P, const double* xs, const double* dN, double* nrm) {
+    double J[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+    const int ld = dim - 1;
+    for (int p = 0; p < P; p++)
+        for (int d = 0; d < dim; d++)
+            for (int a = 0; a < ld; a++) J[d][a] += xs[p * dim + d] * dN[p * ld + a];
+    if (dim == 3) {
+        nrm[0] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+        nrm[1] = J[2][0] * J[0][1] - J[0][0] * J[2][1];
+        nrm[2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+    } else {
+        nrm[0] = J[1][0]; nrm[1] = -J[0][0];
+    }
+}
+
+// physical position, unit normal and surface metric at the points of SurfaceQuadrature<quad_deg> of every surface element
+// (what base::asmb::NeumannForce hands to the caller's force function, base/asmb/NeumannForce.hpp:152-163):
+// x[n_surf * nq * dim], normal[n_surf * nq * dim], detg[n_surf * nq] (any may be null); returns nq
+inline int surface_points(int surf_shape, int geom_deg, int dim, int64_t n_surf, const double* surf_x, int quad_deg,
+                          double* x, double* normal, double* detg) {
+    const Basis sg(surf_shape, geom_deg);
+    const Rule R = make_rule(surf_shape, quad_deg);
+    const int P = sg.nfun, ld = dim - 1;
+    std::vector<double> N((size_t)R.n * P), dN((size_t)R.n * P * ld);
+    for (int q = 0; q < R.n; q++) sg.eval(&R.p[(size_t)q * ld], &N[(size_t)q * P], &dN[(size_t)q * P * ld]);
+    if (!surf_x) return R.n;
+    for (int64_t k = 0; k < n_surf; k++)
+        for (int q = 0; q < R.n; q++) {
+            const double* xs = surf_x + (size_t)k * P * dim;
+            const size_t o = (size_t)k * R.n + q;
+            if (x)
+                for (int d = 0; d < dim; d++) {
+                    double v = 0.;
+                    for (int p = 0; p < P; p++) v += xs[p * dim + d] * N[(size_t)q * P + p];
+                    x[o * dim + d] = v;
+                }
+            double nr[3] = {0., 0., 0.};
+            surface_normal_raw(dim, P, xs, &dN[(size_t)q * P * ld], nr);
+            const double len = (dim == 3) ? std::sqrt(nr[0] * nr[0] + (nr[1] * nr[1] + nr[2] * nr[2])) : std::sqrt(nr[0] * nr[0] + nr[1] * nr[1]);
+            if (detg) detg[o] = len;
+            if (normal) for (int d = 0; d < dim; d++) normal[o * dim + d] = nr[d] / len;
+        }
+    return R.n;
+}
+
 inline int64_t number_dofs(int64_t n_obj, int dof_size, const uint8_t* status, int64_t init, int64_t* eqn) {
     int64_t c = init;
     for (int64_t k = 0; k < n_obj * dof_size; k++) eqn[k] = (status[k] == ACTIVE) ? c++ : -1;

@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
 }
 
 #include "isl_tangent_tiled.cuh"
+#include "isl_neumann.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // specialised hot path: Q1 hex geometry, Q1 scalar field, Laplace, 2x2x2 Gauss rule (BASELINE config 2).
@@ -2410,6 +2411,105 @@ int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_
         p.need_gt = 0; p.need_gc = 0; p.nqdata = 0;
         if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
         ISL_CUDA(cudaStreamSynchronize(h->stream));   // fq is released when this function returns
+    });
+}
+
+// ---- surface terms ----
+namespace {
+void assemble_neumann(isl_engine* h, int shape, int geom_deg, int64_t n_surf, const int32_t* domain_elem, const double* surf_x,
+                      const double* surf_param, int quad_deg, int fe_deg, int ds, int t, const int32_t* rows, int mode, const double* data) {
+    ISL_CUDA(cudaSetDevice(h->device));
+    ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
+    ISL_REQUIRE(shape == ISL_TRI || shape == ISL_QUAD || shape == ISL_TET || shape == ISL_HEX, "surface terms need a 2-D or 3-D domain element");
+    ISL_REQUIRE(mode == ISL_NEUMANN_CONSTANT || mode == ISL_NEUMANN_NORMAL || mode == ISL_NEUMANN_SAMPLED, "unknown surface force mode");
+    ISL_REQUIRE(data != nullptr, "no surface force");
+    ISL_REQUIRE(mode != ISL_NEUMANN_NORMAL || ds == isl::shape_dim(shape), "a force along the normal needs dof_size == dimension");
+    require_live_system(h);
+    flush_pending(h);
+    if (n_surf <= 0) return;
+    ISL_REQUIRE(surf_x != nullptr && surf_param != nullptr, "surface element arrays missing");
+    const int dim = isl::shape_dim(shape), ld = dim - 1, sshape = isl::face_shape(shape);
+    const isl::Basis sg(sshape, geom_deg), fe(shape, fe_deg);
+    const isl::Rule R = isl::make_rule(sshape, quad_deg);
+    const int P = sg.nfun, nq = R.n, nt = fe.nfun;
+    std::vector<double> N((size_t)nq * P), dN((size_t)nq * P * ld);
+    for (int q = 0; q < nq; q++) sg.eval(&R.p[(size_t)q * ld], &N[(size_t)q * P], &dN[(size_t)q * P * ld]);
+    // distinct blocks of parameter coordinates and the test functions at xi(eta_q) for each of them
+    // (SurfaceElement::localDomainCoordinate, base/mesh/SurfaceElement.hpp:42-55: xi = sum_p param_p N_p(eta))
+    std::map<std::vector<double>, int> seen;
+    std::vector<int32_t> pat((size_t)n_surf);
+    std::vector<double> phi, block((size_t)P * dim), fun((size_t)nt);
+    for (int64_t k = 0; k < n_surf; k++) {
+        block.assign(surf_param + (size_t)k * P * dim, surf_param + (size_t)(k + 1) * P * dim);
+        auto it = seen.find(block);
+        if (it == seen.end()) {
+            it = seen.emplace(block, (int)seen.size()).first;
+            for (int q = 0; q < nq; q++) {
+                double xi[3] = {0., 0., 0.};
+                for (int p = 0; p < P; p++) for (int d = 0; d < dim; d++) xi[d] += block[(size_t)p * dim + d] * N[(size_t)q * P + p];
+                fe.eval(xi, fun.data(), nullptr);
+                phi.insert(phi.end(), fun.begin(), fun.end());
+            }
+        }
+        pat[(size_t)k] = it->second;
+    }
+    NeumannParams p; std::memset(&p, 0, sizeof(p));
+    DevBuf<double> d_sx, d_phi, d_dN, d_w, d_data; DevBuf<int32_t> d_pat, d_elem, d_rows;
+    upload(h, d_sx, surf_x, (size_t)n_surf * P * dim); upload(h, d_phi, phi.data(), phi.size());
+    upload(h, d_dN, dN.data(), dN.size()); upload(h, d_w, R.w.data(), (size_t)nq); upload(h, d_pat, pat.data(), pat.size());
+    p.n_surf = n_surf; p.dim = dim; p.P = P; p.nq = nq; p.nt = nt; p.ds = ds; p.mode = mode;
+    p.sx = d_sx.p; p.pat = d_pat.p; p.phi = d_phi.p; p.sdN = d_dN.p; p.w = d_w.p; p.rhs = h->rhs.p;
+    if (mode == ISL_NEUMANN_SAMPLED) { upload(h, d_data, data, (size_t)n_surf * nq * ds); p.data = d_data.p; }
+    else for (int c = 0; c < (mode == ISL_NEUMANN_NORMAL ? 1 : ds); c++) p.f[c] = data[c];
+    if (rows) { upload(h, d_rows, rows, (size_t)n_surf * nt * ds); p.rows = d_rows.p; }
+    else {
+        FieldDev& f = h->fields[t];
+        ISL_REQUIRE(domain_elem != nullptr, "domain elements of the surface elements missing");
+        for (int64_t k = 0; k < n_surf; k++) ISL_REQUIRE(domain_elem[k] >= 0 && domain_elem[k] < h->n_elems, "surface element on an unknown domain element");
+        upload(h, d_elem, domain_elem, (size_t)n_surf);
+        p.elem = d_elem.p; p.ed = f.elem_dof.p; p.eqn = f.eqn.p;
+        p.cptr = f.has_masters ? f.cptr.p : nullptr; p.cm = f.cmaster.p; p.cw = f.cweight.p;
+    }
+    const int64_t total = n_surf * nt * ds;
+    if (dim == 3) ISL_LAUNCH(h, k_neumann<3>, h->grid_for(total, 128), 128, 0, p);
+    else ISL_LAUNCH(h, k_neumann<2>, h->grid_for(total, 128), 128, 0, p);
+    ISL_CUDA(cudaStreamSynchronize(h->stream));   // the staging buffers are released when this function returns
+}
+}  // namespace
+
+int isl_boundary_surface(int shape, int geom_deg, int dim, const double* coords, const int32_t* conn, int64_t n_pairs,
+                         const int64_t* pairs, int32_t* domain_elem, double* surf_x, double* surf_param, int* surf_shape,
+                         int* nodes_per_surf) {
+    return guarded([&] {
+        ISL_REQUIRE(dim == isl::shape_dim(shape) && (dim == 2 || dim == 3), "surface elements of 2-D and 3-D meshes only");
+        const int P = isl::boundary_surface(shape, geom_deg, dim, coords, conn, n_pairs, pairs, domain_elem, surf_x, surf_param);
+        if (surf_shape) *surf_shape = isl::face_shape(shape);
+        if (nodes_per_surf) *nodes_per_surf = P;
+    });
+}
+int isl_surface_points(int surf_shape, int geom_deg, int dim, int64_t n_surf, const double* surf_x, int quad_deg, double* x,
+                       double* normal, double* detg, int* nq) {
+    return guarded([&] {
+        ISL_REQUIRE(dim == isl::shape_dim(surf_shape) + 1, "surface shape and dimension do not match");
+        const int n = isl::surface_points(surf_shape, geom_deg, dim, n_surf, surf_x, quad_deg, x, normal, detg);
+        if (nq) *nq = n;
+    });
+}
+int isl_assemble_neumann(isl_handle h, int64_t n_surf, const int32_t* domain_elem, const double* surf_x, const double* surf_param,
+                         int quad_deg, int test_field, int mode, const double* data) {
+    return guarded([&] {
+        ISL_REQUIRE(test_field >= 0 && test_field < 5 && h->fields[test_field].set, "field not set");
+        const FieldDev& f = h->fields[test_field];
+        ISL_REQUIRE(h->n_elems > 0, "mesh not set");
+        assemble_neumann(h, h->shape, h->geom_deg, n_surf, domain_elem, surf_x, surf_param, quad_deg, f.deg, f.ds, test_field, nullptr, mode, data);
+    });
+}
+int isl_assemble_neumann_rows(isl_handle h, int shape, int geom_deg, int64_t n_surf, const double* surf_x, const double* surf_param,
+                              int quad_deg, int fe_deg, int dof_size, const int32_t* rows, int mode, const double* data) {
+    return guarded([&] {
+        ISL_REQUIRE(rows != nullptr, "no equation numbers");
+        ISL_REQUIRE(dof_size >= 1 && dof_size <= 3, "dof_size must be 1..3");
+        assemble_neumann(h, shape, geom_deg, n_surf, nullptr, surf_x, surf_param, quad_deg, fe_deg, dof_size, -1, rows, mode, data);
     });
 }
 

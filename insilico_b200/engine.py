@@ -40,7 +40,8 @@ EXPORTED = [
     "isl_assemble_matrix", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_csr_async", "isl_copy_wait", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
-    "isl_unpack_add_entries", "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange", "isl_distribute", "isl_field_get_values",
+    "isl_unpack_add_entries", "isl_boundary_surface", "isl_surface_points", "isl_assemble_neumann", "isl_assemble_neumann_rows",
+    "isl_comm_unique_id", "isl_comm_init", "isl_comm_destroy", "isl_exchange_setup", "isl_exchange", "isl_distribute", "isl_field_get_values",
 ]
 
 
@@ -171,6 +172,38 @@ def constrain_boundary(shape, geom_deg, coords, conn, fe_deg, dof_size, elem_dof
     # later visits overwrite earlier ones (DegreeOfFreedom::constrainValue); numpy keeps the last assignment
     prescribed[obj] = vals
     return status, prescribed
+
+
+NEUMANN_CONSTANT, NEUMANN_NORMAL, NEUMANN_SAMPLED = 0, 1, 2
+
+
+def boundary_surface(shape, geom_deg, coords, conn, pairs):
+    """base::mesh::generateBoundaryMesh for (element, face number) pairs: (surf_shape, domain_elem [n], surf_x [n, P, dim],
+    surf_param [n, P, dim]) -- the nodes of every surface element and their coordinates in the domain element."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64)
+    dim = coords.shape[1]
+    ss, P = C.c_int(), C.c_int()
+    args = (shape, geom_deg, dim, _ptr(coords), _ptr(conn), _i64(len(pairs)), _ptr(pairs))
+    _chk(lib().isl_boundary_surface(*args, None, None, None, C.byref(ss), C.byref(P)))
+    de = np.zeros(len(pairs), dtype=np.int32)
+    sx = np.zeros((len(pairs), P.value, dim))
+    sp = np.zeros((len(pairs), P.value, dim))
+    _chk(lib().isl_boundary_surface(*args, _ptr(de), _ptr(sx), _ptr(sp), C.byref(ss), C.byref(P)))
+    return ss.value, de, sx, sp
+
+
+def surface_points(surf_shape, geom_deg, surf_x, quad_deg):
+    """position, unit normal and surface metric at the points of SurfaceQuadrature<quad_deg> of every surface element:
+    (x [n, nq, dim], normal [n, nq, dim], detg [n, nq]) -- the arguments of a Neumann force function f(x, normal)"""
+    surf_x = np.ascontiguousarray(surf_x, dtype=np.float64)
+    n, _, dim = surf_x.shape
+    nq = C.c_int()
+    _chk(lib().isl_surface_points(surf_shape, geom_deg, dim, _i64(n), None, quad_deg, None, None, None, C.byref(nq)))
+    x, nr, dg = np.zeros((n, nq.value, dim)), np.zeros((n, nq.value, dim)), np.zeros((n, nq.value))
+    _chk(lib().isl_surface_points(surf_shape, geom_deg, dim, _i64(n), _ptr(surf_x), quad_deg, _ptr(x), _ptr(nr), _ptr(dg), C.byref(nq)))
+    return x, nr, dg
 
 
 def number_dofs_consecutively(status, init=0):
@@ -307,6 +340,23 @@ class Engine:
         """asmb::bodyForceComputation<FTB> with a general f(x): values [n_elems, nq, ds] = f at the quadrature points"""
         values = np.ascontiguousarray(values, dtype=np.float64)
         _chk(lib().isl_assemble_bodyforce_sampled(self.h, _ptr(values), quad_deg, test))
+
+    def neumann_force_computation(self, domain_elem, surf_x, surf_param, quad_deg, test, mode, data):
+        """asmb::neumannForceComputation<SFTB>: rhs += int f phi ds over the surface elements; mode NEUMANN_CONSTANT
+        (data = f), NEUMANN_NORMAL (data = [p]: f = p * normal) or NEUMANN_SAMPLED (data [n_surf, nq, ds])"""
+        de = np.ascontiguousarray(domain_elem, dtype=np.int32)
+        sx = np.ascontiguousarray(surf_x, dtype=np.float64)
+        sp = np.ascontiguousarray(surf_param, dtype=np.float64)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        _chk(lib().isl_assemble_neumann(self.h, _i64(len(de)), _ptr(de), _ptr(sx), _ptr(sp), quad_deg, test, mode, _ptr(data)))
+
+    def neumann_force_computation_rows(self, shape, geom_deg, surf_x, surf_param, quad_deg, fe_deg, ds, rows, mode, data):
+        """the same with the equation numbers per surface element (rows [n_surf, ndpe * ds], < 0 skipped)"""
+        sx = np.ascontiguousarray(surf_x, dtype=np.float64)
+        sp = np.ascontiguousarray(surf_param, dtype=np.float64)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        _chk(lib().isl_assemble_neumann_rows(self.h, shape, geom_deg, _i64(len(sx)), _ptr(sx), _ptr(sp), quad_deg, fe_deg, ds, _ptr(rows), mode, _ptr(data)))
 
     def insert_to_lhs(self, mat, rows, cols):
         mat = np.ascontiguousarray(mat, dtype=np.float64)

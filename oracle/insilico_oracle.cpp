@@ -1570,6 +1570,161 @@ int orc_bodyforce_sampled(void* s, void* h, const double* values, int quadDeg, i
     for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, 0, values, test, test, 1.0, 2, e);
     return sys.error.empty() ? 0 : -1;
 }
+// ---- surface terms: base/mesh/generateBoundaryMesh.hpp, base/mesh/SurfaceElement.hpp, base/asmb/NeumannForce.hpp -------
+static int faceShapeOf(int shape) { return shape == HEX ? QUAD : (shape == TET ? TRI : LINE); }
+
+// generateBoundaryMesh.hpp:279-432 (no triangulation): the surface element of boundary pair b has the domain element's
+// geometry nodes FaceExtraction lists for the face; parametric coordinates = support points of those nodes.
+// Returns the number of nodes per surface element; arrays may be NULL.
+int orc_boundary_surface(void* h, int64_t nPairs, const int64_t* pairs, int64_t* domainElem, double* surfX, double* surfParam) {
+    Problem& p = *(Problem*)h;
+    const Mesh& m = p.mesh;
+    SFun g; g.init(m.shape, m.geomDeg);
+    std::vector<double> sp(g.nfun * g.dim);
+    g.support(sp.data());
+    const int surf = shapeDim(m.shape) - 1;
+    std::vector<int> ids; faceExtraction(m.shape, m.geomDeg, surf, 0, ids);
+    const int P = (int)ids.size();
+    if (!domainElem) return P;
+    for (int64_t b = 0; b < nPairs; b++) {
+        const int64_t e = pairs[2 * b];
+        ids.clear(); faceExtraction(m.shape, m.geomDeg, surf, (int)pairs[2 * b + 1], ids);
+        domainElem[b] = e;
+        for (int n = 0; n < P; n++) {
+            // node coordinates: Geometry(domainElement, xi) at a support point (generateBoundaryMesh.hpp:344-349)
+            geometryEval(m, e, &sp[ids[n] * g.dim], &surfX[((size_t)b * P + n) * m.dim]);
+            for (int d = 0; d < m.dim; d++) surfParam[((size_t)b * P + n) * m.dim + d] = sp[ids[n] * g.dim + d];
+        }
+    }
+    return P;
+}
+
+// geometry.hpp:256-346 SurfaceNormal: cross product of the Jacobi matrix's columns, its length is the metric
+static double surfaceNormal(const SFun& sg, int dim, const double* xs, const double* eta, double* normal) {
+    const int ld = dim - 1;
+    std::vector<double> dN((size_t)sg.nfun * ld);
+    sg.grad(eta, dN.data());
+    double J[3][2] = {{0., 0.}, {0., 0.}, {0., 0.}};
+    for (int n = 0; n < sg.nfun; n++)
+        for (int d = 0; d < dim; d++)
+            for (int a = 0; a < ld; a++) J[d][a] += xs[n * dim + d] * dN[n * ld + a];
+    double len;
+    if (dim == 3) {
+        normal[0] = J[1][0] * J[2][1] - J[2][0] * J[1][1];
+        normal[1] = J[2][0] * J[0][1] - J[0][0] * J[2][1];
+        normal[2] = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        len = std::sqrt(normal[0] * normal[0] + (normal[1] * normal[1] + normal[2] * normal[2]));
+    } else {
+        normal[0] = J[1][0]; normal[1] = -J[0][0];
+        len = std::sqrt(normal[0] * normal[0] + normal[1] * normal[1]);
+    }
+    for (int d = 0; d < dim; d++) normal[d] /= len;
+    return len;
+}
+
+// x, normal, detG at the points of SurfaceQuadrature<quadDeg> (Quadrature.hpp:148-151) of every surface element
+int orc_surface_points(int surfShape, int geomDeg, int dim, int64_t nSurf, const double* surfX, int quadDeg, double* x,
+                       double* normal, double* detg) {
+    SFun sg; sg.init(surfShape, geomDeg);
+    Quad q = makeQuadrature(surfShape, quadDeg);
+    if (!surfX) return q.n;
+    std::vector<double> N(sg.nfun);
+    for (int64_t k = 0; k < nSurf; k++)
+        for (int g = 0; g < q.n; g++) {
+            const double* xs = surfX + (size_t)k * sg.nfun * dim;
+            const size_t o = (size_t)k * q.n + g;
+            sg.fun(&q.p[g * q.dim], N.data());
+            if (x)
+                for (int d = 0; d < dim; d++) {
+                    double v = 0.;
+                    for (int n = 0; n < sg.nfun; n++) v += xs[n * dim + d] * N[n];
+                    x[o * dim + d] = v;
+                }
+            double nr[3];
+            const double len = surfaceNormal(sg, dim, xs, &q.p[g * q.dim], nr);
+            if (detg) detg[o] = len;
+            if (normal) for (int d = 0; d < dim; d++) normal[o * dim + d] = nr[d];
+        }
+    return q.n;
+}
+
+// asmb/NeumannForce.hpp:33-66,140-184 through ForceIntegrator / assembleForces.  mode 0: f = data[dofSize] constant,
+// 1: f = data[0] * normal, 2: f = data[(k * nq + g) * dofSize ..] sampled by the caller at the surface quadrature points
+int orc_neumann(void* s, void* h, int64_t nSurf, const int64_t* domainElem, const double* surfX, const double* surfParam,
+                int quadDeg, int testId, int mode, const double* data) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    const Mesh& m = p.mesh;
+    const Field& test = p.fields[testId];
+    const int dim = m.dim, sshape = faceShapeOf(m.shape), ds = test.dofSize;
+    SFun sg; sg.init(sshape, m.geomDeg);
+    Quad q = makeQuadrature(sshape, quadDeg);
+    const int P = sg.nfun;
+    std::vector<double> N(P), fv(test.ndpe);
+    for (int64_t k = 0; k < nSurf; k++) {
+        const int64_t e = domainElem[k];
+        std::vector<uint8_t> st; std::vector<size_t> ids; std::vector<double> pv;
+        Constraints con;
+        if (!collectFromDoFs(test, e, st, ids, pv, con, false)) continue;
+        std::vector<double> vec(ids.size(), 0.);
+        const double* xs = surfX + (size_t)k * P * dim;
+        const double* par = surfParam + (size_t)k * P * dim;
+        for (int g = 0; g < q.n; g++) {
+            const double* eta = &q.p[g * q.dim];
+            double normal[3];
+            const double detG = surfaceNormal(sg, dim, xs, eta, normal);
+            double f[3] = {0., 0., 0.};
+            for (int d = 0; d < ds; d++)
+                f[d] = (mode == 2) ? data[((size_t)k * q.n + g) * ds + d] : (mode == 1 ? data[0] * normal[d] : data[d]);
+            // SurfaceElement.hpp:42-55 localDomainCoordinate
+            double xi[3] = {0., 0., 0.};
+            sg.fun(eta, N.data());
+            for (int n = 0; n < P; n++) for (int d = 0; d < dim; d++) xi[d] += par[n * dim + d] * N[n];
+            test.feFun.fun(xi, fv.data());
+            for (int sf = 0; sf < test.ndpe; sf++)
+                for (int d = 0; d < ds; d++) vec[sf * ds + d] += f[d] * fv[sf] * q.w[g] * detG;
+        }
+        assembleForces(vec, st, ids, con, sys);
+    }
+    return sys.error.empty() ? 0 : -1;
+}
+
+// the same for a caller that holds the equation numbers per surface element itself (rows[nSurf][ndpe*dofSize], < 0: not
+// ACTIVE): what the C ABI's isl_assemble_neumann_rows does; used by the mock ABI of the binding's CPU tests
+int orc_neumann_rows(void* s, int shape, int geomDeg, int dim, int feDeg, int dofSize, int64_t nSurf, const double* surfX,
+                     const double* surfParam, int quadDeg, const int32_t* rows, int mode, const double* data) {
+    System& sys = *(System*)s;
+    const int sshape = faceShapeOf(shape), ds = dofSize;
+    SFun sg; sg.init(sshape, geomDeg);
+    SFun fe; fe.init(shape, feDeg);
+    Quad q = makeQuadrature(sshape, quadDeg);
+    const int P = sg.nfun;
+    std::vector<double> N(P), fv(fe.nfun), vec((size_t)fe.nfun * ds);
+    for (int64_t k = 0; k < nSurf; k++) {
+        std::fill(vec.begin(), vec.end(), 0.);
+        const double* xs = surfX + (size_t)k * P * dim;
+        const double* par = surfParam + (size_t)k * P * dim;
+        for (int g = 0; g < q.n; g++) {
+            const double* eta = &q.p[g * q.dim];
+            double normal[3];
+            const double detG = surfaceNormal(sg, dim, xs, eta, normal);
+            double f[3] = {0., 0., 0.};
+            for (int d = 0; d < ds; d++)
+                f[d] = (mode == 2) ? data[((size_t)k * q.n + g) * ds + d] : (mode == 1 ? data[0] * normal[d] : data[d]);
+            double xi[3] = {0., 0., 0.};
+            sg.fun(eta, N.data());
+            for (int n = 0; n < P; n++) for (int d = 0; d < dim; d++) xi[d] += par[n * dim + d] * N[n];
+            fe.fun(xi, fv.data());
+            for (int sf = 0; sf < fe.nfun; sf++)
+                for (int d = 0; d < ds; d++) vec[sf * ds + d] += f[d] * fv[sf] * q.w[g] * detG;
+        }
+        for (size_t i = 0; i < vec.size(); i++) {
+            const int32_t r = rows[(size_t)k * vec.size() + i];
+            if (r >= 0) sys.b[(size_t)r] += vec[i];
+        }
+    }
+    return 0;
+}
+
 // physical coordinates of the quadrature points, [nElems][nq][dim] (base::Geometry, geometry.hpp:105-135)
 void orc_quadrature_points(void* h, int quadDeg, double* x) {
     Problem& p = *(Problem*)h;

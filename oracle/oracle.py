@@ -124,6 +124,16 @@ def number_dofs(status, init=0):
     return eqn, n
 
 
+def surface_points(surf_shape, geom_deg, surf_x, quad_deg):
+    """(x, normal, detg) at the surface quadrature points of every surface element (NeumannForce.hpp:152-163)"""
+    surf_x = np.ascontiguousarray(surf_x, dtype=np.float64)
+    n, _, dim = surf_x.shape
+    nq = lib().orc_surface_points(surf_shape, geom_deg, dim, C.c_int64(n), None, quad_deg, None, None, None)
+    x, nr, dg = np.zeros((n, nq, dim)), np.zeros((n, nq, dim)), np.zeros((n, nq))
+    lib().orc_surface_points(surf_shape, geom_deg, dim, C.c_int64(n), _p(surf_x), quad_deg, _p(x), _p(nr), _p(dg))
+    return x, nr, dg
+
+
 class Problem:
     """Mesh + up to five fields (FieldBinder<Mesh,F1..F5>)."""
 
@@ -164,6 +174,16 @@ class Problem:
         x = np.zeros((n, self.dim))
         lib().orc_boundary_dof_points(self.h, fe_deg, C.c_int64(len(pairs)), _p(pairs), _p(elem), _p(loc), _p(x))
         return elem, loc, x
+
+    def boundary_surface(self, pairs):
+        """generateBoundaryMesh for (element, face) pairs: (domain_elem [n], surf_x [n, P, dim], surf_param [n, P, dim])"""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64)
+        P = lib().orc_boundary_surface(self.h, C.c_int64(len(pairs)), _p(pairs), None, None, None)
+        de = np.zeros(len(pairs), dtype=np.int64)
+        sx = np.zeros((len(pairs), P, self.dim))
+        sp = np.zeros((len(pairs), P, self.dim))
+        lib().orc_boundary_surface(self.h, C.c_int64(len(pairs)), _p(pairs), _p(de), _p(sx), _p(sp))
+        return de, sx, sp
 
     def set_field(self, fid, fe_deg, dof_size, n_obj, elem_dof, eqn, status, prescribed, values):
         a = dict(elem_dof=np.ascontiguousarray(elem_dof, dtype=np.int64),
@@ -242,6 +262,14 @@ class System:
         v = np.ascontiguousarray(values, dtype=np.float64)
         if lib().orc_bodyforce_sampled(self.h, prob.h, _p(v), quad_deg, test):
             raise RuntimeError(lib().orc_system_error(self.h).decode())
+
+    def neumann(self, prob, domain_elem, surf_x, surf_param, quad_deg, test, mode, data):
+        """asmb::neumannForceComputation: mode 0 constant f = data, 1 f = data[0] * normal, 2 data [n_surf, nq, ds] sampled"""
+        de = np.ascontiguousarray(domain_elem, dtype=np.int64)
+        sx = np.ascontiguousarray(surf_x, dtype=np.float64)
+        sp = np.ascontiguousarray(surf_param, dtype=np.float64)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        self._check(lib().orc_neumann(self.h, prob.h, C.c_int64(len(de)), _p(de), _p(sx), _p(sp), quad_deg, test, mode, _p(data)))
 
     def residual(self, prob, kid, params, quad_deg, test, trial):
         params = np.ascontiguousarray(params, dtype=np.float64)

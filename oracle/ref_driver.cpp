@@ -35,6 +35,9 @@
 #include <base/asmb/StiffnessMatrix.hpp>
 #include <base/asmb/ForceIntegrator.hpp>
 #include <base/asmb/BodyForce.hpp>
+#include <base/mesh/generateBoundaryMesh.hpp>
+#include <base/asmb/SurfaceFieldBinder.hpp>
+#include <base/asmb/NeumannForce.hpp>
 #include <base/solver/Eigen3.hpp>
 #include <base/kernel/Mass.hpp>
 #include <heat/Laplace.hpp>
@@ -171,6 +174,31 @@ struct NamedForce {
     }
 };
 
+// the surface forces f(x, normal) of the "neumann" operations of tests/flows.py, by name
+template <unsigned DS, unsigned DIM>
+struct NamedSurfaceForce {
+    typedef typename base::Vector<DS>::Type result_type;
+    std::string name;
+    std::vector<double> p;
+    result_type operator()(const typename base::Vector<DIM>::Type& x, const typename base::Vector<DIM>::Type& n) const {
+        result_type f = base::constantVector<DS>(0.);
+        if (name == "constant") { for (unsigned d = 0; d < DS; d++) f[d] = p[d]; }
+        else if (name == "pressure") { for (unsigned d = 0; d < DS; d++) f[d] = p[0] * n[d % DIM]; }
+        else if (name == "fun") {
+            const double s = 1.0 + x[0] * x[1] + 0.5 * std::sin(2.0 * x[DIM - 1]);
+            for (unsigned d = 0; d < DS; d++) f[d] = s * n[d % DIM] + 0.25 * x[(d + 1) % DIM];
+        } else VERIFY_MSG(false, "unknown surface force " + name);
+        return f;
+    }
+};
+
+// geometry filter of generateBoundaryMesh: 0 = every boundary face, 1 = faces in the plane x0 = 1
+struct FaceFilter {
+    int id;
+    template <typename X>
+    bool operator()(const X& x) const { return id == 0 || x[0] > 1.0 - 1e-9; }
+};
+
 template <typename MESH, typename FEBASIS, typename FIELD>
 void setUpField(const MESH& mesh, FIELD& field, const FieldSpec& spec, const base::mesh::MeshBoundary& boundary) {
     typedef typename FIELD::DegreeOfFreedom DoF;
@@ -291,6 +319,22 @@ int runSingle(const Job& job) {
                 NamedForce<DS, Mesh::Node::dim> f;
                 f.name = op.kernel;
                 base::asmb::bodyForceComputation<FTB>(quadratureBody, solver, fieldBinder, f);
+                continue;
+            }
+            if (op.what == "neumann") {   // base::asmb::neumannForceComputation over (a part of) the boundary
+                typedef typename base::mesh::BoundaryMeshBinder<typename Mesh::Element>::Type BoundaryMesh;
+                BoundaryMesh boundaryMesh;
+                FaceFilter filter;
+                filter.id = op.incremental;
+                base::mesh::generateBoundaryMesh(boundary.begin(), boundary.end(), mesh, boundaryMesh, filter);
+                typedef base::asmb::SurfaceFieldBinder<BoundaryMesh, Field> SurfaceFieldBinder;
+                SurfaceFieldBinder surfaceFieldBinder(boundaryMesh, field);
+                typedef typename SurfaceFieldBinder::template TupleBinder<1>::Type SFTB;
+                base::SurfaceQuadrature<QDEGBODY, SHAPE> surfaceQuadrature;
+                NamedSurfaceForce<DS, Mesh::Node::dim> f;
+                f.name = op.kernel;
+                f.p = op.p;
+                base::asmb::neumannForceComputation<SFTB>(surfaceQuadrature, solver, surfaceFieldBinder, f);
                 continue;
             }
             if (op.what == "body") {

@@ -48,7 +48,7 @@ class Case:
         self.ops = []
         self.n_eqn = 0
 
-    def add_field(self, fe_deg, ds, dirichlet=None, values=None, pin_first=False, linear=None):
+    def add_field(self, fe_deg, ds, dirichlet=None, values=None, pin_first=False, linear=None, where=None):
         """dirichlet: fun(x)->[n,ds] applied on the whole boundary (dof::constrainBoundary);
         values: fun(x_support)->[n_obj,ds] current field state; pin_first: constrain component 0 of DoF 0 to 0
         (drivenCavity.cpp:199-202)."""
@@ -58,6 +58,10 @@ class Case:
         if dirichlet is not None:
             status, presc = E.constrain_boundary(self.shape, self.geom_deg, self.coords, self.conn, fe_deg, ds, ed,
                                                  nobj, dirichlet)
+            if where is not None:   # Dirichlet part of the boundary only: where(x of the DoF) -> bool
+                keep = np.asarray(where(self.dof_positions(fe_deg, ed, nobj)), dtype=bool)
+                status[~keep] = E.ACTIVE
+                presc[~keep] = 0.0
         if pin_first:
             status[0, 0] = E.CONSTRAINED
             presc[0, 0] = 0.0
@@ -73,7 +77,8 @@ class Case:
         if values is not None:
             vals = np.asarray(values(self.dof_positions(fe_deg, ed, nobj)), dtype=np.float64).reshape(nobj, ds)
         self.fields.append(dict(fe_deg=fe_deg, ds=ds, n_obj=nobj, elem_dof=ed, status=status, presc=presc, eqn=eqn,
-                                values=vals, boundary=dirichlet is not None, pin=0 if pin_first else -1, linear=lin))
+                                values=vals, boundary=(2 if where is not None else int(dirichlet is not None)), pin=0 if pin_first else -1,
+                                linear=lin))
         return len(self.fields) - 1
 
     def sampled_factor(self, op):
@@ -91,6 +96,37 @@ class Case:
         x = np.einsum("qa,ead->eqd", Ng, self.coords[self.conn])
         ds = self.fields[op[3]]["ds"]
         return np.ascontiguousarray(np.asarray(op[1](x.reshape(-1, self.dim)), dtype=np.float64).reshape(len(self.conn), len(w), ds))
+
+    def surface_elements(self, op, lib):
+        """surface elements of a ("neumann", name, quad_deg, field, filter, params) operation: all boundary faces
+        (filter 0) or those in the plane x0 = 1 (filter 1, all nodes of the face), from `lib` = the engine's host side
+        (E) or the oracle's (a Problem)"""
+        if lib is E:
+            pairs = E.mesh_boundary(self.shape, self.geom_deg, self.conn)
+            _, de, sx, sp = E.boundary_surface(self.shape, self.geom_deg, self.coords, self.conn, pairs)
+        else:
+            de, sx, sp = lib.boundary_surface(lib.mesh_boundary())
+        if op[4] == 1:
+            keep = np.all(sx[:, :, 0] > 1.0 - 1e-9, axis=1)
+            de, sx, sp = de[keep], sx[keep], sp[keep]
+        return de, np.ascontiguousarray(sx), np.ascontiguousarray(sp)
+
+    def surface_force(self, op, sx, points):
+        """(mode, data) of a neumann operation; points(surf_shape, geom_deg, sx, quad_deg) -> (x, normal, detg)"""
+        name, ds = op[1], self.fields[op[3]]["ds"]
+        if name == "constant":
+            return E.NEUMANN_CONSTANT, np.asarray(op[5], dtype=np.float64)
+        if name == "pressure" and ds == self.dim:
+            return E.NEUMANN_NORMAL, np.asarray(op[5][:1], dtype=np.float64)
+        surf_shape = {E.HEX: E.QUAD, E.TET: E.TRI}.get(self.shape, E.LINE)
+        x, nr, _ = points(surf_shape, self.geom_deg, sx, op[2])
+        dim = self.dim
+        if name == "pressure":
+            f = np.stack([op[5][0] * nr[..., d % dim] for d in range(ds)], axis=-1)
+        else:
+            s = 1.0 + x[..., 0] * x[..., 1] + 0.5 * np.sin(2.0 * x[..., dim - 1])
+            f = np.stack([s * nr[..., d % dim] + 0.25 * x[..., (d + 1) % dim] for d in range(ds)], axis=-1)
+        return E.NEUMANN_SAMPLED, np.ascontiguousarray(f)
 
     @staticmethod
     def constraint_arrays(f):
@@ -139,6 +175,10 @@ class Case:
                 s.bodyforce(prob, op[1], op[2], op[3])
             elif op[0] == "bodyfun":
                 s.bodyforce_sampled(prob, self.sampled_force(op), op[2], op[3])
+            elif op[0] == "neumann":
+                de, sx, sp = self.surface_elements(op, prob)
+                mode, data = self.surface_force(op, sx, orc.surface_points)
+                s.neumann(prob, de, sx, sp, op[2], op[3], mode, data)
         return s.finish()
 
     # ---- run on the CUDA engine ----------------------------------------------------------------------
@@ -168,6 +208,10 @@ class Case:
                 eng.body_force_computation(op[1], op[2], op[3])
             elif op[0] == "bodyfun":
                 eng.body_force_computation_sampled(self.sampled_force(op), op[2], op[3])
+            elif op[0] == "neumann":
+                de, sx, sp = self.surface_elements(op, E)
+                mode, data = self.surface_force(op, sx, E.surface_points)
+                eng.neumann_force_computation(de, sx, sp, op[2], op[3], mode, data)
         out = eng.get_csr()
         if own:
             eng.close()
@@ -299,6 +343,26 @@ def build_case(name, n=4, perturb=True, permute=False):
         c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
         c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, values=lambda x: 0.03 * np.sin(np.pi * x))
         c.ops = [("matrix", E.K_MASS, [7.8], 4, 0, 0, True), ("matrix", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0, True)]
+    elif name == "neumann_q1_hex":     # 05-mixedPoisson: Dirichlet on x0 = 0, a surface force f(x, n) on the whole boundary
+        c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
+        c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), where=lambda x: x[:, 0] < 1e-9)
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 3, 0, 0, True), ("body", [1.0], 3, 0), ("neumann", "fun", 3, 0, 0, [])]
+    elif name == "neumann_p2_tet_solid":   # clamped at x0 = 0, a pressure on the opposite face and a constant traction everywhere
+        lam, mu = lame(1000.0, 0.3)
+        c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
+        c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, where=lambda x: x[:, 0] < 1e-9, values=lambda x: 0.02 * np.sin(np.pi * x))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0, True), ("neumann", "pressure", 4, 0, 1, [-0.7]),
+                 ("neumann", "constant", 4, 0, 0, [0.1, -0.2, 0.3])]
+    elif name == "neumann_p2_tri":         # line elements on the boundary of a triangle mesh, quadratic test functions
+        c = Case(E.TRI, 1, *make_mesh(E.TRI, n, perturb, permute))
+        c.add_field(2, 1, pin_first=True)
+        c.ops = [("matrix", E.K_LAPLACE, [1.0], 4, 0, 0, True), ("neumann", "fun", 4, 0, 0, []), ("neumann", "pressure", 4, 0, 1, [2.0])]
+    elif name == "neumann_q1_quad_solid":  # pressure on the whole boundary of a 2-D solid, two linear constraints on board
+        lam, mu = lame(1000.0, 0.3)
+        c = Case(E.QUAD, 1, *make_mesh(E.QUAD, n, perturb, permute))
+        c.add_field(1, 2, dirichlet=lambda x: 0.0 * x, where=lambda x: x[:, 1] < 1e-9, linear=lambda st: linear_constraints(st, 2, 2))
+        c.ops = [("matrix", E.K_HYPEL_STVENANT, [lam, mu], 3, 0, 0, True), ("neumann", "pressure", 3, 0, 0, [1.5]),
+                 ("neumann", "fun", 3, 0, 1, [])]
     elif name in ("laplace_q1_hex_bodyfun", "laplace_p2_tri_bodyfun", "vector_laplace_q1_hex_bodyfun"):
         # general (non-constant) body force f(x): BodyForce.hpp:172-205 evaluates the caller's function per point
         if "tri" in name:

@@ -36,6 +36,7 @@ int64_t orc_nnz(void*);
 void orc_get_csr(void*, int64_t*, int32_t*, double*, double*);
 const char* orc_system_error(void*);
 double orc_rhs_norm(void*);
+int orc_neumann_rows(void*, int, int, int, int, int, int64_t, const double*, const double*, int, const int32_t*, int, const double*);
 }
 
 struct isl_engine {
@@ -43,7 +44,7 @@ struct isl_engine {
     void* sys = nullptr;
     int64_t n = 0;
     bool finished = false;
-    int shape = 0, npe = 0;
+    int shape = 0, npe = 0, dim = 0;
     int64_t nElems = 0;
     struct F { int deg = 0, ds = 0; int64_t nObj = 0; std::vector<int64_t> elemDof, eqn; std::vector<uint8_t> status;
                std::vector<double> presc, values;
@@ -52,12 +53,12 @@ struct isl_engine {
 };
 static std::string g_err;
 // ISL_MOCK_TRACE=1: count the ABI calls and print them at exit (which path did the application take?)
-static long g_calls[6] = {0, 0, 0, 0, 0, 0};  // assemble_matrix, assemble_residual, assemble_bodyforce, insert_lhs, insert_rhs, solve_cg
+static long g_calls[7] = {0, 0, 0, 0, 0, 0, 0};  // assemble_matrix, assemble_residual, assemble_bodyforce, insert_lhs, insert_rhs, solve_cg, assemble_neumann
 static struct TraceAtExit {
     ~TraceAtExit() {
         if (std::getenv("ISL_MOCK_TRACE"))
-            std::fprintf(stderr, "[mock abi] assemble_matrix %ld  assemble_residual %ld  assemble_bodyforce %ld  insert_lhs %ld  insert_rhs %ld  solve_cg %ld\n",
-                         g_calls[0], g_calls[1], g_calls[2], g_calls[3], g_calls[4], g_calls[5]);
+            std::fprintf(stderr, "[mock abi] assemble_matrix %ld  assemble_residual %ld  assemble_bodyforce %ld  insert_lhs %ld  insert_rhs %ld  solve_cg %ld  assemble_neumann %ld\n",
+                         g_calls[0], g_calls[1], g_calls[2], g_calls[3], g_calls[4], g_calls[5], g_calls[6]);
     }
 } g_trace;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -72,7 +73,7 @@ int isl_mesh_set(isl_handle h, int shape, int gdeg, int dim, int64_t nn, const d
     if (gdeg != 1) return fail("mock ABI: geometry degree 1 only");
     std::vector<int64_t> c(conn, conn + ne * npe);
     orc_set_mesh(h->prob, shape, gdeg, dim, nn, x, ne, c.data());
-    h->shape = shape; h->npe = npe; h->nElems = ne;
+    h->shape = shape; h->npe = npe; h->nElems = ne; h->dim = dim;
     return 0;
 }
 int isl_mesh_update_coords(isl_handle, const double*) { return fail("mock ABI: isl_mesh_update_coords not provided"); }
@@ -154,6 +155,12 @@ int isl_assemble_bodyforce(isl_handle h, const double* f, int q, int t) {
 int isl_assemble_bodyforce_sampled(isl_handle h, const double* v, int q, int t) {
     g_calls[2]++;
     return orc_bodyforce_sampled(h->sys, h->prob, v, q, t) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_neumann_rows(isl_handle h, int shape, int gdeg, int64_t nSurf, const double* sx, const double* sp, int q, int feDeg,
+                              int ds, const int32_t* rows, int mode, const double* data) {
+    g_calls[6]++;
+    const int dim = (shape == ISL_TET || shape == ISL_HEX) ? 3 : 2;
+    return orc_neumann_rows(h->sys, shape, gdeg, dim, feDeg, ds, nSurf, sx, sp, q, rows, mode, data);
 }
 int isl_insert_lhs(isl_handle h, const double* m, const int64_t* r, int nr, const int64_t* c, int nc) {
     g_calls[3]++;

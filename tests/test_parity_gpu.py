@@ -32,6 +32,10 @@ CASES = [
     ("stvenant_q2_hex", 3, True, True), ("stvenant_p2_tet", 3, True, True),
     # heat::Laplace with a conductivity function sampled per quadrature point (isl_assemble_matrix_sampled)
     ("laplace_q1_hex_kappafun", 6, True, True), ("laplace_p2_tet_kappafun", 3, True, False),
+    # surface (Neumann) terms in one launch: isl_assemble_neumann with a sampled f(x, n), a pressure, a constant traction;
+    # quadrilateral / triangle / line surface elements, Dirichlet on a part of the boundary, linear constraints
+    ("neumann_q1_hex", 6, True, True), ("neumann_q1_hex", 5, False, False), ("neumann_p2_tet_solid", 3, True, True),
+    ("neumann_p2_tri", 6, True, False), ("neumann_q1_quad_solid", 7, True, True),
 ]
 
 
@@ -354,3 +358,28 @@ def test_rowgather_kernel_equals_oracle(monkeypatch, threads, rows):
             assert r2["pattern_equal"] and r2["val_diff"] <= TOL and r2["rhs_diff"] <= TOL, r2
     finally:
         e.close()
+
+
+def test_neumann_with_explicit_rows_equals_field_form(eng):
+    """isl_assemble_neumann_rows (equation numbers per surface element, what the reference-tree binding passes) adds the
+    same right-hand side as the field form"""
+    c = flows.build_case("neumann_q1_hex", 5, True, False)
+    a = c.run_engine(eng=eng)
+    f = c.fields[0]
+    op = [o for o in c.ops if o[0] == "neumann"][0]
+    de, sx, sp = c.surface_elements(op, E)
+    mode, data = c.surface_force(op, sx, E.surface_points)
+    rows = np.where(f["status"] == 0, f["eqn"], -1)[f["elem_dof"][de]].reshape(len(de), -1)
+    c.ops = [o for o in c.ops if o[0] != "neumann"]
+    eng.set_mesh(c.shape, c.geom_deg, c.coords, c.conn)
+    eng.set_field(0, f["fe_deg"], f["ds"], f["n_obj"], f["elem_dof"], f["eqn"], f["status"], f["presc"], f["values"])
+    eng.new_solver(c.n_eqn)
+    for o in c.ops:
+        if o[0] == "matrix":
+            eng.stiffness_matrix_computation(o[1], o[2], o[3], o[4], o[5], incremental=o[6])
+        else:
+            eng.body_force_computation(o[1], o[2], o[3])
+    eng.neumann_force_computation_rows(c.shape, c.geom_deg, sx, sp, op[2], f["fe_deg"], f["ds"], rows, mode, data)
+    b = eng.get_csr()
+    r = flows.compare(a, b)
+    assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r

@@ -240,6 +240,22 @@ def test_applications_use_the_assembly_entry_points_not_insert(tmp_path, name):
     assert n_matrix >= 1 and n_ins_lhs == 0 and n_ins_rhs == 0, m.group(0)
 
 
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["mixedPoisson_square020", "mixedPoissonWithDriver_square020", "compressible_neumann_quad010"])
+def test_applications_with_surface_forces_use_the_neumann_entry_point(tmp_path, name):
+    """base::asmb::neumannForceComputation on the B200 solver = one isl_assemble_neumann_rows call per invocation; the
+    reference's host loop (one insertToRHS per surface element) is not taken"""
+    import re
+    exe, args = RA.prepare(name, str(tmp_path))
+    p = subprocess.run([os.path.join(APPS_B200, exe + "_mock")] + args, cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, ISL_MOCK_TRACE="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    m = re.search(r"insert_lhs (\d+)\s+insert_rhs (\d+)\s+solve_cg (\d+)\s+assemble_neumann (\d+)", p.stderr)
+    assert m, p.stderr[-500:]
+    n_ins_lhs, n_ins_rhs, _, n_neumann = map(int, m.groups())
+    assert n_neumann >= 1 and n_ins_lhs == 0 and n_ins_rhs == 0, m.group(0)
+
+
 @needs_ref
 def test_binding_included_too_late_is_a_compile_error(tmp_path):
     """without `-include insilico_b200_reference.hpp` the reference's driver facade would select the reference's generic

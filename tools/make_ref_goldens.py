@@ -60,6 +60,11 @@ CASES = [
     ("laplace_q1_hex_bodyfun_n4", "laplace_q1_hex_bodyfun", "laplace_q1_hex", 4, True, False, False),
     ("laplace_p2_tri_bodyfun_n4", "laplace_p2_tri_bodyfun", "laplace_p2_tri", 4, True, False, False),
     ("vector_laplace_q1_hex_bodyfun_n3", "vector_laplace_q1_hex_bodyfun", "vector_laplace_q1_hex", 3, True, True, False),
+    # surface (Neumann) terms: base::asmb::neumannForceComputation over boundary meshes (NeumannForce.hpp, generateBoundaryMesh.hpp)
+    ("neumann_q1_hex_n4", "neumann_q1_hex", "laplace_q1_hex", 4, True, False, False),
+    ("neumann_p2_tet_solid_n2", "neumann_p2_tet_solid", "solid_p2_tet", 2, True, True, False),
+    ("neumann_p2_tri_n4", "neumann_p2_tri", "laplace_p2_tri", 4, True, False, False),
+    ("neumann_q1_quad_solid_n5", "neumann_q1_quad_solid", "solid_q1_quad", 5, True, False, True),
     # general linear constraints (slave DoFs with weighted ACTIVE masters, asmb/assembleMatrix.hpp:212-338)
     ("laplace_q1_hex_linear_n5", "laplace_q1_hex_linear", "laplace_q1_hex", 5, True, False, False),
     ("laplace_q1_hex_linear_n4_reg", "laplace_q1_hex_linear", "laplace_q1_hex", 4, False, False, True),
@@ -103,7 +108,12 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
         vf = os.path.join(workdir, "values%d.bin" % i)
         np.ascontiguousarray(f["presc"], dtype=np.float64).tofile(pf)
         np.ascontiguousarray(f["values"], dtype=np.float64).tofile(vf)
-        lines.append("field %d %d %d %s %s" % (i, boundary, pin, pf, vf))
+        line = "field %d %d %d %s %s" % (i, boundary, pin, pf, vf)
+        if boundary == 2:    # Dirichlet on a part of the boundary: the status table says which DoF components
+            sf = os.path.join(workdir, "status%d.bin" % i)
+            np.ascontiguousarray(f["status"] == E.CONSTRAINED, dtype=np.float64).tofile(sf)
+            line += " " + sf
+        lines.append(line)
         for obj, comp, rhs, masters in f["linear"]:
             lines.append("constraint %d %d %d %.17g %d %s" % (i, obj, comp, rhs, len(masters), " ".join(
                 "%d %d %.17g" % m for m in masters)))
@@ -118,6 +128,8 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
                                                         " ".join("%.17g" % p for p in op[2])))
         elif op[0] == "bodyfun":
             lines.append("op bodyfun %s %d %d 1" % (BODYFUN_NAME[case_name(case)], op[3], op[3]))
+        elif op[0] == "neumann":   # op neumann <force name> test test <face filter> params
+            lines.append("op neumann %s %d %d %d %s" % (op[1], op[3], op[3], int(op[4]), " ".join("%.17g" % p for p in op[5])))
         elif op[0] == "body":
             lines.append("op body body %d %d 1 %s" % (op[3], op[3], " ".join("%.17g" % p for p in op[1])))
     job = os.path.join(workdir, "job.txt")
@@ -153,7 +165,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     from oracle import oracle as orc  # checker; used here only to report the agreement while generating
     worst = 0.0
+    only = sys.argv[1] if len(sys.argv) > 1 else ""     # e.g. `make_ref_goldens.py neumann`: the cases whose name contains it
     for gname, cname, dtype_, n, perturb, permute, register in CASES:
+        if only not in gname:
+            continue
         case = flows.build_case(cname, n, perturb, permute)
         with tempfile.TemporaryDirectory() as wd:
             ref = run_reference(case, dtype_, register, wd)
