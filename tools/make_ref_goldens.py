@@ -84,15 +84,9 @@ def case_name(case):
 
 
 def write_smf(path, shape, coords, conn):
-    """SMF as base/io/smf/Reader.hpp:66-330 reads it; 17 significant digits so that the doubles round-trip exactly."""
-    c3 = np.zeros((coords.shape[0], 3))
-    c3[:, :coords.shape[1]] = coords
-    with open(path, "w") as f:
-        f.write("! elementShape %s\n! elementNumPoints %d\n%d %d\n" % (SHAPE_NAME[shape], conn.shape[1], len(c3), len(conn)))
-        for x in c3:
-            f.write("%.17g %.17g %.17g\n" % tuple(x))
-        for e in conn:
-            f.write(" ".join(str(int(v)) for v in e) + "\n")
+    """SMF as base/io/smf/Reader.hpp:66-330 reads it (insilico_b200.smf.write: 17 significant digits, doubles round-trip)"""
+    from insilico_b200 import smf
+    smf.write(path, shape, coords, conn)
 
 
 def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
