@@ -47,8 +47,11 @@ enum {
     ISL_K_VELOCITY_DIVERGENCE = 5, /* fluid::VelocityDivergence (fluid/VelocityDivergence.hpp:67-124);
                                       params = {changeSign != 0}                                       */
     ISL_K_VECTOR_LAPLACE = 6,      /* fluid::VectorLaplace (fluid/VectorLaplace.hpp:40-112); {viscosity}   */
-    ISL_K_MASS = 7                 /* base::kernel::Mass (base/kernel/Mass.hpp:88-138), matrix only; {factor}: entry =
+    ISL_K_MASS = 7,                /* base::kernel::Mass (base/kernel/Mass.hpp:88-138), matrix only; {factor}: entry =
                                       factor detJ w phi_M psi_N on every DoF component (time stepping, L2 projections) */
+    ISL_K_CONVECTION = 8           /* fluid::Convection (fluid/Convection.hpp:88-220, Picard form), {density}: tangent entry =
+                                      phi_M (uAdv . grad phi_N + 0.5 div(u) phi_N) rho detJ w on every component, uAdv from the
+                                      tuple's third field; residual rho (u . grad) u_aux phi_M.  Through the _aux entry points. */
 };
 
 typedef struct isl_engine* isl_handle;
@@ -138,6 +141,12 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field);
  * (base/asmb/StiffnessMatrix.hpp:49-87): K scattered into CSR, Dirichlet lift into rhs                      */
 int isl_assemble_matrix(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,
                         int trial_field, int incremental);
+/* kernels that read a third field of the tuple (FieldTupleBinder<I,J,K>: AuxField1Element, base/asmb/FieldTupleBinder.hpp),
+ * e.g. fluid::Convection with the advection velocity; aux_field = its index (same FE basis as the trial field)            */
+int isl_assemble_matrix_aux(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field, int trial_field,
+                            int aux_field, int incremental);
+int isl_assemble_residual_aux(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field, int trial_field,
+                              int aux_field, double factor);
 /* the same for heat::Laplace with a conductivity FUNCTION (heat/Laplace.hpp:85-126, setConductivityFunction): values[n_elems *
  * nq] = conductivity at the quadrature points of Quadrature<quad_deg> of every (owned) element, host or device pointer; the
  * caller's function runs on the host (like isl_assemble_bodyforce_sampled), the integration on the device.  Laplace kernels. */

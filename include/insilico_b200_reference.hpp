@@ -49,6 +49,7 @@
 #include <base/asmb/BodyForce.hpp>
 #include <base/asmb/NeumannForce.hpp>
 #include <base/kernel/Mass.hpp>
+#include <fluid/Convection.hpp>
 #include <heat/Laplace.hpp>
 #include <heat/Static.hpp>
 #include <mat/thermal/IsotropicConstant.hpp>
@@ -432,6 +433,7 @@ struct TupleIndices;
 template <typename EPT, int I, int J, int K, int L, int M>
 struct TupleIndices<base::asmb::FieldTupleBinder<EPT, I, J, K, L, M> > {
     static const int test = I - 1, trial = J - 1;  // the engine addresses fields 0-based
+    static const int aux = (K > 0 ? K - 1 : -1);    // AuxField1 of the tuple (fluid::Convection: the advection velocity)
 };
 
 template <typename QUADRATURE>
@@ -504,7 +506,7 @@ struct B200KernelTraits {
     static_assert(sizeof(KERNEL) == 0,
                   "this kernel object has no implementation in the B200 assembly engine (supported: heat::Laplace, base::kernel::Mass, "
                   "heat::Static<mat::thermal::IsotropicConstant>, fluid::VectorLaplace, fluid::PressureGradient, "
-                  "fluid::VelocityDivergence, solid::HyperElastic<mat::hypel::StVenant | NeoHookeanCompressible>); "
+                  "fluid::VelocityDivergence, fluid::Convection, solid::HyperElastic<mat::hypel::StVenant | NeoHookeanCompressible>); "
                   "there is no CPU fallback");
 };
 
@@ -574,6 +576,30 @@ struct B200KernelTraits<base::kernel::Mass<TUPLE> > {
     static int describe(const base::kernel::Mass<TUPLE>& k, const TUPLE& t0, const TUPLE&, double* p) {
         p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t0), Make(), t0);
         return ISL_K_MASS;
+    }
+};
+
+//! fluid::Convection (fluid/Convection.hpp:88-220, Picard form): rho * (terms of the current velocity state).  The density
+//! is private: K = rho * K(1) on an element whose velocity state is not zero.  p[2] = 1 reports that both probed elements
+//! are at rest; b200_detail::LateProbe then looks further (and skips the launch if the whole field is at rest).
+template <typename TUPLE>
+struct B200KernelTraits<fluid::Convection<TUPLE> > {
+    struct Make {
+        fluid::Convection<TUPLE> operator()(double c) const { return fluid::Convection<TUPLE>(c); }
+    };
+    static bool probe(const fluid::Convection<TUPLE>& k, const TUPLE& t, double* p) {
+        if (b200_detail::maxAbs(b200_detail::probeTangent(Make()(1.0), t)) == 0.) return false;
+        p[0] = b200_detail::probeScalar(b200_detail::probeTangent(k, t), Make(), t);
+        return true;
+    }
+    static int describe(const fluid::Convection<TUPLE>& k, const TUPLE& t0, const TUPLE& t1, double* p) {
+#ifdef ISL_B200_HAVE_KERNEL_ACCESSORS   // `double density() const`
+        (void)t0; (void)t1;
+        p[0] = k.density();
+        return ISL_K_CONVECTION;
+#endif
+        if (!probe(k, t0, p) && !probe(k, t1, p)) p[2] = 1.0;
+        return ISL_K_CONVECTION;
     }
 };
 
@@ -967,6 +993,27 @@ struct SampledFactor<heat::Laplace<TUPLE> > {
 };
 }  // namespace b200_detail
 
+namespace b200_detail {
+//! kernels whose constant cannot be probed on an element at rest (fluid::Convection): look at more elements.
+//! resolve() returns false when the contribution is identically zero (every element at rest): nothing to launch.
+template <typename KERNEL>
+struct LateProbe {
+    template <typename FTB, typename FIELDBINDER>
+    static bool resolve(const KERNEL&, const FIELDBINDER&, double*) { return true; }
+};
+template <typename TUPLE>
+struct LateProbe<fluid::Convection<TUPLE> > {
+    template <typename FTB, typename FIELDBINDER>
+    static bool resolve(const fluid::Convection<TUPLE>& k, const FIELDBINDER& fb, double* p) {
+        if (p[2] == 0.) return true;
+        p[2] = 0.;
+        for (typename FIELDBINDER::FieldIterator it = fb.elementsBegin(); it != fb.elementsEnd(); ++it)
+            if (base::solver::B200KernelTraits<fluid::Convection<TUPLE> >::probe(k, FTB::makeTuple(*it), p)) return true;
+        return false;
+    }
+};
+}  // namespace b200_detail
+
 //! base/asmb/StiffnessMatrix.hpp:49-87 for SOLVER = base::solver::B200
 template <typename FIELDTUPLEBINDER, typename QUADRATURE, typename FIELDBINDER, typename KERNEL>
 void stiffnessMatrixComputation(const QUADRATURE& quadrature, base::solver::B200& solver, const FIELDBINDER& fieldBinder,
@@ -979,6 +1026,7 @@ void stiffnessMatrixComputation(const QUADRATURE& quadrature, base::solver::B200
     const int id = base::solver::B200KernelTraits<KERNEL>::describe(
         kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
         b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
+    if (!b200_detail::LateProbe<KERNEL>::template resolve<FIELDTUPLEBINDER>(kernelObj, fieldBinder, params)) return;
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
     typedef b200_detail::SampledFactor<KERNEL> Sampled;
     if (params[3] != 0. || Sampled::template varies<FIELDTUPLEBINDER>(kernelObj, quadrature, fieldBinder, params[0])) {
@@ -989,8 +1037,8 @@ void stiffnessMatrixComputation(const QUADRATURE& quadrature, base::solver::B200
                                              TI::trial, incremental ? 1 : 0));
         return;
     }
-    D::check(isl_assemble_matrix(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
-                                 incremental ? 1 : 0));
+    D::check(isl_assemble_matrix_aux(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
+                                     TI::aux, incremental ? 1 : 0));
 }
 
 //! base/asmb/ForceIntegrator.hpp:37-71 for SOLVER = base::solver::B200 (forces enter the rhs with factor -1)
@@ -1006,9 +1054,10 @@ void computeResidualForces(const QUADRATURE&, base::solver::B200& solver, const 
         kernelObj, b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, false),
         b200_detail::probeTuple<FIELDTUPLEBINDER>(fieldBinder, true), params);
     VERIFY_MSG(params[3] == 0., "B200 engine: residual forces with a material factor that varies in space are not supported");
+    if (!b200_detail::LateProbe<KERNEL>::template resolve<FIELDTUPLEBINDER>(kernelObj, fieldBinder, params)) return;
     typedef D::TupleIndices<FIELDTUPLEBINDER> TI;
-    D::check(isl_assemble_residual(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
-                                   -1.0));
+    D::check(isl_assemble_residual_aux(D::engine(), id, params, D::QuadratureDegree<QUADRATURE>::value, TI::test, TI::trial,
+                                       TI::aux, -1.0));
 }
 
 //! base/asmb/BodyForce.hpp:65-84 for SOLVER = base::solver::B200.  The caller's function f(x) runs on the host, once per

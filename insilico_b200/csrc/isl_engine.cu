@@ -111,6 +111,8 @@ struct AsmParams {
     int body; double f[3];
     const double* fq;   // body == 2: force sampled at the quadrature points, [n_elems][nq][dst]
     const double* kq;   // Laplace kernels: conductivity sampled at the quadrature points, [n_elems][nq] (nullptr: constant p0)
+    // third field of the tuple (AuxField1; fluid::Convection: the advection velocity), same FE basis as the trial field
+    const int32_t* ed_a; const double* val_a; int dsa;
     // linear constraints with master DoFs (nullptr when the field has none): per DoF component k the masters
     // [cptr[k], cptr[k+1]) as equation numbers cm[] with weights cw[]; CSR pattern for the entries they reach
     const int32_t* cptr_t; const int32_t* cm_t; const double* cw_t;
@@ -273,6 +275,26 @@ __device__ void trial_gradient(const AsmParams& p, const Stage<DIM>& s, int64_t 
     }
 }
 
+// the same for the auxiliary field (same basis as the trial field), and field values u(xi_q) = sum_f phi_f u_f
+// (base/post/evaluateField.hpp)
+template <int DIM>
+__device__ void aux_gradient(const AsmParams& p, const Stage<DIM>& s, int64_t e, int eq, double GradU[3][3]) {
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) GradU[a][b] = 0.;
+    const double* g = s.sGc + (size_t)eq * p.nc * DIM;
+    for (int f = 0; f < p.nc; f++) {
+        const int32_t obj = p.ed_a[e * p.nc + f];
+        for (int J = 0; J < DIM; J++)
+            for (int i = 0; i < p.dsa; i++) GradU[J][i] += g[f * DIM + J] * p.val_a[(size_t)obj * p.dsa + i];
+    }
+}
+__device__ __forceinline__ void field_value(const AsmParams& p, const int32_t* ed, const double* val, int ds, int64_t e, int q, double u[3]) {
+    for (int i = 0; i < 3; i++) u[i] = 0.;
+    for (int f = 0; f < p.nc; f++) {
+        const int32_t obj = ed[e * p.nc + f];
+        for (int i = 0; i < ds; i++) u[i] += p.Nc[q * p.nc + f] * val[(size_t)obj * ds + i];
+    }
+}
+
 template <int DIM>
 __device__ void deformation_gradient(const AsmParams& p, const Stage<DIM>& s, int64_t e, int eq, double F[3][3]) {
     double GradU[3][3];
@@ -385,6 +407,34 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     acc += (p.p0 * s.sDet[eb * p.nq + q] * p.w[q]) * p.Nt[q * p.nt + M] * p.Nc[q * p.nc + N];
                 for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
             }
+        } else if (p.kernel_id == ISL_K_CONVECTION) {
+            // fluid/Convection.hpp:88-166 (Picard form): phi_M (uAdv . grad phi_N + 0.5 div(u) phi_N) rho detJ w on every
+            // component; uAdv from the auxiliary field, div(u) of the trial field's current state, hoisted per point
+            for (int t = tid; t < nb * p.nq; t += nth) {
+                const int eb = t / p.nq, q = t % p.nq;
+                const int64_t e = p.eid(base + eb);
+                double u[3], G[3][3];
+                field_value(p, p.ed_a, p.val_a, p.dsa, e, q, u);
+                trial_gradient<DIM>(p, s, e, t, G);
+                double div = 0.;
+                for (int d = 0; d < p.dsc; d++) div += G[d][d];
+                double* qd = s.sQ + (size_t)t * 4;
+                qd[0] = u[0]; qd[1] = u[1]; qd[2] = u[2]; qd[3] = div;
+            }
+            __syncthreads();
+            for (int t = tid; t < nb * p.nt * p.nc; t += nth) {
+                const int eb = t / (p.nt * p.nc), mn = t % (p.nt * p.nc), M = mn / p.nc, N = mn % p.nc;
+                double acc = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double* gN = s.sGc + ((size_t)eq * p.nc + N) * DIM;
+                    const double* qd = s.sQ + (size_t)eq * 4;
+                    double adv = 0.;
+                    for (int k = 0; k < p.dst; k++) adv += qd[k] * gN[k];
+                    acc += p.Nt[q * p.nt + M] * (adv + 0.5 * qd[3] * p.Nc[q * p.nc + N]) * p.p0 * s.sDet[eq] * p.w[q];
+                }
+                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+            }
         } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
             // B(M d + i, N) = -detJ w g_M[i] psi_N
             for (int t = tid; t < nb * nr * ncl; t += nth) {
@@ -438,6 +488,15 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
                     material_eval(p.kernel_id, p.p0, p.p1, F, S, C, false);
                     for (int i = 0; i < 3; i++)
                         for (int j = 0; j < 3; j++) qd[i * 3 + j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
+                } else if (p.kernel_id == ISL_K_CONVECTION) {   // fluid/Convection.hpp:170-220: (U . grad) u_aux
+                    double U[3], G[3][3];
+                    field_value(p, p.ed_c, p.val_c, p.dsc, e, q, U);
+                    aux_gradient<DIM>(p, s, e, t, G);
+                    for (int i = 0; i < 3; i++) {
+                        double cd = 0.;
+                        for (int k = 0; k < p.dst; k++) cd += U[k] * G[k][i];
+                        qd[i] = cd;
+                    }
                 } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
                     double pr = 0.;
                     for (int f = 0; f < p.nc; f++) pr += p.Nc[q * p.nc + f] * p.val_c[(size_t)p.ed_c[e * p.nc + f] * p.dsc];
@@ -483,6 +542,9 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
                     } break;
                     case ISL_K_PRESSURE_GRADIENT:  // fluid/PressureGradient.hpp:130-155
                         if (ci < DIM) acc += -gM[ci] * qd[0] * detJ * w;
+                        break;
+                    case ISL_K_CONVECTION:
+                        acc += p.p0 * qd[ci] * p.Nt[q * p.nt + M] * detJ * w;
                         break;
                     case ISL_K_VELOCITY_DIVERGENCE: {  // fluid/VelocityDivergence.hpp:100-124
                         double div = 0.;
@@ -1198,6 +1260,9 @@ void check_kernel_fields(isl_engine* h, int kid, int t, int c, bool tangent) {
             break;
         case ISL_K_PRESSURE_GRADIENT:
             ISL_REQUIRE(ft.ds == h->dim && fc.ds == 1, "PressureGradient: test = velocity (dim), trial = pressure (1)");
+            break;
+        case ISL_K_CONVECTION:
+            ISL_REQUIRE(ft.ds == h->dim && fc.ds == h->dim, "fluid::Convection: test and trial must be velocity fields (DoF size = dimension)");
             break;
         case ISL_K_VELOCITY_DIVERGENCE:
             ISL_REQUIRE(ft.ds == 1 && fc.ds == h->dim, "VelocityDivergence: test = pressure (1), trial = velocity (dim)");
@@ -2270,7 +2335,21 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
     });
 }
 
+namespace {
+// the third field of the tuple for kernels that read one (fluid::Convection): same basis as the trial field
+void bind_aux(isl_engine* h, AsmParams& p, int kid, int c, int aux) {
+    if (kid != ISL_K_CONVECTION) return;
+    ISL_REQUIRE(aux >= 0 && aux < 5 && h->fields[aux].set, "fluid::Convection needs the advection velocity as third field of the tuple (isl_assemble_matrix_aux)");
+    const FieldDev& fa = h->fields[aux]; const FieldDev& fc = h->fields[c];
+    ISL_REQUIRE(fa.deg == fc.deg && fa.ndpe == fc.ndpe && fa.ds == h->dim, "fluid::Convection: the advection velocity must have the trial field's basis and DoF size = dimension");
+    p.ed_a = fa.elem_dof.p; p.val_a = fa.values.p; p.dsa = fa.ds;
+}
+}  // namespace
+
 int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, int incremental) {
+    return isl_assemble_matrix_aux(h, kid, params, quad_deg, t, c, -1, incremental);
+}
+int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, int aux, int incremental) {
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
@@ -2312,7 +2391,8 @@ int isl_assemble_matrix(isl_handle h, int kid, const double* params, int quad_de
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT && kid != ISL_K_MASS);
-        p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : 0;
+        p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : (kid == ISL_K_CONVECTION ? 4 : 0);
+        bind_aux(h, p, kid, c, aux);
         if (h->tangent_sym && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == 3 && h->dim == 3 && t == c &&
             !ft.has_masters && ft.ndpe <= 27) {
             launch_hypel_sym(h, p);
@@ -2351,6 +2431,9 @@ int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int
 }
 
 int isl_assemble_residual(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, double factor) {
+    return isl_assemble_residual_aux(h, kid, params, quad_deg, t, c, -1, factor);
+}
+int isl_assemble_residual_aux(isl_handle h, int kid, const double* params, int quad_deg, int t, int c, int aux, double factor) {
     return guarded([&] {
         ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
@@ -2365,6 +2448,7 @@ int isl_assemble_residual(isl_handle h, int kid, const double* params, int quad_
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE);
         p.need_gc = (kid != ISL_K_PRESSURE_GRADIENT);
         p.nqdata = 9;
+        bind_aux(h, p, kid, c, aux);
         if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
     });
 }

@@ -27,6 +27,7 @@ ACTIVE, CONSTRAINED, INACTIVE = range(3)
 K_LAPLACE, K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE, K_PRESSURE_GRADIENT, K_VELOCITY_DIVERGENCE, K_VECTOR_LAPLACE = (
     1, 2, 3, 4, 5, 6)
 K_MASS = 7
+K_CONVECTION = 8
 SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
 
 # every symbol include/insilico_b200.h declares (checked by tests/test_cabi.py)
@@ -37,7 +38,7 @@ EXPORTED = [
     "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
-    "isl_assemble_matrix", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
+    "isl_assemble_matrix", "isl_assemble_matrix_aux", "isl_assemble_residual_aux", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
     "isl_insert_rhs",
     "isl_finish", "isl_get_csr", "isl_get_csr_async", "isl_copy_wait", "isl_get_device_csr", "isl_rhs_value", "isl_rhs_norm", "isl_solve_cg", "isl_pack_entries",
     "isl_unpack_add_entries", "isl_boundary_surface", "isl_surface_points", "isl_assemble_neumann", "isl_assemble_neumann_rows",
@@ -319,18 +320,19 @@ class Engine:
             raise EngineError("kernel %d needs %d parameters (lambda, mu), got %d" % (kernel_id, need, len(params)))
         return params
 
-    def stiffness_matrix_computation(self, kernel_id, params, quad_deg, test, trial, incremental=True):
+    def stiffness_matrix_computation(self, kernel_id, params, quad_deg, test, trial, incremental=True, aux=-1):
+        """aux: index of the tuple's third field for kernels that read one (fluid::Convection: the advection velocity)"""
         params = self._params(kernel_id, params)
-        _chk(lib().isl_assemble_matrix(self.h, kernel_id, _ptr(params), quad_deg, test, trial, int(incremental)))
+        _chk(lib().isl_assemble_matrix_aux(self.h, kernel_id, _ptr(params), quad_deg, test, trial, aux, int(incremental)))
 
     def stiffness_matrix_computation_sampled(self, kernel_id, values, quad_deg, test, trial, incremental=True):
         """asmb::stiffnessMatrixComputation with heat::Laplace + conductivity function: values [n_elems, nq] at the points"""
         values = np.ascontiguousarray(values, dtype=np.float64)
         _chk(lib().isl_assemble_matrix_sampled(self.h, kernel_id, _ptr(values), quad_deg, test, trial, int(incremental)))
 
-    def compute_residual_forces(self, kernel_id, params, quad_deg, test, trial, factor=-1.0):
+    def compute_residual_forces(self, kernel_id, params, quad_deg, test, trial, factor=-1.0, aux=-1):
         params = self._params(kernel_id, params)
-        _chk(lib().isl_assemble_residual(self.h, kernel_id, _ptr(params), quad_deg, test, trial, C.c_double(factor)))
+        _chk(lib().isl_assemble_residual_aux(self.h, kernel_id, _ptr(params), quad_deg, test, trial, aux, C.c_double(factor)))
 
     def body_force_computation(self, f, quad_deg, test):
         f = np.ascontiguousarray(f, dtype=np.float64)

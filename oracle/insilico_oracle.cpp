@@ -799,11 +799,13 @@ enum KernelId {
     K_PRESSURE_GRADIENT = 4, // fluid::PressureGradient
     K_VELOCITY_DIVERGENCE = 5, // fluid::VelocityDivergence (params[0] != 0 : changeSign)
     K_VECTOR_LAPLACE = 6,    // fluid::VectorLaplace (tangent == K_LAPLACE; own residual)
-    K_MASS = 7               // base::kernel::Mass (params[0] = factor, e.g. the density)
+    K_MASS = 7,              // base::kernel::Mass (params[0] = factor, e.g. the density)
+    K_CONVECTION = 8         // fluid::Convection (params[0] = density), needs the tuple's AuxField1
 };
 
 struct Tuple {  // asmb/FieldElementPointerTuple.hpp : (geom, test, trial)
     const Problem* p; int64_t e; const Field* test; const Field* trial;
+    const Field* aux = nullptr;                     // AuxField1 of the tuple (fluid::Convection: the advection velocity)
     bool bubnov() const { return test == trial; }  // auxi/EqualPointers
 };
 
@@ -1085,6 +1087,45 @@ static void velocityDivergenceResidual(const Tuple& t, bool changeSign, const do
     const double detJ = jacobian(m, t.e, xi);
     for (int M = 0; M < t.test->ndpe; M++) v[M] += (changeSign ? -1.0 : +1.0) * testF[M] * divU * detJ * weight;
 }
+// fluid/Convection.hpp:88-166 (NEWTON not defined: the Picard form).  uAdv from AuxField1, divergence of the TRIAL field
+static void convectionTangent(const Tuple& t, double density, const double* xi, double weight, LocalMat& K) {
+    const Mesh& m = t.p->mesh;
+    const int n = t.test->dofSize;
+    double uAdv[3];
+    evaluateField(t, *t.aux, xi, uAdv);
+    double GradU[3][3];
+    evaluateFieldGradient(t, *t.trial, xi, GradU);
+    double divUAdv = 0.;
+    for (int d = 0; d < t.trial->dofSize; d++) divUAdv += GradU[d][d];
+    std::vector<double> trialG;
+    const double detJ = evaluateGradient(m, t.trial->feFun, t.e, xi, trialG);
+    std::vector<double> testF(t.test->ndpe), trialF(t.trial->ndpe);
+    t.test->feFun.fun(xi, testF.data());
+    t.trial->feFun.fun(xi, trialF.data());
+    for (int M = 0; M < t.test->ndpe; M++)
+        for (int N = 0; N < t.trial->ndpe; N++) {
+            double advTrial = 0.;
+            for (int k = 0; k < n; k++) advTrial += uAdv[k] * trialG[N * m.dim + k];
+            const double entry = testF[M] * (advTrial + 0.5 * divUAdv * trialF[N]) * density * detJ * weight;
+            for (int k = 0; k < n; k++) K(M * n + k, N * n + k) += entry;
+        }
+}
+// fluid/Convection.hpp:170-220: U from the trial field, gradU from AuxField1
+static void convectionResidual(const Tuple& t, double density, const double* xi, double weight, std::vector<double>& v) {
+    const Mesh& m = t.p->mesh;
+    const int n = t.test->dofSize;
+    std::vector<double> testF(t.test->ndpe);
+    t.test->feFun.fun(xi, testF.data());
+    const double detJ = jacobian(m, t.e, xi);
+    double gradU[3][3], U[3];
+    evaluateFieldGradient(t, *t.aux, xi, gradU);
+    evaluateField(t, *t.trial, xi, U);
+    for (int i = 0; i < n; i++) {
+        double convectiveDeriv = 0.;
+        for (int k = 0; k < n; k++) convectiveDeriv += U[k] * gradU[k][i];
+        for (int M = 0; M < t.test->ndpe; M++) v[M * n + i] += density * convectiveDeriv * testF[M] * detJ * weight;
+    }
+}
 // asmb/BodyForce.hpp:172-205 with a constant force vector f
 static void bodyForceKernel(const Tuple& t, const double* f, const double* xi, double weight, std::vector<double>& v) {
     const Mesh& m = t.p->mesh;
@@ -1106,6 +1147,7 @@ static void tangentKernel(int kid, const double* params, const Tuple& t, const d
         case K_PRESSURE_GRADIENT: pressureGradientTangent(*t.p, t.e, *t.test, *t.trial, xi, w, K); break;
         case K_VELOCITY_DIVERGENCE: velocityDivergenceTangent(t, params[0] != 0., xi, w, K); break;
         case K_MASS: massTangent(t, params[0], xi, w, K); break;
+        case K_CONVECTION: convectionTangent(t, params[0], xi, w, K); break;
         default: std::abort();
     }
 }
@@ -1120,6 +1162,7 @@ static void residualKernel(int kid, const double* params, const Tuple& t, const 
         } break;
         case K_PRESSURE_GRADIENT: pressureGradientResidual(t, xi, w, v); break;
         case K_VELOCITY_DIVERGENCE: velocityDivergenceResidual(t, params[0] != 0., xi, w, v); break;
+        case K_CONVECTION: convectionResidual(t, params[0], xi, w, v); break;
         default: std::abort();
     }
 }
@@ -1301,9 +1344,10 @@ static void assembleForces(const std::vector<double>& f, const std::vector<uint8
 // sampled != nullptr: heat::Laplace with a conductivity function (heat/Laplace.hpp:85-126): the factor of the Laplace kernel
 // at quadrature point g of element e is sampled[e * nq + g] (the caller evaluated its function there)
 static void stiffnessElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
-                             int trialId, bool incremental, int64_t e, const double* sampled = nullptr) {
+                             int trialId, bool incremental, int64_t e, const double* sampled = nullptr, int auxId = -1) {
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
+    if (auxId >= 0) t.aux = &p.fields[auxId];
     std::vector<uint8_t> rS, cS; std::vector<size_t> rID, cID; std::vector<double> rV, cV;
     Constraints rCon, cCon;
     bool doSomething = collectFromDoFs(test, e, rS, rID, rV, rCon, incremental);
@@ -1321,9 +1365,10 @@ static void stiffnessElement(const Problem& p, System& solver, const Quad& q, in
 
 // asmb/ForceIntegrator.hpp:126-160 ; body = 2: params holds f(x) sampled at the quadrature points, [nElems][nq][dofSize]
 static void forceElement(const Problem& p, System& solver, const Quad& q, int kid, const double* params, int testId,
-                         int trialId, double factor, int body, int64_t e) {
+                         int trialId, double factor, int body, int64_t e, int auxId = -1) {
     const Field& test = p.fields[testId]; const Field& trial = p.fields[trialId];
     Tuple t{&p, e, &test, &trial};
+    if (auxId >= 0) t.aux = &p.fields[auxId];
     std::vector<uint8_t> st; std::vector<size_t> ids; std::vector<double> pv;
     Constraints con;
     if (!collectFromDoFs(test, e, st, ids, pv, con, false)) return;
@@ -1526,6 +1571,19 @@ int orc_stiffness(void* s, void* h, int kid, const double* params, int quadDeg, 
 #pragma omp parallel for num_threads(nthreads)
 #endif
     for (int64_t e = 0; e < p.mesh.nElems; e++) stiffnessElement(p, sys, q, kid, params, test, trial, incremental != 0, e);
+    return sys.error.empty() ? 0 : -1;
+}
+// kernels that read a third field of the tuple (FieldTupleBinder<I,J,K>: AuxField1), e.g. fluid::Convection
+int orc_stiffness_aux(void* s, void* h, int kid, const double* params, int quadDeg, int test, int trial, int aux, int incremental) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) stiffnessElement(p, sys, q, kid, params, test, trial, incremental != 0, e, nullptr, aux);
+    return sys.error.empty() ? 0 : -1;
+}
+int orc_residual_aux(void* s, void* h, int kid, const double* params, int quadDeg, int test, int trial, int aux) {
+    Problem& p = *(Problem*)h; System& sys = *(System*)s;
+    Quad q = makeQuadrature(p.mesh.shape, quadDeg);
+    for (int64_t e = 0; e < p.mesh.nElems; e++) forceElement(p, sys, q, kid, params, test, trial, -1.0, 0, e, aux);
     return sys.error.empty() ? 0 : -1;
 }
 // heat::Laplace with setConductivityFunction (heat/Laplace.hpp:85-126): values [nElems][nq] = conductivity at the points

@@ -17,6 +17,7 @@ POINT, LINE, TRI, QUAD, TET, HEX = range(6)
 VERTEX, EDGE, FACE, CELL = range(4)
 ACTIVE, CONSTRAINED, INACTIVE = range(3)
 K_MASS = 7
+K_CONVECTION = 8
 K_LAPLACE, K_HYPEL_STVENANT, K_HYPEL_NEOHOOKE, K_PRESSURE_GRADIENT, K_VELOCITY_DIVERGENCE, K_VECTOR_LAPLACE = (
     1, 2, 3, 4, 5, 6)
 SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
@@ -256,6 +257,15 @@ class System:
         """heat::Laplace with a conductivity function: values [n_elems, nq] = kappa at the quadrature points"""
         values = np.ascontiguousarray(values, dtype=np.float64)
         self._check(lib().orc_stiffness_sampled(self.h, prob.h, kid, _p(values), quad_deg, test, trial, int(incremental)))
+
+    def stiffness_aux(self, prob, kid, params, quad_deg, test, trial, aux, incremental=True):
+        """kernels reading a third field of the tuple (fluid::Convection: the advection velocity)"""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(lib().orc_stiffness_aux(self.h, prob.h, kid, _p(params), quad_deg, test, trial, aux, int(incremental)))
+
+    def residual_aux(self, prob, kid, params, quad_deg, test, trial, aux):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._check(lib().orc_residual_aux(self.h, prob.h, kid, _p(params), quad_deg, test, trial, aux))
 
     def bodyforce_sampled(self, prob, values, quad_deg, test):
         """asmb::bodyForceComputation with a general f(x): values [n_elems, nq, ds] = f at the quadrature points"""

@@ -42,6 +42,7 @@
 #include <base/kernel/Mass.hpp>
 #include <heat/Laplace.hpp>
 #include <fluid/Stokes.hpp>
+#include <fluid/Convection.hpp>
 #include <mat/Lame.hpp>
 #include <mat/hypel/StVenant.hpp>
 #include <mat/hypel/NeoHookeanCompressible.hpp>
@@ -348,6 +349,17 @@ int runSingle(const Job& job) {
                 base::asmb::stiffnessMatrixComputation<FTB>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
                 continue;
             }
+            if (op.kernel == "convection") {   // fluid::Convection on the tuple (test, trial, advection velocity) = (u, u, u)
+                if constexpr (KIND == VECTOR) {
+                    typedef typename FieldBinder::template TupleBinder<1, 1, 1>::Type UUU;
+                    fluid::Convection<typename UUU::Tuple> kernel(op.p[0]);
+                    if (op.what == "matrix")
+                        base::asmb::stiffnessMatrixComputation<UUU>(quadrature, solver, fieldBinder, kernel, op.incremental != 0);
+                    else
+                        base::asmb::computeResidualForces<UUU>(quadrature, solver, fieldBinder, kernel);
+                }
+                continue;
+            }
             if (op.what == "matrixfun") {   // heat::Laplace with a conductivity function
                 if constexpr (KIND == SCALAR) {
                     typedef heat::Laplace<typename FTB::Tuple> Kernel;
@@ -496,6 +508,7 @@ int main(int argc, char* argv[]) {
     if (t == "laplace_q1_quad") return runSingle<base::QUAD, 1, 1, 3, 3, SCALAR>(job);
     if (t == "laplace_p2_tri") return runSingle<base::TRI, 2, 1, 4, 4, SCALAR>(job);
     if (t == "vector_laplace_q1_hex") return runSingle<base::HEX, 1, 3, 3, 3, VECTOR>(job);
+    if (t == "vector_laplace_q2_quad") return runSingle<base::QUAD, 2, 2, 4, 4, VECTOR>(job);
     if (t == "solid_q1_hex") return runSingle<base::HEX, 1, 3, 3, 3, SOLID>(job);
     if (t == "solid_q2_hex") return runSingle<base::HEX, 2, 3, 4, 4, SOLID>(job);
     if (t == "solid_q1_quad") return runSingle<base::QUAD, 1, 2, 3, 3, SOLID>(job);

@@ -165,7 +165,11 @@ class Case:
                 if op[0] in ("matrix", "matrixfun"):
                     s.register_fields(prob, op[4], op[5])
         for op in self.ops:
-            if op[0] == "matrix":
+            if op[0] == "matrix" and len(op) > 7:     # a third field of the tuple (fluid::Convection: advection velocity)
+                s.stiffness_aux(prob, op[1], op[2], op[3], op[4], op[5], op[7], incremental=op[6])
+            elif op[0] == "residual" and len(op) > 6:
+                s.residual_aux(prob, op[1], op[2], op[3], op[4], op[5], op[6])
+            elif op[0] == "matrix":
                 s.stiffness(prob, op[1], op[2], op[3], op[4], op[5], incremental=op[6], nthreads=nthreads)
             elif op[0] == "matrixfun":
                 s.stiffness_sampled(prob, op[1], self.sampled_factor(op), op[3], op[4], op[5], incremental=op[6])
@@ -198,7 +202,11 @@ class Case:
                 if op[0] in ("matrix", "matrixfun"):
                     eng.register_fields(op[4], op[5])
         for op in self.ops:
-            if op[0] == "matrix":
+            if op[0] == "matrix" and len(op) > 7:
+                eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6], aux=op[7])
+            elif op[0] == "residual" and len(op) > 6:
+                eng.compute_residual_forces(op[1], op[2], op[3], op[4], op[5], aux=op[6])
+            elif op[0] == "matrix":
                 eng.stiffness_matrix_computation(op[1], op[2], op[3], op[4], op[5], incremental=op[6])
             elif op[0] == "matrixfun":
                 eng.stiffness_matrix_computation_sampled(op[1], self.sampled_factor(op), op[3], op[4], op[5], incremental=op[6])
@@ -343,6 +351,18 @@ def build_case(name, n=4, perturb=True, permute=False):
         c = Case(E.TET, 1, *make_mesh(E.TET, n, perturb, permute))
         c.add_field(2, 3, dirichlet=lambda x: 0.0 * x, values=lambda x: 0.03 * np.sin(np.pi * x))
         c.ops = [("matrix", E.K_MASS, [7.8], 4, 0, 0, True), ("matrix", E.K_HYPEL_STVENANT, [lam, mu], 4, 0, 0, True)]
+    elif name in ("convection_q1_hex", "convection_q2_quad", "convection_q1_hex_at_rest"):
+        # one Picard step of the momentum equation: viscous term + fluid::Convection (fluid/Convection.hpp) on the tuple
+        # (test, trial, advection velocity) = (u, u, u) with a non-zero velocity state; residual of the convective term
+        shape, deg = (E.HEX, 1) if "hex" in name else (E.QUAD, 2)
+        dim = E.SHAPE_DIM[shape]
+        c = Case(shape, 1, *make_mesh(shape, n, perturb, permute))
+        lid = lambda x: np.stack([(x[:, dim - 1] > 1 - 1e-9) * 1.0] + [0 * x[:, 0]] * (dim - 1), axis=1)
+        q = 3 if "hex" in name else 4
+        # at rest: the first Picard step from u = 0 (the convective terms vanish; the binding cannot probe the density there)
+        c.add_field(deg, dim, dirichlet=lid, values=None if name.endswith("at_rest") else smooth_u(dim, amp=0.3))
+        c.ops = [("matrix", E.K_VECTOR_LAPLACE, [0.1], q, 0, 0, True), ("matrix", E.K_CONVECTION, [1.2], q, 0, 0, True, 0),
+                 ("residual", E.K_CONVECTION, [1.2], q, 0, 0, 0)]
     elif name == "neumann_q1_hex":     # 05-mixedPoisson: Dirichlet on x0 = 0, a surface force f(x, n) on the whole boundary
         c = Case(E.HEX, 1, *make_mesh(E.HEX, n, perturb, permute))
         c.add_field(1, 1, dirichlet=lambda x: H.fund_sol_laplace(x, src3), where=lambda x: x[:, 0] < 1e-9)

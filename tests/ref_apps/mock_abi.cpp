@@ -36,6 +36,8 @@ int64_t orc_nnz(void*);
 void orc_get_csr(void*, int64_t*, int32_t*, double*, double*);
 const char* orc_system_error(void*);
 double orc_rhs_norm(void*);
+int orc_stiffness_aux(void*, void*, int, const double*, int, int, int, int, int);
+int orc_residual_aux(void*, void*, int, const double*, int, int, int, int);
 int orc_neumann_rows(void*, int, int, int, int, int, int64_t, const double*, const double*, int, const int32_t*, int, const double*);
 }
 
@@ -138,6 +140,17 @@ int isl_pattern_register(isl_handle h, int t, int c) { orc_register_fields(h->sy
 int isl_assemble_matrix(isl_handle h, int kid, const double* p, int q, int t, int c, int incr) {
     g_calls[0]++;
     return orc_stiffness(h->sys, h->prob, kid, p, q, t, c, incr, 1) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_matrix_aux(isl_handle h, int kid, const double* p, int q, int t, int c, int aux, int incr) {
+    if (aux < 0) return isl_assemble_matrix(h, kid, p, q, t, c, incr);
+    g_calls[0]++;
+    return orc_stiffness_aux(h->sys, h->prob, kid, p, q, t, c, aux, incr) ? fail(orc_system_error(h->sys)) : 0;
+}
+int isl_assemble_residual_aux(isl_handle h, int kid, const double* p, int q, int t, int c, int aux, double factor) {
+    if (aux < 0) return isl_assemble_residual(h, kid, p, q, t, c, factor);
+    g_calls[1]++;
+    if (factor != -1.0) return fail("mock ABI: residual factor must be -1");
+    return orc_residual_aux(h->sys, h->prob, kid, p, q, t, c, aux) ? fail(orc_system_error(h->sys)) : 0;
 }
 int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int q, int t, int c, int incr) {
     g_calls[0]++;

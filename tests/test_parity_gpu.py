@@ -32,6 +32,8 @@ CASES = [
     ("stvenant_q2_hex", 3, True, True), ("stvenant_p2_tet", 3, True, True),
     # heat::Laplace with a conductivity function sampled per quadrature point (isl_assemble_matrix_sampled)
     ("laplace_q1_hex_kappafun", 6, True, True), ("laplace_p2_tet_kappafun", 3, True, False),
+    # fluid::Convection on the tuple (u, u, u): advection velocity = third field (isl_assemble_matrix_aux / _residual_aux)
+    ("convection_q1_hex", 5, True, True), ("convection_q2_quad", 6, True, False), ("convection_q1_hex_at_rest", 3, True, False),
     # surface (Neumann) terms in one launch: isl_assemble_neumann with a sampled f(x, n), a pressure, a constant traction;
     # quadrilateral / triangle / line surface elements, Dirichlet on a part of the boundary, linear constraints
     ("neumann_q1_hex", 6, True, True), ("neumann_q1_hex", 5, False, False), ("neumann_p2_tet_solid", 3, True, True),

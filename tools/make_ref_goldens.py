@@ -26,7 +26,7 @@ OUT = os.path.join(ROOT, "tests", "golden", "refrun")
 SHAPE_NAME = {E.TRI: "triangle", E.QUAD: "quadrilateral", E.TET: "tetrahedron", E.HEX: "hexahedron"}
 KERNEL_NAME = {E.K_LAPLACE: "laplace", E.K_VECTOR_LAPLACE: "vector_laplace", E.K_HYPEL_STVENANT: "stvenant",
                E.K_HYPEL_NEOHOOKE: "neohooke", E.K_PRESSURE_GRADIENT: "pressure_gradient",
-               E.K_VELOCITY_DIVERGENCE: "velocity_divergence", E.K_MASS: "mass"}
+               E.K_VELOCITY_DIVERGENCE: "velocity_divergence", E.K_MASS: "mass", E.K_CONVECTION: "convection"}
 
 # (golden name, flows case, driver type, n, perturb, permute, register)
 CASES = [
@@ -60,6 +60,10 @@ CASES = [
     ("laplace_q1_hex_bodyfun_n4", "laplace_q1_hex_bodyfun", "laplace_q1_hex", 4, True, False, False),
     ("laplace_p2_tri_bodyfun_n4", "laplace_p2_tri_bodyfun", "laplace_p2_tri", 4, True, False, False),
     ("vector_laplace_q1_hex_bodyfun_n3", "vector_laplace_q1_hex_bodyfun", "vector_laplace_q1_hex", 3, True, True, False),
+    # fluid::Convection on the tuple (u, u, u) (fluid/Convection.hpp:88-220)
+    ("convection_q1_hex_n3", "convection_q1_hex", "vector_laplace_q1_hex", 3, True, False, False),
+    ("convection_q2_quad_n4", "convection_q2_quad", "vector_laplace_q2_quad", 4, True, True, False),
+    ("convection_q1_hex_at_rest_n3", "convection_q1_hex_at_rest", "vector_laplace_q1_hex", 3, True, False, False),
     # surface (Neumann) terms: base::asmb::neumannForceComputation over boundary meshes (NeumannForce.hpp, generateBoundaryMesh.hpp)
     ("neumann_q1_hex_n4", "neumann_q1_hex", "laplace_q1_hex", 4, True, False, False),
     ("neumann_p2_tet_solid_n2", "neumann_p2_tet_solid", "solid_p2_tet", 2, True, True, False),
