@@ -105,7 +105,8 @@ struct AsmParams {
     const int32_t* eqn_t; const int32_t* eqn_c;
     const uint8_t* st_c; const double* presc_c; const double* val_c;
     // system
-    const int32_t* slot; double* val; double* rhs;
+    const int32_t* slot; const int64_t* slot64;   // element -> CSR position maps: 32-bit, or 64-bit when nnz >= 2^31 (exactly one is set)
+    double* val; double* rhs;
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
     int body; double f[3];
@@ -322,7 +323,8 @@ __device__ __noinline__ void scatter_constrained(const AsmParams& p, size_t kr, 
 // scatter one local matrix entry: ACTIVE x ACTIVE -> CSR value,
 // ACTIVE row x CONSTRAINED column -> rhs -= g * K; slaves of master DoFs -> scatter_constrained
 __device__ __forceinline__ void scatter_entry(const AsmParams& p, int64_t e, int i, int j, int nr, int ncl, double v) {
-    const int32_t sl = p.slot[((size_t)e * nr + i) * ncl + j];
+    const size_t idx = ((size_t)e * nr + i) * ncl + j;
+    const int64_t sl = p.slot64 ? p.slot64[idx] : (int64_t)p.slot[idx];
     if (sl >= 0) { atomicAdd(p.val + sl, v); return; }
     const int M = i / p.dst, ci = i % p.dst;
     const size_t kr = (size_t)p.ed_t[e * p.nt + M] * p.dst + ci;
@@ -758,13 +760,14 @@ __global__ void k_cols_from_keys(const uint64_t* keys, int64_t nnz, int32_t* col
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
         col[k] = (int32_t)(keys[k] & 0xffffffffu);
 }
+template <typename SLOT>
 __global__ void k_slotmap(const int32_t* er, const int32_t* ec, int64_t n_elems, int nr, int ncl, const int64_t* rowptr,
-                          const int32_t* col, int32_t* slot) {
+                          const int32_t* col, SLOT* slot) {
     const int64_t n = n_elems * nr * ncl;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = t / (nr * ncl); const int ij = (int)(t % (nr * ncl));
         const int32_t r = er[e * nr + ij / ncl], c = ec[e * ncl + ij % ncl];
-        slot[t] = (r < 0 || c < 0) ? -1 : (int32_t)find_in_row(rowptr, col, r, c);
+        slot[t] = (r < 0 || c < 0) ? (SLOT)-1 : (SLOT)find_in_row(rowptr, col, r, c);
     }
 }
 __global__ void k_remap_values(const int64_t* old_rowptr, const int32_t* old_col, const double* old_val, int64_t n,
@@ -888,7 +891,11 @@ struct isl_engine {
     DevBuf<double> val_alt, rhs_alt; cudaStream_t copy_stream = nullptr; cudaEvent_t ev_asm = nullptr, ev_copy = nullptr;
     bool copy_in_flight = false, sys_released = false;
     std::set<std::pair<int, int>> pattern_pairs, sys_pairs;
-    std::map<std::pair<int, int>, std::unique_ptr<DevBuf<int32_t>>> slotmaps;
+    struct SlotMap { DevBuf<int32_t> s32; DevBuf<int64_t> s64; };
+    std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
+    bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
+    bool force_slot64 = false;
+    int stage_kb = 96;         // staging budget of the generic kernels per CTA (ISL_STAGE_KB)
     std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
     bool q1_tables_loaded = false;
     DevBuf<double> scratch_d; DevBuf<int> scratch_i;
@@ -1075,7 +1082,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     ISL_CUDA(cudaMemcpyAsync(&nuniq, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     ISL_CUDA(cudaStreamSynchronize(h->stream));
     const int64_t nnz = nuniq - 1;  // drop the invalid key
-    ISL_REQUIRE(nnz < (int64_t)1 << 31, "more than 2^31 non-zeros need 64-bit slots (not supported yet)");
+    h->wide_slots = nnz >= ((int64_t)1 << 31) || h->force_slot64;
     keys2.release(); tmp.release();
 
     DevBuf<int64_t> rowptr; DevBuf<int32_t> col; DevBuf<double> val;
@@ -1107,21 +1114,31 @@ void ensure_pair(isl_engine* h, int t, int c) {
     }
 }
 
-const int32_t* get_slotmap(isl_engine* h, int t, int c) {
+const isl_engine::SlotMap* get_slotmap(isl_engine* h, int t, int c) {
     auto key = std::make_pair(t, c);
     auto it = h->slotmaps.find(key);
-    if (it != h->slotmaps.end()) return it->second->p;
+    if (it != h->slotmaps.end()) return it->second.get();
     FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
     build_elem_eqn(h, ft); build_elem_eqn(h, fc);
     const int nr = ft.ndpe * ft.ds, ncl = fc.ndpe * fc.ds;
     const int64_t n = h->n_owned * nr * ncl;
-    auto buf = std::make_unique<DevBuf<int32_t>>();
-    buf->alloc(n);
-    ISL_LAUNCH(h, k_slotmap, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_owned, nr, ncl,
-               h->rowptr.p, h->col.p, buf->p);
-    const int32_t* p = buf->p;
+    auto buf = std::make_unique<isl_engine::SlotMap>();
+    if (h->wide_slots) {
+        buf->s64.alloc(n);
+        ISL_LAUNCH(h, k_slotmap<int64_t>, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_owned, nr, ncl,
+                   h->rowptr.p, h->col.p, buf->s64.p);
+    } else {
+        buf->s32.alloc(n);
+        ISL_LAUNCH(h, k_slotmap<int32_t>, h->grid_for(n, 256), 256, 0, ft.elem_eqn.p, fc.elem_eqn.p, h->n_owned, nr, ncl,
+                   h->rowptr.p, h->col.p, buf->s32.p);
+    }
+    const isl_engine::SlotMap* p = buf.get();
     h->slotmaps[key] = std::move(buf);
     return p;
+}
+void bind_slots(isl_engine* h, AsmParams& p, int t, int c) {
+    const isl_engine::SlotMap* m = get_slotmap(h, t, c);
+    p.slot = m->s32.p; p.slot64 = m->s64.p;
 }
 
 TableDev* get_tables(isl_engine* h, int quad_deg, int t, int c) {
@@ -1228,7 +1245,7 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
 template <class K>
 void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
     const size_t per = stage_doubles_per_elem(p, h->dim) * sizeof(double);
-    const size_t budget = 96 * 1024;
+    const size_t budget = (size_t)h->stage_kb * 1024;   // shared memory per CTA: fewer elements per batch = more CTAs per SM
     ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
     int EB = (int)std::max<size_t>(1, std::min<size_t>(budget / per, 32));
     p.EB = EB;
@@ -1790,7 +1807,7 @@ PatchSet* get_patchset(isl_engine* h, int field);
 
 // is one of the Q1 fast paths available for this field?  (builds its tables on first use)
 bool q1_ready(isl_engine* h, int field) {
-    if (!h->q1_rows) return get_patchset(h, field) != nullptr;
+    if (!h->q1_rows) return !h->wide_slots && get_patchset(h, field) != nullptr;   // round-1 patch kernels: 32-bit positions
     ensure_affine_state(h);
     if (h->affine_state == 1) { PatchSet* ps = get_patchset(h, field); if (ps && ps->rows_ok) return true; }
     return get_fromk(h, field) != nullptr;   // also serves affine meshes whose patches are not eligible
@@ -2069,6 +2086,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;
+        if (const char* m = getenv("ISL_STAGE_KB")) h->stage_kb = std::max(8, std::min(200, atoi(m)));   // test knob: 64-bit slot maps at any size
         if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_AFF_THREADS")) h->patch_threads_aff = atoi(m);
         if (const char* m = getenv("ISL_AFF_SPLIT")) h->aff_split = atoi(m) ? 1 : 0;
@@ -2371,23 +2390,24 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
                     return;
                 }
             }
-            materialize_zero(h);
-            h->val_is_zero = false;
-            const int32_t* slot = get_slotmap(h, t, c);
-            Q1Params q;
-            q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_owned; q.slot = slot;
-            q.eqn = ft.eqn.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p;
-            q.val = h->val.p; q.rhs = h->rhs.p; q.factor = params ? params[0] : 1.0; q.incremental = incremental;
-            const int block = 128;
-            const int64_t grid = (h->n_owned + block - 1) / block;
-            if (grid > 0) ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
-            return;
+            if (!h->wide_slots) {   // (the one-thread-per-element kernel reads 32-bit slots; larger systems take k_tangent)
+                materialize_zero(h);
+                h->val_is_zero = false;
+                Q1Params q;
+                q.coords = h->coords.p; q.conn = h->conn.p; q.n_elems = h->n_owned; q.slot = get_slotmap(h, t, c)->s32.p;
+                q.eqn = ft.eqn.p; q.status = ft.status.p; q.presc = ft.presc.p; q.values = ft.values.p;
+                q.val = h->val.p; q.rhs = h->rhs.p; q.factor = params ? params[0] : 1.0; q.incremental = incremental;
+                const int block = 128;
+                const int64_t grid = (h->n_owned + block - 1) / block;
+                if (grid > 0) ISL_LAUNCH(h, k_q1hex_laplace, (unsigned)grid, block, 0, q);
+                return;
+            }
         }
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
         materialize_zero(h);
         h->val_is_zero = false;
-        p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental;
+        bind_slots(h, p, t, c); p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT && kid != ISL_K_MASS);
@@ -2423,7 +2443,7 @@ int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int
         h->val_is_zero = false;
         DevBuf<double> kq;   // host or device pointer
         upload(h, kq, values, (size_t)h->n_owned * p.nq);
-        p.slot = get_slotmap(h, t, c); p.kernel_id = kid; p.incremental = incremental; p.kq = kq.p;
+        bind_slots(h, p, t, c); p.kernel_id = kid; p.incremental = incremental; p.kq = kq.p;
         p.need_gt = 1; p.need_gc = 1; p.nqdata = 0;
         if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
         ISL_CUDA(cudaStreamSynchronize(h->stream));   // kq is released when this function returns

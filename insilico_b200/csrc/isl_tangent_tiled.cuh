@@ -281,8 +281,18 @@ __global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p,
         __syncthreads();
         for (int eb = 0; eb < nb; eb++) {
             const int64_t e = p.eid(base + eb);
-            const int32_t* sl = p.slot + (size_t)e * nn;
             const double* Kl = smem + (size_t)eb * L.per_elem;
+            if (p.slot64) {   // systems with 2^31 or more non-zeros: 64-bit positions
+                const int64_t* sw = p.slot64 + (size_t)e * nn;
+                for (int t0 = tid; t0 < nn; t0 += 2 * nth) {
+                    const int t1 = t0 + nth;
+                    const int64_t a = __ldg(sw + t0), b = (t1 < nn) ? __ldg(sw + t1) : 0;
+                    if (a >= 0) atomicAdd(p.val + a, Kl[t0]); else scatter_entry(p, e, t0 / nr, t0 % nr, nr, nr, Kl[t0]);
+                    if (t1 < nn) { if (b >= 0) atomicAdd(p.val + b, Kl[t1]); else scatter_entry(p, e, t1 / nr, t1 % nr, nr, nr, Kl[t1]); }
+                }
+                continue;
+            }
+            const int32_t* sl = p.slot + (size_t)e * nn;
             constexpr int U = 4;   // slot loads in flight per thread
             for (int t0 = tid; t0 < nn; t0 += U * nth) {
                 int32_t s4[U];
