@@ -895,7 +895,7 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
     bool force_slot64 = false;
-    int stage_kb = 96;         // staging budget of the generic kernels per CTA (ISL_STAGE_KB)
+    int stage_kb = 48;         // staging budget of the generic kernels per CTA (ISL_STAGE_KB; sweep in profiles/r2/session23.log)
     std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
     bool q1_tables_loaded = false;
     DevBuf<double> scratch_d; DevBuf<int> scratch_i;
@@ -1011,7 +1011,11 @@ void build_elem_eqn(isl_engine* h, FieldDev& f) {
 void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     ISL_REQUIRE(h->n_eqn >= 0, "isl_system_create must be called first");
     ISL_REQUIRE(h->n_eqn < (int64_t)1 << 31, "more than 2^31 equations are not supported");
-    materialize_zero(h);  // values of the old layout are carried over
+    // values of the old layout are carried over -- unless there are none yet (pattern registration before the first
+    // assembly call): then the old arrays are released first, their memory is needed for the keys of large systems
+    const bool carry = h->nnz > 0 && h->val.p && !h->val_is_zero;
+    if (carry) materialize_zero(h);
+    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->nnz = 0; h->val_zero_pending = false; }
     int64_t total = 0;
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
@@ -1092,7 +1096,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
         ISL_LAUNCH(h, k_cols_from_keys, h->grid_for(nnz, 256), 256, 0, keys.p, nnz, col.p);
         ISL_CUDA(cudaMemsetAsync(val.p, 0, nnz * sizeof(double), h->stream));
     }
-    if (h->nnz > 0 && h->val.p)
+    if (carry)
         ISL_LAUNCH(h, k_remap_values, h->grid_for(h->n_eqn, 128), 128, 0, h->rowptr.p, h->col.p, h->val.p, h->n_eqn,
                    rowptr.p, col.p, val.p);
     ISL_CUDA(cudaStreamSynchronize(h->stream));
