@@ -92,6 +92,11 @@ int isl_support_points(int shape, int degree, double* pts);
 int isl_dof_generate(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int fe_deg, int32_t* elem_dof,
                      int64_t* n_obj);
 int isl_ndpe(int shape, int fe_deg);
+/* the same on the device, for the mesh of the engine (isl_mesh_set): generateDoFIndicesFromFaces
+ * (base/dof/generateDoFIndicesFromFaces.hpp:169-298) as stable radix sorts of (sorted vertex tuple, visiting position) and
+ * a scan of the "met for the first time" flags: same ids as isl_dof_generate.  elem_dof: host or device pointer,
+ * [n_elems * ndpe].                                                                                               */
+int isl_dof_generate_device(isl_handle h, int fe_deg, int32_t* elem_dof, int64_t* n_obj);
 /* base::mesh::MeshBoundary::create (base/mesh/MeshBoundary.hpp, createBoundaryFromUnstructured.hpp:55-106):
  * pairs[2*k] = element, pairs[2*k+1] = face number; pass NULL to query the count (*n_pairs).              */
 int isl_mesh_boundary(int shape, int geom_deg, int64_t n_elems, const int32_t* conn, int64_t* pairs,

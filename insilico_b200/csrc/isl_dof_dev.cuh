@@ -8,7 +8,7 @@
 // the next `stride` ids.  The host restatement (isl_dof.hpp: dof_generate) does the same with a hash table.
 //
 // Here, per n-face type: items i = element * nfaces + local face; key = sorted vertex tuple (a vertex, an edge, or the
-// three smallest vertices of a face -- two distinct faces of a conforming mesh share at most an edge); a STABLE radix
+// vertices of a face: 128 bits, sorted as two 64-bit halves, least significant first); a STABLE radix
 // sort of (key, i) puts the first visitor of every face at the head of its run; "first visitor" flags, an exclusive
 // scan in visiting order = the reference's running counter.  Same ids as the host version, bit for bit.
 // =============================================================================
@@ -16,7 +16,7 @@
 
 struct DgTopo { int nfaces, nv; int vert[12][4]; };   // local vertex numbers of every n-face of the current type
 
-__global__ void k_dg_keys(const int32_t* conn, int64_t n_elems, int npe, DgTopo T, uint64_t* khi, uint32_t* klo, uint32_t* idx) {
+__global__ void k_dg_keys(const int32_t* conn, int64_t n_elems, int npe, DgTopo T, uint64_t* khi, uint64_t* klo, uint32_t* idx) {
     const int64_t n = n_elems * T.nfaces;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t e = i / T.nfaces; const int f = (int)(i % T.nfaces);
@@ -26,7 +26,7 @@ __global__ void k_dg_keys(const int32_t* conn, int64_t n_elems, int npe, DgTopo 
         auto cswap = [](uint32_t& a, uint32_t& b) { if (a > b) { const uint32_t t = a; a = b; b = t; } };
         cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[1], v[2]);
         khi[i] = ((uint64_t)v[0] << 32) | (uint64_t)(T.nv > 1 ? v[1] : 0u);
-        klo[i] = (T.nv > 2) ? v[2] : 0u;
+        klo[i] = (T.nv > 2) ? (((uint64_t)v[2] << 32) | (uint64_t)v[3]) : 0ull;
         idx[i] = (uint32_t)i;
     }
 }
@@ -34,7 +34,7 @@ __global__ void k_dg_gather64(const uint64_t* src, const uint32_t* idx, int64_t 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
 }
 // head of a run of equal keys -> its own position, else 0 (an inclusive max-scan then gives every member its run start)
-__global__ void k_dg_heads(const uint64_t* khi, const uint32_t* klo_orig, const uint32_t* idx, int64_t n, uint32_t* start) {
+__global__ void k_dg_heads(const uint64_t* khi, const uint64_t* klo_orig, const uint32_t* idx, int64_t n, uint32_t* start) {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         const bool head = (j == 0) || khi[j] != khi[j - 1] || klo_orig[idx[j]] != klo_orig[idx[j - 1]];
         start[j] = head ? (uint32_t)j : 0u;
@@ -68,4 +68,4 @@ __global__ void k_dg_copy_conn(const int32_t* conn, int64_t n, int32_t* elem_dof
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(maxid, m);
 }
-struct DgMax { __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+struct DgMax { __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };

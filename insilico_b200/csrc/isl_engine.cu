@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
 
 #include "isl_tangent_tiled.cuh"
 #include "isl_neumann.cuh"
+#include "isl_dof_dev.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // specialised hot path: Q1 hex geometry, Q1 scalar field, Laplace, 2x2x2 Gauss rule (BASELINE config 2).
@@ -2519,6 +2520,97 @@ int isl_assemble_bodyforce_sampled(isl_handle h, const double* values, int quad_
         p.need_gt = 0; p.need_gc = 0; p.nqdata = 0;
         if (h->dim == 3) launch_staged(h, k_force<3>, p); else launch_staged(h, k_force<2>, p);
         ISL_CUDA(cudaStreamSynchronize(h->stream));   // fq is released when this function returns
+    });
+}
+
+// ---- DoF-object ids on the device (isl_dof_dev.cuh) ----
+namespace {
+int64_t dof_generate_device(isl_engine* h, int fe_deg, int32_t* d_elem_dof) {
+    const int shape = h->shape, dim = h->dim, npe = h->npe;
+    const int64_t ne = h->n_elems;
+    const isl::FELayout L = isl::fe_layout(shape, fe_deg);
+    if (fe_deg == h->geom_deg) {   // isoparametric: DoF id = node id
+        DevBuf<int> mx; mx.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(mx.p, 0xff, sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_dg_copy_conn, h->grid_for(ne * npe, 256), 256, 0, h->conn.p, ne * npe, d_elem_dof, mx.p);
+        int m = -1;
+        ISL_CUDA(cudaMemcpyAsync(&m, mx.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        return (int64_t)m + 1;
+    }
+    int64_t next = 0;
+    for (int nf = 0; nf <= dim; nf++) {
+        const int stride = L.per[nf], nfaces = L.count[nf];
+        if (stride == 0 || nfaces == 0) continue;
+        if (nf == dim) {   // interior DoFs, private to the element
+            ISL_LAUNCH(h, k_dg_interior, h->grid_for(ne * stride * nfaces, 256), 256, 0, ne, stride * nfaces, L.total, L.begin[nf], next, d_elem_dof);
+            next += ne * stride * nfaces;
+            continue;
+        }
+        const int64_t n = ne * nfaces;
+        ISL_REQUIRE(n < ((int64_t)1 << 32), "too many n-faces for 32-bit item numbers: partition the mesh first");
+        DgTopo T; std::memset(&T, 0, sizeof(T));
+        T.nfaces = nfaces; T.nv = std::min(4, isl::nface_num_vertices(shape, nf));
+        for (int f = 0; f < nfaces; f++) for (int j = 0; j < T.nv; j++) T.vert[f][j] = isl::nface_vertex(shape, nf, f, j);
+        DevBuf<uint64_t> khi, klo, k2, k3; DevBuf<uint32_t> idx, idx2, start, first, fresh, rank;
+        khi.alloc(n); klo.alloc(n); k2.alloc(n); idx.alloc(n); idx2.alloc(n);
+        ISL_LAUNCH(h, k_dg_keys, h->grid_for(n, 256), 256, 0, h->conn.p, ne, npe, T, khi.p, klo.p, idx.p);
+        size_t tb = 0, tb2 = 0;
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, khi.p, k2.p, idx.p, idx2.p, n, 0, 64, h->stream));
+        DevBuf<char> tmp; tmp.alloc(tb);
+        const uint32_t* sorted_idx;
+        if (T.nv > 2) {   // 128-bit key: least significant half first, both sorts stable
+            ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, klo.p, k2.p, idx.p, idx2.p, n, 0, 64, h->stream));
+            k3.alloc(n);
+            ISL_LAUNCH(h, k_dg_gather64, h->grid_for(n, 256), 256, 0, khi.p, idx2.p, n, k3.p);
+            ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k3.p, k2.p, idx2.p, idx.p, n, 0, 64, h->stream));
+            sorted_idx = idx.p;
+        } else {
+            ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, khi.p, k2.p, idx.p, idx2.p, n, 0, 64, h->stream));
+            sorted_idx = idx2.p;
+        }
+        h->launches += 6;
+        // k2 = sorted most significant halves; run heads, run start per member, first visitor per item
+        start.alloc(n); first.alloc(n); fresh.alloc(n); rank.alloc(n);
+        ISL_LAUNCH(h, k_dg_heads, h->grid_for(n, 256), 256, 0, k2.p, klo.p, sorted_idx, n, start.p);
+        ISL_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb2, start.p, start.p, DgMax(), n, h->stream));
+        if (tb2 > tmp.n) tmp.alloc(tb2);
+        ISL_CUDA(cub::DeviceScan::InclusiveScan(tmp.p, tb2, start.p, start.p, DgMax(), n, h->stream));
+        ISL_LAUNCH(h, k_dg_first, h->grid_for(n, 256), 256, 0, sorted_idx, start.p, n, first.p, fresh.p);
+        ISL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, fresh.p, rank.p, n, h->stream));
+        if (tb2 > tmp.n) tmp.alloc(tb2);
+        ISL_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, fresh.p, rank.p, n, h->stream));
+        h->launches += 2;
+        ISL_LAUNCH(h, k_dg_write, h->grid_for(n, 256), 256, 0, first.p, rank.p, ne, nfaces, stride, L.total, L.begin[nf], next, d_elem_dof);
+        uint32_t last_rank = 0, last_fresh = 0;
+        ISL_CUDA(cudaMemcpyAsync(&last_rank, rank.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaMemcpyAsync(&last_fresh, fresh.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        next += ((int64_t)last_rank + last_fresh) * stride;
+    }
+    return next;
+}
+}  // namespace
+
+int isl_dof_generate_device(isl_handle h, int fe_deg, int32_t* elem_dof, int64_t* n_obj) {
+    return guarded([&] {
+        ISL_CUDA(cudaSetDevice(h->device));
+        ISL_REQUIRE(h->n_elems > 0, "mesh not set");
+        ISL_REQUIRE(elem_dof != nullptr && n_obj != nullptr, "output arrays missing");
+        flush_pending(h);
+        const isl::FELayout L = isl::fe_layout(h->shape, fe_deg);
+        const size_t n = (size_t)h->n_elems * L.total;
+        cudaPointerAttributes at; std::memset(&at, 0, sizeof(at));
+        const bool on_device = cudaPointerGetAttributes(&at, elem_dof) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        DevBuf<int32_t> buf;
+        int32_t* d = elem_dof;
+        if (!on_device) { buf.alloc(n); d = buf.p; }
+        *n_obj = dof_generate_device(h, fe_deg, d);
+        if (!on_device) {
+            ISL_CUDA(cudaMemcpyAsync(elem_dof, d, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            ISL_CUDA(cudaStreamSynchronize(h->stream));
+        }
     });
 }
 

@@ -35,7 +35,7 @@ EXPORTED = [
     "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_engine_set_option", "isl_synchronize", "isl_flush",
     "isl_engine_stream",
     "isl_kernel_launches", "isl_measure_fp64_peak", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
-    "isl_dof_generate", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
+    "isl_dof_generate", "isl_dof_generate_device", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
     "isl_assemble_matrix", "isl_assemble_matrix_aux", "isl_assemble_residual_aux", "isl_assemble_matrix_sampled", "isl_assemble_residual", "isl_assemble_bodyforce", "isl_assemble_bodyforce_sampled", "isl_insert_lhs",
@@ -277,6 +277,14 @@ class Engine:
 
     def set_owned_elements(self, n_owned):
         _chk(lib().isl_mesh_set_owned(self.h, _i64(n_owned)))
+
+    def dof_generate(self, fe_deg):
+        """base::dof::generate on the device for the engine's mesh: (elem_dof [n_elems, ndpe] int32, n_obj), same ids as
+        the host function dof_generate()"""
+        ed = np.zeros((self.n_elems, ndpe(self.shape, fe_deg)), dtype=np.int32)
+        n = C.c_int64()
+        _chk(lib().isl_dof_generate_device(self.h, fe_deg, _ptr(ed), C.byref(n)))
+        return ed, n.value
 
     def update_coords(self, coords):
         if not isinstance(coords, (int, np.integer)):

@@ -385,3 +385,16 @@ def test_neumann_with_explicit_rows_equals_field_form(eng):
     b = eng.get_csr()
     r = flows.compare(a, b)
     assert r["pattern_equal"] and r["val_diff"] <= TOL and r["rhs_diff"] <= TOL, r
+
+
+@pytest.mark.parametrize("shape,fe_deg,n,permute", [(E.HEX, 2, 4, True), (E.HEX, 3, 3, False), (E.TET, 2, 4, True), (E.QUAD, 2, 7, True),
+                                                     (E.QUAD, 3, 5, False), (E.TRI, 2, 6, True), (E.HEX, 1, 5, True), (E.TET, 1, 3, False)])
+def test_device_dof_generation_equals_host(eng, shape, fe_deg, n, permute):
+    """isl_dof_generate_device (radix sorts + scans) gives the ids of the host function, i.e. of base::dof::generate
+    (pinned against the reference run in test_reference_run.py), also on a permuted element order"""
+    coords, conn = flows.make_mesh(shape, n, True, permute)
+    eng.set_mesh(shape, 1, coords, conn)
+    ed_dev, n_dev = eng.dof_generate(fe_deg)
+    ed, nobj = E.dof_generate(shape, 1, conn, fe_deg)
+    assert n_dev == nobj
+    assert np.array_equal(ed_dev, ed)
