@@ -2587,6 +2587,7 @@ int64_t dof_generate_device(isl_engine* h, int fe_deg, int32_t* d_elem_dof) {
         ISL_CUDA(cudaMemcpyAsync(&last_fresh, fresh.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         next += ((int64_t)last_rank + last_fresh) * stride;
+        if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] dof generation on the device: n-face type %d, %lld items, %lld ids so far\n", nf, (long long)n, (long long)next);
     }
     return next;
 }
