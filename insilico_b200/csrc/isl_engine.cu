@@ -896,6 +896,7 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
     bool force_slot64 = false;
+    int fromk_tile_order = 0;  // row tiles of the general Q1 path along a Z-curve (ISL_FROMK_TILE_ORDER=1): measured slower, 4.00 vs 3.67 ms (session27)
     int stage_kb = 48;         // staging budget of the generic kernels per CTA (ISL_STAGE_KB; sweep in profiles/r2/session23.log)
     std::map<std::array<int, 3>, std::unique_ptr<TableDev>> tables;  // (quad_deg, test, trial)
     bool q1_tables_loaded = false;
@@ -1797,6 +1798,22 @@ FromKSet* get_fromk(isl_engine* h, int field) {
             }
             ISL_CUDA(cudaStreamSynchronize(h->stream));
             fk->ok = true;
+            if (h->fromk_tile_order) {   // launch order of the row tiles (see k_q1hex_rows_fromK)
+                const int64_t n_tiles = (nr + 127) / 128;
+                DevBuf<unsigned long long> bb; bb.alloc(6);
+                ISL_CUDA(cudaMemsetAsync(bb.p, 0xff, 3 * sizeof(unsigned long long), h->stream));
+                ISL_CUDA(cudaMemsetAsync(bb.p + 3, 0, 3 * sizeof(unsigned long long), h->stream));
+                ISL_LAUNCH(h, k_bbox, std::min(h->grid_for(h->n_nodes, 256), h->n_sm * 8), 256, 0, h->coords.p, h->n_nodes, h->dim, bb.p, bb.p + 3);
+                DevBuf<int32_t> tk, tk2, ti;
+                tk.alloc(n_tiles); tk2.alloc(n_tiles); ti.alloc(n_tiles); fk->tile_perm.alloc(n_tiles);
+                ISL_LAUNCH(h, k_fromk_tile_key, h->grid_for(n_tiles, 128), 128, 0, h->coords.p, h->conn.p, fk->eorder.p, fk->row_pos.p, nr, 128,
+                           n_tiles, bb.p, bb.p + 3, tk.p, ti.p);
+                size_t tbt = 0;
+                ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tbt, tk.p, tk2.p, ti.p, fk->tile_perm.p, n_tiles, 0, 32, h->stream));
+                DevBuf<char> tmpt; tmpt.alloc(tbt);
+                ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmpt.p, tbt, tk.p, tk2.p, ti.p, fk->tile_perm.p, n_tiles, 0, 32, h->stream));
+                ISL_CUDA(cudaStreamSynchronize(h->stream));
+            }
         }
         if (getenv("ISL_VERBOSE"))
             fprintf(stderr, "[isl] general Q1 path: %s, %d rows next to constrained nodes; %s (%d chunks, look-back %d, %d ring slots of %lld elements)\n",
@@ -1902,6 +1919,7 @@ void launch_q1(isl_engine* h, int field, int matrix, double factor, int incremen
     k.row_pos = fk->row_pos.p; k.meta = reinterpret_cast<const RowMeta*>(fk->meta.p); k.n_rows = fk->n_rows; k.K = fk->K.p;
     q.lift_nodes = fk->lift_nodes.p;
     k.r = q; k.matrix = matrix;
+    k.tile_perm = fk->tile_perm.p;
     constexpr int NT = 128;
     const size_t smem_k = (size_t)(NT / 32) * RG_STAGE * 8;
     if (fk->pipe_ok) {
@@ -2091,6 +2109,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;
         if (const char* m = getenv("ISL_STAGE_KB")) h->stage_kb = std::max(8, std::min(200, atoi(m)));   // test knob: 64-bit slot maps at any size
         if (const char* m = getenv("ISL_AFFINE_KERNEL")) h->affine_kernel = atoi(m) ? 1 : 0;

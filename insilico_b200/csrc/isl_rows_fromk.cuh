@@ -29,6 +29,7 @@ struct FromKSet {
     DevBuf<unsigned char> meta; // RowMeta per row (slot[] unused)
     DevBuf<int32_t> lift_nodes;
     DevBuf<double> K;           // [44][n_elems]: 36 symmetric entries (sym_idx), 8 body-force integrals
+    DevBuf<int32_t> tile_perm;  // launch order of the 128-row tiles of the row kernel: along a Z-curve of their positions
     // producer / consumer pipeline (k_q1hex_pipeline): chunk c = rows [row_b[c], row_b[c+1]) and the elements whose
     // smallest equation lies in that range, sorted positions [elem_b[c], elem_b[c+1]); rows of chunk c only read elements
     // of chunks c - maxback .. c
@@ -63,6 +64,7 @@ struct FromKParams {
     RowsParams r;   // val, rhs, lift tables, flags (patch arrays unused)
     int matrix;     // 0: right-hand side only (body force without a preceding stiffness call)
     int64_t e_lo, e_hi, r_lo, r_hi;   // this launch: sorted element positions [e_lo, e_hi) / rows [r_lo, r_hi)
+    const int32_t* tile_perm;         // CTA -> row tile (nullptr: in equation order)
 };
 
 // first sorted position whose key is >= bound[c], for every chunk boundary
@@ -123,6 +125,29 @@ __global__ void k_fromk_row_meta(int pass, int64_t n_rows, const int32_t* row_po
             int32_t* dst = lift_nodes + (size_t)meta[g].lift * 27;
             for (int k = 0; k < 27; k++) dst[k] = nbn[k];
         }
+    }
+}
+
+// Z-curve key of a row tile: centroid of an element next to its middle row (10 bits per axis inside the bounding box)
+__global__ void k_fromk_tile_key(const double* coords, const int32_t* conn, const int32_t* eorder, const int32_t* row_pos, int64_t n_rows,
+                                 int nt, int64_t n_tiles, const unsigned long long* mn, const unsigned long long* mx, int32_t* key, int32_t* idx) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = min(t * nt + nt / 2, n_rows - 1);
+        int pos = -1;
+        for (int a = 0; a < 8 && pos < 0; a++) pos = row_pos[r * 8 + a];
+        unsigned int code = 0;
+        if (pos >= 0) {
+            const int64_t e = eorder[pos];
+            for (int d = 0; d < 3; d++) {
+                double c = 0.;
+                for (int a = 0; a < 8; a++) c += coords[(size_t)conn[e * 8 + a] * 3 + d];
+                c *= 0.125;
+                const double lo = ord_dbl(mn[d]), hi = ord_dbl(mx[d]);
+                const double u = (hi > lo) ? (c - lo) / (hi - lo) : 0.;
+                code |= spread3((unsigned int)min(1023.0, max(0.0, u * 1024.0))) << d;
+            }
+        }
+        key[t] = (int32_t)code; idx[t] = (int32_t)t;
     }
 }
 
@@ -207,7 +232,11 @@ __global__ void __launch_bounds__(NT, MINB) k_q1hex_rows_fromK(const FromKParams
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* st = smem + (size_t)warp * RG_STAGE;
-    const int64_t r = p.r_lo + (int64_t)blockIdx.x * NT + tid;
+    // Tiles are launched along a Z-curve of their position in space, not in equation order: the element matrices a tile
+    // reads are read again by the tiles of the neighbouring lines and planes, which then run while those lines of K are
+    // still in L2 (in equation order the next plane is 66 k rows = 50 MB of traffic away at 256^3)
+    const int64_t tile = p.tile_perm ? (int64_t)__ldg(p.tile_perm + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t r = p.r_lo + tile * NT + tid;
     const bool act = r < p.r_hi;
     RowMeta m;
     double acc[27];
