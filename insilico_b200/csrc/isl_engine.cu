@@ -28,6 +28,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <set>
@@ -2558,6 +2559,7 @@ int64_t dof_generate_device(isl_engine* h, int fe_deg, int32_t* d_elem_dof) {
         return (int64_t)m + 1;
     }
     int64_t next = 0;
+    const auto t_start = std::chrono::steady_clock::now();
     for (int nf = 0; nf <= dim; nf++) {
         const int stride = L.per[nf], nfaces = L.count[nf];
         if (stride == 0 || nfaces == 0) continue;
@@ -2606,7 +2608,9 @@ int64_t dof_generate_device(isl_engine* h, int fe_deg, int32_t* d_elem_dof) {
         ISL_CUDA(cudaMemcpyAsync(&last_fresh, fresh.p + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         next += ((int64_t)last_rank + last_fresh) * stride;
-        if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] dof generation on the device: n-face type %d, %lld items, %lld ids so far\n", nf, (long long)n, (long long)next);
+        if (getenv("ISL_VERBOSE"))
+            fprintf(stderr, "[isl] dof generation on the device: n-face type %d, %lld items, %lld ids so far, %.2f ms since the start\n", nf, (long long)n,
+                    (long long)next, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     }
     return next;
 }

@@ -9,7 +9,7 @@ timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -6
 echo "== smoke"
 timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -1
 echo "== device dof generation, timed"
-timeout 600 python - <<'PY'
+ISL_VERBOSE=1 timeout 600 python - <<'PY'
 import time, numpy as np
 from insilico_b200 import engine as E, meshgen
 for shape, n, deg in ((E.HEX, 64, 2), (E.TET, 64, 2), (E.HEX, 48, 3)):
