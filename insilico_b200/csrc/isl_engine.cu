@@ -107,6 +107,8 @@ struct AsmParams {
     const uint8_t* st_c; const double* presc_c; const double* val_c;
     // system
     const int32_t* slot; const int64_t* slot64;   // element -> CSR position maps: 32-bit, or 64-bit when nnz >= 2^31 (exactly one is set)
+    // node-block position map of the hyperelastic tile kernel (one base position per pair of nodes instead of ds*ds slots)
+    const int64_t* bbase; const int32_t* blen;
     double* val; double* rhs;
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
@@ -324,14 +326,22 @@ __device__ __noinline__ void scatter_constrained(const AsmParams& p, size_t kr, 
 // scatter one local matrix entry: ACTIVE x ACTIVE -> CSR value,
 // ACTIVE row x CONSTRAINED column -> rhs -= g * K; slaves of master DoFs -> scatter_constrained
 __device__ __forceinline__ void scatter_entry(const AsmParams& p, int64_t e, int i, int j, int nr, int ncl, double v) {
-    const size_t idx = ((size_t)e * nr + i) * ncl + j;
-    const int64_t sl = p.slot64 ? p.slot64[idx] : (int64_t)p.slot[idx];
-    if (sl >= 0) { atomicAdd(p.val + sl, v); return; }
     const int M = i / p.dst, ci = i % p.dst;
+    const int N = j / p.dsc, cj = j % p.dsc;
+    if (p.slot64 || p.slot) {
+        const size_t idx = ((size_t)e * nr + i) * ncl + j;
+        const int64_t sl = p.slot64 ? p.slot64[idx] : (int64_t)p.slot[idx];
+        if (sl >= 0) { atomicAdd(p.val + sl, v); return; }
+    }
     const size_t kr = (size_t)p.ed_t[e * p.nt + M] * p.dst + ci;
     const int32_t r = p.eqn_t[kr];
-    const int N = j / p.dsc, cj = j % p.dsc;
     const size_t k = (size_t)p.ed_c[e * p.nc + N] * p.dsc + cj;
+    if (!p.slot64 && !p.slot && r >= 0 && p.eqn_c[k] >= 0 && p.cptr_t == nullptr && p.cptr_c == nullptr) {
+        // no slot map (node-block map of the tile kernel, irregular pair): the position is searched in the row
+        const int64_t pos = find_in_row(p.rowptr, p.col, r, p.eqn_c[k]);
+        if (pos >= 0) atomicAdd(p.val + pos, v);
+        return;
+    }
     if (p.cptr_t != nullptr || p.cptr_c != nullptr) { scatter_constrained(p, kr, r, k, v); return; }
     if (r < 0) return;
     if (p.st_c[k] == ISL_CONSTRAINED) {
@@ -772,6 +782,34 @@ __global__ void k_slotmap(const int32_t* er, const int32_t* ec, int64_t n_elems,
         slot[t] = (r < 0 || c < 0) ? (SLOT)-1 : (SLOT)find_in_row(rowptr, col, r, c);
     }
 }
+// node-block position map: base[e][M][N] = CSR position of entry (row of (node M, component 0), column of (node N, component
+// 0)) when the pair is REGULAR -- all DS components of both nodes ACTIVE and numbered consecutively, the DS rows of node M
+// of equal length and holding the columns of node N at the same offset -- so that entry (M,i; N,k) sits at
+// base + i * len[e][M] + k; -1 otherwise (the kernel then searches the row).  DS = 3.
+__global__ void k_blockmap(const int32_t* elem_dof, const int32_t* eqn, int64_t n_elems, int nt, const int64_t* rowptr, const int32_t* col,
+                           int64_t* base, int32_t* len) {
+    const int64_t n = n_elems * nt * nt;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = t / (nt * nt); const int mn = (int)(t % (nt * nt)), M = mn / nt, N = mn % nt;
+        const int32_t* qm = eqn + (size_t)elem_dof[e * nt + M] * 3;
+        const int32_t* qn = eqn + (size_t)elem_dof[e * nt + N] * 3;
+        const int32_t r0 = qm[0], c0 = qn[0];
+        int64_t b = -1; int32_t L = 0;
+        if (r0 >= 0 && qm[1] == r0 + 1 && qm[2] == r0 + 2 && c0 >= 0 && qn[1] == c0 + 1 && qn[2] == c0 + 2) {
+            const int64_t s0 = rowptr[r0], s1 = rowptr[r0 + 1], s2 = rowptr[r0 + 2], s3 = rowptr[r0 + 3];
+            L = (int32_t)(s1 - s0);
+            const int64_t p0 = find_in_row(rowptr, col, r0, c0);
+            if (p0 >= 0 && s2 - s1 == L && s3 - s2 == L && p0 + 2 < s1 && col[p0 + 1] == c0 + 1 && col[p0 + 2] == c0 + 2) {
+                const int64_t o = p0 - s0;
+                bool same = true;
+                for (int i = 1; i < 3; i++) { const int64_t q = s0 + (int64_t)i * L + o; same = same && col[q] == c0 && col[q + 1] == c0 + 1 && col[q + 2] == c0 + 2; }
+                if (same) b = p0;
+            }
+        }
+        base[t] = b;
+        if (N == 0) len[e * nt + M] = L;
+    }
+}
 __global__ void k_remap_values(const int64_t* old_rowptr, const int32_t* old_col, const double* old_val, int64_t n,
                                const int64_t* rowptr, const int32_t* col, double* val) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
@@ -895,6 +933,9 @@ struct isl_engine {
     std::set<std::pair<int, int>> pattern_pairs, sys_pairs;
     struct SlotMap { DevBuf<int32_t> s32; DevBuf<int64_t> s64; };
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
+    struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
+    std::map<int, std::unique_ptr<BlockMap>> blockmaps;   // per field (hyperelastic tile kernel)
+    int block_slots = 1;       // ISL_BLOCK_SLOTS
     bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
     bool force_slot64 = false;
     int fromk_tile_order = 0;  // row tiles of the general Q1 path along a Z-curve (ISL_FROMK_TILE_ORDER=1): measured slower, 4.00 vs 3.67 ms (session27)
@@ -994,7 +1035,7 @@ void require_live_system(isl_engine* h) {
 
 void invalidate_pattern(isl_engine* h) {
     h->pattern_pairs.clear();
-    h->slotmaps.clear();
+    h->slotmaps.clear(); h->blockmaps.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
     h->nnz = 0;
@@ -1018,7 +1059,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     // assembly call): then the old arrays are released first, their memory is needed for the keys of large systems
     const bool carry = h->nnz > 0 && h->val.p && !h->val_is_zero;
     if (carry) materialize_zero(h);
-    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->nnz = 0; h->val_zero_pending = false; }
+    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->blockmaps.clear(); h->nnz = 0; h->val_zero_pending = false; }
     int64_t total = 0;
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
@@ -1106,7 +1147,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     h->rowptr.swap(rowptr); h->col.swap(col); h->val.swap(val);
     h->nnz = nnz;
     h->pattern_pairs = pairs;
-    h->slotmaps.clear();
+    h->slotmaps.clear(); h->blockmaps.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
 }
@@ -1146,6 +1187,18 @@ const isl_engine::SlotMap* get_slotmap(isl_engine* h, int t, int c) {
 void bind_slots(isl_engine* h, AsmParams& p, int t, int c) {
     const isl_engine::SlotMap* m = get_slotmap(h, t, c);
     p.slot = m->s32.p; p.slot64 = m->s64.p;
+}
+void bind_blockmap(isl_engine* h, AsmParams& p, int t) {
+    auto it = h->blockmaps.find(t);
+    if (it == h->blockmaps.end()) {
+        FieldDev& f = h->fields[t];
+        auto bm = std::make_unique<isl_engine::BlockMap>();
+        const int64_t n = h->n_owned * f.ndpe * f.ndpe;
+        bm->base.alloc(n); bm->len.alloc(h->n_owned * f.ndpe);
+        ISL_LAUNCH(h, k_blockmap, h->grid_for(n, 256), 256, 0, f.elem_dof.p, f.eqn.p, h->n_owned, f.ndpe, h->rowptr.p, h->col.p, bm->base.p, bm->len.p);
+        it = h->blockmaps.emplace(t, std::move(bm)).first;
+    }
+    p.bbase = it->second->base.p; p.blen = it->second->len.p;
 }
 
 TableDev* get_tables(isl_engine* h, int quad_deg, int t, int c) {
@@ -2110,6 +2163,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;
         if (const char* m = getenv("ISL_STAGE_KB")) h->stage_kb = std::max(8, std::min(200, atoi(m)));   // test knob: 64-bit slot maps at any size
@@ -2246,7 +2300,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned; h->affine_state = -1;
         for (auto& f : h->fields) f.eorder.release();
-        h->slotmaps.clear();
+        h->slotmaps.clear(); h->blockmaps.clear();
         h->patchsets.clear();
         h->fromk_sets.clear();
     });
@@ -2432,14 +2486,17 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
         fill_common(h, p, quad_deg, t, c);
         materialize_zero(h);
         h->val_is_zero = false;
-        bind_slots(h, p, t, c); p.kernel_id = kid; p.incremental = incremental;
+        const bool hypel = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE);
+        const bool sym_kernel = h->tangent_sym && hypel && ft.ds == 3 && h->dim == 3 && t == c && !ft.has_masters && ft.ndpe <= 27;
+        if (sym_kernel && h->block_slots) bind_blockmap(h, p, t);   // one position per node pair, no per-entry slot map
+        else bind_slots(h, p, t, c);
+        p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
         p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT && kid != ISL_K_MASS);
         p.nqdata = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) ? 81 : (kid == ISL_K_CONVECTION ? 4 : 0);
         bind_aux(h, p, kid, c, aux);
-        if (h->tangent_sym && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE) && ft.ds == 3 && h->dim == 3 && t == c &&
-            !ft.has_masters && ft.ndpe <= 27) {
+        if (sym_kernel) {
             launch_hypel_sym(h, p);
             return;
         }

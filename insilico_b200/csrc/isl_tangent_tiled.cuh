@@ -282,6 +282,24 @@ __global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p,
         for (int eb = 0; eb < nb; eb++) {
             const int64_t e = p.eid(base + eb);
             const double* Kl = smem + (size_t)eb * L.per_elem;
+            if (p.bbase) {
+                // node-block positions: work item = (row i of the local matrix, trial node N): three neighbouring CSR
+                // entries at base(M, N) + ci * len(M); the 5.8 KB (Q2) table of an element replaces 26 KB of slots
+                const int64_t* bb = p.bbase + (size_t)e * nt * nt;
+                const int32_t* bl = p.blen + (size_t)e * nt;
+                for (int w = tid; w < nr * nt; w += nth) {
+                    const int i = w / nt, N = w - i * nt, M = i / 3, ci = i - M * 3;
+                    const int64_t b = __ldg(bb + M * nt + N);
+                    const double* kl = Kl + i * nr + N * 3;
+                    if (b >= 0) {
+                        double* dst = p.val + b + (int64_t)ci * __ldg(bl + M);
+                        atomicAdd(dst, kl[0]); atomicAdd(dst + 1, kl[1]); atomicAdd(dst + 2, kl[2]);
+                    } else {
+                        for (int k = 0; k < 3; k++) scatter_entry(p, e, i, N * 3 + k, nr, nr, kl[k]);
+                    }
+                }
+                continue;
+            }
             if (p.slot64) {   // systems with 2^31 or more non-zeros: 64-bit positions
                 const int64_t* sw = p.slot64 + (size_t)e * nn;
                 for (int t0 = tid; t0 < nn; t0 += 2 * nth) {
