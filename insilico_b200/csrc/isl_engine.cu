@@ -350,6 +350,15 @@ __device__ __forceinline__ void scatter_entry(const AsmParams& p, int64_t e, int
     }
 }
 
+// entry (M,i; N,k) through the node-block map when the pair is regular, else the per-entry path
+__device__ __forceinline__ void scatter_block_entry(const AsmParams& p, int64_t e, int M, int i, int N, int k, int nr, int ncl, double v) {
+    if (p.bbase) {
+        const int64_t b = p.bbase[((size_t)e * p.nt + M) * p.nc + N];
+        if (b >= 0) { atomicAdd(p.val + b + (int64_t)i * p.blen[(size_t)e * p.nt + M] + k, v); return; }
+    }
+    scatter_entry(p, e, M * p.dst + i, N * p.dsc + k, nr, ncl, v);
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
     extern __shared__ double smem[];
@@ -394,7 +403,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         for (int L = 0; L < DIM; L++) sum += gM[J] * ce[J * 9 + L] * gN[L];
                     acc += sum * (s.sDet[eq] * p.w[q]);
                 }
-                scatter_entry(p, p.eid(base + eb), i, j, nr, ncl, acc);
+                scatter_block_entry(p, p.eid(base + eb), M, ci, N, ck, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_LAPLACE || p.kernel_id == ISL_K_VECTOR_LAPLACE) {
             for (int t = tid; t < nb * p.nt * p.nc; t += nth) {
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     const double kap = p.kq ? p.kq[(size_t)p.eid(base + eb) * p.nq + q] : p.p0;
                     acc += dot * (kap * s.sDet[eq] * p.w[q]);
                 }
-                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_MASS) {
             // base/kernel/Mass.hpp:88-138: (factor detJ w) phi_M psi_N on every DoF component
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                 double acc = 0.;
                 for (int q = 0; q < p.nq; q++)
                     acc += (p.p0 * s.sDet[eb * p.nq + q] * p.w[q]) * p.Nt[q * p.nt + M] * p.Nc[q * p.nc + N];
-                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_CONVECTION) {
             // fluid/Convection.hpp:88-166 (Picard form): phi_M (uAdv . grad phi_N + 0.5 div(u) phi_N) rho detJ w on every
@@ -446,7 +455,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     for (int k = 0; k < p.dst; k++) adv += qd[k] * gN[k];
                     acc += p.Nt[q * p.nt + M] * (adv + 0.5 * qd[3] * p.Nc[q * p.nc + N]) * p.p0 * s.sDet[eq] * p.w[q];
                 }
-                for (int c = 0; c < p.dsc; c++) scatter_entry(p, p.eid(base + eb), M * p.dst + c, N * p.dsc + c, nr, ncl, acc);
+                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
             // B(M d + i, N) = -detJ w g_M[i] psi_N
@@ -459,7 +468,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGt[((size_t)eq * p.nt + M) * DIM + d] * p.Nc[q * p.nc + N];
                     }
-                scatter_entry(p, p.eid(base + eb), i, N, nr, ncl, acc);
+                scatter_block_entry(p, p.eid(base + eb), M, d, N, 0, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_VELOCITY_DIVERGENCE) {
             // transpose of the pressure-gradient block on the transposed tuple, optional sign change
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGc[((size_t)eq * p.nc + N) * DIM + d] * p.Nt[q * p.nt + Mp];
                     }
-                scatter_entry(p, p.eid(base + eb), Mp, j, nr, ncl, sgn * acc);
+                scatter_block_entry(p, p.eid(base + eb), Mp, 0, N, d, nr, ncl, sgn * acc);
             }
         }
         __syncthreads();
@@ -782,29 +791,31 @@ __global__ void k_slotmap(const int32_t* er, const int32_t* ec, int64_t n_elems,
         slot[t] = (r < 0 || c < 0) ? (SLOT)-1 : (SLOT)find_in_row(rowptr, col, r, c);
     }
 }
-// node-block position map: base[e][M][N] = CSR position of entry (row of (node M, component 0), column of (node N, component
-// 0)) when the pair is REGULAR -- all DS components of both nodes ACTIVE and numbered consecutively, the DS rows of node M
-// of equal length and holding the columns of node N at the same offset -- so that entry (M,i; N,k) sits at
-// base + i * len[e][M] + k; -1 otherwise (the kernel then searches the row).  DS = 3.
-__global__ void k_blockmap(const int32_t* elem_dof, const int32_t* eqn, int64_t n_elems, int nt, const int64_t* rowptr, const int32_t* col,
-                           int64_t* base, int32_t* len) {
-    const int64_t n = n_elems * nt * nt;
+// node-block position map of a (test, trial) field pair: base[e][M][N] = CSR position of entry (row of (test node M,
+// component 0), column of (trial node N, component 0)) when the pair is REGULAR -- all components of both nodes ACTIVE and
+// numbered consecutively, the rows of node M of equal length and holding the columns of node N at the same offset -- so
+// that entry (M,i; N,k) sits at base + i * len[e][M] + k; -1 otherwise (the kernels then take the per-entry path).
+__global__ void k_blockmap(const int32_t* ed_t, const int32_t* eqn_t, int nt, int dst, const int32_t* ed_c, const int32_t* eqn_c, int nc, int dsc,
+                           int64_t n_elems, const int64_t* rowptr, const int32_t* col, int64_t* base, int32_t* len) {
+    const int64_t n = n_elems * nt * nc;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = t / (nt * nt); const int mn = (int)(t % (nt * nt)), M = mn / nt, N = mn % nt;
-        const int32_t* qm = eqn + (size_t)elem_dof[e * nt + M] * 3;
-        const int32_t* qn = eqn + (size_t)elem_dof[e * nt + N] * 3;
+        const int64_t e = t / (nt * nc); const int mn = (int)(t % (nt * nc)), M = mn / nc, N = mn % nc;
+        const int32_t* qm = eqn_t + (size_t)ed_t[e * nt + M] * dst;
+        const int32_t* qn = eqn_c + (size_t)ed_c[e * nc + N] * dsc;
         const int32_t r0 = qm[0], c0 = qn[0];
-        int64_t b = -1; int32_t L = 0;
-        if (r0 >= 0 && qm[1] == r0 + 1 && qm[2] == r0 + 2 && c0 >= 0 && qn[1] == c0 + 1 && qn[2] == c0 + 2) {
-            const int64_t s0 = rowptr[r0], s1 = rowptr[r0 + 1], s2 = rowptr[r0 + 2], s3 = rowptr[r0 + 3];
-            L = (int32_t)(s1 - s0);
-            const int64_t p0 = find_in_row(rowptr, col, r0, c0);
-            if (p0 >= 0 && s2 - s1 == L && s3 - s2 == L && p0 + 2 < s1 && col[p0 + 1] == c0 + 1 && col[p0 + 2] == c0 + 2) {
-                const int64_t o = p0 - s0;
-                bool same = true;
-                for (int i = 1; i < 3; i++) { const int64_t q = s0 + (int64_t)i * L + o; same = same && col[q] == c0 && col[q + 1] == c0 + 1 && col[q + 2] == c0 + 2; }
-                if (same) b = p0;
-            }
+        bool ok = r0 >= 0 && c0 >= 0;
+        for (int i = 1; i < dst && ok; i++) ok = qm[i] == r0 + i;
+        for (int k = 1; k < dsc && ok; k++) ok = qn[k] == c0 + k;
+        int64_t b = -1;
+        const int32_t L = (r0 >= 0) ? (int32_t)(rowptr[r0 + 1] - rowptr[r0]) : 0;   // (independent of the trial node: len[e][M])
+        if (ok) {
+            const int64_t s0 = rowptr[r0];
+            for (int i = 1; i < dst && ok; i++) ok = (rowptr[r0 + i + 1] - rowptr[r0 + i]) == L;
+            const int64_t p0 = ok ? find_in_row(rowptr, col, r0, c0) : -1;
+            ok = ok && p0 >= 0 && p0 + dsc <= s0 + L;
+            for (int i = 0; i < dst && ok; i++)
+                for (int k = 0; k < dsc && ok; k++) ok = col[p0 + (int64_t)i * L + k] == c0 + k;
+            if (ok) b = p0;
         }
         base[t] = b;
         if (N == 0) len[e * nt + M] = L;
@@ -934,7 +945,7 @@ struct isl_engine {
     struct SlotMap { DevBuf<int32_t> s32; DevBuf<int64_t> s64; };
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
-    std::map<int, std::unique_ptr<BlockMap>> blockmaps;   // per field (hyperelastic tile kernel)
+    std::map<std::pair<int, int>, std::unique_ptr<BlockMap>> blockmaps;   // per (test, trial) pair
     int block_slots = 1;       // ISL_BLOCK_SLOTS
     bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
     bool force_slot64 = false;
@@ -1188,17 +1199,21 @@ void bind_slots(isl_engine* h, AsmParams& p, int t, int c) {
     const isl_engine::SlotMap* m = get_slotmap(h, t, c);
     p.slot = m->s32.p; p.slot64 = m->s64.p;
 }
-void bind_blockmap(isl_engine* h, AsmParams& p, int t) {
-    auto it = h->blockmaps.find(t);
+bool bind_blockmap(isl_engine* h, AsmParams& p, int t, int c) {
+    FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
+    if (!h->block_slots || ft.ds * fc.ds <= 1 || ft.ds > 3 || fc.ds > 3 || ft.has_masters || fc.has_masters) return false;
+    auto key = std::make_pair(t, c);
+    auto it = h->blockmaps.find(key);
     if (it == h->blockmaps.end()) {
-        FieldDev& f = h->fields[t];
         auto bm = std::make_unique<isl_engine::BlockMap>();
-        const int64_t n = h->n_owned * f.ndpe * f.ndpe;
-        bm->base.alloc(n); bm->len.alloc(h->n_owned * f.ndpe);
-        ISL_LAUNCH(h, k_blockmap, h->grid_for(n, 256), 256, 0, f.elem_dof.p, f.eqn.p, h->n_owned, f.ndpe, h->rowptr.p, h->col.p, bm->base.p, bm->len.p);
-        it = h->blockmaps.emplace(t, std::move(bm)).first;
+        const int64_t n = h->n_owned * ft.ndpe * fc.ndpe;
+        bm->base.alloc(n); bm->len.alloc(h->n_owned * ft.ndpe);
+        ISL_LAUNCH(h, k_blockmap, h->grid_for(n, 256), 256, 0, ft.elem_dof.p, ft.eqn.p, ft.ndpe, ft.ds, fc.elem_dof.p, fc.eqn.p, fc.ndpe, fc.ds,
+                   h->n_owned, h->rowptr.p, h->col.p, bm->base.p, bm->len.p);
+        it = h->blockmaps.emplace(key, std::move(bm)).first;
     }
     p.bbase = it->second->base.p; p.blen = it->second->len.p;
+    return true;
 }
 
 TableDev* get_tables(isl_engine* h, int quad_deg, int t, int c) {
@@ -2488,8 +2503,10 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
         h->val_is_zero = false;
         const bool hypel = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE);
         const bool sym_kernel = h->tangent_sym && hypel && ft.ds == 3 && h->dim == 3 && t == c && !ft.has_masters && ft.ndpe <= 27;
-        if (sym_kernel && h->block_slots) bind_blockmap(h, p, t);   // one position per node pair, no per-entry slot map
-        else bind_slots(h, p, t, c);
+        // one position per node pair instead of a slot per entry (vector fields without slaves of master DoFs); the
+        // per-entry path of irregular pairs (constrained nodes) then searches the row
+        const bool tiled = h->tangent_tiled && hypel && ft.ds == h->dim && !sym_kernel;   // (experimental kernel: per-entry slots)
+        if (tiled || !bind_blockmap(h, p, t, c)) bind_slots(h, p, t, c);
         p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
