@@ -946,7 +946,7 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
     std::map<std::pair<int, int>, std::unique_ptr<BlockMap>> blockmaps;   // per (test, trial) pair
-    int block_slots = 1;       // ISL_BLOCK_SLOTS
+    int block_slots = 1;       // ISL_BLOCK_SLOTS: 0 per-entry slot maps only, 1 node-block maps in the generic kernels, 2 also in the tile kernel
     bool wide_slots = false;   // nnz >= 2^31 (or ISL_SLOT64=1): CSR positions do not fit 32 bits
     bool force_slot64 = false;
     int fromk_tile_order = 0;  // row tiles of the general Q1 path along a Z-curve (ISL_FROMK_TILE_ORDER=1): measured slower, 4.00 vs 3.67 ms (session27)
@@ -2178,7 +2178,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
-        if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;
         if (const char* m = getenv("ISL_STAGE_KB")) h->stage_kb = std::max(8, std::min(200, atoi(m)));   // test knob: 64-bit slot maps at any size
@@ -2506,7 +2506,9 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
         // one position per node pair instead of a slot per entry (vector fields without slaves of master DoFs); the
         // per-entry path of irregular pairs (constrained nodes) then searches the row
         const bool tiled = h->tangent_tiled && hypel && ft.ds == h->dim && !sym_kernel;   // (experimental kernel: per-entry slots)
-        if (tiled || !bind_blockmap(h, p, t, c)) bind_slots(h, p, t, c);
+        // (measured, session29: the generic kernels gain -- Stokes UU block 15.2 -> 13.5 ms --, the hyperelastic tile kernel does
+        // not -- C3 49.6 / 49.2 ms, C4 61.0 / 62.8 ms --, so it keeps its per-entry slots unless ISL_BLOCK_SLOTS=2)
+        if (tiled || (sym_kernel && h->block_slots < 2) || !bind_blockmap(h, p, t, c)) bind_slots(h, p, t, c);
         p.kernel_id = kid; p.incremental = incremental;
         p.p0 = params ? params[0] : 0.; p.p1 = (params && (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE)) ? params[1] : 0.;
         p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
