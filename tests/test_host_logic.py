@@ -186,3 +186,23 @@ def test_numbering_at_size_equals_reference_run(key):
         assert _digest(np.where(f["eqn"] >= 0, f["eqn"], -1), np.int64) == g["eqn"], "equation numbers differ from the reference's"
         ed0, nobj0 = prob.dof_generate(f["fe_deg"])
         assert nobj0 == g["n_obj"] and _digest(ed0, np.int32) == g["elem_dof"]
+
+
+@pytest.mark.parametrize("shape,n,qdeg", [(E.HEX, 3, 3), (E.TET, 2, 4), (E.QUAD, 5, 3), (E.TRI, 4, 4)])
+def test_boundary_surface_elements_and_points_equal_oracle(shape, n, qdeg):
+    """host side of the surface terms (isl_boundary_surface, isl_surface_points) against the oracle's restatement of
+    generateBoundaryMesh / Geometry / SurfaceNormal (pinned on the reference run by the neumann_* fixtures)"""
+    from oracle import oracle as orc
+    from tests import flows
+    coords, conn = flows.make_mesh(shape, n, True, True)
+    pairs = E.mesh_boundary(shape, 1, conn)
+    ss, de, sx, sp = E.boundary_surface(shape, 1, coords, conn, pairs)
+    prob = orc.Problem(shape, 1, coords, conn.astype(np.int64))
+    de_o, sx_o, sp_o = prob.boundary_surface(prob.mesh_boundary())
+    assert np.array_equal(de, de_o) and np.array_equal(sx, sx_o) and np.array_equal(sp, sp_o)
+    x, nr, dg = E.surface_points(ss, 1, sx, qdeg)
+    xo, nro, dgo = orc.surface_points(ss, 1, sx, qdeg)
+    assert np.abs(x - xo).max() <= 1e-15 and np.abs(nr - nro).max() <= 1e-15 and np.abs(dg - dgo).max() <= 1e-15 * dg.max()
+    assert np.allclose(np.linalg.norm(nr, axis=-1), 1.0, atol=1e-14)
+    # outward: the normal points away from the centre of the unit square / cube on every boundary face
+    assert np.all(((x - 0.5) * nr).sum(axis=-1) > 0)
