@@ -448,12 +448,22 @@ def bench_config(args, rank, world, local_rank, cores):
            "peak_source": "measured (isl_measure_fp64_peak: DFMA chains, CUDA events, this run)",
            "algorithmic_flops_per_element": flops}
     f64["frac"] = f64["achieved"] / fp64_peak if fp64_peak else None
+    # the scatter: FP64 atomic adds per second against the measured rate of the same access pattern (the generic kernels
+    # add three neighbouring entries per node pair for vector fields, single entries for scalar fields)
+    atomics = None
+    if cfg != "C1":
+        n_at = w.atomics_per_element()
+        pattern = 1 if max(f["ds"] for f in w.fields) > 1 else 2
+        red_peak = eng.measure_red_peak(pattern)
+        atomics = {"achieved": n_at * ne_rank / t_asm / 1e9, "peak": red_peak, "unit": "G atomic adds/s", "atomics_per_element": n_at,
+                   "peak_source": "measured (isl_measure_red_peak pattern %d: RED.ADD.F64 into a 2 GiB array, this run)" % pattern}
+        atomics["frac"] = atomics["achieved"] / red_peak if red_peak else None
     main_r = dict(f64 if BOUND[cfg] == "fp64" else hbm)
     op = w.ops[k_dom]
     roof = {"bound": BOUND[cfg], "kernel": "%s %s (k_tangent / k_force family)" % (op[0], KERNEL_NAME.get(op[1], "bodyforce") if op[0] != "body" else "bodyforce"),
             "achieved": main_r["achieved"], "peak": main_r["peak"], "unit": main_r["unit"], "frac": main_r["frac"], "traffic": None,
             "kernel_ms": t_asm * 1e3, "per_op_ms": [{"op": o[0], "kernel": KERNEL_NAME.get(o[1], "body") if o[0] != "body" else "body", "ms": t} for o, t in zip(w.ops, per_op)],
-            "hbm": hbm, "fp64": f64}
+            "hbm": hbm, "fp64": f64, "atomics": atomics}
     cfgd = {"workload": w.description, "n": n, "n_elems": int(ne_global), "n_eqn": int(w.n_eqn), "nnz_per_gpu": int(nnz),
             "partition": ("z-slabs of cube layers generated per rank, owned rows, NCCL ghost-row exchange" if slab else
                           "element blocks along a Z-curve, owned rows, NCCL ghost-row exchange") if world > 1 else "single GPU",

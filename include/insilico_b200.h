@@ -77,6 +77,10 @@ int64_t isl_kernel_launches(isl_handle h);
 /* measured FP64 peak of this device (independent DFMA chains in registers, CUDA events on the engine stream):
  * the denominator of the FP64-pipe roofline fraction SURVEY 8(d) asks for; nothing comparable in the reference */
 int isl_measure_fp64_peak(isl_handle h, double* tflops);
+/* measured throughput (1e9 per second) of FP64 atomic adds without return value into a 2 GiB array: pattern 0 coalesced
+ * sweep, 1 three neighbouring entries at pseudo-random places, 2 single entries at pseudo-random places.  The scatter of
+ * the generic kernels (6 561 adds per Q2 x 3 element) is bounded by it; reported next to configs 3-5.               */
+int isl_measure_red_peak(isl_handle h, int pattern, double* gatomics_per_s);
 
 /* ---- host-side tables (no GPU needed) ------------------------------------ */
 /* base::Quadrature<DEG,SHAPE> (base/Quadrature.hpp:113-143): returns #points; weights[n], points[n*dim] */

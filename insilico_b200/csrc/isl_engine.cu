@@ -3022,6 +3022,32 @@ int isl_measure_fp64_peak(isl_handle h, double* tflops) {
     });
 }
 
+int isl_measure_red_peak(isl_handle h, int pattern, double* gatomics_per_s) {
+    return guarded([&] {
+        ISL_REQUIRE(gatomics_per_s && pattern >= 0 && pattern <= 2, "bad arguments");
+        flush_pending(h);
+        const unsigned long long n = 1ull << 28;   // 2 GiB of doubles: far larger than L2
+        DevBuf<double> a; a.alloc((size_t)n);
+        ISL_CUDA(cudaMemsetAsync(a.p, 0, (size_t)n * sizeof(double), h->stream));
+        cudaEvent_t e0, e1;
+        ISL_CUDA(cudaEventCreate(&e0)); ISL_CUDA(cudaEventCreate(&e1));
+        const int grid = h->n_sm * 8, iters = 512;
+        double best = 0.;
+        for (int rep = 0; rep < 3; rep++) {
+            ISL_CUDA(cudaEventRecord(e0, h->stream));
+            ISL_LAUNCH(h, k_red_peak, grid, 256, 0, a.p, n, pattern, iters);
+            ISL_CUDA(cudaEventRecord(e1, h->stream));
+            ISL_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            ISL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = (double)grid * 256.0 * iters * (pattern == 1 ? 3.0 : 1.0);
+            if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *gatomics_per_s = best;
+    });
+}
+
 // ---- multi-GPU: communicator and interface-row exchange inside the engine (isl_comm.cuh) ----
 int isl_comm_unique_id(void* id128) {
     return guarded([&] {

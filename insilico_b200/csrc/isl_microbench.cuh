@@ -23,3 +23,22 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
     for (int j = 0; j < CHAINS; j++) s += a[j];
     if (s == 123.456) out[0] = s;  // never true for the chosen b, c: keeps the chains alive
 }
+
+// Measured throughput of FP64 atomic adds without return value (RED.E.ADD.F64) into a large array: the scatter of the
+// generic kernels is bounded by it.  pattern 0: consecutive threads add to consecutive entries (fully coalesced sweep);
+// 1: every thread adds to three neighbouring entries at a pseudo-random place (what the vector-field kernels do: the
+// three components of a node pair, rows of an unstructured numbering); 2: single entries at pseudo-random places.
+__global__ void __launch_bounds__(256) k_red_peak(double* a, unsigned long long n, int pattern, int iters) {
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long x = tid * 0x9E3779B97F4A7C15ull + 12345ull;
+    for (int it = 0; it < iters; it++) {
+        if (pattern == 0) {
+            atomicAdd(a + (tid + (unsigned long long)it * nth) % n, 1.0);
+        } else {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+            const unsigned long long p = ((x * 0x2545F4914F6CDD1Dull) >> 11) % (n - 3);
+            atomicAdd(a + p, 1.0);
+            if (pattern == 1) { atomicAdd(a + p + 1, 1.0); atomicAdd(a + p + 2, 1.0); }
+        }
+    }
+}

@@ -34,7 +34,7 @@ SHAPE_DIM = {LINE: 1, TRI: 2, QUAD: 2, TET: 3, HEX: 3}
 EXPORTED = [
     "isl_last_error", "isl_version", "isl_engine_create", "isl_engine_destroy", "isl_engine_set_option", "isl_synchronize", "isl_flush",
     "isl_engine_stream",
-    "isl_kernel_launches", "isl_measure_fp64_peak", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
+    "isl_kernel_launches", "isl_measure_fp64_peak", "isl_measure_red_peak", "isl_quadrature", "isl_shape_nfun", "isl_shape_eval", "isl_support_points",
     "isl_dof_generate", "isl_dof_generate_device", "isl_ndpe", "isl_mesh_boundary", "isl_boundary_dofs", "isl_number_dofs", "isl_mesh_set",
     "isl_mesh_set_owned", "isl_mesh_update_coords", "isl_field_set", "isl_field_set_constraints", "isl_field_update",
     "isl_system_create", "isl_pattern_register",
@@ -263,7 +263,14 @@ class Engine:
         _chk(lib().isl_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
 
+    def measure_red_peak(self, pattern):
+        """1e9 FP64 atomic adds per second into a 2 GiB array (0 coalesced, 1 triples at random places, 2 singles at random places)"""
+        v = C.c_double()
+        _chk(lib().isl_measure_red_peak(self.h, pattern, C.byref(v)))
+        return v.value
+
     # base::Unstructured<SHAPE,GEOMDEG>
+
     def set_mesh(self, shape, geom_deg, coords, conn, n_nodes=None, n_elems=None, dim=None):
         if not isinstance(coords, (int, np.integer)):
             coords = np.ascontiguousarray(coords, dtype=np.float64)

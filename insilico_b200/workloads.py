@@ -141,6 +141,27 @@ class Workload:
             total += nq * (geo + per)
         return total
 
+    def atomics_per_element(self):
+        """FP64 atomic adds one step issues per element in the generic kernels: one per local matrix entry that is
+        integrated (all (nt ds)(nc ds) entries of a hyperelastic tangent, the component-diagonal ones of the Laplace-type
+        kernels, nt dim nc of a Stokes coupling block) and one per local force entry"""
+        total = 0
+        for op in self.ops:
+            if op[0] == "body":
+                f = self.fields[op[3]]
+                total += f["ndpe"] * f["ds"]
+                continue
+            ft, fc = self.fields[op[4]], self.fields[op[5]]
+            if op[0] != "matrix":
+                total += ft["ndpe"] * ft["ds"]
+            elif op[1] in (E.K_HYPEL_STVENANT, E.K_HYPEL_NEOHOOKE):
+                total += (ft["ndpe"] * ft["ds"]) * (fc["ndpe"] * fc["ds"])
+            elif op[1] in (E.K_PRESSURE_GRADIENT, E.K_VELOCITY_DIVERGENCE):
+                total += ft["ndpe"] * fc["ndpe"] * self.dim
+            else:
+                total += ft["ndpe"] * fc["ndpe"] * fc["ds"]
+        return total
+
     def algorithmic_bytes_per_element(self, nnz):
         """compulsory HBM traffic of one step per element, every array touched once: connectivity,
         element -> DoF tables, element -> CSR slot maps of the matrix operations, and per element its share of the
