@@ -109,6 +109,7 @@ struct AsmParams {
     const int32_t* slot; const int64_t* slot64;   // element -> CSR position maps: 32-bit, or 64-bit when nnz >= 2^31 (exactly one is set)
     // node-block position map of the hyperelastic tile kernel (one base position per pair of nodes instead of ds*ds slots)
     const int64_t* bbase; const int32_t* blen;
+    double* kout;   // hyperelastic tile kernel: local matrices go to kout[e][nr][nr] instead of the CSR (isl_gather.cuh)
     double* val; double* rhs;
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
@@ -586,6 +587,7 @@ __global__ void __launch_bounds__(256) k_force(const AsmParams p) {
 }
 
 #include "isl_tangent_tiled.cuh"
+#include "isl_gather.cuh"
 #include "isl_neumann.cuh"
 #include "isl_dof_dev.cuh"
 
@@ -944,6 +946,8 @@ struct isl_engine {
     std::set<std::pair<int, int>> pattern_pairs, sys_pairs;
     struct SlotMap { DevBuf<int32_t> s32; DevBuf<int64_t> s64; };
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
+    std::map<int, std::unique_ptr<GatherSet>> gathersets;   // per field: tables of the atomic-free hyperelastic path
+    int hypel_gather = 1;      // ISL_HYPEL_GATHER
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
     std::map<std::pair<int, int>, std::unique_ptr<BlockMap>> blockmaps;   // per (test, trial) pair
     int block_slots = 1;       // ISL_BLOCK_SLOTS: 0 per-entry slot maps only, 1 node-block maps in the generic kernels, 2 also in the tile kernel
@@ -1046,7 +1050,7 @@ void require_live_system(isl_engine* h) {
 
 void invalidate_pattern(isl_engine* h) {
     h->pattern_pairs.clear();
-    h->slotmaps.clear(); h->blockmaps.clear();
+    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
     h->nnz = 0;
@@ -1070,7 +1074,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     // assembly call): then the old arrays are released first, their memory is needed for the keys of large systems
     const bool carry = h->nnz > 0 && h->val.p && !h->val_is_zero;
     if (carry) materialize_zero(h);
-    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->blockmaps.clear(); h->nnz = 0; h->val_zero_pending = false; }
+    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->nnz = 0; h->val_zero_pending = false; }
     int64_t total = 0;
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
@@ -1158,7 +1162,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     h->rowptr.swap(rowptr); h->col.swap(col); h->val.swap(val);
     h->nnz = nnz;
     h->pattern_pairs = pairs;
-    h->slotmaps.clear(); h->blockmaps.clear();
+    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
 }
@@ -1288,6 +1292,74 @@ const int32_t* get_eorder(isl_engine* h, int field) {
     h->launches += 4;
     ISL_CUDA(cudaStreamSynchronize(h->stream));
     return f.eorder.p;
+}
+
+GatherSet* get_gatherset(isl_engine* h, int t) {
+    auto it = h->gathersets.find(t);
+    if (it != h->gathersets.end()) return it->second->ok ? it->second.get() : nullptr;
+    auto gs = std::make_unique<GatherSet>();
+    FieldDev& f = h->fields[t];
+    build_elem_eqn(h, f);
+    const int nr = f.ndpe * f.ds;
+    const int64_t P = h->n_owned * nr, n_rows = h->n_eqn;
+    gs->nr = nr; gs->n_rows = n_rows;
+    if (P > 0 && P < ((int64_t)1 << 31) && n_rows > 0) {
+        DevBuf<int32_t> key, key2, idx;
+        key.alloc(P); key2.alloc(P); idx.alloc(P); gs->pair.alloc(P);
+        ISL_LAUNCH(h, k_gs_keys, h->grid_for(P, 256), 256, 0, f.elem_eqn.p, P, key.p, idx.p);
+        size_t tb = 0;
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, gs->pair.p, P, 0, 31, h->stream));
+        DevBuf<char> tmp; tmp.alloc(tb);
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, gs->pair.p, P, 0, 31, h->stream));
+        h->launches += 4;
+        gs->row_start.alloc(n_rows + 1);
+        ISL_LAUNCH(h, k_gs_row_start, h->grid_for(n_rows + 1, 256), 256, 0, key2.p, P, n_rows, gs->row_start.p);
+        DevBuf<int> st; st.alloc(2);
+        ISL_CUDA(cudaMemsetAsync(st.p, 0, 2 * sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_gs_max_len, std::min(h->grid_for(n_rows, 256), h->n_sm * 8), 256, 0, h->rowptr.p, n_rows, st.p + 1);
+        ISL_LAUNCH(h, k_gs_dup, h->grid_for(P, 256), 256, 0, f.elem_eqn.p, h->n_owned, nr, st.p);
+        int64_t n_pairs = 0;
+        ISL_CUDA(cudaMemcpyAsync(&n_pairs, gs->row_start.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        gs->n_pairs = n_pairs;
+        gs->pos.alloc((size_t)std::max<int64_t>(n_pairs, 1) * nr);
+        if (n_pairs > 0)
+            ISL_LAUNCH(h, k_gs_pos, h->grid_for(n_pairs * nr, 256), 256, 0, gs->pair.p, key2.p, n_pairs, nr, f.elem_eqn.p, h->rowptr.p, h->col.p,
+                       gs->pos.p, st.p);
+        int hst[2] = {0, 0};
+        ISL_CUDA(cudaMemcpyAsync(hst, st.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        gs->max_len = hst[1];
+        // a row buffer per warp must fit: 8 warps x max_len doubles within the shared memory of a CTA
+        gs->ok = hst[0] == 0 && (size_t)gs->max_len * 8 * sizeof(double) <= 200 * 1024;
+        if (gs->ok) gs->Kbuf.alloc((size_t)h->n_owned * nr * nr);
+        if (getenv("ISL_VERBOSE"))
+            fprintf(stderr, "[isl] atomic-free hyperelastic path: %s, %lld (element, row) pairs, longest row %d, K buffer %.2f GB, positions %.2f GB\n",
+                    gs->ok ? "ok" : "not eligible", (long long)n_pairs, gs->max_len, gs->ok ? (double)h->n_owned * nr * nr * 8 / 1e9 : 0.,
+                    (double)n_pairs * nr * 2 / 1e9);
+    }
+    GatherSet* out = gs->ok ? gs.get() : nullptr;
+    h->gathersets[t] = std::move(gs);
+    return out;
+}
+
+// rows gathered from the stored element matrices (isl_gather.cuh, kernel B)
+void launch_gather_rows(isl_engine* h, GatherSet* gs, const AsmParams& a, const FieldDev& f, bool store) {
+    GatherParams g; std::memset(&g, 0, sizeof(g));
+    g.pair = gs->pair.p; g.row_start = gs->row_start.p; g.pos = gs->pos.p; g.Kbuf = gs->Kbuf.p;
+    g.nr = gs->nr; g.nt = f.ndpe; g.ds = f.ds; g.n_rows = gs->n_rows;
+    g.rowptr = h->rowptr.p; g.val = h->val.p; g.rhs = h->rhs.p;
+    g.ed = f.elem_dof.p; g.status = f.status.p; g.presc = f.presc.p; g.values = f.values.p; g.incremental = a.incremental;
+    g.store = store ? 1 : 0;
+    g.buf_len = (gs->max_len + 1) & ~1;
+    constexpr int W = 8;
+    const size_t smem = (size_t)W * g.buf_len * sizeof(double);
+    ISL_CUDA(cudaFuncSetAttribute(k_gather_rows<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    const int64_t nb = (gs->n_rows + W - 1) / W;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)h->n_sm * 16));
+    k_gather_rows<W><<<grid, W * 32, smem, h->stream>>>(g);
+    h->launches++;
+    ISL_CUDA(cudaGetLastError());
 }
 
 void launch_hypel_sym(isl_engine* h, AsmParams& p) {
@@ -2178,6 +2250,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_TILED")) h->tangent_tiled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_HYPEL_GATHER")) h->hypel_gather = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;
@@ -2315,7 +2388,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned; h->affine_state = -1;
         for (auto& f : h->fields) f.eorder.release();
-        h->slotmaps.clear(); h->blockmaps.clear();
+        h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
         h->patchsets.clear();
         h->fromk_sets.clear();
     });
@@ -2499,10 +2572,25 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
         }
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
-        materialize_zero(h);
-        h->val_is_zero = false;
         const bool hypel = (kid == ISL_K_HYPEL_STVENANT || kid == ISL_K_HYPEL_NEOHOOKE);
         const bool sym_kernel = h->tangent_sym && hypel && ft.ds == 3 && h->dim == 3 && t == c && !ft.has_masters && ft.ndpe <= 27;
+        if (sym_kernel && h->hypel_gather) {
+            // atomic-free: element matrices to memory, CSR rows gathered by one warp each (isl_gather.cuh)
+            if (GatherSet* gs = get_gatherset(h, t)) {
+                const bool store = h->val_is_zero && h->pattern_pairs.size() == 1;   // nothing in the rows yet, nothing else will come
+                if (store) h->val_zero_pending = false; else materialize_zero(h);
+                h->val_is_zero = false;
+                p.kernel_id = kid; p.incremental = incremental;
+                p.p0 = params ? params[0] : 0.; p.p1 = params ? params[1] : 0.;
+                p.need_gt = 1; p.need_gc = 1; p.nqdata = 81;
+                p.kout = gs->Kbuf.p;
+                launch_hypel_sym(h, p);
+                launch_gather_rows(h, gs, p, ft, store);
+                return;
+            }
+        }
+        materialize_zero(h);
+        h->val_is_zero = false;
         // one position per node pair instead of a slot per entry (vector fields without slaves of master DoFs); the
         // per-entry path of irregular pairs (constrained nodes) then searches the row
         const bool tiled = h->tangent_tiled && hypel && ft.ds == h->dim && !sym_kernel;   // (experimental kernel: per-entry slots)

@@ -282,6 +282,11 @@ __global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p,
         for (int eb = 0; eb < nb; eb++) {
             const int64_t e = p.eid(base + eb);
             const double* Kl = smem + (size_t)eb * L.per_elem;
+            if (p.kout) {   // atomic-free path: the local matrix goes to memory, the rows are gathered by k_gather_rows
+                double* out = p.kout + (size_t)e * nn;
+                for (int t = tid; t < nn; t += nth) out[t] = Kl[t];
+                continue;
+            }
             if (p.bbase) {
                 // node-block positions: work item = (row i of the local matrix, trial node N): three neighbouring CSR
                 // entries at base(M, N) + ci * len(M); the 5.8 KB (Q2) table of an element replaces 26 KB of slots
