@@ -119,14 +119,14 @@ __global__ void __launch_bounds__(256) k_tangent_hypel_tiled(const AsmParams p) 
 //     broadcast 16-byte loads) and spends 27 multiply-adds per test node on 3 loads; 9 MC results stay in registers.
 // Multiply-adds per Q2-hex element and point: 75 x 81 + 378 x 27 = 16.3 k (k_tangent: 59 k, the tiled kernel: 32.8 k;
 // the algorithmic count of SURVEY 8(d) without symmetry: 21.9 k).
-// Shared memory per element (doubles): X npe*3 | contra nq*9 | det nq | G nq*nt*3 | Ceff nq*82 | F,S,C nq*54.
+// Shared memory per element (doubles): X npe*3 | U nt*3 | contra nq*9 | det nq | G nq*nt*3 | Ceff nq*82 | F,S,C nq*54.
 constexpr int HS_QSTRIDE = 82;   // 81 numbers of Ceff per point, padded to a 16-byte multiple
 
 struct HypelSymLayout {
     int per_elem;   // doubles
-    int oX, oCon, oDet, oG, oQ, oM;
+    int oX, oU, oCon, oDet, oG, oQ, oM;
     __host__ __device__ HypelSymLayout(int npe, int nq, int nt) {
-        oX = 0; oCon = oX + npe * 3; oDet = oCon + nq * 9; oG = oDet + nq; oG += (oG & 1);
+        oX = 0; oU = oX + npe * 3; oCon = oU + nt * 3; oDet = oCon + nq * 9; oG = oDet + nq; oG += (oG & 1);
         oQ = oG + nq * nt * 3; oQ += (oQ & 1); oM = oQ + nq * HS_QSTRIDE; per_elem = oM + nq * 54;
         if (per_elem < 9 * nt * nt) per_elem = 9 * nt * nt;   // the staging area is reused for the local matrix (3 nt)^2
         per_elem += (per_elem & 1);
@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p,
             const int eb = t / (npe * 3), r = t % (npe * 3);
             smem[(size_t)eb * L.per_elem + L.oX + r] = p.coords[(size_t)p.conn[p.eid(base + eb) * npe + r / 3] * 3 + r % 3];
         }
+        // current nodal values of the trial field (all threads; the displacement gradient below reads them from here)
+        for (int t = tid; t < nb * nt * 3; t += nth) {
+            const int eb = t / (nt * 3), r = t % (nt * 3);
+            smem[(size_t)eb * L.per_elem + L.oU + r] = p.val_c[(size_t)p.ed_c[p.eid(base + eb) * nt + r / 3] * 3 + r % 3];
+        }
         __syncthreads();
         // J^-T and det J per point (base/geometry.hpp:142-177,419-445)
         for (int t = tid; t < nb * nq; t += nth) {
@@ -180,18 +185,24 @@ __global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p,
             for (int c = 0; c < 3; c++) E[L.oG + r * 3 + c] = con[c * 3] * dN[0] + con[c * 3 + 1] * dN[1] + con[c * 3 + 2] * dN[2];
         }
         __syncthreads();
+        // displacement gradient GradU(J,i) = sum_f g_f[J] u_f[i] per point, one thread per (point, J, i); summation over
+        // the nodes in ascending order as in post/evaluateField.hpp:228-274 (parked in the F slot of the point)
+        for (int t = tid; t < nb * nq * 9; t += nth) {
+            const int eb = t / (nq * 9), r = t % (nq * 9), q = r / 9, J = (r % 9) / 3, i = r % 3;
+            double* E = smem + (size_t)eb * L.per_elem;
+            const double* g = E + L.oG + (size_t)q * nt * 3;
+            const double* u = E + L.oU;
+            double a = 0.;
+            for (int f = 0; f < nt; f++) a += g[f * 3 + J] * u[f * 3 + i];
+            E[L.oM + q * 54 + J * 3 + i] = a;
+        }
+        __syncthreads();
         // F, S, C per point (solid/Deformation.hpp:25-46, mat/hypel/*.hpp)
         for (int t = tid; t < nb * nq; t += nth) {
             const int eb = t / nq, q = t % nq;
             double* E = smem + (size_t)eb * L.per_elem;
-            const int64_t e = p.eid(base + eb);
-            double GradU[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-            const double* g = E + L.oG + (size_t)q * nt * 3;
-            for (int f = 0; f < nt; f++) {
-                const int32_t obj = p.ed_c[e * nt + f];
-                for (int J = 0; J < 3; J++)
-                    for (int i = 0; i < 3; i++) GradU[J][i] += g[f * 3 + J] * p.val_c[(size_t)obj * 3 + i];
-            }
+            double GradU[3][3];
+            for (int J = 0; J < 3; J++) for (int i = 0; i < 3; i++) GradU[J][i] = E[L.oM + q * 54 + J * 3 + i];
             double F[3][3], S[3][3], C[6][6];
             for (int i = 0; i < 3; i++) for (int J = 0; J < 3; J++) F[i][J] = (i == J ? 1. : 0.) + GradU[J][i];
             material_eval(p.kernel_id, p.p0, p.p1, F, S, C, true);
