@@ -63,7 +63,7 @@ __global__ void k_gs_pos(const int32_t* pair, const int32_t* sorted_key, int64_t
         uint16_t v = 0xffff;
         if (c >= 0) {
             const int64_t at = isl_find_in_row(rowptr, col, r, c);
-            if (at < 0 || at - rowptr[r] >= 0xffff) err[0] = 1; else v = (uint16_t)(at - rowptr[r]);
+            if (at < 0 || at - rowptr[r] >= 0xfffe) err[0] = 1; else v = (uint16_t)(at - rowptr[r]);
         }
         pos[t] = v;
     }
@@ -98,6 +98,42 @@ __global__ void __launch_bounds__(WARPS * 32) k_gather_rows(const GatherParams p
         for (int k = lane; k < len; k += 32) buf[k] = 0.;
         double lift = 0.;
         __syncwarp();
+        if (p.nr <= 96) {
+            // software pipeline over the (element, local row) pairs: the loads of pair q + 1 are in flight while pair q is
+            // added into the row buffer (up to three entries per lane)
+            uint16_t at_n[3]; double v_n[3]; int64_t e_n = 0;
+            auto fetch = [&](int64_t q) {
+                const int32_t pr = __ldg(p.pair + q);
+                e_n = pr / p.nr;
+                const int i = pr - (int)e_n * p.nr;
+                const double* krow = p.Kbuf + ((size_t)e_n * p.nr + i) * p.nr;
+                const uint16_t* pq = p.pos + (size_t)q * p.nr;
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int j = lane + 32 * u;
+                    const bool in = j < p.nr;
+                    at_n[u] = in ? __ldg(pq + j) : (uint16_t)0xfffe;
+                    v_n[u] = in ? __ldg(krow + j) : 0.;
+                }
+            };
+            if (q0 < q1) fetch(q0);
+            for (int64_t q = q0; q < q1; q++) {
+                uint16_t at[3]; double v[3]; const int64_t e = e_n;
+#pragma unroll
+                for (int u = 0; u < 3; u++) { at[u] = at_n[u]; v[u] = v_n[u]; }
+                if (q + 1 < q1) fetch(q + 1);
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    if (at[u] < 0xfffe) buf[at[u]] += v[u];
+                    else if (at[u] == 0xffff) {   // column not ACTIVE: the Dirichlet lift of a CONSTRAINED DoF, nothing for an inactive one
+                        const int j = lane + 32 * u;
+                        const size_t k = (size_t)p.ed[e * p.nt + j / p.ds] * p.ds + (j % p.ds);
+                        if (p.status[k] == ISL_CONSTRAINED) lift += (p.incremental ? p.presc[k] - p.values[k] : p.presc[k]) * v[u];
+                    }
+                }
+                __syncwarp();
+            }
+        } else
         for (int64_t q = q0; q < q1; q++) {
             const int32_t pr = __ldg(p.pair + q);
             const int64_t e = pr / p.nr; const int i = pr - (int)e * p.nr;
