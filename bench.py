@@ -451,7 +451,7 @@ def bench_config(args, rank, world, local_rank, cores):
     # the scatter: FP64 atomic adds per second against the measured rate of the same access pattern (the generic kernels
     # add three neighbouring entries per node pair for vector fields, single entries for scalar fields)
     atomics = None
-    if cfg != "C1":
+    if cfg != "C1" and w.atomics_per_element() > 0:
         n_at = w.atomics_per_element()
         pattern = 1 if max(f["ds"] for f in w.fields) > 1 else 2
         red_peak = eng.measure_red_peak(pattern)

@@ -948,6 +948,7 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     std::map<int, std::unique_ptr<GatherSet>> gathersets;   // per field: tables of the atomic-free hyperelastic path
     int hypel_gather = 1;      // ISL_HYPEL_GATHER
+    int hypel_occ3 = 1;        // ISL_HYPEL_OCC3: Q2 variant of the tile kernel compiled for three CTAs per SM
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
     std::map<std::pair<int, int>, std::unique_ptr<BlockMap>> blockmaps;   // per (test, trial) pair
     int block_slots = 1;       // ISL_BLOCK_SLOTS: 0 per-entry slot maps only, 1 node-block maps in the generic kernels, 2 also in the tile kernel
@@ -1379,6 +1380,7 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
     const size_t smem = per * EB;
     auto launch = [&](auto kernel) {
         ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         const int64_t nbatch = (h->n_owned + EB - 1) / EB;
         if (nbatch == 0) return;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
@@ -1386,7 +1388,10 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
         h->launches++;
         ISL_CUDA(cudaGetLastError());
     };
-    if (MC == 5) launch(k_tangent_hypel_sym<5>); else launch(k_tangent_hypel_sym<6>);
+    // Q2 hexahedra: one element per CTA of 96 threads; compiled for three CTAs per SM (224 registers instead of 234: nine
+    // warps per SM instead of six -- the kernel is bound by dependent-issue latency, profiles/r2/r2_p_*.md)
+    if (MC == 6 && best_nt <= 96 && h->hypel_occ3) launch(k_tangent_hypel_sym<6, 96, 3>);
+    else if (MC == 5) launch(k_tangent_hypel_sym<5>); else launch(k_tangent_hypel_sym<6>);
 }
 
 template <class K>
@@ -2251,6 +2256,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_GATHER")) h->hypel_gather = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_SLOT64")) h->force_slot64 = atoi(m) != 0;

@@ -133,8 +133,8 @@ struct HypelSymLayout {
     }
 };
 
-template <int MC>
-__global__ void __launch_bounds__(256, 1) k_tangent_hypel_sym(const AsmParams p, int ntiles) {
+template <int MC, int NTH = 256, int MINB = 1>
+__global__ void __launch_bounds__(NTH, MINB) k_tangent_hypel_sym(const AsmParams p, int ntiles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ unsigned char sTileN[160], sTileM0[160];
     const int tid = threadIdx.x, nth = blockDim.x;

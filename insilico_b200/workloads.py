@@ -155,7 +155,9 @@ class Workload:
             if op[0] != "matrix":
                 total += ft["ndpe"] * ft["ds"]
             elif op[1] in (E.K_HYPEL_STVENANT, E.K_HYPEL_NEOHOOKE):
-                total += (ft["ndpe"] * ft["ds"]) * (fc["ndpe"] * fc["ds"])
+                # 3-D vector fields take the atomic-free path (element matrices to memory, rows gathered): no atomics
+                if not (self.dim == 3 and ft["ds"] == 3 and op[4] == op[5]):
+                    total += (ft["ndpe"] * ft["ds"]) * (fc["ndpe"] * fc["ds"])
             elif op[1] in (E.K_PRESSURE_GRADIENT, E.K_VELOCITY_DIVERGENCE):
                 total += ft["ndpe"] * fc["ndpe"] * self.dim
             else:
