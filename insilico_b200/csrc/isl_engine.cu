@@ -948,6 +948,7 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     std::map<int, std::unique_ptr<GatherSet>> gathersets;   // per field: tables of the atomic-free hyperelastic path
     int hypel_gather = 1;      // ISL_HYPEL_GATHER
+    int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
     int hypel_occ3 = 1;        // ISL_HYPEL_OCC3: Q2 variant of the tile kernel compiled for three CTAs per SM
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
     std::map<std::pair<int, int>, std::unique_ptr<BlockMap>> blockmaps;   // per (test, trial) pair
@@ -1365,17 +1366,31 @@ void launch_gather_rows(isl_engine* h, GatherSet* gs, const AsmParams& a, const 
 
 void launch_hypel_sym(isl_engine* h, AsmParams& p) {
     const int nt = p.nt;
-    const int MC = (nt <= 10) ? 5 : 6;
+    // test nodes per register tile.  Few-node elements (P2 tetrahedra) get small tiles = more tiles = more threads per
+    // element: their occupancy is bound by the shared memory per element, not by registers (ISL_HYPEL_MC overrides)
+    int MC = (nt <= 10) ? h->hypel_mc_small : 6;
+    if (MC != 2 && MC != 3 && MC != 5 && MC != 6) MC = (nt <= 10) ? 5 : 6;
     int ntiles = 0;
     for (int N = 0; N < nt; N++) ntiles += N / MC + 1;
     ISL_REQUIRE(ntiles <= 160, "element too large for the tile table");
     const HypelSymLayout L(p.npe, p.nq, nt);
     const size_t per = (size_t)L.per_elem * sizeof(double);
     ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
-    // one tile per thread: EB elements with EB * ntiles <= 256 threads, within ~100 KB of shared memory; CTA size = the
-    // multiple of 32 that holds the tiles
-    int EB = (int)std::max<size_t>(1, std::min<size_t>((size_t)(100 * 1024) / per, (size_t)(256 / ntiles)));
-    const int best_nt = std::min(256, ((EB * ntiles + 31) / 32) * 32);
+    // one tile per thread: EB elements with EB * ntiles threads, CTA size = the multiple of 32 that holds the tiles.  The
+    // variants with few registers (MC 2, 3 and the Q2 variant) take CTAs of at most 128 threads and the EB that keeps the
+    // most tiles resident per SM (shared memory 220 KB, 64 K registers, 168 / 128 registers per thread)
+    const bool small = (MC <= 3) || (MC == 6 && h->hypel_occ3 && ntiles <= 96);
+    const int max_threads = small ? (MC == 6 ? 96 : 128) : 256;
+    int EB = 1, best_score = -1;
+    for (int eb = 1; eb * ntiles <= max_threads; eb++) {
+        if ((size_t)eb * per > (small ? 110u : 100u) * 1024) break;
+        const int threads = ((eb * ntiles + 31) / 32) * 32;
+        const int by_smem = (int)((size_t)(220 * 1024) / ((size_t)eb * per + 1024));
+        const int by_regs = 65536 / ((small ? (MC == 6 ? 168 : 128) : 232) * threads);
+        const int score = std::min(std::min(by_smem, by_regs), 16) * eb * ntiles;
+        if (score > best_score || (score == best_score && !small)) { best_score = score; EB = eb; }
+    }
+    const int best_nt = std::min(max_threads, ((EB * ntiles + 31) / 32) * 32);
     p.EB = EB;
     const size_t smem = per * EB;
     auto launch = [&](auto kernel) {
@@ -1383,15 +1398,19 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
         ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         const int64_t nbatch = (h->n_owned + EB - 1) / EB;
         if (nbatch == 0) return;
-        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 8));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nbatch, (int64_t)h->n_sm * 16));
         kernel<<<grid, best_nt, smem, h->stream>>>(p, ntiles);
         h->launches++;
         ISL_CUDA(cudaGetLastError());
     };
-    // Q2 hexahedra: one element per CTA of 96 threads; compiled for three CTAs per SM (224 registers instead of 234: nine
-    // warps per SM instead of six -- the kernel is bound by dependent-issue latency, profiles/r2/r2_p_*.md)
-    if (MC == 6 && best_nt <= 96 && h->hypel_occ3) launch(k_tangent_hypel_sym<6, 96, 3>);
-    else if (MC == 5) launch(k_tangent_hypel_sym<5>); else launch(k_tangent_hypel_sym<6>);
+    if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl] hyperelastic tile kernel: MC %d, %d tiles per element, %d elements per CTA of %d threads, %.1f KB shared memory\n", MC, ntiles, EB, best_nt, smem / 1024.0);
+    // Q2 hexahedra: one element per CTA of 96 threads, compiled for 168 registers: four CTAs = twelve warps per SM instead of
+    // six (the kernel is bound by dependent-issue latency: 40.4 -> 33.5 ms at 64^3, profiles/r2/session36.log)
+    if (MC == 6 && small) launch(k_tangent_hypel_sym<6, 96, 3>);
+    else if (MC == 2) launch(k_tangent_hypel_sym<2, 128, 4>);
+    else if (MC == 3) launch(k_tangent_hypel_sym<3, 128, 4>);
+    else if (MC == 5) launch(k_tangent_hypel_sym<5>);
+    else launch(k_tangent_hypel_sym<6>);
 }
 
 template <class K>
@@ -2256,6 +2275,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_GATHER")) h->hypel_gather = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_HYPEL_MC")) h->hypel_mc_small = atoi(m);
         if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
         if (const char* m = getenv("ISL_FROMK_TILE_ORDER")) h->fromk_tile_order = atoi(m) ? 1 : 0;
