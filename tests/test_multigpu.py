@@ -41,7 +41,7 @@ def test_two_ranks_on_one_gpu_slab_assembly(mode):
     assert out.returncode == 0 and "DIST_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
-@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 3), ("laplace_q1_hex", 8), ("stokes_slab", 4)])
+@pytest.mark.parametrize("name,n", [("stokes_p2p1_tet", 3), ("laplace_q1_hex", 8), ("stokes_slab", 4), ("stvenant_q1_hex", 4)])
 def test_two_ranks_on_one_gpu_general_partition(name, n):
     out = _torchrun("dist_check_general.py", [name, n], 29542, ONE_GPU)
     assert out.returncode == 0 and "DIST_CHECK_GENERAL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
