@@ -67,7 +67,8 @@ int isl_synchronize(isl_handle h);
 int isl_flush(isl_handle h);
 /* kernel-selection knobs that can change between launches without new preprocessing (tuning sweeps; the same knobs
  * are read from ISL_* environment variables when the engine is created): "q1_rows", "rows_threads", "rows_ss",
- * "affine_kernel", "aff_split", "aff_threads", "tangent_tiled", "defer"                                        */
+ * "affine_kernel", "aff_split", "aff_threads", "tangent_tiled", "defer", "gen_gather", "hypel_gather" (1: element
+ * matrices to memory + CSR rows gathered without atomics, 0: atomic scatter through the slot maps)           */
 int isl_engine_set_option(isl_handle h, const char* name, double value);
 /* CUDA stream the engine launches on (cudaStream_t as void*), for event timing by the caller */
 void* isl_engine_stream(isl_handle h);

@@ -31,7 +31,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <ostream>
 #include <vector>
 
@@ -67,11 +69,28 @@ namespace b200_detail {
 
 inline void check(int rc) { VERIFY_MSG(rc == 0, std::string("B200 engine: ") + isl_last_error()); }
 
-inline isl_handle engine() {
-    static isl_handle h = NULL;
-    if (h == NULL) check(isl_engine_create(0, &h));
-    return h;
+//! The GPU the calling host thread works on (SURVEY 8(b) "one host thread or process drives 1-8 GPUs").  Like
+//! cudaSetDevice it is a per-thread selection: solvers constructed and assembly calls made while device d is selected run
+//! on the engine of device d, every device keeps its own engine and its own flattened copy of the binder behind it.  So
+//! one thread can loop over the GPUs of a node (selectDevice(d); assemble the d-th element block; ...) and an OpenMP
+//! team can drive one GPU per thread.  Default: ISL_B200_DEVICE, else the local rank a launcher exported (torchrun
+//! LOCAL_RANK, Open MPI, MVAPICH, Slurm), else 0 -- one process per GPU needs no code at all.
+inline int defaultDevice() {
+    static const char* const names[] = {"ISL_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID"};
+    for (std::size_t i = 0; i < sizeof(names) / sizeof(names[0]); i++) {
+        const char* v = std::getenv(names[i]);
+        if (v != NULL && *v != 0) return std::atoi(v);
+    }
+    return 0;
 }
+inline int& currentDevice() {
+    static thread_local int d = defaultDevice();
+    return d;
+}
+struct PerDevice;
+inline PerDevice& perDevice();   // the engine and the binder state of the selected device (defined below BinderState)
+
+inline isl_handle engine();
 
 template <typename T>
 bool assignIfChanged(std::vector<T>& cache, const std::vector<T>& fresh) {
@@ -114,10 +133,35 @@ struct BinderState {
     FieldState field[5];
 };
 
-inline BinderState& state() {
-    static BinderState s;
-    return s;
+struct PerDevice {
+    isl_handle handle = NULL;
+    BinderState binder;
+    unsigned long scannedForSolver = 0, currentSolver = 0, latestSolver = 0;   // the engine of a device holds ONE system at a time
+};
+inline PerDevice& perDevice() {
+    static std::map<int, PerDevice> all;   // node-based container: references stay valid while other devices are added
+#ifdef _OPENMP
+    PerDevice* p;
+#pragma omp critical(isl_b200_per_device)
+    p = &all[currentDevice()];
+    return *p;
+#else
+    return all[currentDevice()];
+#endif
 }
+inline isl_handle engine() {
+    PerDevice& d = perDevice();
+    if (d.handle == NULL) {
+        // ISL_B200_PHYSICAL_DEVICES=n folds the selected indices onto n GPUs (tests of the multi-device logic on a box
+        // with fewer GPUs: several engines then share one GPU)
+        int physical = currentDevice();
+        const char* fold = std::getenv("ISL_B200_PHYSICAL_DEVICES");
+        if (fold != NULL && std::atoi(fold) > 0) physical %= std::atoi(fold);
+        check(isl_engine_create(physical, &d.handle));
+    }
+    return d.handle;
+}
+inline BinderState& state() { return perDevice().binder; }
 
 // ---- flatten one field of the binder (slot N = 1..5 of FieldBinder::ElementPtrTuple) -------------------------------
 template <typename ELEMENTPTR>
@@ -258,14 +302,8 @@ inline bool& rescanEveryCall() {
     static bool flag = false;
     return flag;
 }
-inline unsigned long& scannedForSolver() {
-    static unsigned long id = 0;
-    return id;
-}
-inline unsigned long& currentSolver() {
-    static unsigned long id = 0;
-    return id;
-}
+inline unsigned long& scannedForSolver() { return perDevice().scannedForSolver; }
+inline unsigned long& currentSolver() { return perDevice().currentSolver; }
 inline unsigned long& fullScans() {   // statistics for tests
     static unsigned long n = 0;
     return n;
@@ -693,14 +731,30 @@ public:
     }
 
     //! Constructor with the size N of matrix and vector (Eigen3.hpp:71-77)
-    B200(const std::size_t size) : size_(size), solved_(false), id_(++latest_()) {
+    B200(const std::size_t size) : size_(size), solved_(false), id_(nextId_()), device_(b200_detail::currentDevice()) {
+        b200_detail::perDevice().latestSolver = id_;
         b200_detail::currentSolver() = id_;
         b200_detail::check(isl_system_create(b200_detail::engine(), static_cast<int64_t>(size)));
     }
 
-    //! The engine holds ONE system at a time: using a solver after a newer one was constructed is an error
+    //! Select the GPU for the solvers constructed and the assembly calls made by THIS host thread from now on (see
+    //! b200_detail::currentDevice; the reference's only parallel construct, the OpenMP element loop of
+    //! base/auxi/parallel.hpp:25-60, becomes one element block per GPU: selectDevice(d), bind block d, assemble)
+    static void selectDevice(const int device) {
+        VERIFY_MSG(device >= 0, "base::solver::B200::selectDevice: negative device index");
+        b200_detail::currentDevice() = device;
+    }
+    static int selectedDevice() { return b200_detail::currentDevice(); }
+    //! the device this solver's system lives on
+    int device() const { return device_; }
+
+    //! The engine of a device holds ONE system at a time: using a solver after a newer one was constructed on its
+    //! device, or while another device is selected, is an error
     void verifyCurrent() const {
-        VERIFY_MSG(id_ == latest_(), "base::solver::B200: a newer solver object exists; the engine holds one system at a time");
+        VERIFY_MSG(device_ == b200_detail::currentDevice(),
+                   "base::solver::B200: this solver lives on another device than the one selected (B200::selectDevice)");
+        VERIFY_MSG(id_ == b200_detail::perDevice().latestSolver,
+                   "base::solver::B200: a newer solver object exists; the engine holds one system at a time");
     }
 
     //! Insert numbers to matrix storage (Eigen3.hpp:81-108): host-side odd contributions
@@ -890,15 +944,21 @@ private:
         return it;
     }
 
-    static unsigned long& latest_() {
+    static unsigned long nextId_() {
         static unsigned long n = 0;
-        return n;
+        unsigned long id;
+#ifdef _OPENMP
+#pragma omp critical(isl_b200_solver_id)
+#endif
+        id = ++n;
+        return id;
     }
 
     std::size_t size_, nnz_ = 0;
     mutable std::vector<double> x_;  //!< host copy of rhs / the solution after a solve
     bool solved_;
     unsigned long id_;
+    int device_;
 };
 
 }  // namespace solver

@@ -109,7 +109,8 @@ struct AsmParams {
     const int32_t* slot; const int64_t* slot64;   // element -> CSR position maps: 32-bit, or 64-bit when nnz >= 2^31 (exactly one is set)
     // node-block position map of the hyperelastic tile kernel (one base position per pair of nodes instead of ds*ds slots)
     const int64_t* bbase; const int32_t* blen;
-    double* kout;   // hyperelastic tile kernel: local matrices go to kout[e][nr][nr] instead of the CSR (isl_gather.cuh)
+    double* kout;   // hyperelastic tile kernel: local matrices go to kout[e][nr][nr] instead of the CSR (isl_gather.cuh);
+                    // k_tangent: kout[e][nt][nc] (one scalar per node pair) or kout[e][nt dst][nc dsc] (Stokes coupling blocks)
     double* val; double* rhs;
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
@@ -360,6 +361,17 @@ __device__ __forceinline__ void scatter_block_entry(const AsmParams& p, int64_t 
     scatter_entry(p, e, M * p.dst + i, N * p.dsc + k, nr, ncl, v);
 }
 
+// entry K[M][N] of an integrand that repeats one scalar on every DoF component (Laplace, Mass, Convection)
+__device__ __forceinline__ void emit_node_pair(const AsmParams& p, int64_t e, int M, int N, int nr, int ncl, double v) {
+    if (p.kout) { p.kout[((size_t)e * p.nt + M) * p.nc + N] = v; return; }   // atomic-free path: rows gathered by k_gen_gather_rows
+    for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, e, M, c, N, c, nr, ncl, v);
+}
+// entry (M,i; N,k) of a coupling block
+__device__ __forceinline__ void emit_entry(const AsmParams& p, int64_t e, int M, int i, int N, int k, int nr, int ncl, double v) {
+    if (p.kout) { p.kout[((size_t)e * nr + M * p.dst + i) * ncl + N * p.dsc + k] = v; return; }
+    scatter_block_entry(p, e, M, i, N, k, nr, ncl, v);
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
     extern __shared__ double smem[];
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     const double kap = p.kq ? p.kq[(size_t)p.eid(base + eb) * p.nq + q] : p.p0;
                     acc += dot * (kap * s.sDet[eq] * p.w[q]);
                 }
-                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
+                emit_node_pair(p, p.eid(base + eb), M, N, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_MASS) {
             // base/kernel/Mass.hpp:88-138: (factor detJ w) phi_M psi_N on every DoF component
@@ -428,7 +440,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                 double acc = 0.;
                 for (int q = 0; q < p.nq; q++)
                     acc += (p.p0 * s.sDet[eb * p.nq + q] * p.w[q]) * p.Nt[q * p.nt + M] * p.Nc[q * p.nc + N];
-                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
+                emit_node_pair(p, p.eid(base + eb), M, N, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_CONVECTION) {
             // fluid/Convection.hpp:88-166 (Picard form): phi_M (uAdv . grad phi_N + 0.5 div(u) phi_N) rho detJ w on every
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                     for (int k = 0; k < p.dst; k++) adv += qd[k] * gN[k];
                     acc += p.Nt[q * p.nt + M] * (adv + 0.5 * qd[3] * p.Nc[q * p.nc + N]) * p.p0 * s.sDet[eq] * p.w[q];
                 }
-                for (int c = 0; c < p.dsc; c++) scatter_block_entry(p, p.eid(base + eb), M, c, N, c, nr, ncl, acc);
+                emit_node_pair(p, p.eid(base + eb), M, N, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
             // B(M d + i, N) = -detJ w g_M[i] psi_N
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGt[((size_t)eq * p.nt + M) * DIM + d] * p.Nc[q * p.nc + N];
                     }
-                scatter_block_entry(p, p.eid(base + eb), M, d, N, 0, nr, ncl, acc);
+                emit_entry(p, p.eid(base + eb), M, d, N, 0, nr, ncl, acc);
             }
         } else if (p.kernel_id == ISL_K_VELOCITY_DIVERGENCE) {
             // transpose of the pressure-gradient block on the transposed tuple, optional sign change
@@ -483,7 +495,7 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         const int eq = eb * p.nq + q;
                         acc += -s.sDet[eq] * p.w[q] * s.sGc[((size_t)eq * p.nc + N) * DIM + d] * p.Nt[q * p.nt + Mp];
                     }
-                scatter_block_entry(p, p.eid(base + eb), Mp, 0, N, d, nr, ncl, sgn * acc);
+                emit_entry(p, p.eid(base + eb), Mp, 0, N, d, nr, ncl, sgn * acc);
             }
         }
         __syncthreads();
@@ -948,6 +960,12 @@ struct isl_engine {
     std::map<std::pair<int, int>, std::unique_ptr<SlotMap>> slotmaps;
     std::map<int, std::unique_ptr<GatherSet>> gathersets;   // per field: tables of the atomic-free hyperelastic path
     int hypel_gather = 1;      // ISL_HYPEL_GATHER
+    // atomic-free path of the generic kernels (isl_gather.cuh, second half): (element, row) pairs per test field, column
+    // positions per (test, trial, compact), one scratch buffer for the element matrices of the operation in flight
+    std::map<int, std::unique_ptr<RowPairs>> rowpairs;
+    std::map<std::array<int, 3>, std::unique_ptr<GenGatherSet>> gengathers;
+    DevBuf<double> gen_kbuf;
+    int gen_gather = 0;        // ISL_GEN_GATHER
     int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
     int hypel_occ3 = 1;        // ISL_HYPEL_OCC3: Q2 variant of the tile kernel compiled for three CTAs per SM
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
@@ -1052,7 +1070,7 @@ void require_live_system(isl_engine* h) {
 
 void invalidate_pattern(isl_engine* h) {
     h->pattern_pairs.clear();
-    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
+    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->rowpairs.clear(); h->gengathers.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
     h->nnz = 0;
@@ -1076,7 +1094,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     // assembly call): then the old arrays are released first, their memory is needed for the keys of large systems
     const bool carry = h->nnz > 0 && h->val.p && !h->val_is_zero;
     if (carry) materialize_zero(h);
-    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->nnz = 0; h->val_zero_pending = false; }
+    else { h->val.release(); h->col.release(); h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->rowpairs.clear(); h->gengathers.clear(); h->nnz = 0; h->val_zero_pending = false; }
     int64_t total = 0;
     for (auto& pr : pairs) {
         FieldDev& t = h->fields[pr.first]; FieldDev& c = h->fields[pr.second];
@@ -1164,7 +1182,7 @@ void build_pattern(isl_engine* h, const std::set<std::pair<int, int>>& pairs) {
     h->rowptr.swap(rowptr); h->col.swap(col); h->val.swap(val);
     h->nnz = nnz;
     h->pattern_pairs = pairs;
-    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
+    h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->rowpairs.clear(); h->gengathers.clear();
     h->patchsets.clear();
     h->fromk_sets.clear();
 }
@@ -1362,6 +1380,111 @@ void launch_gather_rows(isl_engine* h, GatherSet* gs, const AsmParams& a, const 
     k_gather_rows<W><<<grid, W * 32, smem, h->stream>>>(g);
     h->launches++;
     ISL_CUDA(cudaGetLastError());
+}
+
+// ---- atomic-free path of the generic kernels (isl_gather.cuh, second half) ----
+RowPairs* get_rowpairs(isl_engine* h, int t) {
+    auto it = h->rowpairs.find(t);
+    if (it != h->rowpairs.end()) return it->second->ok ? it->second.get() : nullptr;
+    auto rp = std::make_unique<RowPairs>();
+    FieldDev& f = h->fields[t];
+    build_elem_eqn(h, f);
+    const int nr = f.ndpe * f.ds;
+    const int64_t P = h->n_owned * nr, n_rows = h->n_eqn;
+    rp->nr = nr; rp->n_rows = n_rows;
+    if (P > 0 && P < ((int64_t)1 << 31) && n_rows > 0) {
+        DevBuf<int32_t> key, key2, idx;
+        key.alloc(P); key2.alloc(P); idx.alloc(P); rp->pair.alloc(P);
+        ISL_LAUNCH(h, k_gs_keys, h->grid_for(P, 256), 256, 0, f.elem_eqn.p, P, key.p, idx.p);
+        size_t tb = 0;
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, idx.p, rp->pair.p, P, 0, 31, h->stream));
+        DevBuf<char> tmp; tmp.alloc(tb);
+        ISL_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, idx.p, rp->pair.p, P, 0, 31, h->stream));
+        h->launches += 4;
+        rp->row_start.alloc(n_rows + 1);
+        ISL_LAUNCH(h, k_gs_row_start, h->grid_for(n_rows + 1, 256), 256, 0, key2.p, P, n_rows, rp->row_start.p);
+        int64_t n_pairs = 0;
+        ISL_CUDA(cudaMemcpyAsync(&n_pairs, rp->row_start.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        rp->n_pairs = n_pairs;
+        rp->ok = true;
+    }
+    RowPairs* out = rp->ok ? rp.get() : nullptr;
+    h->rowpairs[t] = std::move(rp);
+    return out;
+}
+
+// integrands whose local matrix repeats one scalar per node pair on every DoF component
+bool gen_gather_compact(int kid) { return kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE || kid == ISL_K_MASS || kid == ISL_K_CONVECTION; }
+
+GenGatherSet* get_gengather(isl_engine* h, int t, int c, int compact) {
+    FieldDev& ft = h->fields[t]; FieldDev& fc = h->fields[c];
+    if (ft.has_masters || fc.has_masters) return nullptr;
+    if (compact && ft.ds != fc.ds) return nullptr;
+    const std::array<int, 3> key = {t, c, compact};
+    auto it = h->gengathers.find(key);
+    if (it != h->gengathers.end()) return it->second->ok ? it->second.get() : nullptr;
+    auto gs = std::make_unique<GenGatherSet>();
+    gs->compact = compact;
+    gs->KR = compact ? ft.ndpe : ft.ndpe * ft.ds;
+    gs->KC = compact ? fc.ndpe : fc.ndpe * fc.ds;
+    RowPairs* rp = gs->KC <= 96 ? get_rowpairs(h, t) : nullptr;
+    if (rp) {
+        build_elem_eqn(h, fc);
+        const int ncl = fc.ndpe * fc.ds;
+        DevBuf<int> st; st.alloc(2);
+        ISL_CUDA(cudaMemsetAsync(st.p, 0, 2 * sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_gs_max_len, std::min(h->grid_for(rp->n_rows, 256), h->n_sm * 8), 256, 0, h->rowptr.p, rp->n_rows, st.p + 1);
+        ISL_LAUNCH(h, k_gs_dup, h->grid_for(h->n_owned * ncl, 256), 256, 0, fc.elem_eqn.p, h->n_owned, ncl, st.p);
+        gs->pos.alloc((size_t)std::max<int64_t>(rp->n_pairs, 1) * gs->KC);
+        if (rp->n_pairs > 0)
+            ISL_LAUNCH(h, k_gg_pos, h->grid_for(rp->n_pairs * gs->KC, 256), 256, 0, rp->pair.p, rp->n_pairs, rp->nr, ft.ds, gs->KC, compact, fc.ds, ncl,
+                       ft.elem_eqn.p, fc.elem_eqn.p, h->rowptr.p, h->col.p, gs->pos.p, st.p);
+        int hst[2] = {0, 0};
+        ISL_CUDA(cudaMemcpyAsync(hst, st.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaStreamSynchronize(h->stream));
+        gs->max_len = hst[1];
+        gs->ok = hst[0] == 0 && (size_t)(gs->max_len + 1) * sizeof(double) * 4 <= 200 * 1024;   // the row buffers of one warp (up to four rows) must fit a CTA
+        if (getenv("ISL_VERBOSE"))
+            fprintf(stderr, "[isl] atomic-free generic path (%d,%d,%s): %s, %lld (element, row) pairs, %d x %d per element, longest row %d, positions %.2f GB\n",
+                    t, c, compact ? "one scalar per node pair" : "full block", gs->ok ? "ok" : "not eligible", (long long)rp->n_pairs, gs->KR, gs->KC,
+                    gs->max_len, (double)rp->n_pairs * gs->KC * 2 / 1e9);
+    }
+    GenGatherSet* out = gs->ok ? gs.get() : nullptr;
+    h->gengathers[key] = std::move(gs);
+    return out;
+}
+
+template <int G, int U>
+void launch_gen_gather_t(isl_engine* h, const GenGatherParams& g) {
+    // rows per CTA: as many sub-warps as fit 256 threads and 64 KB of row buffers
+    int threads = 256;
+    while (threads > 32 && (size_t)(threads / G) * g.buf_len * sizeof(double) > 64 * 1024) threads >>= 1;
+    if (threads < G) threads = G;
+    const int nsub = threads / G;
+    const size_t smem = (size_t)nsub * g.buf_len * sizeof(double);
+    ISL_CUDA(cudaFuncSetAttribute(k_gen_gather_rows<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    const int64_t nb = (g.n_rows + nsub - 1) / nsub;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)h->n_sm * 16));
+    k_gen_gather_rows<G, U><<<grid, threads, smem, h->stream>>>(g);
+    h->launches++;
+    ISL_CUDA(cudaGetLastError());
+}
+
+void launch_gen_gather(isl_engine* h, GenGatherSet* gs, const AsmParams& a, int t, int c, bool store) {
+    const FieldDev& ft = h->fields[t]; const FieldDev& fc = h->fields[c];
+    RowPairs* rp = get_rowpairs(h, t);
+    GenGatherParams g; std::memset(&g, 0, sizeof(g));
+    g.pair = rp->pair.p; g.row_start = rp->row_start.p; g.pos = gs->pos.p; g.Kbuf = h->gen_kbuf.p;
+    g.nr = rp->nr; g.dst = ft.ds; g.KR = gs->KR; g.KC = gs->KC; g.compact = gs->compact; g.nc = fc.ndpe; g.dsc = fc.ds; g.n_rows = rp->n_rows;
+    g.rowptr = h->rowptr.p; g.val = h->val.p; g.rhs = h->rhs.p;
+    g.ed_c = fc.elem_dof.p; g.st_c = fc.status.p; g.presc_c = fc.presc.p; g.val_c = fc.values.p; g.incremental = a.incremental;
+    g.store = store ? 1 : 0;
+    g.buf_len = (gs->max_len + 1) & ~1;
+    if (g.KC <= 8) launch_gen_gather_t<8, 1>(h, g);
+    else if (g.KC <= 16) launch_gen_gather_t<16, 1>(h, g);
+    else if (g.KC <= 32) launch_gen_gather_t<32, 1>(h, g);
+    else launch_gen_gather_t<32, 3>(h, g);
 }
 
 void launch_hypel_sym(isl_engine* h, AsmParams& p) {
@@ -2275,6 +2398,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_TANGENT_SYM")) h->tangent_sym = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_GATHER")) h->hypel_gather = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_GEN_GATHER")) h->gen_gather = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_MC")) h->hypel_mc_small = atoi(m);
         if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
@@ -2324,6 +2448,8 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else if (n == "tangent_sym") h->tangent_sym = v ? 1 : 0;
         else if (n == "elem_order") h->elem_order = v ? 1 : 0;
         else if (n == "defer") h->defer_launch = v ? 1 : 0;
+        else if (n == "gen_gather") h->gen_gather = v ? 1 : 0;
+        else if (n == "hypel_gather") h->hypel_gather = v ? 1 : 0;
         else throw IslError("unknown option '" + n + "'");
     });
 }
@@ -2414,7 +2540,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned; h->affine_state = -1;
         for (auto& f : h->fields) f.eorder.release();
-        h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear();
+        h->slotmaps.clear(); h->blockmaps.clear(); h->gathersets.clear(); h->rowpairs.clear(); h->gengathers.clear();
         h->patchsets.clear();
         h->fromk_sets.clear();
     });
@@ -2543,6 +2669,8 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
         ISL_CUDA(cudaSetDevice(h->device));
         ensure_pair(h, test_field, trial_field);
         if (qualifies_q1(h, test_field, trial_field) && h->q1_mode == 1 && q1_ready(h, test_field)) return;
+        // (atomic-free generic path: its tables are built at the first assembly call, the slot map only if a kernel asks for it)
+        if (h->gen_gather && !h->fields[test_field].has_masters && !h->fields[trial_field].has_masters) return;
         get_slotmap(h, test_field, trial_field);
     });
 }
@@ -2612,6 +2740,27 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
                 p.kout = gs->Kbuf.p;
                 launch_hypel_sym(h, p);
                 launch_gather_rows(h, gs, p, ft, store);
+                return;
+            }
+        }
+        const bool gen_kid = gen_gather_compact(kid) || kid == ISL_K_PRESSURE_GRADIENT || kid == ISL_K_VELOCITY_DIVERGENCE;
+        if (h->gen_gather && gen_kid) {
+            // atomic-free: k_tangent stores the element matrices, a sub-warp per CSR row gathers them (isl_gather.cuh)
+            if (GenGatherSet* gs = get_gengather(h, t, c, gen_gather_compact(kid) ? 1 : 0)) {
+                const bool store = h->val_is_zero;   // fresh system: every row is written completely, zeros where nothing contributes
+                if (store) h->val_zero_pending = false; else materialize_zero(h);
+                h->val_is_zero = false;
+                const size_t need = (size_t)h->n_owned * gs->KR * gs->KC;
+                if (h->gen_kbuf.n < need) h->gen_kbuf.alloc(need);   // (stream-ordered free: the previous gather has been queued before)
+                p.kernel_id = kid; p.incremental = incremental;
+                p.p0 = params ? params[0] : 0.;
+                p.need_gt = (kid != ISL_K_VELOCITY_DIVERGENCE && kid != ISL_K_MASS);
+                p.need_gc = (kid == ISL_K_VELOCITY_DIVERGENCE) || (kid != ISL_K_PRESSURE_GRADIENT && kid != ISL_K_MASS);
+                p.nqdata = (kid == ISL_K_CONVECTION ? 4 : 0);
+                bind_aux(h, p, kid, c, aux);
+                p.kout = h->gen_kbuf.p;
+                if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+                launch_gen_gather(h, gs, p, t, c, store);
                 return;
             }
         }

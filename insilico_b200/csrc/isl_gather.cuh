@@ -157,3 +157,115 @@ __global__ void __launch_bounds__(WARPS * 32) k_gather_rows(const GatherParams p
         __syncwarp();
     }
 }
+
+// =============================================================================
+// The same turn-around for the GENERIC kernels (k_tangent: Laplace with constant / sampled conductivity, vector Laplace,
+// Mass, Convection, PressureGradient, VelocityDivergence; config 5 = three of them on Taylor-Hood tetrahedra), where test
+// and trial field differ and the local matrix is small:
+//   * k_tangent stores its local matrix instead of scattering it: Kgen[e][KR][KC], with KR x KC = nt x nc for the
+//     integrands that repeat one scalar entry on every DoF component (entry (M,c; N,c) = K[M][N]: "compact", 100 doubles
+//     instead of 900 for the P2 velocity block) and (nt dst) x (nc dsc) for the two Stokes coupling blocks;
+//   * k_gen_gather_rows: a SUB-WARP of G = 8, 16 or 32 lanes per CSR row (KC is 4 .. 30 here; a whole warp per row would
+//     leave most lanes idle), the (element, local row) pairs of the TEST field listed once per field (RowPairs), the
+//     positions of the KC local columns of the TRIAL field inside the row per pair (uint16).  Sum order = element order
+//     of the caller, so the result is reproducible bit for bit (the atomic scatter is not).
+// Reference semantics: asmb/assembleMatrix.hpp:56-130, fluid/PressureGradient.hpp:76-112, VelocityDivergence.hpp:67-124.
+// =============================================================================
+struct RowPairs {                // per test field
+    bool ok = false;
+    int nr = 0; int64_t n_pairs = 0, n_rows = 0;
+    DevBuf<int32_t> pair;        // sorted position -> element * nr + local row
+    DevBuf<int64_t> row_start;   // [n_rows + 1] into pair
+};
+struct GenGatherSet {            // per (test field, trial field, compact)
+    bool ok = false;
+    int KR = 0, KC = 0, compact = 0, max_len = 0;
+    DevBuf<uint16_t> pos;        // [n_pairs][KC]
+};
+struct GenGatherParams {
+    const int32_t* pair; const int64_t* row_start; const uint16_t* pos; const double* Kbuf;
+    int nr, dst, KR, KC, compact, nc, dsc; int64_t n_rows;
+    const int64_t* rowptr; double* val; double* rhs;
+    const int32_t* ed_c; const uint8_t* st_c; const double* presc_c; const double* val_c; int incremental;
+    int store;                   // 1: the system holds nothing yet: every row is written completely (no memset needed)
+    int buf_len;                 // row buffer per sub-warp (doubles)
+};
+
+__global__ void k_gg_pos(const int32_t* pair, int64_t n_pairs, int nr, int dst, int KC, int compact, int dsc, int ncl,
+                         const int32_t* elem_eqn_t, const int32_t* elem_eqn_c, const int64_t* rowptr, const int32_t* col,
+                         uint16_t* pos, int* err) {
+    const int64_t n = n_pairs * KC;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = t / KC; const int j = (int)(t - q * KC);
+        const int32_t pr = pair[q];
+        const int64_t e = pr / nr; const int i = pr - (int)e * nr;
+        const int jc = compact ? j * dsc + (i % dst) : j;
+        const int32_t r = elem_eqn_t[pr], c = elem_eqn_c[e * ncl + jc];
+        uint16_t v = 0xffff;
+        if (c >= 0) {
+            const int64_t at = isl_find_in_row(rowptr, col, r, c);
+            if (at < 0 || at - rowptr[r] >= 0xfffe) err[0] = 1; else v = (uint16_t)(at - rowptr[r]);
+        }
+        pos[t] = v;
+    }
+}
+
+template <int G, int U>
+__global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p) {
+    extern __shared__ double gsm[];
+    const int sub = threadIdx.x / G, lane = threadIdx.x % G, nsub = blockDim.x / G;
+    const unsigned mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+    double* buf = gsm + (size_t)sub * p.buf_len;
+    for (int64_t r = (int64_t)blockIdx.x * nsub + sub; r < p.n_rows; r += (int64_t)gridDim.x * nsub) {
+        const int64_t s = p.rowptr[r];
+        const int len = (int)(p.rowptr[r + 1] - s);
+        const int64_t q0 = p.row_start[r], q1 = p.row_start[r + 1];
+        if (q0 == q1 && !p.store) continue;
+        for (int k = lane; k < len; k += G) buf[k] = 0.;
+        double lift = 0.;
+        __syncwarp(mask);
+        // the loads of pair q + 1 are in flight while pair q is added into the row buffer
+        uint16_t at_n[U]; double v_n[U]; int32_t pr_n = 0;
+        auto fetch = [&](int64_t q) {
+            pr_n = __ldg(p.pair + q);
+            const int64_t e = pr_n / p.nr;
+            const int i = pr_n - (int)e * p.nr;
+            const double* krow = p.Kbuf + ((size_t)e * p.KR + (p.compact ? i / p.dst : i)) * p.KC;
+            const uint16_t* pq = p.pos + (size_t)q * p.KC;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = lane + G * u;
+                const bool in = j < p.KC;
+                at_n[u] = in ? __ldg(pq + j) : (uint16_t)0xfffe;
+                v_n[u] = in ? __ldg(krow + j) : 0.;
+            }
+        };
+        if (q0 < q1) fetch(q0);
+        for (int64_t q = q0; q < q1; q++) {
+            uint16_t at[U]; double v[U]; const int32_t pr = pr_n;
+#pragma unroll
+            for (int u = 0; u < U; u++) { at[u] = at_n[u]; v[u] = v_n[u]; }
+            if (q + 1 < q1) fetch(q + 1);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (at[u] < 0xfffe) buf[at[u]] += v[u];
+                else if (at[u] == 0xffff && v[u] != 0.) {   // column not ACTIVE: Dirichlet lift of a CONSTRAINED DoF, nothing for an inactive one
+                    const int64_t e = pr / p.nr; const int i = pr - (int)e * p.nr;
+                    const int j = lane + G * u;
+                    const int N = p.compact ? j : j / p.dsc, cj = p.compact ? i % p.dst : j % p.dsc;
+                    const size_t k = (size_t)p.ed_c[e * p.nc + N] * p.dsc + cj;
+                    if (p.st_c[k] == ISL_CONSTRAINED) lift += (p.incremental ? p.presc_c[k] - p.val_c[k] : p.presc_c[k]) * v[u];
+                }
+            }
+            __syncwarp(mask);
+        }
+        if (p.store) { for (int k = lane; k < len; k += G) p.val[s + k] = buf[k]; }
+        else {   // untouched entries (other blocks of the row, other components) are neither read nor written
+            for (int k = lane; k < len; k += G) { const double b = buf[k]; if (b != 0.) p.val[s + k] += b; }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) lift += __shfl_xor_sync(mask, lift, o);
+        if (lane == 0 && lift != 0.) atomicAdd(p.rhs + r, -lift);
+        __syncwarp(mask);
+    }
+}

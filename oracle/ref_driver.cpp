@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -453,32 +454,63 @@ int runStokes(const Job& job) {
     Binder binder(mesh, velocity, pressure);
     Quadrature quadrature;
     double best = 1e300;
+    auto registerAll = [&](Solver& solver) {
+        if (!job.registerFields) return;
+        solver.template registerFields<UU>(binder);
+        solver.template registerFields<UP>(binder);
+        solver.template registerFields<PU>(binder);
+    };
+    auto applyOp = [&](const Op& op, Solver& solver) {
+        const bool matrix = (op.what == "matrix"), incr = (op.incremental != 0);
+        if (op.kernel == "vector_laplace") {
+            fluid::VectorLaplace<typename UU::Tuple> k(op.p[0]);
+            if (matrix) base::asmb::stiffnessMatrixComputation<UU>(quadrature, solver, binder, k, incr);
+            else base::asmb::computeResidualForces<UU>(quadrature, solver, binder, k);
+        } else if (op.kernel == "pressure_gradient") {
+            fluid::PressureGradient<typename UP::Tuple> k;
+            if (matrix) base::asmb::stiffnessMatrixComputation<UP>(quadrature, solver, binder, k, incr);
+            else base::asmb::computeResidualForces<UP>(quadrature, solver, binder, k);
+        } else if (op.kernel == "velocity_divergence") {
+            fluid::VelocityDivergence<typename PU::Tuple> k(!op.p.empty() && op.p[0] != 0.0);
+            if (matrix) base::asmb::stiffnessMatrixComputation<PU>(quadrature, solver, binder, k, incr);
+            else base::asmb::computeResidualForces<PU>(quadrature, solver, binder, k);
+        } else {
+            VERIFY_MSG(false, "unknown kernel " + op.kernel);
+        }
+    };
+#ifdef INSILICO_B200_REFERENCE_HPP
+    // B200 binding only (ISL_DRIVER_DEVICES=2): ONE host thread drives two devices, the calls of two solvers interleaved
+    // call by call (base::solver::B200::selectDevice).  Both systems are dumped: <out> and <out>.dev1
+    if (const char* nd = std::getenv("ISL_DRIVER_DEVICES")) {
+        if (std::atoi(nd) == 2) {
+            Solver::selectDevice(0);
+            Solver first(nU + nP);
+            registerAll(first);
+            Solver::selectDevice(1);
+            Solver second(nU + nP);
+            registerAll(second);
+            for (const Op& op : job.ops) {
+                Solver::selectDevice(0);
+                applyOp(op, first);
+                Solver::selectDevice(1);
+                applyOp(op, second);
+            }
+            Solver::selectDevice(0);
+            first.finishAssembly();
+            if (job.dump == 1) dumpSystem(first, job.out);
+            Solver::selectDevice(1);
+            second.finishAssembly();
+            if (job.dump == 1) dumpSystem(second, job.out + ".dev1");
+            std::printf("two devices, one host thread: solvers on devices %d and %d\n", first.device(), second.device());
+            return 0;
+        }
+    }
+#endif
     for (int rep = 0; rep < job.repeat; rep++) {
         Solver solver(nU + nP);
-        if (job.registerFields) {
-            solver.template registerFields<UU>(binder);
-            solver.template registerFields<UP>(binder);
-            solver.template registerFields<PU>(binder);
-        }
+        registerAll(solver);
         const double t1 = now();
-        for (const Op& op : job.ops) {
-            const bool matrix = (op.what == "matrix"), incr = (op.incremental != 0);
-            if (op.kernel == "vector_laplace") {
-                fluid::VectorLaplace<typename UU::Tuple> k(op.p[0]);
-                if (matrix) base::asmb::stiffnessMatrixComputation<UU>(quadrature, solver, binder, k, incr);
-                else base::asmb::computeResidualForces<UU>(quadrature, solver, binder, k);
-            } else if (op.kernel == "pressure_gradient") {
-                fluid::PressureGradient<typename UP::Tuple> k;
-                if (matrix) base::asmb::stiffnessMatrixComputation<UP>(quadrature, solver, binder, k, incr);
-                else base::asmb::computeResidualForces<UP>(quadrature, solver, binder, k);
-            } else if (op.kernel == "velocity_divergence") {
-                fluid::VelocityDivergence<typename PU::Tuple> k(!op.p.empty() && op.p[0] != 0.0);
-                if (matrix) base::asmb::stiffnessMatrixComputation<PU>(quadrature, solver, binder, k, incr);
-                else base::asmb::computeResidualForces<PU>(quadrature, solver, binder, k);
-            } else {
-                VERIFY_MSG(false, "unknown kernel " + op.kernel);
-            }
-        }
+        for (const Op& op : job.ops) applyOp(op, solver);
         const double t2 = now();
         solver.finishAssembly();
         best = std::min(best, t2 - t1);

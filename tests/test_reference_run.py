@@ -209,6 +209,46 @@ def _driver_on_binding(path, exe, tmp_path):
     return res
 
 
+def _two_devices_one_thread(exe, tmp_path, extra_env):
+    """SURVEY 8(b) threading row: ONE host thread drives two devices through the binding (B200::selectDevice), the
+    assembly calls of two solvers interleaved call by call; both finished systems equal the reference run's"""
+    from tools import make_ref_goldens as G
+    path = [p for p in GOLD if os.path.basename(p).startswith("stokes_p2p1_tet")][0]
+    g = np.load(path, allow_pickle=False)
+    spec = [c for c in G.CASES if c[0] == os.path.basename(path)[:-4]][0]
+    case = flows.build_case(spec[1], spec[3], spec[4], spec[5])
+    old, old_env = G.DRIVER, dict(os.environ)
+    G.DRIVER = os.path.join(APPS_B200, exe)
+    os.environ.update(dict(ISL_DRIVER_DEVICES="2", **extra_env))
+    try:
+        r0 = G.run_reference(case, spec[2], spec[6], str(tmp_path))
+    finally:
+        G.DRIVER = old
+        os.environ.clear()
+        os.environ.update(old_env)
+    assert "two devices, one host thread: solvers on devices 0 and 1" in r0["log"]
+    out = os.path.join(str(tmp_path), "out")
+    for ext in (".lhs.txt", ".rhs.txt"):       # second device: same reader on the second dump
+        os.replace(out + ".dev1" + ext, out + ext)
+    r1 = G.read_system(out)
+    for r in (r0, r1):
+        res = flows.compare((g["rowptr"], g["col"], g["val"], g["rhs"]), (r["rowptr"], r["col"], r["val"], r["rhs"]))
+        assert res["pattern_equal"] and res["val_diff"] <= 1e-12 and res["rhs_diff"] <= 1e-12, res
+
+
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_one_host_thread_drives_two_devices_with_mock_abi(tmp_path):
+    _two_devices_one_thread("ref_driver_mock", tmp_path, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
+def test_one_host_thread_drives_two_devices_on_b200(tmp_path):
+    """two engines; on a box with one GPU both logical devices are folded onto it (ISL_B200_PHYSICAL_DEVICES)"""
+    import torch
+    _two_devices_one_thread("ref_driver", tmp_path, {"ISL_B200_PHYSICAL_DEVICES": str(max(1, min(2, torch.cuda.device_count())))})
+
+
 @pytest.mark.skipif(not os.path.isdir(APPS_B200), reason="oracle/_ref/apps_b200 not built (needs /root/reference)")
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_reference_api_on_binding_with_mock_abi(tmp_path, path):

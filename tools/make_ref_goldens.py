@@ -146,6 +146,12 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
         assert np.array_equal(d[:, 0], np.arange(len(d)))
         res["status%d" % i] = d[:, 1::2].astype(np.uint8)
         res["eqn%d" % i] = d[:, 2::2].astype(np.int64)
+    res.update(read_system(out))
+    return res
+
+
+def read_system(out):
+    """the finished system the driver dumped (debugLHS / debugRHS) as CSR"""
     lhs = np.loadtxt(out + ".lhs.txt", ndmin=2)
     rhs = np.loadtxt(out + ".rhs.txt", ndmin=2)
     n = len(rhs)
@@ -155,8 +161,7 @@ def run_reference(case, driver_type, register, workdir, repeat=1, dump=True):
     assert not np.any((r[1:] == r[:-1]) & (c[1:] == c[:-1])), "duplicates in the finished matrix"
     rowptr = np.zeros(n + 1, dtype=np.int64)
     np.add.at(rowptr, r + 1, 1)
-    res.update(rowptr=np.cumsum(rowptr), col=c.astype(np.int32), val=v, rhs=rhs[:, 1].copy())
-    return res
+    return dict(rowptr=np.cumsum(rowptr), col=c.astype(np.int32), val=v, rhs=rhs[:, 1].copy())
 
 
 def main():
