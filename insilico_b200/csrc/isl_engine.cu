@@ -114,6 +114,7 @@ struct AsmParams {
     double* val; double* rhs;
     int kernel_id; double p0, p1; int incremental; double factor;
     int EB; int need_gt, need_gc, nqdata;
+    int tile;   // k_tangent: register strips (one thread = one test function x up to five trial functions, or all components of a coupling entry)
     int body; double f[3];
     const double* fq;   // body == 2: force sampled at the quadrature points, [n_elems][nq][dst]
     const double* kq;   // Laplace kernels: conductivity sampled at the quadrature points, [n_elems][nq] (nullptr: constant p0)
@@ -496,6 +497,95 @@ __global__ void __launch_bounds__(256) k_tangent(const AsmParams p) {
                         acc += -s.sDet[eq] * p.w[q] * s.sGc[((size_t)eq * p.nc + N) * DIM + d] * p.Nt[q * p.nt + Mp];
                     }
                 emit_entry(p, p.eid(base + eb), Mp, 0, N, d, nr, ncl, sgn * acc);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// k_tangent with register strips for the Laplace-type integrands and the Stokes coupling blocks (knob gen_tile): the
+// per-entry loops of k_tangent spend half of their instructions on index arithmetic and on loads the neighbouring
+// entries repeat (profiles/r2/r2_t_ncu_C5_gather.md); same staging, same sum order per entry
+template <int DIM>
+__global__ void __launch_bounds__(256, 3) k_tangent_strips(const AsmParams p) {
+    extern __shared__ double smem[];
+    const Stage<DIM> s(smem, p);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int nr = p.nt * p.dst, ncl = p.nc * p.dsc;
+    for (int64_t base = (int64_t)blockIdx.x * p.EB; base < p.n_elems; base += (int64_t)gridDim.x * p.EB) {
+        const int nb = (int)min((int64_t)p.EB, p.n_elems - base);
+        stage_batch<DIM>(p, s, base, nb);
+        if (p.kernel_id == ISL_K_LAPLACE || p.kernel_id == ISL_K_VECTOR_LAPLACE) {
+            // one thread = test function M x a strip of up to five trial functions: the gradient of M, the weight and the
+            // index arithmetic are shared by the strip (same sum order per entry as the per-entry loop below)
+            constexpr int TN = 5;
+            const int strips = (p.nc + TN - 1) / TN, per = p.nt * strips;
+            for (int t = tid; t < nb * per; t += nth) {
+                const int eb = t / per, ms = t - eb * per, M = ms / strips, N0 = (ms - M * strips) * TN;
+                const int cnt = min(TN, p.nc - N0);
+                const int64_t e = p.eid(base + eb);
+                double acc[TN];
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[j] = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
+                    const double* gN = s.sGc + ((size_t)eq * p.nc + N0) * DIM;
+                    const double kap = p.kq ? p.kq[(size_t)e * p.nq + q] : p.p0;
+                    const double f = kap * s.sDet[eq] * p.w[q];
+                    double m[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; k++) m[k] = gM[k];
+#pragma unroll
+                    for (int j = 0; j < TN; j++)
+                        if (j < cnt) {
+                            double dot = m[0] * gN[j * DIM];
+#pragma unroll
+                            for (int k = 1; k < DIM; k++) dot += m[k] * gN[j * DIM + k];
+                            acc[j] += dot * f;
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < TN; j++)
+                    if (j < cnt) emit_node_pair(p, e, M, N0 + j, nr, ncl, acc[j]);
+            }
+        } else if (p.kernel_id == ISL_K_PRESSURE_GRADIENT) {
+            // one thread = node pair (M, N), all components d of the test gradient
+            const int per = p.nt * p.nc;
+            for (int t = tid; t < nb * per; t += nth) {
+                const int eb = t / per, mn = t - eb * per, M = mn / p.nc, N = mn - M * p.nc;
+                double acc[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) acc[d] = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double dw = -s.sDet[eq] * p.w[q], psi = p.Nc[q * p.nc + N];
+                    const double* gM = s.sGt + ((size_t)eq * p.nt + M) * DIM;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) acc[d] += dw * gM[d] * psi;
+                }
+                const int64_t e = p.eid(base + eb);
+#pragma unroll
+                for (int d = 0; d < DIM; d++) emit_entry(p, e, M, d, N, 0, nr, ncl, acc[d]);
+            }
+        } else if (p.kernel_id == ISL_K_VELOCITY_DIVERGENCE) {
+            const double sgn = (p.p0 != 0.) ? -1.0 : 1.0;
+            const int per = p.nt * p.nc;
+            for (int t = tid; t < nb * per; t += nth) {
+                const int eb = t / per, mn = t - eb * per, Mp = mn / p.nc, N = mn - Mp * p.nc;
+                double acc[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; d++) acc[d] = 0.;
+                for (int q = 0; q < p.nq; q++) {
+                    const int eq = eb * p.nq + q;
+                    const double dw = -s.sDet[eq] * p.w[q], phi = p.Nt[q * p.nt + Mp];
+                    const double* gN = s.sGc + ((size_t)eq * p.nc + N) * DIM;
+#pragma unroll
+                    for (int d = 0; d < DIM; d++) acc[d] += dw * gN[d] * phi;
+                }
+                const int64_t e = p.eid(base + eb);
+#pragma unroll
+                for (int d = 0; d < DIM; d++) emit_entry(p, e, Mp, 0, N, d, nr, ncl, sgn * acc[d]);
             }
         }
         __syncthreads();
@@ -966,6 +1056,8 @@ struct isl_engine {
     std::map<std::array<int, 3>, std::unique_ptr<GenGatherSet>> gengathers;
     DevBuf<double> gen_kbuf;
     int gen_gather = 0;        // ISL_GEN_GATHER
+    int gen_range = 1;         // ISL_GEN_RANGE: row buffers cover the column range of the block only
+    int gen_tile = 0;          // ISL_GEN_TILE: register strips in k_tangent (Laplace-type and Stokes coupling blocks)
     int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
     int hypel_occ3 = 1;        // ISL_HYPEL_OCC3: Q2 variant of the tile kernel compiled for three CTAs per SM
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
@@ -1437,11 +1529,17 @@ GenGatherSet* get_gengather(isl_engine* h, int t, int c, int compact) {
         ISL_LAUNCH(h, k_gs_max_len, std::min(h->grid_for(rp->n_rows, 256), h->n_sm * 8), 256, 0, h->rowptr.p, rp->n_rows, st.p + 1);
         ISL_LAUNCH(h, k_gs_dup, h->grid_for(h->n_owned * ncl, 256), 256, 0, fc.elem_eqn.p, h->n_owned, ncl, st.p);
         gs->pos.alloc((size_t)std::max<int64_t>(rp->n_pairs, 1) * gs->KC);
+        gs->row_lo.alloc(rp->n_rows); gs->row_hi.alloc(rp->n_rows);
+        ISL_LAUNCH(h, k_gg_range_init, h->grid_for(rp->n_rows, 256), 256, 0, gs->row_lo.p, gs->row_hi.p, rp->n_rows);
         if (rp->n_pairs > 0)
             ISL_LAUNCH(h, k_gg_pos, h->grid_for(rp->n_pairs * gs->KC, 256), 256, 0, rp->pair.p, rp->n_pairs, rp->nr, ft.ds, gs->KC, compact, fc.ds, ncl,
-                       ft.elem_eqn.p, fc.elem_eqn.p, h->rowptr.p, h->col.p, gs->pos.p, st.p);
+                       ft.elem_eqn.p, fc.elem_eqn.p, h->rowptr.p, h->col.p, gs->pos.p, gs->row_lo.p, gs->row_hi.p, st.p);
+        DevBuf<int> mw; mw.alloc(1);
+        ISL_CUDA(cudaMemsetAsync(mw.p, 0, sizeof(int), h->stream));
+        ISL_LAUNCH(h, k_gg_max_width, std::min(h->grid_for(rp->n_rows, 256), h->n_sm * 8), 256, 0, gs->row_lo.p, gs->row_hi.p, rp->n_rows, mw.p);
         int hst[2] = {0, 0};
         ISL_CUDA(cudaMemcpyAsync(hst, st.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        ISL_CUDA(cudaMemcpyAsync(&gs->max_width, mw.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         gs->max_len = hst[1];
         gs->ok = hst[0] == 0 && (size_t)(gs->max_len + 1) * sizeof(double) * 4 <= 200 * 1024;   // the row buffers of one warp (up to four rows) must fit a CTA
@@ -1449,6 +1547,7 @@ GenGatherSet* get_gengather(isl_engine* h, int t, int c, int compact) {
             fprintf(stderr, "[isl] atomic-free generic path (%d,%d,%s): %s, %lld (element, row) pairs, %d x %d per element, longest row %d, positions %.2f GB\n",
                     t, c, compact ? "one scalar per node pair" : "full block", gs->ok ? "ok" : "not eligible", (long long)rp->n_pairs, gs->KR, gs->KC,
                     gs->max_len, (double)rp->n_pairs * gs->KC * 2 / 1e9);
+        if (getenv("ISL_VERBOSE")) fprintf(stderr, "[isl]   widest column range of the block inside a row: %d\n", gs->max_width);
     }
     GenGatherSet* out = gs->ok ? gs.get() : nullptr;
     h->gengathers[key] = std::move(gs);
@@ -1481,6 +1580,7 @@ void launch_gen_gather(isl_engine* h, GenGatherSet* gs, const AsmParams& a, int 
     g.ed_c = fc.elem_dof.p; g.st_c = fc.status.p; g.presc_c = fc.presc.p; g.val_c = fc.values.p; g.incremental = a.incremental;
     g.store = store ? 1 : 0;
     g.buf_len = (gs->max_len + 1) & ~1;
+    if (h->gen_range) { g.row_lo = gs->row_lo.p; g.row_hi = gs->row_hi.p; g.buf_len = (std::max(gs->max_width, 1) + 1) & ~1; }
     if (g.KC <= 8) launch_gen_gather_t<8, 1>(h, g);
     else if (g.KC <= 16) launch_gen_gather_t<16, 1>(h, g);
     else if (g.KC <= 32) launch_gen_gather_t<32, 1>(h, g);
@@ -1537,11 +1637,22 @@ void launch_hypel_sym(isl_engine* h, AsmParams& p) {
 }
 
 template <class K>
-void launch_staged(isl_engine* h, K kernel, AsmParams& p) {
+void launch_staged(isl_engine* h, K kernel, AsmParams& p, int tasks_per_elem = 0) {
     const size_t per = stage_doubles_per_elem(p, h->dim) * sizeof(double);
     const size_t budget = (size_t)h->stage_kb * 1024;   // shared memory per CTA: fewer elements per batch = more CTAs per SM
     ISL_REQUIRE(per <= 200 * 1024, "element too large for shared-memory staging");
     int EB = (int)std::max<size_t>(1, std::min<size_t>(budget / per, 32));
+    if (tasks_per_elem > 0) {
+        // strip tasks: the batch whose tasks fill whole passes of the 256 threads best (13 elements x 20 tasks = 260 would
+        // run a second pass for four threads)
+        int best = EB; double best_u = 0.;
+        for (int b = EB; b >= std::max(1, EB / 2); b--) {
+            const int tasks = b * tasks_per_elem, passes = (tasks + 255) / 256;
+            const double u = (double)tasks / (passes * 256);
+            if (u > best_u + 1e-9) { best_u = u; best = b; }
+        }
+        EB = best;
+    }
     p.EB = EB;
     const size_t smem = per * EB;
     ISL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
@@ -2399,6 +2510,8 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_ELEM_ORDER")) h->elem_order = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_GATHER")) h->hypel_gather = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_GEN_GATHER")) h->gen_gather = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_GEN_RANGE")) h->gen_range = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_GEN_TILE")) h->gen_tile = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_MC")) h->hypel_mc_small = atoi(m);
         if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
@@ -2449,6 +2562,8 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else if (n == "elem_order") h->elem_order = v ? 1 : 0;
         else if (n == "defer") h->defer_launch = v ? 1 : 0;
         else if (n == "gen_gather") h->gen_gather = v ? 1 : 0;
+        else if (n == "gen_range") h->gen_range = v ? 1 : 0;
+        else if (n == "gen_tile") h->gen_tile = v ? 1 : 0;
         else if (n == "hypel_gather") h->hypel_gather = v ? 1 : 0;
         else throw IslError("unknown option '" + n + "'");
     });
@@ -2676,6 +2791,19 @@ int isl_pattern_register(isl_handle h, int test_field, int trial_field) {
 }
 
 namespace {
+// register strips of k_tangent (knob gen_tile): sets p.tile and returns the tasks per element, 0 = per-entry loop
+int tile_tasks(isl_engine* h, AsmParams& p, int kid) {
+    p.tile = 0;
+    if (!h->gen_tile) return 0;
+    if (kid == ISL_K_LAPLACE || kid == ISL_K_VECTOR_LAPLACE) { p.tile = 1; return p.nt * ((p.nc + 4) / 5); }
+    if (kid == ISL_K_PRESSURE_GRADIENT || kid == ISL_K_VELOCITY_DIVERGENCE) { p.tile = 1; return p.nt * p.nc; }
+    return 0;
+}
+void launch_tangent(isl_engine* h, AsmParams& p, int kid) {
+    const int tpe = tile_tasks(h, p, kid);
+    if (tpe > 0) { if (h->dim == 3) launch_staged(h, k_tangent_strips<3>, p, tpe); else launch_staged(h, k_tangent_strips<2>, p, tpe); }
+    else { if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p); }
+}
 // the third field of the tuple for kernels that read one (fluid::Convection): same basis as the trial field
 void bind_aux(isl_engine* h, AsmParams& p, int kid, int c, int aux) {
     if (kid != ISL_K_CONVECTION) return;
@@ -2759,7 +2887,7 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
                 p.nqdata = (kid == ISL_K_CONVECTION ? 4 : 0);
                 bind_aux(h, p, kid, c, aux);
                 p.kout = h->gen_kbuf.p;
-                if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+                launch_tangent(h, p, kid);
                 launch_gen_gather(h, gs, p, t, c, store);
                 return;
             }
@@ -2786,7 +2914,7 @@ int isl_assemble_matrix_aux(isl_handle h, int kid, const double* params, int qua
             if (h->dim == 3) launch_staged(h, k_tangent_hypel_tiled<3>, p); else launch_staged(h, k_tangent_hypel_tiled<2>, p);
             return;
         }
-        if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+        launch_tangent(h, p, kid);
     });
 }
 

@@ -181,6 +181,9 @@ struct GenGatherSet {            // per (test field, trial field, compact)
     bool ok = false;
     int KR = 0, KC = 0, compact = 0, max_len = 0;
     DevBuf<uint16_t> pos;        // [n_pairs][KC]
+    // the columns a row receives from THIS block lie in [lo, hi] of the row (the trial field's equations; a few pressure
+    // columns at the end of a velocity row for the Stokes coupling block): the row buffer covers that range only
+    DevBuf<int32_t> row_lo, row_hi; int max_width = 0;
 };
 struct GenGatherParams {
     const int32_t* pair; const int64_t* row_start; const uint16_t* pos; const double* Kbuf;
@@ -189,11 +192,22 @@ struct GenGatherParams {
     const int32_t* ed_c; const uint8_t* st_c; const double* presc_c; const double* val_c; int incremental;
     int store;                   // 1: the system holds nothing yet: every row is written completely (no memset needed)
     int buf_len;                 // row buffer per sub-warp (doubles)
+    const int32_t* row_lo; const int32_t* row_hi;   // nullptr: the buffer covers the whole row
 };
+
+__global__ void k_gg_range_init(int32_t* lo, int32_t* hi, int64_t n) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) { lo[r] = 0x7fffffff; hi[r] = -1; }
+}
+__global__ void k_gg_max_width(const int32_t* lo, const int32_t* hi, int64_t n, int* out) {
+    int m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) m = max(m, hi[r] - lo[r] + 1);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
 
 __global__ void k_gg_pos(const int32_t* pair, int64_t n_pairs, int nr, int dst, int KC, int compact, int dsc, int ncl,
                          const int32_t* elem_eqn_t, const int32_t* elem_eqn_c, const int64_t* rowptr, const int32_t* col,
-                         uint16_t* pos, int* err) {
+                         uint16_t* pos, int32_t* row_lo, int32_t* row_hi, int* err) {
     const int64_t n = n_pairs * KC;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = t / KC; const int j = (int)(t - q * KC);
@@ -204,7 +218,12 @@ __global__ void k_gg_pos(const int32_t* pair, int64_t n_pairs, int nr, int dst, 
         uint16_t v = 0xffff;
         if (c >= 0) {
             const int64_t at = isl_find_in_row(rowptr, col, r, c);
-            if (at < 0 || at - rowptr[r] >= 0xfffe) err[0] = 1; else v = (uint16_t)(at - rowptr[r]);
+            if (at < 0 || at - rowptr[r] >= 0xfffe) err[0] = 1;
+            else {
+                v = (uint16_t)(at - rowptr[r]);
+                if (row_lo[r] > (int32_t)v) atomicMin(row_lo + r, (int32_t)v);
+                if (row_hi[r] < (int32_t)v) atomicMax(row_hi + r, (int32_t)v);
+            }
         }
         pos[t] = v;
     }
@@ -221,7 +240,9 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
         const int len = (int)(p.rowptr[r + 1] - s);
         const int64_t q0 = p.row_start[r], q1 = p.row_start[r + 1];
         if (q0 == q1 && !p.store) continue;
-        for (int k = lane; k < len; k += G) buf[k] = 0.;
+        int lo = 0, w = len;   // the part of the row this block reaches
+        if (p.row_lo) { lo = p.row_lo[r]; w = p.row_hi[r] - lo + 1; if (w <= 0) { lo = 0; w = 0; } }
+        for (int k = lane; k < w; k += G) buf[k] = 0.;
         double lift = 0.;
         __syncwarp(mask);
         // the loads of pair q + 1 are in flight while pair q is added into the row buffer
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
             if (q + 1 < q1) fetch(q + 1);
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                if (at[u] < 0xfffe) buf[at[u]] += v[u];
+                if (at[u] < 0xfffe) buf[(int)at[u] - lo] += v[u];
                 else if (at[u] == 0xffff && v[u] != 0.) {   // column not ACTIVE: Dirichlet lift of a CONSTRAINED DoF, nothing for an inactive one
                     const int64_t e = pr / p.nr; const int i = pr - (int)e * p.nr;
                     const int j = lane + G * u;
@@ -259,9 +280,9 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
             }
             __syncwarp(mask);
         }
-        if (p.store) { for (int k = lane; k < len; k += G) p.val[s + k] = buf[k]; }
+        if (p.store) { for (int k = lane; k < len; k += G) { const int kb = k - lo; p.val[s + k] = (kb >= 0 && kb < w) ? buf[kb] : 0.; } }
         else {   // untouched entries (other blocks of the row, other components) are neither read nor written
-            for (int k = lane; k < len; k += G) { const double b = buf[k]; if (b != 0.) p.val[s + k] += b; }
+            for (int k = lane; k < w; k += G) { const double b = buf[k]; if (b != 0.) p.val[s + lo + k] += b; }
         }
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) lift += __shfl_xor_sync(mask, lift, o);

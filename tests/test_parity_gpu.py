@@ -61,15 +61,17 @@ GENERIC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("gather", [0, 1])
+@pytest.mark.parametrize("gather,tile", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("name,n,perturb,permute", GENERIC_CASES)
-def test_generic_kernels_atomic_and_atomic_free_scatter(name, n, perturb, permute, gather):
+def test_generic_kernels_atomic_and_atomic_free_scatter(name, n, perturb, permute, gather, tile):
     """k_tangent with the atomic scatter through the slot / node-block maps (gen_gather 0) and with the element matrices
-    stored and the CSR rows gathered by sub-warps (gen_gather 1, isl_gather.cuh): both against the oracle, registered and
-    dynamic pattern; the gathered system is reproducible bit for bit"""
+    stored and the CSR rows gathered by sub-warps (gen_gather 1, isl_gather.cuh), per-entry loops (gen_tile 0) and register
+    strips (gen_tile 1, k_tangent_strips): all against the oracle, registered and dynamic pattern; the gathered system is
+    reproducible bit for bit"""
     e = E.Engine(0)
     try:
         e.set_option("gen_gather", gather)
+        e.set_option("gen_tile", tile)
         c = flows.build_case(name, n, perturb, permute)
         ref = c.run_oracle()
         out = c.run_engine(eng=e)
