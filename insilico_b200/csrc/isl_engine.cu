@@ -1055,9 +1055,10 @@ struct isl_engine {
     std::map<int, std::unique_ptr<RowPairs>> rowpairs;
     std::map<std::array<int, 3>, std::unique_ptr<GenGatherSet>> gengathers;
     DevBuf<double> gen_kbuf;
-    int gen_gather = 0;        // ISL_GEN_GATHER
+    int gen_gather = 1;        // ISL_GEN_GATHER (0: atomic scatter through the slot / node-block maps)
     int gen_range = 1;         // ISL_GEN_RANGE: row buffers cover the column range of the block only
-    int gen_tile = 0;          // ISL_GEN_TILE: register strips in k_tangent (Laplace-type and Stokes coupling blocks)
+    int gen_krow = 1;          // ISL_GEN_KROW: the gather reads the element-matrix row of a pair from a table (0: two integer divisions per pair)
+    int gen_tile = 1;          // ISL_GEN_TILE: k_tangent_strips for the Laplace-type integrands and the Stokes coupling blocks (0: per-entry loops of k_tangent)
     int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
     int hypel_occ3 = 1;        // ISL_HYPEL_OCC3: Q2 variant of the tile kernel compiled for three CTAs per SM
     struct BlockMap { DevBuf<int64_t> base; DevBuf<int32_t> len; };
@@ -1529,11 +1530,11 @@ GenGatherSet* get_gengather(isl_engine* h, int t, int c, int compact) {
         ISL_LAUNCH(h, k_gs_max_len, std::min(h->grid_for(rp->n_rows, 256), h->n_sm * 8), 256, 0, h->rowptr.p, rp->n_rows, st.p + 1);
         ISL_LAUNCH(h, k_gs_dup, h->grid_for(h->n_owned * ncl, 256), 256, 0, fc.elem_eqn.p, h->n_owned, ncl, st.p);
         gs->pos.alloc((size_t)std::max<int64_t>(rp->n_pairs, 1) * gs->KC);
-        gs->row_lo.alloc(rp->n_rows); gs->row_hi.alloc(rp->n_rows);
+        gs->row_lo.alloc(rp->n_rows); gs->row_hi.alloc(rp->n_rows); gs->krow.alloc(std::max<int64_t>(rp->n_pairs, 1));
         ISL_LAUNCH(h, k_gg_range_init, h->grid_for(rp->n_rows, 256), 256, 0, gs->row_lo.p, gs->row_hi.p, rp->n_rows);
         if (rp->n_pairs > 0)
             ISL_LAUNCH(h, k_gg_pos, h->grid_for(rp->n_pairs * gs->KC, 256), 256, 0, rp->pair.p, rp->n_pairs, rp->nr, ft.ds, gs->KC, compact, fc.ds, ncl,
-                       ft.elem_eqn.p, fc.elem_eqn.p, h->rowptr.p, h->col.p, gs->pos.p, gs->row_lo.p, gs->row_hi.p, st.p);
+                       ft.elem_eqn.p, fc.elem_eqn.p, h->rowptr.p, h->col.p, gs->pos.p, gs->row_lo.p, gs->row_hi.p, gs->krow.p, gs->KR, st.p);
         DevBuf<int> mw; mw.alloc(1);
         ISL_CUDA(cudaMemsetAsync(mw.p, 0, sizeof(int), h->stream));
         ISL_LAUNCH(h, k_gg_max_width, std::min(h->grid_for(rp->n_rows, 256), h->n_sm * 8), 256, 0, gs->row_lo.p, gs->row_hi.p, rp->n_rows, mw.p);
@@ -1580,6 +1581,7 @@ void launch_gen_gather(isl_engine* h, GenGatherSet* gs, const AsmParams& a, int 
     g.ed_c = fc.elem_dof.p; g.st_c = fc.status.p; g.presc_c = fc.presc.p; g.val_c = fc.values.p; g.incremental = a.incremental;
     g.store = store ? 1 : 0;
     g.buf_len = (gs->max_len + 1) & ~1;
+    if (h->gen_krow) g.krow = gs->krow.p;
     if (h->gen_range) { g.row_lo = gs->row_lo.p; g.row_hi = gs->row_hi.p; g.buf_len = (std::max(gs->max_width, 1) + 1) & ~1; }
     if (g.KC <= 8) launch_gen_gather_t<8, 1>(h, g);
     else if (g.KC <= 16) launch_gen_gather_t<16, 1>(h, g);
@@ -2512,6 +2514,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_GEN_GATHER")) h->gen_gather = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_GEN_RANGE")) h->gen_range = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_GEN_TILE")) h->gen_tile = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_GEN_KROW")) h->gen_krow = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_MC")) h->hypel_mc_small = atoi(m);
         if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
@@ -2564,6 +2567,7 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else if (n == "gen_gather") h->gen_gather = v ? 1 : 0;
         else if (n == "gen_range") h->gen_range = v ? 1 : 0;
         else if (n == "gen_tile") h->gen_tile = v ? 1 : 0;
+        else if (n == "gen_krow") h->gen_krow = v ? 1 : 0;
         else if (n == "hypel_gather") h->hypel_gather = v ? 1 : 0;
         else throw IslError("unknown option '" + n + "'");
     });

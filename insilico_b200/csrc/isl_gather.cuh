@@ -181,6 +181,7 @@ struct GenGatherSet {            // per (test field, trial field, compact)
     bool ok = false;
     int KR = 0, KC = 0, compact = 0, max_len = 0;
     DevBuf<uint16_t> pos;        // [n_pairs][KC]
+    DevBuf<int32_t> krow;        // [n_pairs] row of Kgen the pair reads: element * KR + local row (or local node, compact)
     // the columns a row receives from THIS block lie in [lo, hi] of the row (the trial field's equations; a few pressure
     // columns at the end of a velocity row for the Stokes coupling block): the row buffer covers that range only
     DevBuf<int32_t> row_lo, row_hi; int max_width = 0;
@@ -193,6 +194,7 @@ struct GenGatherParams {
     int store;                   // 1: the system holds nothing yet: every row is written completely (no memset needed)
     int buf_len;                 // row buffer per sub-warp (doubles)
     const int32_t* row_lo; const int32_t* row_hi;   // nullptr: the buffer covers the whole row
+    const int32_t* krow;         // nullptr: derived from pair[] with two integer divisions per pair
 };
 
 __global__ void k_gg_range_init(int32_t* lo, int32_t* hi, int64_t n) {
@@ -207,12 +209,13 @@ __global__ void k_gg_max_width(const int32_t* lo, const int32_t* hi, int64_t n, 
 
 __global__ void k_gg_pos(const int32_t* pair, int64_t n_pairs, int nr, int dst, int KC, int compact, int dsc, int ncl,
                          const int32_t* elem_eqn_t, const int32_t* elem_eqn_c, const int64_t* rowptr, const int32_t* col,
-                         uint16_t* pos, int32_t* row_lo, int32_t* row_hi, int* err) {
+                         uint16_t* pos, int32_t* row_lo, int32_t* row_hi, int32_t* krow, int KR, int* err) {
     const int64_t n = n_pairs * KC;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = t / KC; const int j = (int)(t - q * KC);
         const int32_t pr = pair[q];
         const int64_t e = pr / nr; const int i = pr - (int)e * nr;
+        if (j == 0) krow[q] = (int32_t)(e * KR + (compact ? i / dst : i));
         const int jc = compact ? j * dsc + (i % dst) : j;
         const int32_t r = elem_eqn_t[pr], c = elem_eqn_c[e * ncl + jc];
         uint16_t v = 0xffff;
@@ -246,12 +249,17 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
         double lift = 0.;
         __syncwarp(mask);
         // the loads of pair q + 1 are in flight while pair q is added into the row buffer
-        uint16_t at_n[U]; double v_n[U]; int32_t pr_n = 0;
+        uint16_t at_n[U]; double v_n[U];
         auto fetch = [&](int64_t q) {
-            pr_n = __ldg(p.pair + q);
-            const int64_t e = pr_n / p.nr;
-            const int i = pr_n - (int)e * p.nr;
-            const double* krow = p.Kbuf + ((size_t)e * p.KR + (p.compact ? i / p.dst : i)) * p.KC;
+            size_t kr;
+            if (p.krow) kr = (size_t)__ldg(p.krow + q);
+            else {
+                const int32_t pr = __ldg(p.pair + q);
+                const int64_t e = pr / p.nr;
+                const int i = pr - (int)e * p.nr;
+                kr = (size_t)e * p.KR + (p.compact ? i / p.dst : i);
+            }
+            const double* krow = p.Kbuf + kr * p.KC;
             const uint16_t* pq = p.pos + (size_t)q * p.KC;
 #pragma unroll
             for (int u = 0; u < U; u++) {
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
         };
         if (q0 < q1) fetch(q0);
         for (int64_t q = q0; q < q1; q++) {
-            uint16_t at[U]; double v[U]; const int32_t pr = pr_n;
+            uint16_t at[U]; double v[U];
 #pragma unroll
             for (int u = 0; u < U; u++) { at[u] = at_n[u]; v[u] = v_n[u]; }
             if (q + 1 < q1) fetch(q + 1);
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(256) k_gen_gather_rows(const GenGatherParams p
             for (int u = 0; u < U; u++) {
                 if (at[u] < 0xfffe) buf[(int)at[u] - lo] += v[u];
                 else if (at[u] == 0xffff && v[u] != 0.) {   // column not ACTIVE: Dirichlet lift of a CONSTRAINED DoF, nothing for an inactive one
+                    const int32_t pr = __ldg(p.pair + q);   // (rare path: rows next to a Dirichlet boundary)
                     const int64_t e = pr / p.nr; const int i = pr - (int)e * p.nr;
                     const int j = lane + G * u;
                     const int N = p.compact ? j : j / p.dsc, cj = p.compact ? i % p.dst : j % p.dsc;

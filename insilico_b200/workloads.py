@@ -142,9 +142,12 @@ class Workload:
         return total
 
     def atomics_per_element(self):
-        """FP64 atomic adds one step issues per element in the generic kernels: one per local matrix entry that is
-        integrated (all (nt ds)(nc ds) entries of a hyperelastic tangent, the component-diagonal ones of the Laplace-type
-        kernels, nt dim nc of a Stokes coupling block) and one per local force entry"""
+        """FP64 atomic adds one step issues per element: one per local force entry (k_force) and, where the atomic scatter
+        is used, one per local matrix entry that is integrated.  The matrix operations take the atomic-free paths by default
+        (isl_gather.cuh: element matrices to memory, CSR rows gathered), unless ISL_GEN_GATHER=0 selects the atomic scatter of
+        the generic kernels (the component-diagonal entries of the Laplace-type kernels, nt dim nc of a Stokes coupling block)"""
+        import os
+        gather_default = os.environ.get("ISL_GEN_GATHER", "1") != "0"
         total = 0
         for op in self.ops:
             if op[0] == "body":
@@ -158,10 +161,11 @@ class Workload:
                 # 3-D vector fields take the atomic-free path (element matrices to memory, rows gathered): no atomics
                 if not (self.dim == 3 and ft["ds"] == 3 and op[4] == op[5]):
                     total += (ft["ndpe"] * ft["ds"]) * (fc["ndpe"] * fc["ds"])
-            elif op[1] in (E.K_PRESSURE_GRADIENT, E.K_VELOCITY_DIVERGENCE):
-                total += ft["ndpe"] * fc["ndpe"] * self.dim
-            else:
-                total += ft["ndpe"] * fc["ndpe"] * fc["ds"]
+            elif not gather_default:
+                if op[1] in (E.K_PRESSURE_GRADIENT, E.K_VELOCITY_DIVERGENCE):
+                    total += ft["ndpe"] * fc["ndpe"] * self.dim
+                else:
+                    total += ft["ndpe"] * fc["ndpe"] * fc["ds"]
         return total
 
     def algorithmic_bytes_per_element(self, nnz):
