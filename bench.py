@@ -459,9 +459,17 @@ def bench_config(args, rank, world, local_rank, cores):
                    "peak_source": "measured (isl_measure_red_peak pattern %d: RED.ADD.F64 into a 2 GiB array, this run)" % pattern}
         atomics["frac"] = atomics["achieved"] / red_peak if red_peak else None
     main_r = dict(f64 if BOUND[cfg] == "fp64" else hbm)
+    traffic = None   # DRAM bytes per step from the committed ncu capture, valid for the default single-GPU size and kernel path only
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1 and tj.get(cfg + "_n") == n and os.environ.get("ISL_GEN_GATHER", "1") != "0":
+            traffic = tj.get(cfg + "_bytes_per_step")
+    except (OSError, ValueError):
+        pass
     op = w.ops[k_dom]
     roof = {"bound": BOUND[cfg], "kernel": "%s %s (k_tangent / k_force family)" % (op[0], KERNEL_NAME.get(op[1], "bodyforce") if op[0] != "body" else "bodyforce"),
-            "achieved": main_r["achieved"], "peak": main_r["peak"], "unit": main_r["unit"], "frac": main_r["frac"], "traffic": None,
+            "achieved": main_r["achieved"], "peak": main_r["peak"], "unit": main_r["unit"], "frac": main_r["frac"], "traffic": traffic,
             "kernel_ms": t_asm * 1e3, "per_op_ms": [{"op": o[0], "kernel": KERNEL_NAME.get(o[1], "body") if o[0] != "body" else "body", "ms": t} for o, t in zip(w.ops, per_op)],
             "hbm": hbm, "fp64": f64, "atomics": atomics}
     cfgd = {"workload": w.description, "n": n, "n_elems": int(ne_global), "n_eqn": int(w.n_eqn), "nnz_per_gpu": int(nnz),
