@@ -1057,6 +1057,7 @@ struct isl_engine {
     DevBuf<double> gen_kbuf;
     int gen_gather = 1;        // ISL_GEN_GATHER (0: atomic scatter through the slot / node-block maps)
     int gen_range = 1;         // ISL_GEN_RANGE: row buffers cover the column range of the block only
+    int gen_sampled = 0;       // ISL_GEN_SAMPLED: isl_assemble_matrix_sampled through the atomic-free path too (not yet run on a GPU)
     int gen_krow = 1;          // ISL_GEN_KROW: the gather reads the element-matrix row of a pair from a table (0: two integer divisions per pair)
     int gen_tile = 1;          // ISL_GEN_TILE: k_tangent_strips for the Laplace-type integrands and the Stokes coupling blocks (0: per-entry loops of k_tangent)
     int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
@@ -2515,6 +2516,7 @@ int isl_engine_create(int device, isl_handle* out) {
         if (const char* m = getenv("ISL_GEN_RANGE")) h->gen_range = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_GEN_TILE")) h->gen_tile = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_GEN_KROW")) h->gen_krow = atoi(m) ? 1 : 0;
+        if (const char* m = getenv("ISL_GEN_SAMPLED")) h->gen_sampled = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_HYPEL_MC")) h->hypel_mc_small = atoi(m);
         if (const char* m = getenv("ISL_HYPEL_OCC3")) h->hypel_occ3 = atoi(m) ? 1 : 0;
         if (const char* m = getenv("ISL_BLOCK_SLOTS")) h->block_slots = std::max(0, std::min(2, atoi(m)));
@@ -2568,6 +2570,7 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else if (n == "gen_range") h->gen_range = v ? 1 : 0;
         else if (n == "gen_tile") h->gen_tile = v ? 1 : 0;
         else if (n == "gen_krow") h->gen_krow = v ? 1 : 0;
+        else if (n == "gen_sampled") h->gen_sampled = v ? 1 : 0;
         else if (n == "hypel_gather") h->hypel_gather = v ? 1 : 0;
         else throw IslError("unknown option '" + n + "'");
     });
@@ -2935,13 +2938,26 @@ int isl_assemble_matrix_sampled(isl_handle h, int kid, const double* values, int
         check_kernel_fields(h, kid, t, c, true);
         AsmParams p; std::memset(&p, 0, sizeof(p));
         fill_common(h, p, quad_deg, t, c);
-        materialize_zero(h);
-        h->val_is_zero = false;
         DevBuf<double> kq;   // host or device pointer
         upload(h, kq, values, (size_t)h->n_owned * p.nq);
-        bind_slots(h, p, t, c); p.kernel_id = kid; p.incremental = incremental; p.kq = kq.p;
+        p.kernel_id = kid; p.incremental = incremental; p.kq = kq.p;
         p.need_gt = 1; p.need_gc = 1; p.nqdata = 0;
-        if (h->dim == 3) launch_staged(h, k_tangent<3>, p); else launch_staged(h, k_tangent<2>, p);
+        GenGatherSet* gs = (h->gen_gather && h->gen_sampled) ? get_gengather(h, t, c, 1) : nullptr;
+        if (gs) {   // atomic-free, as in isl_assemble_matrix_aux
+            const bool store = h->val_is_zero;
+            if (store) h->val_zero_pending = false; else materialize_zero(h);
+            h->val_is_zero = false;
+            const size_t need = (size_t)h->n_owned * gs->KR * gs->KC;
+            if (h->gen_kbuf.n < need) h->gen_kbuf.alloc(need);
+            p.kout = h->gen_kbuf.p;
+            launch_tangent(h, p, kid);
+            launch_gen_gather(h, gs, p, t, c, store);
+        } else {
+            materialize_zero(h);
+            h->val_is_zero = false;
+            bind_slots(h, p, t, c);
+            launch_tangent(h, p, kid);
+        }
         ISL_CUDA(cudaStreamSynchronize(h->stream));   // kq is released when this function returns
     });
 }

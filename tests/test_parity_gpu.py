@@ -58,6 +58,8 @@ GENERIC_CASES = [
     ("stokes_p2p1_tet", 4, True, True), ("stokes_q2q1_hex", 2, True, False), ("stokes_q2q1_quad", 5, True, True),
     ("mass_q1_hex", 6, True, True), ("mass_p2_tet_vector", 3, True, True), ("convection_q1_hex", 5, True, True),
     ("convection_q2_quad", 6, True, False),
+    # conductivity sampled per quadrature point (isl_assemble_matrix_sampled)
+    ("laplace_q1_hex_kappafun", 6, True, True), ("laplace_p2_tet_kappafun", 3, True, False),
 ]
 
 
