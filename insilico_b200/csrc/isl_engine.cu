@@ -1057,7 +1057,7 @@ struct isl_engine {
     DevBuf<double> gen_kbuf;
     int gen_gather = 1;        // ISL_GEN_GATHER (0: atomic scatter through the slot / node-block maps)
     int gen_range = 1;         // ISL_GEN_RANGE: row buffers cover the column range of the block only
-    int gen_sampled = 0;       // ISL_GEN_SAMPLED: isl_assemble_matrix_sampled through the atomic-free path too (not yet run on a GPU)
+    int gen_sampled = 1;       // ISL_GEN_SAMPLED: isl_assemble_matrix_sampled through the atomic-free path too (0: atomic scatter)
     int gen_krow = 1;          // ISL_GEN_KROW: the gather reads the element-matrix row of a pair from a table (0: two integer divisions per pair)
     int gen_tile = 1;          // ISL_GEN_TILE: k_tangent_strips for the Laplace-type integrands and the Stokes coupling blocks (0: per-entry loops of k_tangent)
     int hypel_mc_small = 5;    // ISL_HYPEL_MC: tile height for elements with at most 10 nodes (2, 3 or 5)
