@@ -148,7 +148,9 @@ int isl_system_create(isl_handle h, int64_t n_eqn);
  * (test,trial) block pattern into the system CSR                                                            */
 int isl_pattern_register(isl_handle h, int test_field, int trial_field);
 /* asmb::stiffnessMatrixComputation<FTB>(quad, solver, binder, kernelObj, incremental)
- * (base/asmb/StiffnessMatrix.hpp:49-87): K scattered into CSR, Dirichlet lift into rhs                      */
+ * (base/asmb/StiffnessMatrix.hpp:49-87): K into the CSR values, Dirichlet lift into rhs.  Every CSR row is summed in the
+ * caller's element order by the threads that own it (no atomics), so the matrix is reproducible bit for bit; fields with
+ * slaves of master DoFs take the atomic scatter (isl_field_set_constraints)                                   */
 int isl_assemble_matrix(isl_handle h, int kernel_id, const double* params, int quad_deg, int test_field,
                         int trial_field, int incremental);
 /* kernels that read a third field of the tuple (FieldTupleBinder<I,J,K>: AuxField1Element, base/asmb/FieldTupleBinder.hpp),
