@@ -2552,7 +2552,7 @@ int isl_engine_destroy(isl_handle h) {
     });
 }
 int isl_engine_set_option(isl_handle h, const char* name, double value) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         const std::string n(name ? name : "");
         const int v = (int)value;
@@ -2575,8 +2575,8 @@ int isl_engine_set_option(isl_handle h, const char* name, double value) {
         else throw IslError("unknown option '" + n + "'");
     });
 }
-int isl_synchronize(isl_handle h) { return guarded([&] { flush_pending(h); ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
-int isl_flush(isl_handle h) { return guarded([&] { flush_pending(h); }); }
+int isl_synchronize(isl_handle h) { return guarded([&] { ISL_CUDA(cudaSetDevice(h->device)); flush_pending(h); ISL_CUDA(cudaStreamSynchronize(h->stream)); }); }
+int isl_flush(isl_handle h) { return guarded([&] { ISL_CUDA(cudaSetDevice(h->device)); flush_pending(h); }); }
 void* isl_engine_stream(isl_handle h) { return (void*)h->stream; }
 int64_t isl_kernel_launches(isl_handle h) { return h->launches; }
 
@@ -2657,7 +2657,7 @@ int isl_mesh_set(isl_handle h, int shape, int geom_deg, int dim, int64_t n_nodes
     });
 }
 int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         ISL_REQUIRE(n_owned >= 0 && n_owned <= h->n_elems, "owned element count out of range");
         h->n_owned = n_owned; h->affine_state = -1;
@@ -2668,7 +2668,7 @@ int isl_mesh_set_owned(isl_handle h, int64_t n_owned) {
     });
 }
 int isl_mesh_update_coords(isl_handle h, const double* coords) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         ISL_REQUIRE(h->n_nodes > 0, "mesh not set");
         h->affine_state = -1;
@@ -2760,7 +2760,7 @@ int isl_field_set_constraints(isl_handle h, int field, int64_t n_con, const int6
     });
 }
 int isl_field_update(isl_handle h, int field, const double* prescribed, const double* values) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
         FieldDev& f = h->fields[field];
@@ -3208,7 +3208,7 @@ int isl_surface_points(int surf_shape, int geom_deg, int dim, int64_t n_surf, co
 }
 int isl_assemble_neumann(isl_handle h, int64_t n_surf, const int32_t* domain_elem, const double* surf_x, const double* surf_param,
                          int quad_deg, int test_field, int mode, const double* data) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(test_field >= 0 && test_field < 5 && h->fields[test_field].set, "field not set");
         const FieldDev& f = h->fields[test_field];
         ISL_REQUIRE(h->n_elems > 0, "mesh not set");
@@ -3217,7 +3217,7 @@ int isl_assemble_neumann(isl_handle h, int64_t n_surf, const int32_t* domain_ele
 }
 int isl_assemble_neumann_rows(isl_handle h, int shape, int geom_deg, int64_t n_surf, const double* surf_x, const double* surf_param,
                               int quad_deg, int fe_deg, int dof_size, const int32_t* rows, int mode, const double* data) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(rows != nullptr, "no equation numbers");
         ISL_REQUIRE(dof_size >= 1 && dof_size <= 3, "dof_size must be 1..3");
         assemble_neumann(h, shape, geom_deg, n_surf, nullptr, surf_x, surf_param, quad_deg, fe_deg, dof_size, -1, rows, mode, data);
@@ -3228,7 +3228,7 @@ int isl_assemble_neumann_rows(isl_handle h, int shape, int geom_deg, int64_t n_s
 // no allocation and no wait per call; the operands are staged in a small arena that the stream reuses in order, a
 // missing pattern entry is recorded on the device and reported by isl_finish
 int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_rows, const int64_t* cols, int n_cols) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         require_live_system(h);
         flush_pending(h);
         materialize_zero(h);
@@ -3249,7 +3249,7 @@ int isl_insert_lhs(isl_handle h, const double* mat, const int64_t* rows, int n_r
     });
 }
 int isl_insert_rhs(isl_handle h, const double* vec, const int64_t* rows, int n_rows) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         require_live_system(h);
         flush_pending(h);
         for (int i = 0; i < n_rows; i++) ISL_REQUIRE(rows[i] >= 0 && rows[i] < h->n_eqn, std::to_string(rows[i]) + " out of bound");
@@ -3324,12 +3324,12 @@ int isl_get_csr_async(isl_handle h, double* val, double* rhs) {
     });
 }
 int isl_copy_wait(isl_handle h) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         if (h->copy_in_flight) ISL_CUDA(cudaEventSynchronize(h->ev_copy));
     });
 }
 int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** val, double** rhs) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         materialize_zero(h);
         if (rowptr) *rowptr = h->rowptr.p;
@@ -3339,7 +3339,7 @@ int isl_get_device_csr(isl_handle h, int64_t** rowptr, int32_t** col, double** v
     });
 }
 int isl_rhs_value(isl_handle h, int64_t index, double* value) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         ISL_REQUIRE(index >= 0 && index < h->n_eqn, "index out of bound");
         ISL_CUDA(cudaMemcpyAsync(value, h->rhs.p + index, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -3347,7 +3347,7 @@ int isl_rhs_value(isl_handle h, int64_t index, double* value) {
     });
 }
 int isl_rhs_norm(isl_handle h, double* norm) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         ISL_REQUIRE(h->n_eqn > 0, "empty system");
         h->scratch_d.alloc(1);
@@ -3398,7 +3398,7 @@ int isl_distribute(isl_handle h, int field, int add) {
     });
 }
 int isl_field_get_values(isl_handle h, int field, double* values) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(field >= 0 && field < 5 && h->fields[field].set, "field not set");
         ISL_REQUIRE(values, "null output");
         flush_pending(h);
@@ -3409,7 +3409,7 @@ int isl_field_get_values(isl_handle h, int field, double* values) {
 }
 
 int isl_measure_fp64_peak(isl_handle h, double* tflops) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(tflops, "null output");
         flush_pending(h);
         DevBuf<double> out; out.alloc(1);
@@ -3434,7 +3434,7 @@ int isl_measure_fp64_peak(isl_handle h, double* tflops) {
 }
 
 int isl_measure_red_peak(isl_handle h, int pattern, double* gatomics_per_s) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         ISL_REQUIRE(gatomics_per_s && pattern >= 0 && pattern <= 2, "bad arguments");
         flush_pending(h);
         const unsigned long long n = 1ull << 28;   // 2 GiB of doubles: far larger than L2
@@ -3488,7 +3488,7 @@ int isl_comm_init(isl_handle h, const void* id128, int rank, int world) {
     });
 }
 int isl_comm_destroy(isl_handle h) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         if (!h->comm) return;
         ISL_CUDA(cudaStreamSynchronize(h->stream));
         ISL_CUDA(cudaStreamSynchronize(h->comm->stream));
@@ -3623,7 +3623,7 @@ int isl_exchange(isl_handle h) {
 }
 
 int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, double* out_dev) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         materialize_zero(h);
         if (n == 0) return;
@@ -3632,7 +3632,7 @@ int isl_pack_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n,
     });
 }
 int isl_unpack_add_entries(isl_handle h, int which, const int64_t* idx_dev, int64_t n, const double* in_dev) {
-    return guarded([&] {
+    return guarded([&] { ISL_CUDA(cudaSetDevice(h->device));
         flush_pending(h);
         materialize_zero(h);
         if (n == 0) return;
