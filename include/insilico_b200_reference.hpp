@@ -212,6 +212,7 @@ struct FlattenField<N, FIELDBINDER, false> {
         std::vector<uint8_t> status(n, ISL_INACTIVE);
         std::vector<double> prescribed(n, 0.), values(n, 0.);
         std::vector<uint8_t> seen(n, 0);
+        std::vector<uint8_t> visited(static_cast<std::size_t>(f.nObj), 0);   // a DoF object is shared by all elements around it: read once
         struct Slave { int64_t dof; std::vector<std::pair<base::number, std::size_t> > masters; };
         std::vector<Slave> slaves;
 #pragma omp parallel for schedule(static) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
@@ -220,7 +221,12 @@ struct FlattenField<N, FIELDBINDER, false> {
             double pv[DoF::size];
             for (typename Element::DoFPtrConstIter d = ep->doFsBegin(); d != ep->doFsEnd(); ++d) {
                 const DoF* doF = *d;
-                const std::size_t o = doF->getID() * ds;
+                const std::size_t id = doF->getID();
+                if (id >= visited.size()) continue;   // (cannot happen: nObj is the largest id seen when the table was built)
+                // (two threads may both find the flag clear: they then store the same values, see storeShared)
+                if (__atomic_load_n(&visited[id], __ATOMIC_RELAXED) != 0) continue;
+                storeShared(visited[id], static_cast<uint8_t>(1));
+                const std::size_t o = id * ds;
                 doF->getPrescribedValues(&pv[0], false);
                 for (int c = 0; c < ds; c++) {
                     if (doF->isActive(c)) {
@@ -435,13 +441,18 @@ void synchronise(const FIELDBINDER& fb) {
     topologyChanged = assignIfChanged(s.conn, conn) || topologyChanged;
     const int64_t nNodes = static_cast<int64_t>(maxNode) + 1;
     std::vector<double> coords(static_cast<std::size_t>(nNodes) * dim, 0.);
+    std::vector<uint8_t> nodeVisited(static_cast<std::size_t>(nNodes), 0);   // a node is shared by all elements around it: read once
 #pragma omp parallel for schedule(static) if (numE > ISL_B200_PARALLEL_SCAN_MIN)
     for (long e = 0; e < numE; e++) {
-        const GeomElement* gep = (*(it0 + e)).geomElementPtr();
-        double x[3];
-        for (typename GeomElement::NodePtrConstIter n = gep->nodesBegin(); n != gep->nodesEnd(); ++n) {
-            (*n)->getX(&x[0]);
-            for (int d = 0; d < dim; d++) storeShared(coords[(*n)->getID() * dim + d], x[d]);
+        const int32_t* ce = &conn[e * npe];   // node ids of the element, read in the loop above
+        const GeomElement* gep = NULL;
+        for (int k = 0; k < npe; k++) {
+            if (__atomic_load_n(&nodeVisited[ce[k]], __ATOMIC_RELAXED) != 0) continue;
+            storeShared(nodeVisited[ce[k]], static_cast<uint8_t>(1));
+            if (gep == NULL) gep = (*(it0 + e)).geomElementPtr();
+            double x[3];
+            (*(gep->nodesBegin() + k))->getX(&x[0]);
+            for (int d = 0; d < dim; d++) storeShared(coords[static_cast<std::size_t>(ce[k]) * dim + d], x[d]);
         }
     }
     const bool coordsChanged = assignIfChanged(s.coords, coords);
